@@ -1,0 +1,923 @@
+// atmrt_lib.cu -- context management and the C ABI of include/atmrt.h.
+//
+// One context per GPU. A render is three stages on two streams (terrain profile || ray paths, then
+// the march); all buffers live in HBM and are reused between renders. There is no CPU fallback:
+// without a CUDA device every entry point fails with ATMRT_ERR_NO_DEVICE / ATMRT_ERR_CUDA.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace atmrt;
+
+static_assert(sizeof(DevScene) < 4000, "DevScene must fit the kernel parameter space");
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct atmrt_ctx {
+    int device = 0;
+    std::string err;
+    cudaStream_t s_a = nullptr, s_b = nullptr, s_main = nullptr;
+    cudaEvent_t ev_prep = nullptr, ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t t_a0 = nullptr, t_a1 = nullptr, t_b0 = nullptr, t_b1 = nullptr, t_c0 = nullptr, t_c1 = nullptr, t_0 = nullptr, t_1 = nullptr;
+    int num_sms = 148;
+
+    // terrain
+    std::vector<atmrt_tile_desc> tile_descs;
+    std::vector<DevTile> tiles_host;
+    void* terrain_owned = nullptr;
+    DevTerrain terrain{};
+    bool has_terrain = false;
+
+    // scene
+    atmrt_params params{};
+    bool has_params = false;
+    std::vector<atmrt_object> objects;
+    std::vector<DevBuf> textures;
+    std::vector<int> tex_w, tex_h;
+    DevBuf d_objects_in, d_objects;
+
+    // render state
+    DevScene scene{};
+    DevBuffers buf{};
+    bool rendered = false;
+    int march_mode = 0;
+    int rows_per_warp = 32;
+    std::vector<double> dist_k;
+    DevBuf d_dist, d_colcalc, d_tlat, d_tlon, d_telev, d_tnx, d_tny, d_tnz, d_tclose;
+    DevBuf d_pdist, d_pelev, d_plen, d_pn;
+    DevBuf d_tmin1, d_tmax1, d_tmin2, d_tmax2, d_close1, d_close2, d_rmin1, d_rmax1, d_rmin2, d_rmax2;
+    DevBuf d_obs, d_counters;
+    DevBuf d_rgb, d_meta, d_steps, d_points, d_counts;
+    DevBuf d_probe_a, d_probe_b, d_probe_c, d_probe_d;
+    int launches = 0;
+};
+
+namespace {
+
+int fail(atmrt_ctx* ctx, int code, const std::string& msg) {
+    if (ctx)
+        ctx->err = msg;
+    else
+        g_create_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(ctx, call)                                                                                  \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return fail(ctx, ATMRT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+int ensure(atmrt_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return 0;
+    if (b.p) CUDA_TRY(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    CUDA_TRY(ctx, cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    return 0;
+}
+
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+// ---- terrain layout -------------------------------------------------------------------------
+struct TerrainLayout {
+    int lat_min = 0, lon_min = 0, nlat_tiles = 0, nlon_tiles = 0;
+    size_t off_tiles = 0, off_lookup = 0, off_posts = 0, total = 0;
+    std::vector<DevTile> tiles;
+    std::vector<int> lookup;
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int make_layout(atmrt_ctx* ctx, const atmrt_tile_desc* descs, int n, TerrainLayout* L) {
+    if (n < 0 || (n > 0 && !descs)) return fail(ctx, ATMRT_ERR_INVALID, "bad tile list");
+    int lat_lo = 0, lat_hi = -1, lon_lo = 0, lon_hi = -1;
+    for (int i = 0; i < n; ++i) {
+        const atmrt_tile_desc& d = descs[i];
+        if (d.nlat < 2 || d.nlon < 2 || !(d.lat_interval > 0.0) || !(d.lon_interval > 0.0))
+            return fail(ctx, ATMRT_ERR_INVALID, "tile with fewer than 2x2 posts or a non-positive interval");
+        if (i == 0) {
+            lat_lo = lat_hi = d.lat0;
+            lon_lo = lon_hi = d.lon0;
+        } else {
+            lat_lo = std::min(lat_lo, d.lat0), lat_hi = std::max(lat_hi, d.lat0);
+            lon_lo = std::min(lon_lo, d.lon0), lon_hi = std::max(lon_hi, d.lon0);
+        }
+    }
+    L->lat_min = lat_lo, L->lon_min = lon_lo;
+    L->nlat_tiles = n ? lat_hi - lat_lo + 1 : 0;
+    L->nlon_tiles = n ? lon_hi - lon_lo + 1 : 0;
+    if ((long long)L->nlat_tiles * L->nlon_tiles > (1 << 22)) return fail(ctx, ATMRT_ERR_INVALID, "tile index span too large");
+    L->lookup.assign((size_t)L->nlat_tiles * L->nlon_tiles, -1);
+    L->tiles.resize(n);
+    long long off = 0;
+    for (int i = 0; i < n; ++i) {
+        const atmrt_tile_desc& d = descs[i];
+        DevTile& t = L->tiles[i];
+        t.min_lat = d.min_lat, t.min_lon = d.min_lon;
+        t.lat_interval = d.lat_interval, t.lon_interval = d.lon_interval;
+        t.max_lat = d.min_lat + (double)(d.nlat - 1) * d.lat_interval / 3600.0;
+        t.max_lon = d.min_lon + (double)(d.nlon - 1) * d.lon_interval / 3600.0;
+        t.nlat = d.nlat, t.nlon = d.nlon;
+        t.mt_lat = (d.nlat + MT - 1) / MT;
+        t._pad = 0;
+        t.post_offset = off;
+        off += (long long)((d.nlon + MT - 1) / MT) * t.mt_lat * (MT * MT);
+        // HashMap::insert: a later tile with the same key replaces the earlier one (terrain/mod.rs:93-97)
+        L->lookup[(size_t)(d.lat0 - lat_lo) * L->nlon_tiles + (d.lon0 - lon_lo)] = i;
+    }
+    L->off_tiles = 0;
+    L->off_lookup = align_up(sizeof(DevTile) * (size_t)std::max(n, 1), 256);
+    L->off_posts = align_up(L->off_lookup + sizeof(int) * std::max<size_t>(L->lookup.size(), 1), 256);
+    L->total = align_up(L->off_posts + sizeof(int16_t) * (size_t)std::max<long long>(off, 1), 256);
+    return 0;
+}
+
+// ---- atmosphere lowering (Atmosphere::from_def; host libm, same as the reference's CPU lowering) --
+constexpr double ATM_G = 9.80665, ATM_M = 0.0289644, ATM_R = 8.3144598;
+
+double host_layer_temperature(const DevAtmLayer& l, double h) { return l.t_ref + l.gradient * (h - l.h_ref); }
+double host_layer_pressure(const DevAtmLayer& l, double h) {
+    if (l.gradient != 0.0) {
+        double t = host_layer_temperature(l, h);
+        return l.p_ref * std::pow(t / l.t_ref, -ATM_G * ATM_M / (ATM_R * l.gradient));
+    }
+    return l.p_ref * std::exp(-ATM_G * ATM_M * (h - l.h_ref) / (ATM_R * l.t_ref));
+}
+
+int lower_atmosphere(atmrt_ctx* ctx, const atmrt_atmosphere_def& def, double wavelength, DevAtmosphere* out) {
+    const int n = def.n_functions;
+    if (n < 1 || n > ATMRT_MAX_ATM_FUNCTIONS) return fail(ctx, ATMRT_ERR_INVALID, "atmosphere: n_functions out of range");
+    DevAtmosphere a{};
+    a.n = n;
+    a.humidity = def.humidity;
+    for (int i = 0; i < n; ++i) {
+        a.layer[i].start = i == 0 ? -std::numeric_limits<double>::infinity() : def.fn_start_altitude[i];
+        a.layer[i].gradient = def.fn_gradient[i];
+        if (i >= 2 && !(def.fn_start_altitude[i] > def.fn_start_altitude[i - 1]))
+            return fail(ctx, ATMRT_ERR_INVALID, "atmosphere: function altitudes must increase");
+    }
+    auto find = [&](double h) {
+        int idx = 0;
+        for (int i = 1; i < n; ++i)
+            if (h >= a.layer[i].start) idx = i;
+        return idx;
+    };
+    // boundary temperatures by continuity from the temperature fixed point
+    std::vector<double> tb(n, 0.0);
+    const int jt = find(def.temperature_altitude);
+    {
+        double ha = def.temperature_altitude, ta = def.temperature;
+        for (int i = jt; i + 1 < n; ++i) {
+            double t = ta + a.layer[i].gradient * (a.layer[i + 1].start - ha);
+            tb[i + 1] = t;
+            ha = a.layer[i + 1].start;
+            ta = t;
+        }
+        ha = def.temperature_altitude, ta = def.temperature;
+        for (int i = jt; i >= 1; --i) {
+            double t = ta + a.layer[i].gradient * (a.layer[i].start - ha);
+            tb[i] = t;
+            ha = a.layer[i].start;
+            ta = t;
+        }
+    }
+    auto temp_at = [&](double h) {
+        int i = find(h);
+        if (i == jt) return def.temperature + a.layer[i].gradient * (h - def.temperature_altitude);
+        if (i > jt) return tb[i] + a.layer[i].gradient * (h - a.layer[i].start);
+        return tb[i + 1] + a.layer[i].gradient * (h - a.layer[i + 1].start);
+    };
+    // reference point per layer: the pressure fixed point in its layer, the lower boundary above it,
+    // the upper boundary below it; pressures propagate hydrostatically from the fixed point.
+    const int jp = find(def.pressure_altitude);
+    a.layer[jp].h_ref = def.pressure_altitude;
+    a.layer[jp].t_ref = temp_at(def.pressure_altitude);
+    a.layer[jp].p_ref = def.pressure;
+    for (int i = jp + 1; i < n; ++i) {
+        a.layer[i].h_ref = a.layer[i].start;
+        a.layer[i].t_ref = tb[i];
+        a.layer[i].p_ref = host_layer_pressure(a.layer[i - 1], a.layer[i].start);
+    }
+    for (int i = jp - 1; i >= 0; --i) {
+        a.layer[i].h_ref = a.layer[i + 1].start;
+        a.layer[i].t_ref = tb[i + 1];
+        a.layer[i].p_ref = host_layer_pressure(a.layer[i + 1], a.layer[i + 1].start);
+    }
+    for (int i = 0; i < n; ++i) {
+        DevAtmLayer& l = a.layer[i];
+        l.gm = -ATM_G * ATM_M;
+        l.rt = ATM_R * l.t_ref;
+        l.expo = l.gradient != 0.0 ? -ATM_G * ATM_M / (ATM_R * l.gradient) : 0.0;
+    }
+    // Ciddor (1996) wavelength-only terms; 450 ppm CO2.
+    const double w0 = 295.235, w1 = 2.6422, w2 = -0.032380, w3 = 0.004028;
+    const double k0 = 238.0185, k1 = 5792105.0, k2 = 57.362, k3 = 167917.0;
+    const double p_r1 = 101325.0, t_r1 = 288.15, z_a = 0.9995922115, gas_r = 8.314510, x_c = 450.0;
+    double lambda_um = wavelength * 1.0e6;
+    double s = 1.0 / (lambda_um * lambda_um);
+    double r_as = 1.0e-8 * (k1 / (k0 - s) + k3 / (k2 - s));
+    a.r_vs = 1.022e-8 * (w0 + w1 * s + w2 * s * s + w3 * s * s * s);
+    a.m_a = 0.0289635 + 1.2011e-8 * (x_c - 400.0);
+    a.r_axs = r_as * (1.0 + 5.34e-7 * (x_c - 450.0));
+    a.rho_axs = p_r1 * a.m_a / (z_a * gas_r * t_r1);
+    *out = a;
+    return 0;
+}
+
+int validate_params(atmrt_ctx* ctx, const atmrt_params& p) {
+    if (p.width <= 0 || p.height <= 0 || p.width > 32767 || p.height > 32767)
+        return fail(ctx, ATMRT_ERR_INVALID, "width/height must be in 1..32767 (i16 pixel centring, fast.rs:116,122)");
+    if (p.x0 < 0 || p.x1 > p.width || p.x0 >= p.x1) return fail(ctx, ATMRT_ERR_INVALID, "column block [x0,x1) out of range");
+    if (!(p.simulation_step > 0.0)) return fail(ctx, ATMRT_ERR_INVALID, "simulation_step must be positive");
+    if (!(p.max_distance > 0.0)) return fail(ctx, ATMRT_ERR_INVALID, "max_distance must be positive");
+    if (p.max_distance / p.simulation_step > 4.0e6) return fail(ctx, ATMRT_ERR_INVALID, "more than 4e6 samples per ray");
+    if (p.earth_model != ATMRT_EARTH_SPHERICAL && p.earth_model != ATMRT_EARTH_FLAT_DISTORTED)
+        return fail(ctx, ATMRT_ERR_INVALID, "earth model not supported on the device path (Spherical, FlatDistorted only)");
+    if (p.earth_model == ATMRT_EARTH_SPHERICAL && !(p.radius > 0.0)) return fail(ctx, ATMRT_ERR_INVALID, "radius must be positive");
+    if (p.coloring != ATMRT_COLORING_SIMPLE && p.coloring != ATMRT_COLORING_SHADING) return fail(ctx, ATMRT_ERR_INVALID, "unknown coloring");
+    return 0;
+}
+
+// Build DevScene + size all render buffers.
+int prepare_render(atmrt_ctx* ctx) {
+    if (!ctx->has_terrain) return fail(ctx, ATMRT_ERR_STATE, "render before set_terrain/bind_terrain");
+    if (!ctx->has_params) return fail(ctx, ATMRT_ERR_STATE, "render before set_params");
+    const atmrt_params& p = ctx->params;
+    DevScene& S = ctx->scene;
+    S = DevScene{};
+    S.lat0 = p.latitude, S.lon0 = p.longitude;
+    S.direction = p.direction, S.tilt = p.tilt, S.fov = p.fov, S.max_distance = p.max_distance;
+    S.step = p.simulation_step;
+    S.radius = p.radius;
+    S.altitude = p.altitude;
+    S.earth_model = p.earth_model;
+    S.flat = p.earth_model == ATMRT_EARTH_FLAT_DISTORTED;  // EarthModel::to_shape, earth_model/mod.rs:95-112
+    S.straight = p.straight_rays != 0;
+    S.width = p.width, S.height = p.height, S.x0 = p.x0, S.x1 = p.x1;
+    if (!S.flat) {
+        S.sin_diff = std::sin(NORMAL_DIFF / p.radius);
+        S.cos_diff = std::cos(NORMAL_DIFF / p.radius);
+    }
+    int rc = lower_atmosphere(ctx, p.atmosphere, p.wavelength, &S.atm);
+    if (rc) return rc;
+    DevShade& sh = S.shade;
+    sh.coloring = p.coloring, sh.palette = p.palette, sh.fog_enabled = p.fog_enabled;
+    sh.water_level = p.water_level, sh.ambient_light = p.ambient_light;
+    sh.light[0] = p.light_dir[0], sh.light[1] = p.light_dir[1], sh.light[2] = p.light_dir[2];
+    sh.simple_max_distance = p.simple_max_distance;
+    sh.fog_distance = p.fog_distance;
+    sh.terrain_alpha = p.terrain_alpha;
+    auto q = [](double v) -> unsigned char { return v != v || v <= 0.0 ? 0 : (v >= 255.0 ? 255 : (unsigned char)v); };
+    if (p.fog_enabled) {  // ColoringMethod::fog_color
+        sh.def_color[0] = sh.def_color[1] = sh.def_color[2] = 160;
+    } else if (p.coloring == ATMRT_COLORING_SIMPLE) {  // simple.rs:46-48
+        sh.def_color[0] = sh.def_color[1] = sh.def_color[2] = 28;
+    } else {  // shading.rs:134-142
+        const double legacy[3] = {0.11, 0.11, 0.11}, improved[3] = {0.23, 0.41, 0.55};
+        const double* c = p.palette == ATMRT_PALETTE_LEGACY ? legacy : improved;
+        for (int i = 0; i < 3; ++i) sh.def_color[i] = q(c[i] * 255.0);
+    }
+    // gen_terrain_cache's running sum: distance = 0; while distance < max { ...; distance += step }
+    ctx->dist_k.clear();
+    for (double d = 0.0; d < p.max_distance; d += p.simulation_step) ctx->dist_k.push_back(d);
+    const int n_t = (int)ctx->dist_k.size();
+    S.n_t = n_t;
+    S.n_pad = (n_t + 31) / 32 * 32;
+    S.n1 = (n_t + CHUNK - 1) / CHUNK;
+    S.n1_pad = (S.n1 + 31) / 32 * 32;
+    S.n2 = (S.n1 + 31) / 32;
+    S.nobjects = (int)ctx->objects.size();
+
+    const size_t wl = (size_t)(p.x1 - p.x0), h = (size_t)p.height, np = (size_t)S.n_pad;
+    const size_t f8 = sizeof(double);
+    int e = 0;
+    e |= ensure(ctx, ctx->d_dist, f8 * n_t);
+    e |= ensure(ctx, ctx->d_colcalc, f8 * 8 * wl);
+    e |= ensure(ctx, ctx->d_tlat, f8 * wl * np);
+    e |= ensure(ctx, ctx->d_tlon, f8 * wl * np);
+    e |= ensure(ctx, ctx->d_telev, f8 * wl * np);
+    e |= ensure(ctx, ctx->d_tnx, f8 * wl * np);
+    e |= ensure(ctx, ctx->d_tny, f8 * wl * np);
+    e |= ensure(ctx, ctx->d_tnz, f8 * wl * np);
+    if (S.nobjects > 0) e |= ensure(ctx, ctx->d_tclose, 8 * wl * np);
+    e |= ensure(ctx, ctx->d_pdist, f8 * h * np);
+    e |= ensure(ctx, ctx->d_pelev, f8 * h * np);
+    e |= ensure(ctx, ctx->d_plen, f8 * h * np);
+    e |= ensure(ctx, ctx->d_pn, sizeof(int) * h);
+    e |= ensure(ctx, ctx->d_tmin1, f8 * wl * S.n1_pad);
+    e |= ensure(ctx, ctx->d_tmax1, f8 * wl * S.n1_pad);
+    e |= ensure(ctx, ctx->d_tmin2, f8 * wl * S.n2);
+    e |= ensure(ctx, ctx->d_tmax2, f8 * wl * S.n2);
+    if (S.nobjects > 0) {
+        e |= ensure(ctx, ctx->d_close1, 8 * wl * S.n1_pad);
+        e |= ensure(ctx, ctx->d_close2, 8 * wl * S.n2);
+    }
+    e |= ensure(ctx, ctx->d_rmin1, f8 * h * S.n1_pad);
+    e |= ensure(ctx, ctx->d_rmax1, f8 * h * S.n1_pad);
+    e |= ensure(ctx, ctx->d_rmin2, f8 * h * S.n2);
+    e |= ensure(ctx, ctx->d_rmax2, f8 * h * S.n2);
+    e |= ensure(ctx, ctx->d_obs, f8);
+    e |= ensure(ctx, ctx->d_counters, 8 * CNT_COUNT);
+    e |= ensure(ctx, ctx->d_objects, sizeof(DevObject) * std::max(1, S.nobjects));
+    e |= ensure(ctx, ctx->d_objects_in, sizeof(atmrt_object) * std::max(1, S.nobjects));
+    if (e) return ATMRT_ERR_CUDA;
+
+    DevBuffers& B = ctx->buf;
+    B = DevBuffers{};
+    B.dist_k = (const double*)ctx->d_dist.p;
+    B.colcalc = (double*)ctx->d_colcalc.p;
+    B.t_lat = (double*)ctx->d_tlat.p, B.t_lon = (double*)ctx->d_tlon.p, B.t_elev = (double*)ctx->d_telev.p;
+    B.t_nx = (double*)ctx->d_tnx.p, B.t_ny = (double*)ctx->d_tny.p, B.t_nz = (double*)ctx->d_tnz.p;
+    B.t_close = S.nobjects > 0 ? (unsigned long long*)ctx->d_tclose.p : nullptr;
+    B.p_dist = (double*)ctx->d_pdist.p, B.p_elev = (double*)ctx->d_pelev.p, B.p_len = (double*)ctx->d_plen.p;
+    B.p_n = (int*)ctx->d_pn.p;
+    B.tmin1 = (double*)ctx->d_tmin1.p, B.tmax1 = (double*)ctx->d_tmax1.p;
+    B.tmin2 = (double*)ctx->d_tmin2.p, B.tmax2 = (double*)ctx->d_tmax2.p;
+    B.close1 = S.nobjects > 0 ? (unsigned long long*)ctx->d_close1.p : nullptr;
+    B.close2 = S.nobjects > 0 ? (unsigned long long*)ctx->d_close2.p : nullptr;
+    B.rmin1 = (double*)ctx->d_rmin1.p, B.rmax1 = (double*)ctx->d_rmax1.p;
+    B.rmin2 = (double*)ctx->d_rmin2.p, B.rmax2 = (double*)ctx->d_rmax2.p;
+    B.obs_alt = (double*)ctx->d_obs.p;
+    B.objects = (DevObject*)ctx->d_objects.p;
+    B.counters = (unsigned long long*)ctx->d_counters.p;
+    return 0;
+}
+
+int upload_scene_inputs(atmrt_ctx* ctx, cudaStream_t s) {
+    const DevScene& S = ctx->scene;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dist.p, ctx->dist_k.data(), sizeof(double) * S.n_t, cudaMemcpyHostToDevice, s));
+    if (S.nobjects > 0) {
+        std::vector<DevObject> host(S.nobjects);
+        for (int i = 0; i < S.nobjects; ++i) {
+            const atmrt_object& o = ctx->objects[i];
+            DevObject& d = host[i];
+            memset(&d, 0, sizeof(d));
+            d.kind = o.kind;
+            d.tex_w = o.texture_width, d.tex_h = o.texture_height;
+            d.r1 = o.r1, d.r2 = o.r2, d.width = o.width, d.height = o.height;
+            d.close_r = o.kind == ATMRT_OBJECT_FRUSTUM ? std::fmax(o.r1, o.r2) : o.width;
+            d.color = Color4{o.color[0], o.color[1], o.color[2], o.color[3]};
+            d.tex = (const uint8_t*)ctx->textures[i].p;
+        }
+        // pageable -> synchronous staging inside cudaMemcpyAsync, so `host` may go out of scope
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_objects.p, host.data(), sizeof(DevObject) * S.nobjects, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_objects_in.p, ctx->objects.data(), sizeof(atmrt_object) * S.nobjects, cudaMemcpyHostToDevice, s));
+    }
+    return 0;
+}
+
+struct RenderTargets {
+    unsigned char* rgb = nullptr;
+    atmrt_meta* meta = nullptr;
+    int* steps = nullptr;
+    atmrt_trace_point* points = nullptr;
+    int* counts = nullptr;
+    int max_points = 0;
+};
+
+// Launch the whole render on (s_a || s_b) -> main. Asynchronous.
+int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main, bool timed) {
+    const DevScene& S = ctx->scene;
+    const DevBuffers& B = ctx->buf;
+    const int wl = S.x1 - S.x0, h = S.height;
+    ctx->launches = 0;
+    if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->t_0, main));
+    int rc = upload_scene_inputs(ctx, main);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 8 * CNT_COUNT, main));
+    k_prepare_scene<<<(S.nobjects + 1 + 63) / 64, 64, 0, main>>>(S, ctx->terrain, B, (const atmrt_object*)ctx->d_objects_in.p);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_prep, main));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_a, ctx->ev_prep, 0));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_b, ctx->ev_prep, 0));
+
+    // Stage A on s_a
+    if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->t_a0, ctx->s_a));
+    k_column_setup<<<(wl + 127) / 128, 128, 0, ctx->s_a>>>(S, B);
+    k_terrain_profile<<<dim3((S.n_t + 127) / 128, wl), 128, 0, ctx->s_a>>>(S, ctx->terrain, B);
+    {
+        long long warps = (long long)wl * S.n2;
+        k_pyramid<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ctx->s_a>>>(B.t_elev, nullptr, B.t_close, wl, S.n_t, S.n_pad, S.n1,
+                                                                             S.n1_pad, S.n2, B.tmin1, B.tmax1, B.tmin2, B.tmax2,
+                                                                             B.close1, B.close2);
+    }
+    ctx->launches += 3;
+    if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->t_a1, ctx->s_a));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->s_a));
+
+    // Stage B on s_b
+    if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->t_b0, ctx->s_b));
+    {
+        int rpw = ctx->rows_per_warp;
+        k_ray_paths<<<(h + rpw - 1) / rpw, 32, 0, ctx->s_b>>>(S, B, rpw);
+        long long warps = (long long)h * S.n2;
+        k_pyramid<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ctx->s_b>>>(B.p_elev, B.p_n, nullptr, h, S.n_t, S.n_pad, S.n1, S.n1_pad,
+                                                                             S.n2, B.rmin1, B.rmax1, B.rmin2, B.rmax2, nullptr, nullptr);
+    }
+    ctx->launches += 2;
+    if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->t_b1, ctx->s_b));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->s_b));
+
+    // Stage C on main
+    CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_a, 0));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_b, 0));
+    if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->t_c0, main));
+    MarchOut O{rt.rgb, rt.meta, rt.steps, rt.points, rt.counts, rt.max_points};
+    const int blocks = ctx->num_sms * 8;
+    const bool trace = rt.points != nullptr || rt.counts != nullptr;
+    if (ctx->march_mode == 1) {
+        if (trace)
+            k_march<true, true><<<blocks, 256, 0, main>>>(S, B, O);
+        else
+            k_march<true, false><<<blocks, 256, 0, main>>>(S, B, O);
+    } else {
+        if (trace)
+            k_march<false, true><<<blocks, 256, 0, main>>>(S, B, O);
+        else
+            k_march<false, false><<<blocks, 256, 0, main>>>(S, B, O);
+    }
+    ctx->launches++;
+    if (timed) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->t_c1, main));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->t_1, main));
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->rendered = true;
+    return 0;
+}
+
+int collect_stats(atmrt_ctx* ctx, atmrt_stats* stats) {
+    if (!stats) return 0;
+    const DevScene& S = ctx->scene;
+    unsigned long long c[CNT_COUNT];
+    CUDA_TRY(ctx, cudaMemcpy(c, ctx->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost));
+    std::vector<int> pn(S.height);
+    CUDA_TRY(ctx, cudaMemcpy(pn.data(), ctx->d_pn.p, sizeof(int) * S.height, cudaMemcpyDeviceToHost));
+    memset(stats, 0, sizeof(*stats));
+    stats->ray_steps = c[CNT_RAY_STEPS];
+    stats->trace_points = c[CNT_TRACE_POINTS];
+    stats->pixels_hit = c[CNT_PIXELS_HIT];
+    stats->step_overflows = c[CNT_OVERFLOWS];
+    stats->path_steps = c[CNT_PATH_STEPS];
+    stats->terrain_samples = (uint64_t)(S.x1 - S.x0) * (uint64_t)S.n_t;
+    stats->n_terrain = S.n_t;
+    int mx = 0;
+    for (int v : pn) mx = std::max(mx, v);
+    stats->n_path_max = mx;
+    cudaEventElapsedTime(&stats->ms_terrain, ctx->t_a0, ctx->t_a1);
+    cudaEventElapsedTime(&stats->ms_paths, ctx->t_b0, ctx->t_b1);
+    cudaEventElapsedTime(&stats->ms_march, ctx->t_c0, ctx->t_c1);
+    cudaEventElapsedTime(&stats->ms_total, ctx->t_0, ctx->t_1);
+    stats->kernel_launches = ctx->launches;
+    return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int atmrt_abi_version(void) { return ATMRT_ABI_VERSION; }
+
+// sizes of the ABI structs, for the ctypes mirror's self-check
+int atmrt_abi_sizes(size_t* out, int n) {
+    const size_t v[] = {sizeof(atmrt_altitude), sizeof(atmrt_atmosphere_def), sizeof(atmrt_params), sizeof(atmrt_tile_desc),
+                        sizeof(atmrt_object),   sizeof(atmrt_meta),           sizeof(atmrt_trace_point), sizeof(atmrt_stats)};
+    const int m = (int)(sizeof(v) / sizeof(v[0]));
+    for (int i = 0; i < n && i < m; ++i) out[i] = v[i];
+    return m;
+}
+
+const char* atmrt_last_error(const atmrt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int atmrt_create(int device, atmrt_ctx** out) {
+    if (!out) return fail(nullptr, ATMRT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, ATMRT_ERR_NO_DEVICE,
+                    std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, ATMRT_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, ATMRT_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major < 10) return fail(nullptr, ATMRT_ERR_NO_DEVICE, "device is not sm_100 (Blackwell): the library is built for sm_100a only");
+    atmrt_ctx* ctx = new atmrt_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, ATMRT_ERR_CUDA, "cudaSetDevice failed");
+    }
+    bool ok = cudaStreamCreateWithFlags(&ctx->s_a, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_b, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking) == cudaSuccess;
+    cudaEvent_t* evs[] = {&ctx->ev_prep, &ctx->ev_a, &ctx->ev_b};
+    for (cudaEvent_t* ev : evs) ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
+    cudaEvent_t* tevs[] = {&ctx->t_a0, &ctx->t_a1, &ctx->t_b0, &ctx->t_b1, &ctx->t_c0, &ctx->t_c1, &ctx->t_0, &ctx->t_1};
+    for (cudaEvent_t* ev : tevs) ok = ok && cudaEventCreate(ev) == cudaSuccess;
+    if (!ok) {
+        delete ctx;
+        return fail(nullptr, ATMRT_ERR_CUDA, "stream/event creation failed");
+    }
+    *out = ctx;
+    return 0;
+}
+
+void atmrt_destroy(atmrt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    DevBuf* bufs[] = {&ctx->d_objects_in, &ctx->d_objects, &ctx->d_dist, &ctx->d_colcalc, &ctx->d_tlat, &ctx->d_tlon, &ctx->d_telev,
+                      &ctx->d_tnx, &ctx->d_tny, &ctx->d_tnz, &ctx->d_tclose, &ctx->d_pdist, &ctx->d_pelev, &ctx->d_plen, &ctx->d_pn,
+                      &ctx->d_tmin1, &ctx->d_tmax1, &ctx->d_tmin2, &ctx->d_tmax2, &ctx->d_close1, &ctx->d_close2, &ctx->d_rmin1,
+                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_rgb, &ctx->d_meta,
+                      &ctx->d_steps, &ctx->d_points, &ctx->d_counts, &ctx->d_probe_a, &ctx->d_probe_b, &ctx->d_probe_c, &ctx->d_probe_d};
+    for (DevBuf* b : bufs) release(*b);
+    for (DevBuf& b : ctx->textures) release(b);
+    if (ctx->terrain_owned) cudaFree(ctx->terrain_owned);
+    cudaEvent_t evs[] = {ctx->ev_prep, ctx->ev_a, ctx->ev_b, ctx->t_a0, ctx->t_a1, ctx->t_b0, ctx->t_b1, ctx->t_c0, ctx->t_c1, ctx->t_0, ctx->t_1};
+    for (cudaEvent_t ev : evs)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->s_a) cudaStreamDestroy(ctx->s_a);
+    if (ctx->s_b) cudaStreamDestroy(ctx->s_b);
+    if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
+    delete ctx;
+}
+
+int atmrt_terrain_packed_bytes(const atmrt_tile_desc* tiles, int ntiles, size_t* bytes) {
+    if (!bytes) return ATMRT_ERR_INVALID;
+    TerrainLayout L;
+    int rc = make_layout(nullptr, tiles, ntiles, &L);
+    if (rc) return rc;
+    *bytes = L.total;
+    return 0;
+}
+
+int atmrt_pack_terrain(atmrt_ctx* ctx, const atmrt_tile_desc* tiles, int ntiles, const int16_t* const* posts, void* dev_dst) {
+    if (!ctx || !dev_dst || (ntiles > 0 && !posts)) return fail(ctx, ATMRT_ERR_INVALID, "pack_terrain: NULL argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TerrainLayout L;
+    int rc = make_layout(ctx, tiles, ntiles, &L);
+    if (rc) return rc;
+    char* base = (char*)dev_dst;
+    cudaStream_t s = ctx->s_main;
+    CUDA_TRY(ctx, cudaMemsetAsync(base, 0, L.total, s));
+    if (ntiles > 0)
+        CUDA_TRY(ctx, cudaMemcpyAsync(base + L.off_tiles, L.tiles.data(), sizeof(DevTile) * ntiles, cudaMemcpyHostToDevice, s));
+    if (!L.lookup.empty())
+        CUDA_TRY(ctx, cudaMemcpyAsync(base + L.off_lookup, L.lookup.data(), sizeof(int) * L.lookup.size(), cudaMemcpyHostToDevice, s));
+    size_t max_posts = 0;
+    for (int i = 0; i < ntiles; ++i) max_posts = std::max(max_posts, (size_t)tiles[i].nlon * tiles[i].nlat);
+    DevBuf staging;
+    rc = ensure(ctx, staging, sizeof(int16_t) * max_posts);
+    if (rc) return rc;
+    for (int i = 0; i < ntiles; ++i) {
+        size_t n = (size_t)tiles[i].nlon * tiles[i].nlat;
+        cudaError_t e = cudaMemcpyAsync(staging.p, posts[i], sizeof(int16_t) * n, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) {
+            k_retile<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const int16_t*)staging.p, (int16_t*)(base + L.off_posts), L.tiles[i]);
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) {
+            release(staging);
+            return fail(ctx, ATMRT_ERR_CUDA, std::string("pack_terrain: ") + cudaGetErrorString(e));
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    release(staging);
+    if (e != cudaSuccess) return fail(ctx, ATMRT_ERR_CUDA, std::string("pack_terrain sync: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+int atmrt_bind_terrain(atmrt_ctx* ctx, const atmrt_tile_desc* tiles, int ntiles, const void* dev_packed) {
+    if (!ctx || !dev_packed) return fail(ctx, ATMRT_ERR_INVALID, "bind_terrain: NULL argument");
+    TerrainLayout L;
+    int rc = make_layout(ctx, tiles, ntiles, &L);
+    if (rc) return rc;
+    const char* base = (const char*)dev_packed;
+    ctx->tile_descs.assign(tiles, tiles + ntiles);
+    ctx->tiles_host = L.tiles;
+    ctx->terrain.tiles = (const DevTile*)(base + L.off_tiles);
+    ctx->terrain.lookup = (const int*)(base + L.off_lookup);
+    ctx->terrain.posts = (const int16_t*)(base + L.off_posts);
+    ctx->terrain.lat_min = L.lat_min, ctx->terrain.lon_min = L.lon_min;
+    ctx->terrain.nlat_tiles = L.nlat_tiles, ctx->terrain.nlon_tiles = L.nlon_tiles;
+    ctx->terrain.ntiles = ntiles;
+    ctx->has_terrain = true;
+    ctx->rendered = false;
+    return 0;
+}
+
+int atmrt_set_terrain(atmrt_ctx* ctx, const atmrt_tile_desc* tiles, int ntiles, const int16_t* const* posts) {
+    if (!ctx) return ATMRT_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    size_t bytes = 0;
+    TerrainLayout L;
+    int rc = make_layout(ctx, tiles, ntiles, &L);
+    if (rc) return rc;
+    bytes = L.total;
+    if (ctx->terrain_owned) {
+        cudaFree(ctx->terrain_owned);
+        ctx->terrain_owned = nullptr;
+        ctx->has_terrain = false;
+    }
+    CUDA_TRY(ctx, cudaMalloc(&ctx->terrain_owned, bytes));
+    rc = atmrt_pack_terrain(ctx, tiles, ntiles, posts, ctx->terrain_owned);
+    if (rc) return rc;
+    return atmrt_bind_terrain(ctx, tiles, ntiles, ctx->terrain_owned);
+}
+
+int atmrt_get_elev(atmrt_ctx* ctx, const double* lat, const double* lon, int n, double* elev) {
+    if (!ctx || !lat || !lon || !elev || n < 0) return fail(ctx, ATMRT_ERR_INVALID, "get_elev: bad argument");
+    if (!ctx->has_terrain) return fail(ctx, ATMRT_ERR_STATE, "get_elev before set_terrain");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return 0;
+    int rc = ensure(ctx, ctx->d_probe_a, 8 * (size_t)n) | ensure(ctx, ctx->d_probe_b, 8 * (size_t)n) | ensure(ctx, ctx->d_probe_c, 8 * (size_t)n);
+    if (rc) return ATMRT_ERR_CUDA;
+    cudaStream_t s = ctx->s_main;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_probe_a.p, lat, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_probe_b.p, lon, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+    k_get_elev<<<(n + 255) / 256, 256, 0, s>>>(ctx->terrain, (const double*)ctx->d_probe_a.p, (const double*)ctx->d_probe_b.p, n, (double*)ctx->d_probe_c.p);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(elev, ctx->d_probe_c.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int atmrt_read_tile(atmrt_ctx* ctx, int tile_index, int16_t* posts) {
+    if (!ctx || !posts) return fail(ctx, ATMRT_ERR_INVALID, "read_tile: NULL argument");
+    if (!ctx->has_terrain) return fail(ctx, ATMRT_ERR_STATE, "read_tile before set_terrain");
+    if (tile_index < 0 || tile_index >= (int)ctx->tiles_host.size()) return fail(ctx, ATMRT_ERR_INVALID, "tile index out of range");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const DevTile& t = ctx->tiles_host[tile_index];
+    size_t n = (size_t)t.nlon * t.nlat;
+    DevBuf raw;
+    int rc = ensure(ctx, raw, sizeof(int16_t) * n);
+    if (rc) return rc;
+    cudaStream_t s = ctx->s_main;
+    k_untile<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ctx->terrain.posts, (int16_t*)raw.p, t);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(posts, raw.p, sizeof(int16_t) * n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    release(raw);
+    if (e != cudaSuccess) return fail(ctx, ATMRT_ERR_CUDA, std::string("read_tile: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+int atmrt_set_params(atmrt_ctx* ctx, const atmrt_params* params) {
+    if (!ctx || !params) return fail(ctx, ATMRT_ERR_INVALID, "set_params: NULL argument");
+    int rc = validate_params(ctx, *params);
+    if (rc) return rc;
+    DevAtmosphere tmp;
+    rc = lower_atmosphere(ctx, params->atmosphere, params->wavelength, &tmp);
+    if (rc) return rc;
+    ctx->params = *params;
+    ctx->has_params = true;
+    ctx->rendered = false;
+    return 0;
+}
+
+int atmrt_set_objects(atmrt_ctx* ctx, const atmrt_object* objects, int nobjects, const uint8_t* const* rgba_textures) {
+    if (!ctx || nobjects < 0 || (nobjects > 0 && !objects)) return fail(ctx, ATMRT_ERR_INVALID, "set_objects: bad argument");
+    if (nobjects > ATMRT_MAX_OBJECTS) return fail(ctx, ATMRT_ERR_INVALID, "too many objects (objects_close is a 64-bit mask)");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < nobjects; ++i) {
+        const atmrt_object& o = objects[i];
+        if (o.kind == ATMRT_OBJECT_BILLBOARD) {
+            if (!rgba_textures || !rgba_textures[i] || o.texture_width < 2 || o.texture_height < 2)
+                return fail(ctx, ATMRT_ERR_INVALID, "billboard needs an RGBA texture of at least 2x2 texels");
+        } else if (o.kind != ATMRT_OBJECT_FRUSTUM) {
+            return fail(ctx, ATMRT_ERR_INVALID, "unknown object kind");
+        }
+    }
+    for (DevBuf& b : ctx->textures) release(b);
+    ctx->textures.assign(nobjects, DevBuf{});
+    ctx->objects.assign(objects, objects + nobjects);
+    for (int i = 0; i < nobjects; ++i) {
+        if (objects[i].kind != ATMRT_OBJECT_BILLBOARD) continue;
+        size_t bytes = (size_t)objects[i].texture_width * objects[i].texture_height * 4;
+        int rc = ensure(ctx, ctx->textures[i], bytes);
+        if (rc) return rc;
+        CUDA_TRY(ctx, cudaMemcpy(ctx->textures[i].p, rgba_textures[i], bytes, cudaMemcpyHostToDevice));
+    }
+    ctx->rendered = false;
+    return 0;
+}
+
+int atmrt_set_march_mode(atmrt_ctx* ctx, int mode) {
+    if (!ctx || (mode != 0 && mode != 1)) return fail(ctx, ATMRT_ERR_INVALID, "march mode must be 0 or 1");
+    ctx->march_mode = mode;
+    return 0;
+}
+
+// Tuning hook for Stage B: image rows integrated per warp (1..32).
+int atmrt_set_rows_per_warp(atmrt_ctx* ctx, int rows) {
+    if (!ctx || rows < 1 || rows > 32) return fail(ctx, ATMRT_ERR_INVALID, "rows per warp must be 1..32");
+    ctx->rows_per_warp = rows;
+    return 0;
+}
+
+int atmrt_render_device(atmrt_ctx* ctx, void* rgb_dev, void* meta_dev, void* steps_dev, atmrt_stats* stats, void* stream) {
+    if (!ctx) return ATMRT_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = prepare_render(ctx);
+    if (rc) return rc;
+    cudaStream_t main = stream ? (cudaStream_t)stream : ctx->s_main;
+    RenderTargets rt;
+    rt.rgb = (unsigned char*)rgb_dev, rt.meta = (atmrt_meta*)meta_dev, rt.steps = (int*)steps_dev;
+    rc = launch_render(ctx, rt, main, stats != nullptr);
+    if (rc) return rc;
+    if (stats) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(main));
+        return collect_stats(ctx, stats);
+    }
+    return 0;
+}
+
+int atmrt_render(atmrt_ctx* ctx, uint8_t* rgb, atmrt_meta* meta, int32_t* steps, atmrt_stats* stats) {
+    if (!ctx) return ATMRT_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = prepare_render(ctx);
+    if (rc) return rc;
+    const DevScene& S = ctx->scene;
+    const size_t npix = (size_t)(S.x1 - S.x0) * S.height;
+    if (rgb && (rc = ensure(ctx, ctx->d_rgb, npix * 3))) return rc;
+    if (meta && (rc = ensure(ctx, ctx->d_meta, npix * sizeof(atmrt_meta)))) return rc;
+    if (steps && (rc = ensure(ctx, ctx->d_steps, npix * sizeof(int)))) return rc;
+    RenderTargets rt;
+    rt.rgb = rgb ? (unsigned char*)ctx->d_rgb.p : nullptr;
+    rt.meta = meta ? (atmrt_meta*)ctx->d_meta.p : nullptr;
+    rt.steps = steps ? (int*)ctx->d_steps.p : nullptr;
+    cudaStream_t main = ctx->s_main;
+    rc = launch_render(ctx, rt, main, true);
+    if (rc) return rc;
+    if (rgb) CUDA_TRY(ctx, cudaMemcpyAsync(rgb, ctx->d_rgb.p, npix * 3, cudaMemcpyDeviceToHost, main));
+    if (meta) CUDA_TRY(ctx, cudaMemcpyAsync(meta, ctx->d_meta.p, npix * sizeof(atmrt_meta), cudaMemcpyDeviceToHost, main));
+    if (steps) CUDA_TRY(ctx, cudaMemcpyAsync(steps, ctx->d_steps.p, npix * sizeof(int), cudaMemcpyDeviceToHost, main));
+    CUDA_TRY(ctx, cudaStreamSynchronize(main));
+    return collect_stats(ctx, stats);
+}
+
+int atmrt_render_trace(atmrt_ctx* ctx, atmrt_trace_point* points, int32_t* counts, int max_points) {
+    if (!ctx || !counts || max_points < 0 || (max_points > 0 && !points)) return fail(ctx, ATMRT_ERR_INVALID, "render_trace: bad argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = prepare_render(ctx);
+    if (rc) return rc;
+    const DevScene& S = ctx->scene;
+    const size_t npix = (size_t)(S.x1 - S.x0) * S.height;
+    if ((rc = ensure(ctx, ctx->d_points, npix * sizeof(atmrt_trace_point) * (size_t)std::max(max_points, 1)))) return rc;
+    if ((rc = ensure(ctx, ctx->d_counts, npix * sizeof(int)))) return rc;
+    RenderTargets rt;
+    rt.points = (atmrt_trace_point*)ctx->d_points.p;
+    rt.counts = (int*)ctx->d_counts.p;
+    rt.max_points = max_points;
+    cudaStream_t main = ctx->s_main;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_points.p, 0, npix * sizeof(atmrt_trace_point) * (size_t)std::max(max_points, 1), main));
+    rc = launch_render(ctx, rt, main, false);
+    if (rc) return rc;
+    if (max_points > 0)
+        CUDA_TRY(ctx, cudaMemcpyAsync(points, ctx->d_points.p, npix * sizeof(atmrt_trace_point) * (size_t)max_points, cudaMemcpyDeviceToHost, main));
+    CUDA_TRY(ctx, cudaMemcpyAsync(counts, ctx->d_counts.p, npix * sizeof(int), cudaMemcpyDeviceToHost, main));
+    CUDA_TRY(ctx, cudaStreamSynchronize(main));
+    return 0;
+}
+
+int atmrt_get_terrain_profile(atmrt_ctx* ctx, int x, int capacity, double* lat, double* lon, double* elev, double* normal,
+                              uint64_t* objects_close, int* n) {
+    if (!ctx || !n) return fail(ctx, ATMRT_ERR_INVALID, "get_terrain_profile: NULL argument");
+    if (!ctx->rendered) return fail(ctx, ATMRT_ERR_STATE, "get_terrain_profile before a render");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const DevScene& S = ctx->scene;
+    if (x < 0 || x >= S.x1 - S.x0) return fail(ctx, ATMRT_ERR_INVALID, "column out of range");
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    *n = S.n_t;
+    int m = std::min(capacity, S.n_t);
+    if (m <= 0) return 0;
+    size_t off = (size_t)x * S.n_pad;
+    const DevBuffers& B = ctx->buf;
+    if (lat) CUDA_TRY(ctx, cudaMemcpy(lat, B.t_lat + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
+    if (lon) CUDA_TRY(ctx, cudaMemcpy(lon, B.t_lon + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
+    if (elev) CUDA_TRY(ctx, cudaMemcpy(elev, B.t_elev + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
+    if (normal) {
+        std::vector<double> nx(m), ny(m), nz(m);
+        CUDA_TRY(ctx, cudaMemcpy(nx.data(), B.t_nx + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
+        CUDA_TRY(ctx, cudaMemcpy(ny.data(), B.t_ny + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
+        CUDA_TRY(ctx, cudaMemcpy(nz.data(), B.t_nz + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m; ++i) normal[3 * i] = nx[i], normal[3 * i + 1] = ny[i], normal[3 * i + 2] = nz[i];
+    }
+    if (objects_close) {
+        if (B.t_close)
+            CUDA_TRY(ctx, cudaMemcpy(objects_close, B.t_close + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
+        else
+            memset(objects_close, 0, 8 * (size_t)m);
+    }
+    return 0;
+}
+
+int atmrt_get_path(atmrt_ctx* ctx, int y, int capacity, double* dist, double* elev, double* path_length, int* n) {
+    if (!ctx || !n) return fail(ctx, ATMRT_ERR_INVALID, "get_path: NULL argument");
+    if (!ctx->rendered) return fail(ctx, ATMRT_ERR_STATE, "get_path before a render");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const DevScene& S = ctx->scene;
+    if (y < 0 || y >= S.height) return fail(ctx, ATMRT_ERR_INVALID, "row out of range");
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    int len = 0;
+    CUDA_TRY(ctx, cudaMemcpy(&len, ctx->buf.p_n + y, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = len;
+    int m = std::min(capacity, len);
+    if (m <= 0) return 0;
+    size_t off = (size_t)y * S.n_pad;
+    if (dist) CUDA_TRY(ctx, cudaMemcpy(dist, ctx->buf.p_dist + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
+    if (elev) CUDA_TRY(ctx, cudaMemcpy(elev, ctx->buf.p_elev + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
+    if (path_length) CUDA_TRY(ctx, cudaMemcpy(path_length, ctx->buf.p_len + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int atmrt_atmosphere_probe(atmrt_ctx* ctx, const double* h, int n, double* temperature, double* pressure, double* refractive_index) {
+    if (!ctx || !h || n < 0) return fail(ctx, ATMRT_ERR_INVALID, "atmosphere_probe: bad argument");
+    if (!ctx->has_params) return fail(ctx, ATMRT_ERR_STATE, "atmosphere_probe before set_params");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return 0;
+    DevScene S{};
+    int rc = lower_atmosphere(ctx, ctx->params.atmosphere, ctx->params.wavelength, &S.atm);
+    if (rc) return rc;
+    size_t bytes = 8 * (size_t)n;
+    if (ensure(ctx, ctx->d_probe_a, bytes) | ensure(ctx, ctx->d_probe_b, bytes) | ensure(ctx, ctx->d_probe_c, bytes) | ensure(ctx, ctx->d_probe_d, bytes))
+        return ATMRT_ERR_CUDA;
+    cudaStream_t s = ctx->s_main;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_probe_a.p, h, bytes, cudaMemcpyHostToDevice, s));
+    k_atm_probe<<<(n + 127) / 128, 128, 0, s>>>(S, (const double*)ctx->d_probe_a.p, n, (double*)ctx->d_probe_b.p, (double*)ctx->d_probe_c.p,
+                                                  (double*)ctx->d_probe_d.p);
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (temperature) CUDA_TRY(ctx, cudaMemcpyAsync(temperature, ctx->d_probe_b.p, bytes, cudaMemcpyDeviceToHost, s));
+    if (pressure) CUDA_TRY(ctx, cudaMemcpyAsync(pressure, ctx->d_probe_c.p, bytes, cudaMemcpyDeviceToHost, s));
+    if (refractive_index) CUDA_TRY(ctx, cudaMemcpyAsync(refractive_index, ctx->d_probe_d.p, bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int atmrt_observer_altitude(atmrt_ctx* ctx, double* alt) {
+    if (!ctx || !alt) return fail(ctx, ATMRT_ERR_INVALID, "observer_altitude: NULL argument");
+    if (!ctx->rendered) return fail(ctx, ATMRT_ERR_STATE, "observer_altitude before a render");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    CUDA_TRY(ctx, cudaMemcpy(alt, ctx->buf.obs_alt, sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int atmrt_fp64_peak(atmrt_ctx* ctx, double* gflops, double* dadd_ginstr) {
+    if (!ctx) return ATMRT_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure(ctx, ctx->d_probe_a, 64);
+    if (rc) return rc;
+    cudaStream_t s = ctx->s_main;
+    const int iters = 4096, blocks = ctx->num_sms * 8, threads = 256;
+    cudaEvent_t e0 = ctx->t_0, e1 = ctx->t_1;
+    double best[2] = {0.0, 0.0};
+    for (int variant = 0; variant < 2; ++variant) {
+        for (int rep = 0; rep < 5; ++rep) {
+            CUDA_TRY(ctx, cudaEventRecord(e0, s));
+            if (variant == 0)
+                k_fp64_peak<true><<<blocks, threads, 0, s>>>((double*)ctx->d_probe_a.p, iters, 1.0000001, 1e-9);
+            else
+                k_fp64_peak<false><<<blocks, threads, 0, s>>>((double*)ctx->d_probe_a.p, iters, 1.0000001, 1e-9);
+            CUDA_TRY(ctx, cudaEventRecord(e1, s));
+            CUDA_TRY(ctx, cudaStreamSynchronize(s));
+            float ms = 0.f;
+            CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+            double instr = (double)blocks * threads * (double)iters * 8.0;
+            double rate = instr / (ms * 1e-3) / 1e9;  // G thread-instr/s
+            if (rep > 0 && rate > best[variant]) best[variant] = rate;
+        }
+    }
+    if (gflops) *gflops = best[0] * 2.0;
+    if (dadd_ginstr) *dadd_ginstr = best[1];
+    return 0;
+}
+
+}  // extern "C"

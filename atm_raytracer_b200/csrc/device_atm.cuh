@@ -1,0 +1,175 @@
+// device_atm.cuh -- atmosphere profiles, Ciddor refractive index and the ray-path stepper in f64.
+//
+// Restates the external crate atm-refraction 0.6 (Cargo.toml:8) from its published algorithms and
+// from the reference's call sites (generators/utils.rs:142-160, ray_path.rs:57-91,
+// atm_printer.rs:33-46): US-1976-style hydrostatic layers with linear temperature, the Ciddor (1996)
+// refractive index, dn/dh by central difference (eps = 0.01 m) and classical RK4 on the Fermat ray
+// equation in polar (spherical Earth) or Cartesian (flat Earth) form. PARITY UNPINNED against the
+// real crate (its source is not available offline); parity is against oracle/atmrt_oracle.cpp.
+#pragma once
+
+#include "device_math.cuh"
+
+namespace atmrt {
+
+// One temperature function of the atmosphere after host lowering (Atmosphere::from_def): a
+// reference altitude with known temperature and pressure, and the hydrostatic exponent.
+struct DevAtmLayer {
+    double start;     // lower boundary (-inf for layer 0)
+    double h_ref, t_ref, p_ref;
+    double gradient;  // K/m
+    double expo;      // gradient != 0: -g*M/(R*gradient)
+    double gm;        // -g*M
+    double rt;        // R*t_ref (isothermal layers)
+};
+
+struct DevAtmosphere {
+    int n;
+    int _pad;
+    double humidity;
+    DevAtmLayer layer[ATMRT_MAX_ATM_FUNCTIONS];
+    // Ciddor terms that depend only on the wavelength (lowered on the host with + - * / only).
+    double r_axs, r_vs, m_a, rho_axs;
+};
+
+__device__ __forceinline__ int atm_layer_index(const DevAtmosphere& a, double h) {
+    int idx = 0;
+    for (int i = 1; i < a.n; ++i)
+        if (h >= a.layer[i].start) idx = i;
+    return idx;
+}
+
+__device__ __forceinline__ double layer_temperature(const DevAtmLayer& l, double h) {
+    return l.t_ref + l.gradient * (h - l.h_ref);
+}
+
+__device__ __forceinline__ double layer_pressure(const DevAtmLayer& l, double h, double t) {
+    if (l.gradient != 0.0) return l.p_ref * pow(t / l.t_ref, l.expo);
+    return l.p_ref * exp(l.gm * (h - l.h_ref) / l.rt);
+}
+
+// Ciddor (1996); p in Pa, t in K.
+__device__ __forceinline__ double air_index(const DevAtmosphere& a, double p, double t_kelvin) {
+    const double a0 = 1.58123e-6, a1 = -2.9331e-8, a2 = 1.1043e-10;
+    const double b0 = 5.707e-6, b1 = -2.051e-8;
+    const double c0 = 1.9898e-4, c1 = -2.376e-6;
+    const double d = 1.83e-11, e = -0.765e-8;
+    const double rho_vs = 0.00985938;
+    const double gas_r = 8.314510, m_v = 0.018015;
+    const double alpha = 1.00062, beta = 3.14e-8, gamma = 5.6e-7;
+    const double sa = 1.2378847e-5, sb = -1.9121316e-2, sc = 33.93711047, sd = -6.3431645e3;
+
+    double t_c = t_kelvin - 273.15;
+    double x_v = 0.0;
+    if (a.humidity != 0.0) {
+        double svp = exp(sa * t_kelvin * t_kelvin + sb * t_kelvin + sc + sd / t_kelvin);
+        double f = alpha + beta * p + gamma * t_c * t_c;
+        x_v = a.humidity * f * svp / p;
+    }
+    double pt = p / t_kelvin;
+    double z_m = 1.0 - pt * (a0 + a1 * t_c + a2 * t_c * t_c + (b0 + b1 * t_c) * x_v + (c0 + c1 * t_c) * x_v * x_v) +
+                 pt * pt * (d + e * x_v * x_v);
+    double rho_v = x_v * p * m_v / (z_m * gas_r * t_kelvin);
+    double rho_a = (1.0 - x_v) * p * a.m_a / (z_m * gas_r * t_kelvin);
+    return 1.0 + (rho_a / a.rho_axs) * a.r_axs + (rho_v / rho_vs) * a.r_vs;
+}
+
+// Environment::n(h)
+__device__ __forceinline__ double env_n(const DevAtmosphere& a, double h) {
+    const DevAtmLayer& l = a.layer[atm_layer_index(a, h)];
+    double t = layer_temperature(l, h);
+    double p = layer_pressure(l, h, t);
+    return air_index(a, p, t);
+}
+
+// n(h) and dn/dh = (n(h+eps) - n(h-eps)) / (2 eps): three independent evaluations.
+__device__ __forceinline__ void env_n_dn(const DevAtmosphere& a, double h, double* n, double* dn) {
+    const double eps = 0.01;
+    double n0 = env_n(a, h);
+    double n1 = env_n(a, h - eps);
+    double n2 = env_n(a, h + eps);
+    *n = n0;
+    *dn = (n2 - n1) / (2.0 * eps);
+}
+
+struct RayState {
+    double x, h;
+};
+
+// Ray stepper state for one row of the path cache.
+struct Stepper {
+    // RK4 state: spherical (r, dr/dphi, phi) or flat (h, dh/dx, x)
+    double a, b, t;
+    // straight-line parameters
+    double h0, ang;
+};
+
+__device__ __forceinline__ void stepper_init(Stepper& s, int flat, double radius, double start_h, double ang_rad) {
+    s.h0 = start_h;
+    s.ang = ang_rad;
+    s.t = 0.0;
+    if (flat) {
+        s.a = start_h;
+        s.b = tan(ang_rad);
+    } else {
+        s.a = radius + start_h;
+        s.b = s.a * tan(ang_rad);
+    }
+}
+
+__device__ __forceinline__ void deriv_sph(const DevAtmosphere& atm, double radius, double r, double dr, double* o_r, double* o_dr) {
+    double n, dn;
+    env_n_dn(atm, r - radius, &n, &dn);
+    *o_r = dr;
+    *o_dr = dr * dr * dn / n + r * r * dn / n + 2.0 * dr * dr / r + r;
+}
+__device__ __forceinline__ void deriv_flat(const DevAtmosphere& atm, double h, double dh, double* o_h, double* o_dh) {
+    double n, dn;
+    env_n_dn(atm, h, &n, &dn);
+    *o_h = dh;
+    *o_dh = dn / n * (1.0 + dh * dh);
+}
+
+// PathStepper::next(): one step of size `step` metres along the ground.
+__device__ __forceinline__ RayState stepper_next(Stepper& s, const DevAtmosphere& atm, int flat, int straight, double radius, double step) {
+    if (straight) {
+        s.t += step;
+        if (flat) return {s.t, s.h0 + s.t * tan(s.ang)};
+        double r0 = radius + s.h0;
+        double ph = s.t / radius;
+        double rr = r0 * cos(s.ang) / cos(ph + s.ang);
+        return {s.t, rr - radius};
+    }
+    double k1a, k1b, k2a, k2b, k3a, k3b, k4a, k4b;
+    if (flat) {
+        double d = step;
+        deriv_flat(atm, s.a, s.b, &k1a, &k1b);
+        deriv_flat(atm, s.a + 0.5 * d * k1a, s.b + 0.5 * d * k1b, &k2a, &k2b);
+        deriv_flat(atm, s.a + 0.5 * d * k2a, s.b + 0.5 * d * k2b, &k3a, &k3b);
+        deriv_flat(atm, s.a + d * k3a, s.b + d * k3b, &k4a, &k4b);
+        s.a = s.a + (k1a + 2.0 * k2a + 2.0 * k3a + k4a) * d / 6.0;
+        s.b = s.b + (k1b + 2.0 * k2b + 2.0 * k3b + k4b) * d / 6.0;
+        s.t += d;
+        return {s.t, s.a};
+    }
+    double d = step / radius;
+    deriv_sph(atm, radius, s.a, s.b, &k1a, &k1b);
+    deriv_sph(atm, radius, s.a + 0.5 * d * k1a, s.b + 0.5 * d * k1b, &k2a, &k2b);
+    deriv_sph(atm, radius, s.a + 0.5 * d * k2a, s.b + 0.5 * d * k2b, &k3a, &k3b);
+    deriv_sph(atm, radius, s.a + d * k3a, s.b + d * k3b, &k4a, &k4b);
+    s.a = s.a + (k1a + 2.0 * k2a + 2.0 * k3a + k4a) * d / 6.0;
+    s.b = s.b + (k1b + 2.0 * k2b + 2.0 * k3b + k4b) * d / 6.0;
+    s.t += d;
+    return {s.t * radius, s.a - radius};
+}
+
+// calc_dist, generators/utils.rs:42-53
+__device__ __forceinline__ double calc_dist(int flat, double radius, RayState o, RayState n) {
+    double dx = n.x - o.x, dh = n.h - o.h;
+    if (flat) return sqrt(dx * dx + dh * dh);
+    double avg_h = (n.h + o.h) / 2.0;
+    dx = dx / radius * (avg_h + radius);
+    return sqrt(dx * dx + dh * dh);
+}
+
+}  // namespace atmrt

@@ -1,0 +1,608 @@
+// kernels.cuh -- the CUDA kernels of the panorama ray march (sm_100a, f64).
+//
+//   Stage A  k_terrain_profile : gen_terrain_cache  (generators/utils.rs:176-199, 72-88, 15-40)
+//   Stage B  k_ray_paths       : gen_path_cache     (generators/utils.rs:136-174)
+//            k_pyramid         : min/max (and objects_close OR) pyramids over both caches
+//   Stage C  k_march           : get_single_pixel   (generators/utils.rs:201-289) fused with
+//                                Object::check_collision, ColoringMethod::color_for_pixel,
+//                                renderer::draw_image compositing and the per-pixel metadata.
+#pragma once
+
+#include "device_atm.cuh"
+#include "device_math.cuh"
+#include "device_shade.cuh"
+
+namespace atmrt {
+
+constexpr int CHUNK = 32;  // march steps per level-1 chunk == warp width
+constexpr unsigned FULL = 0xffffffffu;
+
+// Everything a kernel needs about the scene, passed by value as a __grid_constant__ argument.
+struct DevScene {
+    double lat0, lon0, direction, tilt, fov, max_distance, step;
+    double radius;
+    double sin_diff, cos_diff;  // sin/cos(NORMAL_DIFF / radius), spherical find_normal
+    atmrt_altitude altitude;
+    int earth_model, straight, flat;
+    int width, height, x0, x1;
+    int n_t;     // terrain samples per column (N_t)
+    int n_pad;   // row stride of the [column][k] and [row][k] caches
+    int n1;      // level-1 chunks  = ceil(n_t / 32)
+    int n1_pad;  // row stride of the level-1 pyramids
+    int n2;      // level-2 chunks  = ceil(n1 / 32)
+    int nobjects;
+    int _pad;
+    DevAtmosphere atm;
+    DevShade shade;
+};
+
+struct DevBuffers {
+    const double* dist_k;  // [n_t] accumulated `distance += step` (utils.rs:191-196), host-computed
+    double* colcalc;       // [wl][8]: spherical {dir.xyz, pos.xyz}; flat {cos_az, sin_az, cos_lat0}
+    // Stage A cache, [wl][n_pad]
+    double *t_lat, *t_lon, *t_elev, *t_nx, *t_ny, *t_nz;
+    unsigned long long* t_close;
+    // Stage B cache, [h][n_pad]
+    double *p_dist, *p_elev, *p_len;
+    int* p_n;  // [h] elements per row (capped at n_t)
+    // pyramids
+    double *tmin1, *tmax1, *tmin2, *tmax2;  // [wl][n1_pad], [wl][n2]
+    unsigned long long *close1, *close2;
+    double *rmin1, *rmax1, *rmin2, *rmax2;  // [h][n1_pad], [h][n2]
+    double* obs_alt;  // [1]
+    DevObject* objects;
+    unsigned long long* counters;  // see Counter
+};
+
+enum Counter { CNT_RAY_STEPS = 0, CNT_TRACE_POINTS, CNT_PIXELS_HIT, CNT_OVERFLOWS, CNT_PATH_STEPS, CNT_COUNT };
+
+// ---------------------------------------------------------------------------------------------
+// Terrain packing
+// ---------------------------------------------------------------------------------------------
+__global__ void k_retile(const int16_t* __restrict__ raw, int16_t* __restrict__ posts, DevTile t) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long n = (long long)t.nlon * t.nlat;
+    if (i >= n) return;
+    int ilon = (int)(i / t.nlat), ilat = (int)(i % t.nlat);
+    posts[post_index(t, ilon, ilat)] = raw[i];
+}
+__global__ void k_untile(const int16_t* __restrict__ posts, int16_t* __restrict__ raw, DevTile t) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long n = (long long)t.nlon * t.nlat;
+    if (i >= n) return;
+    int ilon = (int)(i / t.nlat), ilat = (int)(i % t.nlat);
+    raw[i] = posts[post_index(t, ilon, ilat)];
+}
+
+__global__ void k_get_elev(DevTerrain T, const double* lat, const double* lon, int n, double* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double e;
+    out[i] = terrain_get_elev(T, lat[i], lon[i], &e) ? e : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+__global__ void k_atm_probe(const __grid_constant__ DevScene S, const double* h, int n, double* t, double* p, double* idx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DevAtmLayer& l = S.atm.layer[atm_layer_index(S.atm, h[i])];
+    double tt = layer_temperature(l, h[i]);
+    double pp = layer_pressure(l, h[i], tt);
+    t[i] = tt;
+    p[i] = pp;
+    idx[i] = air_index(S.atm, pp, tt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scene preparation: Altitude::abs for the observer (params.rs:23-30) and the objects
+// (object/mod.rs:165-186), object frames.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_prepare_scene(const __grid_constant__ DevScene S, DevTerrain T, DevBuffers B, const atmrt_object* objs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        double alt = S.altitude.value;
+        if (S.altitude.kind == ATMRT_ALT_RELATIVE) alt = elev_or_zero(T, S.lat0, S.lon0) + S.altitude.value;
+        *B.obs_alt = alt;
+    }
+    if (i >= 1 && i <= S.nobjects) {
+        const atmrt_object& o = objs[i - 1];
+        DevObject& d = B.objects[i - 1];
+        double alt = o.altitude.value;
+        if (o.altitude.kind == ATMRT_ALT_RELATIVE) alt = elev_or_zero(T, o.latitude, o.longitude) + o.altitude.value;
+        d.lat = o.latitude;
+        d.lon = o.longitude;
+        d.elev = alt;
+        d.pos = as_cartesian(S.earth_model, S.radius, o.latitude, o.longitude, alt);
+        d.up = world_directions(S.earth_model, o.latitude, o.longitude).up;
+        // kind, sizes, colour and texture pointer are filled by the host
+    }
+}
+
+// get_ray_dir / get_ray_elev, generators/fast.rs:111-125 (pixel centring goes through i16)
+__device__ __forceinline__ double get_ray_dir(const DevScene& S, int x) {
+    double width = (double)S.width;
+    double xx = (double)(short)((short)x - (short)S.width / 2) / width;
+    return S.direction + xx * S.fov;
+}
+__device__ __forceinline__ double get_ray_elev(const DevScene& S, int y) {
+    double width = (double)S.width, height = (double)S.height;
+    double aspect = width / height;
+    double yy = (double)(short)((short)y - (short)S.height / 2) / height;
+    return S.tilt - yy * S.fov / aspect;
+}
+
+// coords_at_dist_calc for every column: SphericalCalc::new (directional_calc.rs:56-69) /
+// FlDsCalc::new (:35-38).
+__global__ void k_column_setup(const __grid_constant__ DevScene S, DevBuffers B) {
+    int xl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xl >= S.x1 - S.x0) return;
+    double dir = get_ray_dir(S, S.x0 + xl);
+    double* c = B.colcalc + (size_t)xl * 8;
+    double sindir, cosdir;
+    sincos(to_radians(dir), &sindir, &cosdir);
+    if (S.flat) {
+        c[0] = cosdir;
+        c[1] = sindir;
+        c[2] = cos(to_radians(S.lat0));
+        return;
+    }
+    double sinlat, coslat, sinlon, coslon;
+    sincos(to_radians(S.lat0), &sinlat, &coslat);
+    sincos(to_radians(S.lon0), &sinlon, &coslon);
+    Dirs d = spherical_directions_sc(sinlat, coslat, sinlon, coslon);
+    V3 dv = d.north * cosdir + d.east * sindir;
+    c[0] = dv.x, c[1] = dv.y, c[2] = dv.z;
+    c[3] = d.up.x, c[4] = d.up.y, c[5] = d.up.z;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage A: terrain profile. One thread per (column, sample); lanes run along the ray so the
+// [column][k] stores are coalesced and the bilinear taps of a warp walk along one azimuth.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__ DevScene S, DevTerrain T, DevBuffers B) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int xl = blockIdx.y;
+    if (k >= S.n_t) return;
+    const double d = B.dist_k[k];
+    const double* cc = B.colcalc + (size_t)xl * 8;
+    double lat, lon;
+    if (S.flat) {  // FlDsCalc::coords_at_dist, directional_calc.rs:41-47
+        double d_lat = cc[0] * d / DEGREE_DISTANCE;
+        double d_lon = cc[1] * d / DEGREE_DISTANCE / cc[2];
+        lat = S.lat0 + d_lat;
+        lon = S.lon0 + d_lon;
+    } else {  // SphericalCalc::coords_at_dist, directional_calc.rs:71-86
+        double sinang, cosang;
+        sincos(d / S.radius, &sinang, &cosang);
+        spherical_walk(V3{cc[3], cc[4], cc[5]}, V3{cc[0], cc[1], cc[2]}, sinang, cosang, &lat, &lon);
+    }
+    double elev = elev_or_zero(T, lat, lon);
+
+    // find_normal, utils.rs:15-40: central differences +-15 m north/south and east/west.
+    double sinlat, coslat, sinlon, coslon;
+    sincos(to_radians(lat), &sinlat, &coslat);
+    sincos(to_radians(lon), &sinlon, &coslon);
+    double n_lat, n_lon, s_lat, s_lon, e_lat, e_lon, w_lat, w_lon;
+    Dirs D;
+    if (S.flat) {
+        // FlDsCalc::new((lat, lon), 0.0 / 90.0).coords_at_dist(+-DIFF)
+        n_lat = lat + 1.0 * NORMAL_DIFF / DEGREE_DISTANCE;
+        n_lon = lon + 0.0 * NORMAL_DIFF / DEGREE_DISTANCE / coslat;
+        s_lat = lat + 1.0 * -NORMAL_DIFF / DEGREE_DISTANCE;
+        s_lon = lon + 0.0 * -NORMAL_DIFF / DEGREE_DISTANCE / coslat;
+        e_lat = lat + COS_90 * NORMAL_DIFF / DEGREE_DISTANCE;
+        e_lon = lon + SIN_90 * NORMAL_DIFF / DEGREE_DISTANCE / coslat;
+        w_lat = lat + COS_90 * -NORMAL_DIFF / DEGREE_DISTANCE;
+        w_lon = lon + SIN_90 * -NORMAL_DIFF / DEGREE_DISTANCE / coslat;
+        D.north = {-coslon, -sinlon, 0.0};
+        D.east = {-sinlon, coslon, 0.0};
+        D.up = {0.0, 0.0, 1.0};
+    } else {
+        // SphericalCalc::new(radius, (lat, lon), 0.0 / 90.0).coords_at_dist(+-DIFF); the sin/cos of
+        // 0 and 90 degrees and of +-DIFF/radius are constants of the render.
+        D = spherical_directions_sc(sinlat, coslat, sinlon, coslon);
+        V3 dir_ns = D.north * 1.0 + D.east * 0.0;
+        V3 dir_ew = D.north * COS_90 + D.east * SIN_90;
+        spherical_walk(D.up, dir_ns, S.sin_diff, S.cos_diff, &n_lat, &n_lon);
+        spherical_walk(D.up, dir_ns, -S.sin_diff, S.cos_diff, &s_lat, &s_lon);
+        spherical_walk(D.up, dir_ew, S.sin_diff, S.cos_diff, &e_lat, &e_lon);
+        spherical_walk(D.up, dir_ew, -S.sin_diff, S.cos_diff, &w_lat, &w_lon);
+    }
+    double diff_ew = elev_or_zero(T, e_lat, e_lon) - elev_or_zero(T, w_lat, w_lon);
+    double diff_ns = elev_or_zero(T, n_lat, n_lon) - elev_or_zero(T, s_lat, s_lon);
+    V3 vec_ns = (2.0 * NORMAL_DIFF) * D.north + diff_ns * D.up;
+    V3 vec_ew = (2.0 * NORMAL_DIFF) * D.east + diff_ew * D.up;
+    V3 normal = cross(vec_ew, vec_ns);
+    normal = normal / sqrt(dot(normal, normal));
+
+    size_t idx = (size_t)xl * S.n_pad + k;
+    B.t_lat[idx] = lat;
+    B.t_lon[idx] = lon;
+    B.t_elev[idx] = elev;
+    B.t_nx[idx] = normal.x;
+    B.t_ny[idx] = normal.y;
+    B.t_nz[idx] = normal.z;
+
+    if (S.nobjects > 0) {  // Object::is_close, frustum.rs:103-114 / billboard.rs:68-78
+        unsigned long long mask = 0;
+        for (int i = 0; i < S.nobjects; ++i) {
+            const DevObject& o = B.objects[i];
+            V3 pos = as_cartesian_sc(S.earth_model, S.radius, lat, o.elev, sinlat, coslat, sinlon, coslon);
+            V3 dist_v = pos - o.pos;
+            if (dot(dist_v, dist_v) < 2.0 * (o.close_r + S.step) * (o.close_r + S.step)) mask |= 1ull << i;
+        }
+        B.t_close[idx] = mask;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage B: ray paths. One serial RK4 chain per image row (the only parallelism the physics
+// offers is across rows and inside one derivative evaluation).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevScene S, DevBuffers B, int rows_per_warp) {
+    int lane = threadIdx.x;
+    if (lane >= rows_per_warp) return;
+    int y = blockIdx.x * rows_per_warp + lane;
+    if (y >= S.height) return;
+    const double alt = *B.obs_alt;
+    const double ray_elev = get_ray_elev(S, y);
+    Stepper st;
+    stepper_init(st, S.flat, S.radius, alt, to_radians(ray_elev));
+    size_t base = (size_t)y * S.n_pad;
+    B.p_dist[base] = 0.0;
+    B.p_elev[base] = alt;
+    B.p_len[base] = 0.0;
+    RayState prev{0.0, alt};
+    double path_length = 0.0;
+    int n = 1;
+    for (int i = 1; i < S.n_t; ++i) {
+        RayState nw = stepper_next(st, S.atm, S.flat, S.straight, S.radius, S.step);
+        path_length += calc_dist(S.flat, S.radius, prev, nw);
+        B.p_dist[base + i] = nw.x;
+        B.p_elev[base + i] = nw.h;
+        B.p_len[base + i] = path_length;
+        n = i + 1;
+        if (prev.x > S.max_distance || prev.h < -1000.0) break;
+        prev = nw;
+    }
+    B.p_n[y] = n;
+    atomicAdd(B.counters + CNT_PATH_STEPS, (unsigned long long)(n - 1));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Min/max pyramids. Level-1 chunk c covers march steps k in [32c, 32c+31] (k >= 1), i.e. samples
+// [32c-1, 32c+31]; level-2 chunk C covers level-1 chunks [32C, 32C+31]. One warp per (row, C).
+// A chunk without any step (or with only NaN samples) gets min=+inf, max=-inf and is never a
+// candidate.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pyramid(const double* __restrict__ vals, const int* __restrict__ lens,
+                                                 const unsigned long long* __restrict__ close, int nrows, int n_total,
+                                                 int n_pad, int n1, int n1_pad, int n2, double* __restrict__ min1,
+                                                 double* __restrict__ max1, double* __restrict__ min2,
+                                                 double* __restrict__ max2, unsigned long long* __restrict__ close1,
+                                                 unsigned long long* __restrict__ close2) {
+    const int lane = threadIdx.x & 31;
+    long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= (long long)nrows * n2) return;
+    const int row = (int)(warp / n2), C = (int)(warp % n2);
+    const int n = lens ? min(lens[row], n_total) : n_total;
+    const double* v = vals + (size_t)row * n_pad;
+    const unsigned long long* cl = close ? close + (size_t)row * n_pad : nullptr;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double lo2 = INF, hi2 = -INF;
+    unsigned long long cm2 = 0;
+    for (int c1 = 0; c1 < 32; ++c1) {
+        int c = C * 32 + c1;
+        if (c >= n1) break;
+        double lo = INF, hi = -INF;
+        unsigned long long cm = 0;
+        bool has_steps = n >= 2 && 32 * c <= n - 1;
+        if (has_steps) {
+            int k = 32 * c + lane;
+            if (k < n) {
+                double x = v[k];
+                lo = fmin(lo, x);
+                hi = fmax(hi, x);
+                if (cl) cm = cl[k];
+            }
+            if (lane == 0 && c > 0) {
+                double x = v[32 * c - 1];
+                lo = fmin(lo, x);
+                hi = fmax(hi, x);
+                if (cl) cm |= cl[32 * c - 1];
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fmin(lo, __shfl_xor_sync(FULL, lo, o));
+            hi = fmax(hi, __shfl_xor_sync(FULL, hi, o));
+            cm |= __shfl_xor_sync(FULL, cm, o);
+        }
+        if (lane == 0) {
+            min1[(size_t)row * n1_pad + c] = lo;
+            max1[(size_t)row * n1_pad + c] = hi;
+            if (close1) close1[(size_t)row * n1_pad + c] = cm;
+        }
+        lo2 = fmin(lo2, lo);
+        hi2 = fmax(hi2, hi);
+        cm2 |= cm;
+    }
+    if (lane == 0) {
+        min2[(size_t)row * n2 + C] = lo2;
+        max2[(size_t)row * n2 + C] = hi2;
+        if (close2) close2[(size_t)row * n2 + C] = cm2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage C: the march.
+// ---------------------------------------------------------------------------------------------
+struct PixelState {
+    Rgb8 result;
+    double accum_neg_alpha;
+    int count;
+    int finished;
+    int consumed;
+    unsigned overflows;
+    double m_lat, m_lon, m_elev, m_dist;
+};
+
+struct MarchOut {
+    unsigned char* rgb;          // [h][wl][3]
+    atmrt_meta* meta;            // [h][wl]
+    int* steps;                  // [h][wl]
+    atmrt_trace_point* points;   // [h][wl][max_points] (TRACE)
+    int* counts;                 // [h][wl]             (TRACE)
+    int max_points;
+};
+
+// One march step with at least one event (terrain crossing or a close object). Executed
+// uniformly by all lanes of the warp that owns the pixel (same addresses -> broadcast loads), so
+// the pixel state stays warp-uniform without shuffles. Follows get_single_pixel's loop body
+// (utils.rs:211-287) and draw_image's inner loop (renderer/mod.rs:399-408).
+template <bool TRACE>
+__device__ __noinline__ void process_step(const DevScene& S, const DevBuffers& B, const MarchOut& O, int xl, int y, int k,
+                                          size_t pixel, PixelState& st) {
+    const size_t ti = (size_t)xl * S.n_pad + k, pi = (size_t)y * S.n_pad + k;
+    // old_tracing_state = (terrain[k-1], path[k-1]) with dist/path_len forced to 0 for k-1 == 0.
+    const double lat0 = B.t_lat[ti - 1], lon0 = B.t_lon[ti - 1], elev0 = B.t_elev[ti - 1];
+    const double lat1 = B.t_lat[ti], lon1 = B.t_lon[ti], elev1 = B.t_elev[ti];
+    const double ray0 = B.p_elev[pi - 1], ray1 = B.p_elev[pi];
+    const double dist0 = k - 1 == 0 ? 0.0 : B.p_dist[pi - 1], dist1 = B.p_dist[pi];
+    const double len0 = k - 1 == 0 ? 0.0 : B.p_len[pi - 1], len1 = B.p_len[pi];
+
+    double c_prop[ATMRT_MAX_STEP_POINTS];
+    V3 c_normal[ATMRT_MAX_STEP_POINTS];
+    Color4 c_color[ATMRT_MAX_STEP_POINTS];
+    bool c_terrain[ATMRT_MAX_STEP_POINTS];
+    int ncand = 0;
+    bool overflow = false;
+    bool finish = false;
+
+    const double diff1 = ray0 - elev0, diff2 = ray1 - elev1;
+    if (diff1 * diff2 < 0.0) {
+        double prop = diff1 / (diff1 - diff2);
+        V3 n0{B.t_nx[ti - 1], B.t_ny[ti - 1], B.t_nz[ti - 1]}, n1{B.t_nx[ti], B.t_ny[ti], B.t_nz[ti]};
+        c_prop[0] = prop;
+        c_normal[0] = n0 + (n1 - n0) * prop;
+        c_color[0] = Color4{0.0, 0.0, 0.0, S.shade.terrain_alpha};
+        c_terrain[0] = true;
+        ncand = 1;
+        if (S.shade.terrain_alpha == 1.0) finish = true;
+    }
+    if (S.nobjects > 0) {
+        unsigned long long mask = B.t_close[ti - 1] | B.t_close[ti];
+        if (mask) {
+            V3 pos1 = as_cartesian(S.earth_model, S.radius, lat0, lon0, ray0);
+            V3 pos2 = as_cartesian(S.earth_model, S.radius, lat1, lon1, ray1);
+            // The reference walks a HashSet (arbitrary order); index order here. Only exact `prop` ties
+            // could tell the difference (stable sort below).
+            while (mask) {
+                int oi = __ffsll((long long)mask) - 1;
+                mask &= mask - 1;
+                const DevObject& o = B.objects[oi];
+                Collision coll[4];
+                int nc = o.kind == ATMRT_OBJECT_FRUSTUM ? frustum_collision(o, pos1, pos2, coll)
+                                                        : billboard_collision(o, pos1, pos2, coll);
+                for (int i = 0; i < nc; ++i) {
+                    if (coll[i].color.a == 0.0) continue;
+                    if (ncand < ATMRT_MAX_STEP_POINTS) {
+                        c_prop[ncand] = coll[i].prop;
+                        c_normal[ncand] = coll[i].normal;
+                        c_color[ncand] = coll[i].color;
+                        c_terrain[ncand] = false;
+                        ++ncand;
+                    } else {
+                        overflow = true;
+                    }
+                    if (coll[i].color.a == 1.0) {
+                        finish = true;
+                        break;
+                    }
+                }
+            }
+        }
+    }
+    if (overflow) st.overflows += 1;
+    // stable sort by prop (step_result.sort_by, utils.rs:281)
+    int order[ATMRT_MAX_STEP_POINTS];
+    for (int i = 0; i < ncand; ++i) {
+        int j = i - 1;
+        while (j >= 0 && c_prop[i] < c_prop[order[j]]) {
+            order[j + 1] = order[j];
+            --j;
+        }
+        order[j + 1] = i;
+    }
+    for (int oi = 0; oi < ncand; ++oi) {
+        const int i = order[oi];
+        const double prop = c_prop[i];
+        // TracingState::interpolate, utils.rs:108-125
+        const double lat = lat0 + (lat1 - lat0) * prop;
+        const double lon = lon0 + (lon1 - lon0) * prop;
+        const double t_elev = elev0 + (elev1 - elev0) * prop;
+        const double r_elev = ray0 + (ray1 - ray0) * prop;
+        const double dist = dist0 + (dist1 - dist0) * prop;
+        const double plen = len0 + (len1 - len0) * prop;
+        const double elevation = c_terrain[i] ? t_elev : r_elev;
+        const double alpha = c_color[i].a;
+        Rgb8 color1 = color_for_pixel(S.shade, c_terrain[i], elevation, dist, c_normal[i], c_color[i]);
+        Rgb8 color2 = S.shade.fog_enabled ? apply_fog(S.shade.fog_distance, plen, color1) : color1;
+        st.result = add_rgb(st.result, color2, st.accum_neg_alpha * alpha);
+        st.accum_neg_alpha *= 1.0 - alpha;
+        if (st.count == 0) {
+            st.m_lat = lat, st.m_lon = lon, st.m_elev = elevation, st.m_dist = dist;
+        }
+        if (TRACE) {
+            if (st.count < O.max_points && (threadIdx.x & 31) == 0) {
+                atmrt_trace_point& tp = O.points[pixel * O.max_points + st.count];
+                tp.lat = lat, tp.lon = lon, tp.distance = dist, tp.elevation = elevation, tp.path_length = plen;
+                tp.normal[0] = c_normal[i].x, tp.normal[1] = c_normal[i].y, tp.normal[2] = c_normal[i].z;
+                tp.color[0] = c_color[i].r, tp.color[1] = c_color[i].g, tp.color[2] = c_color[i].b, tp.color[3] = alpha;
+                tp.is_terrain = c_terrain[i] ? 1 : 0;
+                tp.step = k;
+            }
+        }
+        st.count += 1;
+    }
+    if (finish) {
+        st.finished = 1;
+        st.consumed = k;
+    }
+}
+
+// Level-0: the 32 steps of chunk c1, one per lane. Detects the events exactly like the reference
+// (`diff1 * diff2 < 0.0`, utils.rs:220-222; non-empty objects_close, :241-243) and processes them
+// in step order until the pixel finishes.
+template <bool TRACE>
+__device__ __forceinline__ void march_chunk(const DevScene& S, const DevBuffers& B, const MarchOut& O, int xl, int y, int c1,
+                                            int nlim, size_t pixel, PixelState& st) {
+    const int lane = threadIdx.x & 31;
+    const int k = c1 * CHUNK + lane;
+    bool ev = false;
+    if (k >= 1 && k < nlim) {
+        const size_t ti = (size_t)xl * S.n_pad + k, pi = (size_t)y * S.n_pad + k;
+        double diff1 = B.p_elev[pi - 1] - B.t_elev[ti - 1];
+        double diff2 = B.p_elev[pi] - B.t_elev[ti];
+        ev = diff1 * diff2 < 0.0;
+        if (S.nobjects > 0) ev = ev || (B.t_close[ti - 1] | B.t_close[ti]) != 0;
+    }
+    unsigned m = __ballot_sync(FULL, ev);
+    while (m && !st.finished) {
+        int l = __ffs(m) - 1;
+        m &= m - 1;
+        process_step<TRACE>(S, B, O, xl, y, c1 * CHUNK + l, pixel, st);
+    }
+}
+
+template <bool BRUTE, bool TRACE>
+__global__ void __launch_bounds__(256) k_march(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O) {
+    const int lane = threadIdx.x & 31;
+    const int wl = S.x1 - S.x0;
+    const long long npix = (long long)wl * S.height;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned long long s_steps = 0, s_points = 0, s_hit = 0, s_over = 0;
+    const bool translucent = S.shade.terrain_alpha != 1.0;
+
+    for (long long pixel = warp; pixel < npix; pixel += nwarps) {
+        const int y = (int)(pixel / wl), xl = (int)(pixel % wl);
+        const int nlim = min(S.n_t, B.p_n[y]);
+        PixelState st;
+        st.result = Rgb8{{0, 0, 0}};
+        st.accum_neg_alpha = 1.0;
+        st.count = 0;
+        st.finished = 0;
+        st.consumed = nlim > 0 ? nlim - 1 : 0;
+        st.overflows = 0;
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        st.m_lat = st.m_lon = st.m_elev = st.m_dist = qnan;
+
+        if (BRUTE) {
+            const int nc = (nlim + CHUNK - 1) / CHUNK;
+            for (int c1 = 0; c1 < nc && !st.finished; ++c1) march_chunk<TRACE>(S, B, O, xl, y, c1, nlim, (size_t)pixel, st);
+        } else {
+            // Level 2 -> level 1 -> level 0 descent. A chunk can contain a terrain crossing only if
+            // some diff may be negative AND some may be positive: rmin < tmax && rmax > tmin.
+            // Opaque terrain: the ray starts above ground in practice, but both polarities are
+            // handled so the result is exact for any start. (`translucent` only matters downstream.)
+            (void)translucent;
+            for (int cb = 0; cb < S.n2 && !st.finished; cb += 32) {
+                const int C = cb + lane;
+                bool cand2 = false;
+                if (C < S.n2) {
+                    const size_t tj = (size_t)xl * S.n2 + C, rj = (size_t)y * S.n2 + C;
+                    const double rmin = B.rmin2[rj], rmax = B.rmax2[rj];
+                    cand2 = rmin < B.tmax2[tj] && rmax > B.tmin2[tj];
+                    if (S.nobjects > 0) cand2 = cand2 || (B.close2[tj] != 0 && rmin <= rmax);
+                }
+                unsigned m2 = __ballot_sync(FULL, cand2);
+                while (m2 && !st.finished) {
+                    const int c2 = cb + __ffs(m2) - 1;
+                    m2 &= m2 - 1;
+                    const int c = c2 * 32 + lane;
+                    bool cand1 = false;
+                    if (c < S.n1) {
+                        const size_t tj = (size_t)xl * S.n1_pad + c, rj = (size_t)y * S.n1_pad + c;
+                        const double rmin = B.rmin1[rj], rmax = B.rmax1[rj];
+                        cand1 = rmin < B.tmax1[tj] && rmax > B.tmin1[tj];
+                        if (S.nobjects > 0) cand1 = cand1 || (B.close1[tj] != 0 && rmin <= rmax);
+                    }
+                    unsigned m1 = __ballot_sync(FULL, cand1);
+                    while (m1 && !st.finished) {
+                        const int c1 = c2 * 32 + __ffs(m1) - 1;
+                        m1 &= m1 - 1;
+                        march_chunk<TRACE>(S, B, O, xl, y, c1, nlim, (size_t)pixel, st);
+                    }
+                }
+            }
+        }
+
+        // draw_image tail: *px = add(result, def_color, accum_neg_alpha)  (renderer/mod.rs:410)
+        if (lane == 0) {
+            Rgb8 def{{S.shade.def_color[0], S.shade.def_color[1], S.shade.def_color[2]}};
+            Rgb8 px = add_rgb(st.result, def, st.accum_neg_alpha);
+            if (O.rgb) {
+                O.rgb[pixel * 3 + 0] = px.c[0];
+                O.rgb[pixel * 3 + 1] = px.c[1];
+                O.rgb[pixel * 3 + 2] = px.c[2];
+            }
+            if (O.meta) {
+                atmrt_meta mm{st.m_lat, st.m_lon, st.m_elev, st.m_dist};
+                O.meta[pixel] = mm;
+            }
+            if (O.steps) O.steps[pixel] = st.consumed;
+            if (TRACE && O.counts) O.counts[pixel] = st.count;
+        }
+        s_steps += (unsigned long long)st.consumed;
+        s_points += (unsigned long long)st.count;
+        s_hit += st.count > 0 ? 1 : 0;
+        s_over += st.overflows;
+    }
+    if (lane == 0) {
+        if (s_steps) atomicAdd(B.counters + CNT_RAY_STEPS, s_steps);
+        if (s_points) atomicAdd(B.counters + CNT_TRACE_POINTS, s_points);
+        if (s_hit) atomicAdd(B.counters + CNT_PIXELS_HIT, s_hit);
+        if (s_over) atomicAdd(B.counters + CNT_OVERFLOWS, s_over);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 pipe micro-benchmark (the roofline denominator for this path: MEASURED_PEAKS.json has no
+// FP64 figure). 8 independent DFMA (or DADD) chains per thread.
+// ---------------------------------------------------------------------------------------------
+template <bool FMA>
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double b, double c) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+    for (int i = 0; i < iters; ++i) {
+        if (FMA) {
+            a0 = fma(a0, b, c), a1 = fma(a1, b, c), a2 = fma(a2, b, c), a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c), a5 = fma(a5, b, c), a6 = fma(a6, b, c), a7 = fma(a7, b, c);
+        } else {
+            a0 = a0 + c, a1 = a1 + c, a2 = a2 + c, a3 = a3 + c;
+            a4 = a4 + c, a5 = a5 + c, a6 = a6 + c, a7 = a7 + c;
+        }
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) out[0] = s;  // keep the chains alive
+}
+
+}  // namespace atmrt

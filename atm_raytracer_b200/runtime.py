@@ -1,0 +1,317 @@
+"""ctypes binding of ``libatmrt_cuda.so`` and the host-side mirror of the reference's generator seam.
+
+``Terrain`` mirrors terrain/mod.rs (``Terrain::from_folder``), ``FastGenerator`` mirrors
+generator/generators/fast.rs (``FastGenerator::new(&params, &terrain, start).generate()``) and
+``output_image`` mirrors renderer/mod.rs:416-437. All arithmetic of the hot path runs in the CUDA
+library; there is no CPU fallback -- importing this module without the built library raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libatmrt_cuda.so")
+HOST_LIB_PATH = os.path.join(_HERE, "libatmrt_host.so")
+
+
+class AtmrtError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"atmrt error {code}: {message}")
+        self.code = code
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). The hot path has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    vp = C.c_void_p
+    sig = {
+        "atmrt_abi_version": (C.c_int, []),
+        "atmrt_abi_sizes": (C.c_int, [P(C.c_size_t), C.c_int]),
+        "atmrt_create": (C.c_int, [C.c_int, P(vp)]),
+        "atmrt_destroy": (None, [vp]),
+        "atmrt_last_error": (C.c_char_p, [vp]),
+        "atmrt_terrain_packed_bytes": (C.c_int, [P(abi.TileDesc), C.c_int, P(C.c_size_t)]),
+        "atmrt_pack_terrain": (C.c_int, [vp, P(abi.TileDesc), C.c_int, P(vp), vp]),
+        "atmrt_bind_terrain": (C.c_int, [vp, P(abi.TileDesc), C.c_int, vp]),
+        "atmrt_set_terrain": (C.c_int, [vp, P(abi.TileDesc), C.c_int, P(vp)]),
+        "atmrt_get_elev": (C.c_int, [vp, vp, vp, C.c_int, vp]),
+        "atmrt_read_tile": (C.c_int, [vp, C.c_int, vp]),
+        "atmrt_set_params": (C.c_int, [vp, P(abi.Params)]),
+        "atmrt_set_objects": (C.c_int, [vp, P(abi.Object), C.c_int, P(vp)]),
+        "atmrt_render": (C.c_int, [vp, vp, vp, vp, P(abi.Stats)]),
+        "atmrt_render_device": (C.c_int, [vp, vp, vp, vp, P(abi.Stats), vp]),
+        "atmrt_render_trace": (C.c_int, [vp, vp, vp, C.c_int]),
+        "atmrt_set_march_mode": (C.c_int, [vp, C.c_int]),
+        "atmrt_set_rows_per_warp": (C.c_int, [vp, C.c_int]),
+        "atmrt_get_terrain_profile": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, P(C.c_int)]),
+        "atmrt_get_path": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, P(C.c_int)]),
+        "atmrt_atmosphere_probe": (C.c_int, [vp, vp, C.c_int, vp, vp, vp]),
+        "atmrt_observer_altitude": (C.c_int, [vp, P(C.c_double)]),
+        "atmrt_fp64_peak": (C.c_int, [vp, P(C.c_double), P(C.c_double)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib, sorted(sig)
+
+
+lib, EXPORTED = _load()
+
+META_DTYPE = np.dtype([("lat", "<f8"), ("lon", "<f8"), ("elevation", "<f8"), ("distance", "<f8")])
+TRACE_DTYPE = np.dtype(
+    [("lat", "<f8"), ("lon", "<f8"), ("distance", "<f8"), ("elevation", "<f8"), ("path_length", "<f8"),
+     ("normal", "<f8", 3), ("color", "<f8", 4), ("is_terrain", "<i4"), ("step", "<i4")]
+)
+assert META_DTYPE.itemsize == C.sizeof(abi.Meta) and TRACE_DTYPE.itemsize == C.sizeof(abi.TracePoint)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Terrain:
+    """Decoded DTED tiles on the host (``Terrain``, terrain/mod.rs:55-126).
+
+    ``tiles`` is a list of ``(abi.TileDesc, int16 ndarray [nlon][nlat])``. Decoding is done by the
+    C++ host library (``libatmrt_host.so``: atmrt_host_read_dted) or by the caller.
+    """
+
+    def __init__(self, tiles=None):
+        self.tiles = list(tiles or [])
+
+    @staticmethod
+    def desc(lat0, lon0, posts, lat_interval=None, lon_interval=None):
+        nlon, nlat = posts.shape
+        d = abi.TileDesc()
+        d.lat0, d.lon0 = int(lat0), int(lon0)  # `as i16` truncation of the header origin
+        d.nlon, d.nlat = int(nlon), int(nlat)
+        d.min_lat, d.min_lon = float(lat0), float(lon0)
+        d.lat_interval = 3600.0 / (nlat - 1) if lat_interval is None else float(lat_interval)
+        d.lon_interval = 3600.0 / (nlon - 1) if lon_interval is None else float(lon_interval)
+        return d
+
+    @classmethod
+    def from_arrays(cls, items):
+        """items: iterable of (lat0, lon0, posts[nlon][nlat])."""
+        out = []
+        for lat0, lon0, posts in items:
+            posts = np.ascontiguousarray(posts, dtype=np.int16)
+            out.append((cls.desc(lat0, lon0, posts), posts))
+        return cls(out)
+
+    @classmethod
+    def from_folder(cls, folder):
+        """``Terrain::from_folder`` (terrain/mod.rs:66-83): every entry must be a DTED file."""
+        from . import host
+
+        tiles = []
+        names = sorted(os.listdir(folder))
+        for name in names:
+            tiles.append(host.read_dted(os.path.join(folder, name)))
+        print(f"Detected {len(names)} terrain files")
+        return cls(tiles)
+
+    def c_arrays(self):
+        n = len(self.tiles)
+        descs = (abi.TileDesc * max(n, 1))()
+        ptrs = (C.c_void_p * max(n, 1))()
+        for i, (d, posts) in enumerate(self.tiles):
+            descs[i] = d
+            ptrs[i] = posts.ctypes.data
+        return descs, ptrs, n
+
+    @property
+    def bytes(self):
+        return sum(p.nbytes for _, p in self.tiles)
+
+
+class Context:
+    """One ``atmrt_ctx`` (one GPU)."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        rc = lib.atmrt_create(int(device), C.byref(h))
+        if rc != 0:
+            raise AtmrtError(rc, (lib.atmrt_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+        self._keep = []
+        self.params = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.atmrt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise AtmrtError(rc, (lib.atmrt_last_error(self._h) or b"").decode())
+
+    # ---- terrain ----
+    def set_terrain(self, terrain):
+        descs, ptrs, n = terrain.c_arrays()
+        self._check(lib.atmrt_set_terrain(self._h, descs, n, ptrs))
+        self._terrain = terrain
+
+    def packed_bytes(self, terrain):
+        descs, _, n = terrain.c_arrays()
+        out = C.c_size_t()
+        self._check(lib.atmrt_terrain_packed_bytes(descs, n, C.byref(out)))
+        return out.value
+
+    def pack_terrain(self, terrain, dev_ptr):
+        descs, ptrs, n = terrain.c_arrays()
+        self._check(lib.atmrt_pack_terrain(self._h, descs, n, ptrs, C.c_void_p(dev_ptr)))
+
+    def bind_terrain(self, terrain, dev_ptr):
+        descs, _, n = terrain.c_arrays()
+        self._check(lib.atmrt_bind_terrain(self._h, descs, n, C.c_void_p(dev_ptr)))
+        self._terrain = terrain
+
+    def get_elev(self, lat, lon):
+        lat = np.ascontiguousarray(lat, dtype=np.float64)
+        lon = np.ascontiguousarray(lon, dtype=np.float64)
+        out = np.empty_like(lat)
+        self._check(lib.atmrt_get_elev(self._h, _ptr(lat), _ptr(lon), lat.size, _ptr(out)))
+        return out
+
+    def read_tile(self, index):
+        d, posts = self._terrain.tiles[index]
+        out = np.empty((d.nlon, d.nlat), dtype=np.int16)
+        self._check(lib.atmrt_read_tile(self._h, index, _ptr(out)))
+        return out
+
+    # ---- scene ----
+    def set_params(self, params):
+        self._check(lib.atmrt_set_params(self._h, C.byref(params)))
+        self.params = params
+
+    def set_objects(self, objects, textures=None):
+        n = len(objects)
+        arr = (abi.Object * max(n, 1))()
+        ptrs = (C.c_void_p * max(n, 1))()
+        keep = []
+        for i, o in enumerate(objects):
+            arr[i] = o
+            t = None if textures is None else textures[i]
+            if t is not None:
+                t = np.ascontiguousarray(t, dtype=np.uint8)
+                keep.append(t)
+                ptrs[i] = t.ctypes.data
+        self._check(lib.atmrt_set_objects(self._h, arr, n, ptrs))
+
+    def set_march_mode(self, mode):
+        self._check(lib.atmrt_set_march_mode(self._h, int(mode)))
+
+    def set_rows_per_warp(self, rows):
+        self._check(lib.atmrt_set_rows_per_warp(self._h, int(rows)))
+
+    # ---- render ----
+    def shape(self):
+        p = self.params
+        return p.height, p.x1 - p.x0
+
+    def render(self, rgb=True, meta=True, steps=True, out=None):
+        """Host-buffer render (copies inside the call). Returns dict(rgb, meta, steps, stats).
+        ``out`` may carry preallocated (e.g. pinned) arrays under the same keys."""
+        h, w = self.shape()
+        out = out or {}
+        a_rgb = out.get("rgb") if rgb else None
+        a_meta = out.get("meta") if meta else None
+        a_steps = out.get("steps") if steps else None
+        if rgb and a_rgb is None:
+            a_rgb = np.empty((h, w, 3), dtype=np.uint8)
+        if meta and a_meta is None:
+            a_meta = np.empty((h, w), dtype=META_DTYPE)
+        if steps and a_steps is None:
+            a_steps = np.empty((h, w), dtype=np.int32)
+        st = abi.Stats()
+        self._check(lib.atmrt_render(self._h, _ptr(a_rgb), _ptr(a_meta), _ptr(a_steps), C.byref(st)))
+        return {"rgb": a_rgb, "meta": a_meta, "steps": a_steps, "stats": st.as_dict()}
+
+    def render_device(self, rgb_ptr=0, meta_ptr=0, steps_ptr=0, stream=0, want_stats=False):
+        st = abi.Stats() if want_stats else None
+        self._check(
+            lib.atmrt_render_device(self._h, C.c_void_p(rgb_ptr or None), C.c_void_p(meta_ptr or None), C.c_void_p(steps_ptr or None),
+                                    C.byref(st) if st is not None else None, C.c_void_p(stream or None))
+        )
+        return st.as_dict() if st is not None else None
+
+    def render_trace(self, max_points=8):
+        h, w = self.shape()
+        pts = np.zeros((h, w, max(max_points, 1)), dtype=TRACE_DTYPE)
+        cnt = np.zeros((h, w), dtype=np.int32)
+        self._check(lib.atmrt_render_trace(self._h, _ptr(pts), _ptr(cnt), int(max_points)))
+        return pts, cnt
+
+    # ---- probes ----
+    def terrain_profile(self, x):
+        n = C.c_int()
+        self._check(lib.atmrt_get_terrain_profile(self._h, x, 0, None, None, None, None, None, C.byref(n)))
+        m = n.value
+        lat, lon, elev = np.empty(m), np.empty(m), np.empty(m)
+        normal = np.empty((m, 3))
+        close = np.empty(m, dtype=np.uint64)
+        self._check(lib.atmrt_get_terrain_profile(self._h, x, m, _ptr(lat), _ptr(lon), _ptr(elev), _ptr(normal), _ptr(close), C.byref(n)))
+        return {"lat": lat, "lon": lon, "elev": elev, "normal": normal, "close": close}
+
+    def path(self, y):
+        n = C.c_int()
+        self._check(lib.atmrt_get_path(self._h, y, 0, None, None, None, C.byref(n)))
+        m = n.value
+        dist, elev, plen = np.empty(m), np.empty(m), np.empty(m)
+        self._check(lib.atmrt_get_path(self._h, y, m, _ptr(dist), _ptr(elev), _ptr(plen), C.byref(n)))
+        return {"dist": dist, "elev": elev, "path_length": plen}
+
+    def atmosphere_probe(self, h):
+        h = np.ascontiguousarray(h, dtype=np.float64)
+        t, p, n = np.empty_like(h), np.empty_like(h), np.empty_like(h)
+        self._check(lib.atmrt_atmosphere_probe(self._h, _ptr(h), h.size, _ptr(t), _ptr(p), _ptr(n)))
+        return t, p, n
+
+    def observer_altitude(self):
+        v = C.c_double()
+        self._check(lib.atmrt_observer_altitude(self._h, C.byref(v)))
+        return v.value
+
+    def fp64_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(lib.atmrt_fp64_peak(self._h, C.byref(a), C.byref(b)))
+        return {"dfma_gflops": a.value, "dadd_ginstr": b.value}
+
+
+class FastGenerator:
+    """``FastGenerator`` (generator/generators/fast.rs:16-109): ``generate()`` returns the rendered
+    column block (rgb, per-pixel metadata, ray-step counts, stats) instead of ``Vec<Vec<ResultPixel>>``
+    because colouring and compositing are fused into the march kernel."""
+
+    def __init__(self, params, terrain, objects=(), textures=None, device=0, context=None):
+        self.ctx = context or Context(device)
+        self.ctx.set_terrain(terrain)
+        self.ctx.set_params(params)
+        self.ctx.set_objects(list(objects), textures)
+
+    def generate(self, **kw):
+        return self.ctx.render(**kw)
+
+
+def output_image(rgb, path):
+    """``renderer::output_image`` tail (renderer/mod.rs:433-436): save the RGB8 image as PNG."""
+    from . import host
+
+    host.write_png(path, rgb)

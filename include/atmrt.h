@@ -1,0 +1,237 @@
+/*
+ * atmrt.h -- C ABI of the B200-native panorama ray march (the drop-in boundary).
+ *
+ * The reference (fizyk20/atm-raytracer, Rust) has no FFI; its seam for this path is
+ *   trait Generator { fn generate(&self) -> Vec<Vec<ResultPixel>> }   generator/generators/mod.rs:82-84
+ *   FastGenerator::new(&Params, &Terrain, SystemTime)                 generator/generators/fast.rs:101-109
+ *   renderer::draw_image(&pixels, &params) -> ImageBuffer             renderer/mod.rs:385-414
+ * A thin host (`build.rs` + `extern "C"` block in Rust, or the C++ host in this repo) lowers
+ * `Params` to the flat PODs below and calls these entry points; see INTEGRATION.md for the
+ * reference-side binding.
+ *
+ * Conventions: every call returns 0 on success and a negative atmrt_status on failure; the
+ * message for the last failure is available through atmrt_last_error(). The caller owns every
+ * buffer it passes in; the library owns all device memory it allocates. One host thread per
+ * context. No exceptions cross the ABI. All angles are degrees and all lengths metres, exactly
+ * as in the reference's `Params` (generator/params.rs:496-505).
+ */
+#ifndef ATMRT_H
+#define ATMRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATMRT_ABI_VERSION 1
+#define ATMRT_MAX_ATM_FUNCTIONS 16 /* temperature functions in an atmosphere definition */
+#define ATMRT_MAX_OBJECTS 64       /* objects_close is a 64-bit mask per terrain sample  */
+#define ATMRT_MAX_STEP_POINTS 16   /* trace points produced by ONE march step (overflow is counted) */
+
+typedef enum atmrt_status {
+    ATMRT_OK = 0,
+    ATMRT_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+    ATMRT_ERR_CUDA = -2,        /* a CUDA runtime call failed               */
+    ATMRT_ERR_NO_DEVICE = -3,   /* no usable sm_100 device                  */
+    ATMRT_ERR_STATE = -4,       /* call order violated (e.g. render before set_terrain) */
+    ATMRT_ERR_IO = -5           /* host file IO (host helpers only)         */
+} atmrt_status;
+
+/* EarthModel (utils/earth_model/mod.rs:19-28). Only the models named by the north star are
+ * implemented on the device; the rest return ATMRT_ERR_INVALID. */
+typedef enum atmrt_earth_model {
+    ATMRT_EARTH_SPHERICAL = 0,     /* Spherical{radius}; SimpleSphere = radius 6371000 */
+    ATMRT_EARTH_FLAT_DISTORTED = 1 /* FlatDistorted (--flat)                           */
+} atmrt_earth_model;
+
+/* Altitude (generator/params.rs:17-30) */
+typedef enum atmrt_altitude_kind { ATMRT_ALT_ABSOLUTE = 0, ATMRT_ALT_RELATIVE = 1 } atmrt_altitude_kind;
+typedef struct atmrt_altitude {
+    int32_t kind; /* atmrt_altitude_kind */
+    int32_t _pad;
+    double value; /* metres ASL (absolute) or above terrain (relative) */
+} atmrt_altitude;
+
+/* Coloring (generator/params.rs:215-227) after ConfColoring::into_coloring (:229-267). */
+typedef enum atmrt_coloring_kind { ATMRT_COLORING_SIMPLE = 0, ATMRT_COLORING_SHADING = 1 } atmrt_coloring_kind;
+typedef enum atmrt_palette { ATMRT_PALETTE_LEGACY = 0, ATMRT_PALETTE_IMPROVED = 1 } atmrt_palette;
+
+/* AtmosphereDef of the external `atm-refraction` crate as the reference's YAML exposes it
+ * (README.md:281-323). Function 0 is `first_temperature_function` (valid from -infinity);
+ * function i>0 starts at fn_start_altitude[i]. Only `Linear{gradient}` functions are supported on
+ * the device in this round (Spline -> ATMRT_ERR_INVALID). */
+typedef struct atmrt_atmosphere_def {
+    double pressure_altitude; /* pressure fixed point */
+    double pressure;          /* Pa */
+    double temperature_altitude; /* temperature fixed point (required when all functions are Linear) */
+    double temperature;          /* K */
+    double humidity;             /* relative humidity 0..1, constant with altitude (default 0) */
+    int32_t n_functions;         /* >= 1 */
+    int32_t _pad;
+    double fn_start_altitude[ATMRT_MAX_ATM_FUNCTIONS]; /* [0] unused */
+    double fn_gradient[ATMRT_MAX_ATM_FUNCTIONS];       /* K per metre */
+} atmrt_atmosphere_def;
+
+/* Flat POD image of the reference's `Params` (generator/params.rs:496-505). */
+typedef struct atmrt_params {
+    /* view.position (params.rs:32-60) */
+    double latitude, longitude;
+    atmrt_altitude altitude;
+    /* view.frame (params.rs:144-162) */
+    double direction, tilt, fov, max_distance;
+    /* model / env (params.rs:512-528; earth_model/mod.rs:95-112) */
+    int32_t earth_model; /* atmrt_earth_model */
+    int32_t straight_rays;
+    double radius; /* Spherical only */
+    double wavelength; /* metres; default 530e-9 */
+    double simulation_step;
+    atmrt_atmosphere_def atmosphere;
+    /* scene */
+    double terrain_alpha;
+    /* view.coloring (already lowered: light_dir is the unit vector of params.rs:247-259) */
+    int32_t coloring; /* atmrt_coloring_kind */
+    int32_t palette;  /* atmrt_palette */
+    double water_level;
+    double ambient_light;
+    double light_dir[3];
+    double simple_max_distance; /* Coloring::Simple.max_distance = frame.max_distance */
+    /* view.fog_distance: Option<f64> */
+    int32_t fog_enabled;
+    int32_t _pad0;
+    double fog_distance;
+    /* output (params.rs:394-413); x0..x1 is the column block this context renders
+     * (x0 = 0, x1 = width for a single GPU). */
+    int32_t width, height;
+    int32_t x0, x1;
+} atmrt_params;
+
+/* One DTED tile decoded on the host (terrain/mod.rs:85-98; external crate dted 0.2).
+ * posts are [lon line][lat point], west->east, south->north, exactly as stored in the file. */
+typedef struct atmrt_tile_desc {
+    int32_t lat0, lon0;      /* HashMap key: (origin_lat as i16, origin_lon as i16), terrain/mod.rs:91-92 */
+    int32_t nlon, nlat;      /* longitude lines, latitude points */
+    double min_lat, min_lon; /* header origin in degrees */
+    double lat_interval, lon_interval; /* arc-seconds between posts (header value / 10) */
+} atmrt_tile_desc;
+
+/* Scene object after ConfObject::into_serializable_object (object/mod.rs:165-186) except that a
+ * Relative altitude is still resolved by the library (it needs Terrain::get_elev). */
+typedef enum atmrt_object_kind { ATMRT_OBJECT_FRUSTUM = 0, ATMRT_OBJECT_BILLBOARD = 1 } atmrt_object_kind;
+typedef struct atmrt_object {
+    int32_t kind; /* atmrt_object_kind */
+    int32_t texture_width, texture_height; /* billboard only; RGBA8 row-major, top row first */
+    int32_t _pad;
+    double latitude, longitude;
+    atmrt_altitude altitude;
+    double r1, r2;   /* frustum: Cylinder r1=r2, Cone r2=0 (object/mod.rs:41-54) */
+    double width;    /* billboard */
+    double height;   /* both */
+    double color[4]; /* r,g,b,a in 0..1 (frustum) */
+} atmrt_object;
+
+/* Per-pixel metadata: the first trace point of ResultPixel.trace_points
+ * (generators/mod.rs:14-30). All NaN when the ray hit nothing. */
+typedef struct atmrt_meta {
+    double lat, lon, elevation, distance;
+} atmrt_meta;
+
+/* One TracePoint (generators/mod.rs:21-30) + its resolved colour class. */
+typedef struct atmrt_trace_point {
+    double lat, lon, distance, elevation, path_length;
+    double normal[3];
+    double color[4]; /* Rgba(color); for Terrain(alpha): {0,0,0,alpha} */
+    int32_t is_terrain;
+    int32_t step; /* zip index k of the step that produced it */
+} atmrt_trace_point;
+
+typedef struct atmrt_stats {
+    uint64_t ray_steps;      /* sum over pixels of zip iterations consumed by get_single_pixel */
+    uint64_t trace_points;   /* total trace points produced */
+    uint64_t pixels_hit;     /* pixels with >= 1 trace point */
+    uint64_t step_overflows; /* steps that produced more than ATMRT_MAX_STEP_POINTS points */
+    uint64_t terrain_samples; /* W_local * N_t */
+    uint64_t path_steps;      /* sum over rows of stepper steps taken */
+    int32_t n_terrain;       /* N_t: terrain samples per column */
+    int32_t n_path_max;      /* longest path cache row (elements) */
+    float ms_terrain;        /* stage A device time */
+    float ms_paths;          /* stage B device time */
+    float ms_march;          /* stage C (+pyramids) device time */
+    float ms_total;          /* first launch -> last kernel end, device time */
+    int32_t kernel_launches; /* kernels launched by this render */
+    int32_t _pad;
+} atmrt_stats;
+
+typedef struct atmrt_ctx atmrt_ctx;
+
+/* ---- lifecycle -------------------------------------------------------------------------- */
+int atmrt_abi_version(void);
+/* sizeof() of the ABI structs in declaration order (altitude, atmosphere_def, params, tile_desc,
+ * object, meta, trace_point, stats); returns how many there are. For binding self-checks. */
+int atmrt_abi_sizes(size_t* out, int n);
+int atmrt_create(int device, atmrt_ctx** out);
+void atmrt_destroy(atmrt_ctx* ctx);
+const char* atmrt_last_error(const atmrt_ctx* ctx); /* ctx may be NULL: last create() error */
+
+/* ---- terrain (replaces Terrain::from_folder + lazy tile load, terrain/mod.rs:35-53,66-83) -- */
+/* Size of the device-side packed terrain (tile table + micro-tiled i16 posts). */
+int atmrt_terrain_packed_bytes(const atmrt_tile_desc* tiles, int ntiles, size_t* bytes);
+/* Upload host posts and retile them on the device into dev_dst (caller-owned device memory of
+ * atmrt_terrain_packed_bytes() bytes, e.g. a torch tensor that is then NCCL-broadcast). */
+int atmrt_pack_terrain(atmrt_ctx* ctx, const atmrt_tile_desc* tiles, int ntiles,
+                       const int16_t* const* posts, void* dev_dst);
+/* Use a packed terrain that already lives in device memory (not copied, not owned). */
+int atmrt_bind_terrain(atmrt_ctx* ctx, const atmrt_tile_desc* tiles, int ntiles, const void* dev_packed);
+/* Convenience: allocate + pack + bind (library-owned). */
+int atmrt_set_terrain(atmrt_ctx* ctx, const atmrt_tile_desc* tiles, int ntiles,
+                      const int16_t* const* posts);
+/* Terrain::get_elev (terrain/mod.rs:120-126) evaluated on the device for n points; missing
+ * coverage gives NaN (the reference's None). */
+int atmrt_get_elev(atmrt_ctx* ctx, const double* lat, const double* lon, int n, double* elev);
+/* Read back the decoded grid of one tile from the device layout ([lon][lat]); used to prove the
+ * tiled layout is a bit-exact permutation of the decoded DTED posts. */
+int atmrt_read_tile(atmrt_ctx* ctx, int tile_index, int16_t* posts);
+
+/* ---- scene ------------------------------------------------------------------------------ */
+int atmrt_set_params(atmrt_ctx* ctx, const atmrt_params* params);
+int atmrt_set_objects(atmrt_ctx* ctx, const atmrt_object* objects, int nobjects,
+                      const uint8_t* const* rgba_textures);
+
+/* ---- render (replaces FastGenerator::generate + renderer::draw_image) -------------------- */
+/* Host buffers (any may be NULL): rgb[H][x1-x0][3], meta[H][x1-x0], steps[H][x1-x0] = zip
+ * iterations consumed per pixel. Copies are part of the call. */
+int atmrt_render(atmrt_ctx* ctx, uint8_t* rgb, atmrt_meta* meta, int32_t* steps, atmrt_stats* stats);
+/* Same, writing to caller-owned DEVICE buffers on `stream` (a cudaStream_t, may be NULL);
+ * asynchronous unless stats != NULL (stats requires the stage timings, so it synchronises). */
+int atmrt_render_device(atmrt_ctx* ctx, void* rgb_dev, void* meta_dev, void* steps_dev,
+                        atmrt_stats* stats, void* stream);
+/* Full trace-point lists (ResultPixel.trace_points) for small images: points[H][x1-x0][max_points],
+ * counts[H][x1-x0] (true count, may exceed max_points). Host buffers. */
+int atmrt_render_trace(atmrt_ctx* ctx, atmrt_trace_point* points, int32_t* counts, int max_points);
+/* 0 = hierarchical min/max march (default), 1 = brute-force march that visits every step like the
+ * reference loop (validation + FP64 roofline mode). */
+int atmrt_set_march_mode(atmrt_ctx* ctx, int mode);
+/* Tuning hook for the ray-path stage: image rows integrated per warp (1..32, default 32). */
+int atmrt_set_rows_per_warp(atmrt_ctx* ctx, int rows);
+
+/* ---- probes (the reference's TSV dumpers: elev_profile.rs:43-64, ray_path.rs:65-103,
+ *      atm_printer.rs:35-46) ------------------------------------------------------------ */
+/* Stage-A cache of local column x (gen_terrain_cache, utils.rs:176-199): n = N_t entries. */
+int atmrt_get_terrain_profile(atmrt_ctx* ctx, int x, int capacity, double* lat, double* lon,
+                              double* elev, double* normal /*[n][3]*/, uint64_t* objects_close, int* n);
+/* Stage-B cache of row y (gen_path_cache, utils.rs:136-174). */
+int atmrt_get_path(atmrt_ctx* ctx, int y, int capacity, double* dist, double* elev,
+                   double* path_length, int* n);
+/* Atmosphere::temperature / pressure and Environment::n at n altitudes, on the device. */
+int atmrt_atmosphere_probe(atmrt_ctx* ctx, const double* h, int n, double* temperature,
+                           double* pressure, double* refractive_index);
+/* Observer altitude after Altitude::abs (params.rs:23-30). */
+int atmrt_observer_altitude(atmrt_ctx* ctx, double* alt);
+/* FP64 FMA throughput micro-benchmark (roofline denominator): returns GFLOP/s (2 flop per FMA). */
+int atmrt_fp64_peak(atmrt_ctx* ctx, double* gflops, double* dadd_ginstr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATMRT_H */
