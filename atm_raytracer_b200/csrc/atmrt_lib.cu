@@ -155,7 +155,7 @@ int make_layout(atmrt_ctx* ctx, const atmrt_tile_desc* descs, int n, TerrainLayo
 }
 
 // ---- atmosphere lowering (Atmosphere::from_def; host libm, same as the reference's CPU lowering) --
-constexpr double ATM_G = 9.80665, ATM_M = 0.0289644, ATM_R = 8.3144598;
+constexpr double ATM_G = 9.80665, ATM_M = 0.0289644, ATM_R = 8.31432;  // R* of US Standard Atmosphere 1976
 
 double host_layer_temperature(const DevAtmLayer& l, double h) { return l.t_ref + l.gradient * (h - l.h_ref); }
 double host_layer_pressure(const DevAtmLayer& l, double h) {

@@ -273,7 +273,7 @@ double altitude_abs(const atmrt_altitude& a, const Terrain& t, double lat, doubl
 // ------------------------------------------------------------------------------------------
 constexpr double ATM_G = 9.80665;      // m/s^2
 constexpr double ATM_M = 0.0289644;    // kg/mol
-constexpr double ATM_R = 8.3144598;    // J/(mol K)  [recalled, uncertain: see header]
+constexpr double ATM_R = 8.31432;      // J/(mol K): R* of the US Standard Atmosphere 1976, which reproduces its published p(h) table
 
 struct AtmLayer {
     double start;   // lower boundary (-inf for layer 0)
