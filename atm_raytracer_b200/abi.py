@@ -136,6 +136,11 @@ class Stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("_")}
 
 
+class StageMs(C.Structure):
+    _fields_ = [("ms_terrain", C.c_double), ("ms_paths", C.c_double), ("ms_march", C.c_double), ("ms_total", C.c_double),
+                ("renders", C.c_int32), ("_pad", C.c_int32)]
+
+
 def us_76() -> AtmosphereDef:
     """``AtmosphereDef::us_76()`` of the external atm-refraction crate (params.rs:453): US Standard
     Atmosphere 1976 temperature layers up to 84.852 km, sea-level fixed points 288.15 K / 101325 Pa."""

@@ -32,7 +32,14 @@ struct atmrt_ctx {
     std::string err;
     cudaStream_t s_a = nullptr, s_b = nullptr, s_main = nullptr;
     cudaEvent_t ev_prep = nullptr, ev_a = nullptr, ev_b = nullptr;
-    cudaEvent_t t_a0 = nullptr, t_a1 = nullptr, t_b0 = nullptr, t_b1 = nullptr, t_c0 = nullptr, t_c1 = nullptr, t_0 = nullptr, t_1 = nullptr;
+    // Stage timing: one set of events per render since the last harvest (atmrt_stage_times), so a
+    // whole timed region of asynchronous renders can be averaged without synchronising inside it.
+    struct StageEvents {
+        cudaEvent_t a0, a1, b0, b1, c0, c1, t0, t1;
+    };
+    std::vector<StageEvents> ring;
+    size_t ring_used = 0;
+    cudaEvent_t t_0 = nullptr, t_1 = nullptr;  // fp64 micro-benchmark
     int num_sms = 148;
 
     // terrain
@@ -398,12 +405,31 @@ struct RenderTargets {
 };
 
 // Launch the whole render on (s_a || s_b) -> main. Asynchronous.
-int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main, bool timed) {
+int next_stage_events(atmrt_ctx* ctx, atmrt_ctx::StageEvents** out) {
+    if (ctx->ring_used == ctx->ring.size()) {
+        if (ctx->ring.size() >= 4096) {  // nobody is harvesting: recycle
+            ctx->ring_used = 0;
+        } else {
+            atmrt_ctx::StageEvents e{};
+            cudaEvent_t* evs[] = {&e.a0, &e.a1, &e.b0, &e.b1, &e.c0, &e.c1, &e.t0, &e.t1};
+            for (cudaEvent_t* ev : evs) CUDA_TRY(ctx, cudaEventCreate(ev));
+            ctx->ring.push_back(e);
+        }
+    }
+    *out = &ctx->ring[ctx->ring_used++];
+    return 0;
+}
+
+int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main) {
     const DevScene& S = ctx->scene;
     const DevBuffers& B = ctx->buf;
     const int wl = S.x1 - S.x0, h = S.height;
     ctx->launches = 0;
-    if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->t_0, main));
+    atmrt_ctx::StageEvents* E = nullptr;
+    int erc = next_stage_events(ctx, &E);
+    if (erc) return erc;
+    const bool timed = true;
+    CUDA_TRY(ctx, cudaEventRecord(E->t0, main));
     int rc = upload_scene_inputs(ctx, main);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 8 * CNT_COUNT, main));
@@ -414,7 +440,7 @@ int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main, bo
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_b, ctx->ev_prep, 0));
 
     // Stage A on s_a
-    if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->t_a0, ctx->s_a));
+    if (timed) CUDA_TRY(ctx, cudaEventRecord(E->a0, ctx->s_a));
     k_column_setup<<<(wl + 127) / 128, 128, 0, ctx->s_a>>>(S, B);
     k_terrain_profile<<<dim3((S.n_t + 127) / 128, wl), 128, 0, ctx->s_a>>>(S, ctx->terrain, B);
     {
@@ -424,11 +450,11 @@ int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main, bo
                                                                              B.close1, B.close2);
     }
     ctx->launches += 3;
-    if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->t_a1, ctx->s_a));
+    if (timed) CUDA_TRY(ctx, cudaEventRecord(E->a1, ctx->s_a));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->s_a));
 
     // Stage B on s_b
-    if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->t_b0, ctx->s_b));
+    if (timed) CUDA_TRY(ctx, cudaEventRecord(E->b0, ctx->s_b));
     {
         int rpw = ctx->rows_per_warp;
         k_ray_paths<<<(h + rpw - 1) / rpw, 32, 0, ctx->s_b>>>(S, B, rpw);
@@ -437,13 +463,13 @@ int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main, bo
                                                                              S.n2, B.rmin1, B.rmax1, B.rmin2, B.rmax2, nullptr, nullptr);
     }
     ctx->launches += 2;
-    if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->t_b1, ctx->s_b));
+    if (timed) CUDA_TRY(ctx, cudaEventRecord(E->b1, ctx->s_b));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->s_b));
 
     // Stage C on main
     CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_a, 0));
     CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_b, 0));
-    if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->t_c0, main));
+    if (timed) CUDA_TRY(ctx, cudaEventRecord(E->c0, main));
     MarchOut O{rt.rgb, rt.meta, rt.steps, rt.points, rt.counts, rt.max_points};
     const int blocks = ctx->num_sms * 8;
     const bool trace = rt.points != nullptr || rt.counts != nullptr;
@@ -460,8 +486,8 @@ int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main, bo
     }
     ctx->launches++;
     if (timed) {
-        CUDA_TRY(ctx, cudaEventRecord(ctx->t_c1, main));
-        CUDA_TRY(ctx, cudaEventRecord(ctx->t_1, main));
+        CUDA_TRY(ctx, cudaEventRecord(E->c1, main));
+        CUDA_TRY(ctx, cudaEventRecord(E->t1, main));
     }
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->rendered = true;
@@ -486,10 +512,13 @@ int collect_stats(atmrt_ctx* ctx, atmrt_stats* stats) {
     int mx = 0;
     for (int v : pn) mx = std::max(mx, v);
     stats->n_path_max = mx;
-    cudaEventElapsedTime(&stats->ms_terrain, ctx->t_a0, ctx->t_a1);
-    cudaEventElapsedTime(&stats->ms_paths, ctx->t_b0, ctx->t_b1);
-    cudaEventElapsedTime(&stats->ms_march, ctx->t_c0, ctx->t_c1);
-    cudaEventElapsedTime(&stats->ms_total, ctx->t_0, ctx->t_1);
+    if (ctx->ring_used > 0) {
+        const atmrt_ctx::StageEvents& E = ctx->ring[ctx->ring_used - 1];
+        cudaEventElapsedTime(&stats->ms_terrain, E.a0, E.a1);
+        cudaEventElapsedTime(&stats->ms_paths, E.b0, E.b1);
+        cudaEventElapsedTime(&stats->ms_march, E.c0, E.c1);
+        cudaEventElapsedTime(&stats->ms_total, E.t0, E.t1);
+    }
     stats->kernel_launches = ctx->launches;
     return 0;
 }
@@ -506,7 +535,8 @@ int atmrt_abi_version(void) { return ATMRT_ABI_VERSION; }
 // sizes of the ABI structs, for the ctypes mirror's self-check
 int atmrt_abi_sizes(size_t* out, int n) {
     const size_t v[] = {sizeof(atmrt_altitude), sizeof(atmrt_atmosphere_def), sizeof(atmrt_params), sizeof(atmrt_tile_desc),
-                        sizeof(atmrt_object),   sizeof(atmrt_meta),           sizeof(atmrt_trace_point), sizeof(atmrt_stats)};
+                        sizeof(atmrt_object),   sizeof(atmrt_meta),           sizeof(atmrt_trace_point), sizeof(atmrt_stats),
+                        sizeof(atmrt_stage_ms)};
     const int m = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < n && i < m; ++i) out[i] = v[i];
     return m;
@@ -538,7 +568,7 @@ int atmrt_create(int device, atmrt_ctx** out) {
               cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking) == cudaSuccess;
     cudaEvent_t* evs[] = {&ctx->ev_prep, &ctx->ev_a, &ctx->ev_b};
     for (cudaEvent_t* ev : evs) ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
-    cudaEvent_t* tevs[] = {&ctx->t_a0, &ctx->t_a1, &ctx->t_b0, &ctx->t_b1, &ctx->t_c0, &ctx->t_c1, &ctx->t_0, &ctx->t_1};
+    cudaEvent_t* tevs[] = {&ctx->t_0, &ctx->t_1};
     for (cudaEvent_t* ev : tevs) ok = ok && cudaEventCreate(ev) == cudaSuccess;
     if (!ok) {
         delete ctx;
@@ -560,9 +590,14 @@ void atmrt_destroy(atmrt_ctx* ctx) {
     for (DevBuf* b : bufs) release(*b);
     for (DevBuf& b : ctx->textures) release(b);
     if (ctx->terrain_owned) cudaFree(ctx->terrain_owned);
-    cudaEvent_t evs[] = {ctx->ev_prep, ctx->ev_a, ctx->ev_b, ctx->t_a0, ctx->t_a1, ctx->t_b0, ctx->t_b1, ctx->t_c0, ctx->t_c1, ctx->t_0, ctx->t_1};
+    cudaEvent_t evs[] = {ctx->ev_prep, ctx->ev_a, ctx->ev_b, ctx->t_0, ctx->t_1};
     for (cudaEvent_t ev : evs)
         if (ev) cudaEventDestroy(ev);
+    for (atmrt_ctx::StageEvents& e : ctx->ring) {
+        cudaEvent_t all[] = {e.a0, e.a1, e.b0, e.b1, e.c0, e.c1, e.t0, e.t1};
+        for (cudaEvent_t ev : all)
+            if (ev) cudaEventDestroy(ev);
+    }
     if (ctx->s_a) cudaStreamDestroy(ctx->s_a);
     if (ctx->s_b) cudaStreamDestroy(ctx->s_b);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
@@ -750,7 +785,7 @@ int atmrt_render_device(atmrt_ctx* ctx, void* rgb_dev, void* meta_dev, void* ste
     cudaStream_t main = stream ? (cudaStream_t)stream : ctx->s_main;
     RenderTargets rt;
     rt.rgb = (unsigned char*)rgb_dev, rt.meta = (atmrt_meta*)meta_dev, rt.steps = (int*)steps_dev;
-    rc = launch_render(ctx, rt, main, stats != nullptr);
+    rc = launch_render(ctx, rt, main);
     if (rc) return rc;
     if (stats) {
         CUDA_TRY(ctx, cudaStreamSynchronize(main));
@@ -774,7 +809,7 @@ int atmrt_render(atmrt_ctx* ctx, uint8_t* rgb, atmrt_meta* meta, int32_t* steps,
     rt.meta = meta ? (atmrt_meta*)ctx->d_meta.p : nullptr;
     rt.steps = steps ? (int*)ctx->d_steps.p : nullptr;
     cudaStream_t main = ctx->s_main;
-    rc = launch_render(ctx, rt, main, true);
+    rc = launch_render(ctx, rt, main);
     if (rc) return rc;
     if (rgb) CUDA_TRY(ctx, cudaMemcpyAsync(rgb, ctx->d_rgb.p, npix * 3, cudaMemcpyDeviceToHost, main));
     if (meta) CUDA_TRY(ctx, cudaMemcpyAsync(meta, ctx->d_meta.p, npix * sizeof(atmrt_meta), cudaMemcpyDeviceToHost, main));
@@ -798,7 +833,7 @@ int atmrt_render_trace(atmrt_ctx* ctx, atmrt_trace_point* points, int32_t* count
     rt.max_points = max_points;
     cudaStream_t main = ctx->s_main;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_points.p, 0, npix * sizeof(atmrt_trace_point) * (size_t)std::max(max_points, 1), main));
-    rc = launch_render(ctx, rt, main, false);
+    rc = launch_render(ctx, rt, main);
     if (rc) return rc;
     if (max_points > 0)
         CUDA_TRY(ctx, cudaMemcpyAsync(points, ctx->d_points.p, npix * sizeof(atmrt_trace_point) * (size_t)max_points, cudaMemcpyDeviceToHost, main));
@@ -855,6 +890,33 @@ int atmrt_get_path(atmrt_ctx* ctx, int y, int capacity, double* dist, double* el
     if (dist) CUDA_TRY(ctx, cudaMemcpy(dist, ctx->buf.p_dist + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
     if (elev) CUDA_TRY(ctx, cudaMemcpy(elev, ctx->buf.p_elev + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
     if (path_length) CUDA_TRY(ctx, cudaMemcpy(path_length, ctx->buf.p_len + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int atmrt_stage_times(atmrt_ctx* ctx, atmrt_stage_ms* out) {
+    if (!ctx || !out) return fail(ctx, ATMRT_ERR_INVALID, "stage_times: NULL argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    memset(out, 0, sizeof(*out));
+    double a = 0, b = 0, c = 0, t = 0;
+    for (size_t i = 0; i < ctx->ring_used; ++i) {
+        const atmrt_ctx::StageEvents& E = ctx->ring[i];
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, E.a0, E.a1));
+        a += ms;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, E.b0, E.b1));
+        b += ms;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, E.c0, E.c1));
+        c += ms;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, E.t0, E.t1));
+        t += ms;
+    }
+    out->renders = (int32_t)ctx->ring_used;
+    if (ctx->ring_used > 0) {
+        const double n = (double)ctx->ring_used;
+        out->ms_terrain = a / n, out->ms_paths = b / n, out->ms_march = c / n, out->ms_total = t / n;
+    }
+    ctx->ring_used = 0;
     return 0;
 }
 

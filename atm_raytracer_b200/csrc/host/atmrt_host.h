@@ -18,8 +18,6 @@ int atmrt_host_read_dted(const char* path, atmrt_tile_desc* desc, int16_t* posts
 /* RGB8 or RGBA8 PNG writer/reader on zlib (channels = 3 or 4). */
 int atmrt_host_write_png(const char* path, const uint8_t* pixels, int width, int height, int channels);
 int atmrt_host_read_png(const char* path, uint8_t* rgba, size_t capacity, int* width, int* height);
-/* The `gen` subcommand: argv as after `atm-raytracer gen`. Returns a process exit code. */
-int atmrt_host_gen(int argc, const char* const* argv);
 const char* atmrt_host_last_error(void);
 
 #ifdef __cplusplus

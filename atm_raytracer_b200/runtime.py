@@ -48,6 +48,7 @@ def _load():
         "atmrt_set_objects": (C.c_int, [vp, P(abi.Object), C.c_int, P(vp)]),
         "atmrt_render": (C.c_int, [vp, vp, vp, vp, P(abi.Stats)]),
         "atmrt_render_device": (C.c_int, [vp, vp, vp, vp, P(abi.Stats), vp]),
+        "atmrt_stage_times": (C.c_int, [vp, P(abi.StageMs)]),
         "atmrt_render_trace": (C.c_int, [vp, vp, vp, C.c_int]),
         "atmrt_set_march_mode": (C.c_int, [vp, C.c_int]),
         "atmrt_set_rows_per_warp": (C.c_int, [vp, C.c_int]),
@@ -126,12 +127,16 @@ class Terrain:
         ptrs = (C.c_void_p * max(n, 1))()
         for i, (d, posts) in enumerate(self.tiles):
             descs[i] = d
-            ptrs[i] = posts.ctypes.data
+            ptrs[i] = None if posts is None else posts.ctypes.data  # None: descriptor-only terrain (non-root ranks)
         return descs, ptrs, n
+
+    def descriptors_only(self):
+        """The same tile table without the posts (what a non-root rank needs to bind a broadcast copy)."""
+        return Terrain([(d, None) for d, _ in self.tiles])
 
     @property
     def bytes(self):
-        return sum(p.nbytes for _, p in self.tiles)
+        return sum(int(d.nlon) * int(d.nlat) * 2 for d, _ in self.tiles)
 
 
 class Context:
@@ -251,6 +256,12 @@ class Context:
                                     C.byref(st) if st is not None else None, C.c_void_p(stream or None))
         )
         return st.as_dict() if st is not None else None
+
+    def stage_times(self):
+        """Average device time per stage over the renders since the last call (synchronises)."""
+        st = abi.StageMs()
+        self._check(lib.atmrt_stage_times(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in abi.StageMs._fields_ if not k.startswith("_")}
 
     def render_trace(self, max_points=8):
         h, w = self.shape()

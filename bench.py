@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- panorama pixels/s (and ray-steps/s) of the B200 ray march, one process per GPU.
+
+    python bench.py --gpus N --steps K --warmup W [--workload c5] [--impl reference]
+
+A "step" is one full render of the workload's panorama (stage A terrain profiles, stage B ray paths,
+stage C march + colouring + metadata) with the packed terrain already resident in HBM. With N > 1
+(torchrun) the panorama is sharded by contiguous column blocks, one block per rank; the total work is
+fixed, so scaling is "strong". `value` = W*H / (max-over-ranks device time per step).
+`e2e` is the same metric through the public host API with HOST buffers: every step uploads the decoded
+DTED tiles from pinned memory (rank 0), broadcasts the packed terrain (NCCL), renders, gathers the
+shards to rank 0 and reads RGB + per-pixel metadata back to pinned host memory.
+
+`--impl reference` times the CPU restatement of the reference (oracle/, OpenMP on all host cores): the
+reference itself is Rust and cannot be built in this image. Each step is a bounded
+sample: every S-th column and row of the same panorama; the three stages are extrapolated separately
+(terrain x S, paths x S, pixels x S^2) to the full job, which is what pixels/s is quoted on.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "panorama pixels/s"
+# Algorithmic work per unit (DESIGN.md "Kernels and rooflines"): FP64 instructions counted from the
+# reference arithmetic each stage restates, not from the SASS.
+STAGE_UNITS = {
+    "terrain": ("k_terrain_profile", "terrain samples"),
+    "paths": ("k_ray_paths", "path steps"),
+    "march": ("k_march", "ray steps"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c5", choices=["c1", "c2", "c3_flat", "c3_sph", "c4", "c5"])
+    ap.add_argument("--scale", type=float, default=1.0, help="image scale (1.0 = the BASELINE size; anything else is a dry run)")
+    ap.add_argument("--march-mode", type=int, default=0, help="0 hierarchical (product default), 1 brute force (every step)")
+    ap.add_argument("--cpu-stride", type=int, default=0, help="column/row stride of the bounded CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def build_workload(name, scale, with_posts):
+    from atm_raytracer_b200 import config, runtime, scenes
+
+    cfg, grid = scenes.make_scene(name, scale=scale)
+    params = config.into_params(cfg)
+    objects, textures = config.lower_objects(cfg)
+    lat0, lon0, nlat, nlon = grid
+    keys = [(lat0 + i, lon0 + j) for i in range(nlat) for j in range(nlon)]
+    if with_posts:
+        from atm_raytracer_b200 import synth
+
+        with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+            posts = list(ex.map(lambda k: synth.make_tile(k[0], k[1], 1), keys))
+        terrain = runtime.Terrain.from_arrays([(k[0], k[1], p) for k, p in zip(keys, posts)])
+    else:
+        shape = np.empty((1201, 1201), np.int16)
+        terrain = runtime.Terrain([(runtime.Terrain.desc(k[0], k[1], shape), None) for k in keys])
+    return cfg, params, terrain, objects, textures
+
+
+def describe(name, params, terrain, extra=None):
+    d = {
+        "workload": f"{name}: {params.width}x{params.height} fov {params.fov:g} deg, "
+                    f"{'straight' if params.straight_rays else 'refracted (US-76)'} rays, "
+                    f"{'FlatDistorted' if params.earth_model == 1 else 'Spherical R=%g km' % (params.radius / 1e3)}, "
+                    f"{len(terrain.tiles)} synthetic DTED L1 tiles, max_distance {params.max_distance / 1e3:g} km, step {params.simulation_step:g} m",
+        "generator": "Fast",
+        "l2_policy": "inputs larger than L2 (profile caches >> 126 MB are rewritten and re-read every step)",
+    }
+    d.update(extra or {})
+    return d
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline (oracle; rank 0 only)
+# ---------------------------------------------------------------------------------------------
+def cpu_sample(params, terrain, objects, textures, stride):
+    """One bounded CPU sample; returns (pixels/s of the full job, ray-steps/s, description, timing)."""
+    import oracle
+
+    threads = oracle.num_threads()
+    r = oracle.render(params, terrain.tiles, objects, textures, stride_x=stride, stride_y=stride, meta=True, steps=False)
+    tm = r["timing"]
+    # the reference's three stages scale differently with the image: extrapolate each one
+    t_full = tm["s_terrain"] * stride + tm["s_paths"] * stride + tm["s_pixels"] * stride * stride
+    wl = params.x1 - params.x0
+    pixels = wl * params.height
+    steps_full = r["stats"]["ray_steps"] * stride * stride
+    desc = (f"every {stride}th column and row ({r['rgb'].shape[1]}x{r['rgb'].shape[0]} px), all three stages; "
+            f"stage times extrapolated to the full image (terrain x{stride}, paths x{stride}, pixels x{stride * stride}); "
+            f"sample took {tm['s_total']:.2f} s")
+    return pixels / t_full, steps_full / t_full, desc, tm, threads
+
+
+def auto_stride(params):
+    # aim at ~10-30 s of CPU work: stage A dominates the sample (~2.5 us per terrain sample per core)
+    n_t = params.max_distance / params.simulation_step
+    cores = os.cpu_count() or 1
+    for s in (1, 2, 4, 8, 16, 32, 64, 128):
+        cols = (params.x1 - params.x0) / s
+        est = cols * n_t * 2.5e-6 / cores + (cols * params.height / s) * n_t * 2.0e-9 / cores
+        if est < 12.0:
+            return s
+    return 128
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, params, terrain, objects, textures = build_workload(args.workload, args.scale, True)
+    stride = args.cpu_stride or auto_stride(params)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_sample(params, terrain, objects, textures, stride * 2)
+    vals, steps_rate, desc, threads = [], [], "", 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, sr, desc, tm, threads = cpu_sample(params, terrain, objects, textures, stride)
+        vals.append(v)
+        steps_rate.append(sr)
+    wall = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pixels/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * params.width * params.height / value, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": describe(args.workload, params, terrain),
+        "ray_steps_per_s": float(np.mean(steps_rate)),
+        "cpu_baseline": {"value": value, "unit": "pixels/s", "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of the reference (C++/OpenMP oracle); the Rust reference cannot be built here. "
+                "ms_per_step is the extrapolated full-image time; wall time of the sampled steps was %.1f s" % wall,
+    }
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from atm_raytracer_b200 import parallel, runtime
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg, params, terrain, objects, textures = build_workload(args.workload, args.scale, rank == 0)
+    my = parallel.shard_params(params, rank, world)
+    wl, H, W = my.x1 - my.x0, params.height, params.width
+
+    ctx = runtime.Context(local)
+    ctx.set_march_mode(args.march_mode)
+    # terrain: rank 0 uploads + retiles, everyone receives the packed copy over NCCL (once, untimed)
+    nbytes = ctx.packed_bytes(terrain)
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        ctx.pack_terrain(terrain, packed.data_ptr())
+    parallel.broadcast_terrain(packed)
+    ctx.bind_terrain(terrain if rank == 0 else terrain.descriptors_only(), packed.data_ptr())
+    ctx.set_params(my)
+    ctx.set_objects(objects, textures)
+
+    rgb = torch.empty((H, wl, 3), dtype=torch.uint8, device=dev)
+    meta = torch.empty((H, wl, 4), dtype=torch.float64, device=dev)
+    # a dedicated (non-default) stream: the library forks its stage streams from it and joins back,
+    # so CUDA events recorded on it bracket every kernel of a render
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+
+    def step():
+        ctx.render_device(rgb.data_ptr(), meta.data_ptr(), 0, stream)
+
+    for _ in range(max(args.warmup, 0)):
+        step()
+    barrier()
+    ctx.stage_times()  # drop the warm-up renders from the stage averages
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    stage = ctx.stage_times()
+    t = torch.tensor([ms, stage["ms_terrain"], stage["ms_paths"], stage["ms_march"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_a, ms_b, ms_c = t.tolist()
+
+    # one extra (untimed) render for the counters
+    st = ctx.render_device(rgb.data_ptr(), meta.data_ptr(), 0, stream, want_stats=True)
+    st = parallel.reduce_stats(st, dev)
+    launches_per_step = st["kernel_launches"]
+    fp = ctx.fp64_peak() if rank == 0 else None
+
+    # ---- e2e: host buffers in, host buffers out ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_rgb = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
+        host_meta = torch.empty((H, W, 4), dtype=torch.float64).pin_memory() if rank == 0 else None
+        if rank == 0:  # decoded tiles staged in pinned memory, as a host that just decoded them would hold them
+            pinned = [torch.from_numpy(p).pin_memory() for _, p in terrain.tiles]
+            terrain_pinned = runtime.Terrain([(d, t_.numpy()) for (d, _), t_ in zip(terrain.tiles, pinned)])
+
+        def e2e_step():
+            if rank == 0:
+                ctx.pack_terrain(terrain_pinned, packed.data_ptr())  # H2D + retile
+            parallel.broadcast_terrain(packed)
+            ctx.render_device(rgb.data_ptr(), meta.data_ptr(), 0, stream)
+            full_rgb = parallel.gather_columns(rgb, W)
+            full_meta = parallel.gather_columns(meta, W)
+            if rank == 0:
+                host_rgb.copy_(full_rgb, non_blocking=True)
+                host_meta.copy_(full_meta, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_steps = max(1, min(args.steps, 3))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = tt.item()
+        e2e = {"value": W * H / dt, "unit": "pixels/s", "h2d_bytes_per_step": int(terrain.bytes),
+               "d2h_bytes_per_step": int(W * H * 3 + W * H * 32), "ms_per_step": dt * 1e3, "steps": e2e_steps,
+               "api": "Context.pack_terrain + render_device + gather_columns + D2H of rgb and per-pixel metadata"}
+        if rank == 0:
+            assert host_rgb.numpy().any()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------
+    n_t = st["n_terrain"]
+    units = {"terrain": wl * n_t, "paths": st["path_steps"] / world if world > 1 else st["path_steps"],
+             "march": st["ray_steps"] / world}
+    stage_ms = {"terrain": ms_a, "paths": ms_b, "march": ms_c}
+    dom = max(stage_ms, key=stage_ms.get)
+    roof = roofline(dom, stage_ms[dom], units[dom], params, fp, args)
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        stride = args.cpu_stride or auto_stride(params)
+        v, sr, desc, tm, threads = cpu_sample(params, terrain, objects, textures, stride)
+        cpu = {"value": v, "unit": "pixels/s", "cores": threads, "kind": "port", "sample": desc, "ray_steps_per_s": sr,
+               "stage_s_in_sample": {k: tm[k] for k in ("s_terrain", "s_paths", "s_pixels")}}
+
+    out = {
+        "metric": METRIC, "value": W * H / (ms * 1e-3), "unit": "pixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": describe(args.workload, params, terrain, {"parallelism": f"column blocks x{world}", "march_mode": "hierarchical" if args.march_mode == 0 else "brute force"}),
+        "ray_steps_per_s": st["ray_steps"] / (ms * 1e-3),
+        "ray_steps_per_step": st["ray_steps"],
+        "stage_ms": {"terrain_profile": ms_a, "ray_paths": ms_b, "march": ms_c, "note": "terrain and paths overlap on two streams; max over ranks"},
+        "clocks": clocks.summary(),
+        "e2e": e2e,
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "fp64_peak_measured": fp,
+        "pixels_hit": st["pixels_hit"], "step_overflows": st["step_overflows"],
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline(stage, ms, units, params, fp, args):
+    """FP64-pipe roofline of the dominant kernel. `achieved` = algorithmic FP64 instructions per launch
+    (per-unit figure from DESIGN.md x units per launch) / measured launch duration; `peak` = the DFMA
+    issue rate measured live by atmrt_fp64_peak (MEASURED_PEAKS.json has no FP64 figure)."""
+    per_unit = fp64_instr_per_unit(stage, params)
+    peak = (fp or {}).get("dfma_gflops", 0.0) / 2.0  # G FP64 instr/s
+    achieved = per_unit * units / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    hbm_peak = 6548.2
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    bytes_unit = hbm_bytes_per_unit(stage, params)
+    return {
+        "kernel": STAGE_UNITS[stage][0], "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "G FP64 instr/s",
+        "frac": achieved / peak if peak else None, "traffic": None,
+        "units_per_launch": units, "unit_name": STAGE_UNITS[stage][1], "fp64_instr_per_unit": per_unit, "launch_ms": ms,
+        "peak_source": "measured live (atmrt_fp64_peak: 8 independent DFMA chains/thread); MEASURED_PEAKS.json has no FP64 entry",
+        "hbm": {"algorithmic_bytes_per_unit": bytes_unit, "achieved_gbs": bytes_unit * units / (ms * 1e-3) / 1e9 if ms > 0 else 0.0,
+                "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs"},
+    }
+
+
+def fp64_instr_per_unit(stage, params):
+    # DESIGN.md, "Kernels and rooflines": arithmetic the reference performs per unit, transcendentals
+    # costed at the instruction count of CUDA's f64 libm paths.
+    if stage == "march":
+        return 3.0  # 1 DADD (diff), 1 DMUL (product), 1 DSETP (sign test) per ray step (utils.rs:220-222)
+    if stage == "paths":
+        return 25.0 if params.straight_rays else 2600.0
+    return 1500.0 if params.earth_model == 0 else 700.0
+
+
+def hbm_bytes_per_unit(stage, params):
+    if stage == "march":
+        return 8.0 * (1.0 / params.height + 1.0 / max(1, params.x1 - params.x0))
+    if stage == "paths":
+        return 24.0
+    return 48.0 + 40.0  # six f64 outputs + five bilinear taps of 4 i16 posts
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

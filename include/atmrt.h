@@ -163,12 +163,22 @@ typedef struct atmrt_stats {
     int32_t _pad;
 } atmrt_stats;
 
+/* Device time per stage, averaged over the renders since the previous atmrt_stage_times() call. */
+typedef struct atmrt_stage_ms {
+    double ms_terrain; /* stage A kernels (column setup, terrain profile, terrain pyramid), on their stream */
+    double ms_paths;   /* stage B kernels (ray paths, path pyramid), on their stream (overlaps stage A) */
+    double ms_march;   /* stage C kernel */
+    double ms_total;   /* first launch -> last kernel end */
+    int32_t renders;   /* how many renders were averaged */
+    int32_t _pad;
+} atmrt_stage_ms;
+
 typedef struct atmrt_ctx atmrt_ctx;
 
 /* ---- lifecycle -------------------------------------------------------------------------- */
 int atmrt_abi_version(void);
 /* sizeof() of the ABI structs in declaration order (altitude, atmosphere_def, params, tile_desc,
- * object, meta, trace_point, stats); returns how many there are. For binding self-checks. */
+ * object, meta, trace_point, stats, stage_ms); returns how many there are. For binding self-checks. */
 int atmrt_abi_sizes(size_t* out, int n);
 int atmrt_create(int device, atmrt_ctx** out);
 void atmrt_destroy(atmrt_ctx* ctx);
@@ -206,6 +216,9 @@ int atmrt_render(atmrt_ctx* ctx, uint8_t* rgb, atmrt_meta* meta, int32_t* steps,
  * asynchronous unless stats != NULL (stats requires the stage timings, so it synchronises). */
 int atmrt_render_device(atmrt_ctx* ctx, void* rgb_dev, void* meta_dev, void* steps_dev,
                         atmrt_stats* stats, void* stream);
+/* Harvest the per-stage CUDA-event timings of every render issued since the last call (the renders
+ * themselves stay asynchronous); synchronises the device. */
+int atmrt_stage_times(atmrt_ctx* ctx, atmrt_stage_ms* out);
 /* Full trace-point lists (ResultPixel.trace_points) for small images: points[H][x1-x0][max_points],
  * counts[H][x1-x0] (true count, may exceed max_points). Host buffers. */
 int atmrt_render_trace(atmrt_ctx* ctx, atmrt_trace_point* points, int32_t* counts, int max_points);

@@ -1,0 +1,323 @@
+"""GPU parity tests: the CUDA path (through the C ABI of include/atmrt.h) against the CPU oracle on
+the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): decoded elevation grids bit-exact; metadata distance,
+elevation and coordinates within 1e-6 relative; RGB within 1/255 on >= 99.9 % of pixels; silhouette
+hit/miss flips counted and reported (and bounded here).
+"""
+import numpy as np
+import pytest
+
+from atm_raytracer_b200 import abi, runtime
+from conftest import ramp_tile, scene
+
+pytestmark = pytest.mark.gpu
+
+META_RTOL = 1e-6
+META_ATOL = 1e-6  # metres / degrees, for values near zero (sea-level elevations)
+
+
+# ---------------------------------------------------------------------------------------------
+# terrain store
+# ---------------------------------------------------------------------------------------------
+def test_tiled_layout_is_a_bit_exact_permutation(ctx):
+    rng = np.random.default_rng(3)
+    a = rng.integers(-32767, 32767, size=(1201, 1201)).astype(np.int16)
+    b = rng.integers(-500, 9000, size=(601, 1201)).astype(np.int16)  # 50-70 degree band: 601 longitude lines
+    c = ramp_tile(0, 0, 121)
+    t = runtime.Terrain([(runtime.Terrain.desc(45, 5, a), a), (runtime.Terrain.desc(55, 5, b), b), (runtime.Terrain.desc(-1, -1, c), c)])
+    ctx.set_terrain(t)
+    for i, (_, posts) in enumerate(t.tiles):
+        np.testing.assert_array_equal(ctx.read_tile(i), posts)
+
+
+def test_get_elev_bit_exact(ctx, oracle_lib):
+    _, terrain, _, _ = scene("c2", 0.05)
+    ctx.set_terrain(terrain)
+    rng = np.random.default_rng(4)
+    lat = rng.uniform(44.9, 47.1, 20000)
+    lon = rng.uniform(4.9, 7.1, 20000)
+    # tile corners, seams and max edges
+    edge = np.array([45.0, 46.0, 47.0, 45.0 + 1e-13, 46.0 - 1e-13, 46.0 + 1e-13, 47.0 - 1e-13, 45.5])
+    lat = np.concatenate([lat, np.repeat(edge, len(edge))])
+    lon = np.concatenate([lon, np.tile(edge - 40.0, len(edge))])
+    got = ctx.get_elev(lat, lon)
+    want = oracle_lib.get_elev(terrain.tiles, lat, lon)
+    assert np.isnan(want).any() and (~np.isnan(want)).sum() > 15000
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    # same posts, same operation order, no FMA contraction: bit-exact
+    np.testing.assert_array_equal(got[ok], want[ok])
+
+
+def test_get_elev_exact_on_ramp_and_negative(ctx):
+    c = ramp_tile(-1, -1, 121, a=3, b=-2, c=-100)
+    t = runtime.Terrain.from_arrays([(-1, -1, c)])
+    ctx.set_terrain(t)
+    rng = np.random.default_rng(5)
+    lat, lon = -1 + rng.uniform(0, 1, 1000), -1 + rng.uniform(0, 1, 1000)
+    want = 3 * (lon + 1) * 120 - 2 * (lat + 1) * 120 - 100
+    np.testing.assert_allclose(ctx.get_elev(lat, lon), want, atol=1e-8)
+    assert np.isnan(ctx.get_elev(np.array([0.5]), np.array([0.5]))).all()
+    # empty terrain: every sample is None
+    ctx.set_terrain(runtime.Terrain([]))
+    assert np.isnan(ctx.get_elev(np.array([0.5, 45.0]), np.array([0.5, 5.0]))).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# stages
+# ---------------------------------------------------------------------------------------------
+def test_atmosphere_probe(ctx, oracle_lib):
+    p, terrain, _, _ = scene("c2", 0.05)
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    h = np.concatenate([np.linspace(-1000, 40000, 2001), [10999.99, 11000.0, 11000.01, 20000.0, 32000.0]])
+    t, pr, n = ctx.atmosphere_probe(h)
+    to, po, no = oracle_lib.atmosphere(p.atmosphere, p.wavelength, h)
+    np.testing.assert_array_equal(t, to)
+    np.testing.assert_allclose(pr, po, rtol=1e-14)
+    np.testing.assert_allclose(n - 1.0, no - 1.0, rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c3_flat", "c4"])
+def test_terrain_profile_matches_oracle(ctx, oracle_lib, name):
+    p, terrain, objects, textures = scene(name, 0.05)
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects(objects, textures)
+    ctx.render(meta=False, steps=False)
+    for x in (0, p.width // 3, p.width - 1):
+        got = ctx.terrain_profile(x)
+        want = oracle_lib.terrain_cache(p, terrain.tiles, x, objects)
+        assert len(got["lat"]) == len(want["lat"])
+        np.testing.assert_allclose(got["lat"], want["lat"], rtol=1e-13)
+        np.testing.assert_allclose(got["lon"], want["lon"], rtol=1e-13)
+        # bilinear of i16 posts at coordinates that differ by ~1 ulp
+        np.testing.assert_allclose(got["elev"], want["elev"], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(got["normal"], want["normal"], rtol=0, atol=1e-7)
+        flips = int((got["close"] != want["close"]).sum())
+        assert flips <= 2, f"objects_close differs at {flips} samples"
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c3_flat"])
+def test_path_cache_matches_oracle(ctx, oracle_lib, name):
+    p, terrain, _, _ = scene(name, 0.05)
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects([])
+    ctx.render(meta=False, steps=False)
+    assert ctx.observer_altitude() == oracle_lib.path_cache(p, terrain.tiles, 0)["elev"][0]
+    for y in (0, p.height // 2 - 1, p.height // 2, p.height // 2 + 3, p.height - 1):
+        got = ctx.path(y)
+        want = oracle_lib.path_cache(p, terrain.tiles, y)
+        n = len(got["dist"])
+        # the device keeps only the elements the zip with the terrain cache can consume
+        assert n == min(len(want["dist"]), ctx.terrain_profile(0)["lat"].size)
+        np.testing.assert_allclose(got["dist"], want["dist"][:n], rtol=1e-14)
+        np.testing.assert_allclose(got["elev"], want["elev"][:n], rtol=1e-9, atol=1e-6)
+        np.testing.assert_allclose(got["path_length"], want["path_length"][:n], rtol=1e-12, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------
+# full renders
+# ---------------------------------------------------------------------------------------------
+def compare_render(got, want, label="", finish_moves_frac=0.001):
+    """Returns a report dict; asserts the north-star tolerances.
+
+    silhouette_flips : pixels that hit something in one render and nothing in the other
+    first_hit_moves  : both hit, but the first trace point is a different surface crossing
+    finish_step_moves: the march ended at a different zip step. With translucent scenes this is
+                       dominated by a knife edge of the reference itself: an opaque billboard texel
+                       blends to alpha 1.0 or 1.0-1ulp -> `(a*255) as u8` = 255 or 254 -> the pixel
+                       finishes or keeps marching (object/mod.rs:111-116, utils.rs:274-277).
+    """
+    g_hit = ~np.isnan(got["meta"]["distance"])
+    w_hit = ~np.isnan(want["meta"]["distance"])
+    npix = g_hit.size
+    flips = int((g_hit != w_hit).sum())
+    both = g_hit & w_hit
+    dg, dw = got["meta"]["distance"], want["meta"]["distance"]
+    with np.errstate(invalid="ignore"):
+        close = both & (np.abs(dg - dw) <= META_RTOL * np.abs(dw) + META_ATOL)
+    first_moves = int((both & ~close).sum())
+    finish_moves = int((got["steps"] != want["steps"]).sum())
+    worst = 0.0
+    for f in ("lat", "lon", "elevation", "distance"):
+        a, b = got["meta"][f][close], want["meta"][f][close]
+        err = np.abs(a - b) / (META_ATOL / META_RTOL + np.abs(b))
+        worst = max(worst, float(err.max()) if err.size else 0.0)
+    diff = np.abs(got["rgb"].astype(np.int16) - want["rgb"].astype(np.int16)).max(axis=-1)
+    rgb_ok = float((diff <= 1).mean())
+    report = {"label": label, "pixels": npix, "silhouette_flips": flips, "first_hit_moves": first_moves,
+              "finish_step_moves": finish_moves, "meta_worst_rel": worst, "rgb_within_1": rgb_ok,
+              "rgb_exact": float((diff == 0).mean())}
+    print("PARITY", report)
+    assert flips <= max(2, npix // 1000), report
+    assert first_moves <= max(2, npix // 1000), report
+    assert finish_moves <= max(2, int(npix * finish_moves_frac)), report
+    assert worst <= META_RTOL, report
+    assert rgb_ok >= 0.999, report
+    return report
+
+
+@pytest.mark.parametrize("name,scale", [("c1", 0.5), ("c2", 0.2), ("c3_flat", 0.15), ("c3_sph", 0.15), ("c4", 0.2)])
+def test_render_matches_oracle(ctx, oracle_lib, name, scale):
+    p, terrain, objects, textures = scene(name, scale)
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects(objects, textures)
+    ctx.set_march_mode(0)
+    got = ctx.render()
+    want = oracle_lib.render(p, terrain.tiles, objects, textures)
+    rep = compare_render(got, want, name, finish_moves_frac=0.01 if objects else 0.001)
+    # ray-step accounting agrees up to the counted flips
+    gs, ws = got["stats"], want["stats"]
+    assert gs["n_terrain"] == ws["n_terrain"]
+    moved = rep["silhouette_flips"] + rep["finish_step_moves"]
+    assert abs(gs["ray_steps"] - ws["ray_steps"]) <= moved * gs["n_terrain"]
+    if moved == 0:
+        assert gs["ray_steps"] == ws["ray_steps"] and gs["trace_points"] == ws["trace_points"]
+        np.testing.assert_array_equal(got["steps"], want["steps"])
+    assert gs["step_overflows"] == 0 and gs["kernel_launches"] >= 5
+
+
+@pytest.mark.parametrize("name,scale", [("c1", 0.25), ("c2", 0.1), ("c4", 0.1)])
+def test_brute_force_march_equals_hierarchical(ctx, name, scale):
+    p, terrain, objects, textures = scene(name, scale)
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects(objects, textures)
+    ctx.set_march_mode(0)
+    a = ctx.render()
+    ctx.set_march_mode(1)
+    b = ctx.render()
+    ctx.set_march_mode(0)
+    np.testing.assert_array_equal(a["rgb"], b["rgb"])
+    np.testing.assert_array_equal(a["steps"], b["steps"])
+    for f in ("lat", "lon", "elevation", "distance"):
+        np.testing.assert_array_equal(a["meta"][f], b["meta"][f])
+    assert a["stats"]["ray_steps"] == b["stats"]["ray_steps"]
+
+
+def test_trace_point_lists_translucent_scene(ctx, oracle_lib):
+    """c4: translucent terrain + objects -> variable-length ResultPixel.trace_points."""
+    p, terrain, objects, textures = scene("c4", 0.08)
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects(objects, textures)
+    pts, cnt = ctx.render_trace(max_points=24)
+    want = oracle_lib.render(p, terrain.tiles, objects, textures, max_points=24)
+    same = cnt == want["counts"]
+    assert same.mean() >= 0.995, f"trace point counts differ on {(~same).sum()} pixels"
+    assert want["counts"].max() >= 3 and (want["counts"] == 0).any()
+    kinds = set()
+    ys, xs = np.nonzero(same & (cnt > 0))
+    for y, x in zip(ys[::7], xs[::7]):
+        n = min(int(cnt[y, x]), 24)
+        g, w = pts[y, x, :n], want["points"][y, x, :n]
+        if not np.array_equal(g["step"], w["step"]):
+            continue  # a crossing moved to the neighbouring step (counted by the count/step tests)
+        np.testing.assert_array_equal(g["is_terrain"], w["is_terrain"])
+        for f in ("lat", "lon", "distance", "elevation", "path_length"):
+            np.testing.assert_allclose(g[f], w[f], rtol=META_RTOL, atol=META_ATOL)
+        np.testing.assert_allclose(g["normal"], w["normal"], atol=1e-6)
+        np.testing.assert_allclose(g["color"], w["color"], atol=1.0 / 255 + 1e-12)
+        kinds.update(g["is_terrain"].tolist())
+    assert kinds == {0, 1}  # both terrain and object points were compared
+
+
+def test_column_shards_equal_full_render(ctx):
+    p, terrain, objects, textures = scene("c4", 0.1)
+    ctx.set_terrain(terrain)
+    ctx.set_objects(objects, textures)
+    ctx.set_params(p)
+    full = ctx.render()
+    parts = []
+    w = p.width
+    cuts = [0, w // 3, w // 3 + 1, w]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        q = abi.Params.from_buffer_copy(p)
+        q.x0, q.x1 = a, b
+        ctx.set_params(q)
+        parts.append(ctx.render())
+    np.testing.assert_array_equal(np.concatenate([r["rgb"] for r in parts], axis=1), full["rgb"])
+    np.testing.assert_array_equal(np.concatenate([r["steps"] for r in parts], axis=1), full["steps"])
+    got = np.concatenate([r["meta"] for r in parts], axis=1)
+    for f in ("lat", "lon", "elevation", "distance"):
+        np.testing.assert_array_equal(got[f], full["meta"][f])
+    assert sum(r["stats"]["ray_steps"] for r in parts) == full["stats"]["ray_steps"]
+
+
+def test_fog_simple_colouring_and_relative_altitude(ctx, oracle_lib):
+    p, terrain, objects, textures = scene("c2", 0.1)
+    p.coloring = abi.COLORING_SIMPLE
+    p.fog_enabled, p.fog_distance = 1, 60000.0
+    p.altitude.kind, p.altitude.value = abi.ALT_RELATIVE, 25.0
+    p.tilt, p.direction = -1.5, 33.0
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects([])
+    got = ctx.render()
+    want = oracle_lib.render(p, terrain.tiles)
+    compare_render(got, want, "c2-simple-fog-relative")
+
+
+def test_rays_leaving_coverage_see_sea_level(ctx, oracle_lib):
+    """Missing terrain coverage is sea level, not an error (utils.rs:28-31,84)."""
+    p, terrain, _, _ = scene("c1", 0.2)
+    p.direction = 180.0  # looking south, out of the single tile
+    p.altitude.kind, p.altitude.value = abi.ALT_ABSOLUTE, 900.0
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects([])
+    got = ctx.render()
+    want = oracle_lib.render(p, terrain.tiles)
+    compare_render(got, want, "c1-south")
+    assert (got["meta"]["elevation"][~np.isnan(got["meta"]["elevation"])] == 0.0).any()
+
+
+# ---------------------------------------------------------------------------------------------
+# full BASELINE sizes, checked through size-independent properties
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,stride", [("c2", 12), ("c4", 15)])
+def test_full_size_render_against_strided_oracle(ctx, oracle_lib, name, stride):
+    """The full-size GPU image, sub-sampled, must equal the oracle run on exactly those pixels."""
+    p, terrain, objects, textures = scene(name, 1.0)
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects(objects, textures)
+    got = ctx.render()
+    want = oracle_lib.render(p, terrain.tiles, objects, textures, stride_x=stride, stride_y=stride)
+    sub = {"rgb": got["rgb"][::stride, ::stride], "meta": got["meta"][::stride, ::stride], "steps": got["steps"][::stride, ::stride]}
+    compare_render(sub, want, f"{name}-full/{stride}", finish_moves_frac=0.01 if objects else 0.001)
+    st = got["stats"]
+    assert st["pixels_hit"] > 0 and st["ray_steps"] <= p.width * p.height * (st["n_terrain"] - 1)
+
+
+def test_errors_are_reported_not_swallowed(ctx):
+    c = runtime.Context(0)
+    try:
+        with pytest.raises(runtime.AtmrtError) as e:
+            c.render()
+        assert e.value.code == -4  # ATMRT_ERR_STATE: render before set_terrain
+        p, terrain, _, _ = scene("c1", 0.05)
+        c.set_terrain(terrain)
+        bad = abi.Params.from_buffer_copy(p)
+        bad.earth_model = 7
+        with pytest.raises(runtime.AtmrtError) as e:
+            c.set_params(bad)
+        assert e.value.code == -1
+        bad = abi.Params.from_buffer_copy(p)
+        bad.width = 40000
+        with pytest.raises(runtime.AtmrtError):
+            c.set_params(bad)
+        bad = abi.Params.from_buffer_copy(p)
+        bad.x0, bad.x1 = 5, 5
+        with pytest.raises(runtime.AtmrtError):
+            c.set_params(bad)
+        o = abi.Object()
+        o.kind = abi.OBJECT_BILLBOARD
+        with pytest.raises(runtime.AtmrtError):
+            c.set_objects([o], [None])
+    finally:
+        c.close()
