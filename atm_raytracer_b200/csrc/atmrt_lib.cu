@@ -66,7 +66,8 @@ struct atmrt_ctx {
     std::vector<double> dist_k;
     DevBuf d_dist, d_colcalc, d_tlat, d_tlon, d_telev, d_tnx, d_tny, d_tnz, d_tclose;
     DevBuf d_pdist, d_pelev, d_plen, d_pn;
-    DevBuf d_tmin1, d_tmax1, d_tmin2, d_tmax2, d_close1, d_close2, d_rmin1, d_rmax1, d_rmin2, d_rmax2;
+    DevBuf d_tmin1, d_tmax1, d_tmin2, d_tmax2, d_tmin3, d_tmax3, d_close1, d_close2, d_close3;
+    DevBuf d_rmin1, d_rmax1, d_rmin2, d_rmax2, d_rmin3, d_rmax3;
     DevBuf d_obs, d_counters;
     DevBuf d_rgb, d_meta, d_steps, d_points, d_counts;
     DevBuf d_probe_a, d_probe_b, d_probe_c, d_probe_d;
@@ -315,6 +316,7 @@ int prepare_render(atmrt_ctx* ctx) {
     S.n1 = (n_t + CHUNK - 1) / CHUNK;
     S.n1_pad = (S.n1 + 31) / 32 * 32;
     S.n2 = (S.n1 + 31) / 32;
+    S.h_pad = (p.height + 31) / 32 * 32;
     S.nobjects = (int)ctx->objects.size();
 
     const size_t wl = (size_t)(p.x1 - p.x0), h = (size_t)p.height, np = (size_t)S.n_pad;
@@ -329,22 +331,29 @@ int prepare_render(atmrt_ctx* ctx) {
     e |= ensure(ctx, ctx->d_tny, f8 * wl * np);
     e |= ensure(ctx, ctx->d_tnz, f8 * wl * np);
     if (S.nobjects > 0) e |= ensure(ctx, ctx->d_tclose, 8 * wl * np);
-    e |= ensure(ctx, ctx->d_pdist, f8 * h * np);
-    e |= ensure(ctx, ctx->d_pelev, f8 * h * np);
-    e |= ensure(ctx, ctx->d_plen, f8 * h * np);
+    const size_t hp = (size_t)S.h_pad;
+    e |= ensure(ctx, ctx->d_pdist, f8 * hp * n_t);
+    e |= ensure(ctx, ctx->d_pelev, f8 * hp * n_t);
+    e |= ensure(ctx, ctx->d_plen, f8 * hp * n_t);
     e |= ensure(ctx, ctx->d_pn, sizeof(int) * h);
     e |= ensure(ctx, ctx->d_tmin1, f8 * wl * S.n1_pad);
     e |= ensure(ctx, ctx->d_tmax1, f8 * wl * S.n1_pad);
     e |= ensure(ctx, ctx->d_tmin2, f8 * wl * S.n2);
     e |= ensure(ctx, ctx->d_tmax2, f8 * wl * S.n2);
+    e |= ensure(ctx, ctx->d_tmin3, f8 * wl);
+    e |= ensure(ctx, ctx->d_tmax3, f8 * wl);
     if (S.nobjects > 0) {
         e |= ensure(ctx, ctx->d_close1, 8 * wl * S.n1_pad);
         e |= ensure(ctx, ctx->d_close2, 8 * wl * S.n2);
+        e |= ensure(ctx, ctx->d_close3, 8 * wl);
     }
-    e |= ensure(ctx, ctx->d_rmin1, f8 * h * S.n1_pad);
-    e |= ensure(ctx, ctx->d_rmax1, f8 * h * S.n1_pad);
-    e |= ensure(ctx, ctx->d_rmin2, f8 * h * S.n2);
-    e |= ensure(ctx, ctx->d_rmax2, f8 * h * S.n2);
+    e |= ensure(ctx, ctx->d_rmin1, f8 * hp * S.n1);
+    e |= ensure(ctx, ctx->d_rmax1, f8 * hp * S.n1);
+    e |= ensure(ctx, ctx->d_rmin2, f8 * hp * S.n2);
+    e |= ensure(ctx, ctx->d_rmax2, f8 * hp * S.n2);
+    e |= ensure(ctx, ctx->d_rmin3, f8 * hp);
+    e |= ensure(ctx, ctx->d_rmax3, f8 * hp);
+    (void)h;
     e |= ensure(ctx, ctx->d_obs, f8);
     e |= ensure(ctx, ctx->d_counters, 8 * CNT_COUNT);
     e |= ensure(ctx, ctx->d_objects, sizeof(DevObject) * std::max(1, S.nobjects));
@@ -362,10 +371,13 @@ int prepare_render(atmrt_ctx* ctx) {
     B.p_n = (int*)ctx->d_pn.p;
     B.tmin1 = (double*)ctx->d_tmin1.p, B.tmax1 = (double*)ctx->d_tmax1.p;
     B.tmin2 = (double*)ctx->d_tmin2.p, B.tmax2 = (double*)ctx->d_tmax2.p;
+    B.tmin3 = (double*)ctx->d_tmin3.p, B.tmax3 = (double*)ctx->d_tmax3.p;
+    B.close3 = S.nobjects > 0 ? (unsigned long long*)ctx->d_close3.p : nullptr;
     B.close1 = S.nobjects > 0 ? (unsigned long long*)ctx->d_close1.p : nullptr;
     B.close2 = S.nobjects > 0 ? (unsigned long long*)ctx->d_close2.p : nullptr;
     B.rmin1 = (double*)ctx->d_rmin1.p, B.rmax1 = (double*)ctx->d_rmax1.p;
     B.rmin2 = (double*)ctx->d_rmin2.p, B.rmax2 = (double*)ctx->d_rmax2.p;
+    B.rmin3 = (double*)ctx->d_rmin3.p, B.rmax3 = (double*)ctx->d_rmax3.p;
     B.obs_alt = (double*)ctx->d_obs.p;
     B.objects = (DevObject*)ctx->d_objects.p;
     B.counters = (unsigned long long*)ctx->d_counters.p;
@@ -445,24 +457,20 @@ int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main) {
     k_terrain_profile<<<dim3((S.n_t + 127) / 128, wl), 128, 0, ctx->s_a>>>(S, ctx->terrain, B);
     {
         long long warps = (long long)wl * S.n2;
-        k_pyramid<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ctx->s_a>>>(B.t_elev, nullptr, B.t_close, wl, S.n_t, S.n_pad, S.n1,
-                                                                             S.n1_pad, S.n2, B.tmin1, B.tmax1, B.tmin2, B.tmax2,
-                                                                             B.close1, B.close2);
+        k_terrain_pyramid<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ctx->s_a>>>(B.t_elev, B.t_close, wl, S.n_t, S.n_pad, S.n1, S.n1_pad, S.n2,
+                                                                                    B.tmin1, B.tmax1, B.tmin2, B.tmax2, B.close1, B.close2);
+        k_terrain_top<<<(wl + 127) / 128, 128, 0, ctx->s_a>>>(B.tmin2, B.tmax2, B.close2, wl, S.n2, B.tmin3, B.tmax3, B.close3);
     }
-    ctx->launches += 3;
+    ctx->launches += 4;
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->a1, ctx->s_a));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->s_a));
 
     // Stage B on s_b
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->b0, ctx->s_b));
-    {
-        int rpw = ctx->rows_per_warp;
-        k_ray_paths<<<(h + rpw - 1) / rpw, 32, 0, ctx->s_b>>>(S, B, rpw);
-        long long warps = (long long)h * S.n2;
-        k_pyramid<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ctx->s_b>>>(B.p_elev, B.p_n, nullptr, h, S.n_t, S.n_pad, S.n1, S.n1_pad,
-                                                                             S.n2, B.rmin1, B.rmax1, B.rmin2, B.rmax2, nullptr, nullptr);
-    }
-    ctx->launches += 2;
+    k_ray_paths<<<(h + ROWS_PER_WARP - 1) / ROWS_PER_WARP, 32, 0, ctx->s_b>>>(S, B);
+    k_path_pyramid1<<<dim3((h + 255) / 256, S.n1), 256, 0, ctx->s_b>>>(B.p_elev, B.p_n, h, S.h_pad, S.n_t, S.n1, B.rmin1, B.rmax1);
+    k_path_pyramid23<<<(h + 255) / 256, 256, 0, ctx->s_b>>>(h, S.h_pad, S.n1, S.n2, B.rmin1, B.rmax1, B.rmin2, B.rmax2, B.rmin3, B.rmax3);
+    ctx->launches += 3;
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->b1, ctx->s_b));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->s_b));
 
@@ -471,19 +479,18 @@ int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main) {
     CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_b, 0));
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->c0, main));
     MarchOut O{rt.rgb, rt.meta, rt.steps, rt.points, rt.counts, rt.max_points};
-    const int blocks = ctx->num_sms * 8;
     const bool trace = rt.points != nullptr || rt.counts != nullptr;
-    if (ctx->march_mode == 1) {
-        if (trace)
-            k_march<true, true><<<blocks, 256, 0, main>>>(S, B, O);
-        else
-            k_march<true, false><<<blocks, 256, 0, main>>>(S, B, O);
+    const bool brute = ctx->march_mode == 1, objs = S.nobjects > 0;
+    const dim3 grid((h + MARCH_THREADS - 1) / MARCH_THREADS, wl);
+#define ATMRT_LAUNCH_MARCH(OB, BR, TR) k_march<OB, BR, TR><<<grid, MARCH_THREADS, 0, main>>>(S, B, O)
+    if (objs) {
+        if (brute) { if (trace) ATMRT_LAUNCH_MARCH(true, true, true); else ATMRT_LAUNCH_MARCH(true, true, false); }
+        else       { if (trace) ATMRT_LAUNCH_MARCH(true, false, true); else ATMRT_LAUNCH_MARCH(true, false, false); }
     } else {
-        if (trace)
-            k_march<false, true><<<blocks, 256, 0, main>>>(S, B, O);
-        else
-            k_march<false, false><<<blocks, 256, 0, main>>>(S, B, O);
+        if (brute) { if (trace) ATMRT_LAUNCH_MARCH(false, true, true); else ATMRT_LAUNCH_MARCH(false, true, false); }
+        else       { if (trace) ATMRT_LAUNCH_MARCH(false, false, true); else ATMRT_LAUNCH_MARCH(false, false, false); }
     }
+#undef ATMRT_LAUNCH_MARCH
     ctx->launches++;
     if (timed) {
         CUDA_TRY(ctx, cudaEventRecord(E->c1, main));
@@ -584,7 +591,7 @@ void atmrt_destroy(atmrt_ctx* ctx) {
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&ctx->d_objects_in, &ctx->d_objects, &ctx->d_dist, &ctx->d_colcalc, &ctx->d_tlat, &ctx->d_tlon, &ctx->d_telev,
                       &ctx->d_tnx, &ctx->d_tny, &ctx->d_tnz, &ctx->d_tclose, &ctx->d_pdist, &ctx->d_pelev, &ctx->d_plen, &ctx->d_pn,
-                      &ctx->d_tmin1, &ctx->d_tmax1, &ctx->d_tmin2, &ctx->d_tmax2, &ctx->d_close1, &ctx->d_close2, &ctx->d_rmin1,
+                      &ctx->d_tmin1, &ctx->d_tmax1, &ctx->d_tmin2, &ctx->d_tmax2, &ctx->d_tmin3, &ctx->d_tmax3, &ctx->d_close1, &ctx->d_close2, &ctx->d_close3, &ctx->d_rmin1, &ctx->d_rmin3, &ctx->d_rmax3,
                       &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_rgb, &ctx->d_meta,
                       &ctx->d_steps, &ctx->d_points, &ctx->d_counts, &ctx->d_probe_a, &ctx->d_probe_b, &ctx->d_probe_c, &ctx->d_probe_d};
     for (DevBuf* b : bufs) release(*b);
@@ -773,7 +780,7 @@ int atmrt_set_march_mode(atmrt_ctx* ctx, int mode) {
 // Tuning hook for Stage B: image rows integrated per warp (1..32).
 int atmrt_set_rows_per_warp(atmrt_ctx* ctx, int rows) {
     if (!ctx || rows < 1 || rows > 32) return fail(ctx, ATMRT_ERR_INVALID, "rows per warp must be 1..32");
-    ctx->rows_per_warp = rows;
+    ctx->rows_per_warp = rows;  // kept for ABI stability: the 3-lanes-per-row stepper fixes 10 rows per warp
     return 0;
 }
 
@@ -886,10 +893,12 @@ int atmrt_get_path(atmrt_ctx* ctx, int y, int capacity, double* dist, double* el
     *n = len;
     int m = std::min(capacity, len);
     if (m <= 0) return 0;
-    size_t off = (size_t)y * S.n_pad;
-    if (dist) CUDA_TRY(ctx, cudaMemcpy(dist, ctx->buf.p_dist + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
-    if (elev) CUDA_TRY(ctx, cudaMemcpy(elev, ctx->buf.p_elev + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
-    if (path_length) CUDA_TRY(ctx, cudaMemcpy(path_length, ctx->buf.p_len + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
+    // the cache is step-major [k][h_pad]: gather row y with a strided 2-D copy
+    const size_t pitch = (size_t)S.h_pad * sizeof(double);
+    if (dist) CUDA_TRY(ctx, cudaMemcpy2D(dist, sizeof(double), ctx->buf.p_dist + y, pitch, sizeof(double), (size_t)m, cudaMemcpyDeviceToHost));
+    if (elev) CUDA_TRY(ctx, cudaMemcpy2D(elev, sizeof(double), ctx->buf.p_elev + y, pitch, sizeof(double), (size_t)m, cudaMemcpyDeviceToHost));
+    if (path_length)
+        CUDA_TRY(ctx, cudaMemcpy2D(path_length, sizeof(double), ctx->buf.p_len + y, pitch, sizeof(double), (size_t)m, cudaMemcpyDeviceToHost));
     return 0;
 }
 

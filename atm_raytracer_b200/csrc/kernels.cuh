@@ -30,6 +30,7 @@ struct DevScene {
     int n1;      // level-1 chunks  = ceil(n_t / 32)
     int n1_pad;  // row stride of the level-1 pyramids
     int n2;      // level-2 chunks  = ceil(n1 / 32)
+    int h_pad;   // row stride of the step-major [k][row] path cache and of the node-major path pyramids
     int nobjects;
     int _pad;
     DevAtmosphere atm;
@@ -42,13 +43,13 @@ struct DevBuffers {
     // Stage A cache, [wl][n_pad]
     double *t_lat, *t_lon, *t_elev, *t_nx, *t_ny, *t_nz;
     unsigned long long* t_close;
-    // Stage B cache, [h][n_pad]
+    // Stage B cache, step-major [n_t][h_pad]
     double *p_dist, *p_elev, *p_len;
     int* p_n;  // [h] elements per row (capped at n_t)
     // pyramids
-    double *tmin1, *tmax1, *tmin2, *tmax2;  // [wl][n1_pad], [wl][n2]
-    unsigned long long *close1, *close2;
-    double *rmin1, *rmax1, *rmin2, *rmax2;  // [h][n1_pad], [h][n2]
+    double *tmin1, *tmax1, *tmin2, *tmax2, *tmin3, *tmax3;  // [wl][n1_pad], [wl][n2], [wl]
+    unsigned long long *close1, *close2, *close3;
+    double *rmin1, *rmax1, *rmin2, *rmax2, *rmin3, *rmax3;  // [n1][h_pad], [n2][h_pad], [h]
     double* obs_alt;  // [1]
     DevObject* objects;
     unsigned long long* counters;  // see Counter
@@ -235,56 +236,125 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stage B: ray paths. One serial RK4 chain per image row (the only parallelism the physics
-// offers is across rows and inside one derivative evaluation).
+// Stage B: ray paths. The physics offers one serial RK4 chain per image row, so this stage is bound
+// by the dependent-issue latency of ONE chain, not by FP64 throughput. Three lanes cooperate on a
+// row: the three refractive-index evaluations of the central difference dn/dh (at h-eps, h, h+eps)
+// run on three lanes and are exchanged with shuffles; every lane then applies the identical RK4
+// update, so the three copies of the state never diverge. 10 rows per warp, one warp per block so
+// the chains spread over all SMs. The cache is written step-major ([k][row]) so that both these
+// stores and the march kernel's loads (lanes = adjacent rows) are coalesced.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevScene S, DevBuffers B, int rows_per_warp) {
-    int lane = threadIdx.x;
-    if (lane >= rows_per_warp) return;
-    int y = blockIdx.x * rows_per_warp + lane;
-    if (y >= S.height) return;
+constexpr int ROWS_PER_WARP = 10;
+
+__device__ __forceinline__ void env_n_dn3(const DevAtmosphere& a, double h, int role, unsigned gmask, int gbase, double* n, double* dn) {
+    const double eps = 0.01;
+    const double off = role == 0 ? -eps : (role == 1 ? 0.0 : eps);
+    const double mine = env_n(a, h + off);
+    const double n1 = __shfl_sync(gmask, mine, gbase + 0);
+    const double n0 = __shfl_sync(gmask, mine, gbase + 1);
+    const double n2 = __shfl_sync(gmask, mine, gbase + 2);
+    *n = n0;
+    *dn = (n2 - n1) / (2.0 * eps);
+}
+
+__device__ __forceinline__ RayState stepper_next3(Stepper& s, const DevAtmosphere& atm, int flat, double radius, double step, int role,
+                                                  unsigned gmask, int gbase) {
+    double k1a, k1b, k2a, k2b, k3a, k3b, k4a, k4b, n, dn;
+    if (flat) {  // h'' = n'/n (1 + h'^2)
+        const double d = step;
+        double h = s.a, dh = s.b;
+        env_n_dn3(atm, h, role, gmask, gbase, &n, &dn);
+        k1a = dh, k1b = dn / n * (1.0 + dh * dh);
+        h = s.a + 0.5 * d * k1a, dh = s.b + 0.5 * d * k1b;
+        env_n_dn3(atm, h, role, gmask, gbase, &n, &dn);
+        k2a = dh, k2b = dn / n * (1.0 + dh * dh);
+        h = s.a + 0.5 * d * k2a, dh = s.b + 0.5 * d * k2b;
+        env_n_dn3(atm, h, role, gmask, gbase, &n, &dn);
+        k3a = dh, k3b = dn / n * (1.0 + dh * dh);
+        h = s.a + d * k3a, dh = s.b + d * k3b;
+        env_n_dn3(atm, h, role, gmask, gbase, &n, &dn);
+        k4a = dh, k4b = dn / n * (1.0 + dh * dh);
+        s.a = s.a + (k1a + 2.0 * k2a + 2.0 * k3a + k4a) * d / 6.0;
+        s.b = s.b + (k1b + 2.0 * k2b + 2.0 * k3b + k4b) * d / 6.0;
+        s.t += d;
+        return {s.t, s.a};
+    }
+    // r'' = (n'/n)(r'^2 + r^2) + 2 r'^2 / r + r, independent variable phi = x / R
+    const double d = step / radius;
+    double r = s.a, dr = s.b;
+    env_n_dn3(atm, r - radius, role, gmask, gbase, &n, &dn);
+    k1a = dr, k1b = dr * dr * dn / n + r * r * dn / n + 2.0 * dr * dr / r + r;
+    r = s.a + 0.5 * d * k1a, dr = s.b + 0.5 * d * k1b;
+    env_n_dn3(atm, r - radius, role, gmask, gbase, &n, &dn);
+    k2a = dr, k2b = dr * dr * dn / n + r * r * dn / n + 2.0 * dr * dr / r + r;
+    r = s.a + 0.5 * d * k2a, dr = s.b + 0.5 * d * k2b;
+    env_n_dn3(atm, r - radius, role, gmask, gbase, &n, &dn);
+    k3a = dr, k3b = dr * dr * dn / n + r * r * dn / n + 2.0 * dr * dr / r + r;
+    r = s.a + d * k3a, dr = s.b + d * k3b;
+    env_n_dn3(atm, r - radius, role, gmask, gbase, &n, &dn);
+    k4a = dr, k4b = dr * dr * dn / n + r * r * dn / n + 2.0 * dr * dr / r + r;
+    s.a = s.a + (k1a + 2.0 * k2a + 2.0 * k3a + k4a) * d / 6.0;
+    s.b = s.b + (k1b + 2.0 * k2b + 2.0 * k3b + k4b) * d / 6.0;
+    s.t += d;
+    return {s.t * radius, s.a - radius};
+}
+
+__global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevScene S, DevBuffers B) {
+    const int lane = threadIdx.x;
+    const int slot = lane / 3, role = lane - slot * 3;
+    const int y = blockIdx.x * ROWS_PER_WARP + slot;
+    if (slot >= ROWS_PER_WARP || y >= S.height) return;
+    const int gbase = slot * 3;
+    const unsigned gmask = 7u << gbase;
     const double alt = *B.obs_alt;
     const double ray_elev = get_ray_elev(S, y);
     Stepper st;
     stepper_init(st, S.flat, S.radius, alt, to_radians(ray_elev));
-    size_t base = (size_t)y * S.n_pad;
-    B.p_dist[base] = 0.0;
-    B.p_elev[base] = alt;
-    B.p_len[base] = 0.0;
+    const size_t hp = (size_t)S.h_pad;
+    if (role == 1) {
+        B.p_dist[y] = 0.0;
+        B.p_elev[y] = alt;
+        B.p_len[y] = 0.0;
+    }
     RayState prev{0.0, alt};
     double path_length = 0.0;
     int n = 1;
     for (int i = 1; i < S.n_t; ++i) {
-        RayState nw = stepper_next(st, S.atm, S.flat, S.straight, S.radius, S.step);
+        RayState nw = S.straight ? stepper_next(st, S.atm, S.flat, 1, S.radius, S.step)
+                                 : stepper_next3(st, S.atm, S.flat, S.radius, S.step, role, gmask, gbase);
         path_length += calc_dist(S.flat, S.radius, prev, nw);
-        B.p_dist[base + i] = nw.x;
-        B.p_elev[base + i] = nw.h;
-        B.p_len[base + i] = path_length;
+        if (role == 1) {
+            const size_t o = (size_t)i * hp + y;
+            B.p_dist[o] = nw.x;
+            B.p_elev[o] = nw.h;
+            B.p_len[o] = path_length;
+        }
         n = i + 1;
         if (prev.x > S.max_distance || prev.h < -1000.0) break;
         prev = nw;
     }
-    B.p_n[y] = n;
-    atomicAdd(B.counters + CNT_PATH_STEPS, (unsigned long long)(n - 1));
+    if (role == 1) {
+        B.p_n[y] = n;
+        atomicAdd(B.counters + CNT_PATH_STEPS, (unsigned long long)(n - 1));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Min/max pyramids. Level-1 chunk c covers march steps k in [32c, 32c+31] (k >= 1), i.e. samples
-// [32c-1, 32c+31]; level-2 chunk C covers level-1 chunks [32C, 32C+31]. One warp per (row, C).
-// A chunk without any step (or with only NaN samples) gets min=+inf, max=-inf and is never a
-// candidate.
+// Min/max pyramids. Level-1 node c covers march steps k in [32c, 32c+31] (k >= 1), i.e. samples
+// [32c-1, 32c+31]; level-2 node C covers level-1 nodes [32C, 32C+31]; level 3 is the whole ray.
+// A node without any step gets min=+inf, max=-inf and is never a candidate.
+// Terrain pyramids are [column][node] (one warp per (column, C), lanes along k); path pyramids are
+// node-major [node][row] (one thread per (row, node), lanes along rows) to match the cache layouts.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pyramid(const double* __restrict__ vals, const int* __restrict__ lens,
-                                                 const unsigned long long* __restrict__ close, int nrows, int n_total,
-                                                 int n_pad, int n1, int n1_pad, int n2, double* __restrict__ min1,
-                                                 double* __restrict__ max1, double* __restrict__ min2,
-                                                 double* __restrict__ max2, unsigned long long* __restrict__ close1,
-                                                 unsigned long long* __restrict__ close2) {
+__global__ void __launch_bounds__(256) k_terrain_pyramid(const double* __restrict__ vals, const unsigned long long* __restrict__ close,
+                                                         int nrows, int n, int n_pad, int n1, int n1_pad, int n2,
+                                                         double* __restrict__ min1, double* __restrict__ max1,
+                                                         double* __restrict__ min2, double* __restrict__ max2,
+                                                         unsigned long long* __restrict__ close1, unsigned long long* __restrict__ close2) {
     const int lane = threadIdx.x & 31;
     long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= (long long)nrows * n2) return;
     const int row = (int)(warp / n2), C = (int)(warp % n2);
-    const int n = lens ? min(lens[row], n_total) : n_total;
     const double* v = vals + (size_t)row * n_pad;
     const unsigned long long* cl = close ? close + (size_t)row * n_pad : nullptr;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
@@ -332,16 +402,84 @@ __global__ void __launch_bounds__(256) k_pyramid(const double* __restrict__ vals
     }
 }
 
+// level 3 of the terrain pyramid: one thread per column
+__global__ void k_terrain_top(const double* __restrict__ min2, const double* __restrict__ max2, const unsigned long long* __restrict__ close2,
+                              int nrows, int n2, double* __restrict__ min3, double* __restrict__ max3, unsigned long long* __restrict__ close3) {
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double lo = INF, hi = -INF;
+    unsigned long long cm = 0;
+    for (int C = 0; C < n2; ++C) {
+        lo = fmin(lo, min2[(size_t)row * n2 + C]);
+        hi = fmax(hi, max2[(size_t)row * n2 + C]);
+        if (close2) cm |= close2[(size_t)row * n2 + C];
+    }
+    min3[row] = lo;
+    max3[row] = hi;
+    if (close3) close3[row] = cm;
+}
+
+// path pyramid level 1: thread per (row, node c); vals is step-major [k][h_pad]
+__global__ void __launch_bounds__(256) k_path_pyramid1(const double* __restrict__ vals, const int* __restrict__ lens, int h, int h_pad,
+                                                       int n_total, int n1, double* __restrict__ min1, double* __restrict__ max1) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (y >= h) return;
+    const int n = min(lens[y], n_total);
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double lo = INF, hi = -INF;
+    if (n >= 2 && 32 * c <= n - 1) {
+        const int k0 = max(32 * c - 1, 0), k1 = min(32 * c + 31, n - 1);
+        for (int k = k0; k <= k1; ++k) {
+            double x = vals[(size_t)k * h_pad + y];
+            lo = fmin(lo, x);
+            hi = fmax(hi, x);
+        }
+    }
+    min1[(size_t)c * h_pad + y] = lo;
+    max1[(size_t)c * h_pad + y] = hi;
+}
+
+// path pyramid levels 2 and 3: thread per row
+__global__ void __launch_bounds__(256) k_path_pyramid23(int h, int h_pad, int n1, int n2, const double* __restrict__ min1,
+                                                        const double* __restrict__ max1, double* __restrict__ min2,
+                                                        double* __restrict__ max2, double* __restrict__ min3, double* __restrict__ max3) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= h) return;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double lo3 = INF, hi3 = -INF;
+    for (int C = 0; C < n2; ++C) {
+        double lo = INF, hi = -INF;
+        for (int c = 32 * C; c < min(32 * C + 32, n1); ++c) {
+            lo = fmin(lo, min1[(size_t)c * h_pad + y]);
+            hi = fmax(hi, max1[(size_t)c * h_pad + y]);
+        }
+        min2[(size_t)C * h_pad + y] = lo;
+        max2[(size_t)C * h_pad + y] = hi;
+        lo3 = fmin(lo3, lo);
+        hi3 = fmax(hi3, hi);
+    }
+    min3[y] = lo3;
+    max3[y] = hi3;
+}
+
 // ---------------------------------------------------------------------------------------------
-// Stage C: the march.
+// Stage C: the march. One thread per pixel; the 32 lanes of a warp are 32 adjacent rows of ONE
+// column, so every terrain-side load (profile, pyramids) is a warp-wide broadcast and every
+// path-side load is coalesced ([k][row] layout). Each lane alternates between
+//   phase 1: a cheap search for its next event (a step with a terrain crossing, or with a close
+//            object) that skips 1024-, 32-step nodes whose min/max intervals cannot cross, and
+//   phase 2: the expensive event processing (interpolation, object intersection, colouring,
+//            compositing), executed after the warp has reconverged so that all lanes holding an
+//            event run it together; finished pixels retire through a warp vote.
+// Follows get_single_pixel (utils.rs:201-289) and draw_image (renderer/mod.rs:395-411).
 // ---------------------------------------------------------------------------------------------
 struct PixelState {
     Rgb8 result;
     double accum_neg_alpha;
     int count;
-    int finished;
-    int consumed;
-    unsigned overflows;
+    int overflows;
     double m_lat, m_lon, m_elev, m_dist;
 };
 
@@ -354,20 +492,58 @@ struct MarchOut {
     int max_points;
 };
 
-// One march step with at least one event (terrain crossing or a close object). Executed
-// uniformly by all lanes of the warp that owns the pixel (same addresses -> broadcast loads), so
-// the pixel state stays warp-uniform without shuffles. Follows get_single_pixel's loop body
-// (utils.rs:211-287) and draw_image's inner loop (renderer/mod.rs:399-408).
+// One emitted trace point: colour it, composite it, remember the first one as the pixel metadata
+// (renderer/mod.rs:399-408).
 template <bool TRACE>
-__device__ __noinline__ void process_step(const DevScene& S, const DevBuffers& B, const MarchOut& O, int xl, int y, int k,
-                                          size_t pixel, PixelState& st) {
-    const size_t ti = (size_t)xl * S.n_pad + k, pi = (size_t)y * S.n_pad + k;
+__device__ __forceinline__ void emit_point(const DevScene& S, const MarchOut& O, size_t pixel, int k, PixelState& st, bool is_terrain,
+                                           double lat, double lon, double dist, double elevation, double plen, V3 normal, Color4 color) {
+    const double alpha = color.a;
+    Rgb8 color1 = color_for_pixel(S.shade, is_terrain, elevation, dist, normal, color);
+    Rgb8 color2 = S.shade.fog_enabled ? apply_fog(S.shade.fog_distance, plen, color1) : color1;
+    st.result = add_rgb(st.result, color2, st.accum_neg_alpha * alpha);
+    st.accum_neg_alpha *= 1.0 - alpha;
+    if (st.count == 0) {
+        st.m_lat = lat, st.m_lon = lon, st.m_elev = elevation, st.m_dist = dist;
+    }
+    if (TRACE) {
+        if (st.count < O.max_points) {
+            atmrt_trace_point& tp = O.points[pixel * O.max_points + st.count];
+            tp.lat = lat, tp.lon = lon, tp.distance = dist, tp.elevation = elevation, tp.path_length = plen;
+            tp.normal[0] = normal.x, tp.normal[1] = normal.y, tp.normal[2] = normal.z;
+            tp.color[0] = color.r, tp.color[1] = color.g, tp.color[2] = color.b, tp.color[3] = alpha;
+            tp.is_terrain = is_terrain ? 1 : 0;
+            tp.step = k;
+        }
+    }
+    st.count += 1;
+}
+
+// One march step that holds an event. Returns true when the pixel finishes (an alpha == 1 surface).
+template <bool OBJECTS, bool TRACE>
+__device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers& B, const MarchOut& O, int xl, int y, int k,
+                                             size_t pixel, PixelState& st) {
+    const size_t ti = (size_t)xl * S.n_pad + k;
+    const size_t p1 = (size_t)k * S.h_pad + y, p0 = p1 - S.h_pad;
     // old_tracing_state = (terrain[k-1], path[k-1]) with dist/path_len forced to 0 for k-1 == 0.
     const double lat0 = B.t_lat[ti - 1], lon0 = B.t_lon[ti - 1], elev0 = B.t_elev[ti - 1];
     const double lat1 = B.t_lat[ti], lon1 = B.t_lon[ti], elev1 = B.t_elev[ti];
-    const double ray0 = B.p_elev[pi - 1], ray1 = B.p_elev[pi];
-    const double dist0 = k - 1 == 0 ? 0.0 : B.p_dist[pi - 1], dist1 = B.p_dist[pi];
-    const double len0 = k - 1 == 0 ? 0.0 : B.p_len[pi - 1], len1 = B.p_len[pi];
+    const double ray0 = B.p_elev[p0], ray1 = B.p_elev[p1];
+    const double dist0 = k - 1 == 0 ? 0.0 : B.p_dist[p0], dist1 = B.p_dist[p1];
+    const double len0 = k - 1 == 0 ? 0.0 : B.p_len[p0], len1 = B.p_len[p1];
+    const double diff1 = ray0 - elev0, diff2 = ray1 - elev1;
+    const bool terrain_hit = diff1 * diff2 < 0.0;
+    bool finish = false;
+
+    if (!OBJECTS) {
+        if (!terrain_hit) return false;
+        const double prop = diff1 / (diff1 - diff2);
+        V3 n0{B.t_nx[ti - 1], B.t_ny[ti - 1], B.t_nz[ti - 1]}, n1{B.t_nx[ti], B.t_ny[ti], B.t_nz[ti]};
+        // TracingState::interpolate, utils.rs:108-125
+        emit_point<TRACE>(S, O, pixel, k, st, true, lat0 + (lat1 - lat0) * prop, lon0 + (lon1 - lon0) * prop,
+                          dist0 + (dist1 - dist0) * prop, elev0 + (elev1 - elev0) * prop, len0 + (len1 - len0) * prop,
+                          n0 + (n1 - n0) * prop, Color4{0.0, 0.0, 0.0, S.shade.terrain_alpha});
+        return S.shade.terrain_alpha == 1.0;
+    }
 
     double c_prop[ATMRT_MAX_STEP_POINTS];
     V3 c_normal[ATMRT_MAX_STEP_POINTS];
@@ -375,10 +551,7 @@ __device__ __noinline__ void process_step(const DevScene& S, const DevBuffers& B
     bool c_terrain[ATMRT_MAX_STEP_POINTS];
     int ncand = 0;
     bool overflow = false;
-    bool finish = false;
-
-    const double diff1 = ray0 - elev0, diff2 = ray1 - elev1;
-    if (diff1 * diff2 < 0.0) {
+    if (terrain_hit) {
         double prop = diff1 / (diff1 - diff2);
         V3 n0{B.t_nx[ti - 1], B.t_ny[ti - 1], B.t_nz[ti - 1]}, n1{B.t_nx[ti], B.t_ny[ti], B.t_nz[ti]};
         c_prop[0] = prop;
@@ -388,35 +561,32 @@ __device__ __noinline__ void process_step(const DevScene& S, const DevBuffers& B
         ncand = 1;
         if (S.shade.terrain_alpha == 1.0) finish = true;
     }
-    if (S.nobjects > 0) {
-        unsigned long long mask = B.t_close[ti - 1] | B.t_close[ti];
-        if (mask) {
-            V3 pos1 = as_cartesian(S.earth_model, S.radius, lat0, lon0, ray0);
-            V3 pos2 = as_cartesian(S.earth_model, S.radius, lat1, lon1, ray1);
-            // The reference walks a HashSet (arbitrary order); index order here. Only exact `prop` ties
-            // could tell the difference (stable sort below).
-            while (mask) {
-                int oi = __ffsll((long long)mask) - 1;
-                mask &= mask - 1;
-                const DevObject& o = B.objects[oi];
-                Collision coll[4];
-                int nc = o.kind == ATMRT_OBJECT_FRUSTUM ? frustum_collision(o, pos1, pos2, coll)
-                                                        : billboard_collision(o, pos1, pos2, coll);
-                for (int i = 0; i < nc; ++i) {
-                    if (coll[i].color.a == 0.0) continue;
-                    if (ncand < ATMRT_MAX_STEP_POINTS) {
-                        c_prop[ncand] = coll[i].prop;
-                        c_normal[ncand] = coll[i].normal;
-                        c_color[ncand] = coll[i].color;
-                        c_terrain[ncand] = false;
-                        ++ncand;
-                    } else {
-                        overflow = true;
-                    }
-                    if (coll[i].color.a == 1.0) {
-                        finish = true;
-                        break;
-                    }
+    unsigned long long mask = B.t_close[ti - 1] | B.t_close[ti];
+    if (mask) {
+        V3 pos1 = as_cartesian(S.earth_model, S.radius, lat0, lon0, ray0);
+        V3 pos2 = as_cartesian(S.earth_model, S.radius, lat1, lon1, ray1);
+        // The reference walks a HashSet (arbitrary order); index order here. Only exact `prop` ties
+        // could tell the difference (stable sort below).
+        while (mask) {
+            int oi = __ffsll((long long)mask) - 1;
+            mask &= mask - 1;
+            const DevObject& o = B.objects[oi];
+            Collision coll[4];
+            int nc = o.kind == ATMRT_OBJECT_FRUSTUM ? frustum_collision(o, pos1, pos2, coll) : billboard_collision(o, pos1, pos2, coll);
+            for (int i = 0; i < nc; ++i) {
+                if (coll[i].color.a == 0.0) continue;
+                if (ncand < ATMRT_MAX_STEP_POINTS) {
+                    c_prop[ncand] = coll[i].prop;
+                    c_normal[ncand] = coll[i].normal;
+                    c_color[ncand] = coll[i].color;
+                    c_terrain[ncand] = false;
+                    ++ncand;
+                } else {
+                    overflow = true;
+                }
+                if (coll[i].color.a == 1.0) {
+                    finish = true;
+                    break;
                 }
             }
         }
@@ -435,153 +605,132 @@ __device__ __noinline__ void process_step(const DevScene& S, const DevBuffers& B
     for (int oi = 0; oi < ncand; ++oi) {
         const int i = order[oi];
         const double prop = c_prop[i];
-        // TracingState::interpolate, utils.rs:108-125
-        const double lat = lat0 + (lat1 - lat0) * prop;
-        const double lon = lon0 + (lon1 - lon0) * prop;
         const double t_elev = elev0 + (elev1 - elev0) * prop;
         const double r_elev = ray0 + (ray1 - ray0) * prop;
-        const double dist = dist0 + (dist1 - dist0) * prop;
-        const double plen = len0 + (len1 - len0) * prop;
-        const double elevation = c_terrain[i] ? t_elev : r_elev;
-        const double alpha = c_color[i].a;
-        Rgb8 color1 = color_for_pixel(S.shade, c_terrain[i], elevation, dist, c_normal[i], c_color[i]);
-        Rgb8 color2 = S.shade.fog_enabled ? apply_fog(S.shade.fog_distance, plen, color1) : color1;
-        st.result = add_rgb(st.result, color2, st.accum_neg_alpha * alpha);
-        st.accum_neg_alpha *= 1.0 - alpha;
-        if (st.count == 0) {
-            st.m_lat = lat, st.m_lon = lon, st.m_elev = elevation, st.m_dist = dist;
-        }
-        if (TRACE) {
-            if (st.count < O.max_points && (threadIdx.x & 31) == 0) {
-                atmrt_trace_point& tp = O.points[pixel * O.max_points + st.count];
-                tp.lat = lat, tp.lon = lon, tp.distance = dist, tp.elevation = elevation, tp.path_length = plen;
-                tp.normal[0] = c_normal[i].x, tp.normal[1] = c_normal[i].y, tp.normal[2] = c_normal[i].z;
-                tp.color[0] = c_color[i].r, tp.color[1] = c_color[i].g, tp.color[2] = c_color[i].b, tp.color[3] = alpha;
-                tp.is_terrain = c_terrain[i] ? 1 : 0;
-                tp.step = k;
-            }
-        }
-        st.count += 1;
+        emit_point<TRACE>(S, O, pixel, k, st, c_terrain[i], lat0 + (lat1 - lat0) * prop, lon0 + (lon1 - lon0) * prop,
+                          dist0 + (dist1 - dist0) * prop, c_terrain[i] ? t_elev : r_elev, len0 + (len1 - len0) * prop, c_normal[i],
+                          c_color[i]);
     }
-    if (finish) {
-        st.finished = 1;
-        st.consumed = k;
-    }
+    return finish;
 }
 
-// Level-0: the 32 steps of chunk c1, one per lane. Detects the events exactly like the reference
-// (`diff1 * diff2 < 0.0`, utils.rs:220-222; non-empty objects_close, :241-243) and processes them
-// in step order until the pixel finishes.
-template <bool TRACE>
-__device__ __forceinline__ void march_chunk(const DevScene& S, const DevBuffers& B, const MarchOut& O, int xl, int y, int c1,
-                                            int nlim, size_t pixel, PixelState& st) {
-    const int lane = threadIdx.x & 31;
-    const int k = c1 * CHUNK + lane;
-    bool ev = false;
-    if (k >= 1 && k < nlim) {
-        const size_t ti = (size_t)xl * S.n_pad + k, pi = (size_t)y * S.n_pad + k;
-        double diff1 = B.p_elev[pi - 1] - B.t_elev[ti - 1];
-        double diff2 = B.p_elev[pi] - B.t_elev[ti];
-        ev = diff1 * diff2 < 0.0;
-        if (S.nobjects > 0) ev = ev || (B.t_close[ti - 1] | B.t_close[ti]) != 0;
-    }
-    unsigned m = __ballot_sync(FULL, ev);
-    while (m && !st.finished) {
-        int l = __ffs(m) - 1;
-        m &= m - 1;
-        process_step<TRACE>(S, B, O, xl, y, c1 * CHUNK + l, pixel, st);
-    }
-}
+constexpr int MARCH_THREADS = 128;
 
-template <bool BRUTE, bool TRACE>
-__global__ void __launch_bounds__(256) k_march(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O) {
+template <bool OBJECTS, bool BRUTE, bool TRACE>
+__global__ void __launch_bounds__(MARCH_THREADS) k_march(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O) {
     const int lane = threadIdx.x & 31;
+    const int xl = blockIdx.y;
+    const int y = blockIdx.x * MARCH_THREADS + threadIdx.x;
+    const bool active = y < S.height;
+    const int yy = active ? y : S.height - 1;  // inactive lanes shadow the last row and write nothing
     const int wl = S.x1 - S.x0;
-    const long long npix = (long long)wl * S.height;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    unsigned long long s_steps = 0, s_points = 0, s_hit = 0, s_over = 0;
-    const bool translucent = S.shade.terrain_alpha != 1.0;
+    const size_t pixel = (size_t)yy * wl + xl;
+    const int nlim = min(S.n_t, B.p_n[yy]);
+    const size_t tbase = (size_t)xl * S.n_pad;
+    const size_t hp = (size_t)S.h_pad;
 
-    for (long long pixel = warp; pixel < npix; pixel += nwarps) {
-        const int y = (int)(pixel / wl), xl = (int)(pixel % wl);
-        const int nlim = min(S.n_t, B.p_n[y]);
-        PixelState st;
-        st.result = Rgb8{{0, 0, 0}};
-        st.accum_neg_alpha = 1.0;
-        st.count = 0;
-        st.finished = 0;
-        st.consumed = nlim > 0 ? nlim - 1 : 0;
-        st.overflows = 0;
-        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-        st.m_lat = st.m_lon = st.m_elev = st.m_dist = qnan;
+    PixelState st;
+    st.result = Rgb8{{0, 0, 0}};
+    st.accum_neg_alpha = 1.0;
+    st.count = 0;
+    st.overflows = 0;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    st.m_lat = st.m_lon = st.m_elev = st.m_dist = qnan;
+    int consumed = nlim > 0 ? nlim - 1 : 0;
+    bool finished = !active || nlim < 2;
+    int k = 1;
 
-        if (BRUTE) {
-            const int nc = (nlim + CHUNK - 1) / CHUNK;
-            for (int c1 = 0; c1 < nc && !st.finished; ++c1) march_chunk<TRACE>(S, B, O, xl, y, c1, nlim, (size_t)pixel, st);
-        } else {
-            // Level 2 -> level 1 -> level 0 descent. A chunk can contain a terrain crossing only if
-            // some diff may be negative AND some may be positive: rmin < tmax && rmax > tmin.
-            // Opaque terrain: the ray starts above ground in practice, but both polarities are
-            // handled so the result is exact for any start. (`translucent` only matters downstream.)
-            (void)translucent;
-            for (int cb = 0; cb < S.n2 && !st.finished; cb += 32) {
-                const int C = cb + lane;
-                bool cand2 = false;
-                if (C < S.n2) {
-                    const size_t tj = (size_t)xl * S.n2 + C, rj = (size_t)y * S.n2 + C;
-                    const double rmin = B.rmin2[rj], rmax = B.rmax2[rj];
-                    cand2 = rmin < B.tmax2[tj] && rmax > B.tmin2[tj];
-                    if (S.nobjects > 0) cand2 = cand2 || (B.close2[tj] != 0 && rmin <= rmax);
-                }
-                unsigned m2 = __ballot_sync(FULL, cand2);
-                while (m2 && !st.finished) {
-                    const int c2 = cb + __ffs(m2) - 1;
-                    m2 &= m2 - 1;
-                    const int c = c2 * 32 + lane;
-                    bool cand1 = false;
-                    if (c < S.n1) {
-                        const size_t tj = (size_t)xl * S.n1_pad + c, rj = (size_t)y * S.n1_pad + c;
-                        const double rmin = B.rmin1[rj], rmax = B.rmax1[rj];
-                        cand1 = rmin < B.tmax1[tj] && rmax > B.tmin1[tj];
-                        if (S.nobjects > 0) cand1 = cand1 || (B.close1[tj] != 0 && rmin <= rmax);
-                    }
-                    unsigned m1 = __ballot_sync(FULL, cand1);
-                    while (m1 && !st.finished) {
-                        const int c1 = c2 * 32 + __ffs(m1) - 1;
-                        m1 &= m1 - 1;
-                        march_chunk<TRACE>(S, B, O, xl, y, c1, nlim, (size_t)pixel, st);
-                    }
-                }
-            }
-        }
-
-        // draw_image tail: *px = add(result, def_color, accum_neg_alpha)  (renderer/mod.rs:410)
-        if (lane == 0) {
-            Rgb8 def{{S.shade.def_color[0], S.shade.def_color[1], S.shade.def_color[2]}};
-            Rgb8 px = add_rgb(st.result, def, st.accum_neg_alpha);
-            if (O.rgb) {
-                O.rgb[pixel * 3 + 0] = px.c[0];
-                O.rgb[pixel * 3 + 1] = px.c[1];
-                O.rgb[pixel * 3 + 2] = px.c[2];
-            }
-            if (O.meta) {
-                atmrt_meta mm{st.m_lat, st.m_lon, st.m_elev, st.m_dist};
-                O.meta[pixel] = mm;
-            }
-            if (O.steps) O.steps[pixel] = st.consumed;
-            if (TRACE && O.counts) O.counts[pixel] = st.count;
-        }
-        s_steps += (unsigned long long)st.consumed;
-        s_points += (unsigned long long)st.count;
-        s_hit += st.count > 0 ? 1 : 0;
-        s_over += st.overflows;
+    if (!BRUTE && !finished) {  // level 3: can this ray cross this column's terrain at all?
+        bool cand = B.rmin3[yy] < B.tmax3[xl] && B.rmax3[yy] > B.tmin3[xl];
+        if (OBJECTS) cand = cand || B.close3[xl] != 0;
+        if (!cand) finished = true;
     }
+    double d_prev = 0.0;
+    bool have_prev = false;
+    for (;;) {
+        // ---- phase 1: search for this lane's next event ----
+        int ev = -1;
+        if (!finished) {
+            while (k < nlim) {
+                if (!BRUTE) {
+                    if (k == 1 || (k & 1023) == 0) {
+                        const int C = k >> 10;
+                        const double rmin = B.rmin2[(size_t)C * hp + yy], rmax = B.rmax2[(size_t)C * hp + yy];
+                        bool cand = rmin < B.tmax2[(size_t)xl * S.n2 + C] && rmax > B.tmin2[(size_t)xl * S.n2 + C];
+                        if (OBJECTS) cand = cand || (B.close2[(size_t)xl * S.n2 + C] != 0 && rmin <= rmax);
+                        if (!cand) {
+                            k = (C + 1) << 10;
+                            have_prev = false;
+                            continue;
+                        }
+                    }
+                    if (k == 1 || (k & 31) == 0) {
+                        const int c = k >> 5;
+                        const double rmin = B.rmin1[(size_t)c * hp + yy], rmax = B.rmax1[(size_t)c * hp + yy];
+                        bool cand = rmin < B.tmax1[(size_t)xl * S.n1_pad + c] && rmax > B.tmin1[(size_t)xl * S.n1_pad + c];
+                        if (OBJECTS) cand = cand || (B.close1[(size_t)xl * S.n1_pad + c] != 0 && rmin <= rmax);
+                        if (!cand) {
+                            k = (c + 1) << 5;
+                            have_prev = false;
+                            continue;
+                        }
+                    }
+                }
+                // the reference's test: diff1 * diff2 < 0.0 (utils.rs:220-222); diff1 of step k is diff2 of step k-1
+                const double dp = have_prev ? d_prev : B.p_elev[(size_t)(k - 1) * hp + yy] - B.t_elev[tbase + k - 1];
+                const double dn = B.p_elev[(size_t)k * hp + yy] - B.t_elev[tbase + k];
+                d_prev = dn;
+                have_prev = true;
+                bool e = dp * dn < 0.0;
+                if (OBJECTS) e = e || (B.t_close[tbase + k - 1] | B.t_close[tbase + k]) != 0;
+                if (e) {
+                    ev = k;
+                    break;
+                }
+                ++k;
+            }
+            if (ev < 0) finished = true;
+        }
+        if (__all_sync(FULL, finished)) break;
+        // ---- phase 2: lanes holding an event process it together ----
+        if (ev >= 0) {
+            if (process_step<OBJECTS, TRACE>(S, B, O, xl, yy, ev, pixel, st)) {
+                finished = true;
+                consumed = ev;
+            } else {
+                k = ev + 1;
+            }
+        }
+    }
+
+    // draw_image tail: *px = add(result, def_color, accum_neg_alpha)  (renderer/mod.rs:410)
+    if (active) {
+        Rgb8 def{{S.shade.def_color[0], S.shade.def_color[1], S.shade.def_color[2]}};
+        Rgb8 px = add_rgb(st.result, def, st.accum_neg_alpha);
+        if (O.rgb) {
+            O.rgb[pixel * 3 + 0] = px.c[0];
+            O.rgb[pixel * 3 + 1] = px.c[1];
+            O.rgb[pixel * 3 + 2] = px.c[2];
+        }
+        if (O.meta) {
+            atmrt_meta mm{st.m_lat, st.m_lon, st.m_elev, st.m_dist};
+            O.meta[pixel] = mm;
+        }
+        if (O.steps) O.steps[pixel] = consumed;
+        if (TRACE && O.counts) O.counts[pixel] = st.count;
+    }
+    // counters: one atomic per warp
+    unsigned long long s_steps = active ? (unsigned long long)consumed : 0ull;
+    unsigned s_points = active ? (unsigned)st.count : 0u, s_hit = active && st.count > 0 ? 1u : 0u, s_over = active ? (unsigned)st.overflows : 0u;
+    for (int o = 16; o > 0; o >>= 1) s_steps += __shfl_xor_sync(FULL, s_steps, o);
+    s_points = __reduce_add_sync(FULL, s_points);
+    s_hit = __reduce_add_sync(FULL, s_hit);
+    s_over = __reduce_add_sync(FULL, s_over);
     if (lane == 0) {
         if (s_steps) atomicAdd(B.counters + CNT_RAY_STEPS, s_steps);
-        if (s_points) atomicAdd(B.counters + CNT_TRACE_POINTS, s_points);
-        if (s_hit) atomicAdd(B.counters + CNT_PIXELS_HIT, s_hit);
-        if (s_over) atomicAdd(B.counters + CNT_OVERFLOWS, s_over);
+        if (s_points) atomicAdd(B.counters + CNT_TRACE_POINTS, (unsigned long long)s_points);
+        if (s_hit) atomicAdd(B.counters + CNT_PIXELS_HIT, (unsigned long long)s_hit);
+        if (s_over) atomicAdd(B.counters + CNT_OVERFLOWS, (unsigned long long)s_over);
     }
 }
 

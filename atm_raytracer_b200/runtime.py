@@ -234,6 +234,8 @@ class Context:
     def render(self, rgb=True, meta=True, steps=True, out=None):
         """Host-buffer render (copies inside the call). Returns dict(rgb, meta, steps, stats).
         ``out`` may carry preallocated (e.g. pinned) arrays under the same keys."""
+        if self.params is None:  # let the library report the call-order violation (ATMRT_ERR_STATE)
+            self._check(lib.atmrt_render(self._h, None, None, None, None))
         h, w = self.shape()
         out = out or {}
         a_rgb = out.get("rgb") if rgb else None
