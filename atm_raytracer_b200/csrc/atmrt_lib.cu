@@ -467,7 +467,17 @@ int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main) {
 
     // Stage B on s_b
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->b0, ctx->s_b));
-    k_ray_paths<<<(h + ROWS_PER_WARP - 1) / ROWS_PER_WARP, 32, 0, ctx->s_b>>>(S, B);
+    {
+        const int rb = (h + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
+        const bool dry = S.atm.humidity == 0.0;
+        if (S.flat) {
+            if (dry) k_ray_paths<true, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
+            else     k_ray_paths<true, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
+        } else {
+            if (dry) k_ray_paths<false, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
+            else     k_ray_paths<false, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
+        }
+    }
     k_path_pyramid1<<<dim3((h + 255) / 256, S.n1), 256, 0, ctx->s_b>>>(B.p_elev, B.p_n, h, S.h_pad, S.n_t, S.n1, B.rmin1, B.rmax1);
     k_path_pyramid23<<<(h + 255) / 256, 256, 0, ctx->s_b>>>(h, S.h_pad, S.n1, S.n2, B.rmin1, B.rmax1, B.rmin2, B.rmax2, B.rmin3, B.rmax3);
     ctx->launches += 3;

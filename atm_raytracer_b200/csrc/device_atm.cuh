@@ -44,19 +44,24 @@ __device__ __forceinline__ double layer_temperature(const DevAtmLayer& l, double
 }
 
 // Hydrostatic pressure inside one layer: p_ref (T/T_ref)^expo for a linear temperature function,
-// p_ref exp(-g M (h - h_ref) / (R T_ref)) for an isothermal one. Written branch-free (both exponents,
-// one select, one exp) because this sits on the serial critical path of the ray stepper: pow() is
-// evaluated as exp(expo * log(x)), which for x in [0.5, 1.5] and |expo| < 40 stays within ~3 ulp of
-// the correctly rounded power -- far below the half-ulp-of-n noise (2e-7 relative in dn/dh) that the
-// reference's finite-difference derivative carries anyway.
+// p_ref exp(-g M (h - h_ref) / (R T_ref)) for an isothermal one. pow() is evaluated as
+// exp(expo * log(x)) because this sits on the serial critical path of the ray stepper (pow costs 740
+// dependent cycles on B200, log + exp 430): for x in [0.5, 1.5] and |expo| < 40 that stays within
+// ~3 ulp of the correctly rounded power -- far below the half-ulp-of-n noise (4e-7 relative in
+// dn/dh) that the reference's finite-difference derivative carries anyway.
 __device__ __forceinline__ double layer_pressure(const DevAtmLayer& l, double h, double t) {
-    const double a_lin = l.expo * log(t / l.t_ref);
-    const double a_iso = l.gm * (h - l.h_ref) / l.rt;
-    return l.p_ref * exp(l.gradient != 0.0 ? a_lin : a_iso);
+    double arg;
+    if (l.gradient != 0.0)
+        arg = l.expo * log(t / l.t_ref);
+    else
+        arg = l.gm * (h - l.h_ref) / l.rt;
+    return l.p_ref * exp(arg);
 }
 
-// Ciddor (1996); p in Pa, t in K.
-__device__ __forceinline__ double air_index(const DevAtmosphere& a, double p, double t_kelvin) {
+// Ciddor (1996); p in Pa, t in K. DRY = relative humidity 0: every water-vapour term is then an
+// exact zero (x_v = 0 => rho_v = 0, (..)*x_v = 0, 1 - x_v = 1), so dropping them is bit-identical.
+template <bool DRY>
+__device__ __forceinline__ double air_index_t(const DevAtmosphere& a, double p, double t_kelvin) {
     const double a0 = 1.58123e-6, a1 = -2.9331e-8, a2 = 1.1043e-10;
     const double b0 = 5.707e-6, b1 = -2.051e-8;
     const double c0 = 1.9898e-4, c1 = -2.376e-6;
@@ -66,27 +71,36 @@ __device__ __forceinline__ double air_index(const DevAtmosphere& a, double p, do
     const double alpha = 1.00062, beta = 3.14e-8, gamma = 5.6e-7;
     const double sa = 1.2378847e-5, sb = -1.9121316e-2, sc = 33.93711047, sd = -6.3431645e3;
 
-    double t_c = t_kelvin - 273.15;
-    double x_v = 0.0;
-    if (a.humidity != 0.0) {
-        double svp = exp(sa * t_kelvin * t_kelvin + sb * t_kelvin + sc + sd / t_kelvin);
-        double f = alpha + beta * p + gamma * t_c * t_c;
-        x_v = a.humidity * f * svp / p;
+    const double t_c = t_kelvin - 273.15;
+    const double pt = p / t_kelvin;
+    if (DRY) {
+        const double z_m = 1.0 - pt * (a0 + a1 * t_c + a2 * t_c * t_c) + pt * pt * d;
+        const double rho_a = p * a.m_a / (z_m * gas_r * t_kelvin);
+        return 1.0 + (rho_a / a.rho_axs) * a.r_axs;
     }
-    double pt = p / t_kelvin;
-    double z_m = 1.0 - pt * (a0 + a1 * t_c + a2 * t_c * t_c + (b0 + b1 * t_c) * x_v + (c0 + c1 * t_c) * x_v * x_v) +
-                 pt * pt * (d + e * x_v * x_v);
-    double rho_v = x_v * p * m_v / (z_m * gas_r * t_kelvin);
-    double rho_a = (1.0 - x_v) * p * a.m_a / (z_m * gas_r * t_kelvin);
+    const double svp = exp(sa * t_kelvin * t_kelvin + sb * t_kelvin + sc + sd / t_kelvin);
+    const double f = alpha + beta * p + gamma * t_c * t_c;
+    const double x_v = a.humidity * f * svp / p;
+    const double z_m = 1.0 - pt * (a0 + a1 * t_c + a2 * t_c * t_c + (b0 + b1 * t_c) * x_v + (c0 + c1 * t_c) * x_v * x_v) +
+                       pt * pt * (d + e * x_v * x_v);
+    const double rho_v = x_v * p * m_v / (z_m * gas_r * t_kelvin);
+    const double rho_a = (1.0 - x_v) * p * a.m_a / (z_m * gas_r * t_kelvin);
     return 1.0 + (rho_a / a.rho_axs) * a.r_axs + (rho_v / rho_vs) * a.r_vs;
+}
+__device__ __forceinline__ double air_index(const DevAtmosphere& a, double p, double t_kelvin) {
+    return a.humidity != 0.0 ? air_index_t<false>(a, p, t_kelvin) : air_index_t<true>(a, p, t_kelvin);
 }
 
 // Environment::n(h)
-__device__ __forceinline__ double env_n(const DevAtmosphere& a, double h) {
+template <bool DRY>
+__device__ __forceinline__ double env_n_t(const DevAtmosphere& a, double h) {
     const DevAtmLayer& l = a.layer[atm_layer_index(a, h)];
     double t = layer_temperature(l, h);
     double p = layer_pressure(l, h, t);
-    return air_index(a, p, t);
+    return air_index_t<DRY>(a, p, t);
+}
+__device__ __forceinline__ double env_n(const DevAtmosphere& a, double h) {
+    return a.humidity != 0.0 ? env_n_t<false>(a, h) : env_n_t<true>(a, h);
 }
 
 // n(h) and dn/dh = (n(h+eps) - n(h-eps)) / (2 eps): three independent evaluations.

@@ -246,10 +246,10 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 constexpr int ROWS_PER_WARP = 10;
 
-__device__ __forceinline__ void env_n_dn3(const DevAtmosphere& a, double h, int role, unsigned gmask, int gbase, double* n, double* dn) {
+template <bool DRY>
+__device__ __forceinline__ void env_n_dn3(const DevAtmosphere& a, double h, double off, unsigned gmask, int gbase, double* n, double* dn) {
     const double eps = 0.01;
-    const double off = role == 0 ? -eps : (role == 1 ? 0.0 : eps);
-    const double mine = env_n(a, h + off);
+    const double mine = env_n_t<DRY>(a, h + off);
     const double n1 = __shfl_sync(gmask, mine, gbase + 0);
     const double n0 = __shfl_sync(gmask, mine, gbase + 1);
     const double n2 = __shfl_sync(gmask, mine, gbase + 2);
@@ -257,48 +257,37 @@ __device__ __forceinline__ void env_n_dn3(const DevAtmosphere& a, double h, int 
     *dn = (n2 - n1) / (2.0 * eps);
 }
 
-__device__ __forceinline__ RayState stepper_next3(Stepper& s, const DevAtmosphere& atm, int flat, double radius, double step, int role,
+// One classical RK4 step. The four derivative evaluations run through ONE copy of the code (a
+// rolled loop over the stages) so that the hot loop stays inside the instruction cache.
+template <bool FLAT, bool DRY>
+__device__ __forceinline__ RayState stepper_next3(Stepper& s, const DevAtmosphere& atm, double radius, double step, double off,
                                                   unsigned gmask, int gbase) {
-    double k1a, k1b, k2a, k2b, k3a, k3b, k4a, k4b, n, dn;
-    if (flat) {  // h'' = n'/n (1 + h'^2)
-        const double d = step;
-        double h = s.a, dh = s.b;
-        env_n_dn3(atm, h, role, gmask, gbase, &n, &dn);
-        k1a = dh, k1b = dn / n * (1.0 + dh * dh);
-        h = s.a + 0.5 * d * k1a, dh = s.b + 0.5 * d * k1b;
-        env_n_dn3(atm, h, role, gmask, gbase, &n, &dn);
-        k2a = dh, k2b = dn / n * (1.0 + dh * dh);
-        h = s.a + 0.5 * d * k2a, dh = s.b + 0.5 * d * k2b;
-        env_n_dn3(atm, h, role, gmask, gbase, &n, &dn);
-        k3a = dh, k3b = dn / n * (1.0 + dh * dh);
-        h = s.a + d * k3a, dh = s.b + d * k3b;
-        env_n_dn3(atm, h, role, gmask, gbase, &n, &dn);
-        k4a = dh, k4b = dn / n * (1.0 + dh * dh);
-        s.a = s.a + (k1a + 2.0 * k2a + 2.0 * k3a + k4a) * d / 6.0;
-        s.b = s.b + (k1b + 2.0 * k2b + 2.0 * k3b + k4b) * d / 6.0;
-        s.t += d;
-        return {s.t, s.a};
+    const double d = FLAT ? step : step / radius;
+    double a = s.a, b = s.b;      // stage input: (h, h') or (r, r')
+    // (k1 + 2 k2 + 2 k3 + k4) accumulated left to right, as the reference's expression evaluates
+    double acc_a = 0.0, acc_b = 0.0;
+#pragma unroll 1
+    for (int st = 0; st < 4; ++st) {
+        double n, dn;
+        env_n_dn3<DRY>(atm, FLAT ? a : a - radius, off, gmask, gbase, &n, &dn);
+        const double ka = b;
+        // flat: h'' = n'/n (1 + h'^2);  spherical: r'' = (n'/n)(r'^2 + r^2) + 2 r'^2 / r + r
+        const double kb = FLAT ? dn / n * (1.0 + b * b) : b * b * dn / n + a * a * dn / n + 2.0 * b * b / a + a;
+        const double wk = (st == 1 || st == 2) ? 2.0 : 1.0;  // 1.0 * k and 0.0 + k are exact
+        acc_a = acc_a + wk * ka;
+        acc_b = acc_b + wk * kb;
+        const double w = st == 2 ? 1.0 : 0.5;
+        a = s.a + w * d * ka;
+        b = s.b + w * d * kb;
     }
-    // r'' = (n'/n)(r'^2 + r^2) + 2 r'^2 / r + r, independent variable phi = x / R
-    const double d = step / radius;
-    double r = s.a, dr = s.b;
-    env_n_dn3(atm, r - radius, role, gmask, gbase, &n, &dn);
-    k1a = dr, k1b = dr * dr * dn / n + r * r * dn / n + 2.0 * dr * dr / r + r;
-    r = s.a + 0.5 * d * k1a, dr = s.b + 0.5 * d * k1b;
-    env_n_dn3(atm, r - radius, role, gmask, gbase, &n, &dn);
-    k2a = dr, k2b = dr * dr * dn / n + r * r * dn / n + 2.0 * dr * dr / r + r;
-    r = s.a + 0.5 * d * k2a, dr = s.b + 0.5 * d * k2b;
-    env_n_dn3(atm, r - radius, role, gmask, gbase, &n, &dn);
-    k3a = dr, k3b = dr * dr * dn / n + r * r * dn / n + 2.0 * dr * dr / r + r;
-    r = s.a + d * k3a, dr = s.b + d * k3b;
-    env_n_dn3(atm, r - radius, role, gmask, gbase, &n, &dn);
-    k4a = dr, k4b = dr * dr * dn / n + r * r * dn / n + 2.0 * dr * dr / r + r;
-    s.a = s.a + (k1a + 2.0 * k2a + 2.0 * k3a + k4a) * d / 6.0;
-    s.b = s.b + (k1b + 2.0 * k2b + 2.0 * k3b + k4b) * d / 6.0;
+    s.a = s.a + acc_a * d / 6.0;
+    s.b = s.b + acc_b * d / 6.0;
     s.t += d;
+    if (FLAT) return {s.t, s.a};
     return {s.t * radius, s.a - radius};
 }
 
+template <bool FLAT, bool DRY>
 __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevScene S, DevBuffers B) {
     const int lane = threadIdx.x;
     const int slot = lane / 3, role = lane - slot * 3;
@@ -306,10 +295,11 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
     if (slot >= ROWS_PER_WARP || y >= S.height) return;
     const int gbase = slot * 3;
     const unsigned gmask = 7u << gbase;
+    const double off = role == 0 ? -0.01 : (role == 1 ? 0.0 : 0.01);  // h - eps, h, h + eps
     const double alt = *B.obs_alt;
     const double ray_elev = get_ray_elev(S, y);
     Stepper st;
-    stepper_init(st, S.flat, S.radius, alt, to_radians(ray_elev));
+    stepper_init(st, FLAT, S.radius, alt, to_radians(ray_elev));
     const size_t hp = (size_t)S.h_pad;
     if (role == 1) {
         B.p_dist[y] = 0.0;
@@ -319,10 +309,23 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
     RayState prev{0.0, alt};
     double path_length = 0.0;
     int n = 1;
+    const bool straight = S.straight != 0;
+#pragma unroll 1
     for (int i = 1; i < S.n_t; ++i) {
-        RayState nw = S.straight ? stepper_next(st, S.atm, S.flat, 1, S.radius, S.step)
-                                 : stepper_next3(st, S.atm, S.flat, S.radius, S.step, role, gmask, gbase);
-        path_length += calc_dist(S.flat, S.radius, prev, nw);
+        RayState nw;
+        if (straight) {
+            nw = stepper_next(st, S.atm, FLAT, 1, S.radius, S.step);
+        } else if (st.a != st.a) {
+            // The state is NaN (the ray climbed above the altitude where the last temperature function
+            // reaches 0 K, e.g. 178 km for US-76): every later state is NaN as well, only the
+            // independent variable keeps advancing. Skip the (slow-path) arithmetic; the outputs are
+            // exactly what the full step would produce: x = t * R, h = NaN, path_length = NaN.
+            st.t += FLAT ? S.step : S.step / S.radius;
+            nw = RayState{FLAT ? st.t : st.t * S.radius, st.a};
+        } else {
+            nw = stepper_next3<FLAT, DRY>(st, S.atm, S.radius, S.step, off, gmask, gbase);
+        }
+        path_length += calc_dist(FLAT, S.radius, prev, nw);
         if (role == 1) {
             const size_t o = (size_t)i * hp + y;
             B.p_dist[o] = nw.x;

@@ -321,3 +321,26 @@ def test_errors_are_reported_not_swallowed(ctx):
             c.set_objects([o], [None])
     finally:
         c.close()
+
+
+def test_rays_leaving_the_atmosphere_model(ctx, oracle_lib):
+    """Steep rays climb past the altitude where US-76's last linear temperature function reaches 0 K;
+    n(h) is NaN from there on in the reference's arithmetic and the pixel is sky. The kernel's NaN
+    fast-forward must produce the same cache rows as the oracle's full arithmetic."""
+    p, terrain, _, _ = scene("c2", 0.1)
+    p.tilt, p.fov = 40.0, 60.0
+    p.max_distance = 400000.0
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects([])
+    got = ctx.render()
+    want = oracle_lib.render(p, terrain.tiles)
+    compare_render(got, want, "steep")
+    g, w = ctx.path(0), oracle_lib.path_cache(p, terrain.tiles, 0)
+    n = len(g["dist"])
+    assert np.isnan(w["elev"][:n]).any()
+    np.testing.assert_array_equal(np.isnan(g["elev"]), np.isnan(w["elev"][:n]))
+    np.testing.assert_array_equal(np.isnan(g["path_length"]), np.isnan(w["path_length"][:n]))
+    np.testing.assert_allclose(g["dist"], w["dist"][:n], rtol=1e-14)
+    ok = ~np.isnan(g["elev"])
+    np.testing.assert_allclose(g["elev"][ok], w["elev"][:n][ok], rtol=1e-9, atol=1e-6)
