@@ -580,8 +580,12 @@ int atmrt_create(int device, atmrt_ctx** out) {
         delete ctx;
         return fail(nullptr, ATMRT_ERR_CUDA, "cudaSetDevice failed");
     }
-    bool ok = cudaStreamCreateWithFlags(&ctx->s_a, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&ctx->s_b, cudaStreamNonBlocking) == cudaSuccess &&
+    // Stage B is a handful of latency-bound warps, stage A saturates the issue slots: give B's stream
+    // the higher priority so that its blocks are placed first.
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    bool ok = cudaStreamCreateWithPriority(&ctx->s_a, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&ctx->s_b, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking) == cudaSuccess;
     cudaEvent_t* evs[] = {&ctx->ev_prep, &ctx->ev_a, &ctx->ev_b};
     for (cudaEvent_t* ev : evs) ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
