@@ -1,0 +1,729 @@
+// gen.cpp -- the thin C++ host of the `gen` subcommand (generator/mod.rs:47-99): YAML config + CLI
+// overrides (generator/params.rs:447-777) -> flat PODs of include/atmrt.h -> the CUDA library ->
+// PNG (+ optional per-pixel metadata sidecar). The reference's host is Rust; there is no Rust
+// toolchain in this image, so the same surface is restated in C++ on top of the same C ABI a Rust
+// host would bind. Nothing here computes the hot path.
+#include <dirent.h>
+#include <sys/stat.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "atmrt_host.h"
+
+namespace atmrt_host {
+extern std::string g_error;
+int fail(int code, const std::string& msg);
+
+// ---------------------------------------------------------------------------------------------
+// A YAML subset big enough for the reference's Config (README.md:76-324): block maps and lists,
+// flow maps/lists, scalars, comments, quoted strings. serde's externally tagged enums appear as a
+// bare string (unit variant) or a single-key map.
+// ---------------------------------------------------------------------------------------------
+struct Node {
+    enum Kind { Null, Scalar, Map, Seq } kind = Null;
+    std::string scalar;
+    std::vector<std::pair<std::string, Node>> map;
+    std::vector<Node> seq;
+
+    const Node* get(const std::string& key) const {
+        if (kind != Map) return nullptr;
+        for (const auto& kv : map)
+            if (kv.first == key) return &kv.second;
+        return nullptr;
+    }
+    bool is_null() const { return kind == Null || (kind == Scalar && (scalar == "~" || scalar == "null" || scalar.empty())); }
+    double as_double(const std::string& what) const {
+        if (kind != Scalar) throw std::runtime_error(what + ": expected a number");
+        char* end = nullptr;
+        double v = strtod(scalar.c_str(), &end);
+        if (end == scalar.c_str() || *end != '\0') throw std::runtime_error(what + ": invalid number '" + scalar + "'");
+        return v;
+    }
+    bool as_bool(const std::string& what) const {
+        if (kind == Scalar && (scalar == "true" || scalar == "True")) return true;
+        if (kind == Scalar && (scalar == "false" || scalar == "False")) return false;
+        throw std::runtime_error(what + ": expected true/false");
+    }
+};
+
+struct Line {
+    int indent;
+    std::string text;  // without indentation and trailing comment
+    int number;
+};
+
+static std::string trim(const std::string& s) {
+    size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+    return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+}
+
+static std::string strip_comment(const std::string& s) {
+    bool sq = false, dq = false;
+    for (size_t i = 0; i < s.size(); ++i) {
+        char c = s[i];
+        if (c == '\'' && !dq) sq = !sq;
+        if (c == '"' && !sq) dq = !dq;
+        if (c == '#' && !sq && !dq && (i == 0 || s[i - 1] == ' ' || s[i - 1] == '\t')) return s.substr(0, i);
+    }
+    return s;
+}
+
+static std::string unquote(const std::string& s) {
+    if (s.size() >= 2 && ((s.front() == '"' && s.back() == '"') || (s.front() == '\'' && s.back() == '\''))) return s.substr(1, s.size() - 2);
+    return s;
+}
+
+// flow-style value: {a: 1, b: [2, 3]} / [..] / scalar
+struct FlowParser {
+    const std::string& s;
+    size_t i = 0;
+    explicit FlowParser(const std::string& str) : s(str) {}
+    void ws() {
+        while (i < s.size() && (s[i] == ' ' || s[i] == '\t')) ++i;
+    }
+    Node value() {
+        ws();
+        Node n;
+        if (i < s.size() && s[i] == '{') {
+            ++i;
+            n.kind = Node::Map;
+            ws();
+            if (i < s.size() && s[i] == '}') {
+                ++i;
+                return n;
+            }
+            for (;;) {
+                ws();
+                std::string key = token(":");
+                ws();
+                if (i >= s.size() || s[i] != ':') throw std::runtime_error("flow map: expected ':' after '" + key + "'");
+                ++i;
+                Node v = value();
+                n.map.emplace_back(unquote(trim(key)), v);
+                ws();
+                if (i < s.size() && s[i] == ',') {
+                    ++i;
+                    continue;
+                }
+                if (i < s.size() && s[i] == '}') {
+                    ++i;
+                    return n;
+                }
+                throw std::runtime_error("flow map: expected ',' or '}'");
+            }
+        }
+        if (i < s.size() && s[i] == '[') {
+            ++i;
+            n.kind = Node::Seq;
+            ws();
+            if (i < s.size() && s[i] == ']') {
+                ++i;
+                return n;
+            }
+            for (;;) {
+                n.seq.push_back(value());
+                ws();
+                if (i < s.size() && s[i] == ',') {
+                    ++i;
+                    continue;
+                }
+                if (i < s.size() && s[i] == ']') {
+                    ++i;
+                    return n;
+                }
+                throw std::runtime_error("flow list: expected ',' or ']'");
+            }
+        }
+        std::string t = trim(token(",}]"));
+        if (t.empty() || t == "~" || t == "null") return n;
+        n.kind = Node::Scalar;
+        n.scalar = unquote(t);
+        return n;
+    }
+    std::string token(const char* stops) {
+        size_t a = i;
+        bool sq = false, dq = false;
+        while (i < s.size()) {
+            char c = s[i];
+            if (c == '\'' && !dq) sq = !sq;
+            if (c == '"' && !sq) dq = !dq;
+            if (!sq && !dq && strchr(stops, c)) break;
+            ++i;
+        }
+        return s.substr(a, i - a);
+    }
+};
+
+static Node parse_inline(const std::string& text) {
+    std::string t = trim(text);
+    FlowParser fp(t);
+    Node n = fp.value();
+    fp.ws();
+    if (fp.i != t.size()) {  // a plain scalar containing ',' etc.
+        Node s;
+        s.kind = Node::Scalar;
+        s.scalar = unquote(t);
+        return s;
+    }
+    return n;
+}
+
+// position of the ':' that separates key and value in a block-map line (or npos)
+static size_t key_colon(const std::string& t) {
+    bool sq = false, dq = false;
+    int depth = 0;
+    for (size_t i = 0; i < t.size(); ++i) {
+        char c = t[i];
+        if (c == '\'' && !dq) sq = !sq;
+        if (c == '"' && !sq) dq = !dq;
+        if (sq || dq) continue;
+        if (c == '{' || c == '[') ++depth;
+        if (c == '}' || c == ']') --depth;
+        if (c == ':' && depth == 0 && (i + 1 == t.size() || t[i + 1] == ' ')) return i;
+    }
+    return std::string::npos;
+}
+
+struct BlockParser {
+    std::vector<Line> lines;
+    size_t pos = 0;
+
+    Node block(int indent) {
+        Node n;
+        if (pos >= lines.size() || lines[pos].indent < indent) return n;
+        const int ind = lines[pos].indent;
+        if (lines[pos].text.rfind("- ", 0) == 0 || lines[pos].text == "-") {
+            n.kind = Node::Seq;
+            while (pos < lines.size() && lines[pos].indent == ind && (lines[pos].text.rfind("- ", 0) == 0 || lines[pos].text == "-")) {
+                std::string rest = lines[pos].text.size() > 2 ? trim(lines[pos].text.substr(2)) : std::string();
+                const int child = ind + 2;
+                if (rest.empty()) {
+                    ++pos;
+                    n.seq.push_back(block(ind + 1));
+                } else if (key_colon(rest) != std::string::npos && rest[0] != '{' && rest[0] != '[') {
+                    // "- key: value" starts a map whose other keys follow at the same column as `key`
+                    lines[pos].indent = child;
+                    lines[pos].text = rest;
+                    n.seq.push_back(block(child));
+                } else {
+                    ++pos;
+                    n.seq.push_back(parse_inline(rest));
+                }
+            }
+            return n;
+        }
+        n.kind = Node::Map;
+        while (pos < lines.size() && lines[pos].indent == ind) {
+            const std::string& t = lines[pos].text;
+            size_t c = key_colon(t);
+            if (c == std::string::npos) throw std::runtime_error("line " + std::to_string(lines[pos].number) + ": expected 'key: value'");
+            std::string key = unquote(trim(t.substr(0, c)));
+            std::string rest = trim(t.substr(c + 1));
+            ++pos;
+            if (rest.empty()) {
+                if (pos < lines.size() && lines[pos].indent > ind)
+                    n.map.emplace_back(key, block(lines[pos].indent));
+                else if (pos < lines.size() && lines[pos].indent == ind && lines[pos].text.rfind("- ", 0) == 0)
+                    n.map.emplace_back(key, block(ind));  // list at the same indentation as its key
+                else
+                    n.map.emplace_back(key, Node());
+            } else {
+                n.map.emplace_back(key, parse_inline(rest));
+            }
+        }
+        if (pos < lines.size() && lines[pos].indent > ind) throw std::runtime_error("line " + std::to_string(lines[pos].number) + ": bad indentation");
+        return n;
+    }
+};
+
+static Node parse_yaml(const std::string& text) {
+    BlockParser bp;
+    size_t a = 0;
+    int number = 0;
+    while (a <= text.size()) {
+        size_t b = text.find('\n', a);
+        if (b == std::string::npos) b = text.size();
+        std::string raw = text.substr(a, b - a);
+        a = b + 1;
+        ++number;
+        std::string nc = strip_comment(raw);
+        std::string t = trim(nc);
+        if (t.empty() || t == "---") continue;
+        int indent = 0;
+        while (indent < (int)nc.size() && nc[indent] == ' ') ++indent;
+        bp.lines.push_back({indent, t, number});
+    }
+    if (bp.lines.empty()) return Node();
+    Node n = bp.block(bp.lines[0].indent);
+    if (bp.pos != bp.lines.size()) throw std::runtime_error("line " + std::to_string(bp.lines[bp.pos].number) + ": unexpected content");
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Config (generator/params.rs:447-494) with the reference's defaults
+// ---------------------------------------------------------------------------------------------
+struct ConfObject {
+    atmrt_object o{};
+    std::string texture_path;
+};
+
+struct Config {
+    std::string terrain_folder = "./terrain";
+    std::vector<ConfObject> objects;
+    double terrain_alpha = 1.0;
+    double latitude = 0.0, longitude = 0.0;
+    atmrt_altitude altitude{ATMRT_ALT_RELATIVE, 0, 1.0};
+    double direction = 0.0, tilt = 0.0, fov = 30.0, max_distance = 150000.0;
+    int coloring = ATMRT_COLORING_SHADING, palette = ATMRT_PALETTE_IMPROVED;
+    double water_level = 0.0, ambient_light = 0.4, light_zenith_angle = 45.0, light_dir = 0.0;
+    bool fog = false;
+    double fog_distance = 0.0;
+    atmrt_atmosphere_def atmosphere{};
+    int earth_model = ATMRT_EARTH_SPHERICAL;
+    double radius = 6371000.0;
+    double wavelength = 530e-9;
+    bool straight_rays = false;
+    double simulation_step = 50.0;
+    std::string file = "./output.png", file_metadata;
+    int width = 640, height = 480;
+};
+
+static atmrt_atmosphere_def us_76() {  // AtmosphereDef::us_76() (params.rs:453)
+    atmrt_atmosphere_def a{};
+    a.pressure_altitude = 0.0, a.pressure = 101325.0, a.temperature_altitude = 0.0, a.temperature = 288.15, a.humidity = 0.0;
+    const double starts[] = {0.0, 11000.0, 20000.0, 32000.0, 47000.0, 51000.0, 71000.0};
+    const double grads[] = {-0.0065, 0.0, 0.001, 0.0028, 0.0, -0.0028, -0.002};
+    a.n_functions = 7;
+    for (int i = 0; i < 7; ++i) a.fn_start_altitude[i] = starts[i], a.fn_gradient[i] = grads[i];
+    return a;
+}
+
+static void tagged(const Node& n, const std::string& what, std::string* tag, const Node** body) {
+    static const Node empty;
+    if (n.kind == Node::Scalar) {
+        *tag = n.scalar;
+        *body = &empty;
+        return;
+    }
+    if (n.kind == Node::Map && n.map.size() == 1) {
+        *tag = n.map[0].first;
+        *body = &n.map[0].second;
+        return;
+    }
+    throw std::runtime_error("invalid " + what);
+}
+
+static atmrt_altitude parse_altitude(const Node& n) {
+    std::string tag;
+    const Node* body;
+    tagged(n, "altitude", &tag, &body);
+    atmrt_altitude a{};
+    if (tag == "Absolute")
+        a.kind = ATMRT_ALT_ABSOLUTE;
+    else if (tag == "Relative")
+        a.kind = ATMRT_ALT_RELATIVE;
+    else
+        throw std::runtime_error("unknown altitude kind " + tag);
+    a.value = body->as_double("altitude");
+    return a;
+}
+
+static double num(const Node& m, const char* key, double def) {
+    const Node* n = m.get(key);
+    return n && !n->is_null() ? n->as_double(key) : def;
+}
+
+static void parse_position(const Node& n, double* lat, double* lon, atmrt_altitude* alt) {
+    *lat = num(n, "latitude", 0.0);
+    *lon = num(n, "longitude", 0.0);
+    if (const Node* a = n.get("altitude")) *alt = parse_altitude(*a);
+}
+
+static void apply_yaml(const Node& doc, Config* c) {
+    if (doc.kind == Node::Null) return;
+    if (doc.kind != Node::Map) throw std::runtime_error("config: top level must be a map");
+    if (const Node* scene = doc.get("scene")) {
+        if (const Node* t = scene->get("terrain_folder")) c->terrain_folder = t->scalar;
+        c->terrain_alpha = num(*scene, "terrain_alpha", c->terrain_alpha);
+        if (const Node* objs = scene->get("objects")) {
+            if (objs->kind != Node::Seq && !objs->is_null()) throw std::runtime_error("scene.objects must be a list");
+            for (const Node& on : objs->seq) {
+                ConfObject co;
+                co.o.altitude = atmrt_altitude{ATMRT_ALT_RELATIVE, 0, 1.0};
+                const Node* pos = on.get("position");
+                const Node* shape = on.get("shape");
+                if (!pos || !shape) throw std::runtime_error("object needs position and shape");
+                parse_position(*pos, &co.o.latitude, &co.o.longitude, &co.o.altitude);
+                co.o.color[0] = co.o.color[1] = co.o.color[2] = co.o.color[3] = 1.0;
+                if (const Node* col = on.get("color")) {
+                    co.o.color[0] = num(*col, "r", 1.0), co.o.color[1] = num(*col, "g", 1.0), co.o.color[2] = num(*col, "b", 1.0);
+                    co.o.color[3] = num(*col, "a", 1.0);  // default_alpha, object/mod.rs:147-156
+                }
+                std::string tag;
+                const Node* body;
+                tagged(*shape, "shape", &tag, &body);
+                if (tag == "Cylinder") {  // ConfShape::into_shape, object/mod.rs:41-54
+                    co.o.kind = ATMRT_OBJECT_FRUSTUM;
+                    co.o.r1 = co.o.r2 = num(*body, "radius", 0.0);
+                    co.o.height = num(*body, "height", 0.0);
+                } else if (tag == "Cone") {
+                    co.o.kind = ATMRT_OBJECT_FRUSTUM;
+                    co.o.r1 = num(*body, "radius", 0.0), co.o.r2 = 0.0, co.o.height = num(*body, "height", 0.0);
+                } else if (tag == "Frustum") {
+                    co.o.kind = ATMRT_OBJECT_FRUSTUM;
+                    co.o.r1 = num(*body, "r1", 0.0), co.o.r2 = num(*body, "r2", 0.0), co.o.height = num(*body, "height", 0.0);
+                } else if (tag == "Billboard") {
+                    co.o.kind = ATMRT_OBJECT_BILLBOARD;
+                    co.o.width = num(*body, "width", 0.0), co.o.height = num(*body, "height", 0.0);
+                    const Node* tp = body->get("texture_path");
+                    if (!tp) throw std::runtime_error("Billboard needs texture_path");
+                    co.texture_path = tp->scalar;
+                } else {
+                    throw std::runtime_error("unknown shape " + tag);
+                }
+                c->objects.push_back(co);
+            }
+        }
+    }
+    if (const Node* view = doc.get("view")) {
+        if (const Node* pos = view->get("position")) parse_position(*pos, &c->latitude, &c->longitude, &c->altitude);
+        if (const Node* fr = view->get("frame")) {
+            c->direction = num(*fr, "direction", c->direction), c->tilt = num(*fr, "tilt", c->tilt);
+            c->fov = num(*fr, "fov", c->fov), c->max_distance = num(*fr, "max_distance", c->max_distance);
+        }
+        if (const Node* col = view->get("coloring")) {
+            std::string tag;
+            const Node* body;
+            tagged(*col, "coloring", &tag, &body);
+            c->water_level = num(*body, "water_level", 0.0);
+            if (tag == "Simple") {
+                c->coloring = ATMRT_COLORING_SIMPLE;
+            } else if (tag == "Shading") {
+                c->coloring = ATMRT_COLORING_SHADING;
+                c->ambient_light = num(*body, "ambient_light", 0.4);
+                c->light_zenith_angle = num(*body, "light_zenith_angle", 45.0);
+                c->light_dir = num(*body, "light_dir", 0.0);
+                if (const Node* pal = body->get("palette")) {
+                    if (pal->scalar == "Legacy")
+                        c->palette = ATMRT_PALETTE_LEGACY;
+                    else if (pal->scalar == "Improved")
+                        c->palette = ATMRT_PALETTE_IMPROVED;
+                    else
+                        throw std::runtime_error("unknown palette " + pal->scalar);
+                }
+            } else {
+                throw std::runtime_error("unknown coloring " + tag);
+            }
+        }
+        if (const Node* fog = view->get("fog_distance")) {
+            c->fog = !fog->is_null();
+            if (c->fog) c->fog_distance = fog->as_double("fog_distance");
+        }
+    }
+    if (const Node* atm = doc.get("atmosphere")) {
+        if (!atm->is_null()) {
+            atmrt_atmosphere_def a{};
+            const Node* pr = atm->get("pressure");
+            const Node* first = atm->get("first_temperature_function");
+            if (!pr || !first) throw std::runtime_error("atmosphere needs pressure and first_temperature_function");
+            a.pressure_altitude = num(*pr, "altitude", 0.0), a.pressure = num(*pr, "pressure", 101325.0);
+            a.humidity = num(*atm, "humidity", 0.0);
+            std::vector<std::pair<double, const Node*>> fns{{0.0, first}};
+            if (const Node* next = atm->get("next_functions"))
+                for (const Node& nf : next->seq) {
+                    const Node* fn = nf.get("function");
+                    if (!fn) throw std::runtime_error("next_functions entry needs altitude and function");
+                    fns.emplace_back(num(nf, "altitude", 0.0), fn);
+                }
+            if ((int)fns.size() > ATMRT_MAX_ATM_FUNCTIONS) throw std::runtime_error("too many temperature functions");
+            a.n_functions = (int)fns.size();
+            for (size_t i = 0; i < fns.size(); ++i) {
+                std::string tag;
+                const Node* body;
+                tagged(*fns[i].second, "temperature function", &tag, &body);
+                if (tag != "Linear") throw std::runtime_error("Spline temperature functions are not supported by the device path yet");
+                a.fn_start_altitude[i] = fns[i].first;
+                a.fn_gradient[i] = num(*body, "gradient", 0.0);
+            }
+            const Node* tfp = atm->get("temperature_fixed_point");
+            if (!tfp) throw std::runtime_error("temperature_fixed_point is required when every function is Linear");
+            a.temperature_altitude = num(*tfp, "altitude", 0.0), a.temperature = num(*tfp, "temperature", 288.15);
+            c->atmosphere = a;
+        }
+    }
+    if (const Node* es = doc.get("earth_shape")) {
+        std::string tag;
+        const Node* body;
+        tagged(*es, "earth_shape", &tag, &body);
+        if (tag == "Spherical")
+            c->earth_model = ATMRT_EARTH_SPHERICAL, c->radius = num(*body, "radius", 6371000.0);
+        else if (tag == "SimpleSphere")
+            c->earth_model = ATMRT_EARTH_SPHERICAL, c->radius = 6371000.0;
+        else if (tag == "FlatDistorted")
+            c->earth_model = ATMRT_EARTH_FLAT_DISTORTED;
+        else
+            throw std::runtime_error("earth_shape " + tag + " is outside the device path (Spherical, SimpleSphere, FlatDistorted)");
+    }
+    c->wavelength = num(doc, "wavelength", c->wavelength);
+    if (const Node* s = doc.get("straight_rays")) c->straight_rays = s->as_bool("straight_rays");
+    c->simulation_step = num(doc, "simulation_step", c->simulation_step);
+    if (const Node* out = doc.get("output")) {
+        if (const Node* f = out->get("file")) c->file = f->scalar;
+        if (const Node* f = out->get("file_metadata"))
+            if (!f->is_null()) c->file_metadata = f->scalar;
+        c->width = (int)num(*out, "width", c->width), c->height = (int)num(*out, "height", c->height);
+        if (const Node* g = out->get("generator"))
+            if (g->scalar != "Fast") throw std::runtime_error("generator " + g->scalar + " is outside the device path (Fast only)");
+        for (const char* k : {"ticks", "vertical_ticks"})
+            if (const Node* t = out->get(k))
+                if (t->kind == Node::Seq && !t->seq.empty()) fprintf(stderr, "warning: output.%s is ignored (overlays are out of scope)\n", k);
+    }
+}
+
+static std::string read_file(const std::string& path) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("cannot open " + path);
+    std::string s;
+    char buf[65536];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) s.append(buf, n);
+    fclose(f);
+    return s;
+}
+
+// read_config (params.rs:694-777): YAML first, then the CLI flags.
+static Config read_config(int argc, const char* const* argv) {
+    Config c;
+    c.atmosphere = us_76();
+    std::map<std::string, std::string> val;
+    std::map<std::string, bool> flag;
+    const std::map<std::string, std::string> takes = {
+        {"-c", "config"}, {"--config", "config"}, {"-t", "terrain"}, {"--terrain", "terrain"}, {"-l", "lat"}, {"--lat", "lat"},
+        {"-g", "lon"}, {"--lon", "lon"}, {"-a", "alt"}, {"--alt", "alt"}, {"-e", "elev"}, {"--elev", "elev"}, {"-d", "dir"},
+        {"--dir", "dir"}, {"-f", "fov"}, {"--fov", "fov"}, {"-i", "tilt"}, {"--tilt", "tilt"}, {"-m", "maxdist"},
+        {"--maxdist", "maxdist"}, {"--step", "step"}, {"-R", "radius"}, {"--radius", "radius"}, {"--output", "output"},
+        {"--output-meta", "output-meta"}, {"-w", "width"}, {"--width", "width"}, {"-h", "height"}, {"--height", "height"}};
+    const std::map<std::string, std::string> flags = {{"--flat", "flat"}, {"-s", "straight"}, {"--straight", "straight"}};
+    for (int i = 0; i < argc; ++i) {
+        std::string a = argv[i];
+        auto t = takes.find(a);
+        if (t != takes.end()) {
+            if (i + 1 >= argc) throw std::runtime_error("missing value for " + a);
+            val[t->second] = argv[++i];  // AllowLeadingHyphen: negative numbers are values (params.rs:533)
+            continue;
+        }
+        auto f = flags.find(a);
+        if (f != flags.end()) {
+            flag[f->second] = true;
+            continue;
+        }
+        throw std::runtime_error("unknown argument " + a);
+    }
+    if (val.count("alt") && val.count("elev")) throw std::runtime_error("--alt conflicts with --elev");
+    if (flag.count("flat") && val.count("radius")) throw std::runtime_error("--flat conflicts with --radius");
+    if (val.count("config")) apply_yaml(parse_yaml(read_file(val["config"])), &c);
+    auto d = [&](const char* k) { return strtod(val[k].c_str(), nullptr); };
+    if (val.count("terrain")) c.terrain_folder = val["terrain"];
+    if (val.count("output")) c.file = val["output"];
+    if (val.count("output-meta")) c.file_metadata = val["output-meta"];
+    if (val.count("width")) c.width = atoi(val["width"].c_str());
+    if (val.count("height")) c.height = atoi(val["height"].c_str());
+    if (val.count("lat")) c.latitude = d("lat");
+    if (val.count("lon")) c.longitude = d("lon");
+    if (val.count("alt")) c.altitude = atmrt_altitude{ATMRT_ALT_ABSOLUTE, 0, d("alt")};
+    if (val.count("elev")) c.altitude = atmrt_altitude{ATMRT_ALT_RELATIVE, 0, d("elev")};
+    if (val.count("dir")) c.direction = d("dir");
+    if (val.count("fov")) c.fov = d("fov");
+    if (val.count("tilt")) c.tilt = d("tilt");
+    if (val.count("maxdist")) c.max_distance = d("maxdist") * 1e3;  // km on the CLI (params.rs:751-754)
+    if (val.count("step")) c.simulation_step = d("step");
+    if (flag.count("flat")) c.earth_model = ATMRT_EARTH_FLAT_DISTORTED;
+    if (val.count("radius")) c.earth_model = ATMRT_EARTH_SPHERICAL, c.radius = d("radius") * 1e3;  // km (params.rs:764-767)
+    if (flag.count("straight")) c.straight_rays = true;
+    return c;
+}
+
+// ConfColoring::into_coloring light vector (params.rs:243-259); host libm like the reference.
+static void light_direction(const Config& c, double out[3]) {
+    const double PI = 3.14159265358979323846;
+    auto rad = [&](double d) { return d * (PI / 180.0); };
+    double zen = rad(c.light_zenith_angle), ld = rad(c.light_dir);
+    double lon = rad(c.longitude), lat = rad(c.latitude);
+    double sinlon = std::sin(lon), coslon = std::cos(lon);
+    double north[3], east[3], up[3];
+    if (c.earth_model == ATMRT_EARTH_FLAT_DISTORTED) {
+        north[0] = -coslon, north[1] = -sinlon, north[2] = 0.0;
+        east[0] = -sinlon, east[1] = coslon, east[2] = 0.0;
+        up[0] = 0.0, up[1] = 0.0, up[2] = 1.0;
+    } else {
+        double sinlat = std::sin(lat), coslat = std::cos(lat);
+        up[0] = coslat * coslon, up[1] = coslat * sinlon, up[2] = sinlat;
+        north[0] = -sinlat * coslon, north[1] = -sinlat * sinlon, north[2] = coslat;
+        east[0] = -sinlon, east[1] = coslon, east[2] = 0.0;
+    }
+    double az = rad(c.direction);
+    double v[3];
+    for (int i = 0; i < 3; ++i) {
+        double front = north[i] * std::cos(az) + east[i] * std::sin(az);
+        double right = east[i] * std::cos(az) - north[i] * std::sin(az);
+        v[i] = -front * std::sin(zen) * std::cos(ld) + right * std::sin(zen) * std::sin(ld) + up[i] * std::cos(zen);
+    }
+    double n = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    for (int i = 0; i < 3; ++i) out[i] = v[i] / n;
+}
+
+static atmrt_params into_params(const Config& c) {
+    atmrt_params p{};
+    p.latitude = c.latitude, p.longitude = c.longitude, p.altitude = c.altitude;
+    p.direction = c.direction, p.tilt = c.tilt, p.fov = c.fov, p.max_distance = c.max_distance;
+    p.earth_model = c.earth_model, p.straight_rays = c.straight_rays ? 1 : 0, p.radius = c.radius;
+    p.wavelength = c.wavelength, p.simulation_step = c.simulation_step, p.atmosphere = c.atmosphere;
+    p.terrain_alpha = c.terrain_alpha;
+    p.coloring = c.coloring, p.water_level = c.water_level;
+    if (c.coloring == ATMRT_COLORING_SHADING) {  // Coloring::Simple carries none of these (params.rs:215-227)
+        p.palette = c.palette, p.ambient_light = c.ambient_light;
+        light_direction(c, p.light_dir);
+    }
+    if (c.earth_model != ATMRT_EARTH_SPHERICAL) p.radius = 0.0;
+    p.simple_max_distance = c.max_distance;
+    p.fog_enabled = c.fog ? 1 : 0, p.fog_distance = c.fog_distance;
+    p.width = c.width, p.height = c.height, p.x0 = 0, p.x1 = c.width;
+    return p;
+}
+
+static bool write_metadata(const std::string& path, const atmrt_params& p, const std::vector<atmrt_meta>& meta) {
+    // Own sidecar format (the reference's gzip(bincode(AllData)) depends on serde layouts of external
+    // crates -- SURVEY section 8 f2): gzip of "ATMRTMETA1\n", i32 width, i32 height, then
+    // width*height records of 4 little-endian f64 (lat, lon, elevation, distance; NaN = no hit).
+    gzFile f = gzopen(path.c_str(), "wb6");
+    if (!f) return false;
+    const char magic[] = "ATMRTMETA1\n";
+    int32_t wh[2] = {p.width, p.height};
+    bool ok = gzwrite(f, magic, sizeof(magic) - 1) > 0 && gzwrite(f, wh, sizeof wh) > 0;
+    const char* data = (const char*)meta.data();
+    size_t left = meta.size() * sizeof(atmrt_meta);
+    while (ok && left > 0) {
+        unsigned chunk = (unsigned)std::min<size_t>(left, 1u << 30);
+        ok = gzwrite(f, data, chunk) == (int)chunk;
+        data += chunk, left -= chunk;
+    }
+    return gzclose(f) == Z_OK && ok;
+}
+
+}  // namespace atmrt_host
+
+using namespace atmrt_host;
+
+extern "C" int atmrt_host_gen(int argc, const char* const* argv) {
+    const auto start = std::chrono::steady_clock::now();
+    auto t = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count(); };
+    atmrt_ctx* ctx = nullptr;
+    try {
+        Config c = read_config(argc, argv);
+        printf("%.3f: Using terrain data directory: \"%s\"\n", t(), c.terrain_folder.c_str());
+        // Terrain::from_folder (terrain/mod.rs:66-83): every entry must be a terrain file
+        std::vector<atmrt_tile_desc> descs;
+        std::vector<std::vector<int16_t>> posts;
+        DIR* dir = opendir(c.terrain_folder.c_str());
+        if (!dir) throw std::runtime_error("Error opening the terrain data directory " + c.terrain_folder);
+        std::vector<std::string> names;
+        while (dirent* e = readdir(dir)) {
+            std::string n = e->d_name;
+            if (n != "." && n != "..") names.push_back(n);
+        }
+        closedir(dir);
+        std::sort(names.begin(), names.end());
+        for (const std::string& n : names) {
+            std::string path = c.terrain_folder + "/" + n;
+            atmrt_tile_desc d{};
+            if (atmrt_host_read_dted(path.c_str(), &d, nullptr, 0) != 0) throw std::runtime_error("Could not buffer terrain file " + path);
+            std::vector<int16_t> buf((size_t)d.nlon * d.nlat);
+            if (atmrt_host_read_dted(path.c_str(), &d, buf.data(), buf.size()) != 0) throw std::runtime_error(g_error);
+            descs.push_back(d);
+            posts.push_back(std::move(buf));
+        }
+        printf("Detected %zu terrain files\n", names.size());
+
+        atmrt_params p = into_params(c);
+        std::vector<atmrt_object> objects;
+        std::vector<std::vector<uint8_t>> textures(c.objects.size());
+        std::vector<const uint8_t*> tex_ptrs(c.objects.size(), nullptr);
+        for (size_t i = 0; i < c.objects.size(); ++i) {
+            atmrt_object o = c.objects[i].o;
+            if (o.kind == ATMRT_OBJECT_BILLBOARD) {  // texture path joined onto cwd (object/mod.rs:60-61)
+                int w = 0, h = 0;
+                if (atmrt_host_read_png(c.objects[i].texture_path.c_str(), nullptr, 0, &w, &h) != 0) throw std::runtime_error(g_error);
+                textures[i].resize((size_t)w * h * 4);
+                if (atmrt_host_read_png(c.objects[i].texture_path.c_str(), textures[i].data(), textures[i].size(), &w, &h) != 0)
+                    throw std::runtime_error(g_error);
+                o.texture_width = w, o.texture_height = h;
+                tex_ptrs[i] = textures[i].data();
+            }
+            objects.push_back(o);
+        }
+
+        auto check = [&](int rc, const char* what) {
+            if (rc != 0) throw std::runtime_error(std::string(what) + ": " + atmrt_last_error(ctx));
+        };
+        check(atmrt_create(0, &ctx), "atmrt_create");
+        std::vector<const int16_t*> post_ptrs;
+        for (auto& v : posts) post_ptrs.push_back(v.data());
+        check(atmrt_set_terrain(ctx, descs.data(), (int)descs.size(), post_ptrs.data()), "atmrt_set_terrain");
+        check(atmrt_set_params(ctx, &p), "atmrt_set_params");
+        check(atmrt_set_objects(ctx, objects.data(), (int)objects.size(), tex_ptrs.data()), "atmrt_set_objects");
+        printf("%.3f: Generating terrain cache...\n%.3f: Generating path cache...\n%.3f: Calculating pixels...\n", t(), t(), t());
+        std::vector<uint8_t> rgb((size_t)p.width * p.height * 3);
+        std::vector<atmrt_meta> meta;
+        if (!c.file_metadata.empty()) meta.resize((size_t)p.width * p.height);
+        atmrt_stats st{};
+        check(atmrt_render(ctx, rgb.data(), meta.empty() ? nullptr : meta.data(), nullptr, &st), "atmrt_render");
+        printf("%.3f: Done calculating (terrain %.2f ms, paths %.2f ms, march %.2f ms on the GPU; %llu ray steps, %llu pixels hit)\n", t(),
+               st.ms_terrain, st.ms_paths, st.ms_march, (unsigned long long)st.ray_steps, (unsigned long long)st.pixels_hit);
+        printf("%.3f: Outputting image...\n", t());
+        if (atmrt_host_write_png(c.file.c_str(), rgb.data(), p.width, p.height, 3) != 0) throw std::runtime_error(g_error);
+        if (!c.file_metadata.empty()) {
+            printf("%.3f: Outputting metadata...\n", t());
+            if (!write_metadata(c.file_metadata, p, meta)) throw std::runtime_error("cannot write " + c.file_metadata);
+        }
+        printf("%.3f: Done.\n", t());
+        atmrt_destroy(ctx);
+        return 0;
+    } catch (const std::exception& e) {
+        if (ctx) atmrt_destroy(ctx);
+        fail(ATMRT_ERR_INVALID, e.what());
+        fprintf(stderr, "ERROR: %s\n", e.what());  // main.rs:36-38
+        return 1;
+    }
+}
+
+// Parse-only entry for tests: YAML + CLI -> params/objects, no GPU needed.
+extern "C" int atmrt_host_parse_config(int argc, const char* const* argv, atmrt_params* params, atmrt_object* objects, int max_objects,
+                                       int* nobjects, char* terrain_folder, size_t folder_cap, char* output_file, size_t file_cap,
+                                       char* meta_file, size_t meta_cap) {
+    try {
+        Config c = read_config(argc, argv);
+        if (params) *params = into_params(c);
+        if (nobjects) *nobjects = (int)c.objects.size();
+        for (int i = 0; objects && i < max_objects && i < (int)c.objects.size(); ++i) objects[i] = c.objects[i].o;
+        auto put = [](char* dst, size_t cap, const std::string& s) {
+            if (dst && cap) snprintf(dst, cap, "%s", s.c_str());
+        };
+        put(terrain_folder, folder_cap, c.terrain_folder);
+        put(output_file, file_cap, c.file);
+        put(meta_file, meta_cap, c.file_metadata);
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(ATMRT_ERR_INVALID, e.what());
+    }
+}

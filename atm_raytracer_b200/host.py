@@ -25,9 +25,11 @@ def _load():
     lib.atmrt_host_read_png.restype = C.c_int
     lib.atmrt_host_read_png.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.atmrt_host_last_error.restype = C.c_char_p
-    if hasattr(lib, "atmrt_host_gen"):
-        lib.atmrt_host_gen.restype = C.c_int
-        lib.atmrt_host_gen.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    lib.atmrt_host_gen.restype = C.c_int
+    lib.atmrt_host_gen.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    lib.atmrt_host_parse_config.restype = C.c_int
+    lib.atmrt_host_parse_config.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(abi.Params), C.POINTER(abi.Object), C.c_int,
+                                            C.POINTER(C.c_int), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
     return lib
 
 
@@ -71,3 +73,18 @@ def gen(argv):
     """Run the C++ `gen` subcommand in-process; returns its exit code."""
     arr = (C.c_char_p * len(argv))(*[os.fsencode(a) for a in argv])
     return lib.atmrt_host_gen(len(argv), arr)
+
+
+def parse_config(argv, max_objects=64):
+    """`read_config` + `Config::into_params` of the C++ host (YAML subset parser + CLI overrides) without
+    touching the GPU: returns (Params, [Object], terrain_folder, output_file, metadata_file)."""
+    arr = (C.c_char_p * len(argv))(*[os.fsencode(a) for a in argv])
+    p = abi.Params()
+    objs = (abi.Object * max_objects)()
+    n = C.c_int()
+    folder, out, meta = (C.create_string_buffer(4096) for _ in range(3))
+    _check(lib.atmrt_host_parse_config(len(argv), arr, C.byref(p), objs, max_objects, C.byref(n), folder, 4096, out, 4096, meta, 4096))
+    return p, list(objs[: n.value]), folder.value.decode(), out.value.decode(), meta.value.decode()
+
+
+EXECUTABLE = os.path.join(_HERE, "atm-raytracer")

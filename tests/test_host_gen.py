@@ -1,0 +1,181 @@
+"""The thin C++ host of `gen` (csrc/host/gen.cpp; generator/mod.rs:47-99, generator/params.rs:447-777):
+its hand-written YAML-subset parser + CLI overrides must lower to the same flat `atmrt_params` as the
+Python mirror (PyYAML + argparse), and the executable must render the same image as the library."""
+import ctypes as C
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from atm_raytracer_b200 import abi, config, host, synth
+from test_config import YAML
+
+BLOCK_YAML = """
+# block style, comments, quoted strings, list at the key's indentation
+scene:
+  terrain_folder: "./my terrain"   # trailing comment
+  objects:
+  - position:
+      latitude: 45.1
+      longitude: 6.0
+      altitude:
+        Relative: 0.0
+    shape:
+      Cylinder:
+        radius: 60.0
+        height: 900.0
+    color:
+      r: 0.9
+      g: 0.1
+      b: 0.1
+  - position: {latitude: 45.2, longitude: 6.1, altitude: {Absolute: 1500.0}}
+    shape:
+      Frustum: {r1: 500.0, r2: 200.0, height: 2500.0}
+    color: {r: 1.0, g: 1.0, b: 1.0, a: 0.25}
+view:
+  position:
+    latitude: 45.05
+    longitude: 6.0
+  frame:
+    fov: 20
+    max_distance: 1.2e5
+  coloring:
+    Simple:
+      water_level: 2.0
+atmosphere:
+  pressure: {altitude: 0.0, pressure: 101325.0}
+  temperature_fixed_point: {altitude: 0.0, temperature: 283.0}
+  first_temperature_function:
+    Linear: {gradient: 0.01}
+  next_functions:
+    - altitude: 300.0
+      function:
+        Linear:
+          gradient: -0.0065
+earth_shape:
+  Spherical:
+    radius: 6400000.0
+wavelength: 600e-9
+output:
+  width: 320
+  height: 200
+"""
+
+
+def _fields(s, skip=()):
+    out = {}
+    for name, _ in s._fields_:
+        if name.startswith("_") or name in skip:
+            continue
+        v = getattr(s, name)
+        if isinstance(v, C.Structure):
+            out[name] = _fields(v)
+        elif isinstance(v, C.Array):
+            out[name] = list(v)
+        else:
+            out[name] = v
+    return out
+
+
+def _same_params(a, b):
+    fa, fb = _fields(a), _fields(b)
+    la, lb = fa.pop("light_dir"), fb.pop("light_dir")
+    np.testing.assert_allclose(la, lb, atol=1e-15)  # host libm on both sides, different expression grouping
+    # unused tail of the fixed-size atmosphere arrays
+    n = fa["atmosphere"]["n_functions"]
+    for f in (fa, fb):
+        for k in ("fn_start_altitude", "fn_gradient"):
+            f["atmosphere"][k] = f["atmosphere"][k][:n]
+        f["atmosphere"]["fn_start_altitude"][0] = 0.0
+        if f["earth_model"] == abi.EARTH_FLAT_DISTORTED:
+            f["radius"] = 0.0  # unused by the flat model
+    assert fa == fb
+
+
+@pytest.mark.parametrize("text", [YAML, BLOCK_YAML], ids=["flow", "block"])
+def test_cpp_yaml_parser_matches_pyyaml(tmp_path, text):
+    f = tmp_path / "c.yaml"
+    f.write_text(text)
+    argv = ["-c", str(f)]
+    p_cpp, objs_cpp, folder, out, meta = host.parse_config(argv)
+    cfg = config.read_config(argv)
+    _same_params(p_cpp, config.into_params(cfg))
+    objs_py, _ = config.lower_objects(cfg)
+    assert len(objs_cpp) == len(objs_py)
+    for a, b in zip(objs_cpp, objs_py):
+        assert _fields(a, skip=("texture_width", "texture_height")) == _fields(b, skip=("texture_width", "texture_height"))
+    assert folder == cfg["scene"]["terrain_folder"] and out == cfg["output"]["file"]
+    assert meta == (cfg["output"].get("file_metadata") or "")
+
+
+def test_cpp_cli_overrides_match_the_mirror(tmp_path):
+    f = tmp_path / "c.yaml"
+    f.write_text(YAML)
+    argv = ["-c", str(f), "-m", "100", "-R", "7000", "-w", "320", "-h", "200", "-e", "12", "-s", "--step", "50", "-d", "-30", "-l", "46",
+            "-g", "7", "-f", "45", "-i", "2.5", "--output", "x.png", "--output-meta", "x.dat", "-t", "/data/terrain"]
+    p_cpp, _, folder, out, meta = host.parse_config(argv)
+    _same_params(p_cpp, config.into_params(config.read_config(argv)))
+    assert (folder, out, meta) == ("/data/terrain", "x.png", "x.dat")
+    assert p_cpp.max_distance == 100e3 and p_cpp.radius == 7000e3 and p_cpp.altitude.kind == abi.ALT_RELATIVE  # km on the CLI
+    p_def, objs, folder, out, meta = host.parse_config([])
+    _same_params(p_def, config.into_params(config.default_config()))
+    assert (objs, folder, out, meta) == ([], "./terrain", "./output.png", "")
+    p_flat, *_ = host.parse_config(["--flat", "-a", "2500"])
+    assert p_flat.earth_model == abi.EARTH_FLAT_DISTORTED and p_flat.altitude.kind == abi.ALT_ABSOLUTE and p_flat.altitude.value == 2500.0
+    for bad in (["--flat", "-R", "6371"], ["-a", "1", "-e", "2"], ["--bogus"], ["-w"]):
+        with pytest.raises(host.HostError):
+            host.parse_config(bad)
+
+
+def test_cpp_scope_errors(tmp_path):
+    for body in ("earth_shape: Wgs84\n", "output: {generator: Rectilinear}\n",
+                 "atmosphere:\n  pressure: {altitude: 0, pressure: 101325}\n  first_temperature_function:\n    Spline: {points: [[0, 288]]}\n"):
+        f = tmp_path / "bad.yaml"
+        f.write_text(body)
+        with pytest.raises(host.HostError):
+            host.parse_config(["-c", str(f)])
+
+
+def test_executable_reports_errors_like_the_reference(tmp_path):
+    r = subprocess.run([host.EXECUTABLE, "gen", "-t", str(tmp_path / "missing")], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.startswith("ERROR: ")      # main.rs:36-38
+    r = subprocess.run([host.EXECUTABLE, "view", "x.dat"], capture_output=True, text=True)
+    assert r.returncode == 2
+
+
+@pytest.mark.gpu
+def test_gen_executable_end_to_end(tmp_path, ctx):
+    """`atm-raytracer gen` on DTED files on disk == the library driven through the Python mirror."""
+    from atm_raytracer_b200 import runtime
+
+    folder = tmp_path / "terrain"
+    folder.mkdir()
+    synth.write_tile_grid(str(folder), 45, 5, 1, 2, level=0)
+    conf = tmp_path / "c.yaml"
+    conf.write_text("view:\n  position: {latitude: 45.4, longitude: 5.9, altitude: {Relative: 30.0}}\n"
+                    "  frame: {direction: 80.0, tilt: -2.0, fov: 40.0, max_distance: 60000.0}\n  fog_distance: 50000.0\n"
+                    "scene:\n  terrain_alpha: 0.75\noutput: {width: 200, height: 120}\n")
+    png, dat = tmp_path / "out.png", tmp_path / "out.dat"
+    argv = ["-c", str(conf), "-t", str(folder), "--output", str(png), "--output-meta", str(dat), "--step", "100"]
+    r = subprocess.run([host.EXECUTABLE, "gen"] + argv, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for stamp in ("Using terrain data directory", "Detected 2 terrain files", "Generating terrain cache...", "Generating path cache...",
+                  "Calculating pixels...", "Outputting image...", "Outputting metadata...", "Done."):
+        assert stamp in r.stdout  # the reference's stdout protocol (generator/mod.rs:62-96)
+    img = host.read_png(str(png))[..., :3]
+    assert img.shape == (120, 200, 3)
+    raw = gzip.decompress(dat.read_bytes())
+    assert raw.startswith(b"ATMRTMETA1\n")
+    w, h = np.frombuffer(raw, "<i4", 2, 11)
+    meta = np.frombuffer(raw, runtime.META_DTYPE, offset=19).reshape(h, w)
+    # the same render through the Python mirror of the host
+    cfg = config.read_config(argv)
+    terrain = runtime.Terrain.from_folder(str(folder))
+    gen = runtime.FastGenerator(config.into_params(cfg), terrain, [], [], context=ctx)
+    want = gen.generate()
+    np.testing.assert_array_equal(img, want["rgb"])
+    for k in ("lat", "lon", "elevation", "distance"):
+        np.testing.assert_array_equal(meta[k], want["meta"][k])
+    assert np.isfinite(meta["distance"]).mean() > 0.2
