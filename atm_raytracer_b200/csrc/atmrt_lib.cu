@@ -250,6 +250,7 @@ int lower_atmosphere(atmrt_ctx* ctx, const atmrt_atmosphere_def& def, double wav
     a.m_a = 0.0289635 + 1.2011e-8 * (x_c - 400.0);
     a.r_axs = r_as * (1.0 + 5.34e-7 * (x_c - 450.0));
     a.rho_axs = p_r1 * a.m_a / (z_a * gas_r * t_r1);
+    a.k_dry = a.m_a * a.r_axs / (gas_r * a.rho_axs);  // n - 1 = (p/T) k_dry / Z for dry air
     *out = a;
     return 0;
 }
@@ -470,7 +471,9 @@ int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main) {
     {
         const int rb = (h + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
         const bool dry = S.atm.humidity == 0.0;
-        if (S.flat) {
+        if (S.straight) {
+            k_ray_paths_straight<<<(h + 127) / 128, 128, 0, ctx->s_b>>>(S, B);
+        } else if (S.flat) {
             if (dry) k_ray_paths<true, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
             else     k_ray_paths<true, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
         } else {

@@ -30,6 +30,7 @@ struct DevAtmosphere {
     DevAtmLayer layer[ATMRT_MAX_ATM_FUNCTIONS];
     // Ciddor terms that depend only on the wavelength (lowered on the host with + - * / only).
     double r_axs, r_vs, m_a, rho_axs;
+    double k_dry;  // m_a r_axs / (R rho_axs)
 };
 
 __device__ __forceinline__ int atm_layer_index(const DevAtmosphere& a, double h) {

@@ -9,6 +9,7 @@
 #pragma once
 
 #include "device_atm.cuh"
+#include "device_paths.cuh"
 #include "device_math.cuh"
 #include "device_shade.cuh"
 
@@ -236,72 +237,43 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stage B: ray paths. The physics offers one serial RK4 chain per image row, so this stage is bound
-// by the dependent-issue latency of ONE chain, not by FP64 throughput. Three lanes cooperate on a
-// row: the three refractive-index evaluations of the central difference dn/dh (at h-eps, h, h+eps)
-// run on three lanes and are exchanged with shuffles; every lane then applies the identical RK4
-// update, so the three copies of the state never diverge. 10 rows per warp, one warp per block so
-// the chains spread over all SMs. The cache is written step-major ([k][row]) so that both these
-// stores and the march kernel's loads (lanes = adjacent rows) are coalesced.
+// Stage B: ray paths (gen_path_cache, utils.rs:136-174). The physics offers one serial RK4 chain per
+// image row, so the stage is bound by the dependent-issue latency of ONE chain, not by FP64
+// throughput; see device_paths.cuh for how the critical path of a step is shortened (two rounds of
+// index evaluations per step instead of four, six lanes per row, short-chain log/exp/reciprocals).
+// Five rows per warp, one warp per block so that the chains spread over all SMs. The cache is
+// written step-major ([k][row]) so that both these stores and the march kernel's loads (lanes =
+// adjacent rows) are coalesced.
 // ---------------------------------------------------------------------------------------------
-constexpr int ROWS_PER_WARP = 10;
-
-template <bool DRY>
-__device__ __forceinline__ void env_n_dn3(const DevAtmosphere& a, double h, double off, unsigned gmask, int gbase, double* n, double* dn) {
-    const double eps = 0.01;
-    const double mine = env_n_t<DRY>(a, h + off);
-    const double n1 = __shfl_sync(gmask, mine, gbase + 0);
-    const double n0 = __shfl_sync(gmask, mine, gbase + 1);
-    const double n2 = __shfl_sync(gmask, mine, gbase + 2);
-    *n = n0;
-    *dn = (n2 - n1) / (2.0 * eps);
-}
-
-// One classical RK4 step. The four derivative evaluations run through ONE copy of the code (a
-// rolled loop over the stages) so that the hot loop stays inside the instruction cache.
-template <bool FLAT, bool DRY>
-__device__ __forceinline__ RayState stepper_next3(Stepper& s, const DevAtmosphere& atm, double radius, double step, double off,
-                                                  unsigned gmask, int gbase) {
-    const double d = FLAT ? step : step / radius;
-    double a = s.a, b = s.b;      // stage input: (h, h') or (r, r')
-    // (k1 + 2 k2 + 2 k3 + k4) accumulated left to right, as the reference's expression evaluates
-    double acc_a = 0.0, acc_b = 0.0;
-#pragma unroll 1
-    for (int st = 0; st < 4; ++st) {
-        double n, dn;
-        env_n_dn3<DRY>(atm, FLAT ? a : a - radius, off, gmask, gbase, &n, &dn);
-        const double ka = b;
-        // flat: h'' = n'/n (1 + h'^2);  spherical: r'' = (n'/n)(r'^2 + r^2) + 2 r'^2 / r + r
-        const double kb = FLAT ? dn / n * (1.0 + b * b) : b * b * dn / n + a * a * dn / n + 2.0 * b * b / a + a;
-        const double wk = (st == 1 || st == 2) ? 2.0 : 1.0;  // 1.0 * k and 0.0 + k are exact
-        acc_a = acc_a + wk * ka;
-        acc_b = acc_b + wk * kb;
-        const double w = st == 2 ? 1.0 : 0.5;
-        a = s.a + w * d * ka;
-        b = s.b + w * d * kb;
-    }
-    s.a = s.a + acc_a * d / 6.0;
-    s.b = s.b + acc_b * d / 6.0;
-    s.t += d;
-    if (FLAT) return {s.t, s.a};
-    return {s.t * radius, s.a - radius};
-}
+constexpr int ROWS_PER_WARP = 5;
+constexpr int LANES_PER_ROW = 6;
 
 template <bool FLAT, bool DRY>
 __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevScene S, DevBuffers B) {
     const int lane = threadIdx.x;
-    const int slot = lane / 3, role = lane - slot * 3;
+    const int slot = lane / LANES_PER_ROW, role = lane - slot * LANES_PER_ROW;
     const int y = blockIdx.x * ROWS_PER_WARP + slot;
     if (slot >= ROWS_PER_WARP || y >= S.height) return;
-    const int gbase = slot * 3;
-    const unsigned gmask = 7u << gbase;
-    const double off = role == 0 ? -0.01 : (role == 1 ? 0.0 : 0.01);  // h - eps, h, h + eps
+    const int gbase = slot * LANES_PER_ROW;
+    const unsigned gmask = 63u << gbase;
+    const bool second = role >= 3;  // lanes 0-2 evaluate stages 1 and 3, lanes 3-5 stages 2 and 4
+    const int r3 = second ? role - 3 : role;
+    const double off = r3 == 0 ? -0.01 : (r3 == 1 ? 0.0 : 0.01);  // h - eps, h, h + eps
     const double alt = *B.obs_alt;
-    const double ray_elev = get_ray_elev(S, y);
-    Stepper st;
-    stepper_init(st, FLAT, S.radius, alt, to_radians(ray_elev));
+    const double radius = S.radius;
+    const double d = FLAT ? S.step : S.step / radius;
+    const double hd = 0.5 * d, d6 = d / 6.0;
+    // stepper state: spherical (r, dr/dphi, phi) or flat (h, dh/dx, x)
+    double a = FLAT ? alt : radius + alt;
+    double b = a * tan(to_radians(get_ray_elev(S, y)));
+    if (FLAT) b = tan(to_radians(get_ray_elev(S, y)));
+    double t = 0.0;
+    LayerRegs L;
+    L.lo = L.hi = 0.0;  // empty range: the first evaluation loads the temperature function
+    L.h_ref = L.t_ref = L.p_ref = L.gradient = L.expo = L.inv_t_ref = L.k_iso = 0.0;
     const size_t hp = (size_t)S.h_pad;
-    if (role == 1) {
+    const bool writer = role == 1;
+    if (writer) {
         B.p_dist[y] = 0.0;
         B.p_elev[y] = alt;
         B.p_len[y] = 0.0;
@@ -309,24 +281,54 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
     RayState prev{0.0, alt};
     double path_length = 0.0;
     int n = 1;
-    const bool straight = S.straight != 0;
 #pragma unroll 1
     for (int i = 1; i < S.n_t; ++i) {
         RayState nw;
-        if (straight) {
-            nw = stepper_next(st, S.atm, FLAT, 1, S.radius, S.step);
-        } else if (st.a != st.a) {
+        if (a != a) {
             // The state is NaN (the ray climbed above the altitude where the last temperature function
             // reaches 0 K, e.g. 178 km for US-76): every later state is NaN as well, only the
-            // independent variable keeps advancing. Skip the (slow-path) arithmetic; the outputs are
-            // exactly what the full step would produce: x = t * R, h = NaN, path_length = NaN.
-            st.t += FLAT ? S.step : S.step / S.radius;
-            nw = RayState{FLAT ? st.t : st.t * S.radius, st.a};
+            // independent variable keeps advancing. Skip the arithmetic; the outputs are exactly what
+            // the full step would produce: x = t * R, h = NaN, path_length = NaN.
+            t += d;
+            nw = RayState{FLAT ? t : t * radius, a};
         } else {
-            nw = stepper_next3<FLAT, DRY>(st, S.atm, S.radius, S.step, off, gmask, gbase);
+            // Two rounds: {stage 1, stage 2} then {stage 3, stage 4}. In each round the first group of
+            // lanes evaluates n around altitude aA, the second around aB = a + wB * (slope input of A);
+            // one copy of the code (rolled) keeps the hot loop small.
+            double aA = a, bA = b;                   // stage 1 inputs
+            double acc_a = 0.0, acc_b = 0.0;
+#pragma unroll 1
+            for (int round = 0; round < 2; ++round) {
+                const double wB = round == 0 ? hd : d;       // w*d of stages 2 and 4
+                const double aB = a + wB * bA;               // ka of stage A is its slope input bA
+                double hh = second ? aB : aA;
+                if (!FLAT) hh -= radius;
+                const double mine = env_n_fast<DRY>(S.atm, L, hh + off);
+                const double inv_aA = FLAT ? 0.0 : rcp_nr(aA), inv_aB = FLAT ? 0.0 : rcp_nr(aB);
+                const double nm = __shfl_sync(gmask, mine, gbase + 0), n0 = __shfl_sync(gmask, mine, gbase + 1),
+                             np = __shfl_sync(gmask, mine, gbase + 2);
+                const double om = __shfl_sync(gmask, mine, gbase + 3), o0 = __shfl_sync(gmask, mine, gbase + 4),
+                             op = __shfl_sync(gmask, mine, gbase + 5);
+                const double kbA = ray_accel<FLAT>(aA, bA, inv_aA, n0, nm, np);
+                const double bB = b + wB * kbA;
+                const double kbB = ray_accel<FLAT>(aB, bB, inv_aB, o0, om, op);
+                // (k1 + 2 k2 + 2 k3 + k4), accumulated left to right (0.0 + k1 and 1.0 * k are exact)
+                const double wa = round == 0 ? 1.0 : 2.0, wb = round == 0 ? 2.0 : 1.0;
+                acc_a = acc_a + wa * bA;
+                acc_a = acc_a + wb * bB;
+                acc_b = acc_b + wa * kbA;
+                acc_b = acc_b + wb * kbB;
+                // stage 3 inputs: a + d/2 * ka2, b + d/2 * kb2
+                aA = a + hd * bB;
+                bA = b + hd * kbB;
+            }
+            a = a + acc_a * d6;
+            b = b + acc_b * d6;
+            t += d;
+            nw = FLAT ? RayState{t, a} : RayState{t * radius, a - radius};
         }
-        path_length += calc_dist(FLAT, S.radius, prev, nw);
-        if (role == 1) {
+        path_length += calc_dist(FLAT, radius, prev, nw);
+        if (writer) {
             const size_t o = (size_t)i * hp + y;
             B.p_dist[o] = nw.x;
             B.p_elev[o] = nw.h;
@@ -336,10 +338,41 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
         if (prev.x > S.max_distance || prev.h < -1000.0) break;
         prev = nw;
     }
-    if (role == 1) {
+    if (writer) {
         B.p_n[y] = n;
         atomicAdd(B.counters + CNT_PATH_STEPS, (unsigned long long)(n - 1));
     }
+}
+
+// Straight rays (-s): the path is a closed form of the step index (no chain through the state), one
+// thread per row.
+__global__ void __launch_bounds__(128) k_ray_paths_straight(const __grid_constant__ DevScene S, DevBuffers B) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= S.height) return;
+    const bool flat = S.flat != 0;
+    const double alt = *B.obs_alt;
+    Stepper st;
+    stepper_init(st, flat, S.radius, alt, to_radians(get_ray_elev(S, y)));
+    const size_t hp = (size_t)S.h_pad;
+    B.p_dist[y] = 0.0;
+    B.p_elev[y] = alt;
+    B.p_len[y] = 0.0;
+    RayState prev{0.0, alt};
+    double path_length = 0.0;
+    int n = 1;
+    for (int i = 1; i < S.n_t; ++i) {
+        const RayState nw = stepper_next(st, S.atm, flat, 1, S.radius, S.step);
+        path_length += calc_dist(flat, S.radius, prev, nw);
+        const size_t o = (size_t)i * hp + y;
+        B.p_dist[o] = nw.x;
+        B.p_elev[o] = nw.h;
+        B.p_len[o] = path_length;
+        n = i + 1;
+        if (prev.x > S.max_distance || prev.h < -1000.0) break;
+        prev = nw;
+    }
+    B.p_n[y] = n;
+    atomicAdd(B.counters + CNT_PATH_STEPS, (unsigned long long)(n - 1));
 }
 
 // ---------------------------------------------------------------------------------------------
