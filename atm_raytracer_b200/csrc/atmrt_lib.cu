@@ -64,6 +64,8 @@ struct atmrt_ctx {
     int march_mode = 0;
     int rows_per_warp = 32;
     std::vector<double> dist_k;
+    std::vector<double> atm_cells;
+    DevBuf d_atm_cells;
     DevBuf d_dist, d_colcalc, d_tlat, d_tlon, d_telev, d_tnx, d_tny, d_tnz, d_tclose;
     DevBuf d_pdist, d_pelev, d_plen, d_pn;
     DevBuf d_tmin1, d_tmax1, d_tmin2, d_tmax2, d_tmin3, d_tmax3, d_close1, d_close2, d_close3;
@@ -172,6 +174,41 @@ double host_layer_pressure(const DevAtmLayer& l, double h) {
         return l.p_ref * std::pow(t / l.t_ref, -ATM_G * ATM_M / (ATM_R * l.gradient));
     }
     return l.p_ref * std::exp(-ATM_G * ATM_M * (h - l.h_ref) / (ATM_R * l.t_ref));
+}
+
+// The anchor table of the ray-path stage (device_paths.cuh): [ATM_FIELDS][ATM_CELLS]. Anchors use the
+// reference's own expressions for T(h) and p(h) (host libm), evaluated at the cell centres. Cells the
+// series cannot serve hold NaN.
+void build_atm_table(const DevAtmosphere& a, std::vector<double>& cells) {
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    cells.assign((size_t)ATM_FIELDS * ATM_CELLS, nan);
+    auto find = [&](double h) {
+        int idx = 0;
+        for (int i = 1; i < a.n; ++i)
+            if (h >= a.layer[i].start) idx = i;
+        return idx;
+    };
+    for (int j = 1; j + 1 < ATM_CELLS; ++j) {  // the first and the last cell catch out-of-range and NaN altitudes
+        const double hj = ATM_BASE + (double)j * ATM_CELL, lo = hj - 0.5 * ATM_CELL, hi = hj + 0.5 * ATM_CELL;
+        const int li = find(lo);
+        bool whole = true;  // no temperature function starts inside the cell (or on its upper edge: rounding of the index)
+        for (int i = 1; i < a.n; ++i)
+            if (a.layer[i].start > lo && a.layer[i].start <= hi) whole = false;
+        const DevAtmLayer& l = a.layer[li];
+        const double t_lo = host_layer_temperature(l, lo), t_hi = host_layer_temperature(l, hi), tj = host_layer_temperature(l, hj);
+        if (!whole || !(t_lo >= 60.0) || !(t_hi >= 60.0)) continue;
+        const double pj = host_layer_pressure(l, hj);
+        if (!(pj > 0.0) || !std::isfinite(pj)) continue;
+        const bool linear = l.gradient != 0.0;
+        const double k = linear ? l.gradient / tj : l.gm / l.rt;  // d ln T / dh, or d ln p / dh for an isothermal function
+        const double w_max = std::fabs(k) * 0.51 * ATM_CELL;
+        if (linear ? (w_max > ATM_W_MAX || std::fabs(l.expo) * w_max > ATM_V_MAX) : w_max > ATM_V_MAX) continue;
+        cells[0 * ATM_CELLS + j] = pj;
+        cells[1 * ATM_CELLS + j] = tj;
+        cells[2 * ATM_CELLS + j] = l.gradient;
+        cells[3 * ATM_CELLS + j] = linear ? k : k / ATM_ISO_SCALE;
+        cells[4 * ATM_CELLS + j] = linear ? l.expo : ATM_ISO_SCALE;
+    }
 }
 
 int lower_atmosphere(atmrt_ctx* ctx, const atmrt_atmosphere_def& def, double wavelength, DevAtmosphere* out) {
@@ -288,6 +325,10 @@ int prepare_render(atmrt_ctx* ctx) {
     if (!S.flat) {
         S.sin_diff = std::sin(NORMAL_DIFF / p.radius);
         S.cos_diff = std::cos(NORMAL_DIFF / p.radius);
+        const double delta = NORMAL_DIFF / p.radius;
+        S.tan_diff = std::tan(delta);
+        S.versin_diff = 2.0 * std::sin(0.5 * delta) * std::sin(0.5 * delta);  // 1 - cos(delta) without cancellation
+        S.diff_deg = to_degrees(delta);
     }
     int rc = lower_atmosphere(ctx, p.atmosphere, p.wavelength, &S.atm);
     if (rc) return rc;
@@ -356,6 +397,8 @@ int prepare_render(atmrt_ctx* ctx) {
     e |= ensure(ctx, ctx->d_rmax3, f8 * hp);
     (void)h;
     e |= ensure(ctx, ctx->d_obs, f8);
+    e |= ensure(ctx, ctx->d_atm_cells, f8 * ATM_FIELDS * ATM_CELLS);
+    build_atm_table(S.atm, ctx->atm_cells);
     e |= ensure(ctx, ctx->d_counters, 8 * CNT_COUNT);
     e |= ensure(ctx, ctx->d_objects, sizeof(DevObject) * std::max(1, S.nobjects));
     e |= ensure(ctx, ctx->d_objects_in, sizeof(atmrt_object) * std::max(1, S.nobjects));
@@ -382,12 +425,14 @@ int prepare_render(atmrt_ctx* ctx) {
     B.obs_alt = (double*)ctx->d_obs.p;
     B.objects = (DevObject*)ctx->d_objects.p;
     B.counters = (unsigned long long*)ctx->d_counters.p;
+    B.atm_cells = (const double*)ctx->d_atm_cells.p;
     return 0;
 }
 
 int upload_scene_inputs(atmrt_ctx* ctx, cudaStream_t s) {
     const DevScene& S = ctx->scene;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dist.p, ctx->dist_k.data(), sizeof(double) * S.n_t, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_atm_cells.p, ctx->atm_cells.data(), sizeof(double) * ATM_FIELDS * ATM_CELLS, cudaMemcpyHostToDevice, s));
     if (S.nobjects > 0) {
         std::vector<DevObject> host(S.nobjects);
         for (int i = 0; i < S.nobjects; ++i) {
@@ -609,7 +654,7 @@ void atmrt_destroy(atmrt_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_objects_in, &ctx->d_objects, &ctx->d_dist, &ctx->d_colcalc, &ctx->d_tlat, &ctx->d_tlon, &ctx->d_telev,
                       &ctx->d_tnx, &ctx->d_tny, &ctx->d_tnz, &ctx->d_tclose, &ctx->d_pdist, &ctx->d_pelev, &ctx->d_plen, &ctx->d_pn,
                       &ctx->d_tmin1, &ctx->d_tmax1, &ctx->d_tmin2, &ctx->d_tmax2, &ctx->d_tmin3, &ctx->d_tmax3, &ctx->d_close1, &ctx->d_close2, &ctx->d_close3, &ctx->d_rmin1, &ctx->d_rmin3, &ctx->d_rmax3,
-                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_rgb, &ctx->d_meta,
+                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_rgb, &ctx->d_meta,
                       &ctx->d_steps, &ctx->d_points, &ctx->d_counts, &ctx->d_probe_a, &ctx->d_probe_b, &ctx->d_probe_c, &ctx->d_probe_d};
     for (DevBuf* b : bufs) release(*b);
     for (DevBuf& b : ctx->textures) release(b);

@@ -23,6 +23,7 @@ struct DevScene {
     double lat0, lon0, direction, tilt, fov, max_distance, step;
     double radius;
     double sin_diff, cos_diff;  // sin/cos(NORMAL_DIFF / radius), spherical find_normal
+    double tan_diff, versin_diff, diff_deg;  // tan(delta), 1 - cos(delta), delta in degrees
     atmrt_altitude altitude;
     int earth_model, straight, flat;
     int width, height, x0, x1;
@@ -54,6 +55,7 @@ struct DevBuffers {
     double* obs_alt;  // [1]
     DevObject* objects;
     unsigned long long* counters;  // see Counter
+    const double* atm_cells;  // hydrostatic anchors of the ray-path stage (device_paths.cuh): [ATM_FIELDS][ATM_CELLS]
 };
 
 enum Counter { CNT_RAY_STEPS = 0, CNT_TRACE_POINTS, CNT_PIXELS_HIT, CNT_OVERFLOWS, CNT_PATH_STEPS, CNT_COUNT };
@@ -156,6 +158,59 @@ __global__ void k_column_setup(const __grid_constant__ DevScene S, DevBuffers B)
     c[3] = d.up.x, c[4] = d.up.y, c[5] = d.up.z;
 }
 
+// find_normal, utils.rs:15-40: central differences +-15 m north/south and east/west on the terrain.
+// A pure function of (lat, lon); sin/cos of both are passed in because the callers have them.
+__device__ __forceinline__ V3 find_normal(const DevScene& S, const DevTerrain& T, double lat, double lon, double sinlat, double coslat,
+                                          double sinlon, double coslon) {
+    double n_lat, n_lon, s_lat, s_lon, e_lat, e_lon, w_lat, w_lon;
+    Dirs D;
+    if (S.flat) {
+        // FlDsCalc::new((lat, lon), 0.0 / 90.0).coords_at_dist(+-DIFF)
+        n_lat = lat + 1.0 * NORMAL_DIFF / DEGREE_DISTANCE;
+        n_lon = lon + 0.0 * NORMAL_DIFF / DEGREE_DISTANCE / coslat;
+        s_lat = lat + 1.0 * -NORMAL_DIFF / DEGREE_DISTANCE;
+        s_lon = lon + 0.0 * -NORMAL_DIFF / DEGREE_DISTANCE / coslat;
+        e_lat = lat + COS_90 * NORMAL_DIFF / DEGREE_DISTANCE;
+        e_lon = lon + SIN_90 * NORMAL_DIFF / DEGREE_DISTANCE / coslat;
+        w_lat = lat + COS_90 * -NORMAL_DIFF / DEGREE_DISTANCE;
+        w_lon = lon + SIN_90 * -NORMAL_DIFF / DEGREE_DISTANCE / coslat;
+        D.north = {-coslon, -sinlon, 0.0};
+        D.east = {-sinlon, coslon, 0.0};
+        D.up = {0.0, 0.0, 1.0};
+    } else {
+        // SphericalCalc::new(radius, (lat, lon), 0.0 / 90.0).coords_at_dist(+-DIFF). With delta = DIFF/radius
+        // (2.4e-6 rad) the great-circle walk has closed forms that agree with asin(fpos.z), atan2(fpos.y,
+        // fpos.x) to ~1e-15 degrees -- below the 1-2 ulp (1e-14 degrees) those libm calls carry themselves:
+        //   north/south: fpos.z = sin(lat +- delta), fpos.xy parallel to (cos lon, sin lon)  => (lat +- delta, lon)
+        //   east/west:   fpos.z = sin(lat) cos(delta)       => lat - tan(lat) (1 - cos delta)   (next term 1e-23)
+        //                lon +- atan(tan(delta) / cos(lat)) => q - q^3/3, q = tan(delta)/cos(lat) (next term 1e-28)
+        // (the cos(90 deg) = 6e-17 north component of the east direction moves the point by 1e-22 rad).
+        // Near the poles (|lat| > 85 deg) the expansions lose accuracy: use the walk itself.
+        D = spherical_directions_sc(sinlat, coslat, sinlon, coslon);
+        if (fabs(lat) <= 85.0) {
+            const double q = S.tan_diff / coslat;
+            const double dlon = to_degrees(q - q * q * q * (1.0 / 3.0));
+            const double lat_ew = lat - to_degrees(sinlat / coslat * S.versin_diff);
+            n_lat = lat + S.diff_deg, n_lon = lon;
+            s_lat = lat - S.diff_deg, s_lon = lon;
+            e_lat = lat_ew, e_lon = lon + dlon;
+            w_lat = lat_ew, w_lon = lon - dlon;
+        } else {
+            V3 dir_ns = D.north * 1.0 + D.east * 0.0;
+            V3 dir_ew = D.north * COS_90 + D.east * SIN_90;
+            spherical_walk(D.up, dir_ns, S.sin_diff, S.cos_diff, &n_lat, &n_lon);
+            spherical_walk(D.up, dir_ns, -S.sin_diff, S.cos_diff, &s_lat, &s_lon);
+            spherical_walk(D.up, dir_ew, S.sin_diff, S.cos_diff, &e_lat, &e_lon);
+            spherical_walk(D.up, dir_ew, -S.sin_diff, S.cos_diff, &w_lat, &w_lon);
+        }
+    }
+    double diff_ew = elev_or_zero(T, e_lat, e_lon) - elev_or_zero(T, w_lat, w_lon);
+    double diff_ns = elev_or_zero(T, n_lat, n_lon) - elev_or_zero(T, s_lat, s_lon);
+    V3 vec_ns = (2.0 * NORMAL_DIFF) * D.north + diff_ns * D.up;
+    V3 vec_ew = (2.0 * NORMAL_DIFF) * D.east + diff_ew * D.up;
+    V3 normal = cross(vec_ew, vec_ns);
+    return normal / sqrt(dot(normal, normal));
+}
 // ---------------------------------------------------------------------------------------------
 // Stage A: terrain profile. One thread per (column, sample); lanes run along the ray so the
 // [column][k] stores are coalesced and the bilinear taps of a warp walk along one azimuth.
@@ -178,48 +233,15 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
         spherical_walk(V3{cc[3], cc[4], cc[5]}, V3{cc[0], cc[1], cc[2]}, sinang, cosang, &lat, &lon);
     }
     double elev = elev_or_zero(T, lat, lon);
-
-    // find_normal, utils.rs:15-40: central differences +-15 m north/south and east/west.
-    double sinlat, coslat, sinlon, coslon;
-    sincos(to_radians(lat), &sinlat, &coslat);
-    sincos(to_radians(lon), &sinlon, &coslon);
-    double n_lat, n_lon, s_lat, s_lon, e_lat, e_lon, w_lat, w_lon;
-    Dirs D;
-    if (S.flat) {
-        // FlDsCalc::new((lat, lon), 0.0 / 90.0).coords_at_dist(+-DIFF)
-        n_lat = lat + 1.0 * NORMAL_DIFF / DEGREE_DISTANCE;
-        n_lon = lon + 0.0 * NORMAL_DIFF / DEGREE_DISTANCE / coslat;
-        s_lat = lat + 1.0 * -NORMAL_DIFF / DEGREE_DISTANCE;
-        s_lon = lon + 0.0 * -NORMAL_DIFF / DEGREE_DISTANCE / coslat;
-        e_lat = lat + COS_90 * NORMAL_DIFF / DEGREE_DISTANCE;
-        e_lon = lon + SIN_90 * NORMAL_DIFF / DEGREE_DISTANCE / coslat;
-        w_lat = lat + COS_90 * -NORMAL_DIFF / DEGREE_DISTANCE;
-        w_lon = lon + SIN_90 * -NORMAL_DIFF / DEGREE_DISTANCE / coslat;
-        D.north = {-coslon, -sinlon, 0.0};
-        D.east = {-sinlon, coslon, 0.0};
-        D.up = {0.0, 0.0, 1.0};
-    } else {
-        // SphericalCalc::new(radius, (lat, lon), 0.0 / 90.0).coords_at_dist(+-DIFF); the sin/cos of
-        // 0 and 90 degrees and of +-DIFF/radius are constants of the render.
-        D = spherical_directions_sc(sinlat, coslat, sinlon, coslon);
-        V3 dir_ns = D.north * 1.0 + D.east * 0.0;
-        V3 dir_ew = D.north * COS_90 + D.east * SIN_90;
-        spherical_walk(D.up, dir_ns, S.sin_diff, S.cos_diff, &n_lat, &n_lon);
-        spherical_walk(D.up, dir_ns, -S.sin_diff, S.cos_diff, &s_lat, &s_lon);
-        spherical_walk(D.up, dir_ew, S.sin_diff, S.cos_diff, &e_lat, &e_lon);
-        spherical_walk(D.up, dir_ew, -S.sin_diff, S.cos_diff, &w_lat, &w_lon);
-    }
-    double diff_ew = elev_or_zero(T, e_lat, e_lon) - elev_or_zero(T, w_lat, w_lon);
-    double diff_ns = elev_or_zero(T, n_lat, n_lon) - elev_or_zero(T, s_lat, s_lon);
-    V3 vec_ns = (2.0 * NORMAL_DIFF) * D.north + diff_ns * D.up;
-    V3 vec_ew = (2.0 * NORMAL_DIFF) * D.east + diff_ew * D.up;
-    V3 normal = cross(vec_ew, vec_ns);
-    normal = normal / sqrt(dot(normal, normal));
-
     size_t idx = (size_t)xl * S.n_pad + k;
     B.t_lat[idx] = lat;
     B.t_lon[idx] = lon;
     B.t_elev[idx] = elev;
+
+    double sinlat, coslat, sinlon, coslon;
+    sincos(to_radians(lat), &sinlat, &coslat);
+    sincos(to_radians(lon), &sinlon, &coslon);
+    V3 normal = find_normal(S, T, lat, lon, sinlat, coslat, sinlon, coslon);
     B.t_nx[idx] = normal.x;
     B.t_ny[idx] = normal.y;
     B.t_nz[idx] = normal.z;
@@ -240,39 +262,43 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
 // Stage B: ray paths (gen_path_cache, utils.rs:136-174). The physics offers one serial RK4 chain per
 // image row, so the stage is bound by the dependent-issue latency of ONE chain, not by FP64
 // throughput; see device_paths.cuh for how the critical path of a step is shortened (two rounds of
-// index evaluations per step instead of four, six lanes per row, short-chain log/exp/reciprocals).
-// Five rows per warp, one warp per block so that the chains spread over all SMs. The cache is
-// written step-major ([k][row]) so that both these stores and the march kernel's loads (lanes =
-// adjacent rows) are coalesced.
+// index evaluations per step instead of four, six lanes per row, re-anchored hydrostatic series,
+// reciprocals). Five rows per warp, one warp per block so that the chains spread over all SMs. The
+// cache is written step-major ([k][row]) so that both these stores and the march kernel's loads
+// (lanes = adjacent rows) are coalesced.
 // ---------------------------------------------------------------------------------------------
 constexpr int ROWS_PER_WARP = 5;
 constexpr int LANES_PER_ROW = 6;
 
 template <bool FLAT, bool DRY>
 __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevScene S, DevBuffers B) {
+    __shared__ double cells[ATM_FIELDS * ATM_CELLS];
     const int lane = threadIdx.x;
-    const int slot = lane / LANES_PER_ROW, role = lane - slot * LANES_PER_ROW;
-    const int y = blockIdx.x * ROWS_PER_WARP + slot;
-    if (slot >= ROWS_PER_WARP || y >= S.height) return;
+    for (int i = lane; i < ATM_FIELDS * ATM_CELLS; i += 32) cells[i] = B.atm_cells[i];
+    __syncwarp();
+    // All 32 lanes stay in the loop so that the exchanges are plain full-mask shuffles: lanes 30-31 and
+    // the slots of rows past the image shadow a real row and write nothing.
+    const int slot = min(lane / LANES_PER_ROW, ROWS_PER_WARP - 1), role = lane - slot * LANES_PER_ROW;
+    const int y_raw = blockIdx.x * ROWS_PER_WARP + slot;
+    const int y = min(y_raw, S.height - 1);
     const int gbase = slot * LANES_PER_ROW;
-    const unsigned gmask = 63u << gbase;
-    const bool second = role >= 3;  // lanes 0-2 evaluate stages 1 and 3, lanes 3-5 stages 2 and 4
-    const int r3 = second ? role - 3 : role;
+    const bool second = role >= 3 && role < 6;  // lanes 0-2 evaluate stages 1 and 3, lanes 3-5 stages 2 and 4
+    const int r3 = role % 3;
     const double off = r3 == 0 ? -0.01 : (r3 == 1 ? 0.0 : 0.01);  // h - eps, h, h + eps
+    const bool writer = role == 1 && y_raw < S.height;
     const double alt = *B.obs_alt;
     const double radius = S.radius;
     const double d = FLAT ? S.step : S.step / radius;
     const double hd = 0.5 * d, d6 = d / 6.0;
+    const double inv_radius = FLAT ? 0.0 : 1.0 / radius;
+    // cell index chain: (altitude + off - ATM_BASE) / ATM_CELL + 1.5 * 2^52, from r (spherical) or h (flat)
+    const double magic = 6755399441055744.0;
+    const double xc = ((FLAT ? 0.0 : -radius) + off - ATM_BASE) * (1.0 / ATM_CELL) + magic;
     // stepper state: spherical (r, dr/dphi, phi) or flat (h, dh/dx, x)
     double a = FLAT ? alt : radius + alt;
-    double b = a * tan(to_radians(get_ray_elev(S, y)));
-    if (FLAT) b = tan(to_radians(get_ray_elev(S, y)));
+    double b = FLAT ? tan(to_radians(get_ray_elev(S, y))) : a * tan(to_radians(get_ray_elev(S, y)));
     double t = 0.0;
-    LayerRegs L;
-    L.lo = L.hi = 0.0;  // empty range: the first evaluation loads the temperature function
-    L.h_ref = L.t_ref = L.p_ref = L.gradient = L.expo = L.inv_t_ref = L.k_iso = 0.0;
     const size_t hp = (size_t)S.h_pad;
-    const bool writer = role == 1;
     if (writer) {
         B.p_dist[y] = 0.0;
         B.p_elev[y] = alt;
@@ -281,63 +307,74 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
     RayState prev{0.0, alt};
     double path_length = 0.0;
     int n = 1;
+    bool done = S.n_t < 2;
+
+    // One round: the first lane group evaluates n around altitude aA, the second around
+    // aB = a + wB * bA (ka of stage A is its slope input bA); then kbA, bB = b + wB kbA and kbB follow.
+    // The centre lanes also form (1/(2 eps)) / n before the exchange, so that after the shuffles only
+    // one subtraction and one multiplication separate the index values from n'/n.
+#define ATMRT_RK4_ROUND(aA, bA, wB, aB, kbA, bB, kbB)                                                            \
+    const double aB = fma(wB, bA, a);                                                                            \
+    double kbA, bB, kbB;                                                                                         \
+    {                                                                                                            \
+        const double sel = second ? aB : aA;                                                                     \
+        const double hh = (FLAT ? sel : sel - radius) + off;                                                     \
+        bool bad;                                                                                                \
+        double mine = env_n_fast<DRY>(S.atm, cells, hh, fma(sel, 1.0 / ATM_CELL, xc), &bad);                     \
+        if (bad) mine = env_n_slow<DRY>(S.atm, hh);                                                              \
+        const double r50 = 50.0 * rcp_1p(mine - 1.0);                                                            \
+        const double bbA = bA * bA;                                                                              \
+        const double sA = FLAT ? 1.0 + bbA : fma(aA, aA, bbA);                                                   \
+        const double cA = FLAT ? 0.0 : fma(2.0 * bbA, rcp_nr(aA), aA);                                           \
+        const double inv_aB = FLAT ? 0.0 : rcp_nr(aB);                                                           \
+        const double nm = __shfl_sync(FULL, mine, gbase + 0), rA = __shfl_sync(FULL, r50, gbase + 1),            \
+                     np = __shfl_sync(FULL, mine, gbase + 2);                                                    \
+        const double om = __shfl_sync(FULL, mine, gbase + 3), rB = __shfl_sync(FULL, r50, gbase + 4),            \
+                     op = __shfl_sync(FULL, mine, gbase + 5);                                                    \
+        kbA = fma((np - nm) * rA, sA, cA);                                                                       \
+        bB = fma(wB, kbA, b);                                                                                    \
+        const double bbB = bB * bB;                                                                              \
+        const double sB = FLAT ? 1.0 + bbB : fma(aB, aB, bbB);                                                   \
+        const double cB = FLAT ? 0.0 : fma(2.0 * bbB, inv_aB, aB);                                               \
+        kbB = fma((op - om) * rB, sB, cB);                                                                       \
+    }
+
 #pragma unroll 1
     for (int i = 1; i < S.n_t; ++i) {
-        RayState nw;
-        if (a != a) {
-            // The state is NaN (the ray climbed above the altitude where the last temperature function
-            // reaches 0 K, e.g. 178 km for US-76): every later state is NaN as well, only the
-            // independent variable keeps advancing. Skip the arithmetic; the outputs are exactly what
-            // the full step would produce: x = t * R, h = NaN, path_length = NaN.
-            t += d;
-            nw = RayState{FLAT ? t : t * radius, a};
-        } else {
-            // Two rounds: {stage 1, stage 2} then {stage 3, stage 4}. In each round the first group of
-            // lanes evaluates n around altitude aA, the second around aB = a + wB * (slope input of A);
-            // one copy of the code (rolled) keeps the hot loop small.
-            double aA = a, bA = b;                   // stage 1 inputs
-            double acc_a = 0.0, acc_b = 0.0;
-#pragma unroll 1
-            for (int round = 0; round < 2; ++round) {
-                const double wB = round == 0 ? hd : d;       // w*d of stages 2 and 4
-                const double aB = a + wB * bA;               // ka of stage A is its slope input bA
-                double hh = second ? aB : aA;
-                if (!FLAT) hh -= radius;
-                const double mine = env_n_fast<DRY>(S.atm, L, hh + off);
-                const double inv_aA = FLAT ? 0.0 : rcp_nr(aA), inv_aB = FLAT ? 0.0 : rcp_nr(aB);
-                const double nm = __shfl_sync(gmask, mine, gbase + 0), n0 = __shfl_sync(gmask, mine, gbase + 1),
-                             np = __shfl_sync(gmask, mine, gbase + 2);
-                const double om = __shfl_sync(gmask, mine, gbase + 3), o0 = __shfl_sync(gmask, mine, gbase + 4),
-                             op = __shfl_sync(gmask, mine, gbase + 5);
-                const double kbA = ray_accel<FLAT>(aA, bA, inv_aA, n0, nm, np);
-                const double bB = b + wB * kbA;
-                const double kbB = ray_accel<FLAT>(aB, bB, inv_aB, o0, om, op);
-                // (k1 + 2 k2 + 2 k3 + k4), accumulated left to right (0.0 + k1 and 1.0 * k are exact)
-                const double wa = round == 0 ? 1.0 : 2.0, wb = round == 0 ? 2.0 : 1.0;
-                acc_a = acc_a + wa * bA;
-                acc_a = acc_a + wb * bB;
-                acc_b = acc_b + wa * kbA;
-                acc_b = acc_b + wb * kbB;
-                // stage 3 inputs: a + d/2 * ka2, b + d/2 * kb2
-                aA = a + hd * bB;
-                bA = b + hd * kbB;
-            }
-            a = a + acc_a * d6;
-            b = b + acc_b * d6;
-            t += d;
-            nw = FLAT ? RayState{t, a} : RayState{t * radius, a - radius};
+        // When the state is NaN (the ray climbed above the altitude where the last temperature function
+        // reaches 0 K, e.g. 178 km for US-76) every later state is NaN as well and only the independent
+        // variable keeps advancing: x = t * R, h = NaN, path_length = NaN, exactly what the arithmetic
+        // below produces (NaN in, NaN out), so nothing special is needed for the values -- only speed:
+        // a warp whose rows are all NaN or finished skips the evaluations.
+        if (!__all_sync(FULL, done || a != a)) {
+            // stages 1 and 2 (altitudes a and a + d/2 b are both known now), then stages 3 and 4
+            ATMRT_RK4_ROUND(a, b, hd, a2, kb1, b2, kb2)
+            const double a3 = fma(hd, b2, a), b3 = fma(hd, kb2, b);
+            ATMRT_RK4_ROUND(a3, b3, d, a4, kb3, b4, kb4)
+            // y += (k1 + 2 k2 + 2 k3 + k4) d / 6
+            a = fma((b + 2.0 * b2) + (2.0 * b3 + b4), d6, a);
+            b = fma((kb1 + 2.0 * kb2) + (2.0 * kb3 + kb4), d6, b);
         }
-        path_length += calc_dist(FLAT, radius, prev, nw);
-        if (writer) {
+        t += d;
+        const RayState nw = FLAT ? RayState{t, a} : RayState{t * radius, a - radius};
+        {  // calc_dist, utils.rs:42-53 (dx / R as dx * (1/R): off the chain, but it still costs issue slots)
+            double dx = nw.x - prev.x;
+            const double dh = nw.h - prev.h;
+            if (!FLAT) dx = dx * inv_radius * ((nw.h + prev.h) * 0.5 + radius);
+            path_length += sqrt(dx * dx + dh * dh);
+        }
+        if (writer && !done) {
             const size_t o = (size_t)i * hp + y;
             B.p_dist[o] = nw.x;
             B.p_elev[o] = nw.h;
             B.p_len[o] = path_length;
+            n = i + 1;
         }
-        n = i + 1;
-        if (prev.x > S.max_distance || prev.h < -1000.0) break;
+        if (prev.x > S.max_distance || prev.h < -1000.0) done = true;
+        if (__all_sync(FULL, done)) break;
         prev = nw;
     }
+#undef ATMRT_RK4_ROUND
     if (writer) {
         B.p_n[y] = n;
         atomicAdd(B.counters + CNT_PATH_STEPS, (unsigned long long)(n - 1));
