@@ -65,6 +65,25 @@ __device__ __forceinline__ double rcp_nr(double x) {
     return fma(y, e, y);
 }
 
+// sqrt(x) for normal positive x (NaN in, NaN out): MUFU.RSQ64H seed, two coupled Newton steps and a
+// final residual correction -- the libm sequence without its special-case branch, so that it can be
+// scheduled inside the straight-line step.
+__device__ __forceinline__ double sqrt_nr(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g), h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g), h = fma(h, r, h);
+    return fma(fma(-g, g, x), h, g);
+}
+
+// predicated 8-byte global store (no branch)
+__device__ __forceinline__ void stg_if(double* p, double v, bool ok) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.global.f64 [%1], %2;\n\t}" ::"r"((unsigned)ok), "l"(p), "d"(v) : "memory");
+}
+
 // 1/(1 + x) for |x| < 1e-2: (1 - x)(1 + x^2)(1 + x^4) = 1 - x + ... - x^7 (remainder x^8 < 1e-16).
 __device__ __forceinline__ double rcp_1p(double x) {
     const double x2 = x * x, m = 1.0 - x;
@@ -78,17 +97,24 @@ __device__ __noinline__ double env_n_slow(const DevAtmosphere& a, double h) {
     return env_n_t<DRY>(a, h);
 }
 
-// Environment::n(h) on the short-chain path. `cells` is the anchor table in shared memory,
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// Environment::n(h) on the short-chain path. `cells` is the shared-space address of the anchor table,
 // [ATM_FIELDS][ATM_CELLS]; `sel` is the lane's stage altitude before the eps offset (r or h) and `hx` the
 // same altitude in cell units plus 1.5 * 2^52 (an imprecise copy of the chain that is only used to pick
 // the cell: its low word is the nearest cell index). *bad is set when the cell cannot serve the
 // altitude (NaN anchors); the caller then takes env_n_slow.
 template <bool DRY>
-__device__ __forceinline__ double env_n_fast(const DevAtmosphere& a, const double* cells, double h, double hx, bool* bad) {
+__device__ __forceinline__ double env_n_fast(const DevAtmosphere& a, unsigned cells, double h, double hx, bool* bad) {
     const double magic = 6755399441055744.0;  // 1.5 * 2^52
     const unsigned j = min((unsigned)__double2loint(hx), (unsigned)(ATM_CELLS - 1));  // negative, NaN -> an edge cell (NaN anchors)
-    const double pj = cells[j], tj = cells[ATM_CELLS + j], gj = cells[2 * ATM_CELLS + j], sj = cells[3 * ATM_CELLS + j],
-                 aj = cells[4 * ATM_CELLS + j];
+    const unsigned cj = cells + j * 8u;
+    const double pj = lds_f64(cj), tj = lds_f64(cj + 8u * ATM_CELLS), gj = lds_f64(cj + 16u * ATM_CELLS),
+                 sj = lds_f64(cj + 24u * ATM_CELLS), aj = lds_f64(cj + 32u * ATM_CELLS);
     *bad = pj != pj;
     const double dh = h - fma(hx - magic, ATM_CELL, ATM_BASE);
     const double t = fma(gj, dh, tj);

@@ -272,10 +272,11 @@ constexpr int LANES_PER_ROW = 6;
 
 template <bool FLAT, bool DRY>
 __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevScene S, DevBuffers B) {
-    __shared__ double cells[ATM_FIELDS * ATM_CELLS];
+    __shared__ double cells_smem[ATM_FIELDS * ATM_CELLS];
     const int lane = threadIdx.x;
-    for (int i = lane; i < ATM_FIELDS * ATM_CELLS; i += 32) cells[i] = B.atm_cells[i];
+    for (int i = lane; i < ATM_FIELDS * ATM_CELLS; i += 32) cells_smem[i] = B.atm_cells[i];
     __syncwarp();
+    const unsigned cells = (unsigned)__cvta_generic_to_shared(cells_smem);
     // All 32 lanes stay in the loop so that the exchanges are plain full-mask shuffles: lanes 30-31 and
     // the slots of rows past the image shadow a real row and write nothing.
     const int slot = min(lane / LANES_PER_ROW, ROWS_PER_WARP - 1), role = lane - slot * LANES_PER_ROW;
@@ -294,26 +295,17 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
     // cell index chain: (altitude + off - ATM_BASE) / ATM_CELL + 1.5 * 2^52, from r (spherical) or h (flat)
     const double magic = 6755399441055744.0;
     const double xc = ((FLAT ? 0.0 : -radius) + off - ATM_BASE) * (1.0 / ATM_CELL) + magic;
-    // stepper state: spherical (r, dr/dphi, phi) or flat (h, dh/dx, x)
-    double a = FLAT ? alt : radius + alt;
-    double b = FLAT ? tan(to_radians(get_ray_elev(S, y))) : a * tan(to_radians(get_ray_elev(S, y)));
-    double t = 0.0;
     const size_t hp = (size_t)S.h_pad;
-    if (writer) {
-        B.p_dist[y] = 0.0;
-        B.p_elev[y] = alt;
-        B.p_len[y] = 0.0;
-    }
-    RayState prev{0.0, alt};
-    double path_length = 0.0;
-    int n = 1;
-    bool done = S.n_t < 2;
+    double* const o_dist = B.p_dist + y;
+    double* const o_elev = B.p_elev + y;
+    double* const o_len = B.p_len + y;
 
     // One round: the first lane group evaluates n around altitude aA, the second around
     // aB = a + wB * bA (ka of stage A is its slope input bA); then kbA, bB = b + wB kbA and kbB follow.
     // The centre lanes also form (1/(2 eps)) / n before the exchange, so that after the shuffles only
-    // one subtraction and one multiplication separate the index values from n'/n.
-#define ATMRT_RK4_ROUND(aA, bA, wB, aB, kbA, bB, kbB)                                                            \
+    // one subtraction and one multiplication separate the index values from n'/n. FALLBACK: take the
+    // libm path for a lane whose cell cannot serve it (branchy); otherwise just record the fact.
+#define ATMRT_RK4_ROUND(FALLBACK, aA, bA, wB, aB, kbA, bB, kbB)                                                  \
     const double aB = fma(wB, bA, a);                                                                            \
     double kbA, bB, kbB;                                                                                         \
     {                                                                                                            \
@@ -321,7 +313,11 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
         const double hh = (FLAT ? sel : sel - radius) + off;                                                     \
         bool bad;                                                                                                \
         double mine = env_n_fast<DRY>(S.atm, cells, hh, fma(sel, 1.0 / ATM_CELL, xc), &bad);                     \
-        if (bad) mine = env_n_slow<DRY>(S.atm, hh);                                                              \
+        if (FALLBACK) {                                                                                          \
+            if (bad) mine = env_n_slow<DRY>(S.atm, hh);                                                          \
+        } else {                                                                                                 \
+            any_bad = any_bad || bad;                                                                            \
+        }                                                                                                        \
         const double r50 = 50.0 * rcp_1p(mine - 1.0);                                                            \
         const double bbA = bA * bA;                                                                              \
         const double sA = FLAT ? 1.0 + bbA : fma(aA, aA, bbA);                                                   \
@@ -338,42 +334,80 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
         const double cB = FLAT ? 0.0 : fma(2.0 * bbB, inv_aB, aB);                                               \
         kbB = fma((op - om) * rB, sB, cB);                                                                       \
     }
-
-#pragma unroll 1
-    for (int i = 1; i < S.n_t; ++i) {
-        // When the state is NaN (the ray climbed above the altitude where the last temperature function
-        // reaches 0 K, e.g. 178 km for US-76) every later state is NaN as well and only the independent
-        // variable keeps advancing: x = t * R, h = NaN, path_length = NaN, exactly what the arithmetic
-        // below produces (NaN in, NaN out), so nothing special is needed for the values -- only speed:
-        // a warp whose rows are all NaN or finished skips the evaluations.
-        if (!__all_sync(FULL, done || a != a)) {
-            // stages 1 and 2 (altitudes a and a + d/2 b are both known now), then stages 3 and 4
-            ATMRT_RK4_ROUND(a, b, hd, a2, kb1, b2, kb2)
-            const double a3 = fma(hd, b2, a), b3 = fma(hd, kb2, b);
-            ATMRT_RK4_ROUND(a3, b3, d, a4, kb3, b4, kb4)
-            // y += (k1 + 2 k2 + 2 k3 + k4) d / 6
-            a = fma((b + 2.0 * b2) + (2.0 * b3 + b4), d6, a);
-            b = fma((kb1 + 2.0 * kb2) + (2.0 * kb3 + kb4), d6, b);
-        }
-        t += d;
-        const RayState nw = FLAT ? RayState{t, a} : RayState{t * radius, a - radius};
-        {  // calc_dist, utils.rs:42-53 (dx / R as dx * (1/R): off the chain, but it still costs issue slots)
-            double dx = nw.x - prev.x;
-            const double dh = nw.h - prev.h;
-            if (!FLAT) dx = dx * inv_radius * ((nw.h + prev.h) * 0.5 + radius);
-            path_length += sqrt(dx * dx + dh * dh);
-        }
-        if (writer && !done) {
-            const size_t o = (size_t)i * hp + y;
-            B.p_dist[o] = nw.x;
-            B.p_elev[o] = nw.h;
-            B.p_len[o] = path_length;
-            n = i + 1;
-        }
-        if (prev.x > S.max_distance || prev.h < -1000.0) done = true;
-        if (__all_sync(FULL, done)) break;
-        prev = nw;
+    // Outputs of step i-1 (`cur`, reached from `prev`): calc_dist (utils.rs:42-53, dx / R as dx * (1/R)), the
+    // three cache entries, and the termination test of utils.rs:167-170 on the state before it. Branch-free
+    // so that it can be scheduled in the shadow of the integration chain; for i == 1 it (re)writes the
+    // initial element (0, alt, 0).
+#define ATMRT_PATH_OUTPUTS()                                                                                     \
+    {                                                                                                            \
+        double dx = cur.x - prev.x;                                                                              \
+        const double dh = cur.h - prev.h;                                                                        \
+        if (!FLAT) dx = dx * inv_radius * ((cur.h + prev.h) * 0.5 + radius);                                     \
+        const double seg = sqrt_nr(dx * dx + dh * dh);                                                           \
+        path_length = i >= 2 ? path_length + seg : 0.0;                                                          \
+        const bool emit = writer && !done;                                                                       \
+        const size_t o = (size_t)(i - 1) * hp;                                                                   \
+        stg_if(o_dist + o, cur.x, emit);                                                                         \
+        stg_if(o_elev + o, cur.h, emit);                                                                         \
+        stg_if(o_len + o, path_length, emit);                                                                    \
+        n = emit ? i : n;                                                                                        \
+        done = done || (i >= 2 && (prev.x > S.max_distance || prev.h < -1000.0));                                \
     }
+
+    // stepper state: spherical (r, dr/dphi, phi) or flat (h, dh/dx, x). The loop is software-pipelined:
+    // iteration i integrates step i (the latency chain) while the outputs of step i-1 are produced in its
+    // shadow (between the two rounds).
+    double a = FLAT ? alt : radius + alt;
+    double b = FLAT ? tan(to_radians(get_ray_elev(S, y))) : a * tan(to_radians(get_ray_elev(S, y)));
+    double t = 0.0;
+    RayState prev{0.0, alt};  // state i-2
+    RayState cur{0.0, alt};   // state i-1
+    double path_length = 0.0;
+    int n = 1;
+    bool done = false;  // this row's cache is complete
+    int i = 1;
+#pragma unroll 1
+    for (; i < S.n_t; ++i) {
+        // A NaN state (the ray climbed above the altitude where the last temperature function reaches
+        // 0 K, e.g. 178 km for US-76) stays NaN: x = t R, h = NaN, path_length = NaN, exactly what the
+        // arithmetic produces (NaN in, NaN out). When every row of the warp is complete or NaN the
+        // integration stops (tested on the incoming state, acted upon at the end of the iteration).
+        const bool idle = __all_sync(FULL, done || a != a);
+        bool any_bad = false;
+        ATMRT_RK4_ROUND(false, a, b, hd, a2, kb1, b2, kb2)   // stages 1 and 2: altitudes a and a + d/2 b are both known
+        ATMRT_PATH_OUTPUTS()
+        const double a3 = fma(hd, b2, a), b3 = fma(hd, kb2, b);
+        ATMRT_RK4_ROUND(false, a3, b3, d, a4, kb3, b4, kb4)  // stages 3 and 4
+        // y += (k1 + 2 k2 + 2 k3 + k4) d / 6
+        double a_new = fma((b + 2.0 * b2) + (2.0 * b3 + b4), d6, a);
+        double b_new = fma((kb1 + 2.0 * kb2) + (2.0 * kb3 + kb4), d6, b);
+        if (__any_sync(FULL, any_bad)) {  // rare: a lane left the anchor table (boundary cell, > 194 km, < -2 km): redo
+            ATMRT_RK4_ROUND(true, a, b, hd, a2s, kb1s, b2s, kb2s)
+            const double a3s = fma(hd, b2s, a), b3s = fma(hd, kb2s, b);
+            ATMRT_RK4_ROUND(true, a3s, b3s, d, a4s, kb3s, b4s, kb4s)
+            a_new = fma((b + 2.0 * b2s) + (2.0 * b3s + b4s), d6, a);
+            b_new = fma((kb1s + 2.0 * kb2s) + (2.0 * kb3s + kb4s), d6, b);
+        }
+        a = a_new, b = b_new;
+        t += d;
+        prev = cur;
+        cur = FLAT ? RayState{t, a} : RayState{t * radius, a - radius};
+        if (idle || __all_sync(FULL, done)) {
+            ++i;
+            break;
+        }
+    }
+    // Here cur = state i-1 and the outputs of steps < i-1 are written. Rows that are NaN keep advancing
+    // the independent variable only; then the last state's outputs.
+#pragma unroll 1
+    for (; i <= S.n_t; ++i) {
+        ATMRT_PATH_OUTPUTS()
+        if (__all_sync(FULL, done)) break;
+        t += d;
+        prev = cur;
+        cur = FLAT ? RayState{t, a} : RayState{t * radius, a - radius};
+    }
+#undef ATMRT_PATH_OUTPUTS
 #undef ATMRT_RK4_ROUND
     if (writer) {
         B.p_n[y] = n;
