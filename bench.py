@@ -337,7 +337,8 @@ def run_b200(args):
              "march": st["ray_steps"] / world}
     stage_ms = {"terrain": ms_a, "paths": ms_b, "march": ms_c}
     dom = max(stage_ms, key=stage_ms.get)
-    roof = roofline(dom, stage_ms[dom], units[dom], params, fp, args)
+    roofs = {k: roofline(k, stage_ms[k], units[k], params, fp, args) for k in stage_ms}
+    roof = roofs[dom]
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -357,6 +358,8 @@ def run_b200(args):
         "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roof,
+        "roofline_stages": {k: {f: v[f] for f in ("kernel", "achieved", "peak", "frac", "unit", "launch_ms", "units_per_launch", "traffic")}
+                            for k, v in roofs.items()},
         "cpu_baseline": cpu,
         "fp64_peak_measured": fp,
         "pixels_hit": st["pixels_hit"], "step_overflows": st["step_overflows"],
@@ -381,12 +384,23 @@ def roofline(stage, ms, units, params, fp, args):
     bytes_unit = hbm_bytes_per_unit(stage, params)
     return {
         "kernel": STAGE_UNITS[stage][0], "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "G FP64 instr/s",
-        "frac": achieved / peak if peak else None, "traffic": None,
+        "frac": achieved / peak if peak else None, "traffic": ncu_traffic(STAGE_UNITS[stage][0], args),
         "units_per_launch": units, "unit_name": STAGE_UNITS[stage][1], "fp64_instr_per_unit": per_unit, "launch_ms": ms,
         "peak_source": "measured live (atmrt_fp64_peak: 8 independent DFMA chains/thread); MEASURED_PEAKS.json has no FP64 entry",
         "hbm": {"algorithmic_bytes_per_unit": bytes_unit, "achieved_gbs": bytes_unit * units / (ms * 1e-3) / 1e9 if ms > 0 else 0.0,
                 "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs"},
     }
+
+
+def ncu_traffic(kernel, args):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` on this workload, from the
+    committed ncu --set full capture (profiles/traffic.json); None when no capture matches."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = table.get(f"{args.workload}:{kernel}") if args.gpus == 1 and args.scale == 1.0 else None
+        return None if e is None else {"bytes": e["dram_bytes"], "source": e["source"]}
+    except Exception:
+        return None
 
 
 def fp64_instr_per_unit(stage, params):
