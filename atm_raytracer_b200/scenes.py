@@ -72,6 +72,8 @@ def make_scene(name, scale=1.0):
         view["position"] = {"latitude": 45.05, "longitude": 6.0, "altitude": {"Absolute": 1800.0}}
         c["simulation_step"] = 50.0
         grid = (45, 5, 2, 2)
+        if name == "c2":
+            out["file_metadata"] = "./output.dat"  # BASELINE config 2 is the one "with --output-meta"
         if name == "c3_flat":
             c["earth_shape"] = "FlatDistorted"
         if name == "c4":
