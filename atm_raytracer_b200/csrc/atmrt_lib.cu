@@ -66,6 +66,8 @@ struct atmrt_ctx {
     std::vector<double> dist_k;
     std::vector<double> atm_cells;
     DevBuf d_atm_cells;
+    DevBuf d_sweep_flags, d_sweep_col, d_sweep_hit;
+    bool sweep_enabled = true;
     DevBuf d_dist, d_colcalc, d_tlat, d_tlon, d_telev, d_tnx, d_tny, d_tnz, d_tclose;
     DevBuf d_pdist, d_pelev, d_plen, d_pn;
     DevBuf d_tmin1, d_tmax1, d_tmin2, d_tmax2, d_tmin3, d_tmax3, d_close1, d_close2, d_close3;
@@ -147,6 +149,7 @@ int make_layout(atmrt_ctx* ctx, const atmrt_tile_desc* descs, int n, TerrainLayo
         DevTile& t = L->tiles[i];
         t.min_lat = d.min_lat, t.min_lon = d.min_lon;
         t.lat_interval = d.lat_interval, t.lon_interval = d.lon_interval;
+        t.inv_lat_interval = 1.0 / d.lat_interval, t.inv_lon_interval = 1.0 / d.lon_interval;
         t.max_lat = d.min_lat + (double)(d.nlat - 1) * d.lat_interval / 3600.0;
         t.max_lon = d.min_lon + (double)(d.nlon - 1) * d.lon_interval / 3600.0;
         t.nlat = d.nlat, t.nlon = d.nlon;
@@ -196,13 +199,19 @@ void build_atm_table(const DevAtmosphere& a, std::vector<double>& cells) {
             if (a.layer[i].start > lo && a.layer[i].start <= hi) whole = false;
         const DevAtmLayer& l = a.layer[li];
         const double t_lo = host_layer_temperature(l, lo), t_hi = host_layer_temperature(l, hi), tj = host_layer_temperature(l, hj);
-        if (!whole || !(t_lo >= 60.0) || !(t_hi >= 60.0)) continue;
+        if (!whole || !(t_lo >= 1.0) || !(t_hi >= 1.0)) continue;
         const double pj = host_layer_pressure(l, hj);
-        if (!(pj > 0.0) || !std::isfinite(pj)) continue;
+        if (!(pj > 1e-280) || !std::isfinite(pj)) continue;
         const bool linear = l.gradient != 0.0;
         const double k = linear ? l.gradient / tj : l.gm / l.rt;  // d ln T / dh, or d ln p / dh for an isothermal function
-        const double w_max = std::fabs(k) * 0.51 * ATM_CELL;
-        if (linear ? (w_max > ATM_W_MAX || std::fabs(l.expo) * w_max > ATM_V_MAX) : w_max > ATM_V_MAX) continue;
+        // Validity: the truncation errors of the two series (log1p after w^7, exp after v^9), as an absolute
+        // error of n, must stay below 3e-20 -- four orders under the rounding of `1 + x`. n - 1 scales with
+        // p / T, so the thin air far above the real atmosphere tolerates the larger |w| of its cold cells.
+        const double w_max = std::fabs(k) * 0.51 * ATM_CELL * (linear ? 1.0 : 0.0);
+        const double v_max = linear ? std::fabs(l.expo) * w_max * (1.0 + w_max) : std::fabs(k) * 0.51 * ATM_CELL;
+        const double err_rel = (linear ? std::fabs(l.expo) * std::pow(w_max, 8) / 8.0 : 0.0) + std::pow(v_max, 10) / 3628800.0;
+        const double n_minus_1 = 2.9e-4 * (pj / 101325.0) * (288.15 / std::min(t_lo, t_hi)) * std::exp(v_max);
+        if (!(w_max < 0.25) || !(v_max < 1.0) || !(err_rel * n_minus_1 <= 3e-20)) continue;
         cells[0 * ATM_CELLS + j] = pj;
         cells[1 * ATM_CELLS + j] = tj;
         cells[2 * ATM_CELLS + j] = l.gradient;
@@ -377,7 +386,7 @@ int prepare_render(atmrt_ctx* ctx) {
     e |= ensure(ctx, ctx->d_pdist, f8 * hp * n_t);
     e |= ensure(ctx, ctx->d_pelev, f8 * hp * n_t);
     e |= ensure(ctx, ctx->d_plen, f8 * hp * n_t);
-    e |= ensure(ctx, ctx->d_pn, sizeof(int) * h);
+    e |= ensure(ctx, ctx->d_pn, sizeof(int) * hp);
     e |= ensure(ctx, ctx->d_tmin1, f8 * wl * S.n1_pad);
     e |= ensure(ctx, ctx->d_tmax1, f8 * wl * S.n1_pad);
     e |= ensure(ctx, ctx->d_tmin2, f8 * wl * S.n2);
@@ -398,6 +407,9 @@ int prepare_render(atmrt_ctx* ctx) {
     (void)h;
     e |= ensure(ctx, ctx->d_obs, f8);
     e |= ensure(ctx, ctx->d_atm_cells, f8 * ATM_FIELDS * ATM_CELLS);
+    e |= ensure(ctx, ctx->d_sweep_flags, 16);
+    e |= ensure(ctx, ctx->d_sweep_col, wl);
+    e |= ensure(ctx, ctx->d_sweep_hit, sizeof(int) * wl * hp);
     build_atm_table(S.atm, ctx->atm_cells);
     e |= ensure(ctx, ctx->d_counters, 8 * CNT_COUNT);
     e |= ensure(ctx, ctx->d_objects, sizeof(DevObject) * std::max(1, S.nobjects));
@@ -426,6 +438,9 @@ int prepare_render(atmrt_ctx* ctx) {
     B.objects = (DevObject*)ctx->d_objects.p;
     B.counters = (unsigned long long*)ctx->d_counters.p;
     B.atm_cells = (const double*)ctx->d_atm_cells.p;
+    B.sweep_flags = (unsigned*)ctx->d_sweep_flags.p;
+    B.sweep_col = (unsigned char*)ctx->d_sweep_col.p;
+    B.sweep_hit = (int*)ctx->d_sweep_hit.p;
     return 0;
 }
 
@@ -493,25 +508,20 @@ int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main) {
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 8 * CNT_COUNT, main));
     k_prepare_scene<<<(S.nobjects + 1 + 63) / 64, 64, 0, main>>>(S, ctx->terrain, B, (const atmrt_object*)ctx->d_objects_in.p);
     ctx->launches++;
+
+    // Opaque terrain without objects ends every pixel at its first crossing: the horizon sweep
+    // (kernels.cuh) finds those in O(N_t + H) per column when the rays of this render do not cross each
+    // other, which k_path_check verifies on the device; the general march is launched behind it as the
+    // fallback (it returns at once when the sweep served the image).
+    const bool trace = rt.points != nullptr || rt.counts != nullptr;
+    const bool brute = ctx->march_mode == 1, objs = S.nobjects > 0;
+    const bool sweep = ctx->sweep_enabled && !objs && !trace && !brute && ctx->params.terrain_alpha == 1.0;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_sweep_flags.p, 0, 16, main));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_prep, main));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_a, ctx->ev_prep, 0));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_b, ctx->ev_prep, 0));
 
-    // Stage A on s_a
-    if (timed) CUDA_TRY(ctx, cudaEventRecord(E->a0, ctx->s_a));
-    k_column_setup<<<(wl + 127) / 128, 128, 0, ctx->s_a>>>(S, B);
-    k_terrain_profile<<<dim3((S.n_t + 127) / 128, wl), 128, 0, ctx->s_a>>>(S, ctx->terrain, B);
-    {
-        long long warps = (long long)wl * S.n2;
-        k_terrain_pyramid<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ctx->s_a>>>(B.t_elev, B.t_close, wl, S.n_t, S.n_pad, S.n1, S.n1_pad, S.n2,
-                                                                                    B.tmin1, B.tmax1, B.tmin2, B.tmax2, B.close1, B.close2);
-        k_terrain_top<<<(wl + 127) / 128, 128, 0, ctx->s_a>>>(B.tmin2, B.tmax2, B.close2, wl, S.n2, B.tmin3, B.tmax3, B.close3);
-    }
-    ctx->launches += 4;
-    if (timed) CUDA_TRY(ctx, cudaEventRecord(E->a1, ctx->s_a));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->s_a));
-
-    // Stage B on s_b
+    // Stage B on s_b: all rows (every column needs every row)
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->b0, ctx->s_b));
     {
         const int rb = (h + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
@@ -525,31 +535,72 @@ int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main) {
             if (dry) k_ray_paths<false, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
             else     k_ray_paths<false, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
         }
+        ctx->launches++;
     }
-    k_path_pyramid1<<<dim3((h + 255) / 256, S.n1), 256, 0, ctx->s_b>>>(B.p_elev, B.p_n, h, S.h_pad, S.n_t, S.n1, B.rmin1, B.rmax1);
-    k_path_pyramid23<<<(h + 255) / 256, 256, 0, ctx->s_b>>>(h, S.h_pad, S.n1, S.n2, B.rmin1, B.rmax1, B.rmin2, B.rmax2, B.rmin3, B.rmax3);
-    ctx->launches += 3;
+    auto path_pyramids = [&](cudaStream_t st, int only_if_not_swept) {
+        k_path_pyramid1<<<dim3((h + 255) / 256, S.n1), 256, 0, st>>>(B.p_elev, B.p_n, h, S.h_pad, S.n_t, S.n1, B.rmin1, B.rmax1,
+                                                                     only_if_not_swept ? B.sweep_flags : nullptr);
+        k_path_pyramid23<<<(h + 255) / 256, 256, 0, st>>>(h, S.h_pad, S.n1, S.n2, B.rmin1, B.rmax1, B.rmin2, B.rmax2, B.rmin3, B.rmax3,
+                                                          only_if_not_swept ? B.sweep_flags : nullptr);
+        ctx->launches += 2;
+    };
+    if (sweep) {
+        k_path_check<<<dim3((h + 255) / 256, (S.n_t + 63) / 64), 256, 0, ctx->s_b>>>(B.p_elev, B.p_n, h, S.h_pad, S.n_t, B.sweep_flags);
+        ctx->launches++;
+    } else {
+        path_pyramids(ctx->s_b, 0);
+    }
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->b1, ctx->s_b));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->s_b));
+
+    // Stage A on s_a
+    if (timed) CUDA_TRY(ctx, cudaEventRecord(E->a0, ctx->s_a));
+    k_column_setup<<<(wl + 127) / 128, 128, 0, ctx->s_a>>>(S, B);
+    k_terrain_profile<<<dim3((S.n_t + 127) / 128, wl), 128, 0, ctx->s_a>>>(S, ctx->terrain, B, 0);
+    ctx->launches += 2;
+    auto terrain_pyramids = [&](cudaStream_t st, int only_if_not_swept) {
+        const long long warps = (long long)wl * S.n2;
+        k_terrain_pyramid<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(B.t_elev, B.t_close, wl, S.n_t, S.n_pad, S.n1, S.n1_pad, S.n2, B.tmin1,
+                                                                                B.tmax1, B.tmin2, B.tmax2, B.close1, B.close2,
+                                                                                only_if_not_swept ? B.sweep_flags : nullptr);
+        k_terrain_top<<<(wl + 127) / 128, 128, 0, st>>>(B.tmin2, B.tmax2, B.close2, wl, S.n2, B.tmin3, B.tmax3, B.close3,
+                                                        only_if_not_swept ? B.sweep_flags : nullptr);
+        ctx->launches += 2;
+    };
+    if (!sweep) terrain_pyramids(ctx->s_a, 0);
+    if (timed) CUDA_TRY(ctx, cudaEventRecord(E->a1, ctx->s_a));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->s_a));
 
     // Stage C on main
     CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_a, 0));
     CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_b, 0));
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->c0, main));
     MarchOut O{rt.rgb, rt.meta, rt.steps, rt.points, rt.counts, rt.max_points};
-    const bool trace = rt.points != nullptr || rt.counts != nullptr;
-    const bool brute = ctx->march_mode == 1, objs = S.nobjects > 0;
     const dim3 grid((h + MARCH_THREADS - 1) / MARCH_THREADS, wl);
-#define ATMRT_LAUNCH_MARCH(OB, BR, TR) k_march<OB, BR, TR><<<grid, MARCH_THREADS, 0, main>>>(S, B, O)
-    if (objs) {
-        if (brute) { if (trace) ATMRT_LAUNCH_MARCH(true, true, true); else ATMRT_LAUNCH_MARCH(true, true, false); }
-        else       { if (trace) ATMRT_LAUNCH_MARCH(true, false, true); else ATMRT_LAUNCH_MARCH(true, false, false); }
+    if (sweep) {
+        k_sweep<<<(wl + SWEEP_THREADS / 32 - 1) / (SWEEP_THREADS / 32), SWEEP_THREADS, 0, main>>>(S, B);
+        k_sweep_shade<<<dim3((h + 31) / 32, (wl + SHADE_COLS - 1) / SHADE_COLS), 32 * SHADE_COLS, 0, main>>>(S, B, O);
+        ctx->launches += 2;
+        // fallbacks, no-ops unless the device-side checks ask for them: pyramids + hierarchical march of the
+        // whole image (rays cross), brute-force march of flagged columns
+        terrain_pyramids(main, 1);
+        path_pyramids(main, 1);
+        const dim3 fgrid(grid.x, std::min(wl, 64));
+        k_march<false, false, false><<<fgrid, MARCH_THREADS, 0, main>>>(S, B, O, MARCH_IF_NOT_SWEPT);
+        k_march<false, true, false><<<fgrid, MARCH_THREADS, 0, main>>>(S, B, O, MARCH_FLAGGED_COLUMNS);
+        ctx->launches += 2;
     } else {
-        if (brute) { if (trace) ATMRT_LAUNCH_MARCH(false, true, true); else ATMRT_LAUNCH_MARCH(false, true, false); }
-        else       { if (trace) ATMRT_LAUNCH_MARCH(false, false, true); else ATMRT_LAUNCH_MARCH(false, false, false); }
-    }
+#define ATMRT_LAUNCH_MARCH(OB, BR, TR) k_march<OB, BR, TR><<<grid, MARCH_THREADS, 0, main>>>(S, B, O, MARCH_ALWAYS)
+        if (objs) {
+            if (brute) { if (trace) ATMRT_LAUNCH_MARCH(true, true, true); else ATMRT_LAUNCH_MARCH(true, true, false); }
+            else       { if (trace) ATMRT_LAUNCH_MARCH(true, false, true); else ATMRT_LAUNCH_MARCH(true, false, false); }
+        } else {
+            if (brute) { if (trace) ATMRT_LAUNCH_MARCH(false, true, true); else ATMRT_LAUNCH_MARCH(false, true, false); }
+            else       { if (trace) ATMRT_LAUNCH_MARCH(false, false, true); else ATMRT_LAUNCH_MARCH(false, false, false); }
+        }
 #undef ATMRT_LAUNCH_MARCH
-    ctx->launches++;
+        ctx->launches++;
+    }
     if (timed) {
         CUDA_TRY(ctx, cudaEventRecord(E->c1, main));
         CUDA_TRY(ctx, cudaEventRecord(E->t1, main));
@@ -654,7 +705,7 @@ void atmrt_destroy(atmrt_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_objects_in, &ctx->d_objects, &ctx->d_dist, &ctx->d_colcalc, &ctx->d_tlat, &ctx->d_tlon, &ctx->d_telev,
                       &ctx->d_tnx, &ctx->d_tny, &ctx->d_tnz, &ctx->d_tclose, &ctx->d_pdist, &ctx->d_pelev, &ctx->d_plen, &ctx->d_pn,
                       &ctx->d_tmin1, &ctx->d_tmax1, &ctx->d_tmin2, &ctx->d_tmax2, &ctx->d_tmin3, &ctx->d_tmax3, &ctx->d_close1, &ctx->d_close2, &ctx->d_close3, &ctx->d_rmin1, &ctx->d_rmin3, &ctx->d_rmax3,
-                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_rgb, &ctx->d_meta,
+                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_sweep_flags, &ctx->d_sweep_col, &ctx->d_sweep_hit, &ctx->d_rgb, &ctx->d_meta,
                       &ctx->d_steps, &ctx->d_points, &ctx->d_counts, &ctx->d_probe_a, &ctx->d_probe_b, &ctx->d_probe_c, &ctx->d_probe_d};
     for (DevBuf* b : bufs) release(*b);
     for (DevBuf& b : ctx->textures) release(b);
@@ -834,8 +885,9 @@ int atmrt_set_objects(atmrt_ctx* ctx, const atmrt_object* objects, int nobjects,
 }
 
 int atmrt_set_march_mode(atmrt_ctx* ctx, int mode) {
-    if (!ctx || (mode != 0 && mode != 1)) return fail(ctx, ATMRT_ERR_INVALID, "march mode must be 0 or 1");
-    ctx->march_mode = mode;
+    if (!ctx || mode < 0 || mode > 2) return fail(ctx, ATMRT_ERR_INVALID, "march mode must be 0, 1 or 2");
+    ctx->march_mode = mode == 1 ? 1 : 0;
+    ctx->sweep_enabled = mode == 0;
     return 0;
 }
 

@@ -64,6 +64,7 @@ constexpr int MT = 8;  // micro-tile edge in posts
 struct DevTile {
     double min_lat, min_lon, max_lat, max_lon;
     double lat_interval, lon_interval;  // arc-seconds
+    double inv_lat_interval, inv_lon_interval;  // RN(1 / interval), for the exact division below
     int nlat, nlon;
     int mt_lat;           // micro-tiles along latitude
     int _pad;
@@ -82,11 +83,19 @@ __device__ __forceinline__ long long post_index(const DevTile& t, int ilon, int 
     return t.post_offset + ((long long)((ilon >> 3) * t.mt_lat + (ilat >> 3)) << 6) + ((ilon & 7) << 3) + (ilat & 7);
 }
 
+// a / b correctly rounded from y = RN(1/b) (Markstein: q0 = RN(a y), r = a - b q0 exactly by FMA,
+// q = RN(q0 + r y)); a finite, b a normal number whose significand is not all ones. Same bits as the
+// IEEE division the reference performs, without the division's slow-path bookkeeping.
+__device__ __forceinline__ double div_by(double a, double b, double y) {
+    const double q = a * y;
+    return fma(fma(-b, q, a), y, q);
+}
+
 // DtedData::get_elev (external; bilinear form witnessed by terrain/geotiff.rs:61-100)
 __device__ __forceinline__ bool tile_get_elev(const DevTerrain& T, const DevTile& t, double lat, double lon, double* out) {
     if (lat < t.min_lat || lat > t.max_lat || lon < t.min_lon || lon > t.max_lon) return false;
-    double plat = (lat - t.min_lat) * 3600.0 / t.lat_interval;
-    double plon = (lon - t.min_lon) * 3600.0 / t.lon_interval;
+    double plat = div_by((lat - t.min_lat) * 3600.0, t.lat_interval, t.inv_lat_interval);
+    double plon = div_by((lon - t.min_lon) * 3600.0, t.lon_interval, t.inv_lon_interval);
     int lat_int = (int)plat, lon_int = (int)plon;  // in [0, n-1] after the bounds check
     double lat_frac = plat - (double)lat_int, lon_frac = plon - (double)lon_int;
     if (lat_int == t.nlat - 1) {

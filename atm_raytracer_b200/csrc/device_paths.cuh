@@ -24,9 +24,10 @@
 //  4. The remaining divisions use reciprocals: MUFU.RCP64H + two Newton steps for 1/T and 1/r (issued
 //     early, they overlap the series), geometric series for 1/Z and 1/n (both within 1e-2 of 1).
 //  5. The fast path is one straight-line block: cells it cannot serve (a temperature-function
-//     boundary inside the cell, T < 60 K, |w| too large, outside the table, NaN altitude) hold NaN
+//     boundary inside the cell, series not accurate enough, outside the table, NaN altitude) hold NaN
 //     anchors, and a NaN result sends that one evaluation to the libm path of device_atm.cuh, which
-//     is the arithmetic the oracle restates op for op.
+//     is the arithmetic the oracle restates op for op. A cell is served when the truncation errors of
+//     the two series, as an absolute error of n, stay below 3e-20 (atmrt_lib.cu:build_atm_table).
 //
 // Accuracy: p and (n - 1) carry ~1e-16 relative error, i.e. 3e-20 absolute in n -- four orders below
 // the rounding of `1.0 + x` (1.1e-16) that the reference's own finite difference carries as noise (a
@@ -41,7 +42,6 @@ constexpr int ATM_CELLS = 768;  // 256 m cells centred on ATM_BASE + j * 256 m, 
 constexpr double ATM_CELL = 256.0;
 constexpr double ATM_BASE = -2048.0;
 constexpr int ATM_FIELDS = 5;   // per cell: p_j, T_j, g (K/m), w scale, alpha
-constexpr double ATM_W_MAX = 8.0e-3, ATM_V_MAX = 8.0e-2;  // validity of the two series
 // An isothermal function p_j exp(k dh) is served by the same formula as a linear one,
 // p_j (1 + w)^alpha with w = k dh 2^-50 and alpha = 2^50 (relative error |k dh| 2^-51 < 1e-17).
 constexpr double ATM_ISO_SCALE = 1125899906842624.0;  // 2^50

@@ -55,6 +55,9 @@ struct DevBuffers {
     double* obs_alt;  // [1]
     DevObject* objects;
     unsigned long long* counters;  // see Counter
+    unsigned* sweep_flags;   // [1]: bit 0 = the path cache of this render is not monotone in the row (no sweep)
+    unsigned char* sweep_col;  // [wl]: 1 = column needs the general march
+    int* sweep_hit;          // [wl][h_pad]: first-hit step per pixel (0 = none)
     const double* atm_cells;  // hydrostatic anchors of the ray-path stage (device_paths.cuh): [ATM_FIELDS][ATM_CELLS]
 };
 
@@ -188,9 +191,10 @@ __device__ __forceinline__ V3 find_normal(const DevScene& S, const DevTerrain& T
         // Near the poles (|lat| > 85 deg) the expansions lose accuracy: use the walk itself.
         D = spherical_directions_sc(sinlat, coslat, sinlon, coslon);
         if (fabs(lat) <= 85.0) {
-            const double q = S.tan_diff / coslat;
+            const double icos = 1.0 / coslat;
+            const double q = S.tan_diff * icos;
             const double dlon = to_degrees(q - q * q * q * (1.0 / 3.0));
-            const double lat_ew = lat - to_degrees(sinlat / coslat * S.versin_diff);
+            const double lat_ew = lat - to_degrees(sinlat * icos * S.versin_diff);
             n_lat = lat + S.diff_deg, n_lon = lon;
             s_lat = lat - S.diff_deg, s_lon = lon;
             e_lat = lat_ew, e_lon = lon + dlon;
@@ -215,22 +219,41 @@ __device__ __forceinline__ V3 find_normal(const DevScene& S, const DevTerrain& T
 // Stage A: terrain profile. One thread per (column, sample); lanes run along the ray so the
 // [column][k] stores are coalesced and the bilinear taps of a warp walk along one azimuth.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__ DevScene S, DevTerrain T, DevBuffers B) {
+__global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__ DevScene S, DevTerrain T, DevBuffers B, int col0) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
-    int xl = blockIdx.y;
+    int xl = col0 + blockIdx.y;  // the render is issued in column chunks (atmrt_lib.cu:launch_render)
     if (k >= S.n_t) return;
     const double d = B.dist_k[k];
     const double* cc = B.colcalc + (size_t)xl * 8;
     double lat, lon;
+    double sinlat, coslat, sinlon, coslon;  // of the sample's coordinates, for find_normal and is_close
     if (S.flat) {  // FlDsCalc::coords_at_dist, directional_calc.rs:41-47
         double d_lat = cc[0] * d / DEGREE_DISTANCE;
         double d_lon = cc[1] * d / DEGREE_DISTANCE / cc[2];
         lat = S.lat0 + d_lat;
         lon = S.lon0 + d_lon;
+        sincos(to_radians(lat), &sinlat, &coslat);
+        sincos(to_radians(lon), &sinlon, &coslon);
     } else {  // SphericalCalc::coords_at_dist, directional_calc.rs:71-86
         double sinang, cosang;
         sincos(d / S.radius, &sinang, &cosang);
-        spherical_walk(V3{cc[3], cc[4], cc[5]}, V3{cc[0], cc[1], cc[2]}, sinang, cosang, &lat, &lon);
+        const V3 fpos = V3{cc[3], cc[4], cc[5]} * cosang + V3{cc[0], cc[1], cc[2]} * sinang;
+        lat = to_degrees(asin(fpos.z));
+        lon = to_degrees(atan2(fpos.y, fpos.x));
+        // fpos is the unit vector of (lat, lon): its components ARE sin(lat), cos(lat) cos(lon), cos(lat) sin(lon)
+        // to the rounding of the walk (|fpos| = 1 +- 2e-16), so the reference's sin/cos of the degree values
+        // (world_directions, as_cartesian) are recovered without four more libm calls. Near the poles
+        // (cos lat < 0.05) the division loses bits: evaluate them from the angles as the reference does.
+        const double c2 = fpos.x * fpos.x + fpos.y * fpos.y;
+        if (c2 > 0.0025) {
+            sinlat = fpos.z;
+            coslat = sqrt(c2);
+            const double ic = 1.0 / coslat;
+            sinlon = fpos.y * ic, coslon = fpos.x * ic;
+        } else {
+            sincos(to_radians(lat), &sinlat, &coslat);
+            sincos(to_radians(lon), &sinlon, &coslon);
+        }
     }
     double elev = elev_or_zero(T, lat, lon);
     size_t idx = (size_t)xl * S.n_pad + k;
@@ -238,9 +261,6 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
     B.t_lon[idx] = lon;
     B.t_elev[idx] = elev;
 
-    double sinlat, coslat, sinlon, coslon;
-    sincos(to_radians(lat), &sinlat, &coslat);
-    sincos(to_radians(lon), &sinlon, &coslon);
     V3 normal = find_normal(S, T, lat, lon, sinlat, coslat, sinlon, coslon);
     B.t_nx[idx] = normal.x;
     B.t_ny[idx] = normal.y;
@@ -457,7 +477,9 @@ __global__ void __launch_bounds__(256) k_terrain_pyramid(const double* __restric
                                                          int nrows, int n, int n_pad, int n1, int n1_pad, int n2,
                                                          double* __restrict__ min1, double* __restrict__ max1,
                                                          double* __restrict__ min2, double* __restrict__ max2,
-                                                         unsigned long long* __restrict__ close1, unsigned long long* __restrict__ close2) {
+                                                         unsigned long long* __restrict__ close1, unsigned long long* __restrict__ close2,
+                                                         const unsigned* only_if_set) {
+    if (only_if_set && *only_if_set == 0) return;  // fallback launch behind the horizon sweep
     const int lane = threadIdx.x & 31;
     long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= (long long)nrows * n2) return;
@@ -511,7 +533,9 @@ __global__ void __launch_bounds__(256) k_terrain_pyramid(const double* __restric
 
 // level 3 of the terrain pyramid: one thread per column
 __global__ void k_terrain_top(const double* __restrict__ min2, const double* __restrict__ max2, const unsigned long long* __restrict__ close2,
-                              int nrows, int n2, double* __restrict__ min3, double* __restrict__ max3, unsigned long long* __restrict__ close3) {
+                              int nrows, int n2, double* __restrict__ min3, double* __restrict__ max3, unsigned long long* __restrict__ close3,
+                              const unsigned* only_if_set) {
+    if (only_if_set && *only_if_set == 0) return;
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= nrows) return;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
@@ -529,7 +553,9 @@ __global__ void k_terrain_top(const double* __restrict__ min2, const double* __r
 
 // path pyramid level 1: thread per (row, node c); vals is step-major [k][h_pad]
 __global__ void __launch_bounds__(256) k_path_pyramid1(const double* __restrict__ vals, const int* __restrict__ lens, int h, int h_pad,
-                                                       int n_total, int n1, double* __restrict__ min1, double* __restrict__ max1) {
+                                                       int n_total, int n1, double* __restrict__ min1, double* __restrict__ max1,
+                                                       const unsigned* only_if_set) {
+    if (only_if_set && *only_if_set == 0) return;
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
     if (y >= h) return;
@@ -551,7 +577,9 @@ __global__ void __launch_bounds__(256) k_path_pyramid1(const double* __restrict_
 // path pyramid levels 2 and 3: thread per row
 __global__ void __launch_bounds__(256) k_path_pyramid23(int h, int h_pad, int n1, int n2, const double* __restrict__ min1,
                                                         const double* __restrict__ max1, double* __restrict__ min2,
-                                                        double* __restrict__ max2, double* __restrict__ min3, double* __restrict__ max3) {
+                                                        double* __restrict__ max2, double* __restrict__ min3, double* __restrict__ max3,
+                                                        const unsigned* only_if_set) {
+    if (only_if_set && *only_if_set == 0) return;
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= h) return;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
@@ -723,10 +751,65 @@ __device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers
 
 constexpr int MARCH_THREADS = 128;
 
+__device__ __forceinline__ void init_pixel(PixelState& st) {
+    st.result = Rgb8{{0, 0, 0}};
+    st.accum_neg_alpha = 1.0;
+    st.count = 0;
+    st.overflows = 0;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    st.m_lat = st.m_lon = st.m_elev = st.m_dist = qnan;
+}
+
+// draw_image tail: *px = add(result, def_color, accum_neg_alpha) (renderer/mod.rs:410), the per-pixel
+// metadata, and the render counters (one atomic per warp).
+// render counters: one atomic per warp
+__device__ __forceinline__ void count_pixel(const DevBuffers& B, bool active, const PixelState& st, int consumed) {
+    unsigned long long s_steps = active ? (unsigned long long)consumed : 0ull;
+    unsigned s_points = active ? (unsigned)st.count : 0u, s_hit = active && st.count > 0 ? 1u : 0u, s_over = active ? (unsigned)st.overflows : 0u;
+    for (int o = 16; o > 0; o >>= 1) s_steps += __shfl_xor_sync(FULL, s_steps, o);
+    s_points = __reduce_add_sync(FULL, s_points);
+    s_hit = __reduce_add_sync(FULL, s_hit);
+    s_over = __reduce_add_sync(FULL, s_over);
+    if ((threadIdx.x & 31) == 0) {
+        if (s_steps) atomicAdd(B.counters + CNT_RAY_STEPS, s_steps);
+        if (s_points) atomicAdd(B.counters + CNT_TRACE_POINTS, (unsigned long long)s_points);
+        if (s_hit) atomicAdd(B.counters + CNT_PIXELS_HIT, (unsigned long long)s_hit);
+        if (s_over) atomicAdd(B.counters + CNT_OVERFLOWS, (unsigned long long)s_over);
+    }
+}
+
+// draw_image tail: *px = add(result, def_color, accum_neg_alpha) (renderer/mod.rs:410)
+__device__ __forceinline__ Rgb8 final_color(const DevScene& S, const PixelState& st) {
+    Rgb8 def{{S.shade.def_color[0], S.shade.def_color[1], S.shade.def_color[2]}};
+    return add_rgb(st.result, def, st.accum_neg_alpha);
+}
+
+template <bool TRACE>
+__device__ __forceinline__ void write_pixel(const DevScene& S, const DevBuffers& B, const MarchOut& O, size_t pixel, bool active,
+                                            const PixelState& st, int consumed) {
+    if (active) {
+        Rgb8 px = final_color(S, st);
+        if (O.rgb) {
+            O.rgb[pixel * 3 + 0] = px.c[0];
+            O.rgb[pixel * 3 + 1] = px.c[1];
+            O.rgb[pixel * 3 + 2] = px.c[2];
+        }
+        if (O.meta) {
+            atmrt_meta mm{st.m_lat, st.m_lon, st.m_elev, st.m_dist};
+            O.meta[pixel] = mm;
+        }
+        if (O.steps) O.steps[pixel] = consumed;
+        if (TRACE && O.counts) O.counts[pixel] = st.count;
+    }
+    count_pixel(B, active, st, consumed);
+}
+
+// When a render is eligible for the horizon sweep (below) the general march is still launched, as the
+// fallback: `when` tells it for which outcome of the device-side checks it has to run.
+enum MarchWhen { MARCH_ALWAYS = 0, MARCH_IF_NOT_SWEPT = 1, MARCH_FLAGGED_COLUMNS = 2 };
+
 template <bool OBJECTS, bool BRUTE, bool TRACE>
-__global__ void __launch_bounds__(MARCH_THREADS) k_march(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O) {
-    const int lane = threadIdx.x & 31;
-    const int xl = blockIdx.y;
+__device__ __forceinline__ void march_column(const DevScene& S, const DevBuffers& B, const MarchOut& O, int xl) {
     const int y = blockIdx.x * MARCH_THREADS + threadIdx.x;
     const bool active = y < S.height;
     const int yy = active ? y : S.height - 1;  // inactive lanes shadow the last row and write nothing
@@ -737,12 +820,7 @@ __global__ void __launch_bounds__(MARCH_THREADS) k_march(const __grid_constant__
     const size_t hp = (size_t)S.h_pad;
 
     PixelState st;
-    st.result = Rgb8{{0, 0, 0}};
-    st.accum_neg_alpha = 1.0;
-    st.count = 0;
-    st.overflows = 0;
-    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    st.m_lat = st.m_lon = st.m_elev = st.m_dist = qnan;
+    init_pixel(st);
     int consumed = nlim > 0 ? nlim - 1 : 0;
     bool finished = !active || nlim < 2;
     int k = 1;
@@ -810,34 +888,205 @@ __global__ void __launch_bounds__(MARCH_THREADS) k_march(const __grid_constant__
         }
     }
 
-    // draw_image tail: *px = add(result, def_color, accum_neg_alpha)  (renderer/mod.rs:410)
-    if (active) {
-        Rgb8 def{{S.shade.def_color[0], S.shade.def_color[1], S.shade.def_color[2]}};
-        Rgb8 px = add_rgb(st.result, def, st.accum_neg_alpha);
-        if (O.rgb) {
-            O.rgb[pixel * 3 + 0] = px.c[0];
-            O.rgb[pixel * 3 + 1] = px.c[1];
-            O.rgb[pixel * 3 + 2] = px.c[2];
-        }
-        if (O.meta) {
-            atmrt_meta mm{st.m_lat, st.m_lon, st.m_elev, st.m_dist};
-            O.meta[pixel] = mm;
-        }
-        if (O.steps) O.steps[pixel] = consumed;
-        if (TRACE && O.counts) O.counts[pixel] = st.count;
+    write_pixel<TRACE>(S, B, O, pixel, active, st, consumed);
+}
+
+// grid = (rows / MARCH_THREADS, columns per pass): a block walks the columns blockIdx.y, blockIdx.y +
+// gridDim.y, ... so that the fallback launches behind the horizon sweep can use a small grid.
+template <bool OBJECTS, bool BRUTE, bool TRACE>
+__global__ void __launch_bounds__(MARCH_THREADS) k_march(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, int when) {
+    if (when == MARCH_IF_NOT_SWEPT && B.sweep_flags[0] == 0) return;
+    if (when == MARCH_FLAGGED_COLUMNS && (B.sweep_flags[0] != 0 || B.sweep_flags[1] == 0)) return;
+    const int wl = S.x1 - S.x0;
+    for (int xl = blockIdx.y; xl < wl; xl += gridDim.y) {
+        if (when == MARCH_FLAGGED_COLUMNS && B.sweep_col[xl] == 0) continue;
+        march_column<OBJECTS, BRUTE, TRACE>(S, B, O, xl);
     }
-    // counters: one atomic per warp
-    unsigned long long s_steps = active ? (unsigned long long)consumed : 0ull;
-    unsigned s_points = active ? (unsigned)st.count : 0u, s_hit = active && st.count > 0 ? 1u : 0u, s_over = active ? (unsigned)st.overflows : 0u;
-    for (int o = 16; o > 0; o >>= 1) s_steps += __shfl_xor_sync(FULL, s_steps, o);
-    s_points = __reduce_add_sync(FULL, s_points);
-    s_hit = __reduce_add_sync(FULL, s_hit);
-    s_over = __reduce_add_sync(FULL, s_over);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage C for opaque terrain without objects: the horizon sweep.
+//
+// With terrain_alpha == 1 and no objects a pixel ends at its FIRST sign change of ray - terrain
+// (utils.rs:220-239). If the rays of one column never cross each other -- r[k][y] >= r[k][y+1] for
+// every step k, row y above row y+1 -- and every ray starts above the terrain, then the first-hit step
+// is monotone in the row: while row y+1 has not hit (its differences are all > 0), the differences of
+// row y are larger still, so row y's first crossing cannot come before row y+1's. One thread per column
+// therefore walks k forward and y upward, testing exactly the reference's product on the cells it
+// visits: O(N_t + H) work per column instead of a search per pixel. k_path_check verifies the
+// monotonicity on the path cache of THIS render (any atmosphere: ducting makes rays cross); a column
+// where a visited difference is exactly 0, the start is not above the terrain, or a hit does not go
+// from above to below is flagged. The general march (k_march) runs for the whole image when the check
+// fails and for the flagged columns otherwise, so the result is always the reference's.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_path_check(const double* __restrict__ elev, const int* __restrict__ lens, int h, int h_pad, int n_t,
+                                                    unsigned* __restrict__ flags) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;  // compares row y (above) with row y + 1
+    const int k0 = blockIdx.y * 64;
+    bool bad = false;
+    if (y + 1 < h) {
+        const int n_up = min(n_t, lens[y]), n_dn = min(n_t, lens[y + 1]);
+        if (n_up < n_dn) bad = true;  // the upper ray must live at least as long
+        const int k1 = min(k0 + 64, n_dn);
+        for (int k = k0; k < k1; ++k) {
+            const double up = elev[(size_t)k * h_pad + y], dn = elev[(size_t)k * h_pad + y + 1];
+            // A NaN ray (it left the atmosphere model) never hits; it must be the upper one of the pair.
+            if (up < dn || (dn != dn && up == up)) bad = true;
+        }
+    }
+    if (__any_sync(FULL, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, 1u);
+}
+
+constexpr int SWEEP_THREADS = 128;  // one warp per column
+constexpr int SWEEP_ROWS = 4;       // rows resolved per window from one 32-byte load per lane
+
+// One warp per column. The lanes hold a window of 32 consecutive steps (lane l: step k + l) for a group of
+// SWEEP_ROWS adjacent rows at once -- the path cache is [k][row], so the rows of a group are one 32-byte
+// sector per step. The rows of the group are resolved bottom-up from those registers: row y's first event
+// in the window decides it, and the row above continues from the same step. The window advances only when
+// the lowest unresolved row has no event in it.
+__global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(const __grid_constant__ DevScene S, DevBuffers B) {
+    if (B.sweep_flags[0] != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int xl = blockIdx.x * (SWEEP_THREADS / 32) + (threadIdx.x >> 5);
+    if (xl >= S.x1 - S.x0) return;
+    const double* __restrict__ te = B.t_elev + (size_t)xl * S.n_pad;
+    const double* __restrict__ pe = B.p_elev;
+    int* __restrict__ hit = B.sweep_hit + (size_t)xl * S.h_pad;
+    const int hpi = S.h_pad;
+    bool flagged = !(pe[0] - te[0] > 0.0);  // every ray starts at the observer altitude (element 0 of every row)
+    const int k_last = S.n_t - 1;
+    int k = 1;  // first step the current row may still cross at
+    // groups of SWEEP_ROWS rows (local row 0 is the top one), bottom group first, rows bottom-up inside
+    for (int g = (S.height - 1) / SWEEP_ROWS; g >= 0 && !flagged; --g) {
+        const int ybase = g * SWEEP_ROWS;
+        int r = min(SWEEP_ROWS - 1, S.height - 1 - ybase);
+        const int4 len = *reinterpret_cast<const int4*>(B.p_n + ybase);  // p_n is padded to h_pad entries
+        const int n0 = min(S.n_t, len.x), n1 = min(S.n_t, len.y), n2 = min(S.n_t, len.z), n3 = min(S.n_t, len.w);
+        while (r >= 0 && !flagged) {
+            int nlim = r == 3 ? n3 : (r == 2 ? n2 : (r == 1 ? n1 : n0));
+            if (k >= nlim) {  // this row's path ends without a sign change
+                if (lane == 0) hit[ybase + r] = 0;
+                --r;
+                continue;
+            }
+            // the window: steps k + lane for all rows of the group; the "before" side comes from the lane below
+            const int kk = min(k + lane, k_last);
+            const double4 cur = *reinterpret_cast<const double4*>(pe + (size_t)kk * hpi + ybase);
+            const double t_cur = te[kk];
+            double4 prv;
+            prv.x = __shfl_up_sync(FULL, cur.x, 1), prv.y = __shfl_up_sync(FULL, cur.y, 1);
+            prv.z = __shfl_up_sync(FULL, cur.z, 1), prv.w = __shfl_up_sync(FULL, cur.w, 1);
+            double t_prv = __shfl_up_sync(FULL, t_cur, 1);
+            if (lane == 0) {
+                prv = *reinterpret_cast<const double4*>(pe + (size_t)(k - 1) * hpi + ybase);
+                t_prv = te[k - 1];
+            }
+            int lo = 0;        // lanes below `lo` are steps the current row cannot cross at any more
+            bool odd = false;  // an exact zero or an exit from below among the cells of this window
+            // Resolve rows from the registers while the window serves them. A crossing from above
+            // (d1 > 0 > d2, utils.rs:220-222) at the first such lane >= lo is the row's hit; the row above
+            // continues from that lane.
+#define ATMRT_SWEEP_ROW(C, R, NABOVE)                                                                        \
+    {                                                                                                        \
+        const double d1 = prv.C - t_prv, d2 = cur.C - t_cur;                                                 \
+        const bool in = k + lane < nlim;                                                                     \
+        const bool oddcell = in && lane >= lo && (d2 == 0.0 || (d1 * d2 < 0.0 && !(d1 > 0.0)));              \
+        const unsigned hits = __ballot_sync(FULL, in && lane >= lo && d1 > 0.0 && d2 < 0.0);                 \
+        odd = odd || (oddcell && (hits == 0 || lane < __ffs(hits) - 1)); /* only cells the row visits */     \
+        if (hits == 0) {                                                                                     \
+            if (k + 32 >= nlim) { /* the row ends inside the window: no hit; the row above goes on from there */ \
+                if (lane == 0) hit[ybase + R] = 0;                                                           \
+                r = R - 1;                                                                                   \
+                k = nlim;                                                                                    \
+            } else {                                                                                         \
+                r = R;                                                                                       \
+                k += 32;                                                                                     \
+            }                                                                                                \
+            lo = 0;                                                                                          \
+            goto window_done;                                                                                \
+        }                                                                                                    \
+        lo = __ffs(hits) - 1;                                                                                \
+        if (lane == 0) hit[ybase + R] = k + lo;                                                              \
+        r = R - 1;                                                                                           \
+        nlim = NABOVE;                                                                                       \
+    }
+            switch (r) {
+                case 3: ATMRT_SWEEP_ROW(w, 3, n2)
+                case 2: ATMRT_SWEEP_ROW(z, 2, n1)
+                case 1: ATMRT_SWEEP_ROW(y, 1, n0)
+                default: ATMRT_SWEEP_ROW(x, 0, n0)
+            }
+#undef ATMRT_SWEEP_ROW
+        window_done:
+            // An odd cell among those a row visits before its hit (an exact zero of ray - terrain, or an exit
+            // from below: a ray that started under the surface) sends the column to the general march.
+            if (__any_sync(FULL, odd)) flagged = true;
+            k += lo;  // the next window starts at the last hit
+        }
+    }
     if (lane == 0) {
-        if (s_steps) atomicAdd(B.counters + CNT_RAY_STEPS, s_steps);
-        if (s_points) atomicAdd(B.counters + CNT_TRACE_POINTS, (unsigned long long)s_points);
-        if (s_hit) atomicAdd(B.counters + CNT_PIXELS_HIT, (unsigned long long)s_hit);
-        if (s_over) atomicAdd(B.counters + CNT_OVERFLOWS, (unsigned long long)s_over);
+        B.sweep_col[xl] = flagged ? 1 : 0;
+        if (flagged) atomicOr(B.sweep_flags + 1, 1u);  // some column needs the brute-force march
+    }
+}
+
+// Colour, composite and write the pixels of the swept columns (get_single_pixel's hit processing +
+// draw_image). A block is a tile of 32 rows x SHADE_COLS columns: each warp shades 32 adjacent rows of
+// one column (adjacent rows hit adjacent steps, so the cache reads of a warp share sectors), the
+// results are staged in shared memory and written with the lanes running along x, so that the
+// row-major [y][x] image and metadata are stored as contiguous row segments.
+constexpr int SHADE_COLS = 16;
+
+__global__ void __launch_bounds__(32 * SHADE_COLS) k_sweep_shade(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O) {
+    if (B.sweep_flags[0] != 0) return;
+    __shared__ double s_meta[32][SHADE_COLS * 4];
+    __shared__ unsigned char s_rgb[32][SHADE_COLS * 3];
+    __shared__ int s_steps[32][SHADE_COLS];
+    __shared__ unsigned char s_skip[SHADE_COLS];
+    const int wl = S.x1 - S.x0;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c0 = blockIdx.y * SHADE_COLS, y0 = blockIdx.x * 32;
+    const int xl = c0 + w, y = y0 + lane;
+    const bool col_ok = xl < wl && B.sweep_col[xl] == 0;  // flagged columns belong to the brute-force march
+    const bool active = col_ok && y < S.height;
+    if (lane == 0) s_skip[w] = col_ok ? 0 : 1;
+    const int xx = min(xl, wl - 1), yy = min(y, S.height - 1);
+    const size_t pixel = (size_t)yy * wl + xx;
+    const int nlim = min(S.n_t, B.p_n[yy]);
+    PixelState st;
+    init_pixel(st);
+    int consumed = nlim > 0 ? nlim - 1 : 0;
+    const int k = active ? B.sweep_hit[(size_t)xx * S.h_pad + yy] : 0;
+    if (k > 0) {
+        process_step<false, false>(S, B, O, xx, yy, k, pixel, st);
+        consumed = k;
+    }
+    const Rgb8 px = final_color(S, st);
+    s_rgb[lane][w * 3 + 0] = px.c[0], s_rgb[lane][w * 3 + 1] = px.c[1], s_rgb[lane][w * 3 + 2] = px.c[2];
+    s_meta[lane][w * 4 + 0] = st.m_lat, s_meta[lane][w * 4 + 1] = st.m_lon, s_meta[lane][w * 4 + 2] = st.m_elev, s_meta[lane][w * 4 + 3] = st.m_dist;
+    s_steps[lane][w] = consumed;
+    count_pixel(B, active, st, consumed);
+    __syncthreads();
+    const int rows = min(32, S.height - y0);
+    if (O.meta) {
+        double* out = reinterpret_cast<double*>(O.meta);
+        for (int e = threadIdx.x; e < rows * SHADE_COLS * 4; e += 32 * SHADE_COLS) {
+            const int r = e / (SHADE_COLS * 4), q = e % (SHADE_COLS * 4), c = q >> 2;
+            if (c0 + c < wl && !s_skip[c]) out[((size_t)(y0 + r) * wl + c0) * 4 + q] = s_meta[r][q];
+        }
+    }
+    if (O.rgb) {
+        for (int e = threadIdx.x; e < rows * SHADE_COLS * 3; e += 32 * SHADE_COLS) {
+            const int r = e / (SHADE_COLS * 3), q = e % (SHADE_COLS * 3), c = q / 3;
+            if (c0 + c < wl && !s_skip[c]) O.rgb[((size_t)(y0 + r) * wl + c0) * 3 + q] = s_rgb[r][q];
+        }
+    }
+    if (O.steps) {
+        for (int e = threadIdx.x; e < rows * SHADE_COLS; e += 32 * SHADE_COLS) {
+            const int r = e / SHADE_COLS, c = e % SHADE_COLS;
+            if (c0 + c < wl && !s_skip[c]) O.steps[(size_t)(y0 + r) * wl + c0 + c] = s_steps[r][c];
+        }
     }
 }
 

@@ -222,8 +222,10 @@ int atmrt_stage_times(atmrt_ctx* ctx, atmrt_stage_ms* out);
 /* Full trace-point lists (ResultPixel.trace_points) for small images: points[H][x1-x0][max_points],
  * counts[H][x1-x0] (true count, may exceed max_points). Host buffers. */
 int atmrt_render_trace(atmrt_ctx* ctx, atmrt_trace_point* points, int32_t* counts, int max_points);
-/* 0 = hierarchical min/max march (default), 1 = brute-force march that visits every step like the
- * reference loop (validation + FP64 roofline mode). */
+/* 0 = default: horizon sweep for opaque terrain without objects (with the hierarchical march as its
+ * device-side fallback), hierarchical min/max march otherwise; 1 = brute-force march that visits every
+ * step like the reference loop (validation); 2 = hierarchical march always (validation of the sweep).
+ * All three produce identical images. */
 int atmrt_set_march_mode(atmrt_ctx* ctx, int mode);
 /* Tuning hook for the ray-path stage: image rows integrated per warp (1..32, default 32). */
 int atmrt_set_rows_per_warp(atmrt_ctx* ctx, int rows);

@@ -188,22 +188,66 @@ def test_render_matches_oracle(ctx, oracle_lib, name, scale):
     assert gs["step_overflows"] == 0 and gs["kernel_launches"] >= 5
 
 
-@pytest.mark.parametrize("name,scale", [("c1", 0.25), ("c2", 0.1), ("c4", 0.1)])
-def test_brute_force_march_equals_hierarchical(ctx, name, scale):
-    p, terrain, objects, textures = scene(name, scale)
-    ctx.set_terrain(terrain)
-    ctx.set_params(p)
-    ctx.set_objects(objects, textures)
-    ctx.set_march_mode(0)
-    a = ctx.render()
-    ctx.set_march_mode(1)
-    b = ctx.render()
-    ctx.set_march_mode(0)
+def _same_render(a, b):
     np.testing.assert_array_equal(a["rgb"], b["rgb"])
     np.testing.assert_array_equal(a["steps"], b["steps"])
     for f in ("lat", "lon", "elevation", "distance"):
         np.testing.assert_array_equal(a["meta"][f], b["meta"][f])
-    assert a["stats"]["ray_steps"] == b["stats"]["ray_steps"]
+    for f in ("ray_steps", "trace_points", "pixels_hit"):
+        assert a["stats"][f] == b["stats"][f]
+
+
+@pytest.mark.parametrize("name,scale", [("c1", 0.25), ("c2", 0.1), ("c3_flat", 0.05), ("c4", 0.1)])
+def test_march_variants_are_bit_identical(ctx, name, scale):
+    """Default (horizon sweep when terrain is opaque and there are no objects), brute force (every step,
+    like the reference loop) and the hierarchical min/max march give the same image, bit for bit."""
+    p, terrain, objects, textures = scene(name, scale)
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects(objects, textures)
+    out = []
+    for mode in (0, 1, 2):
+        ctx.set_march_mode(mode)
+        out.append(ctx.render())
+    ctx.set_march_mode(0)
+    _same_render(out[0], out[1])
+    _same_render(out[0], out[2])
+    assert out[0]["stats"]["pixels_hit"] > 0
+
+
+def test_sweep_falls_back_when_rays_cross(ctx, oracle_lib):
+    """A strong temperature inversion (duct) bends rays back down and makes neighbouring rays cross: the
+    path cache is no longer monotone in the row, k_path_check says so on the device and the general
+    march renders the image. Also: an observer below the terrain surface (every column is flagged)."""
+    p, terrain, _, _ = scene("c2", 0.1)
+    a = p.atmosphere
+    a.n_functions = 3
+    a.fn_gradient[0], a.fn_start_altitude[1], a.fn_gradient[1] = -0.0065, 1850.0, 0.5   # +0.5 K/m over 40 m
+    a.fn_start_altitude[2], a.fn_gradient[2] = 1890.0, -0.0065
+    p.tilt, p.fov = 0.0, 4.0
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects([])
+    want = oracle_lib.render(p, terrain.tiles)
+    el = np.stack([oracle_lib.path_cache(p, terrain.tiles, y)["elev"][:3000] for y in range(0, p.height, 4)])
+    assert (np.diff(el, axis=0) > 0).any(), "the duct was meant to make rays cross"
+    ctx.set_march_mode(0)
+    got = ctx.render()
+    ctx.set_march_mode(1)
+    ref = ctx.render()
+    ctx.set_march_mode(0)
+    _same_render(got, ref)
+    compare_render(got, want, "duct")
+    # observer inside the terrain: the first sign change is an exit, not an entry
+    q, terrain, _, _ = scene("c2", 0.05)
+    q.altitude.kind, q.altitude.value = abi.ALT_ABSOLUTE, 200.0
+    ctx.set_params(q)
+    got = ctx.render()
+    ctx.set_march_mode(1)
+    ref = ctx.render()
+    ctx.set_march_mode(0)
+    _same_render(got, ref)
+    compare_render(got, oracle_lib.render(q, terrain.tiles), "underground")
 
 
 def test_trace_point_lists_translucent_scene(ctx, oracle_lib):
