@@ -1007,12 +1007,12 @@ int atmrt_get_path(atmrt_ctx* ctx, int y, int capacity, double* dist, double* el
     *n = len;
     int m = std::min(capacity, len);
     if (m <= 0) return 0;
-    // the cache is step-major [k][h_pad]: gather row y with a strided 2-D copy
-    const size_t pitch = (size_t)S.h_pad * sizeof(double);
-    if (dist) CUDA_TRY(ctx, cudaMemcpy2D(dist, sizeof(double), ctx->buf.p_dist + y, pitch, sizeof(double), (size_t)m, cudaMemcpyDeviceToHost));
-    if (elev) CUDA_TRY(ctx, cudaMemcpy2D(elev, sizeof(double), ctx->buf.p_elev + y, pitch, sizeof(double), (size_t)m, cudaMemcpyDeviceToHost));
+    // the cache is [row / 4][k][row % 4]: gather row y with a strided 2-D copy (pitch = one row group)
+    const size_t pitch = (size_t)PATH_ROWS * sizeof(double), off = path_index(S.n_t, 0, y);
+    if (dist) CUDA_TRY(ctx, cudaMemcpy2D(dist, sizeof(double), ctx->buf.p_dist + off, pitch, sizeof(double), (size_t)m, cudaMemcpyDeviceToHost));
+    if (elev) CUDA_TRY(ctx, cudaMemcpy2D(elev, sizeof(double), ctx->buf.p_elev + off, pitch, sizeof(double), (size_t)m, cudaMemcpyDeviceToHost));
     if (path_length)
-        CUDA_TRY(ctx, cudaMemcpy2D(path_length, sizeof(double), ctx->buf.p_len + y, pitch, sizeof(double), (size_t)m, cudaMemcpyDeviceToHost));
+        CUDA_TRY(ctx, cudaMemcpy2D(path_length, sizeof(double), ctx->buf.p_len + off, pitch, sizeof(double), (size_t)m, cudaMemcpyDeviceToHost));
     return 0;
 }
 

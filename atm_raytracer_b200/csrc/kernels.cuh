@@ -15,6 +15,15 @@
 
 namespace atmrt {
 
+// Path cache layout: groups of PATH_ROWS adjacent rows, step-major inside a group: [row / 4][k][row % 4].
+// A warp of the march (32 adjacent rows, one step) reads 8 whole 32-byte sectors; a warp of the horizon
+// sweep (one row group, 32 consecutive steps) reads 1 KB of contiguous memory; the ray-path kernel's
+// rows store next to each other.
+constexpr int PATH_ROWS = 4;
+__host__ __device__ __forceinline__ size_t path_index(int n_t, int k, int y) {
+    return ((size_t)(y / PATH_ROWS) * (size_t)n_t + (size_t)k) * PATH_ROWS + (size_t)(y % PATH_ROWS);
+}
+
 constexpr int CHUNK = 32;  // march steps per level-1 chunk == warp width
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -315,10 +324,10 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
     // cell index chain: (altitude + off - ATM_BASE) / ATM_CELL + 1.5 * 2^52, from r (spherical) or h (flat)
     const double magic = 6755399441055744.0;
     const double xc = ((FLAT ? 0.0 : -radius) + off - ATM_BASE) * (1.0 / ATM_CELL) + magic;
-    const size_t hp = (size_t)S.h_pad;
-    double* const o_dist = B.p_dist + y;
-    double* const o_elev = B.p_elev + y;
-    double* const o_len = B.p_len + y;
+    const size_t row0 = path_index(S.n_t, 0, y);
+    double* const o_dist = B.p_dist + row0;
+    double* const o_elev = B.p_elev + row0;
+    double* const o_len = B.p_len + row0;
 
     // One round: the first lane group evaluates n around altitude aA, the second around
     // aB = a + wB * bA (ka of stage A is its slope input bA); then kbA, bB = b + wB kbA and kbB follow.
@@ -366,7 +375,7 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
         const double seg = sqrt_nr(dx * dx + dh * dh);                                                           \
         path_length = i >= 2 ? path_length + seg : 0.0;                                                          \
         const bool emit = writer && !done;                                                                       \
-        const size_t o = (size_t)(i - 1) * hp;                                                                   \
+        const size_t o = (size_t)(i - 1) * PATH_ROWS;                                                            \
         stg_if(o_dist + o, cur.x, emit);                                                                         \
         stg_if(o_elev + o, cur.h, emit);                                                                         \
         stg_if(o_len + o, path_length, emit);                                                                    \
@@ -444,17 +453,17 @@ __global__ void __launch_bounds__(128) k_ray_paths_straight(const __grid_constan
     const double alt = *B.obs_alt;
     Stepper st;
     stepper_init(st, flat, S.radius, alt, to_radians(get_ray_elev(S, y)));
-    const size_t hp = (size_t)S.h_pad;
-    B.p_dist[y] = 0.0;
-    B.p_elev[y] = alt;
-    B.p_len[y] = 0.0;
+    const size_t row0 = path_index(S.n_t, 0, y);
+    B.p_dist[row0] = 0.0;
+    B.p_elev[row0] = alt;
+    B.p_len[row0] = 0.0;
     RayState prev{0.0, alt};
     double path_length = 0.0;
     int n = 1;
     for (int i = 1; i < S.n_t; ++i) {
         const RayState nw = stepper_next(st, S.atm, flat, 1, S.radius, S.step);
         path_length += calc_dist(flat, S.radius, prev, nw);
-        const size_t o = (size_t)i * hp + y;
+        const size_t o = row0 + (size_t)i * PATH_ROWS;
         B.p_dist[o] = nw.x;
         B.p_elev[o] = nw.h;
         B.p_len[o] = path_length;
@@ -565,7 +574,7 @@ __global__ void __launch_bounds__(256) k_path_pyramid1(const double* __restrict_
     if (n >= 2 && 32 * c <= n - 1) {
         const int k0 = max(32 * c - 1, 0), k1 = min(32 * c + 31, n - 1);
         for (int k = k0; k <= k1; ++k) {
-            double x = vals[(size_t)k * h_pad + y];
+            double x = vals[path_index(n_total, k, y)];
             lo = fmin(lo, x);
             hi = fmax(hi, x);
         }
@@ -658,7 +667,7 @@ template <bool OBJECTS, bool TRACE>
 __device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers& B, const MarchOut& O, int xl, int y, int k,
                                              size_t pixel, PixelState& st) {
     const size_t ti = (size_t)xl * S.n_pad + k;
-    const size_t p1 = (size_t)k * S.h_pad + y, p0 = p1 - S.h_pad;
+    const size_t p1 = path_index(S.n_t, k, y), p0 = p1 - PATH_ROWS;
     // old_tracing_state = (terrain[k-1], path[k-1]) with dist/path_len forced to 0 for k-1 == 0.
     const double lat0 = B.t_lat[ti - 1], lon0 = B.t_lon[ti - 1], elev0 = B.t_elev[ti - 1];
     const double lat1 = B.t_lat[ti], lon1 = B.t_lon[ti], elev1 = B.t_elev[ti];
@@ -818,6 +827,7 @@ __device__ __forceinline__ void march_column(const DevScene& S, const DevBuffers
     const int nlim = min(S.n_t, B.p_n[yy]);
     const size_t tbase = (size_t)xl * S.n_pad;
     const size_t hp = (size_t)S.h_pad;
+    const size_t prow = path_index(S.n_t, 0, yy);
 
     PixelState st;
     init_pixel(st);
@@ -862,8 +872,8 @@ __device__ __forceinline__ void march_column(const DevScene& S, const DevBuffers
                     }
                 }
                 // the reference's test: diff1 * diff2 < 0.0 (utils.rs:220-222); diff1 of step k is diff2 of step k-1
-                const double dp = have_prev ? d_prev : B.p_elev[(size_t)(k - 1) * hp + yy] - B.t_elev[tbase + k - 1];
-                const double dn = B.p_elev[(size_t)k * hp + yy] - B.t_elev[tbase + k];
+                const double dp = have_prev ? d_prev : B.p_elev[prow + (size_t)(k - 1) * PATH_ROWS] - B.t_elev[tbase + k - 1];
+                const double dn = B.p_elev[prow + (size_t)k * PATH_ROWS] - B.t_elev[tbase + k];
                 d_prev = dn;
                 have_prev = true;
                 bool e = dp * dn < 0.0;
@@ -929,7 +939,7 @@ __global__ void __launch_bounds__(256) k_path_check(const double* __restrict__ e
         if (n_up < n_dn) bad = true;  // the upper ray must live at least as long
         const int k1 = min(k0 + 64, n_dn);
         for (int k = k0; k < k1; ++k) {
-            const double up = elev[(size_t)k * h_pad + y], dn = elev[(size_t)k * h_pad + y + 1];
+            const double up = elev[path_index(n_t, k, y)], dn = elev[path_index(n_t, k, y + 1)];
             // A NaN ray (it left the atmosphere model) never hits; it must be the upper one of the pair.
             if (up < dn || (dn != dn && up == up)) bad = true;
         }
@@ -953,9 +963,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(const __grid_constant__
     const double* __restrict__ te = B.t_elev + (size_t)xl * S.n_pad;
     const double* __restrict__ pe = B.p_elev;
     int* __restrict__ hit = B.sweep_hit + (size_t)xl * S.h_pad;
-    const int hpi = S.h_pad;
     bool flagged = !(pe[0] - te[0] > 0.0);  // every ray starts at the observer altitude (element 0 of every row)
     const int k_last = S.n_t - 1;
+    static_assert(SWEEP_ROWS == PATH_ROWS, "the sweep reads one row group of the path cache per 32-byte load");
     int k = 1;  // first step the current row may still cross at
     // groups of SWEEP_ROWS rows (local row 0 is the top one), bottom group first, rows bottom-up inside
     for (int g = (S.height - 1) / SWEEP_ROWS; g >= 0 && !flagged; --g) {
@@ -972,14 +982,14 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(const __grid_constant__
             }
             // the window: steps k + lane for all rows of the group; the "before" side comes from the lane below
             const int kk = min(k + lane, k_last);
-            const double4 cur = *reinterpret_cast<const double4*>(pe + (size_t)kk * hpi + ybase);
+            const double4 cur = *reinterpret_cast<const double4*>(pe + path_index(S.n_t, kk, ybase));
             const double t_cur = te[kk];
             double4 prv;
             prv.x = __shfl_up_sync(FULL, cur.x, 1), prv.y = __shfl_up_sync(FULL, cur.y, 1);
             prv.z = __shfl_up_sync(FULL, cur.z, 1), prv.w = __shfl_up_sync(FULL, cur.w, 1);
             double t_prv = __shfl_up_sync(FULL, t_cur, 1);
             if (lane == 0) {
-                prv = *reinterpret_cast<const double4*>(pe + (size_t)(k - 1) * hpi + ybase);
+                prv = *reinterpret_cast<const double4*>(pe + path_index(S.n_t, k - 1, ybase));
                 t_prv = te[k - 1];
             }
             int lo = 0;        // lanes below `lo` are steps the current row cannot cross at any more
