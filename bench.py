@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5", choices=["c1", "c2", "c3_flat", "c3_sph", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="image scale (1.0 = the BASELINE size; anything else is a dry run)")
-    ap.add_argument("--march-mode", type=int, default=0, help="0 hierarchical (product default), 1 brute force (every step)")
+    ap.add_argument("--march-mode", type=int, default=0, help="0 product default, 1 brute force (every step), 2 hierarchical march always")
     ap.add_argument("--cpu-stride", type=int, default=0, help="column/row stride of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -351,6 +351,8 @@ def run_b200(args):
     units = {"terrain": wl * n_t, "paths": st["path_steps"] / world if world > 1 else st["path_steps"],
              "march": st["ray_steps"] / world}
     stage_ms = {"terrain": ms_a, "paths": ms_b, "march": ms_c}
+    if args.march_mode == 0 and params.terrain_alpha == 1.0 and not objects:
+        STAGE_UNITS["march"] = ("k_sweep+k_sweep_shade", "ray steps")  # opaque terrain, no objects: the horizon sweep
     dom = max(stage_ms, key=stage_ms.get)
     roofs = {k: roofline(k, stage_ms[k], units[k], params, fp, args) for k in stage_ms}
     roof = roofs[dom]
@@ -365,7 +367,7 @@ def run_b200(args):
     out = {
         "metric": METRIC, "value": W * H / (ms * 1e-3), "unit": "pixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": describe(args.workload, params, terrain, {"parallelism": f"column blocks x{world}", "march_mode": "hierarchical" if args.march_mode == 0 else "brute force"}),
+        "config": describe(args.workload, params, terrain, {"parallelism": f"column blocks x{world}", "march_mode": {0: "horizon sweep (opaque terrain, no objects) / hierarchical march", 1: "brute force", 2: "hierarchical march"}[args.march_mode]}),
         "ray_steps_per_s": st["ray_steps"] / (ms * 1e-3),
         "ray_steps_per_step": st["ray_steps"],
         "stage_ms": {"terrain_profile": ms_a, "ray_paths": ms_b, "march": ms_c, "note": "terrain and paths overlap on two streams; max over ranks"},
