@@ -8,6 +8,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <functional>
 #include <vector>
 
 #include "kernels.cuh"
@@ -64,7 +65,13 @@ struct atmrt_ctx {
     int march_mode = 0;
     int rows_per_warp = 32;
     std::vector<double> dist_k;
-    std::vector<double> atm_cells;
+    std::vector<double> atm_cells;  // g(h) table of the ray-path stage, [ATM_FIELDS][ATM_CELLS]
+    std::vector<DevGPiece> atm_pieces;  // its cells that hold the start of a temperature function
+    int atm_cells_served = 0;
+    bool atm_table_valid = false;
+    atmrt_atmosphere_def atm_table_def{};
+    double atm_table_wavelength = 0.0;
+    int path_mode = 0;  // 0: g(h) from the table, 1: every evaluation through libm (validation)
     DevBuf d_atm_cells;
     DevBuf d_sweep_flags, d_sweep_col, d_sweep_hit;
     bool sweep_enabled = true;
@@ -179,45 +186,160 @@ double host_layer_pressure(const DevAtmLayer& l, double h) {
     return l.p_ref * std::exp(-ATM_G * ATM_M * (h - l.h_ref) / (ATM_R * l.t_ref));
 }
 
-// The anchor table of the ray-path stage (device_paths.cuh): [ATM_FIELDS][ATM_CELLS]. Anchors use the
-// reference's own expressions for T(h) and p(h) (host libm), evaluated at the cell centres. Cells the
-// series cannot serve hold NaN.
-void build_atm_table(const DevAtmosphere& a, std::vector<double>& cells) {
-    const double nan = std::numeric_limits<double>::quiet_NaN();
+// ---- the g(h) table of the ray-path stage (device_paths.cuh) -----------------------------------
+// The reference's atmosphere function as a function of real numbers, evaluated in x87 extended
+// precision (64-bit significand): the same layer lookup, hydrostatic law (layer_pressure), Ciddor terms
+// (air_index) and central difference (env_dn, eps = 0.01 m) as oracle/atmrt_oracle.cpp / device_atm.cuh,
+// with n - 1 kept apart from the 1 so that the difference does not cancel against it.
+struct LdAtmosphere {
+    const DevAtmosphere* a;
+    long double r_axs, r_vs, m_a, rho_axs;  // wavelength terms, re-lowered in extended precision
+    int forced_layer;
+};
+
+long double ld_n_minus_1(const LdAtmosphere& A, long double h) {
+    const DevAtmosphere& a = *A.a;
+    int idx = 0;
+    for (int i = 1; i < a.n; ++i)
+        if (h >= (long double)a.layer[i].start) idx = i;
+    if (A.forced_layer >= 0) idx = A.forced_layer;  // that temperature function's law, continued past its boundaries
+    const DevAtmLayer& l = a.layer[idx];
+    const long double t = (long double)l.t_ref + (long double)l.gradient * (h - (long double)l.h_ref);
+    long double p;
+    if (l.gradient != 0.0)
+        p = (long double)l.p_ref * powl(t / (long double)l.t_ref, -(long double)ATM_G * ATM_M / ((long double)ATM_R * l.gradient));
+    else
+        p = (long double)l.p_ref * expl(-(long double)ATM_G * ATM_M * (h - (long double)l.h_ref) / ((long double)ATM_R * l.t_ref));
+    const long double a0 = 1.58123e-6L, a1 = -2.9331e-8L, a2 = 1.1043e-10L, b0 = 5.707e-6L, b1 = -2.051e-8L, c0 = 1.9898e-4L, c1 = -2.376e-6L;
+    const long double d = 1.83e-11L, e = -0.765e-8L, rho_vs = 0.00985938L, gas_r = 8.314510L, m_v = 0.018015L;
+    const long double alpha = 1.00062L, beta = 3.14e-8L, gamma = 5.6e-7L;
+    const long double sa = 1.2378847e-5L, sb = -1.9121316e-2L, sc = 33.93711047L, sd = -6.3431645e3L;
+    const long double t_c = t - 273.15L;
+    long double x_v = 0.0L;
+    if (a.humidity != 0.0) {
+        const long double svp = expl(sa * t * t + sb * t + sc + sd / t);
+        const long double f = alpha + beta * p + gamma * t_c * t_c;
+        x_v = (long double)a.humidity * f * svp / p;
+    }
+    const long double pt = p / t;
+    const long double z_m = 1.0L - pt * (a0 + a1 * t_c + a2 * t_c * t_c + (b0 + b1 * t_c) * x_v + (c0 + c1 * t_c) * x_v * x_v) + pt * pt * (d + e * x_v * x_v);
+    const long double rho_v = x_v * p * m_v / (z_m * gas_r * t);
+    const long double rho_a = (1.0L - x_v) * p * A.m_a / (z_m * gas_r * t);
+    return (rho_a / A.rho_axs) * A.r_axs + (rho_v / rho_vs) * A.r_vs;
+}
+
+// g = n'/n. The derivative is taken with the five-point stencil at 2 m spacing instead of the reference's
+// two-point one at 0.01 m: both approximate the same n'(h) (truncation (2 m / H)^4 / 30 < 1e-13 and
+// (0.01 m / H)^2 / 6 < 1e-12 relative, H > 1.7 km the density scale height), but the wide stencil does not
+// amplify the 1e-18 rounding of powl by H / 0.01 m.
+long double ld_g(const LdAtmosphere& A, long double h) {
+    const long double s = 2.0L;
+    const long double d1 = ld_n_minus_1(A, h + s) - ld_n_minus_1(A, h - s), d2 = ld_n_minus_1(A, h + 2.0L * s) - ld_n_minus_1(A, h - 2.0L * s);
+    return (8.0L * d1 - d2) / (12.0L * s) / (1.0L + ld_n_minus_1(A, h));
+}
+
+// Degree-6 interpolant of g at the 7 Chebyshev nodes of [centre - half, centre + half], as monomial
+// coefficients in u = (h - centre) / half; kept only if it reproduces g at 33 check points to 1e-10
+// relative or 1e-19 /m absolute (g is 3.5e-8 /m at sea level; either error bends a 400 km ray by less
+// than 1e-6 m -- the reference's own evaluation of g carries 3e-7 relative noise).
+bool fit_g_cell(const LdAtmosphere& A, double centre, double half_width, double* cd) {
+    constexpr int M = ATM_FIELDS;  // nodes = coefficients
+    static_assert(M == 7, "the Chebyshev-to-monomial table below is for degree 6");
+    static const long double cheb[7][7] = {{1, 0, 0, 0, 0, 0, 0},  {0, 1, 0, 0, 0, 0, 0},    {-1, 0, 2, 0, 0, 0, 0},    {0, -3, 0, 4, 0, 0, 0},
+                                           {1, 0, -8, 0, 8, 0, 0}, {0, 5, 0, -20, 0, 16, 0}, {-1, 0, 18, 0, -48, 0, 32}};  // T_k(u) as monomials
+    const long double pi = 3.14159265358979323846264338327950288L, half = half_width;
+    long double f[M], c[M];
+    for (int k = 0; k < M; ++k) {
+        f[k] = ld_g(A, (long double)centre + half * cosl(pi * (k + 0.5L) / M));
+        if (!std::isfinite((double)f[k])) return false;
+    }
+    for (int m = 0; m < M; ++m) {
+        long double acc = 0;
+        for (int k = 0; k < M; ++k) acc += f[k] * cosl(pi * m * (k + 0.5L) / M);
+        c[m] = acc * (m == 0 ? 1.0L : 2.0L) / M;
+    }
+    for (int q = 0; q < M; ++q) {
+        long double mono = 0;
+        for (int m = 0; m < M; ++m) mono += c[m] * cheb[m][q];
+        cd[q] = (double)mono;
+    }
+    for (int k = 0; k <= 32; ++k) {  // the device's evaluation order, in f64
+        const double u = -1.0 + k / 16.0;
+        const double u2 = u * u, u4 = u2 * u2;
+        const double v = std::fma(std::fma(cd[6], u2, std::fma(cd[5], u, cd[4])), u4, std::fma(std::fma(cd[3], u, cd[2]), u2, std::fma(cd[1], u, cd[0])));
+        const long double want = ld_g(A, (long double)centre + half * u);
+        const long double err = fabsl((long double)v - want);
+        if (!(std::isfinite(v) && (err <= 1e-10L * fabsl(want) || err <= 1e-19L))) {
+            if (getenv("ATMRT_DEBUG_TABLE"))
+                fprintf(stderr, "fit_g_cell: centre %.1f +- %.1f function %d u %.4f got %.17g want %.17Lg rel %.3Lg\n", centre, half_width, A.forced_layer, u, v, want,
+                        err / fabsl(want));
+            return false;
+        }
+    }
+    return true;
+}
+
+// The table, [ATM_FIELDS][ATM_CELLS] (cells that cannot be served hold NaN), and the pieces that serve the
+// cells holding the start of a temperature function.
+void build_g_table(const DevAtmosphere& a, double wavelength, std::vector<double>& cells, std::vector<DevGPiece>& pieces, int* served_out) {
+    const double nan = std::numeric_limits<double>::quiet_NaN(), inf = std::numeric_limits<double>::infinity();
     cells.assign((size_t)ATM_FIELDS * ATM_CELLS, nan);
-    auto find = [&](double h) {
-        int idx = 0;
-        for (int i = 1; i < a.n; ++i)
-            if (h >= a.layer[i].start) idx = i;
-        return idx;
+    pieces.clear();
+    LdAtmosphere A{&a, 0, 0, 0, 0, -1};
+    {  // air_index's wavelength terms (oracle: air_index; lower_atmosphere does the same in f64)
+        const long double lambda_um = (long double)wavelength * 1.0e6L, s = 1.0L / (lambda_um * lambda_um);
+        const long double r_as = 1.0e-8L * (5792105.0L / (238.0185L - s) + 167917.0L / (57.362L - s));
+        A.r_vs = 1.022e-8L * (295.235L + 2.6422L * s + -0.032380L * s * s + 0.004028L * s * s * s);
+        A.m_a = 0.0289635L + 1.2011e-8L * (450.0L - 400.0L);
+        A.r_axs = r_as * (1.0L + 5.34e-7L * (450.0L - 450.0L));
+        A.rho_axs = 101325.0L * A.m_a / (0.9995922115L * 8.314510L * 288.15L);
+    }
+    int served = 0;
+    // [lo, hi) inside one temperature function: one piece if the fit holds, else halves down to 1 m (what
+    // stays unserved -- e.g. the last metres before a temperature function reaches 0 K -- is left to libm)
+    std::function<void(double, double, int)> add_pieces = [&](double lo, double hi, int depth) {
+        if (pieces.size() >= (size_t)ATM_MAX_PIECES) return;
+        if (!std::isfinite((double)ld_g(A, lo)) && !std::isfinite((double)ld_g(A, 0.5 * (lo + hi))) && !std::isfinite((double)ld_g(A, hi))) return;  // no law here (T <= 0)
+        DevGPiece pc{};
+        pc.h_lo = lo, pc.h_hi = hi, pc.centre = 0.5 * (lo + hi);
+        const double half_width = 0.5 * (hi - lo);
+        pc.inv_half = 1.0 / half_width;
+        if (fit_g_cell(A, pc.centre, half_width, pc.c)) {
+            pieces.push_back(pc);
+        } else if (depth < 8 && hi - lo > 1.0) {
+            add_pieces(lo, pc.centre, depth + 1);
+            add_pieces(pc.centre, hi, depth + 1);
+        }
     };
     for (int j = 1; j + 1 < ATM_CELLS; ++j) {  // the first and the last cell catch out-of-range and NaN altitudes
-        const double hj = ATM_BASE + (double)j * ATM_CELL, lo = hj - 0.5 * ATM_CELL, hi = hj + 0.5 * ATM_CELL;
-        const int li = find(lo);
-        bool whole = true;  // no temperature function starts inside the cell (or on its upper edge: rounding of the index)
-        for (int i = 1; i < a.n; ++i)
-            if (a.layer[i].start > lo && a.layer[i].start <= hi) whole = false;
-        const DevAtmLayer& l = a.layer[li];
-        const double t_lo = host_layer_temperature(l, lo), t_hi = host_layer_temperature(l, hi), tj = host_layer_temperature(l, hj);
-        if (!whole || !(t_lo >= 1.0) || !(t_hi >= 1.0)) continue;
-        const double pj = host_layer_pressure(l, hj);
-        if (!(pj > 1e-280) || !std::isfinite(pj)) continue;
-        const bool linear = l.gradient != 0.0;
-        const double k = linear ? l.gradient / tj : l.gm / l.rt;  // d ln T / dh, or d ln p / dh for an isothermal function
-        // Validity: the truncation errors of the two series (log1p after w^7, exp after v^9), as an absolute
-        // error of n, must stay below 3e-20 -- four orders under the rounding of `1 + x`. n - 1 scales with
-        // p / T, so the thin air far above the real atmosphere tolerates the larger |w| of its cold cells.
-        const double w_max = std::fabs(k) * 0.51 * ATM_CELL * (linear ? 1.0 : 0.0);
-        const double v_max = linear ? std::fabs(l.expo) * w_max * (1.0 + w_max) : std::fabs(k) * 0.51 * ATM_CELL;
-        const double err_rel = (linear ? std::fabs(l.expo) * std::pow(w_max, 8) / 8.0 : 0.0) + std::pow(v_max, 10) / 3628800.0;
-        const double n_minus_1 = 2.9e-4 * (pj / 101325.0) * (288.15 / std::min(t_lo, t_hi)) * std::exp(v_max);
-        if (!(w_max < 0.25) || !(v_max < 1.0) || !(err_rel * n_minus_1 <= 3e-20)) continue;
-        cells[0 * ATM_CELLS + j] = pj;
-        cells[1 * ATM_CELLS + j] = tj;
-        cells[2 * ATM_CELLS + j] = l.gradient;
-        cells[3 * ATM_CELLS + j] = linear ? k : k / ATM_ISO_SCALE;
-        cells[4 * ATM_CELLS + j] = linear ? l.expo : ATM_ISO_SCALE;
+        const double hj = ATM_BASE + (double)j * ATM_CELL, half = 0.5 * ATM_CELL, lo = hj - half, hi = hj + half;
+        // temperature functions that own a part of the cell's interior (a function that starts on an edge,
+        // give or take the rounding of the cell index, does not split the cell)
+        int first = 0, last = 0;
+        for (int i = 1; i < a.n; ++i) {
+            if (lo + 1e-6 >= a.layer[i].start) first = i;
+            if (hi - 1e-6 > a.layer[i].start) last = i;
+        }
+        double cd[ATM_FIELDS];
+        A.forced_layer = first;  // its law, continued past its ends for the stencil of ld_g
+        if (first == last && fit_g_cell(A, hj, half, cd)) {
+            for (int q = 0; q < ATM_FIELDS; ++q) cells[(size_t)q * ATM_CELLS + j] = cd[q];
+            ++served;
+            continue;
+        }
+        // Not served as a whole: pieces, one or more per temperature function over the part of the cell that
+        // function owns (the cell index rounds: overlap the neighbours by 1 m). The reference's difference
+        // quotient blends two laws within 0.01 m of a start; here g switches at the start itself.
+        for (int i = first; i <= last; ++i) {
+            const double p_lo = std::max(i == first ? -inf : a.layer[i].start, lo - 1.0);
+            const double p_hi = std::min(i == last ? inf : a.layer[i + 1].start, hi + 1.0);
+            if (!(p_hi > p_lo)) continue;
+            A.forced_layer = i;  // that function's law, continued past its ends for the stencil
+            add_pieces(p_lo, p_hi, 0);
+        }
+        A.forced_layer = -1;
     }
+    if (served_out) *served_out = served;
 }
 
 int lower_atmosphere(atmrt_ctx* ctx, const atmrt_atmosphere_def& def, double wavelength, DevAtmosphere* out) {
@@ -406,11 +528,17 @@ int prepare_render(atmrt_ctx* ctx) {
     e |= ensure(ctx, ctx->d_rmax3, f8 * hp);
     (void)h;
     e |= ensure(ctx, ctx->d_obs, f8);
-    e |= ensure(ctx, ctx->d_atm_cells, f8 * ATM_FIELDS * ATM_CELLS);
+    e |= ensure(ctx, ctx->d_atm_cells, f8 * ATM_FIELDS * ATM_CELLS + sizeof(DevGPiece) * ATM_MAX_PIECES);
     e |= ensure(ctx, ctx->d_sweep_flags, 16);
     e |= ensure(ctx, ctx->d_sweep_col, wl);
     e |= ensure(ctx, ctx->d_sweep_hit, sizeof(int) * wl * hp);
-    build_atm_table(S.atm, ctx->atm_cells);
+    // the g(h) table depends on the atmosphere and the wavelength only: rebuilt when they change
+    if (!ctx->atm_table_valid || memcmp(&ctx->atm_table_def, &p.atmosphere, sizeof(p.atmosphere)) != 0 || ctx->atm_table_wavelength != p.wavelength) {
+        build_g_table(S.atm, p.wavelength, ctx->atm_cells, ctx->atm_pieces, &ctx->atm_cells_served);
+        ctx->atm_table_def = p.atmosphere;
+        ctx->atm_table_wavelength = p.wavelength;
+        ctx->atm_table_valid = true;
+    }
     e |= ensure(ctx, ctx->d_counters, 8 * CNT_COUNT);
     e |= ensure(ctx, ctx->d_objects, sizeof(DevObject) * std::max(1, S.nobjects));
     e |= ensure(ctx, ctx->d_objects_in, sizeof(atmrt_object) * std::max(1, S.nobjects));
@@ -438,6 +566,8 @@ int prepare_render(atmrt_ctx* ctx) {
     B.objects = (DevObject*)ctx->d_objects.p;
     B.counters = (unsigned long long*)ctx->d_counters.p;
     B.atm_cells = (const double*)ctx->d_atm_cells.p;
+    B.atm_pieces = (const DevGPiece*)((const char*)ctx->d_atm_cells.p + f8 * ATM_FIELDS * ATM_CELLS);
+    B.n_atm_pieces = (int)ctx->atm_pieces.size();
     B.sweep_flags = (unsigned*)ctx->d_sweep_flags.p;
     B.sweep_col = (unsigned char*)ctx->d_sweep_col.p;
     B.sweep_hit = (int*)ctx->d_sweep_hit.p;
@@ -448,6 +578,9 @@ int upload_scene_inputs(atmrt_ctx* ctx, cudaStream_t s) {
     const DevScene& S = ctx->scene;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dist.p, ctx->dist_k.data(), sizeof(double) * S.n_t, cudaMemcpyHostToDevice, s));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_atm_cells.p, ctx->atm_cells.data(), sizeof(double) * ATM_FIELDS * ATM_CELLS, cudaMemcpyHostToDevice, s));
+    if (!ctx->atm_pieces.empty())
+        CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->d_atm_cells.p + sizeof(double) * ATM_FIELDS * ATM_CELLS, ctx->atm_pieces.data(),
+                                      sizeof(DevGPiece) * ctx->atm_pieces.size(), cudaMemcpyHostToDevice, s));
     if (S.nobjects > 0) {
         std::vector<DevObject> host(S.nobjects);
         for (int i = 0; i < S.nobjects; ++i) {
@@ -524,16 +657,15 @@ int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main) {
     // Stage B on s_b: all rows (every column needs every row)
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->b0, ctx->s_b));
     {
-        const int rb = (h + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
-        const bool dry = S.atm.humidity == 0.0;
+        const int rb = (h + 31) / 32;
         if (S.straight) {
             k_ray_paths_straight<<<(h + 127) / 128, 128, 0, ctx->s_b>>>(S, B);
         } else if (S.flat) {
-            if (dry) k_ray_paths<true, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
-            else     k_ray_paths<true, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
+            if (ctx->path_mode == 1) k_ray_paths<true, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
+            else k_ray_paths<true, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
         } else {
-            if (dry) k_ray_paths<false, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
-            else     k_ray_paths<false, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
+            if (ctx->path_mode == 1) k_ray_paths<false, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
+            else k_ray_paths<false, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
         }
         ctx->launches++;
     }
@@ -892,6 +1024,12 @@ int atmrt_set_march_mode(atmrt_ctx* ctx, int mode) {
 }
 
 // Tuning hook for Stage B: image rows integrated per warp (1..32).
+int atmrt_set_path_mode(atmrt_ctx* ctx, int mode) {
+    if (!ctx) return ATMRT_ERR_INVALID;
+    ctx->path_mode = mode == 1 ? 1 : 0;
+    return 0;
+}
+
 int atmrt_set_rows_per_warp(atmrt_ctx* ctx, int rows) {
     if (!ctx || rows < 1 || rows > 32) return fail(ctx, ATMRT_ERR_INVALID, "rows per warp must be 1..32");
     ctx->rows_per_warp = rows;  // kept for ABI stability: the 3-lanes-per-row stepper fixes 10 rows per warp
@@ -1047,13 +1185,13 @@ int atmrt_atmosphere_probe(atmrt_ctx* ctx, const double* h, int n, double* tempe
     if (!ctx || !h || n < 0) return fail(ctx, ATMRT_ERR_INVALID, "atmosphere_probe: bad argument");
     if (!ctx->has_params) return fail(ctx, ATMRT_ERR_STATE, "atmosphere_probe before set_params");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    if (n == 0) return 0;
     DevScene S{};
     int rc = lower_atmosphere(ctx, ctx->params.atmosphere, ctx->params.wavelength, &S.atm);
     if (rc) return rc;
-    size_t bytes = 8 * (size_t)n;
-    if (ensure(ctx, ctx->d_probe_a, bytes) | ensure(ctx, ctx->d_probe_b, bytes) | ensure(ctx, ctx->d_probe_c, bytes) | ensure(ctx, ctx->d_probe_d, bytes))
+    size_t bytes = sizeof(double) * (size_t)std::max(n, 1);
+    if (ensure(ctx, ctx->d_probe_a, bytes) || ensure(ctx, ctx->d_probe_b, bytes) || ensure(ctx, ctx->d_probe_c, bytes) || ensure(ctx, ctx->d_probe_d, bytes))
         return ATMRT_ERR_CUDA;
+    if (n == 0) return 0;
     cudaStream_t s = ctx->s_main;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_probe_a.p, h, bytes, cudaMemcpyHostToDevice, s));
     k_atm_probe<<<(n + 127) / 128, 128, 0, s>>>(S, (const double*)ctx->d_probe_a.p, n, (double*)ctx->d_probe_b.p, (double*)ctx->d_probe_c.p,
@@ -1062,6 +1200,62 @@ int atmrt_atmosphere_probe(atmrt_ctx* ctx, const double* h, int n, double* tempe
     if (temperature) CUDA_TRY(ctx, cudaMemcpyAsync(temperature, ctx->d_probe_b.p, bytes, cudaMemcpyDeviceToHost, s));
     if (pressure) CUDA_TRY(ctx, cudaMemcpyAsync(pressure, ctx->d_probe_c.p, bytes, cudaMemcpyDeviceToHost, s));
     if (refractive_index) CUDA_TRY(ctx, cudaMemcpyAsync(refractive_index, ctx->d_probe_d.p, bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int atmrt_refraction_table(const atmrt_atmosphere_def* def, double wavelength, double* cells, int capacity, int* ncells, int* ncoef,
+                           double* base, double* cell_height, int* cells_served, int* npieces) {
+    if (!def) return ATMRT_ERR_INVALID;
+    if (ncells) *ncells = ATM_CELLS;
+    if (ncoef) *ncoef = ATM_FIELDS;
+    if (base) *base = ATM_BASE;
+    if (cell_height) *cell_height = ATM_CELL;
+    DevAtmosphere a;
+    int rc = lower_atmosphere(nullptr, *def, wavelength, &a);
+    if (rc) return rc;
+    std::vector<double> t;
+    std::vector<DevGPiece> pieces;
+    int served = 0;
+    build_g_table(a, wavelength, t, pieces, &served);
+    if (npieces) *npieces = (int)pieces.size();
+    if (cells_served) *cells_served = served;
+    if (cells) {
+        if (capacity < (int)t.size()) return ATMRT_ERR_INVALID;
+        memcpy(cells, t.data(), sizeof(double) * t.size());
+    }
+    return 0;
+}
+
+int atmrt_refraction_probe(atmrt_ctx* ctx, const double* h, int n, int with_pieces, double* g_table, double* g_libm, int* cells_served) {
+    if (!ctx || !h || n < 0) return fail(ctx, ATMRT_ERR_INVALID, "refraction_probe: bad argument");
+    if (!ctx->has_params) return fail(ctx, ATMRT_ERR_STATE, "refraction_probe before set_params");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DevScene S{};
+    int rc = lower_atmosphere(ctx, ctx->params.atmosphere, ctx->params.wavelength, &S.atm);
+    if (rc) return rc;
+    std::vector<double> cells;
+    std::vector<DevGPiece> pieces;
+    int served = 0;
+    build_g_table(S.atm, ctx->params.wavelength, cells, pieces, &served);
+    if (cells_served) *cells_served = served;
+    const size_t cell_bytes = sizeof(double) * cells.size();
+    size_t bytes = sizeof(double) * (size_t)std::max(n, 1);
+    if (ensure(ctx, ctx->d_probe_a, bytes) || ensure(ctx, ctx->d_probe_b, bytes) || ensure(ctx, ctx->d_probe_c, bytes) ||
+        ensure(ctx, ctx->d_probe_d, cell_bytes + sizeof(DevGPiece) * ATM_MAX_PIECES))
+        return ATMRT_ERR_CUDA;
+    if (n == 0) return 0;
+    cudaStream_t s = ctx->s_main;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_probe_a.p, h, bytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_probe_d.p, cells.data(), cell_bytes, cudaMemcpyHostToDevice, s));
+    if (!pieces.empty())
+        CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->d_probe_d.p + cell_bytes, pieces.data(), sizeof(DevGPiece) * pieces.size(), cudaMemcpyHostToDevice, s));
+    k_refraction_probe<<<(n + 127) / 128, 128, 0, s>>>(S, (const double*)ctx->d_probe_d.p, (const double*)ctx->d_probe_a.p, n, (double*)ctx->d_probe_b.p,
+                                                         (double*)ctx->d_probe_c.p, with_pieces ? (const DevGPiece*)((const char*)ctx->d_probe_d.p + cell_bytes) : nullptr,
+                                                         (int)pieces.size());
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (g_table) CUDA_TRY(ctx, cudaMemcpyAsync(g_table, ctx->d_probe_b.p, bytes, cudaMemcpyDeviceToHost, s));
+    if (g_libm) CUDA_TRY(ctx, cudaMemcpyAsync(g_libm, ctx->d_probe_c.p, bytes, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     return 0;
 }

@@ -3,57 +3,47 @@
 //
 // The stage is bound by the dependent-issue latency of ONE chain (N_t steps x the critical path of a
 // step; a dependent f64 op costs 8.2 cycles on B200), not by throughput: all H chains are resident at
-// once and the kernel ends when the longest one does. Everything here shortens the critical path of a
-// step while keeping the reference's arithmetic in f64:
+// once and the kernel ends when the longest one does -- and because every rank needs every row, this
+// latency is the floor of the multi-GPU frame time. Everything here shortens the critical path of a
+// step while the integration itself stays the reference's classical RK4 in f64:
 //
-//  1. RK4 structure. The refractive index is a function of altitude only, and the altitude input of
-//     stage s+1 is a0 + w*d*ka_s with ka_s = b_s (the slope input of stage s). Stage 2's altitude
-//     a0 + d/2*b0 is therefore known when the step starts, and stage 4's altitude needs kb_2 only.
-//     The four index evaluations collapse into two dependent rounds: {stage 1, stage 2} then
-//     {stage 3, stage 4}. No arithmetic changes, only the schedule.
-//  2. Six lanes per row. Each round evaluates n at 2 altitudes x {h-eps, h, h+eps} (the central
-//     difference dn/dh) on six lanes; the values are exchanged with shuffles and every lane applies
-//     the identical RK4 update, so the six copies of the state never diverge.
-//  3. Re-anchored hydrostatic pressure. Inside one temperature function T is linear in h, so for any
-//     anchor altitude h_j of that function  p(h) = p(h_j) (T(h)/T(h_j))^alpha = p_j exp(alpha log1p(w))
-//     with w = g (h - h_j) / T_j  (isothermal: p_j exp(k (h - h_j))) -- the same identity the reference
-//     uses with the function's own reference point, moved to the centre of a 256 m cell. |w| <= 8e-3
-//     and |alpha w| <= 0.034 * 128 / T, so log1p and exp are two short series (remainders < 1e-17)
-//     with no range reduction, evaluated in Estrin form. The anchors p_j, T_j come from the
-//     reference's own expressions (host libm pow / exp) and are staged in shared memory.
-//  4. The remaining divisions use reciprocals: MUFU.RCP64H + two Newton steps for 1/T and 1/r (issued
-//     early, they overlap the series), geometric series for 1/Z and 1/n (both within 1e-2 of 1).
-//  5. The fast path is one straight-line block: cells it cannot serve (a temperature-function
-//     boundary inside the cell, series not accurate enough, outside the table, NaN altitude) hold NaN
-//     anchors, and a NaN result sends that one evaluation to the libm path of device_atm.cuh, which
-//     is the arithmetic the oracle restates op for op. A cell is served when the truncation errors of
-//     the two series, as an absolute error of n, stay below 3e-20 (atmrt_lib.cu:build_atm_table).
-//
-// Accuracy: p and (n - 1) carry ~1e-16 relative error, i.e. 3e-20 absolute in n -- four orders below
-// the rounding of `1.0 + x` (1.1e-16) that the reference's own finite difference carries as noise (a
-// relative 2e-7 of dn/dh per evaluation, ~2e-6 m of path altitude at 200 km; tests/test_noise_floor).
+//  1. The ray equation needs the atmosphere only through ONE function of altitude,
+//         g(h) = dn(h) / n(h),   dn(h) = (n(h + eps) - n(h - eps)) / (2 eps),  eps = 0.01 m
+//     (spherical: r'' = g (r'^2 + r^2) + 2 r'^2 / r + r; flat: h'' = g (1 + h'^2)). The reference
+//     evaluates it with three Ciddor indices per RK4 stage (pow/exp + divisions: ~500 dependent
+//     cycles even when the three run on separate lanes) and, because n = 1 + 2.8e-4 is rounded to
+//     1.1e-16 before the difference is taken, every evaluation carries a relative noise of 2e-7.
+//     The host lowers the atmosphere once per set_params into a table of g: 250 m cells, a degree-6
+//     polynomial per cell fitted at Chebyshev nodes to the reference's own definition (same layers,
+//     hydrostatic law, Ciddor terms and central difference) evaluated in x87 extended precision, and
+//     checked at 33 points per cell to 1e-12 relative (atmrt_lib.cu:build_g_table). A table lookup is
+//     one magic-number cell index, seven shared-memory loads and an Estrin evaluation: ~80 dependent
+//     cycles. The table is 5 orders of magnitude closer to the real-number value of the reference's
+//     formula than the reference's own f64 evaluation is (tests/test_noise_floor.py).
+//  2. Cells the table cannot serve hold NaN coefficients, and a NaN result sends that lane's step to the
+//     fallback: a cell with the start of a temperature function inside (g has a kink there) is served
+//     by one polynomial per function (`pieces`), everything else (T <= 1 K, fit check failed, outside
+//     -2.25 .. 189.75 km) by g_libm(), which is the oracle's arithmetic op for op (device_atm.cuh).
+//     atmrt_set_path_mode(1) forces every evaluation through g_libm (validation, tests).
+//  3. RK4 structure: stage 2's altitude a + d/2 b is known when the step starts and stage 4's needs
+//     kb2 only, so the lookups of stages {1, 2} and {3, 4} overlap; 1/r for the geometric term comes
+//     from MUFU.RCP64H + two Newton steps issued in the shadow of the lookups.
+//  4. One lane per row, one warp per block: 32 adjacent rows (8 row groups of the tiled cache) step
+//     together, H / 32 warps spread over the SMs; the stage leaves the FP64 pipe almost idle for the
+//     terrain stage that runs beside it.
 #pragma once
 
 #include "device_atm.cuh"
 
 namespace atmrt {
 
-constexpr int ATM_CELLS = 768;  // 256 m cells centred on ATM_BASE + j * 256 m, j = 0 .. 767 (up to 194 km)
-constexpr double ATM_CELL = 256.0;
-constexpr double ATM_BASE = -2048.0;
-constexpr int ATM_FIELDS = 5;   // per cell: p_j, T_j, g (K/m), w scale, alpha
-// An isothermal function p_j exp(k dh) is served by the same formula as a linear one,
-// p_j (1 + w)^alpha with w = k dh 2^-50 and alpha = 2^50 (relative error |k dh| 2^-51 < 1e-17).
-constexpr double ATM_ISO_SCALE = 1125899906842624.0;  // 2^50
-
-// Series coefficients live in constant memory so that DFMA reads them as constant-bank operands (a
-// 64-bit literal costs two MOVs per use otherwise).
-__constant__ double K_SER[16] = {
-    -1.0 / 2.0, 1.0 / 3.0, -1.0 / 4.0, 1.0 / 5.0, -1.0 / 6.0, 1.0 / 7.0,                        // log1p: [0..5]
-    1.0 / 2.0, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, 1.0 / 40320.0,  // exp:   [6..13]
-    1.0 / 362880.0,
-    0.0, 0.0};
-__constant__ double K_AIR[4] = {1.58123e-6, -2.9331e-8, 1.1043e-10, 1.83e-11};  // Ciddor compressibility a0, a1, a2, d
+// 250 m cells centred on ATM_BASE + j * 250 m, j = 0 .. 767 (-2.25 .. 189.75 km). The cell edges are the
+// multiples of 250 m, so that the temperature functions of US-76 (and of any definition written in round
+// numbers) start on an edge and no cell holds a kink of g.
+constexpr int ATM_CELLS = 768;
+constexpr double ATM_CELL = 250.0;
+constexpr double ATM_BASE = -2125.0;
+constexpr int ATM_FIELDS = 7;   // per cell: coefficients c0 .. c6 of g(h_j + 128 u), u in [-1, 1]; coefficient-major
 
 // 1/x for normal x: MUFU.RCP64H seed (>= 20 bits) and two Newton steps (error ~1 ulp).
 __device__ __forceinline__ double rcp_nr(double x) {
@@ -84,61 +74,117 @@ __device__ __forceinline__ void stg_if(double* p, double v, bool ok) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.global.f64 [%1], %2;\n\t}" ::"r"((unsigned)ok), "l"(p), "d"(v) : "memory");
 }
 
-// 1/(1 + x) for |x| < 1e-2: (1 - x)(1 + x^2)(1 + x^4) = 1 - x + ... - x^7 (remainder x^8 < 1e-16).
-__device__ __forceinline__ double rcp_1p(double x) {
-    const double x2 = x * x, m = 1.0 - x;
-    const double q = fma(x2, m, m);
-    return fma(x2 * x2, q, q);
-}
-
-// The libm path, out of line so that it stays out of the hot loop's instruction footprint.
-template <bool DRY>
-__device__ __noinline__ double env_n_slow(const DevAtmosphere& a, double h) {
-    return env_n_t<DRY>(a, h);
-}
-
 __device__ __forceinline__ double lds_f64(unsigned addr) {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
     return v;
 }
 
-// Environment::n(h) on the short-chain path. `cells` is the shared-space address of the anchor table,
-// [ATM_FIELDS][ATM_CELLS]; `sel` is the lane's stage altitude before the eps offset (r or h) and `hx` the
-// same altitude in cell units plus 1.5 * 2^52 (an imprecise copy of the chain that is only used to pick
-// the cell: its low word is the nearest cell index). *bad is set when the cell cannot serve the
-// altitude (NaN anchors); the caller then takes env_n_slow.
-template <bool DRY>
-__device__ __forceinline__ double env_n_fast(const DevAtmosphere& a, unsigned cells, double h, double hx, bool* bad) {
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52
-    const unsigned j = min((unsigned)__double2loint(hx), (unsigned)(ATM_CELLS - 1));  // negative, NaN -> an edge cell (NaN anchors)
-    const unsigned cj = cells + j * 8u;
-    const double pj = lds_f64(cj), tj = lds_f64(cj + 8u * ATM_CELLS), gj = lds_f64(cj + 16u * ATM_CELLS),
-                 sj = lds_f64(cj + 24u * ATM_CELLS), aj = lds_f64(cj + 32u * ATM_CELLS);
-    *bad = pj != pj;
-    const double dh = h - fma(hx - magic, ATM_CELL, ATM_BASE);
-    const double t = fma(gj, dh, tj);
-    const double rt = rcp_nr(t);  // independent of the pressure chain: overlaps it
-    const double w = dh * sj;
-    // log1p(w) = w (1 - w/2 + w^2/3 - ... + w^6/7)
-    const double w2 = w * w;
-    const double l01 = fma(w, K_SER[0], 1.0), l23 = fma(w, K_SER[2], K_SER[1]), l45 = fma(w, K_SER[4], K_SER[3]);
-    const double lq = fma(w2 * w2, fma(w2, K_SER[5], l45), fma(w2, l23, l01));
-    const double v = (aj * w) * lq;  // alpha log1p(w)
-    // exp(v), |v| < 0.08: Taylor to v^9
-    const double v2 = v * v, v4 = v2 * v2;
-    const double e01 = 1.0 + v, e23 = fma(v, K_SER[7], K_SER[6]), e45 = fma(v, K_SER[9], K_SER[8]),
-                 e67 = fma(v, K_SER[11], K_SER[10]), e89 = fma(v, K_SER[13], K_SER[12]);
-    const double ev = fma(v4 * v4, e89, fma(v4, fma(v2, e67, e45), fma(v2, e23, e01)));
-    const double p = pj * ev;
-    if (!DRY) return air_index_t<false>(a, p, t);
-    // air_index_t<true>: n = 1 + (rho_a / rho_axs) r_axs, rho_a = p m_a / (Z R T),
-    // Z = 1 - (p/T)(a0 + a1 tc + a2 tc^2) + (p/T)^2 d = 1 - e
-    const double t_c = t - 273.15;
-    const double poly = fma(fma(K_AIR[2], t_c, K_AIR[1]), t_c, K_AIR[0]);
-    const double pt = p * rt;
-    const double e = pt * fma(-pt, K_AIR[3], poly);
-    return fma(pt * a.k_dry, rcp_1p(-e), 1.0);
+// g(h) = dn/n exactly as the reference forms it (Environment::n three times, central difference): the
+// libm path, out of line so that it stays out of the hot loop's instruction footprint.
+__device__ __noinline__ double g_libm(const DevAtmosphere& a, double h) {
+    double n, dn;
+    env_n_dn(a, h, &n, &dn);
+    return dn / n;
+}
+
+// g(h) from the table. `tab` is the shared-space address of [ATM_FIELDS][ATM_CELLS]; `hs` = h - ATM_BASE,
+// the altitude above the centre of cell 0 (the callers fold ATM_BASE into the subtraction that turns r
+// into h). NaN when the cell does not serve the altitude (also for NaN, negative-overflow and too-high
+// altitudes: they select the first or the last cell, which are never served).
+__device__ __forceinline__ double g_table(unsigned tab, double hs) {
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52: the low word of hs / 250 + magic is the nearest cell index
+    const double hx = fma(hs, 1.0 / ATM_CELL, magic);
+    const unsigned j = min((unsigned)__double2loint(hx), (unsigned)(ATM_CELLS - 1));
+    const unsigned cj = tab + j * 8u;
+    const double c0 = lds_f64(cj), c1 = lds_f64(cj + 8u * ATM_CELLS), c2 = lds_f64(cj + 16u * ATM_CELLS),
+                 c3 = lds_f64(cj + 24u * ATM_CELLS), c4 = lds_f64(cj + 32u * ATM_CELLS), c5 = lds_f64(cj + 40u * ATM_CELLS),
+                 c6 = lds_f64(cj + 48u * ATM_CELLS);
+    const double u = fma(magic - hx, ATM_CELL, hs) * (2.0 / ATM_CELL);  // (hs - 250 j) / 125; 250 j is exact
+    const double u2 = u * u;
+    const double p01 = fma(c1, u, c0), p23 = fma(c3, u, c2), p45 = fma(c5, u, c4);
+    const double u4 = u2 * u2;
+    return fma(fma(c6, u2, p45), u4, fma(p23, u2, p01));
+}
+
+// A cell that holds the start of a temperature function is not served by the table (g has a kink
+// there); it is served piecewise instead: one polynomial per (cell, temperature function) over the part
+// of the cell that function owns. A cell whose fit fails for another reason (the law degenerates where a
+// temperature function approaches 0 K) is bisected down to 1 m pieces. Few, scanned linearly.
+struct DevGPiece {
+    double h_lo, h_hi;        // the piece serves h_lo <= h < h_hi
+    double centre, inv_half;  // u = (h - centre) * inv_half
+    double c[ATM_FIELDS];
+};
+constexpr int ATM_MAX_PIECES = 96;
+
+// The fallback of a failed table lookup: the pieces, then libm. Out of line (rare).
+__device__ __noinline__ double g_fallback(unsigned tab, const DevGPiece* __restrict__ pieces, int npieces, const DevAtmosphere& a, double h) {
+    const double g = g_table(tab, h - ATM_BASE);
+    if (g == g || h != h) return g;
+    for (int k = 0; k < npieces; ++k) {
+        const DevGPiece& p = pieces[k];
+        if (h >= p.h_lo && h < p.h_hi) {
+            const double u = (h - p.centre) * p.inv_half;
+            const double u2 = u * u, u4 = u2 * u2;
+            return fma(fma(p.c[6], u2, fma(p.c[5], u, p.c[4])), u4, fma(fma(p.c[3], u, p.c[2]), u2, fma(p.c[1], u, p.c[0])));
+        }
+    }
+    return g_libm(a, h);
+}
+
+// One classical RK4 step of the ray equation (PathStepper::next, restated in device_atm.cuh:
+// stepper_next) on the state (a, b) = (r, dr/dphi) or (h, dh/dx). MODE 0: g from the table only; returns
+// false when a lookup could not serve a finite altitude (the caller redoes the step in mode 1).
+// MODE 1: table, then pieces, then libm, per evaluation. MODE 2: every g through g_libm.
+struct GSource {
+    unsigned tab;
+    const DevGPiece* pieces;
+    int npieces;
+};
+template <bool FLAT, int MODE>
+__device__ __forceinline__ bool rk4_step(const DevAtmosphere& atm, const GSource& gs, double radius, double d, double hd, double d6, double a,
+                                         double b, double* a_out, double* b_out) {
+    auto G = [&](double alt) -> double {
+        if (MODE == 0) return g_table(gs.tab, alt - (FLAT ? ATM_BASE : radius + ATM_BASE));
+        const double h = FLAT ? alt : alt - radius;
+        if (MODE == 1) return g_fallback(gs.tab, gs.pieces, gs.npieces, atm, h);
+        return g_libm(atm, h);
+    };
+    const double a2 = fma(hd, b, a);  // ka1 = b
+    const double g1 = G(a), g2 = G(a2);
+    const double bb1 = b * b;
+    const double s1 = FLAT ? 1.0 + bb1 : fma(a, a, bb1);
+    const double c1 = FLAT ? 0.0 : fma(2.0 * bb1, rcp_nr(a), a);
+    const double inv_a2 = FLAT ? 0.0 : rcp_nr(a2);
+    const double kb1 = fma(g1, s1, c1);
+    const double b2 = fma(hd, kb1, b);
+    const double a3 = fma(hd, b2, a);
+    const double g3 = G(a3);
+    const double inv_a3 = FLAT ? 0.0 : rcp_nr(a3);
+    const double bb2 = b2 * b2;
+    const double s2 = FLAT ? 1.0 + bb2 : fma(a2, a2, bb2);
+    const double c2 = FLAT ? 0.0 : fma(2.0 * bb2, inv_a2, a2);
+    const double kb2 = fma(g2, s2, c2);
+    const double b3 = fma(hd, kb2, b);
+    const double a4 = fma(d, b3, a);
+    const double g4 = G(a4);
+    const double inv_a4 = FLAT ? 0.0 : rcp_nr(a4);
+    const double bb3 = b3 * b3;
+    const double s3 = FLAT ? 1.0 + bb3 : fma(a3, a3, bb3);
+    const double c3 = FLAT ? 0.0 : fma(2.0 * bb3, inv_a3, a3);
+    const double kb3 = fma(g3, s3, c3);
+    const double b4 = fma(d, kb3, b);
+    const double bb4 = b4 * b4;
+    const double s4 = FLAT ? 1.0 + bb4 : fma(a4, a4, bb4);
+    const double c4 = FLAT ? 0.0 : fma(2.0 * bb4, inv_a4, a4);
+    const double kb4 = fma(g4, s4, c4);
+    // y += (k1 + 2 k2 + 2 k3 + k4) d / 6
+    *a_out = fma((b + 2.0 * b2) + (2.0 * b3 + b4), d6, a);
+    *b_out = fma((kb1 + 2.0 * kb2) + (2.0 * kb3 + kb4), d6, b);
+    // a NaN g with finite altitudes = an unserved cell; with a NaN state every g is NaN and stays so.
+    const double sum = (g1 + g2) + (g3 + g4);
+    return MODE != 0 || sum == sum || a != a || b != b;
 }
 
 }  // namespace atmrt

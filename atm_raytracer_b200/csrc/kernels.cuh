@@ -67,7 +67,9 @@ struct DevBuffers {
     unsigned* sweep_flags;   // [1]: bit 0 = the path cache of this render is not monotone in the row (no sweep)
     unsigned char* sweep_col;  // [wl]: 1 = column needs the general march
     int* sweep_hit;          // [wl][h_pad]: first-hit step per pixel (0 = none)
-    const double* atm_cells;  // hydrostatic anchors of the ray-path stage (device_paths.cuh): [ATM_FIELDS][ATM_CELLS]
+    const double* atm_cells;  // g(h) table of the ray-path stage (device_paths.cuh): [ATM_FIELDS][ATM_CELLS]
+    const DevGPiece* atm_pieces;  // its cells that hold the start of a temperature function, piecewise
+    int n_atm_pieces;
 };
 
 enum Counter { CNT_RAY_STEPS = 0, CNT_TRACE_POINTS, CNT_PIXELS_HIT, CNT_OVERFLOWS, CNT_PATH_STEPS, CNT_COUNT };
@@ -106,6 +108,20 @@ __global__ void k_atm_probe(const __grid_constant__ DevScene S, const double* h,
     t[i] = tt;
     p[i] = pp;
     idx[i] = air_index(S.atm, pp, tt);
+}
+
+// Probe of the ray-path stage's atmosphere function g(h) = dn/n (device_paths.cuh): through the table (NaN
+// where the table does not serve the altitude) and through the libm path.
+__global__ void __launch_bounds__(128) k_refraction_probe(const __grid_constant__ DevScene S, const double* __restrict__ table, const double* h,
+                                                          int n, double* g_tab, double* g_ref, const DevGPiece* pieces, int npieces) {
+    __shared__ double tab_smem[ATM_FIELDS * ATM_CELLS];
+    for (int i = threadIdx.x; i < ATM_FIELDS * ATM_CELLS; i += blockDim.x) tab_smem[i] = table[i];
+    __syncthreads();
+    const unsigned tab = (unsigned)__cvta_generic_to_shared(tab_smem);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g_tab[i] = pieces ? g_fallback(tab, pieces, npieces, S.atm, h[i]) : g_table(tab, h[i] - ATM_BASE);
+    g_ref[i] = g_libm(S.atm, h[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -290,79 +306,33 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 // Stage B: ray paths (gen_path_cache, utils.rs:136-174). The physics offers one serial RK4 chain per
 // image row, so the stage is bound by the dependent-issue latency of ONE chain, not by FP64
-// throughput; see device_paths.cuh for how the critical path of a step is shortened (two rounds of
-// index evaluations per step instead of four, six lanes per row, re-anchored hydrostatic series,
-// reciprocals). Five rows per warp, one warp per block so that the chains spread over all SMs. The
-// cache is written step-major ([k][row]) so that both these stores and the march kernel's loads
-// (lanes = adjacent rows) are coalesced.
+// throughput; see device_paths.cuh for how the critical path of a step is shortened (g(h) = dn/n from
+// a per-atmosphere polynomial table in shared memory, overlapped lookups, reciprocals). One lane per
+// row, one warp per block so that the chains spread over all SMs. The cache is written tiled by groups
+// of four rows ([row/4][k][row%4]): four adjacent lanes store one 32-byte sector per plane.
 // ---------------------------------------------------------------------------------------------
-constexpr int ROWS_PER_WARP = 5;
-constexpr int LANES_PER_ROW = 6;
-
-template <bool FLAT, bool DRY>
+template <bool FLAT, bool LIBM>
 __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevScene S, DevBuffers B) {
-    __shared__ double cells_smem[ATM_FIELDS * ATM_CELLS];
+    __shared__ double tab_smem[ATM_FIELDS * ATM_CELLS];
     const int lane = threadIdx.x;
-    for (int i = lane; i < ATM_FIELDS * ATM_CELLS; i += 32) cells_smem[i] = B.atm_cells[i];
+#pragma unroll 8
+    for (int i = lane; i < ATM_FIELDS * ATM_CELLS; i += 32) tab_smem[i] = B.atm_cells[i];
     __syncwarp();
-    const unsigned cells = (unsigned)__cvta_generic_to_shared(cells_smem);
-    // All 32 lanes stay in the loop so that the exchanges are plain full-mask shuffles: lanes 30-31 and
-    // the slots of rows past the image shadow a real row and write nothing.
-    const int slot = min(lane / LANES_PER_ROW, ROWS_PER_WARP - 1), role = lane - slot * LANES_PER_ROW;
-    const int y_raw = blockIdx.x * ROWS_PER_WARP + slot;
+    const GSource gs{(unsigned)__cvta_generic_to_shared(tab_smem), B.atm_pieces, B.n_atm_pieces};
+    // All 32 lanes stay in the loop (rows past the image shadow the last row and write nothing).
+    const int y_raw = blockIdx.x * 32 + lane;
     const int y = min(y_raw, S.height - 1);
-    const int gbase = slot * LANES_PER_ROW;
-    const bool second = role >= 3 && role < 6;  // lanes 0-2 evaluate stages 1 and 3, lanes 3-5 stages 2 and 4
-    const int r3 = role % 3;
-    const double off = r3 == 0 ? -0.01 : (r3 == 1 ? 0.0 : 0.01);  // h - eps, h, h + eps
-    const bool writer = role == 1 && y_raw < S.height;
+    const bool writer = y_raw < S.height;
     const double alt = *B.obs_alt;
     const double radius = S.radius;
     const double d = FLAT ? S.step : S.step / radius;
     const double hd = 0.5 * d, d6 = d / 6.0;
     const double inv_radius = FLAT ? 0.0 : 1.0 / radius;
-    // cell index chain: (altitude + off - ATM_BASE) / ATM_CELL + 1.5 * 2^52, from r (spherical) or h (flat)
-    const double magic = 6755399441055744.0;
-    const double xc = ((FLAT ? 0.0 : -radius) + off - ATM_BASE) * (1.0 / ATM_CELL) + magic;
     const size_t row0 = path_index(S.n_t, 0, y);
     double* const o_dist = B.p_dist + row0;
     double* const o_elev = B.p_elev + row0;
     double* const o_len = B.p_len + row0;
 
-    // One round: the first lane group evaluates n around altitude aA, the second around
-    // aB = a + wB * bA (ka of stage A is its slope input bA); then kbA, bB = b + wB kbA and kbB follow.
-    // The centre lanes also form (1/(2 eps)) / n before the exchange, so that after the shuffles only
-    // one subtraction and one multiplication separate the index values from n'/n. FALLBACK: take the
-    // libm path for a lane whose cell cannot serve it (branchy); otherwise just record the fact.
-#define ATMRT_RK4_ROUND(FALLBACK, aA, bA, wB, aB, kbA, bB, kbB)                                                  \
-    const double aB = fma(wB, bA, a);                                                                            \
-    double kbA, bB, kbB;                                                                                         \
-    {                                                                                                            \
-        const double sel = second ? aB : aA;                                                                     \
-        const double hh = (FLAT ? sel : sel - radius) + off;                                                     \
-        bool bad;                                                                                                \
-        double mine = env_n_fast<DRY>(S.atm, cells, hh, fma(sel, 1.0 / ATM_CELL, xc), &bad);                     \
-        if (FALLBACK) {                                                                                          \
-            if (bad) mine = env_n_slow<DRY>(S.atm, hh);                                                          \
-        } else {                                                                                                 \
-            any_bad = any_bad || bad;                                                                            \
-        }                                                                                                        \
-        const double r50 = 50.0 * rcp_1p(mine - 1.0);                                                            \
-        const double bbA = bA * bA;                                                                              \
-        const double sA = FLAT ? 1.0 + bbA : fma(aA, aA, bbA);                                                   \
-        const double cA = FLAT ? 0.0 : fma(2.0 * bbA, rcp_nr(aA), aA);                                           \
-        const double inv_aB = FLAT ? 0.0 : rcp_nr(aB);                                                           \
-        const double nm = __shfl_sync(FULL, mine, gbase + 0), rA = __shfl_sync(FULL, r50, gbase + 1),            \
-                     np = __shfl_sync(FULL, mine, gbase + 2);                                                    \
-        const double om = __shfl_sync(FULL, mine, gbase + 3), rB = __shfl_sync(FULL, r50, gbase + 4),            \
-                     op = __shfl_sync(FULL, mine, gbase + 5);                                                    \
-        kbA = fma((np - nm) * rA, sA, cA);                                                                       \
-        bB = fma(wB, kbA, b);                                                                                    \
-        const double bbB = bB * bB;                                                                              \
-        const double sB = FLAT ? 1.0 + bbB : fma(aB, aB, bbB);                                                   \
-        const double cB = FLAT ? 0.0 : fma(2.0 * bbB, inv_aB, aB);                                               \
-        kbB = fma((op - om) * rB, sB, cB);                                                                       \
-    }
     // Outputs of step i-1 (`cur`, reached from `prev`): calc_dist (utils.rs:42-53, dx / R as dx * (1/R)), the
     // three cache entries, and the termination test of utils.rs:167-170 on the state before it. Branch-free
     // so that it can be scheduled in the shadow of the integration chain; for i == 1 it (re)writes the
@@ -385,7 +355,7 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
 
     // stepper state: spherical (r, dr/dphi, phi) or flat (h, dh/dx, x). The loop is software-pipelined:
     // iteration i integrates step i (the latency chain) while the outputs of step i-1 are produced in its
-    // shadow (between the two rounds).
+    // shadow.
     double a = FLAT ? alt : radius + alt;
     double b = FLAT ? tan(to_radians(get_ray_elev(S, y))) : a * tan(to_radians(get_ray_elev(S, y)));
     double t = 0.0;
@@ -402,22 +372,14 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
         // arithmetic produces (NaN in, NaN out). When every row of the warp is complete or NaN the
         // integration stops (tested on the incoming state, acted upon at the end of the iteration).
         const bool idle = __all_sync(FULL, done || a != a);
-        bool any_bad = false;
-        ATMRT_RK4_ROUND(false, a, b, hd, a2, kb1, b2, kb2)   // stages 1 and 2: altitudes a and a + d/2 b are both known
+        double a_new, b_new;
+        // one basic block: the outputs of step i-1 are scheduled into the stalls of the integration chain
+        const bool ok = rk4_step<FLAT, LIBM ? 2 : 0>(S.atm, gs, radius, d, hd, d6, a, b, &a_new, &b_new);
         ATMRT_PATH_OUTPUTS()
-        const double a3 = fma(hd, b2, a), b3 = fma(hd, kb2, b);
-        ATMRT_RK4_ROUND(false, a3, b3, d, a4, kb3, b4, kb4)  // stages 3 and 4
-        // y += (k1 + 2 k2 + 2 k3 + k4) d / 6
-        double a_new = fma((b + 2.0 * b2) + (2.0 * b3 + b4), d6, a);
-        double b_new = fma((kb1 + 2.0 * kb2) + (2.0 * kb3 + kb4), d6, b);
-        if (__any_sync(FULL, any_bad)) {  // rare: a lane left the anchor table (boundary cell, > 194 km, < -2 km): redo
-            ATMRT_RK4_ROUND(true, a, b, hd, a2s, kb1s, b2s, kb2s)
-            const double a3s = fma(hd, b2s, a), b3s = fma(hd, kb2s, b);
-            ATMRT_RK4_ROUND(true, a3s, b3s, d, a4s, kb3s, b4s, kb4s)
-            a_new = fma((b + 2.0 * b2s) + (2.0 * b3s + b4s), d6, a);
-            b_new = fma((kb1s + 2.0 * kb2s) + (2.0 * kb3s + kb4s), d6, b);
-        }
-        a = a_new, b = b_new;
+        if (!ok) rk4_step<FLAT, 1>(S.atm, gs, radius, d, hd, d6, a, b, &a_new, &b_new);  // rare: an altitude the table does not serve
+        // a complete row stops moving: its state would otherwise leave the table (below -2 km) and drag the
+        // warp through the libm path on every step
+        a = done ? a : a_new, b = done ? b : b_new;
         t += d;
         prev = cur;
         cur = FLAT ? RayState{t, a} : RayState{t * radius, a - radius};
@@ -437,7 +399,6 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
         cur = FLAT ? RayState{t, a} : RayState{t * radius, a - radius};
     }
 #undef ATMRT_PATH_OUTPUTS
-#undef ATMRT_RK4_ROUND
     if (writer) {
         B.p_n[y] = n;
         atomicAdd(B.counters + CNT_PATH_STEPS, (unsigned long long)(n - 1));

@@ -55,6 +55,9 @@ def _load():
         "atmrt_get_terrain_profile": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, P(C.c_int)]),
         "atmrt_get_path": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, P(C.c_int)]),
         "atmrt_atmosphere_probe": (C.c_int, [vp, vp, C.c_int, vp, vp, vp]),
+        "atmrt_refraction_probe": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, P(C.c_int)]),
+        "atmrt_set_path_mode": (C.c_int, [vp, C.c_int]),
+        "atmrt_refraction_table": (C.c_int, [vp, C.c_double, vp, C.c_int, P(C.c_int), P(C.c_int), P(C.c_double), P(C.c_double), P(C.c_int), P(C.c_int)]),
         "atmrt_observer_altitude": (C.c_int, [vp, P(C.c_double)]),
         "atmrt_fp64_peak": (C.c_int, [vp, P(C.c_double), P(C.c_double)]),
     }
@@ -77,6 +80,21 @@ assert META_DTYPE.itemsize == C.sizeof(abi.Meta) and TRACE_DTYPE.itemsize == C.s
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def refraction_table(atmosphere, wavelength):
+    """The ray-path stage's g(h) table for an abi.AtmosphereDef (host only, no GPU):
+    (cells[ncoef, ncells], base, cell_height, cells_served, pieces)."""
+    nc, nq, served, npieces = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    base, ch = C.c_double(), C.c_double()
+    rc = lib.atmrt_refraction_table(C.byref(atmosphere), wavelength, None, 0, C.byref(nc), C.byref(nq), C.byref(base), C.byref(ch), C.byref(served), C.byref(npieces))
+    if rc:
+        raise AtmrtError(rc, "refraction_table: invalid atmosphere")
+    cells = np.empty((nq.value, nc.value), dtype=np.float64)
+    rc = lib.atmrt_refraction_table(C.byref(atmosphere), wavelength, _ptr(cells), cells.size, None, None, None, None, C.byref(served), None)
+    if rc:
+        raise AtmrtError(rc, "refraction_table: invalid atmosphere")
+    return cells, base.value, ch.value, served.value, npieces.value
 
 
 class Terrain:
@@ -296,6 +314,17 @@ class Context:
         t, p, n = np.empty_like(h), np.empty_like(h), np.empty_like(h)
         self._check(lib.atmrt_atmosphere_probe(self._h, _ptr(h), h.size, _ptr(t), _ptr(p), _ptr(n)))
         return t, p, n
+
+    def refraction_probe(self, h, with_pieces=True):
+        """g(h) = dn/n of the ray-path stage: (without libm -- table and pieces --, NaN where unserved; through libm; cells served)."""
+        h = np.ascontiguousarray(h, dtype=np.float64)
+        gt, gl = np.empty_like(h), np.empty_like(h)
+        served = C.c_int()
+        self._check(lib.atmrt_refraction_probe(self._h, _ptr(h), h.size, int(bool(with_pieces)), _ptr(gt), _ptr(gl), C.byref(served)))
+        return gt, gl, served.value
+
+    def set_path_mode(self, mode):
+        self._check(lib.atmrt_set_path_mode(self._h, int(mode)))
 
     def observer_altitude(self):
         v = C.c_double()

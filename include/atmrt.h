@@ -227,6 +227,9 @@ int atmrt_render_trace(atmrt_ctx* ctx, atmrt_trace_point* points, int32_t* count
  * step like the reference loop (validation); 2 = hierarchical march always (validation of the sweep).
  * All three produce identical images. */
 int atmrt_set_march_mode(atmrt_ctx* ctx, int mode);
+/* Ray-path stage: 0 (default) g(h) from the table with libm for unserved altitudes, 1 every evaluation
+ * through libm, op for op the oracle's arithmetic (validation). */
+int atmrt_set_path_mode(atmrt_ctx* ctx, int mode);
 /* Tuning hook for the ray-path stage: image rows integrated per warp (1..32, default 32). */
 int atmrt_set_rows_per_warp(atmrt_ctx* ctx, int rows);
 
@@ -241,6 +244,19 @@ int atmrt_get_path(atmrt_ctx* ctx, int y, int capacity, double* dist, double* el
 /* Atmosphere::temperature / pressure and Environment::n at n altitudes, on the device. */
 int atmrt_atmosphere_probe(atmrt_ctx* ctx, const double* h, int n, double* temperature,
                            double* pressure, double* refractive_index);
+/* The ray-path stage's atmosphere function g(h) = dn/n, dn = (n(h+eps) - n(h-eps)) / (2 eps), eps = 0.01 m
+ * (atm-refraction's Environment::n / dn as the stepper combines them): as the stage
+ * evaluates it without libm -- the per-atmosphere polynomial table, plus (with_pieces != 0) the pieces that
+ * serve cells holding the start of a temperature function; NaN where neither serves the altitude, the
+ * stage then uses libm -- and through libm. cells_served: cells the table serves. Outputs may be NULL. */
+int atmrt_refraction_probe(atmrt_ctx* ctx, const double* h, int n, int with_pieces, double* g_table,
+                           double* g_libm, int* cells_served);
+/* The table itself, built on the host (no GPU needed): cells[ncoef][ncells], coefficient q of cell j at
+ * cells[q * ncells + j]; cell j is centred on base + j * cell_height and g(h) = sum_q c_q u^q with
+ * u = 2 (h - centre) / cell_height. NaN coefficients: cell not served. cells may be NULL (sizes only). */
+int atmrt_refraction_table(const atmrt_atmosphere_def* def, double wavelength, double* cells, int capacity,
+                           int* ncells, int* ncoef, double* base, double* cell_height, int* cells_served,
+                           int* npieces);
 /* Observer altitude after Altitude::abs (params.rs:23-30). */
 int atmrt_observer_altitude(atmrt_ctx* ctx, double* alt);
 /* FP64 FMA throughput micro-benchmark (roofline denominator): returns GFLOP/s (2 flop per FMA). */

@@ -121,6 +121,97 @@ def test_path_cache_matches_oracle(ctx, oracle_lib, name):
         np.testing.assert_allclose(got["path_length"], want["path_length"][:n], rtol=1e-12, atol=1e-9)
 
 
+def _custom_atmosphere(a):
+    """Humid air (the water-vapour terms of Ciddor's equation), a warm surface layer, a thin inversion
+    inside one table cell, an isothermal function and a lapse layer."""
+    a.humidity = 0.6
+    a.pressure_altitude, a.pressure = 0.0, 100800.0
+    a.temperature_altitude, a.temperature = 0.0, 291.0
+    grads = [-0.004, 0.05, 0.0, -0.0065, 0.0]
+    starts = [0.0, 2050.0, 2090.0, 4000.0, 11000.0]
+    a.n_functions = len(grads)
+    for i, (g, s) in enumerate(zip(grads, starts)):
+        a.fn_gradient[i], a.fn_start_altitude[i] = g, s
+
+
+@pytest.mark.parametrize("custom", [False, True])
+def test_refraction_table_on_the_device(ctx, custom):
+    """g(h) = dn/n as the ray-path stage evaluates it (table + pieces) against the libm evaluation (the
+    oracle's arithmetic op for op, 3e-7 relative rounding noise per evaluation)."""
+    p, terrain, _, _ = scene("c2", 0.04)
+    if custom:
+        _custom_atmosphere(p.atmosphere)
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    rng = np.random.default_rng(7)
+    # (below 12 km: n - 1 shrinks with altitude and the rounding noise of the libm evaluation grows like 1 / (n - 1))
+    starts = [p.atmosphere.fn_start_altitude[i] for i in range(1, p.atmosphere.n_functions) if p.atmosphere.fn_start_altitude[i] < 12000.0]
+    near = np.concatenate([s + rng.uniform(-150.0, 150.0, 400) for s in starts])
+    h = np.concatenate([rng.uniform(-1500.0, 12000.0, 40000), near, [-5000.0, 250000.0, np.nan, np.inf]])
+    gt, gl, served = ctx.refraction_probe(h, with_pieces=True)
+    g0, _, _ = ctx.refraction_probe(h, with_pieces=False)
+    assert served > 650
+    # out of range / NaN: not served by the table (the stage then uses libm, which yields what the arithmetic yields)
+    assert np.isnan(g0[-4:]).all() and np.isnan(gt[-2:]).all()
+    np.testing.assert_array_equal(gt[-4:-2], gl[-4:-2])
+    body = slice(0, 40000)
+    ok = ~np.isnan(gt[body])
+    assert ok.all()  # table + pieces serve every altitude of the lower atmosphere
+    if custom:  # ... a cell with the start of a temperature function inside (not on its edge) through the pieces
+        assert np.isnan(g0[body]).any()
+    rel = gt[body] / gl[body] - 1.0
+    assert np.abs(rel).max() < 5e-6
+    assert abs(rel.mean()) < 1e-8, rel.mean()
+    # next to the starts of the temperature functions, away from the +-0.01 m where the difference quotient blends two laws
+    m = np.ones(near.size, bool)
+    for s in starts:
+        m &= np.abs(near - s) > 0.02
+    reln = gt[40000:-4][m] / gl[40000:-4][m] - 1.0
+    assert not np.isnan(reln).any()
+    assert np.abs(reln).max() < 5e-6 and abs(reln.mean()) < 5e-8
+
+
+@pytest.mark.parametrize("flat", [False, True])
+def test_humid_custom_atmosphere_paths(ctx, oracle_lib, flat):
+    """The ray-path kernel under a humid custom atmosphere (pieces at every start of a temperature
+    function, an inversion, an isothermal function), against the oracle and against its own libm mode."""
+    p, terrain, _, _ = scene("c3_flat" if flat else "c2", 0.04)
+    _custom_atmosphere(p.atmosphere)
+    p.tilt, p.fov = 1.0, 12.0
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects([])
+    got = ctx.render()
+    h = np.concatenate([np.linspace(-500, 30000, 1500), [2049.99, 2050.0, 2050.01, 2090.0, 4000.0, 11000.0]])
+    t, pr, n = ctx.atmosphere_probe(h)
+    to, po, no = oracle_lib.atmosphere(p.atmosphere, p.wavelength, h)
+    np.testing.assert_array_equal(t, to)
+    np.testing.assert_allclose(pr, po, rtol=1e-14)
+    np.testing.assert_allclose(n - 1.0, no - 1.0, rtol=1e-12)
+    assert abs((no[0] - 1.0) / 2.8e-4 - 1.0) < 0.2
+    rows = (0, p.height // 3, p.height // 2, p.height - 1)
+    table = {y: ctx.path(y) for y in rows}
+    top = 0.0
+    for y in rows:
+        g, w = table[y], oracle_lib.path_cache(p, terrain.tiles, y)
+        k = len(g["dist"])
+        np.testing.assert_allclose(g["dist"], w["dist"][:k], rtol=1e-14)
+        np.testing.assert_allclose(g["elev"], w["elev"][:k], rtol=1e-9, atol=PATH_ATOL)
+        np.testing.assert_allclose(g["path_length"], w["path_length"][:k], rtol=1e-11, atol=1e-9)
+        top = max(top, float(np.nanmax(g["elev"])))
+    assert top > (9000.0 if flat else 11000.0)  # the rays crossed the inversion, the isothermal and the lapse functions
+    compare_render(got, oracle_lib.render(p, terrain.tiles), "humid-custom-" + ("flat" if flat else "sph"))
+    ctx.set_path_mode(1)  # every g through libm
+    try:
+        ctx.render(meta=False, steps=False)
+        for y in rows:
+            g, w = ctx.path(y), table[y]
+            assert len(g["dist"]) == len(w["dist"])
+            np.testing.assert_allclose(g["elev"], w["elev"], rtol=1e-9, atol=PATH_ATOL)
+    finally:
+        ctx.set_path_mode(0)
+
+
 # ---------------------------------------------------------------------------------------------
 # full renders
 # ---------------------------------------------------------------------------------------------
@@ -167,7 +258,7 @@ def compare_render(got, want, label="", finish_moves_frac=0.001):
     return report
 
 
-@pytest.mark.parametrize("name,scale", [("c1", 0.5), ("c2", 0.2), ("c3_flat", 0.15), ("c3_sph", 0.15), ("c4", 0.2)])
+@pytest.mark.parametrize("name,scale", [("c1", 0.5), ("c2", 0.2), ("c3_flat", 0.15), ("c3_sph", 0.15), ("c4", 0.2), ("c5", 0.0125)])
 def test_render_matches_oracle(ctx, oracle_lib, name, scale):
     p, terrain, objects, textures = scene(name, scale)
     ctx.set_terrain(terrain)
