@@ -75,7 +75,7 @@ struct atmrt_ctx {
     DevBuf d_atm_cells;
     DevBuf d_sweep_flags, d_sweep_col, d_sweep_hit;
     bool sweep_enabled = true;
-    DevBuf d_dist, d_colcalc, d_tlat, d_tlon, d_telev, d_tnx, d_tny, d_tnz, d_tclose;
+    DevBuf d_dist, d_colcalc, d_tlat, d_tlon, d_telev, d_tclose;
     DevBuf d_pdist, d_pelev, d_plen, d_pn;
     DevBuf d_tmin1, d_tmax1, d_tmin2, d_tmax2, d_tmin3, d_tmax3, d_close1, d_close2, d_close3;
     DevBuf d_rmin1, d_rmax1, d_rmin2, d_rmax2, d_rmin3, d_rmax3;
@@ -500,9 +500,6 @@ int prepare_render(atmrt_ctx* ctx) {
     e |= ensure(ctx, ctx->d_tlat, f8 * wl * np);
     e |= ensure(ctx, ctx->d_tlon, f8 * wl * np);
     e |= ensure(ctx, ctx->d_telev, f8 * wl * np);
-    e |= ensure(ctx, ctx->d_tnx, f8 * wl * np);
-    e |= ensure(ctx, ctx->d_tny, f8 * wl * np);
-    e |= ensure(ctx, ctx->d_tnz, f8 * wl * np);
     if (S.nobjects > 0) e |= ensure(ctx, ctx->d_tclose, 8 * wl * np);
     const size_t hp = (size_t)S.h_pad;
     e |= ensure(ctx, ctx->d_pdist, f8 * hp * n_t);
@@ -549,7 +546,7 @@ int prepare_render(atmrt_ctx* ctx) {
     B.dist_k = (const double*)ctx->d_dist.p;
     B.colcalc = (double*)ctx->d_colcalc.p;
     B.t_lat = (double*)ctx->d_tlat.p, B.t_lon = (double*)ctx->d_tlon.p, B.t_elev = (double*)ctx->d_telev.p;
-    B.t_nx = (double*)ctx->d_tnx.p, B.t_ny = (double*)ctx->d_tny.p, B.t_nz = (double*)ctx->d_tnz.p;
+    B.terrain = ctx->terrain;
     B.t_close = S.nobjects > 0 ? (unsigned long long*)ctx->d_tclose.p : nullptr;
     B.p_dist = (double*)ctx->d_pdist.p, B.p_elev = (double*)ctx->d_pelev.p, B.p_len = (double*)ctx->d_plen.p;
     B.p_n = (int*)ctx->d_pn.p;
@@ -835,7 +832,7 @@ void atmrt_destroy(atmrt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&ctx->d_objects_in, &ctx->d_objects, &ctx->d_dist, &ctx->d_colcalc, &ctx->d_tlat, &ctx->d_tlon, &ctx->d_telev,
-                      &ctx->d_tnx, &ctx->d_tny, &ctx->d_tnz, &ctx->d_tclose, &ctx->d_pdist, &ctx->d_pelev, &ctx->d_plen, &ctx->d_pn,
+                      &ctx->d_tclose, &ctx->d_pdist, &ctx->d_pelev, &ctx->d_plen, &ctx->d_pn,
                       &ctx->d_tmin1, &ctx->d_tmax1, &ctx->d_tmin2, &ctx->d_tmax2, &ctx->d_tmin3, &ctx->d_tmax3, &ctx->d_close1, &ctx->d_close2, &ctx->d_close3, &ctx->d_rmin1, &ctx->d_rmin3, &ctx->d_rmax3,
                       &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_sweep_flags, &ctx->d_sweep_col, &ctx->d_sweep_hit, &ctx->d_rgb, &ctx->d_meta,
                       &ctx->d_steps, &ctx->d_points, &ctx->d_counts, &ctx->d_probe_a, &ctx->d_probe_b, &ctx->d_probe_c, &ctx->d_probe_d};
@@ -1117,12 +1114,12 @@ int atmrt_get_terrain_profile(atmrt_ctx* ctx, int x, int capacity, double* lat, 
     if (lat) CUDA_TRY(ctx, cudaMemcpy(lat, B.t_lat + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
     if (lon) CUDA_TRY(ctx, cudaMemcpy(lon, B.t_lon + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
     if (elev) CUDA_TRY(ctx, cudaMemcpy(elev, B.t_elev + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
-    if (normal) {
-        std::vector<double> nx(m), ny(m), nz(m);
-        CUDA_TRY(ctx, cudaMemcpy(nx.data(), B.t_nx + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
-        CUDA_TRY(ctx, cudaMemcpy(ny.data(), B.t_ny + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
-        CUDA_TRY(ctx, cudaMemcpy(nz.data(), B.t_nz + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
-        for (int i = 0; i < m; ++i) normal[3 * i] = nx[i], normal[3 * i + 1] = ny[i], normal[3 * i + 2] = nz[i];
+    if (normal) {  // TerrainData::normal is not cached (kernels.cuh: sample_normal): evaluate it for this column
+        if (ensure(ctx, ctx->d_probe_a, 24 * (size_t)S.n_t)) return ATMRT_ERR_CUDA;
+        k_profile_normals<<<(S.n_t + 127) / 128, 128, 0, ctx->s_main>>>(S, ctx->terrain, B, x, (double*)ctx->d_probe_a.p);
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->s_main));
+        CUDA_TRY(ctx, cudaMemcpy(normal, ctx->d_probe_a.p, 24 * (size_t)m, cudaMemcpyDeviceToHost));
     }
     if (objects_close) {
         if (B.t_close)

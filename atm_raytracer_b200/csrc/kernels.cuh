@@ -52,7 +52,8 @@ struct DevBuffers {
     const double* dist_k;  // [n_t] accumulated `distance += step` (utils.rs:191-196), host-computed
     double* colcalc;       // [wl][8]: spherical {dir.xyz, pos.xyz}; flat {cos_az, sin_az, cos_lat0}
     // Stage A cache, [wl][n_pad]
-    double *t_lat, *t_lon, *t_elev, *t_nx, *t_ny, *t_nz;
+    DevTerrain terrain;  // the packed terrain (the march samples it for the deferred normals)
+    double *t_lat, *t_lon, *t_elev;
     unsigned long long* t_close;
     // Stage B cache, step-major [n_t][h_pad]
     double *p_dist, *p_elev, *p_len;
@@ -243,7 +244,44 @@ __device__ __forceinline__ V3 find_normal(const DevScene& S, const DevTerrain& T
 // ---------------------------------------------------------------------------------------------
 // Stage A: terrain profile. One thread per (column, sample); lanes run along the ray so the
 // [column][k] stores are coalesced and the bilinear taps of a warp walk along one azimuth.
+//
+// The reference computes find_normal for every sample (utils.rs:72-88) although only the two samples
+// that bracket a hit are ever read (utils.rs:108-125 through :233). The normal is a pure function of the
+// sample's coordinates, so it is deferred to the hit (sample_normal below, called from process_step):
+// same arithmetic, same result, 2 evaluations per hit instead of one per sample.
 // ---------------------------------------------------------------------------------------------
+struct SampleTrig {
+    double sinlat, coslat, sinlon, coslon;
+};
+
+// Sine and cosine of a sample's latitude and longitude as the reference's world_directions / as_cartesian
+// need them (sin/cos of the degree values).
+// Spherical: fpos is the unit vector of (lat, lon): its components ARE sin(lat), cos(lat) cos(lon),
+// cos(lat) sin(lon) to the rounding of the walk (|fpos| = 1 +- 2e-16), so they are recovered without four
+// more libm calls. Near the poles (cos lat < 0.05) the division loses bits: evaluate them from the angles
+// as the reference does.
+__device__ __forceinline__ SampleTrig sample_trig(const DevScene& S, V3 fpos, double lat, double lon) {
+    SampleTrig t;
+    const double c2 = fpos.x * fpos.x + fpos.y * fpos.y;
+    if (!S.flat && c2 > 0.0025) {
+        t.sinlat = fpos.z;
+        t.coslat = sqrt(c2);
+        const double ic = 1.0 / t.coslat;
+        t.sinlon = fpos.y * ic, t.coslon = fpos.x * ic;
+    } else {
+        sincos(to_radians(lat), &t.sinlat, &t.coslat);
+        sincos(to_radians(lon), &t.sinlon, &t.coslon);
+    }
+    return t;
+}
+
+// SphericalCalc::coords_at_dist (directional_calc.rs:71-86) up to the unit vector of the sample.
+__device__ __forceinline__ V3 walk_fpos(const DevScene& S, const double* __restrict__ cc, double d) {
+    double sinang, cosang;
+    sincos(d / S.radius, &sinang, &cosang);
+    return V3{cc[3], cc[4], cc[5]} * cosang + V3{cc[0], cc[1], cc[2]} * sinang;
+}
+
 __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__ DevScene S, DevTerrain T, DevBuffers B, int col0) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     int xl = col0 + blockIdx.y;  // the render is issued in column chunks (atmrt_lib.cu:launch_render)
@@ -251,34 +289,16 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
     const double d = B.dist_k[k];
     const double* cc = B.colcalc + (size_t)xl * 8;
     double lat, lon;
-    double sinlat, coslat, sinlon, coslon;  // of the sample's coordinates, for find_normal and is_close
+    V3 fpos{0.0, 0.0, 0.0};
     if (S.flat) {  // FlDsCalc::coords_at_dist, directional_calc.rs:41-47
         double d_lat = cc[0] * d / DEGREE_DISTANCE;
         double d_lon = cc[1] * d / DEGREE_DISTANCE / cc[2];
         lat = S.lat0 + d_lat;
         lon = S.lon0 + d_lon;
-        sincos(to_radians(lat), &sinlat, &coslat);
-        sincos(to_radians(lon), &sinlon, &coslon);
     } else {  // SphericalCalc::coords_at_dist, directional_calc.rs:71-86
-        double sinang, cosang;
-        sincos(d / S.radius, &sinang, &cosang);
-        const V3 fpos = V3{cc[3], cc[4], cc[5]} * cosang + V3{cc[0], cc[1], cc[2]} * sinang;
+        fpos = walk_fpos(S, cc, d);
         lat = to_degrees(asin(fpos.z));
         lon = to_degrees(atan2(fpos.y, fpos.x));
-        // fpos is the unit vector of (lat, lon): its components ARE sin(lat), cos(lat) cos(lon), cos(lat) sin(lon)
-        // to the rounding of the walk (|fpos| = 1 +- 2e-16), so the reference's sin/cos of the degree values
-        // (world_directions, as_cartesian) are recovered without four more libm calls. Near the poles
-        // (cos lat < 0.05) the division loses bits: evaluate them from the angles as the reference does.
-        const double c2 = fpos.x * fpos.x + fpos.y * fpos.y;
-        if (c2 > 0.0025) {
-            sinlat = fpos.z;
-            coslat = sqrt(c2);
-            const double ic = 1.0 / coslat;
-            sinlon = fpos.y * ic, coslon = fpos.x * ic;
-        } else {
-            sincos(to_radians(lat), &sinlat, &coslat);
-            sincos(to_radians(lon), &sinlon, &coslon);
-        }
     }
     double elev = elev_or_zero(T, lat, lon);
     size_t idx = (size_t)xl * S.n_pad + k;
@@ -286,21 +306,35 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
     B.t_lon[idx] = lon;
     B.t_elev[idx] = elev;
 
-    V3 normal = find_normal(S, T, lat, lon, sinlat, coslat, sinlon, coslon);
-    B.t_nx[idx] = normal.x;
-    B.t_ny[idx] = normal.y;
-    B.t_nz[idx] = normal.z;
-
     if (S.nobjects > 0) {  // Object::is_close, frustum.rs:103-114 / billboard.rs:68-78
+        const SampleTrig t = sample_trig(S, fpos, lat, lon);
         unsigned long long mask = 0;
         for (int i = 0; i < S.nobjects; ++i) {
             const DevObject& o = B.objects[i];
-            V3 pos = as_cartesian_sc(S.earth_model, S.radius, lat, o.elev, sinlat, coslat, sinlon, coslon);
+            V3 pos = as_cartesian_sc(S.earth_model, S.radius, lat, o.elev, t.sinlat, t.coslat, t.sinlon, t.coslon);
             V3 dist_v = pos - o.pos;
             if (dot(dist_v, dist_v) < 2.0 * (o.close_r + S.step) * (o.close_r + S.step)) mask |= 1ull << i;
         }
         B.t_close[idx] = mask;
     }
+}
+
+// TerrainData::normal of sample k of column xl (find_normal at the sample's coordinates, utils.rs:84):
+// the coordinates come from the cache, the unit vector of the walk is recomputed (one sincos).
+__device__ __forceinline__ V3 sample_normal(const DevScene& S, const DevTerrain& T, const DevBuffers& B, int xl, int k, double lat, double lon) {
+    V3 fpos{0.0, 0.0, 0.0};
+    if (!S.flat) fpos = walk_fpos(S, B.colcalc + (size_t)xl * 8, B.dist_k[k]);
+    const SampleTrig t = sample_trig(S, fpos, lat, lon);
+    return find_normal(S, T, lat, lon, t.sinlat, t.coslat, t.sinlon, t.coslon);
+}
+
+// The normals of one column (probe: atmrt_get_terrain_profile), [k][3].
+__global__ void __launch_bounds__(128) k_profile_normals(const __grid_constant__ DevScene S, DevTerrain T, DevBuffers B, int xl, double* out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= S.n_t) return;
+    const size_t idx = (size_t)xl * S.n_pad + k;
+    const V3 n = sample_normal(S, T, B, xl, k, B.t_lat[idx], B.t_lon[idx]);
+    out[3 * k] = n.x, out[3 * k + 1] = n.y, out[3 * k + 2] = n.z;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -642,7 +676,7 @@ __device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers
     if (!OBJECTS) {
         if (!terrain_hit) return false;
         const double prop = diff1 / (diff1 - diff2);
-        V3 n0{B.t_nx[ti - 1], B.t_ny[ti - 1], B.t_nz[ti - 1]}, n1{B.t_nx[ti], B.t_ny[ti], B.t_nz[ti]};
+        const V3 n0 = sample_normal(S, B.terrain, B, xl, k - 1, lat0, lon0), n1 = sample_normal(S, B.terrain, B, xl, k, lat1, lon1);
         // TracingState::interpolate, utils.rs:108-125
         emit_point<TRACE>(S, O, pixel, k, st, true, lat0 + (lat1 - lat0) * prop, lon0 + (lon1 - lon0) * prop,
                           dist0 + (dist1 - dist0) * prop, elev0 + (elev1 - elev0) * prop, len0 + (len1 - len0) * prop,
@@ -658,7 +692,7 @@ __device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers
     bool overflow = false;
     if (terrain_hit) {
         double prop = diff1 / (diff1 - diff2);
-        V3 n0{B.t_nx[ti - 1], B.t_ny[ti - 1], B.t_nz[ti - 1]}, n1{B.t_nx[ti], B.t_ny[ti], B.t_nz[ti]};
+        const V3 n0 = sample_normal(S, B.terrain, B, xl, k - 1, lat0, lon0), n1 = sample_normal(S, B.terrain, B, xl, k, lat1, lon1);
         c_prop[0] = prop;
         c_normal[0] = n0 + (n1 - n0) * prop;
         c_color[0] = Color4{0.0, 0.0, 0.0, S.shade.terrain_alpha};
@@ -1009,7 +1043,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(const __grid_constant__
 // row-major [y][x] image and metadata are stored as contiguous row segments.
 constexpr int SHADE_COLS = 16;
 
-__global__ void __launch_bounds__(32 * SHADE_COLS) k_sweep_shade(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O) {
+__global__ void __launch_bounds__(32 * SHADE_COLS, 2) k_sweep_shade(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O) {
     if (B.sweep_flags[0] != 0) return;
     __shared__ double s_meta[32][SHADE_COLS * 4];
     __shared__ unsigned char s_rgb[32][SHADE_COLS * 3];
