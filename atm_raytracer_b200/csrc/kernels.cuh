@@ -660,7 +660,7 @@ __device__ __forceinline__ void emit_point(const DevScene& S, const MarchOut& O,
 // One march step that holds an event. Returns true when the pixel finishes (an alpha == 1 surface).
 template <bool OBJECTS, bool TRACE>
 __device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers& B, const MarchOut& O, int xl, int y, int k,
-                                             size_t pixel, PixelState& st) {
+                                             size_t pixel, PixelState& st, const V3* normals = nullptr) {
     const size_t ti = (size_t)xl * S.n_pad + k;
     const size_t p1 = path_index(S.n_t, k, y), p0 = p1 - PATH_ROWS;
     // old_tracing_state = (terrain[k-1], path[k-1]) with dist/path_len forced to 0 for k-1 == 0.
@@ -676,7 +676,12 @@ __device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers
     if (!OBJECTS) {
         if (!terrain_hit) return false;
         const double prop = diff1 / (diff1 - diff2);
-        const V3 n0 = sample_normal(S, B.terrain, B, xl, k - 1, lat0, lon0), n1 = sample_normal(S, B.terrain, B, xl, k, lat1, lon1);
+        V3 n0, n1;
+        if (normals) {
+            n0 = normals[0], n1 = normals[1];
+        } else {
+            n0 = sample_normal(S, B.terrain, B, xl, k - 1, lat0, lon0), n1 = sample_normal(S, B.terrain, B, xl, k, lat1, lon1);
+        }
         // TracingState::interpolate, utils.rs:108-125
         emit_point<TRACE>(S, O, pixel, k, st, true, lat0 + (lat1 - lat0) * prop, lon0 + (lon1 - lon0) * prop,
                           dist0 + (dist1 - dist0) * prop, elev0 + (elev1 - elev0) * prop, len0 + (len1 - len0) * prop,
@@ -1049,6 +1054,7 @@ __global__ void __launch_bounds__(32 * SHADE_COLS, 2) k_sweep_shade(const __grid
     __shared__ unsigned char s_rgb[32][SHADE_COLS * 3];
     __shared__ int s_steps[32][SHADE_COLS];
     __shared__ unsigned char s_skip[SHADE_COLS];
+    __shared__ double s_nrm[SHADE_COLS][64][3];
     const int wl = S.x1 - S.x0;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c0 = blockIdx.y * SHADE_COLS, y0 = blockIdx.x * 32;
@@ -1063,8 +1069,49 @@ __global__ void __launch_bounds__(32 * SHADE_COLS, 2) k_sweep_shade(const __grid
     init_pixel(st);
     int consumed = nlim > 0 ? nlim - 1 : 0;
     const int k = active ? B.sweep_hit[(size_t)xx * S.h_pad + yy] : 0;
-    if (k > 0) {
-        process_step<false, false>(S, B, O, xx, yy, k, pixel, st);
+    const bool hit = k > 0;
+    // The terrain normals of the two samples that bracket each hit (TerrainData::normal, deferred from stage
+    // A: sample_normal). The 32 rows of the warp hit a handful of distinct samples -- the foreground rows
+    // share one step, rows on a slope hit consecutive steps, and sample k - 1 of one row is sample k of the
+    // next run -- so each distinct sample is evaluated once: the first lane of every run of equal k owns
+    // sample k, and sample k - 1 unless the next run owns it as its k; the owned samples are numbered,
+    // dealt to the lanes 32 at a time, and read back through shared memory.
+    V3 nrm[2] = {V3{0.0, 0.0, 0.0}, V3{0.0, 0.0, 0.0}};
+    {
+        const int k_up = __shfl_up_sync(FULL, k, 1);
+        const bool lead = hit && (lane == 0 || k_up != k);
+        const unsigned mask1 = __ballot_sync(FULL, lead);
+        if (mask1) {  // warp-uniform
+            const int leader = 31 - __clz(mask1 & (0xffffffffu >> (31 - lane)));         // of this lane's run (when it hit)
+            const unsigned later = leader >= 31 || leader < 0 ? 0u : (mask1 & (0xfffffffeu << leader));
+            const int next = later ? __ffs(later) - 1 : -1;                               // leader of the next run
+            const int k_next = __shfl_sync(FULL, k, next < 0 ? 0 : next);
+            const bool own0 = lead && !(next >= 0 && k_next == k - 1);
+            const unsigned mask0 = __ballot_sync(FULL, own0);
+            const int n1cnt = __popc(mask1), total = n1cnt + __popc(mask0);
+            for (int base = 0; base < total; base += 32) {
+                const int item = base + lane;
+                const bool mine = item < total, second = item >= n1cnt;
+                const unsigned src = mine ? __fns(second ? mask0 : mask1, 0, (second ? item - n1cnt : item) + 1) : 0u;
+                const int ks = __shfl_sync(FULL, k, src & 31);
+                if (mine) {
+                    const int smp = ks - (second ? 1 : 0);
+                    const size_t ti = (size_t)xx * S.n_pad + smp;
+                    const V3 n = sample_normal(S, B.terrain, B, xx, smp, B.t_lat[ti], B.t_lon[ti]);
+                    s_nrm[w][item][0] = n.x, s_nrm[w][item][1] = n.y, s_nrm[w][item][2] = n.z;
+                }
+            }
+            __syncwarp();
+            if (hit) {
+                const int i1 = __popc(mask1 & ((1u << leader) - 1u));
+                const int i0 = ((mask0 >> leader) & 1u) ? n1cnt + __popc(mask0 & ((1u << leader) - 1u)) : i1 + 1;
+                nrm[0] = V3{s_nrm[w][i0][0], s_nrm[w][i0][1], s_nrm[w][i0][2]};
+                nrm[1] = V3{s_nrm[w][i1][0], s_nrm[w][i1][1], s_nrm[w][i1][2]};
+            }
+        }
+    }
+    if (hit) {
+        process_step<false, false>(S, B, O, xx, yy, k, pixel, st, nrm);
         consumed = k;
     }
     const Rgb8 px = final_color(S, st);
