@@ -65,6 +65,8 @@ struct atmrt_ctx {
     int march_mode = 0;
     int rows_per_warp = 32;
     std::vector<double> dist_k;
+    std::vector<double> path_x;  // [2][n_t]: x of path element k (the same for every row), and (x_k - x_{k-1}) / R
+    int path_k_far = 0;
     std::vector<double> atm_cells;  // g(h) table of the ray-path stage, [ATM_FIELDS][ATM_CELLS]
     std::vector<DevGPiece> atm_pieces;  // its cells that hold the start of a temperature function
     int atm_cells_served = 0;
@@ -485,6 +487,27 @@ int prepare_render(atmrt_ctx* ctx) {
     for (double d = 0.0; d < p.max_distance; d += p.simulation_step) ctx->dist_k.push_back(d);
     const int n_t = (int)ctx->dist_k.size();
     S.n_t = n_t;
+    {
+        // PathElem::dist does not depend on the row: the stepper's independent variable advances by the same
+        // step for every ray (phi += step / R, x = phi * R; flat and straight rays: x += step). The same
+        // running sums here, element by element.
+        const bool sph_rk4 = !S.flat && !S.straight;
+        const double d = sph_rk4 ? p.simulation_step / p.radius : p.simulation_step;
+        const double inv_radius = S.flat ? 0.0 : 1.0 / p.radius;
+        ctx->path_x.assign((size_t)2 * n_t, 0.0);
+        double t = 0.0;
+        ctx->path_k_far = n_t;
+        for (int k = 1; k < n_t; ++k) {
+            t += d;
+            const double x = sph_rk4 ? t * p.radius : t;
+            ctx->path_x[k] = x;
+            const double dx = x - ctx->path_x[k - 1];
+            ctx->path_x[(size_t)n_t + k] = S.flat ? dx : dx * inv_radius;  // calc_dist's dx / R (utils.rs:49)
+        }
+        for (int k = n_t - 1; k >= 0; --k)
+            if (ctx->path_x[k] > p.max_distance) ctx->path_k_far = k;  // first element past max_distance (utils.rs:167)
+        S.path_k_far = ctx->path_k_far;
+    }
     S.n_pad = (n_t + 31) / 32 * 32;
     S.n1 = (n_t + CHUNK - 1) / CHUNK;
     S.n1_pad = (S.n1 + 31) / 32 * 32;
@@ -502,7 +525,7 @@ int prepare_render(atmrt_ctx* ctx) {
     e |= ensure(ctx, ctx->d_telev, f8 * wl * np);
     if (S.nobjects > 0) e |= ensure(ctx, ctx->d_tclose, 8 * wl * np);
     const size_t hp = (size_t)S.h_pad;
-    e |= ensure(ctx, ctx->d_pdist, f8 * hp * n_t);
+    e |= ensure(ctx, ctx->d_pdist, f8 * 2 * n_t);
     e |= ensure(ctx, ctx->d_pelev, f8 * hp * n_t);
     e |= ensure(ctx, ctx->d_plen, f8 * hp * n_t);
     e |= ensure(ctx, ctx->d_pn, sizeof(int) * hp);
@@ -548,7 +571,8 @@ int prepare_render(atmrt_ctx* ctx) {
     B.t_lat = (double*)ctx->d_tlat.p, B.t_lon = (double*)ctx->d_tlon.p, B.t_elev = (double*)ctx->d_telev.p;
     B.terrain = ctx->terrain;
     B.t_close = S.nobjects > 0 ? (unsigned long long*)ctx->d_tclose.p : nullptr;
-    B.p_dist = (double*)ctx->d_pdist.p, B.p_elev = (double*)ctx->d_pelev.p, B.p_len = (double*)ctx->d_plen.p;
+    B.path_x = (const double*)ctx->d_pdist.p, B.path_dxr = B.path_x + S.n_t;
+    B.p_elev = (double*)ctx->d_pelev.p, B.p_len = (double*)ctx->d_plen.p;
     B.p_n = (int*)ctx->d_pn.p;
     B.tmin1 = (double*)ctx->d_tmin1.p, B.tmax1 = (double*)ctx->d_tmax1.p;
     B.tmin2 = (double*)ctx->d_tmin2.p, B.tmax2 = (double*)ctx->d_tmax2.p;
@@ -574,6 +598,7 @@ int prepare_render(atmrt_ctx* ctx) {
 int upload_scene_inputs(atmrt_ctx* ctx, cudaStream_t s) {
     const DevScene& S = ctx->scene;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dist.p, ctx->dist_k.data(), sizeof(double) * S.n_t, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pdist.p, ctx->path_x.data(), sizeof(double) * 2 * S.n_t, cudaMemcpyHostToDevice, s));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_atm_cells.p, ctx->atm_cells.data(), sizeof(double) * ATM_FIELDS * ATM_CELLS, cudaMemcpyHostToDevice, s));
     if (!ctx->atm_pieces.empty())
         CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->d_atm_cells.p + sizeof(double) * ATM_FIELDS * ATM_CELLS, ctx->atm_pieces.data(),
@@ -1144,7 +1169,7 @@ int atmrt_get_path(atmrt_ctx* ctx, int y, int capacity, double* dist, double* el
     if (m <= 0) return 0;
     // the cache is [row / 4][k][row % 4]: gather row y with a strided 2-D copy (pitch = one row group)
     const size_t pitch = (size_t)PATH_ROWS * sizeof(double), off = path_index(S.n_t, 0, y);
-    if (dist) CUDA_TRY(ctx, cudaMemcpy2D(dist, sizeof(double), ctx->buf.p_dist + off, pitch, sizeof(double), (size_t)m, cudaMemcpyDeviceToHost));
+    if (dist) memcpy(dist, ctx->path_x.data(), sizeof(double) * (size_t)m);  // row-independent (prepare_render)
     if (elev) CUDA_TRY(ctx, cudaMemcpy2D(elev, sizeof(double), ctx->buf.p_elev + off, pitch, sizeof(double), (size_t)m, cudaMemcpyDeviceToHost));
     if (path_length)
         CUDA_TRY(ctx, cudaMemcpy2D(path_length, sizeof(double), ctx->buf.p_len + off, pitch, sizeof(double), (size_t)m, cudaMemcpyDeviceToHost));

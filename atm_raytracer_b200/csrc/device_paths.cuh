@@ -25,12 +25,16 @@
 //     by one polynomial per function (`pieces`), everything else (T <= 1 K, fit check failed, outside
 //     -2.25 .. 189.75 km) by g_libm(), which is the oracle's arithmetic op for op (device_atm.cuh).
 //     atmrt_set_path_mode(1) forces every evaluation through g_libm (validation, tests).
-//  3. RK4 structure: stage 2's altitude a + d/2 b is known when the step starts and stage 4's needs
-//     kb2 only, so the lookups of stages {1, 2} and {3, 4} overlap; 1/r for the geometric term comes
-//     from MUFU.RCP64H + two Newton steps issued in the shadow of the lookups.
+//  3. Two lookups per step instead of four, predicted one step ahead (rk4_step_shared): the stage
+//     altitudes lie within 1e-4 m of the points a + d/2 b and a + d b, also when those are extrapolated
+//     from the previous state; g and 1/r at the stages are the values at those points with a first-order
+//     correction (neglected term < 1e-12 relative). The lookups leave the critical path; what remains on
+//     it is the chain of the four slope updates.
 //  4. One lane per row, one warp per block: 32 adjacent rows (8 row groups of the tiled cache) step
 //     together, H / 32 warps spread over the SMs; the stage leaves the FP64 pipe almost idle for the
-//     terrain stage that runs beside it.
+//     terrain stage that runs beside it. A lone warp issues one instruction every ~2.3 cycles (ncu), so
+//     the step is also trimmed in instructions: PathElem::dist and calc_dist's dx / R do not depend on
+//     the row and come from two host tables.
 #pragma once
 
 #include "device_atm.cuh"
@@ -105,6 +109,92 @@ __device__ __forceinline__ double g_table(unsigned tab, double hs) {
     const double p01 = fma(c1, u, c0), p23 = fma(c3, u, c2), p45 = fma(c5, u, c4);
     const double u4 = u2 * u2;
     return fma(fma(c6, u2, p45), u4, fma(p23, u2, p01));
+}
+
+// g and dg/dh at a base altitude: the value as g_table, the slope from the first two derivative terms
+// (c1 + 2 c2 u) / 125 -- relative error x^2 / 2 with x = 125 m / H < 0.07, H the scale height of g, which
+// is ample for the first-order corrections below (they move g by a relative 1e-8).
+struct GBase {
+    double g, t;
+};
+__device__ __forceinline__ GBase g_table2(unsigned tab, double hs) {
+    const double magic = 6755399441055744.0;
+    const double hx = fma(hs, 1.0 / ATM_CELL, magic);
+    const unsigned j = min((unsigned)__double2loint(hx), (unsigned)(ATM_CELLS - 1));
+    const unsigned cj = tab + j * 8u;
+    const double c0 = lds_f64(cj), c1 = lds_f64(cj + 8u * ATM_CELLS), c2 = lds_f64(cj + 16u * ATM_CELLS),
+                 c3 = lds_f64(cj + 24u * ATM_CELLS), c4 = lds_f64(cj + 32u * ATM_CELLS), c5 = lds_f64(cj + 40u * ATM_CELLS),
+                 c6 = lds_f64(cj + 48u * ATM_CELLS);
+    const double u = fma(magic - hx, ATM_CELL, hs) * (2.0 / ATM_CELL);
+    const double u2 = u * u;
+    const double p01 = fma(c1, u, c0), p23 = fma(c3, u, c2), p45 = fma(c5, u, c4);
+    const double u4 = u2 * u2;
+    GBase r;
+    r.g = fma(fma(c6, u2, p45), u4, fma(p23, u2, p01));
+    r.t = fma(c2 + c2, u, c1) * (2.0 / ATM_CELL);
+    return r;
+}
+
+// A base point of the lookups: the altitude variable P (r or h), g and dg/dh there, and 1/P.
+struct PathBase {
+    double P, g, t, r;
+};
+template <bool FLAT>
+__device__ __forceinline__ PathBase path_base(unsigned tab, double shift, double P) {
+    const GBase v = g_table2(tab, P - shift);
+    return PathBase{P, v.g, v.t, FLAT ? 0.0 : rcp_nr(P)};
+}
+
+// One classical RK4 step with two table lookups instead of four, both OFF the critical path. The four
+// stage altitudes of step i are
+//   a,   a + d/2 b,   a + d/2 b + (d/2)^2 kb1,   a + d b + d (d/2) kb2
+// and step i+1 starts at a + d b + O(d^2 kb). With M_i ~ a + d/2 b and N_i ~ a + d b, every altitude lies
+// within a few d^2 |kb| of one of M_i, N_i, N_{i-1} -- 1e-4 m for a 25 m step, 1e-2 m at 80 degrees of
+// elevation -- even when M_i, N_i are PREDICTED one step ahead from the previous state
+// (a_{i-1} + 3/2 d b_{i-1}, a_{i-1} + 2 d b_{i-1}). g is smooth on the scale of kilometres, so g at the
+// stage altitudes is g at the base plus a first-order correction; the neglected g'' e^2 / 2 is below
+// 1e-12 relative for |e| < 0.01 m (the reference's own g carries 3e-7 of rounding noise), and 1/r for the
+// geometric term likewise (error (e/r)^2). `ok` is false -- the caller redoes the step with per-stage
+// evaluations -- when a base is not served by the table or a correction distance exceeds 0.25 m
+// (kilometre-long steps). The lookups for step i+1 depend only on the state at the start of step i, so
+// the scheduler interleaves them with the chain of the four slope updates, which is all that is left on
+// the critical path.
+template <bool FLAT>
+__device__ __forceinline__ bool rk4_step_shared(double d, double hd, double d6, double a, double b, const PathBase& E, const PathBase& M,
+                                                const PathBase& N, double* a_out, double* b_out) {
+    // stage 1 at a, from the previous step's N
+    const double e1 = a - E.P;
+    const double g1 = fma(E.t, e1, E.g);
+    const double i1 = FLAT ? 0.0 : fma(-(e1 * E.r), E.r, E.r);
+    const double bb1 = b * b;
+    const double kb1 = fma(g1, FLAT ? 1.0 + bb1 : fma(a, a, bb1), FLAT ? 0.0 : fma(bb1 + bb1, i1, a));
+    const double b2 = fma(hd, kb1, b), a2 = fma(hd, b, a);
+    // stage 2 at a2 ~ M
+    const double e2 = a2 - M.P;
+    const double g2 = fma(M.t, e2, M.g);
+    const double i2 = FLAT ? 0.0 : fma(-(e2 * M.r), M.r, M.r);
+    const double bb2 = b2 * b2;
+    const double kb2 = fma(g2, FLAT ? 1.0 + bb2 : fma(a2, a2, bb2), FLAT ? 0.0 : fma(bb2 + bb2, i2, a2));
+    const double b3 = fma(hd, kb2, b), a3 = fma(hd, b2, a);
+    // stage 3 at a3 = a2 + (d/2)^2 kb1
+    const double e3 = a3 - M.P;
+    const double g3 = fma(M.t, e3, M.g);
+    const double i3 = FLAT ? 0.0 : fma(-(e3 * M.r), M.r, M.r);
+    const double bb3 = b3 * b3;
+    const double kb3 = fma(g3, FLAT ? 1.0 + bb3 : fma(a3, a3, bb3), FLAT ? 0.0 : fma(bb3 + bb3, i3, a3));
+    const double b4 = fma(d, kb3, b), a4 = fma(d, b3, a);
+    // stage 4 at a4 = a + d b + d (d/2) kb2 ~ N
+    const double e4 = a4 - N.P;
+    const double g4 = fma(N.t, e4, N.g);
+    const double i4 = FLAT ? 0.0 : fma(-(e4 * N.r), N.r, N.r);
+    const double bb4 = b4 * b4;
+    const double kb4 = fma(g4, FLAT ? 1.0 + bb4 : fma(a4, a4, bb4), FLAT ? 0.0 : fma(bb4 + bb4, i4, a4));
+    *a_out = fma((b + 2.0 * b2) + (2.0 * b3 + b4), d6, a);
+    *b_out = fma((kb1 + 2.0 * kb2) + (2.0 * kb3 + kb4), d6, b);
+    // served bases (a NaN g is an unserved cell -- or a NaN state, which the caller accepts) and short corrections
+    const double sum = (E.g + M.g) + N.g;
+    const double emax = fmax(fmax(fabs(e1), fabs(e2)), fmax(fabs(e3), fabs(e4)));
+    return sum == sum && emax < 0.25;
 }
 
 // A cell that holds the start of a temperature function is not served by the table (g has a kink

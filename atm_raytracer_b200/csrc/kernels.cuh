@@ -37,6 +37,7 @@ struct DevScene {
     int earth_model, straight, flat;
     int width, height, x0, x1;
     int n_t;     // terrain samples per column (N_t)
+    int path_k_far;  // first path element with dist > max_distance (n_t if none): the row-independent half of utils.rs:167
     int n_pad;   // row stride of the [column][k] and [row][k] caches
     int n1;      // level-1 chunks  = ceil(n_t / 32)
     int n1_pad;  // row stride of the level-1 pyramids
@@ -56,7 +57,8 @@ struct DevBuffers {
     double *t_lat, *t_lon, *t_elev;
     unsigned long long* t_close;
     // Stage B cache, step-major [n_t][h_pad]
-    double *p_dist, *p_elev, *p_len;
+    const double *path_x, *path_dxr;  // [n_t] each: PathElem::dist (row-independent) and calc_dist's dx / R per step
+    double *p_elev, *p_len;
     int* p_n;  // [h] elements per row (capped at n_t)
     // pyramids
     double *tmin1, *tmax1, *tmin2, *tmax2, *tmin3, *tmax3;  // [wl][n1_pad], [wl][n2], [wl]
@@ -361,40 +363,44 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
     const double radius = S.radius;
     const double d = FLAT ? S.step : S.step / radius;
     const double hd = 0.5 * d, d6 = d / 6.0;
-    const double inv_radius = FLAT ? 0.0 : 1.0 / radius;
+    const double shift = FLAT ? ATM_BASE : radius + ATM_BASE;
+    const int k_far = S.path_k_far;
     const size_t row0 = path_index(S.n_t, 0, y);
-    double* const o_dist = B.p_dist + row0;
-    double* const o_elev = B.p_elev + row0;
-    double* const o_len = B.p_len + row0;
+    double* o_elev = B.p_elev + row0;
+    double* o_len = B.p_len + row0;
+    const double* __restrict__ dxr = B.path_dxr;
 
-    // Outputs of step i-1 (`cur`, reached from `prev`): calc_dist (utils.rs:42-53, dx / R as dx * (1/R)), the
-    // three cache entries, and the termination test of utils.rs:167-170 on the state before it. Branch-free
-    // so that it can be scheduled in the shadow of the integration chain; for i == 1 it (re)writes the
-    // initial element (0, alt, 0).
+    // Outputs of step i-1 (`cur_h`, reached from `prev_h`): calc_dist (utils.rs:42-53; its dx / R is the
+    // row-independent path_dxr[i-1]), the two cache entries (PathElem::dist is the row-independent
+    // path_x[i-1]), and the termination test of utils.rs:167-170 on the state before it (x > max_distance
+    // is i - 2 >= k_far). Branch-free so that it is scheduled into the stalls of the integration chain; for
+    // i == 1 it (re)writes the initial element (alt, 0).
 #define ATMRT_PATH_OUTPUTS()                                                                                     \
     {                                                                                                            \
-        double dx = cur.x - prev.x;                                                                              \
-        const double dh = cur.h - prev.h;                                                                        \
-        if (!FLAT) dx = dx * inv_radius * ((cur.h + prev.h) * 0.5 + radius);                                     \
+        double dx = dx_next;                                                                                     \
+        dx_next = dxr[min(i, S.n_t - 1)]; /* for the next iteration: the load leaves the critical path */       \
+        const double dh = cur_h - prev_h;                                                                        \
+        if (!FLAT) dx = dx * ((cur_h + prev_h) * 0.5 + radius);                                                  \
         const double seg = sqrt_nr(dx * dx + dh * dh);                                                           \
         path_length = i >= 2 ? path_length + seg : 0.0;                                                          \
         const bool emit = writer && !done;                                                                       \
-        const size_t o = (size_t)(i - 1) * PATH_ROWS;                                                            \
-        stg_if(o_dist + o, cur.x, emit);                                                                         \
-        stg_if(o_elev + o, cur.h, emit);                                                                         \
-        stg_if(o_len + o, path_length, emit);                                                                    \
+        stg_if(o_elev, cur_h, emit);                                                                             \
+        stg_if(o_len, path_length, emit);                                                                        \
+        o_elev += PATH_ROWS, o_len += PATH_ROWS;                                                                 \
         n = emit ? i : n;                                                                                        \
-        done = done || (i >= 2 && (prev.x > S.max_distance || prev.h < -1000.0));                                \
+        done = done || (i >= 2 && (i - 2 >= k_far || prev_h < -1000.0));                                         \
     }
 
-    // stepper state: spherical (r, dr/dphi, phi) or flat (h, dh/dx, x). The loop is software-pipelined:
-    // iteration i integrates step i (the latency chain) while the outputs of step i-1 are produced in its
-    // shadow.
+    // stepper state: spherical (r, dr/dphi) or flat (h, dh/dx). The loop is software-pipelined: iteration i
+    // integrates step i (the latency chain) while the outputs of step i-1 are produced in its shadow.
     double a = FLAT ? alt : radius + alt;
     double b = FLAT ? tan(to_radians(get_ray_elev(S, y))) : a * tan(to_radians(get_ray_elev(S, y)));
-    double t = 0.0;
-    RayState prev{0.0, alt};  // state i-2
-    RayState cur{0.0, alt};   // state i-1
+    // bases of the lookups (device_paths.cuh): E serves stage 1, M stages 2-3, N stage 4 and the next step's stage 1
+    PathBase bE = path_base<FLAT>(gs.tab, shift, a), bM = path_base<FLAT>(gs.tab, shift, fma(hd, b, a)), bN = path_base<FLAT>(gs.tab, shift, fma(d, b, a));
+    const double d15 = 1.5 * d, d2 = 2.0 * d;
+    double dx_next = dxr[0];
+    double prev_h = alt;  // state i-2
+    double cur_h = alt;   // state i-1
     double path_length = 0.0;
     int n = 1;
     bool done = false;  // this row's cache is complete
@@ -402,35 +408,41 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
 #pragma unroll 1
     for (; i < S.n_t; ++i) {
         // A NaN state (the ray climbed above the altitude where the last temperature function reaches
-        // 0 K, e.g. 178 km for US-76) stays NaN: x = t R, h = NaN, path_length = NaN, exactly what the
-        // arithmetic produces (NaN in, NaN out). When every row of the warp is complete or NaN the
-        // integration stops (tested on the incoming state, acted upon at the end of the iteration).
+        // 0 K, e.g. 178 km for US-76) stays NaN: h = NaN, path_length = NaN, exactly what the arithmetic
+        // produces (NaN in, NaN out). When every row of the warp is complete or NaN the integration stops
+        // (tested on the incoming state, acted upon at the end of the iteration).
         const bool idle = __all_sync(FULL, done || a != a);
         double a_new, b_new;
         // one basic block: the outputs of step i-1 are scheduled into the stalls of the integration chain
-        const bool ok = rk4_step<FLAT, LIBM ? 2 : 0>(S.atm, gs, radius, d, hd, d6, a, b, &a_new, &b_new);
+        bool ok;
+        if (LIBM) {
+            ok = rk4_step<FLAT, 2>(S.atm, gs, radius, d, hd, d6, a, b, &a_new, &b_new);
+        } else {
+            ok = rk4_step_shared<FLAT>(d, hd, d6, a, b, bE, bM, bN, &a_new, &b_new) || done || a != a || b != b;
+            // the bases of step i+1, extrapolated from the state at the start of step i: independent of the chain above
+            bE = bN;
+            bM = path_base<FLAT>(gs.tab, shift, fma(d15, b, a));
+            bN = path_base<FLAT>(gs.tab, shift, fma(d2, b, a));
+        }
         ATMRT_PATH_OUTPUTS()
         if (!ok) rk4_step<FLAT, 1>(S.atm, gs, radius, d, hd, d6, a, b, &a_new, &b_new);  // rare: an altitude the table does not serve
         // a complete row stops moving: its state would otherwise leave the table (below -2 km) and drag the
         // warp through the libm path on every step
         a = done ? a : a_new, b = done ? b : b_new;
-        t += d;
-        prev = cur;
-        cur = FLAT ? RayState{t, a} : RayState{t * radius, a - radius};
+        prev_h = cur_h;
+        cur_h = FLAT ? a : a - radius;
         if (idle || __all_sync(FULL, done)) {
             ++i;
             break;
         }
     }
-    // Here cur = state i-1 and the outputs of steps < i-1 are written. Rows that are NaN keep advancing
-    // the independent variable only; then the last state's outputs.
+    // Here cur_h = state i-1 and the outputs of steps < i-1 are written; then the last state's outputs
+    // (rows that are NaN stay NaN).
 #pragma unroll 1
     for (; i <= S.n_t; ++i) {
         ATMRT_PATH_OUTPUTS()
         if (__all_sync(FULL, done)) break;
-        t += d;
-        prev = cur;
-        cur = FLAT ? RayState{t, a} : RayState{t * radius, a - radius};
+        prev_h = cur_h;
     }
 #undef ATMRT_PATH_OUTPUTS
     if (writer) {
@@ -449,7 +461,6 @@ __global__ void __launch_bounds__(128) k_ray_paths_straight(const __grid_constan
     Stepper st;
     stepper_init(st, flat, S.radius, alt, to_radians(get_ray_elev(S, y)));
     const size_t row0 = path_index(S.n_t, 0, y);
-    B.p_dist[row0] = 0.0;
     B.p_elev[row0] = alt;
     B.p_len[row0] = 0.0;
     RayState prev{0.0, alt};
@@ -459,7 +470,6 @@ __global__ void __launch_bounds__(128) k_ray_paths_straight(const __grid_constan
         const RayState nw = stepper_next(st, S.atm, flat, 1, S.radius, S.step);
         path_length += calc_dist(flat, S.radius, prev, nw);
         const size_t o = row0 + (size_t)i * PATH_ROWS;
-        B.p_dist[o] = nw.x;
         B.p_elev[o] = nw.h;
         B.p_len[o] = path_length;
         n = i + 1;
@@ -667,7 +677,7 @@ __device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers
     const double lat0 = B.t_lat[ti - 1], lon0 = B.t_lon[ti - 1], elev0 = B.t_elev[ti - 1];
     const double lat1 = B.t_lat[ti], lon1 = B.t_lon[ti], elev1 = B.t_elev[ti];
     const double ray0 = B.p_elev[p0], ray1 = B.p_elev[p1];
-    const double dist0 = k - 1 == 0 ? 0.0 : B.p_dist[p0], dist1 = B.p_dist[p1];
+    const double dist0 = B.path_x[k - 1], dist1 = B.path_x[k];  // path_x[0] = 0
     const double len0 = k - 1 == 0 ? 0.0 : B.p_len[p0], len1 = B.p_len[p1];
     const double diff1 = ray0 - elev0, diff2 = ray1 - elev1;
     const bool terrain_hit = diff1 * diff2 < 0.0;
