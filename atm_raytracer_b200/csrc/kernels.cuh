@@ -965,11 +965,11 @@ constexpr int SWEEP_ROWS = 4;       // rows resolved per window from one 32-byte
 // sector per step. The rows of the group are resolved bottom-up from those registers: row y's first event
 // in the window decides it, and the row above continues from the same step. The window advances only when
 // the lowest unresolved row has no event in it.
-__global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(const __grid_constant__ DevScene S, DevBuffers B) {
+__global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(const __grid_constant__ DevScene S, DevBuffers B, int col0, int col1) {
     if (B.sweep_flags[0] != 0) return;
     const int lane = threadIdx.x & 31;
-    const int xl = blockIdx.x * (SWEEP_THREADS / 32) + (threadIdx.x >> 5);
-    if (xl >= S.x1 - S.x0) return;
+    const int xl = col0 + blockIdx.x * (SWEEP_THREADS / 32) + (threadIdx.x >> 5);  // the image is swept in column chunks
+    if (xl >= col1) return;
     const double* __restrict__ te = B.t_elev + (size_t)xl * S.n_pad;
     const double* __restrict__ pe = B.p_elev;
     int* __restrict__ hit = B.sweep_hit + (size_t)xl * S.h_pad;
@@ -1058,16 +1058,16 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(const __grid_constant__
 // row-major [y][x] image and metadata are stored as contiguous row segments.
 constexpr int SHADE_COLS = 16;
 
-__global__ void __launch_bounds__(32 * SHADE_COLS, 2) k_sweep_shade(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O) {
+__global__ void __launch_bounds__(32 * SHADE_COLS, 2) k_sweep_shade(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, int col0) {
     if (B.sweep_flags[0] != 0) return;
     __shared__ double s_meta[32][SHADE_COLS * 4];
-    __shared__ unsigned char s_rgb[32][SHADE_COLS * 3];
+    __shared__ __align__(16) unsigned char s_rgb[32][SHADE_COLS * 3];
     __shared__ int s_steps[32][SHADE_COLS];
     __shared__ unsigned char s_skip[SHADE_COLS];
     __shared__ double s_nrm[SHADE_COLS][64][3];
     const int wl = S.x1 - S.x0;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int c0 = blockIdx.y * SHADE_COLS, y0 = blockIdx.x * 32;
+    const int c0 = col0 + blockIdx.y * SHADE_COLS, y0 = blockIdx.x * 32;  // col0: a multiple of SHADE_COLS
     const int xl = c0 + w, y = y0 + lane;
     const bool col_ok = xl < wl && B.sweep_col[xl] == 0;  // flagged columns belong to the brute-force march
     const bool active = col_ok && y < S.height;
@@ -1131,23 +1131,34 @@ __global__ void __launch_bounds__(32 * SHADE_COLS, 2) k_sweep_shade(const __grid
     count_pixel(B, active, st, consumed);
     __syncthreads();
     const int rows = min(32, S.height - y0);
-    if (O.meta) {
-        double* out = reinterpret_cast<double*>(O.meta);
-        for (int e = threadIdx.x; e < rows * SHADE_COLS * 4; e += 32 * SHADE_COLS) {
-            const int r = e / (SHADE_COLS * 4), q = e % (SHADE_COLS * 4), c = q >> 2;
-            if (c0 + c < wl && !s_skip[c]) out[((size_t)(y0 + r) * wl + c0) * 4 + q] = s_meta[r][q];
+    // Write-out with the lanes along x: thread t handles pixel (row t / 16, column t % 16) of the tile -- its
+    // 32 bytes of metadata as two 16-byte stores, so a warp writes two 512-byte row segments -- and, for the
+    // colour, word t of the tile's 32 x 12 four-byte words when the row segments are word-aligned.
+    {
+        const int r = threadIdx.x / SHADE_COLS, c = threadIdx.x % SHADE_COLS;
+        const bool live = r < rows && c0 + c < wl && !s_skip[c];
+        if (O.meta && live) {
+            double2* out = reinterpret_cast<double2*>(O.meta + (size_t)(y0 + r) * wl + c0 + c);
+            out[0] = make_double2(s_meta[r][c * 4 + 0], s_meta[r][c * 4 + 1]);
+            out[1] = make_double2(s_meta[r][c * 4 + 2], s_meta[r][c * 4 + 3]);
         }
+        if (O.steps && live) O.steps[(size_t)(y0 + r) * wl + c0 + c] = s_steps[r][c];
     }
     if (O.rgb) {
-        for (int e = threadIdx.x; e < rows * SHADE_COLS * 3; e += 32 * SHADE_COLS) {
-            const int r = e / (SHADE_COLS * 3), q = e % (SHADE_COLS * 3), c = q / 3;
-            if (c0 + c < wl && !s_skip[c]) O.rgb[((size_t)(y0 + r) * wl + c0) * 3 + q] = s_rgb[r][q];
-        }
-    }
-    if (O.steps) {
-        for (int e = threadIdx.x; e < rows * SHADE_COLS; e += 32 * SHADE_COLS) {
-            const int r = e / SHADE_COLS, c = e % SHADE_COLS;
-            if (c0 + c < wl && !s_skip[c]) O.steps[(size_t)(y0 + r) * wl + c0 + c] = s_steps[r][c];
+        bool whole = c0 + SHADE_COLS <= wl && (wl & 3) == 0;  // every row segment of the tile is 48 aligned bytes
+        for (int c = 0; c < SHADE_COLS; ++c) whole = whole && !s_skip[c];
+        if (whole) {
+            constexpr int WORDS = SHADE_COLS * 3 / 4;
+            if ((int)threadIdx.x < rows * WORDS) {
+                const int r = threadIdx.x / WORDS, q = threadIdx.x % WORDS;
+                const unsigned v = *reinterpret_cast<const unsigned*>(&s_rgb[r][q * 4]);
+                *reinterpret_cast<unsigned*>(O.rgb + ((size_t)(y0 + r) * wl + c0) * 3 + q * 4) = v;
+            }
+        } else {
+            for (int e = threadIdx.x; e < rows * SHADE_COLS * 3; e += 32 * SHADE_COLS) {
+                const int r = e / (SHADE_COLS * 3), q = e % (SHADE_COLS * 3), c = q / 3;
+                if (c0 + c < wl && !s_skip[c]) O.rgb[((size_t)(y0 + r) * wl + c0) * 3 + q] = s_rgb[r][q];
+            }
         }
     }
 }

@@ -121,6 +121,32 @@ def test_path_cache_matches_oracle(ctx, oracle_lib, name):
         np.testing.assert_allclose(got["path_length"], want["path_length"][:n], rtol=1e-12, atol=1e-9)
 
 
+@pytest.mark.parametrize("name", ["c2", "c3_flat", "c5"])
+def test_path_modes_agree(ctx, oracle_lib, name):
+    """The ray-path stage with g(h) from the table (default: two lookups per step, predicted one step ahead,
+    first-order corrections at the stage altitudes) against every g(h) through libm -- the oracle's
+    arithmetic op for op: within the noise floor of the reference's own evaluation."""
+    p, terrain, _, _ = scene(name, 0.05 if name != "c5" else 0.0125)
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects([])
+    rows = sorted(set([0, 1, p.height // 4, p.height // 2 - 1, p.height // 2, p.height // 2 + 1, 3 * p.height // 4, p.height - 1]))
+    got = {}
+    try:
+        for mode in (0, 1):
+            ctx.set_path_mode(mode)
+            ctx.render(meta=False, steps=False)
+            got[mode] = {y: ctx.path(y) for y in rows}
+    finally:
+        ctx.set_path_mode(0)
+    for y in rows:
+        a, c = got[0][y], got[1][y]
+        assert len(a["elev"]) == len(c["elev"])
+        np.testing.assert_array_equal(a["dist"], c["dist"])
+        np.testing.assert_allclose(a["elev"], c["elev"], rtol=1e-9, atol=PATH_ATOL)
+        np.testing.assert_allclose(a["path_length"], c["path_length"], rtol=1e-11, atol=1e-9)
+
+
 def _custom_atmosphere(a):
     """Humid air (the water-vapour terms of Ciddor's equation), a warm surface layer, a thin inversion
     inside one table cell, an isothermal function and a lapse layer."""
