@@ -208,7 +208,7 @@ def run_reference(args):
         "note": "CPU restatement of the reference (C++/OpenMP oracle); the Rust reference cannot be built here. "
                 "ms_per_step is the extrapolated full-image time; wall time of the sampled steps was %.1f s" % wall,
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -382,7 +382,7 @@ def run_b200(args):
         "fp64_peak_measured": fp,
         "pixels_hit": st["pixels_hit"], "step_overflows": st["step_overflows"],
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -439,7 +439,18 @@ def hbm_bytes_per_unit(stage, params):
     return 48.0 + 40.0  # six f64 outputs + five bilinear taps of 4 i16 posts
 
 
+def emit(obj):
+    """The one JSON line, on the process's ORIGINAL stdout. File descriptor 1 itself is pointed at stderr for
+    the whole run (see below), so that nothing a library prints from native code (NCCL's version banner at
+    communicator creation, whatever NCCL_DEBUG the box sets) can land on stdout next to it."""
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)

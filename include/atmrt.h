@@ -39,11 +39,15 @@ typedef enum atmrt_status {
     ATMRT_ERR_IO = -5           /* host file IO (host helpers only)         */
 } atmrt_status;
 
-/* EarthModel (utils/earth_model/mod.rs:19-28). Only the models named by the north star are
- * implemented on the device; the rest return ATMRT_ERR_INVALID. */
+/* EarthModel (utils/earth_model/mod.rs:19-28). The parameterless variants are lowered by the host:
+ * SimpleSphere = Spherical{6371000}, Wgs84 = Ellipsoid{6378137, 6356752.314245},
+ * SimpleObserverAe = ObserverAe{6371000} (mod.rs:14-16, 66-74, 127-143). */
 typedef enum atmrt_earth_model {
-    ATMRT_EARTH_SPHERICAL = 0,     /* Spherical{radius}; SimpleSphere = radius 6371000 */
-    ATMRT_EARTH_FLAT_DISTORTED = 1 /* FlatDistorted (--flat)                           */
+    ATMRT_EARTH_SPHERICAL = 0,              /* Spherical{radius}                                        */
+    ATMRT_EARTH_FLAT_DISTORTED = 1,         /* FlatDistorted (--flat)                                   */
+    ATMRT_EARTH_ELLIPSOID = 2,              /* Ellipsoid{a, b}: radius = a, ellipsoid_b = b             */
+    ATMRT_EARTH_AZIMUTHAL_EQUIDISTANT = 3,  /* AzimuthalEquidistant                                     */
+    ATMRT_EARTH_OBSERVER_AE = 4             /* ObserverAe{proj_radius}: radius = proj_radius            */
 } atmrt_earth_model;
 
 /* Altitude (generator/params.rs:17-30) */
@@ -84,7 +88,8 @@ typedef struct atmrt_params {
     /* model / env (params.rs:512-528; earth_model/mod.rs:95-112) */
     int32_t earth_model; /* atmrt_earth_model */
     int32_t straight_rays;
-    double radius; /* Spherical only */
+    double radius;      /* Spherical: radius; Ellipsoid: a; ObserverAe: proj_radius */
+    double ellipsoid_b; /* Ellipsoid: b */
     double wavelength; /* metres; default 530e-9 */
     double simulation_step;
     atmrt_atmosphere_def atmosphere;

@@ -95,9 +95,15 @@ struct Coords {
 };
 
 struct EarthModel {
-    int kind;  // atmrt_earth_model
-    double radius;
+    int kind;       // atmrt_earth_model
+    double radius;  // Spherical: radius; Ellipsoid: a; ObserverAe: proj_radius
+    double b = 0.0; // Ellipsoid: b
 };
+
+// the family whose world is the azimuthal-equidistant plane (mod.rs:37-51, 80-91, 106-110)
+inline bool flat_family(const EarthModel& m) {
+    return m.kind == ATMRT_EARTH_FLAT_DISTORTED || m.kind == ATMRT_EARTH_AZIMUTHAL_EQUIDISTANT || m.kind == ATMRT_EARTH_OBSERVER_AE;
+}
 
 struct Dirs {
     V3 north, east, up;
@@ -117,7 +123,7 @@ Dirs spherical_directions(double lat, double lon) {
 
 // EarthModel::world_directions, mod.rs:31-57
 Dirs world_directions(const EarthModel& m, double lat, double lon) {
-    if (m.kind == ATMRT_EARTH_FLAT_DISTORTED) {
+    if (flat_family(m)) {
         double lon_rad = to_radians(lon);
         double sinlon = std::sin(lon_rad), coslon = std::cos(lon_rad);
         Dirs d;
@@ -139,36 +145,79 @@ V3 spherical_to_cartesian(double r, double lat, double lon) {
 
 // EarthModel::as_cartesian, mod.rs:59-93
 V3 as_cartesian(const EarthModel& m, const Coords& c) {
-    if (m.kind == ATMRT_EARTH_FLAT_DISTORTED) {
+    if (flat_family(m)) {
         double z = c.elev;
         double r = (90.0 - c.lat) * DEGREE_DISTANCE;
         double x = r * std::cos(to_radians(c.lon));
         double y = r * std::sin(to_radians(c.lon));
         return {x, y, z};
     }
+    if (m.kind == ATMRT_EARTH_ELLIPSOID) {  // mod.rs:70-79
+        double a = m.radius, b = m.b;
+        double e2 = 1.0 - (b * b) / (a * a);
+        double lat = to_radians(c.lat), lon = to_radians(c.lon);
+        double sl = std::sin(lat);
+        double n = a / std::sqrt(1.0 - e2 * (sl * sl));
+        double x = (n + c.elev) * std::cos(lat) * std::cos(lon);
+        double y = (n + c.elev) * std::cos(lat) * std::sin(lon);
+        double z = (n * (1.0 - e2) + c.elev) * std::sin(lat);
+        return {x, y, z};
+    }
     return spherical_to_cartesian(m.radius + c.elev, c.lat, c.lon);
 }
 
-// DirectionalCalc: SphericalCalc (directional_calc.rs:50-86) / FlDsCalc (:30-48)
+// EarthModel::to_shape, mod.rs:95-112: the ray physics sees a plane or a sphere
+inline bool shape_flat(const EarthModel& m) { return flat_family(m); }
+inline double shape_radius(const EarthModel& m) { return m.kind == ATMRT_EARTH_ELLIPSOID ? (2.0 * m.radius + m.b) / 3.0 : m.radius; }
+
+// DirectionalCalc (directional_calc.rs): SphericalCalc (:50-86), FlDsCalc (:30-48), AzEqCalc (:9-28),
+// EllipsoidCalc (:88-185, Vincenty's direct formula after NGS "inverse.pdf")
+enum { CALC_SPHERICAL = 0, CALC_FLDS = 1, CALC_AZEQ = 2, CALC_ELLIPSOID = 3 };
 struct DirCalc {
     int kind;
     // spherical
     double radius;
-    V3 pos, dir;
+    V3 pos, dir;  // AzEq: pos = start in the plane, dir = dir_v
     // flat distorted
     double start_lat, start_lon, dir_deg;
+    // ellipsoid
+    double eb, f, red_lat, lon, az1, alfa, sig1, cap_a, cap_b, cap_c;
 };
 
 DirCalc coords_at_dist_calc(const EarthModel& m, double lat, double lon, double dir_deg) {
     DirCalc c{};
-    c.kind = m.kind;
     if (m.kind == ATMRT_EARTH_FLAT_DISTORTED) {
+        c.kind = CALC_FLDS;
         c.start_lat = lat;
         c.start_lon = lon;
         c.dir_deg = dir_deg;
         return c;
     }
-    // SphericalCalc::new, directional_calc.rs:56-69
+    if (m.kind == ATMRT_EARTH_AZIMUTHAL_EQUIDISTANT) {  // mod.rs:116-125
+        c.kind = CALC_AZEQ;
+        c.pos = as_cartesian(m, Coords{lat, lon, 0.0});
+        Dirs d = world_directions(m, lat, lon);
+        c.dir = d.north * std::cos(to_radians(dir_deg)) + d.east * std::sin(to_radians(dir_deg));
+        return c;
+    }
+    if (m.kind == ATMRT_EARTH_ELLIPSOID) {  // EllipsoidCalc::new, directional_calc.rs:104-135
+        c.kind = CALC_ELLIPSOID;
+        double a = m.radius, b = m.b;
+        double la = to_radians(lat), lo = to_radians(lon), az1 = to_radians(dir_deg);
+        double f = (a - b) / a;
+        double red_lat = std::atan((1.0 - f) * std::tan(la));
+        double sig1 = std::atan(std::tan(red_lat) / std::cos(az1));
+        double alfa = std::asin(std::cos(red_lat) * std::sin(az1));
+        double ca = std::cos(alfa);
+        double u2 = ca * ca * (a * a - b * b) / (b * b);
+        c.cap_a = 1.0 + u2 / 256.0 * (64.0 + u2 * (-12.0 + 5.0 * u2));
+        c.cap_b = u2 / 512.0 * (128.0 + u2 * (-64.0 + 37.0 * u2));
+        c.cap_c = f / 16.0 * (ca * ca) * (4.0 + f * (4.0 - 3.0 * (ca * ca)));
+        c.eb = b, c.f = f, c.red_lat = red_lat, c.lon = lo, c.az1 = az1, c.alfa = alfa, c.sig1 = sig1;
+        return c;
+    }
+    // SphericalCalc::new, directional_calc.rs:56-69 (Spherical{radius}, ObserverAe{proj_radius}: mod.rs:127-131)
+    c.kind = CALC_SPHERICAL;
     Dirs d = spherical_directions(lat, lon);
     double dir_rad = to_radians(dir_deg);
     double sindir = std::sin(dir_rad), cosdir = std::cos(dir_rad);
@@ -179,12 +228,46 @@ DirCalc coords_at_dist_calc(const EarthModel& m, double lat, double lon, double 
 }
 
 void coords_at_dist(const DirCalc& c, double dist, double* lat, double* lon) {
-    if (c.kind == ATMRT_EARTH_FLAT_DISTORTED) {
+    if (c.kind == CALC_FLDS) {
         // FlDsCalc::coords_at_dist, directional_calc.rs:41-47
         double d_lat = std::cos(to_radians(c.dir_deg)) * dist / DEGREE_DISTANCE;
         double d_lon = std::sin(to_radians(c.dir_deg)) * dist / DEGREE_DISTANCE / std::cos(to_radians(c.start_lat));
         *lat = c.start_lat + d_lat;
         *lon = c.start_lon + d_lon;
+        return;
+    }
+    if (c.kind == CALC_AZEQ) {
+        // AzEqCalc::coords_at_dist, directional_calc.rs:20-27
+        V3 pos2 = c.pos + c.dir * dist;
+        *lon = to_degrees(std::atan2(pos2.y, pos2.x));
+        double r = std::sqrt(pos2.x * pos2.x + pos2.y * pos2.y);
+        *lat = 90.0 - r / DEGREE_DISTANCE;
+        return;
+    }
+    if (c.kind == CALC_ELLIPSOID) {
+        // EllipsoidCalc::coords_at_dist, directional_calc.rs:139-184
+        const double EPSILON = 1e-10;
+        double sig = dist / c.eb / c.cap_a;
+        for (;;) {
+            double sigm = 2.0 * c.sig1 + sig;
+            double csm = std::cos(sigm);
+            double dsig = c.cap_b * std::sin(sig) * (csm + c.cap_b / 4.0 * std::cos(sig) * (-1.0 + 2.0 * (csm * csm)));
+            double new_sig = dist / c.eb / c.cap_a + dsig;
+            double ds = std::fabs(new_sig - sig);
+            sig = new_sig;
+            if (ds < EPSILON) break;
+            if (!(ds == ds)) break;  // NaN: the reference would spin; never reached with finite inputs
+        }
+        double sigm = 2.0 * c.sig1 + sig;
+        double sr = std::sin(c.red_lat), cr = std::cos(c.red_lat), ss = std::sin(sig), cs = std::cos(sig);
+        double caz = std::cos(c.az1), saz = std::sin(c.az1), sal = std::sin(c.alfa);
+        double t = sr * ss - cr * cs * caz;
+        double lat2 = std::atan((sr * cs + cr * ss * caz) / ((1.0 - c.f) * std::sqrt(sal * sal + t * t)));
+        double lambda = std::atan(ss * saz / (cr * cs - sr * ss * caz));
+        double csm = std::cos(sigm);
+        double dl = lambda - (1.0 - c.cap_c) * c.f * sal * (sig + c.cap_c * ss * (csm + c.cap_c * cs * (-1.0 + 2.0 * (csm * csm))));
+        *lat = to_degrees(lat2);
+        *lon = to_degrees(c.lon + dl);
         return;
     }
     // SphericalCalc::coords_at_dist, directional_calc.rs:71-86
@@ -993,9 +1076,9 @@ Rgb8 draw_pixel(const atmrt_params& p, const std::vector<TracePoint>& tps) {
 bool build_scene(const atmrt_params* p, const atmrt_tile_desc* tiles, int ntiles, const int16_t* const* posts,
                  const atmrt_object* objects, int nobjects, const uint8_t* const* textures, Scene* s) {
     s->p = *p;
-    s->model = {p->earth_model, p->radius};
-    s->env.flat = p->earth_model == ATMRT_EARTH_FLAT_DISTORTED;  // EarthModel::to_shape, mod.rs:95-112
-    s->env.radius = p->radius;
+    s->model = {p->earth_model, p->radius, p->ellipsoid_b};
+    s->env.flat = shape_flat(s->model);  // EarthModel::to_shape, mod.rs:95-112
+    s->env.radius = shape_radius(s->model);
     s->env.wavelength = p->wavelength;
     if (!atmosphere_from_def(p->atmosphere, &s->env.atm)) return false;
     s->terrain = make_terrain(tiles, ntiles, posts);
@@ -1160,8 +1243,8 @@ int oracle_get_elev(const atmrt_tile_desc* tiles, int ntiles, const int16_t* con
 }
 
 int oracle_coords_at_dist(int earth_model, double radius, double lat0, double lon0, double dir, const double* dist,
-                          int n, double* lat, double* lon) {
-    EarthModel m{earth_model, radius};
+                          int n, double* lat, double* lon, double ellipsoid_b) {
+    EarthModel m{earth_model, radius, ellipsoid_b};
     DirCalc c = coords_at_dist_calc(m, lat0, lon0, dir);
     for (int i = 0; i < n; ++i) coords_at_dist(c, dist[i], &lat[i], &lon[i]);
     return 0;
@@ -1175,8 +1258,8 @@ int oracle_world_directions(int earth_model, double radius, double lat, double l
     return 0;
 }
 
-int oracle_as_cartesian(int earth_model, double radius, double lat, double lon, double elev, double* out3) {
-    V3 v = as_cartesian(EarthModel{earth_model, radius}, Coords{lat, lon, elev});
+int oracle_as_cartesian(int earth_model, double radius, double lat, double lon, double elev, double* out3, double ellipsoid_b) {
+    V3 v = as_cartesian(EarthModel{earth_model, radius, ellipsoid_b}, Coords{lat, lon, elev});
     out3[0] = v.x, out3[1] = v.y, out3[2] = v.z;
     return 0;
 }
