@@ -9,7 +9,8 @@ MAX_ATM_FUNCTIONS = 16
 MAX_OBJECTS = 64
 MAX_STEP_POINTS = 16
 
-EARTH_SPHERICAL, EARTH_FLAT_DISTORTED = 0, 1
+EARTH_SPHERICAL, EARTH_FLAT_DISTORTED, EARTH_ELLIPSOID, EARTH_AZIMUTHAL_EQUIDISTANT, EARTH_OBSERVER_AE = 0, 1, 2, 3, 4
+FLAT_FAMILY = (EARTH_FLAT_DISTORTED, EARTH_AZIMUTHAL_EQUIDISTANT, EARTH_OBSERVER_AE)  # the world is the azimuthal-equidistant plane
 ALT_ABSOLUTE, ALT_RELATIVE = 0, 1
 COLORING_SIMPLE, COLORING_SHADING = 0, 1
 PALETTE_LEGACY, PALETTE_IMPROVED = 0, 1
@@ -46,6 +47,7 @@ class Params(C.Structure):
         ("earth_model", C.c_int32),
         ("straight_rays", C.c_int32),
         ("radius", C.c_double),
+        ("ellipsoid_b", C.c_double),
         ("wavelength", C.c_double),
         ("simulation_step", C.c_double),
         ("atmosphere", AtmosphereDef),

@@ -160,22 +160,37 @@ def _altitude(node):
     return a
 
 
+WGS84_A, WGS84_B = 6378137.0, 6356752.314245  # earth_model/mod.rs:15-16
+
+
 def _earth_model(node):
+    """``EarthModel`` (earth_model/mod.rs:19-28) -> (atmrt_earth_model, radius, ellipsoid_b); the parameterless
+    variants are lowered as the reference lowers them (mod.rs:66-74, 127-143)."""
     kind, val = _tagged(node, "earth_shape")
     if kind == "Spherical":
-        return abi.EARTH_SPHERICAL, float(val["radius"])
+        return abi.EARTH_SPHERICAL, float(val["radius"]), 0.0
     if kind == "SimpleSphere":
-        return abi.EARTH_SPHERICAL, EARTH_R
+        return abi.EARTH_SPHERICAL, EARTH_R, 0.0
     if kind == "FlatDistorted":
-        return abi.EARTH_FLAT_DISTORTED, 0.0
-    raise ConfigError(f"earth_shape {kind} is outside the hot-path scope (SURVEY section 8 f3)")
+        return abi.EARTH_FLAT_DISTORTED, 0.0, 0.0
+    if kind == "Ellipsoid":
+        return abi.EARTH_ELLIPSOID, float(val["a"]), float(val["b"])
+    if kind == "Wgs84":
+        return abi.EARTH_ELLIPSOID, WGS84_A, WGS84_B
+    if kind == "AzimuthalEquidistant":
+        return abi.EARTH_AZIMUTHAL_EQUIDISTANT, 0.0, 0.0
+    if kind == "ObserverAe":
+        return abi.EARTH_OBSERVER_AE, float(val["proj_radius"]), 0.0
+    if kind == "SimpleObserverAe":
+        return abi.EARTH_OBSERVER_AE, EARTH_R, 0.0
+    raise ConfigError(f"unknown earth_shape {kind}")
 
 
 def world_directions(model, lat, lon):
     """``EarthModel::world_directions`` (earth_model/mod.rs:31-57,155-172)."""
     lon_r = math.radians(lon)
     sinlon, coslon = math.sin(lon_r), math.cos(lon_r)
-    if model == abi.EARTH_FLAT_DISTORTED:
+    if model in abi.FLAT_FAMILY:
         return (np.array([-coslon, -sinlon, 0.0]), np.array([-sinlon, coslon, 0.0]), np.array([0.0, 0.0, 1.0]))
     lat_r = math.radians(lat)
     sinlat, coslat = math.sin(lat_r), math.cos(lat_r)
@@ -276,7 +291,7 @@ def into_params(cfg, x0=None, x1=None):
     p.altitude = _altitude(pos["altitude"])
     p.direction, p.tilt = float(frame["direction"]), float(frame["tilt"])
     p.fov, p.max_distance = float(frame["fov"]), float(frame["max_distance"])
-    p.earth_model, p.radius = _earth_model(cfg["earth_shape"])
+    p.earth_model, p.radius, p.ellipsoid_b = _earth_model(cfg["earth_shape"])
     p.straight_rays = 1 if cfg["straight_rays"] else 0
     p.wavelength = float(cfg["wavelength"])
     p.simulation_step = float(cfg["simulation_step"])

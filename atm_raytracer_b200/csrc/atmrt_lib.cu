@@ -433,9 +433,10 @@ int validate_params(atmrt_ctx* ctx, const atmrt_params& p) {
     if (!(p.simulation_step > 0.0)) return fail(ctx, ATMRT_ERR_INVALID, "simulation_step must be positive");
     if (!(p.max_distance > 0.0)) return fail(ctx, ATMRT_ERR_INVALID, "max_distance must be positive");
     if (p.max_distance / p.simulation_step > 4.0e6) return fail(ctx, ATMRT_ERR_INVALID, "more than 4e6 samples per ray");
-    if (p.earth_model != ATMRT_EARTH_SPHERICAL && p.earth_model != ATMRT_EARTH_FLAT_DISTORTED)
-        return fail(ctx, ATMRT_ERR_INVALID, "earth model not supported on the device path (Spherical, FlatDistorted only)");
-    if (p.earth_model == ATMRT_EARTH_SPHERICAL && !(p.radius > 0.0)) return fail(ctx, ATMRT_ERR_INVALID, "radius must be positive");
+    if (p.earth_model < ATMRT_EARTH_SPHERICAL || p.earth_model > ATMRT_EARTH_OBSERVER_AE) return fail(ctx, ATMRT_ERR_INVALID, "unknown earth model");
+    if ((p.earth_model == ATMRT_EARTH_SPHERICAL || p.earth_model == ATMRT_EARTH_ELLIPSOID || p.earth_model == ATMRT_EARTH_OBSERVER_AE) && !(p.radius > 0.0))
+        return fail(ctx, ATMRT_ERR_INVALID, "radius (Spherical radius, Ellipsoid a, ObserverAe proj_radius) must be positive");
+    if (p.earth_model == ATMRT_EARTH_ELLIPSOID && !(p.ellipsoid_b > 0.0)) return fail(ctx, ATMRT_ERR_INVALID, "ellipsoid_b must be positive");
     if (p.coloring != ATMRT_COLORING_SIMPLE && p.coloring != ATMRT_COLORING_SHADING) return fail(ctx, ATMRT_ERR_INVALID, "unknown coloring");
     return 0;
 }
@@ -450,13 +451,28 @@ int prepare_render(atmrt_ctx* ctx) {
     S.lat0 = p.latitude, S.lon0 = p.longitude;
     S.direction = p.direction, S.tilt = p.tilt, S.fov = p.fov, S.max_distance = p.max_distance;
     S.step = p.simulation_step;
-    S.radius = p.radius;
     S.altitude = p.altitude;
     S.earth_model = p.earth_model;
-    S.flat = p.earth_model == ATMRT_EARTH_FLAT_DISTORTED;  // EarthModel::to_shape, earth_model/mod.rs:95-112
+    {
+        DevEarth& E = S.earth;
+        E.model = p.earth_model;
+        E.flat_dirs = p.earth_model == ATMRT_EARTH_FLAT_DISTORTED || p.earth_model == ATMRT_EARTH_AZIMUTHAL_EQUIDISTANT || p.earth_model == ATMRT_EARTH_OBSERVER_AE;
+        E.walker = p.earth_model == ATMRT_EARTH_FLAT_DISTORTED ? WALK_FLDS
+                   : p.earth_model == ATMRT_EARTH_AZIMUTHAL_EQUIDISTANT ? WALK_AZEQ
+                   : p.earth_model == ATMRT_EARTH_ELLIPSOID ? WALK_ELLIPSOID : WALK_SPHERICAL;
+        E.radius = p.radius;
+        E.b = p.ellipsoid_b;
+        if (p.earth_model == ATMRT_EARTH_ELLIPSOID) {
+            E.f = (p.radius - p.ellipsoid_b) / p.radius;
+            E.e2 = 1.0 - (p.ellipsoid_b * p.ellipsoid_b) / (p.radius * p.radius);
+        }
+        // EarthModel::to_shape, earth_model/mod.rs:95-112: the ray physics sees a plane or a sphere
+        S.flat = E.flat_dirs;
+        S.radius = p.earth_model == ATMRT_EARTH_ELLIPSOID ? (2.0 * p.radius + p.ellipsoid_b) / 3.0 : p.radius;
+    }
     S.straight = p.straight_rays != 0;
     S.width = p.width, S.height = p.height, S.x0 = p.x0, S.x1 = p.x1;
-    if (!S.flat) {
+    if (S.earth.walker == WALK_SPHERICAL) {
         S.sin_diff = std::sin(NORMAL_DIFF / p.radius);
         S.cos_diff = std::cos(NORMAL_DIFF / p.radius);
         const double delta = NORMAL_DIFF / p.radius;
@@ -493,14 +509,14 @@ int prepare_render(atmrt_ctx* ctx) {
         // step for every ray (phi += step / R, x = phi * R; flat and straight rays: x += step). The same
         // running sums here, element by element.
         const bool sph_rk4 = !S.flat && !S.straight;
-        const double d = sph_rk4 ? p.simulation_step / p.radius : p.simulation_step;
-        const double inv_radius = S.flat ? 0.0 : 1.0 / p.radius;
+        const double d = sph_rk4 ? p.simulation_step / S.radius : p.simulation_step;
+        const double inv_radius = S.flat ? 0.0 : 1.0 / S.radius;
         ctx->path_x.assign((size_t)2 * n_t, 0.0);
         double t = 0.0;
         ctx->path_k_far = n_t;
         for (int k = 1; k < n_t; ++k) {
             t += d;
-            const double x = sph_rk4 ? t * p.radius : t;
+            const double x = sph_rk4 ? t * S.radius : t;
             ctx->path_x[k] = x;
             const double dx = x - ctx->path_x[k - 1];
             ctx->path_x[(size_t)n_t + k] = S.flat ? dx : dx * inv_radius;  // calc_dist's dx / R (utils.rs:49)

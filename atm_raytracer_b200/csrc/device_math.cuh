@@ -146,11 +146,22 @@ __device__ __forceinline__ Dirs spherical_directions_sc(double sinlat, double co
     return d;
 }
 
+// The geometry of an EarthModel (earth_model/mod.rs:19-28) as the kernels need it.
+enum { WALK_SPHERICAL = 0, WALK_FLDS = 1, WALK_AZEQ = 2, WALK_ELLIPSOID = 3 };
+struct DevEarth {
+    int model;      // atmrt_earth_model
+    int flat_dirs;  // world_directions / as_cartesian of the azimuthal-equidistant plane (mod.rs:37-51, 80-91)
+    int walker;     // coords_at_dist_calc (mod.rs:114-145): which DirectionalCalc walks the azimuth
+    int _pad;
+    double radius;  // Spherical: radius; Ellipsoid: a; ObserverAe: proj_radius
+    double b, f, e2;  // Ellipsoid: b, (a - b) / a, 1 - b^2 / a^2
+};
+
 // EarthModel::world_directions, mod.rs:31-57
-__device__ __forceinline__ Dirs world_directions(int model, double lat, double lon) {
+__device__ __forceinline__ Dirs world_directions(const DevEarth& E, double lat, double lon) {
     double sinlon, coslon;
     sincos(to_radians(lon), &sinlon, &coslon);
-    if (model == ATMRT_EARTH_FLAT_DISTORTED) {
+    if (E.flat_dirs) {
         Dirs d;
         d.north = {-coslon, -sinlon, 0.0};
         d.east = {-sinlon, coslon, 0.0};
@@ -163,20 +174,80 @@ __device__ __forceinline__ Dirs world_directions(int model, double lat, double l
 }
 
 // EarthModel::as_cartesian (mod.rs:59-93) from already evaluated sin/cos of lat/lon.
-__device__ __forceinline__ V3 as_cartesian_sc(int model, double radius, double lat, double elev, double sinlat,
-                                               double coslat, double sinlon, double coslon) {
-    if (model == ATMRT_EARTH_FLAT_DISTORTED) {
+__device__ __forceinline__ V3 as_cartesian_sc(const DevEarth& E, double lat, double elev, double sinlat, double coslat, double sinlon,
+                                               double coslon) {
+    if (E.flat_dirs) {
         double r = (90.0 - lat) * DEGREE_DISTANCE;
         return {r * coslon, r * sinlon, elev};
     }
-    double r = radius + elev;  // spherical_to_cartesian, mod.rs:148-153
+    if (E.model == ATMRT_EARTH_ELLIPSOID) {  // mod.rs:70-79
+        const double n = E.radius / sqrt(1.0 - E.e2 * (sinlat * sinlat));
+        return {(n + elev) * coslat * coslon, (n + elev) * coslat * sinlon, (n * (1.0 - E.e2) + elev) * sinlat};
+    }
+    double r = E.radius + elev;  // spherical_to_cartesian, mod.rs:148-153
     return {r * coslat * coslon, r * coslat * sinlon, r * sinlat};
 }
-__device__ __forceinline__ V3 as_cartesian(int model, double radius, double lat, double lon, double elev) {
+__device__ __forceinline__ V3 as_cartesian(const DevEarth& E, double lat, double lon, double elev) {
     double sinlat = 0.0, coslat = 1.0, sinlon, coslon;
     sincos(to_radians(lon), &sinlon, &coslon);
-    if (model != ATMRT_EARTH_FLAT_DISTORTED) sincos(to_radians(lat), &sinlat, &coslat);
-    return as_cartesian_sc(model, radius, lat, elev, sinlat, coslat, sinlon, coslon);
+    if (!E.flat_dirs) sincos(to_radians(lat), &sinlat, &coslat);
+    return as_cartesian_sc(E, lat, elev, sinlat, coslat, sinlon, coslon);
+}
+
+// EllipsoidCalc (directional_calc.rs:88-185): Vincenty's direct formula, after NGS "inverse.pdf".
+struct EllipsoidCalc {
+    double red_lat, lon, cos_az1, sin_az1, sin_alfa, sig1, cap_a, cap_b, cap_c;
+};
+__device__ __forceinline__ EllipsoidCalc ellipsoid_calc(const DevEarth& E, double lat_deg, double lon_deg, double dir_deg) {  // ::new, :104-135
+    const double a = E.radius, b = E.b, f = E.f;
+    const double lat = to_radians(lat_deg), az1 = to_radians(dir_deg);
+    EllipsoidCalc c;
+    c.lon = to_radians(lon_deg);
+    c.red_lat = atan((1.0 - f) * tan(lat));
+    sincos(az1, &c.sin_az1, &c.cos_az1);
+    c.sig1 = atan(tan(c.red_lat) / c.cos_az1);
+    const double alfa = asin(cos(c.red_lat) * c.sin_az1);
+    double ca;
+    sincos(alfa, &c.sin_alfa, &ca);
+    const double u2 = ca * ca * (a * a - b * b) / (b * b);
+    c.cap_a = 1.0 + u2 / 256.0 * (64.0 + u2 * (-12.0 + 5.0 * u2));
+    c.cap_b = u2 / 512.0 * (128.0 + u2 * (-64.0 + 37.0 * u2));
+    c.cap_c = f / 16.0 * (ca * ca) * (4.0 + f * (4.0 - 3.0 * (ca * ca)));
+    return c;
+}
+__device__ __forceinline__ void ellipsoid_walk(const DevEarth& E, const EllipsoidCalc& c, double dist, double* lat, double* lon) {  // :139-184
+    const double s0 = dist / E.b / c.cap_a;
+    double sig = s0;
+    for (int it = 0; it < 64; ++it) {  // the reference loops until |d sigma| < 1e-10 (2-4 rounds); the cap only guards NaN input
+        const double sigm = 2.0 * c.sig1 + sig;
+        double ss, cs;
+        sincos(sig, &ss, &cs);
+        const double csm = cos(sigm);
+        const double dsig = c.cap_b * ss * (csm + c.cap_b / 4.0 * cs * (-1.0 + 2.0 * (csm * csm)));
+        const double new_sig = s0 + dsig;
+        const double ds = fabs(new_sig - sig);
+        sig = new_sig;
+        if (ds < 1e-10) break;
+    }
+    const double sigm = 2.0 * c.sig1 + sig;
+    double sr, cr, ss, cs;
+    sincos(c.red_lat, &sr, &cr);
+    sincos(sig, &ss, &cs);
+    const double t = sr * ss - cr * cs * c.cos_az1;
+    const double lat2 = atan((sr * cs + cr * ss * c.cos_az1) / ((1.0 - E.f) * sqrt(c.sin_alfa * c.sin_alfa + t * t)));
+    const double lambda = atan(ss * c.sin_az1 / (cr * cs - sr * ss * c.cos_az1));
+    const double csm = cos(sigm);
+    const double dl = lambda - (1.0 - c.cap_c) * E.f * c.sin_alfa * (sig + c.cap_c * ss * (csm + c.cap_c * cs * (-1.0 + 2.0 * (csm * csm))));
+    *lat = to_degrees(lat2);
+    *lon = to_degrees(c.lon + dl);
+}
+
+// AzEqCalc::coords_at_dist (directional_calc.rs:20-27): a straight line in the azimuthal-equidistant plane.
+__device__ __forceinline__ void azeq_walk(V3 pos, V3 dir_v, double dist, double* lat, double* lon) {
+    const V3 pos2 = pos + dir_v * dist;
+    *lon = to_degrees(atan2(pos2.y, pos2.x));
+    const double r = sqrt(pos2.x * pos2.x + pos2.y * pos2.y);
+    *lat = 90.0 - r / DEGREE_DISTANCE;
 }
 
 // SphericalCalc::coords_at_dist (directional_calc.rs:71-86) with sin/cos of dist/radius given.

@@ -292,6 +292,7 @@ struct Config {
     atmrt_atmosphere_def atmosphere{};
     int earth_model = ATMRT_EARTH_SPHERICAL;
     double radius = 6371000.0;
+    double ellipsoid_b = 0.0;
     double wavelength = 530e-9;
     bool straight_rays = false;
     double simulation_step = 50.0;
@@ -472,8 +473,18 @@ static void apply_yaml(const Node& doc, Config* c) {
             c->earth_model = ATMRT_EARTH_SPHERICAL, c->radius = 6371000.0;
         else if (tag == "FlatDistorted")
             c->earth_model = ATMRT_EARTH_FLAT_DISTORTED;
+        else if (tag == "Ellipsoid")
+            c->earth_model = ATMRT_EARTH_ELLIPSOID, c->radius = num(*body, "a", 6378137.0), c->ellipsoid_b = num(*body, "b", 6356752.314245);
+        else if (tag == "Wgs84")  // earth_model/mod.rs:15-16, 66-70
+            c->earth_model = ATMRT_EARTH_ELLIPSOID, c->radius = 6378137.0, c->ellipsoid_b = 6356752.314245;
+        else if (tag == "AzimuthalEquidistant")
+            c->earth_model = ATMRT_EARTH_AZIMUTHAL_EQUIDISTANT;
+        else if (tag == "ObserverAe")
+            c->earth_model = ATMRT_EARTH_OBSERVER_AE, c->radius = num(*body, "proj_radius", 6371000.0);
+        else if (tag == "SimpleObserverAe")  // mod.rs:139-143
+            c->earth_model = ATMRT_EARTH_OBSERVER_AE, c->radius = 6371000.0;
         else
-            throw std::runtime_error("earth_shape " + tag + " is outside the device path (Spherical, SimpleSphere, FlatDistorted)");
+            throw std::runtime_error("unknown earth_shape " + tag);
     }
     c->wavelength = num(doc, "wavelength", c->wavelength);
     if (const Node* s = doc.get("straight_rays")) c->straight_rays = s->as_bool("straight_rays");
@@ -562,7 +573,7 @@ static void light_direction(const Config& c, double out[3]) {
     double lon = rad(c.longitude), lat = rad(c.latitude);
     double sinlon = std::sin(lon), coslon = std::cos(lon);
     double north[3], east[3], up[3];
-    if (c.earth_model == ATMRT_EARTH_FLAT_DISTORTED) {
+    if (c.earth_model == ATMRT_EARTH_FLAT_DISTORTED || c.earth_model == ATMRT_EARTH_AZIMUTHAL_EQUIDISTANT || c.earth_model == ATMRT_EARTH_OBSERVER_AE) {
         north[0] = -coslon, north[1] = -sinlon, north[2] = 0.0;
         east[0] = -sinlon, east[1] = coslon, east[2] = 0.0;
         up[0] = 0.0, up[1] = 0.0, up[2] = 1.0;
@@ -587,7 +598,7 @@ static atmrt_params into_params(const Config& c) {
     atmrt_params p{};
     p.latitude = c.latitude, p.longitude = c.longitude, p.altitude = c.altitude;
     p.direction = c.direction, p.tilt = c.tilt, p.fov = c.fov, p.max_distance = c.max_distance;
-    p.earth_model = c.earth_model, p.straight_rays = c.straight_rays ? 1 : 0, p.radius = c.radius;
+    p.earth_model = c.earth_model, p.straight_rays = c.straight_rays ? 1 : 0, p.radius = c.radius, p.ellipsoid_b = c.ellipsoid_b;
     p.wavelength = c.wavelength, p.simulation_step = c.simulation_step, p.atmosphere = c.atmosphere;
     p.terrain_alpha = c.terrain_alpha;
     p.coloring = c.coloring, p.water_level = c.water_level;
@@ -595,7 +606,8 @@ static atmrt_params into_params(const Config& c) {
         p.palette = c.palette, p.ambient_light = c.ambient_light;
         light_direction(c, p.light_dir);
     }
-    if (c.earth_model != ATMRT_EARTH_SPHERICAL) p.radius = 0.0;
+    if (c.earth_model == ATMRT_EARTH_FLAT_DISTORTED || c.earth_model == ATMRT_EARTH_AZIMUTHAL_EQUIDISTANT) p.radius = 0.0;
+    if (c.earth_model != ATMRT_EARTH_ELLIPSOID) p.ellipsoid_b = 0.0;
     p.simple_max_distance = c.max_distance;
     p.fog_enabled = c.fog ? 1 : 0, p.fog_distance = c.fog_distance;
     p.width = c.width, p.height = c.height, p.x0 = 0, p.x1 = c.width;

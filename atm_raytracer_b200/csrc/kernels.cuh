@@ -30,8 +30,9 @@ constexpr unsigned FULL = 0xffffffffu;
 // Everything a kernel needs about the scene, passed by value as a __grid_constant__ argument.
 struct DevScene {
     double lat0, lon0, direction, tilt, fov, max_distance, step;
-    double radius;
-    double sin_diff, cos_diff;  // sin/cos(NORMAL_DIFF / radius), spherical find_normal
+    double radius;  // of the ray physics (EarthModel::to_shape, mod.rs:95-112); the geometry's own is earth.radius
+    DevEarth earth;
+    double sin_diff, cos_diff;  // sin/cos(NORMAL_DIFF / earth.radius), spherical find_normal
     double tan_diff, versin_diff, diff_deg;  // tan(delta), 1 - cos(delta), delta in degrees
     atmrt_altitude altitude;
     int earth_model, straight, flat;
@@ -146,8 +147,8 @@ __global__ void k_prepare_scene(const __grid_constant__ DevScene S, DevTerrain T
         d.lat = o.latitude;
         d.lon = o.longitude;
         d.elev = alt;
-        d.pos = as_cartesian(S.earth_model, S.radius, o.latitude, o.longitude, alt);
-        d.up = world_directions(S.earth_model, o.latitude, o.longitude).up;
+        d.pos = as_cartesian(S.earth, o.latitude, o.longitude, alt);
+        d.up = world_directions(S.earth, o.latitude, o.longitude).up;
         // kind, sizes, colour and texture pointer are filled by the host
     }
 }
@@ -165,19 +166,33 @@ __device__ __forceinline__ double get_ray_elev(const DevScene& S, int y) {
     return S.tilt - yy * S.fov / aspect;
 }
 
-// coords_at_dist_calc for every column: SphericalCalc::new (directional_calc.rs:56-69) /
-// FlDsCalc::new (:35-38).
+// coords_at_dist_calc for every column (mod.rs:114-145): SphericalCalc::new (directional_calc.rs:56-69; also
+// ObserverAe with its proj_radius), FlDsCalc::new (:35-38), AzEqCalc::new (:15-17), EllipsoidCalc::new (:104-135).
+// Eight doubles per column.
 __global__ void k_column_setup(const __grid_constant__ DevScene S, DevBuffers B) {
     int xl = blockIdx.x * blockDim.x + threadIdx.x;
     if (xl >= S.x1 - S.x0) return;
     double dir = get_ray_dir(S, S.x0 + xl);
     double* c = B.colcalc + (size_t)xl * 8;
+    if (S.earth.walker == WALK_ELLIPSOID) {
+        const EllipsoidCalc e = ellipsoid_calc(S.earth, S.lat0, S.lon0, dir);
+        c[0] = e.cos_az1, c[1] = e.sin_az1, c[2] = e.sin_alfa, c[3] = e.sig1, c[4] = e.cap_a, c[5] = e.cap_b, c[6] = e.cap_c, c[7] = e.red_lat;
+        return;
+    }
     double sindir, cosdir;
     sincos(to_radians(dir), &sindir, &cosdir);
-    if (S.flat) {
+    if (S.earth.walker == WALK_FLDS) {
         c[0] = cosdir;
         c[1] = sindir;
         c[2] = cos(to_radians(S.lat0));
+        return;
+    }
+    if (S.earth.walker == WALK_AZEQ) {  // mod.rs:116-125
+        const V3 pos = as_cartesian(S.earth, S.lat0, S.lon0, 0.0);
+        const Dirs d = world_directions(S.earth, S.lat0, S.lon0);
+        const V3 dv = d.north * cosdir + d.east * sindir;
+        c[0] = dv.x, c[1] = dv.y, c[2] = dv.z;
+        c[3] = pos.x, c[4] = pos.y, c[5] = pos.z;
         return;
     }
     double sinlat, coslat, sinlon, coslon;
@@ -189,13 +204,28 @@ __global__ void k_column_setup(const __grid_constant__ DevScene S, DevBuffers B)
     c[3] = d.up.x, c[4] = d.up.y, c[5] = d.up.z;
 }
 
-// find_normal, utils.rs:15-40: central differences +-15 m north/south and east/west on the terrain.
+__device__ __forceinline__ EllipsoidCalc column_ellipsoid_calc(const DevScene& S, const double* __restrict__ c) {
+    EllipsoidCalc e;
+    e.cos_az1 = c[0], e.sin_az1 = c[1], e.sin_alfa = c[2], e.sig1 = c[3], e.cap_a = c[4], e.cap_b = c[5], e.cap_c = c[6], e.red_lat = c[7];
+    e.lon = to_radians(S.lon0);
+    return e;
+}
+
+// find_normal, utils.rs:15-40: central differences +-15 m north/south and east/west on the terrain, walked
+// with the model's own DirectionalCalc from (lat, lon) at azimuths 0 and 90 degrees.
 // A pure function of (lat, lon); sin/cos of both are passed in because the callers have them.
 __device__ __forceinline__ V3 find_normal(const DevScene& S, const DevTerrain& T, double lat, double lon, double sinlat, double coslat,
                                           double sinlon, double coslon) {
     double n_lat, n_lon, s_lat, s_lon, e_lat, e_lon, w_lat, w_lon;
-    Dirs D;
-    if (S.flat) {
+    Dirs D;  // world_directions(lat, lon)
+    if (S.earth.flat_dirs) {
+        D.north = {-coslon, -sinlon, 0.0};
+        D.east = {-sinlon, coslon, 0.0};
+        D.up = {0.0, 0.0, 1.0};
+    } else {
+        D = spherical_directions_sc(sinlat, coslat, sinlon, coslon);
+    }
+    if (S.earth.walker == WALK_FLDS) {
         // FlDsCalc::new((lat, lon), 0.0 / 90.0).coords_at_dist(+-DIFF)
         n_lat = lat + 1.0 * NORMAL_DIFF / DEGREE_DISTANCE;
         n_lon = lon + 0.0 * NORMAL_DIFF / DEGREE_DISTANCE / coslat;
@@ -205,9 +235,23 @@ __device__ __forceinline__ V3 find_normal(const DevScene& S, const DevTerrain& T
         e_lon = lon + SIN_90 * NORMAL_DIFF / DEGREE_DISTANCE / coslat;
         w_lat = lat + COS_90 * -NORMAL_DIFF / DEGREE_DISTANCE;
         w_lon = lon + SIN_90 * -NORMAL_DIFF / DEGREE_DISTANCE / coslat;
-        D.north = {-coslon, -sinlon, 0.0};
-        D.east = {-sinlon, coslon, 0.0};
-        D.up = {0.0, 0.0, 1.0};
+    } else if (S.earth.walker == WALK_AZEQ) {
+        // AzEqCalc::new(north cos(az) + east sin(az), as_cartesian(lat, lon, 0)).coords_at_dist(+-DIFF), mod.rs:116-125
+        const double r = (90.0 - lat) * DEGREE_DISTANCE;
+        const V3 pos{r * coslon, r * sinlon, 0.0};
+        const V3 dir_ns = D.north * 1.0 + D.east * 0.0;
+        const V3 dir_ew = D.north * COS_90 + D.east * SIN_90;
+        azeq_walk(pos, dir_ns, NORMAL_DIFF, &n_lat, &n_lon);
+        azeq_walk(pos, dir_ns, -NORMAL_DIFF, &s_lat, &s_lon);
+        azeq_walk(pos, dir_ew, NORMAL_DIFF, &e_lat, &e_lon);
+        azeq_walk(pos, dir_ew, -NORMAL_DIFF, &w_lat, &w_lon);
+    } else if (S.earth.walker == WALK_ELLIPSOID) {
+        // EllipsoidCalc::new(a, b, (lat, lon), 0.0 / 90.0).coords_at_dist(+-DIFF)
+        const EllipsoidCalc ns = ellipsoid_calc(S.earth, lat, lon, 0.0), ew = ellipsoid_calc(S.earth, lat, lon, 90.0);
+        ellipsoid_walk(S.earth, ns, NORMAL_DIFF, &n_lat, &n_lon);
+        ellipsoid_walk(S.earth, ns, -NORMAL_DIFF, &s_lat, &s_lon);
+        ellipsoid_walk(S.earth, ew, NORMAL_DIFF, &e_lat, &e_lon);
+        ellipsoid_walk(S.earth, ew, -NORMAL_DIFF, &w_lat, &w_lon);
     } else {
         // SphericalCalc::new(radius, (lat, lon), 0.0 / 90.0).coords_at_dist(+-DIFF). With delta = DIFF/radius
         // (2.4e-6 rad) the great-circle walk has closed forms that agree with asin(fpos.z), atan2(fpos.y,
@@ -217,7 +261,6 @@ __device__ __forceinline__ V3 find_normal(const DevScene& S, const DevTerrain& T
         //                lon +- atan(tan(delta) / cos(lat)) => q - q^3/3, q = tan(delta)/cos(lat) (next term 1e-28)
         // (the cos(90 deg) = 6e-17 north component of the east direction moves the point by 1e-22 rad).
         // Near the poles (|lat| > 85 deg) the expansions lose accuracy: use the walk itself.
-        D = spherical_directions_sc(sinlat, coslat, sinlon, coslon);
         if (fabs(lat) <= 85.0) {
             const double icos = 1.0 / coslat;
             const double q = S.tan_diff * icos;
@@ -228,12 +271,13 @@ __device__ __forceinline__ V3 find_normal(const DevScene& S, const DevTerrain& T
             e_lat = lat_ew, e_lon = lon + dlon;
             w_lat = lat_ew, w_lon = lon - dlon;
         } else {
-            V3 dir_ns = D.north * 1.0 + D.east * 0.0;
-            V3 dir_ew = D.north * COS_90 + D.east * SIN_90;
-            spherical_walk(D.up, dir_ns, S.sin_diff, S.cos_diff, &n_lat, &n_lon);
-            spherical_walk(D.up, dir_ns, -S.sin_diff, S.cos_diff, &s_lat, &s_lon);
-            spherical_walk(D.up, dir_ew, S.sin_diff, S.cos_diff, &e_lat, &e_lon);
-            spherical_walk(D.up, dir_ew, -S.sin_diff, S.cos_diff, &w_lat, &w_lon);
+            const Dirs G = spherical_directions_sc(sinlat, coslat, sinlon, coslon);  // SphericalCalc's own frame (ObserverAe: not D)
+            V3 dir_ns = G.north * 1.0 + G.east * 0.0;
+            V3 dir_ew = G.north * COS_90 + G.east * SIN_90;
+            spherical_walk(G.up, dir_ns, S.sin_diff, S.cos_diff, &n_lat, &n_lon);
+            spherical_walk(G.up, dir_ns, -S.sin_diff, S.cos_diff, &s_lat, &s_lon);
+            spherical_walk(G.up, dir_ew, S.sin_diff, S.cos_diff, &e_lat, &e_lon);
+            spherical_walk(G.up, dir_ew, -S.sin_diff, S.cos_diff, &w_lat, &w_lon);
         }
     }
     double diff_ew = elev_or_zero(T, e_lat, e_lon) - elev_or_zero(T, w_lat, w_lon);
@@ -265,7 +309,7 @@ struct SampleTrig {
 __device__ __forceinline__ SampleTrig sample_trig(const DevScene& S, V3 fpos, double lat, double lon) {
     SampleTrig t;
     const double c2 = fpos.x * fpos.x + fpos.y * fpos.y;
-    if (!S.flat && c2 > 0.0025) {
+    if (S.earth.walker == WALK_SPHERICAL && c2 > 0.0025) {
         t.sinlat = fpos.z;
         t.coslat = sqrt(c2);
         const double ic = 1.0 / t.coslat;
@@ -280,7 +324,7 @@ __device__ __forceinline__ SampleTrig sample_trig(const DevScene& S, V3 fpos, do
 // SphericalCalc::coords_at_dist (directional_calc.rs:71-86) up to the unit vector of the sample.
 __device__ __forceinline__ V3 walk_fpos(const DevScene& S, const double* __restrict__ cc, double d) {
     double sinang, cosang;
-    sincos(d / S.radius, &sinang, &cosang);
+    sincos(d / S.earth.radius, &sinang, &cosang);
     return V3{cc[3], cc[4], cc[5]} * cosang + V3{cc[0], cc[1], cc[2]} * sinang;
 }
 
@@ -292,11 +336,15 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
     const double* cc = B.colcalc + (size_t)xl * 8;
     double lat, lon;
     V3 fpos{0.0, 0.0, 0.0};
-    if (S.flat) {  // FlDsCalc::coords_at_dist, directional_calc.rs:41-47
+    if (S.earth.walker == WALK_FLDS) {  // FlDsCalc::coords_at_dist, directional_calc.rs:41-47
         double d_lat = cc[0] * d / DEGREE_DISTANCE;
         double d_lon = cc[1] * d / DEGREE_DISTANCE / cc[2];
         lat = S.lat0 + d_lat;
         lon = S.lon0 + d_lon;
+    } else if (S.earth.walker == WALK_AZEQ) {  // AzEqCalc::coords_at_dist, directional_calc.rs:20-27
+        azeq_walk(V3{cc[3], cc[4], cc[5]}, V3{cc[0], cc[1], cc[2]}, d, &lat, &lon);
+    } else if (S.earth.walker == WALK_ELLIPSOID) {  // EllipsoidCalc::coords_at_dist, directional_calc.rs:139-184
+        ellipsoid_walk(S.earth, column_ellipsoid_calc(S, cc), d, &lat, &lon);
     } else {  // SphericalCalc::coords_at_dist, directional_calc.rs:71-86
         fpos = walk_fpos(S, cc, d);
         lat = to_degrees(asin(fpos.z));
@@ -313,7 +361,7 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
         unsigned long long mask = 0;
         for (int i = 0; i < S.nobjects; ++i) {
             const DevObject& o = B.objects[i];
-            V3 pos = as_cartesian_sc(S.earth_model, S.radius, lat, o.elev, t.sinlat, t.coslat, t.sinlon, t.coslon);
+            V3 pos = as_cartesian_sc(S.earth, lat, o.elev, t.sinlat, t.coslat, t.sinlon, t.coslon);
             V3 dist_v = pos - o.pos;
             if (dot(dist_v, dist_v) < 2.0 * (o.close_r + S.step) * (o.close_r + S.step)) mask |= 1ull << i;
         }
@@ -325,7 +373,7 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
 // the coordinates come from the cache, the unit vector of the walk is recomputed (one sincos).
 __device__ __forceinline__ V3 sample_normal(const DevScene& S, const DevTerrain& T, const DevBuffers& B, int xl, int k, double lat, double lon) {
     V3 fpos{0.0, 0.0, 0.0};
-    if (!S.flat) fpos = walk_fpos(S, B.colcalc + (size_t)xl * 8, B.dist_k[k]);
+    if (S.earth.walker == WALK_SPHERICAL) fpos = walk_fpos(S, B.colcalc + (size_t)xl * 8, B.dist_k[k]);
     const SampleTrig t = sample_trig(S, fpos, lat, lon);
     return find_normal(S, T, lat, lon, t.sinlat, t.coslat, t.sinlon, t.coslon);
 }
@@ -717,8 +765,8 @@ __device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers
     }
     unsigned long long mask = B.t_close[ti - 1] | B.t_close[ti];
     if (mask) {
-        V3 pos1 = as_cartesian(S.earth_model, S.radius, lat0, lon0, ray0);
-        V3 pos2 = as_cartesian(S.earth_model, S.radius, lat1, lon1, ray1);
+        V3 pos1 = as_cartesian(S.earth, lat0, lon0, ray0);
+        V3 pos2 = as_cartesian(S.earth, lat1, lon1, ray1);
         // The reference walks a HashSet (arbitrary order); index order here. Only exact `prop` ties
         // could tell the difference (stable sort below).
         while (mask) {

@@ -48,6 +48,18 @@ def scene_objects():
     ]
 
 
+EARTH_VARIANTS = {
+    "c3_wgs84": "Wgs84",
+    "c3_ellipsoid": {"Ellipsoid": {"a": 6_400_000.0, "b": 6_300_000.0}},
+    "c3_azeq": "AzimuthalEquidistant",
+    "c3_obsae": {"ObserverAe": {"proj_radius": 6_371_000.0}},
+    "c3_simple": "SimpleSphere",
+    "c4_wgs84": "Wgs84",
+    "c4_azeq": "AzimuthalEquidistant",
+    "c4_obsae": "SimpleObserverAe",
+}
+
+
 def make_scene(name, scale=1.0):
     c = _base()
     out, view = c["output"], c["view"]
@@ -65,7 +77,7 @@ def make_scene(name, scale=1.0):
         view["position"] = {"latitude": 45.05, "longitude": 5.5, "altitude": {"Relative": 2.0}}
         c["simulation_step"] = 50.0
         grid = (45, 5, 1, 1)
-    elif name in ("c2", "c4", "c3_flat", "c3_sph"):
+    elif name in ("c2", "c4", "c3_flat", "c3_sph") or name in EARTH_VARIANTS:
         # refracted, US-76, 1920x1080, fov 10, 2x2 tiles, 200 km, step 50
         size(3840 if name.startswith("c3") else 1920, 1080)
         view["frame"].update(direction=0.0, tilt=0.0, fov=20.0 if name.startswith("c3") else 10.0, max_distance=200_000.0)
@@ -76,9 +88,11 @@ def make_scene(name, scale=1.0):
             out["file_metadata"] = "./output.dat"  # BASELINE config 2 is the one "with --output-meta"
         if name == "c3_flat":
             c["earth_shape"] = "FlatDistorted"
-        if name == "c4":
+        if name == "c4" or name.startswith("c4_"):
             c["scene"]["objects"] = scene_objects()
             c["scene"]["terrain_alpha"] = 0.5
+        if name in EARTH_VARIANTS:  # the remaining earth models, on c3's / c4's geometry
+            c["earth_shape"] = EARTH_VARIANTS[name]
     elif name == "c5":
         # 360-degree 16384x4096 refracted panorama over 8x8 tiles, 400 km, step 25
         size(16384, 4096)

@@ -126,11 +126,11 @@ def get_elev(tiles, lat, lon):
     return out
 
 
-def coords_at_dist(earth_model, radius, lat0, lon0, direction, dist):
+def coords_at_dist(earth_model, radius, lat0, lon0, direction, dist, ellipsoid_b=0.0):
     dist = np.ascontiguousarray(dist, np.float64)
     lat, lon = np.empty_like(dist), np.empty_like(dist)
     lib().oracle_coords_at_dist(int(earth_model), C.c_double(radius), C.c_double(lat0), C.c_double(lon0), C.c_double(direction),
-                                _p(dist), int(dist.size), _p(lat), _p(lon))
+                                _p(dist), int(dist.size), _p(lat), _p(lon), C.c_double(ellipsoid_b))
     return lat, lon
 
 
@@ -140,9 +140,10 @@ def world_directions(earth_model, radius, lat, lon):
     return out[0:3], out[3:6], out[6:9]
 
 
-def as_cartesian(earth_model, radius, lat, lon, elev):
+def as_cartesian(earth_model, radius, lat, lon, elev, ellipsoid_b=0.0):
     out = np.empty(3)
-    lib().oracle_as_cartesian(int(earth_model), C.c_double(radius), C.c_double(lat), C.c_double(lon), C.c_double(elev), _p(out))
+    lib().oracle_as_cartesian(int(earth_model), C.c_double(radius), C.c_double(lat), C.c_double(lon), C.c_double(elev), _p(out),
+                              C.c_double(ellipsoid_b))
     return out
 
 

@@ -109,11 +109,18 @@ def test_custom_atmosphere_and_scope_errors(tmp_path):
     cfg["atmosphere"]["first_temperature_function"] = {"Spline": {"points": [[0, 288.0], [100, 287.0]], "boundary_condition": "Natural"}}
     with pytest.raises(config.ConfigError):
         config.into_params(cfg)
-    for shape in ("Wgs84", {"Ellipsoid": {"a": 1.0, "b": 1.0}}, "AzimuthalEquidistant"):
+    # every EarthModel of the reference lowers (earth_model/mod.rs:19-28); the parameterless ones as the reference lowers them
+    for shape, want in (("Wgs84", (abi.EARTH_ELLIPSOID, 6378137.0, 6356752.314245)), ({"Ellipsoid": {"a": 7.0e6, "b": 6.9e6}}, (abi.EARTH_ELLIPSOID, 7.0e6, 6.9e6)),
+                        ("AzimuthalEquidistant", (abi.EARTH_AZIMUTHAL_EQUIDISTANT, 0.0, 0.0)), ("SimpleObserverAe", (abi.EARTH_OBSERVER_AE, 6371000.0, 0.0)),
+                        ({"ObserverAe": {"proj_radius": 6.4e6}}, (abi.EARTH_OBSERVER_AE, 6.4e6, 0.0)), ("SimpleSphere", (abi.EARTH_SPHERICAL, 6371000.0, 0.0))):
         c = config.default_config()
         c["earth_shape"] = shape
-        with pytest.raises(config.ConfigError):
-            config.into_params(c)
+        q = config.into_params(c)
+        assert (q.earth_model, q.radius, q.ellipsoid_b) == want
+    c = config.default_config()
+    c["earth_shape"] = "Geoid"
+    with pytest.raises(config.ConfigError):
+        config.into_params(c)
     c = config.default_config()
     c["output"]["generator"] = "Rectilinear"
     with pytest.raises(config.ConfigError):

@@ -82,7 +82,7 @@ def test_atmosphere_probe(ctx, oracle_lib):
     np.testing.assert_allclose(n - 1.0, no - 1.0, rtol=1e-12)
 
 
-@pytest.mark.parametrize("name", ["c1", "c2", "c3_flat", "c4"])
+@pytest.mark.parametrize("name", ["c1", "c2", "c3_flat", "c4", "c3_wgs84", "c3_azeq", "c3_obsae", "c4_wgs84", "c4_azeq"])
 def test_terrain_profile_matches_oracle(ctx, oracle_lib, name):
     p, terrain, objects, textures = scene(name, 0.05)
     ctx.set_terrain(terrain)
@@ -284,7 +284,9 @@ def compare_render(got, want, label="", finish_moves_frac=0.001):
     return report
 
 
-@pytest.mark.parametrize("name,scale", [("c1", 0.5), ("c2", 0.2), ("c3_flat", 0.15), ("c3_sph", 0.15), ("c4", 0.2), ("c5", 0.0125)])
+@pytest.mark.parametrize("name,scale", [("c1", 0.5), ("c2", 0.2), ("c3_flat", 0.15), ("c3_sph", 0.15), ("c4", 0.2), ("c5", 0.0125),
+                                        ("c3_wgs84", 0.1), ("c3_ellipsoid", 0.1), ("c3_azeq", 0.1), ("c3_obsae", 0.1), ("c3_simple", 0.05),
+                                        ("c4_wgs84", 0.15), ("c4_azeq", 0.15), ("c4_obsae", 0.15)])
 def test_render_matches_oracle(ctx, oracle_lib, name, scale):
     p, terrain, objects, textures = scene(name, scale)
     ctx.set_terrain(terrain)

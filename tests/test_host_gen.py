@@ -110,6 +110,16 @@ def test_cpp_yaml_parser_matches_pyyaml(tmp_path, text):
     assert meta == (cfg["output"].get("file_metadata") or "")
 
 
+@pytest.mark.parametrize("shape", ["Wgs84", "SimpleSphere", "AzimuthalEquidistant", "SimpleObserverAe", "FlatDistorted",
+                                   "{Ellipsoid: {a: 6400000.0, b: 6300000.0}}", "{ObserverAe: {proj_radius: 6380000.0}}",
+                                   "{Spherical: {radius: 7000000.0}}"])
+def test_cpp_parser_lowers_every_earth_model_like_the_mirror(tmp_path, shape):
+    f = tmp_path / "c.yaml"
+    f.write_text(f"earth_shape: {shape}\nview:\n  coloring:\n    Shading: {{water_level: 0.0, ambient_light: 0.4, light_zenith_angle: 45.0, light_dir: 0.0}}\n")
+    p_cpp, *_ = host.parse_config(["-c", str(f)])
+    _same_params(p_cpp, config.into_params(config.read_config(["-c", str(f)])))
+
+
 def test_cpp_cli_overrides_match_the_mirror(tmp_path):
     f = tmp_path / "c.yaml"
     f.write_text(YAML)
@@ -130,7 +140,7 @@ def test_cpp_cli_overrides_match_the_mirror(tmp_path):
 
 
 def test_cpp_scope_errors(tmp_path):
-    for body in ("earth_shape: Wgs84\n", "output: {generator: Rectilinear}\n",
+    for body in ("earth_shape: Geoid\n", "output: {generator: Rectilinear}\n",
                  "atmosphere:\n  pressure: {altitude: 0, pressure: 101325}\n  first_temperature_function:\n    Spline: {points: [[0, 288]]}\n"):
         f = tmp_path / "bad.yaml"
         f.write_text(body)
