@@ -12,6 +12,7 @@ MAX_STEP_POINTS = 16
 EARTH_SPHERICAL, EARTH_FLAT_DISTORTED, EARTH_ELLIPSOID, EARTH_AZIMUTHAL_EQUIDISTANT, EARTH_OBSERVER_AE = 0, 1, 2, 3, 4
 FLAT_FAMILY = (EARTH_FLAT_DISTORTED, EARTH_AZIMUTHAL_EQUIDISTANT, EARTH_OBSERVER_AE)  # the world is the azimuthal-equidistant plane
 ALT_ABSOLUTE, ALT_RELATIVE = 0, 1
+GENERATOR_FAST, GENERATOR_RECTILINEAR = 0, 1
 COLORING_SIMPLE, COLORING_SHADING = 0, 1
 PALETTE_LEGACY, PALETTE_IMPROVED = 0, 1
 OBJECT_FRUSTUM, OBJECT_BILLBOARD = 0, 1
@@ -59,7 +60,7 @@ class Params(C.Structure):
         ("light_dir", C.c_double * 3),
         ("simple_max_distance", C.c_double),
         ("fog_enabled", C.c_int32),
-        ("_pad0", C.c_int32),
+        ("generator", C.c_int32),
         ("fog_distance", C.c_double),
         ("width", C.c_int32),
         ("height", C.c_int32),

@@ -320,8 +320,12 @@ def into_params(cfg, x0=None, x1=None):
     p.width, p.height = int(out["width"]), int(out["height"])
     if not (0 < p.width <= 32767 and 0 < p.height <= 32767):
         raise ConfigError("width/height must fit the reference's i16 pixel centring (fast.rs:116,122)")
-    gen = out.get("generator", "Fast")
-    if gen != "Fast":
+    gen = out.get("generator", "Fast")  # GeneratorDef, params.rs:387-392
+    if gen == "Fast":
+        p.generator = abi.GENERATOR_FAST
+    elif gen == "Rectilinear":
+        p.generator = abi.GENERATOR_RECTILINEAR
+    else:
         raise ConfigError(f"generator {gen} is outside the hot-path scope (SURVEY section 8 f1)")
     p.x0 = 0 if x0 is None else int(x0)
     p.x1 = p.width if x1 is None else int(x1)

@@ -438,6 +438,7 @@ int validate_params(atmrt_ctx* ctx, const atmrt_params& p) {
         return fail(ctx, ATMRT_ERR_INVALID, "radius (Spherical radius, Ellipsoid a, ObserverAe proj_radius) must be positive");
     if (p.earth_model == ATMRT_EARTH_ELLIPSOID && !(p.ellipsoid_b > 0.0)) return fail(ctx, ATMRT_ERR_INVALID, "ellipsoid_b must be positive");
     if (p.coloring != ATMRT_COLORING_SIMPLE && p.coloring != ATMRT_COLORING_SHADING) return fail(ctx, ATMRT_ERR_INVALID, "unknown coloring");
+    if (p.generator != ATMRT_GENERATOR_FAST && p.generator != ATMRT_GENERATOR_RECTILINEAR) return fail(ctx, ATMRT_ERR_INVALID, "unknown generator");
     return 0;
 }
 
@@ -511,15 +512,19 @@ int prepare_render(atmrt_ctx* ctx) {
         const bool sph_rk4 = !S.flat && !S.straight;
         const double d = sph_rk4 ? p.simulation_step / S.radius : p.simulation_step;
         const double inv_radius = S.flat ? 0.0 : 1.0 / S.radius;
-        ctx->path_x.assign((size_t)2 * n_t, 0.0);
+        // two entries more than the Fast generator's caches hold: the Rectilinear generator's stream ends at the
+        // first state PAST max_distance (rectilinear.rs:175-177)
+        const int n_x = n_t + 2;
+        S.n_x = n_x;
+        ctx->path_x.assign((size_t)2 * n_x, 0.0);
         double t = 0.0;
         ctx->path_k_far = n_t;
-        for (int k = 1; k < n_t; ++k) {
+        for (int k = 1; k < n_x; ++k) {
             t += d;
             const double x = sph_rk4 ? t * S.radius : t;
             ctx->path_x[k] = x;
             const double dx = x - ctx->path_x[k - 1];
-            ctx->path_x[(size_t)n_t + k] = S.flat ? dx : dx * inv_radius;  // calc_dist's dx / R (utils.rs:49)
+            ctx->path_x[(size_t)n_x + k] = S.flat ? dx : dx * inv_radius;  // calc_dist's dx / R (utils.rs:49)
         }
         for (int k = n_t - 1; k >= 0; --k)
             if (ctx->path_x[k] > p.max_distance) ctx->path_k_far = k;  // first element past max_distance (utils.rs:167)
@@ -535,14 +540,18 @@ int prepare_render(atmrt_ctx* ctx) {
     const size_t wl = (size_t)(p.x1 - p.x0), h = (size_t)p.height, np = (size_t)S.n_pad;
     const size_t f8 = sizeof(double);
     int e = 0;
+    const bool rect = p.generator == ATMRT_GENERATOR_RECTILINEAR;  // one ray and one walk per pixel: no caches
+    S.generator = p.generator;
     e |= ensure(ctx, ctx->d_dist, f8 * n_t);
+    e |= ensure(ctx, ctx->d_pdist, f8 * 2 * S.n_x);
+    if (!rect) {
     e |= ensure(ctx, ctx->d_colcalc, f8 * 8 * wl);
     e |= ensure(ctx, ctx->d_tlat, f8 * wl * np);
     e |= ensure(ctx, ctx->d_tlon, f8 * wl * np);
     e |= ensure(ctx, ctx->d_telev, f8 * wl * np);
     if (S.nobjects > 0) e |= ensure(ctx, ctx->d_tclose, 8 * wl * np);
     const size_t hp = (size_t)S.h_pad;
-    e |= ensure(ctx, ctx->d_pdist, f8 * 2 * n_t);
+    e |= ensure(ctx, ctx->d_pdist, f8 * 2 * S.n_x);
     e |= ensure(ctx, ctx->d_pelev, f8 * hp * n_t);
     e |= ensure(ctx, ctx->d_plen, f8 * hp * n_t);
     e |= ensure(ctx, ctx->d_pn, sizeof(int) * hp);
@@ -563,12 +572,15 @@ int prepare_render(atmrt_ctx* ctx) {
     e |= ensure(ctx, ctx->d_rmax2, f8 * hp * S.n2);
     e |= ensure(ctx, ctx->d_rmin3, f8 * hp);
     e |= ensure(ctx, ctx->d_rmax3, f8 * hp);
+    }
     (void)h;
     e |= ensure(ctx, ctx->d_obs, f8);
     e |= ensure(ctx, ctx->d_atm_cells, f8 * ATM_FIELDS * ATM_CELLS + sizeof(DevGPiece) * ATM_MAX_PIECES);
     e |= ensure(ctx, ctx->d_sweep_flags, 16);
-    e |= ensure(ctx, ctx->d_sweep_col, wl);
-    e |= ensure(ctx, ctx->d_sweep_hit, sizeof(int) * wl * hp);
+    if (!rect) {
+        e |= ensure(ctx, ctx->d_sweep_col, wl);
+        e |= ensure(ctx, ctx->d_sweep_hit, sizeof(int) * wl * (size_t)S.h_pad);
+    }
     // the g(h) table depends on the atmosphere and the wavelength only: rebuilt when they change
     if (!ctx->atm_table_valid || memcmp(&ctx->atm_table_def, &p.atmosphere, sizeof(p.atmosphere)) != 0 || ctx->atm_table_wavelength != p.wavelength) {
         build_g_table(S.atm, p.wavelength, ctx->atm_cells, ctx->atm_pieces, &ctx->atm_cells_served);
@@ -588,7 +600,7 @@ int prepare_render(atmrt_ctx* ctx) {
     B.t_lat = (double*)ctx->d_tlat.p, B.t_lon = (double*)ctx->d_tlon.p, B.t_elev = (double*)ctx->d_telev.p;
     B.terrain = ctx->terrain;
     B.t_close = S.nobjects > 0 ? (unsigned long long*)ctx->d_tclose.p : nullptr;
-    B.path_x = (const double*)ctx->d_pdist.p, B.path_dxr = B.path_x + S.n_t;
+    B.path_x = (const double*)ctx->d_pdist.p, B.path_dxr = B.path_x + S.n_x;
     B.p_elev = (double*)ctx->d_pelev.p, B.p_len = (double*)ctx->d_plen.p;
     B.p_n = (int*)ctx->d_pn.p;
     B.tmin1 = (double*)ctx->d_tmin1.p, B.tmax1 = (double*)ctx->d_tmax1.p;
@@ -615,7 +627,7 @@ int prepare_render(atmrt_ctx* ctx) {
 int upload_scene_inputs(atmrt_ctx* ctx, cudaStream_t s) {
     const DevScene& S = ctx->scene;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dist.p, ctx->dist_k.data(), sizeof(double) * S.n_t, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pdist.p, ctx->path_x.data(), sizeof(double) * 2 * S.n_t, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pdist.p, ctx->path_x.data(), sizeof(double) * 2 * S.n_x, cudaMemcpyHostToDevice, s));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_atm_cells.p, ctx->atm_cells.data(), sizeof(double) * ATM_FIELDS * ATM_CELLS, cudaMemcpyHostToDevice, s));
     if (!ctx->atm_pieces.empty())
         CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->d_atm_cells.p + sizeof(double) * ATM_FIELDS * ATM_CELLS, ctx->atm_pieces.data(),
@@ -680,6 +692,30 @@ int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main) {
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 8 * CNT_COUNT, main));
     k_prepare_scene<<<(S.nobjects + 1 + 63) / 64, 64, 0, main>>>(S, ctx->terrain, B, (const atmrt_object*)ctx->d_objects_in.p);
     ctx->launches++;
+
+    if (S.generator == ATMRT_GENERATOR_RECTILINEAR) {
+        // generators/rectilinear.rs: one ray and one azimuth walk per pixel, a single kernel (the stage events
+        // bracket it as the march; trace lists are a Fast-generator probe)
+        if (rt.points || rt.counts) return fail(ctx, ATMRT_ERR_INVALID, "render_trace is not available with the Rectilinear generator");
+        MarchOut O{rt.rgb, rt.meta, rt.steps, nullptr, nullptr, 0};
+        cudaEvent_t marks[] = {E->a0, E->a1, E->b0, E->b1, E->c0};
+        for (cudaEvent_t ev : marks) CUDA_TRY(ctx, cudaEventRecord(ev, main));
+        const dim3 grid((wl + RECT_THREADS - 1) / RECT_THREADS, h);
+        const int libm = ctx->path_mode == 1 ? 1 : 0;
+        if (S.flat) {
+            if (S.nobjects > 0) k_rectilinear<true, true><<<grid, RECT_THREADS, 0, main>>>(S, B, O, libm);
+            else k_rectilinear<true, false><<<grid, RECT_THREADS, 0, main>>>(S, B, O, libm);
+        } else {
+            if (S.nobjects > 0) k_rectilinear<false, true><<<grid, RECT_THREADS, 0, main>>>(S, B, O, libm);
+            else k_rectilinear<false, false><<<grid, RECT_THREADS, 0, main>>>(S, B, O, libm);
+        }
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaEventRecord(E->c1, main));
+        CUDA_TRY(ctx, cudaEventRecord(E->t1, main));
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->rendered = true;
+        return 0;
+    }
 
     // Opaque terrain without objects ends every pixel at its first crossing: the horizon sweep
     // (kernels.cuh) finds those in O(N_t + H) per column when the rays of this render do not cross each
@@ -789,16 +825,17 @@ int collect_stats(atmrt_ctx* ctx, atmrt_stats* stats) {
     const DevScene& S = ctx->scene;
     unsigned long long c[CNT_COUNT];
     CUDA_TRY(ctx, cudaMemcpy(c, ctx->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost));
-    std::vector<int> pn(S.height);
-    CUDA_TRY(ctx, cudaMemcpy(pn.data(), ctx->d_pn.p, sizeof(int) * S.height, cudaMemcpyDeviceToHost));
+    std::vector<int> pn(S.height, 0);
+    const bool rect = S.generator == ATMRT_GENERATOR_RECTILINEAR;  // no path cache
+    if (!rect) CUDA_TRY(ctx, cudaMemcpy(pn.data(), ctx->d_pn.p, sizeof(int) * S.height, cudaMemcpyDeviceToHost));
     memset(stats, 0, sizeof(*stats));
     stats->ray_steps = c[CNT_RAY_STEPS];
     stats->trace_points = c[CNT_TRACE_POINTS];
     stats->pixels_hit = c[CNT_PIXELS_HIT];
     stats->step_overflows = c[CNT_OVERFLOWS];
     stats->path_steps = c[CNT_PATH_STEPS];
-    stats->terrain_samples = (uint64_t)(S.x1 - S.x0) * (uint64_t)S.n_t;
-    stats->n_terrain = S.n_t;
+    stats->terrain_samples = rect ? c[CNT_PATH_STEPS] : (uint64_t)(S.x1 - S.x0) * (uint64_t)S.n_t;
+    stats->n_terrain = rect ? 0 : S.n_t;
     int mx = 0;
     for (int v : pn) mx = std::max(mx, v);
     stats->n_path_max = mx;
@@ -1143,6 +1180,7 @@ int atmrt_get_terrain_profile(atmrt_ctx* ctx, int x, int capacity, double* lat, 
                               uint64_t* objects_close, int* n) {
     if (!ctx || !n) return fail(ctx, ATMRT_ERR_INVALID, "get_terrain_profile: NULL argument");
     if (!ctx->rendered) return fail(ctx, ATMRT_ERR_STATE, "get_terrain_profile before a render");
+    if (ctx->scene.generator != ATMRT_GENERATOR_FAST) return fail(ctx, ATMRT_ERR_STATE, "get_terrain_profile: only the Fast generator keeps a terrain cache");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const DevScene& S = ctx->scene;
     if (x < 0 || x >= S.x1 - S.x0) return fail(ctx, ATMRT_ERR_INVALID, "column out of range");
@@ -1174,6 +1212,7 @@ int atmrt_get_terrain_profile(atmrt_ctx* ctx, int x, int capacity, double* lat, 
 int atmrt_get_path(atmrt_ctx* ctx, int y, int capacity, double* dist, double* elev, double* path_length, int* n) {
     if (!ctx || !n) return fail(ctx, ATMRT_ERR_INVALID, "get_path: NULL argument");
     if (!ctx->rendered) return fail(ctx, ATMRT_ERR_STATE, "get_path before a render");
+    if (ctx->scene.generator != ATMRT_GENERATOR_FAST) return fail(ctx, ATMRT_ERR_STATE, "get_path: only the Fast generator keeps a path cache");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const DevScene& S = ctx->scene;
     if (y < 0 || y >= S.height) return fail(ctx, ATMRT_ERR_INVALID, "row out of range");

@@ -293,6 +293,7 @@ struct Config {
     int earth_model = ATMRT_EARTH_SPHERICAL;
     double radius = 6371000.0;
     double ellipsoid_b = 0.0;
+    int generator = ATMRT_GENERATOR_FAST;
     double wavelength = 530e-9;
     bool straight_rays = false;
     double simulation_step = 50.0;
@@ -495,7 +496,11 @@ static void apply_yaml(const Node& doc, Config* c) {
             if (!f->is_null()) c->file_metadata = f->scalar;
         c->width = (int)num(*out, "width", c->width), c->height = (int)num(*out, "height", c->height);
         if (const Node* g = out->get("generator"))
-            if (g->scalar != "Fast") throw std::runtime_error("generator " + g->scalar + " is outside the device path (Fast only)");
+        {
+            if (g->scalar == "Fast") c->generator = ATMRT_GENERATOR_FAST;
+            else if (g->scalar == "Rectilinear") c->generator = ATMRT_GENERATOR_RECTILINEAR;
+            else throw std::runtime_error("generator " + g->scalar + " is outside the device path (Fast, Rectilinear)");
+        }
         for (const char* k : {"ticks", "vertical_ticks"})
             if (const Node* t = out->get(k))
                 if (t->kind == Node::Seq && !t->seq.empty()) fprintf(stderr, "warning: output.%s is ignored (overlays are out of scope)\n", k);
@@ -610,6 +615,7 @@ static atmrt_params into_params(const Config& c) {
     if (c.earth_model != ATMRT_EARTH_ELLIPSOID) p.ellipsoid_b = 0.0;
     p.simple_max_distance = c.max_distance;
     p.fog_enabled = c.fog ? 1 : 0, p.fog_distance = c.fog_distance;
+    p.generator = c.generator;
     p.width = c.width, p.height = c.height, p.x0 = 0, p.x1 = c.width;
     return p;
 }

@@ -37,6 +37,8 @@ struct DevScene {
     atmrt_altitude altitude;
     int earth_model, straight, flat;
     int width, height, x0, x1;
+    int generator;  // atmrt_generator
+    int n_x;     // entries of path_x / path_dxr (n_t + 2)
     int n_t;     // terrain samples per column (N_t)
     int path_k_far;  // first path element with dist > max_distance (n_t if none): the row-independent half of utils.rs:167
     int n_pad;   // row stride of the [column][k] and [row][k] caches
@@ -169,11 +171,7 @@ __device__ __forceinline__ double get_ray_elev(const DevScene& S, int y) {
 // coords_at_dist_calc for every column (mod.rs:114-145): SphericalCalc::new (directional_calc.rs:56-69; also
 // ObserverAe with its proj_radius), FlDsCalc::new (:35-38), AzEqCalc::new (:15-17), EllipsoidCalc::new (:104-135).
 // Eight doubles per column.
-__global__ void k_column_setup(const __grid_constant__ DevScene S, DevBuffers B) {
-    int xl = blockIdx.x * blockDim.x + threadIdx.x;
-    if (xl >= S.x1 - S.x0) return;
-    double dir = get_ray_dir(S, S.x0 + xl);
-    double* c = B.colcalc + (size_t)xl * 8;
+__device__ __forceinline__ void direction_calc(const DevScene& S, double dir, double* c) {
     if (S.earth.walker == WALK_ELLIPSOID) {
         const EllipsoidCalc e = ellipsoid_calc(S.earth, S.lat0, S.lon0, dir);
         c[0] = e.cos_az1, c[1] = e.sin_az1, c[2] = e.sin_alfa, c[3] = e.sig1, c[4] = e.cap_a, c[5] = e.cap_b, c[6] = e.cap_c, c[7] = e.red_lat;
@@ -202,6 +200,12 @@ __global__ void k_column_setup(const __grid_constant__ DevScene S, DevBuffers B)
     V3 dv = d.north * cosdir + d.east * sindir;
     c[0] = dv.x, c[1] = dv.y, c[2] = dv.z;
     c[3] = d.up.x, c[4] = d.up.y, c[5] = d.up.z;
+}
+
+__global__ void k_column_setup(const __grid_constant__ DevScene S, DevBuffers B) {
+    int xl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xl >= S.x1 - S.x0) return;
+    direction_calc(S, get_ray_dir(S, S.x0 + xl), B.colcalc + (size_t)xl * 8);
 }
 
 __device__ __forceinline__ EllipsoidCalc column_ellipsoid_calc(const DevScene& S, const double* __restrict__ c) {
@@ -328,6 +332,38 @@ __device__ __forceinline__ V3 walk_fpos(const DevScene& S, const double* __restr
     return V3{cc[3], cc[4], cc[5]} * cosang + V3{cc[0], cc[1], cc[2]} * sinang;
 }
 
+// DirectionalCalc::coords_at_dist of the walker lowered into cc (direction_calc). fpos: the unit vector of the
+// sample for the spherical walker (sample_trig reads the sample's sines and cosines off it), else untouched.
+__device__ __forceinline__ void walk_coords(const DevScene& S, const double* __restrict__ cc, double d, double* lat, double* lon, V3* fpos) {
+    if (S.earth.walker == WALK_FLDS) {  // FlDsCalc::coords_at_dist, directional_calc.rs:41-47
+        double d_lat = cc[0] * d / DEGREE_DISTANCE;
+        double d_lon = cc[1] * d / DEGREE_DISTANCE / cc[2];
+        *lat = S.lat0 + d_lat;
+        *lon = S.lon0 + d_lon;
+    } else if (S.earth.walker == WALK_AZEQ) {  // AzEqCalc::coords_at_dist, directional_calc.rs:20-27
+        azeq_walk(V3{cc[3], cc[4], cc[5]}, V3{cc[0], cc[1], cc[2]}, d, lat, lon);
+    } else if (S.earth.walker == WALK_ELLIPSOID) {  // EllipsoidCalc::coords_at_dist, directional_calc.rs:139-184
+        ellipsoid_walk(S.earth, column_ellipsoid_calc(S, cc), d, lat, lon);
+    } else {  // SphericalCalc::coords_at_dist, directional_calc.rs:71-86
+        *fpos = walk_fpos(S, cc, d);
+        *lat = to_degrees(asin(fpos->z));
+        *lon = to_degrees(atan2(fpos->y, fpos->x));
+    }
+}
+
+// TerrainData::objects_close (utils.rs:76-82): Object::is_close, frustum.rs:103-114 / billboard.rs:68-78
+__device__ __forceinline__ unsigned long long objects_close(const DevScene& S, const DevBuffers& B, V3 fpos, double lat, double lon) {
+    const SampleTrig t = sample_trig(S, fpos, lat, lon);
+    unsigned long long mask = 0;
+    for (int i = 0; i < S.nobjects; ++i) {
+        const DevObject& o = B.objects[i];
+        V3 pos = as_cartesian_sc(S.earth, lat, o.elev, t.sinlat, t.coslat, t.sinlon, t.coslon);
+        V3 dist_v = pos - o.pos;
+        if (dot(dist_v, dist_v) < 2.0 * (o.close_r + S.step) * (o.close_r + S.step)) mask |= 1ull << i;
+    }
+    return mask;
+}
+
 __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__ DevScene S, DevTerrain T, DevBuffers B, int col0) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     int xl = col0 + blockIdx.y;  // the render is issued in column chunks (atmrt_lib.cu:launch_render)
@@ -336,37 +372,14 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
     const double* cc = B.colcalc + (size_t)xl * 8;
     double lat, lon;
     V3 fpos{0.0, 0.0, 0.0};
-    if (S.earth.walker == WALK_FLDS) {  // FlDsCalc::coords_at_dist, directional_calc.rs:41-47
-        double d_lat = cc[0] * d / DEGREE_DISTANCE;
-        double d_lon = cc[1] * d / DEGREE_DISTANCE / cc[2];
-        lat = S.lat0 + d_lat;
-        lon = S.lon0 + d_lon;
-    } else if (S.earth.walker == WALK_AZEQ) {  // AzEqCalc::coords_at_dist, directional_calc.rs:20-27
-        azeq_walk(V3{cc[3], cc[4], cc[5]}, V3{cc[0], cc[1], cc[2]}, d, &lat, &lon);
-    } else if (S.earth.walker == WALK_ELLIPSOID) {  // EllipsoidCalc::coords_at_dist, directional_calc.rs:139-184
-        ellipsoid_walk(S.earth, column_ellipsoid_calc(S, cc), d, &lat, &lon);
-    } else {  // SphericalCalc::coords_at_dist, directional_calc.rs:71-86
-        fpos = walk_fpos(S, cc, d);
-        lat = to_degrees(asin(fpos.z));
-        lon = to_degrees(atan2(fpos.y, fpos.x));
-    }
+    walk_coords(S, cc, d, &lat, &lon, &fpos);
     double elev = elev_or_zero(T, lat, lon);
     size_t idx = (size_t)xl * S.n_pad + k;
     B.t_lat[idx] = lat;
     B.t_lon[idx] = lon;
     B.t_elev[idx] = elev;
 
-    if (S.nobjects > 0) {  // Object::is_close, frustum.rs:103-114 / billboard.rs:68-78
-        const SampleTrig t = sample_trig(S, fpos, lat, lon);
-        unsigned long long mask = 0;
-        for (int i = 0; i < S.nobjects; ++i) {
-            const DevObject& o = B.objects[i];
-            V3 pos = as_cartesian_sc(S.earth, lat, o.elev, t.sinlat, t.coslat, t.sinlon, t.coslon);
-            V3 dist_v = pos - o.pos;
-            if (dot(dist_v, dist_v) < 2.0 * (o.close_r + S.step) * (o.close_r + S.step)) mask |= 1ull << i;
-        }
-        B.t_close[idx] = mask;
-    }
+    if (S.nobjects > 0) B.t_close[idx] = objects_close(S, B, fpos, lat, lon);
 }
 
 // TerrainData::normal of sample k of column xl (find_normal at the sample's coordinates, utils.rs:84):
@@ -715,18 +728,21 @@ __device__ __forceinline__ void emit_point(const DevScene& S, const MarchOut& O,
     st.count += 1;
 }
 
-// One march step that holds an event. Returns true when the pixel finishes (an alpha == 1 surface).
-template <bool OBJECTS, bool TRACE>
-__device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers& B, const MarchOut& O, int xl, int y, int k,
-                                             size_t pixel, PixelState& st, const V3* normals = nullptr) {
-    const size_t ti = (size_t)xl * S.n_pad + k;
-    const size_t p1 = path_index(S.n_t, k, y), p0 = p1 - PATH_ROWS;
-    // old_tracing_state = (terrain[k-1], path[k-1]) with dist/path_len forced to 0 for k-1 == 0.
-    const double lat0 = B.t_lat[ti - 1], lon0 = B.t_lon[ti - 1], elev0 = B.t_elev[ti - 1];
-    const double lat1 = B.t_lat[ti], lon1 = B.t_lon[ti], elev1 = B.t_elev[ti];
-    const double ray0 = B.p_elev[p0], ray1 = B.p_elev[p1];
-    const double dist0 = B.path_x[k - 1], dist1 = B.path_x[k];  // path_x[0] = 0
-    const double len0 = k - 1 == 0 ? 0.0 : B.p_len[p0], len1 = B.p_len[p1];
+// The two ends of one step of get_single_pixel's stream: old_tracing_state and new_tracing_state
+// (utils.rs:207-219), with dist / path_len of state 0 already forced to 0.
+struct StepEnds {
+    double lat0, lon0, elev0, ray0, dist0, len0;
+    double lat1, lon1, elev1, ray1, dist1, len1;
+    unsigned long long mask;  // objects_close of either end
+};
+
+// One step that holds an event (utils.rs:220-285). `normals(&n0, &n1)` yields TerrainData::normal of the two
+// ends; it is called only when the terrain is hit. Returns true when the pixel finishes (an alpha == 1 surface).
+template <bool OBJECTS, bool TRACE, class NormalFn>
+__device__ __forceinline__ bool process_ends(const DevScene& S, const DevBuffers& B, const MarchOut& O, const StepEnds& e, int k, size_t pixel,
+                                             PixelState& st, NormalFn normals) {
+    const double lat0 = e.lat0, lon0 = e.lon0, elev0 = e.elev0, lat1 = e.lat1, lon1 = e.lon1, elev1 = e.elev1;
+    const double ray0 = e.ray0, ray1 = e.ray1, dist0 = e.dist0, dist1 = e.dist1, len0 = e.len0, len1 = e.len1;
     const double diff1 = ray0 - elev0, diff2 = ray1 - elev1;
     const bool terrain_hit = diff1 * diff2 < 0.0;
     bool finish = false;
@@ -735,11 +751,7 @@ __device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers
         if (!terrain_hit) return false;
         const double prop = diff1 / (diff1 - diff2);
         V3 n0, n1;
-        if (normals) {
-            n0 = normals[0], n1 = normals[1];
-        } else {
-            n0 = sample_normal(S, B.terrain, B, xl, k - 1, lat0, lon0), n1 = sample_normal(S, B.terrain, B, xl, k, lat1, lon1);
-        }
+        normals(&n0, &n1);
         // TracingState::interpolate, utils.rs:108-125
         emit_point<TRACE>(S, O, pixel, k, st, true, lat0 + (lat1 - lat0) * prop, lon0 + (lon1 - lon0) * prop,
                           dist0 + (dist1 - dist0) * prop, elev0 + (elev1 - elev0) * prop, len0 + (len1 - len0) * prop,
@@ -755,7 +767,8 @@ __device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers
     bool overflow = false;
     if (terrain_hit) {
         double prop = diff1 / (diff1 - diff2);
-        const V3 n0 = sample_normal(S, B.terrain, B, xl, k - 1, lat0, lon0), n1 = sample_normal(S, B.terrain, B, xl, k, lat1, lon1);
+        V3 n0, n1;
+        normals(&n0, &n1);
         c_prop[0] = prop;
         c_normal[0] = n0 + (n1 - n0) * prop;
         c_color[0] = Color4{0.0, 0.0, 0.0, S.shade.terrain_alpha};
@@ -763,7 +776,7 @@ __device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers
         ncand = 1;
         if (S.shade.terrain_alpha == 1.0) finish = true;
     }
-    unsigned long long mask = B.t_close[ti - 1] | B.t_close[ti];
+    unsigned long long mask = e.mask;
     if (mask) {
         V3 pos1 = as_cartesian(S.earth, lat0, lon0, ray0);
         V3 pos2 = as_cartesian(S.earth, lat1, lon1, ray1);
@@ -814,6 +827,28 @@ __device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers
                           c_color[i]);
     }
     return finish;
+}
+
+// The Fast generator's step k of pixel (xl, y): the ends come from the two caches (fast.rs:56-64).
+template <bool OBJECTS, bool TRACE>
+__device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers& B, const MarchOut& O, int xl, int y, int k,
+                                             size_t pixel, PixelState& st, const V3* normals = nullptr) {
+    const size_t ti = (size_t)xl * S.n_pad + k;
+    const size_t p1 = path_index(S.n_t, k, y), p0 = p1 - PATH_ROWS;
+    StepEnds e;
+    e.lat0 = B.t_lat[ti - 1], e.lon0 = B.t_lon[ti - 1], e.elev0 = B.t_elev[ti - 1];
+    e.lat1 = B.t_lat[ti], e.lon1 = B.t_lon[ti], e.elev1 = B.t_elev[ti];
+    e.ray0 = B.p_elev[p0], e.ray1 = B.p_elev[p1];
+    e.dist0 = B.path_x[k - 1], e.dist1 = B.path_x[k];  // path_x[0] = 0
+    e.len0 = k - 1 == 0 ? 0.0 : B.p_len[p0], e.len1 = B.p_len[p1];
+    e.mask = OBJECTS ? (B.t_close[ti - 1] | B.t_close[ti]) : 0ull;
+    return process_ends<OBJECTS, TRACE>(S, B, O, e, k, pixel, st, [&](V3* n0, V3* n1) {
+        if (normals) {
+            *n0 = normals[0], *n1 = normals[1];
+        } else {
+            *n0 = sample_normal(S, B.terrain, B, xl, k - 1, e.lat0, e.lon0), *n1 = sample_normal(S, B.terrain, B, xl, k, e.lat1, e.lon1);
+        }
+    });
 }
 
 constexpr int MARCH_THREADS = 128;
@@ -970,6 +1005,135 @@ __global__ void __launch_bounds__(MARCH_THREADS) k_march(const __grid_constant__
         if (when == MARCH_FLAGGED_COLUMNS && B.sweep_col[xl] == 0) continue;
         march_column<OBJECTS, BRUTE, TRACE>(S, B, O, xl);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The Rectilinear generator (generators/rectilinear.rs): a rectilinear projection, so every pixel has its
+// own elevation AND azimuth -- one ray integration and one azimuth walk per pixel, nothing to cache. One
+// thread per pixel runs the reference's PathIterator (rectilinear.rs:112-186) fused with get_single_pixel:
+// per step one RK4 step (g(h) from the table in shared memory, device_paths.cuh), one DirectionalCalc walk
+// and one bilinear terrain tap (plus objects_close when the scene has objects); the normals are evaluated at
+// the hits only. The 32 lanes of a warp are 32 adjacent pixels of one row: neighbouring azimuths and the
+// same elevation to within a pixel, so their terrain taps share the 128-byte micro-tiles.
+// ---------------------------------------------------------------------------------------------
+// RectilinearGenerator::get_ray_params, rectilinear.rs:80-105 (nalgebra: Rz(yaw) Ry(pitch) Rx(roll), the
+// product accumulated column by column).
+__device__ __forceinline__ void get_ray_params(const DevScene& S, int x, int y, double* elevation, double* direction) {
+    const double width = (double)S.width;
+    const double xf = (double)(short)((short)x - (short)S.width / 2);
+    const double yf = (double)(short)((short)y - (short)S.height / 2);
+    const double z = width / 2.0 / tan(to_radians(S.fov) / 2.0);
+    double sr, cr, sp, cp, sy, cy;
+    sincos(0.0, &sr, &cr);
+    sincos(-to_radians(S.tilt), &sp, &cp);
+    sincos(to_radians(S.direction), &sy, &cy);
+    const double m[3][3] = {{cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr},
+                            {sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr},
+                            {-sp, cp * sr, cp * cr}};
+    const double v[3] = {z, xf, -yf};  // [forward, right, up]
+    double d[3];
+    for (int i = 0; i < 3; ++i) d[i] = (m[i][0] * v[0] + m[i][1] * v[1]) + m[i][2] * v[2];
+    const double n = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    for (int i = 0; i < 3; ++i) d[i] = d[i] / n;
+    *elevation = asin(d[2]);
+    *direction = atan2(d[1], d[0]);
+}
+
+constexpr int RECT_THREADS = 128;
+
+template <bool FLAT, bool OBJECTS>
+__global__ void __launch_bounds__(RECT_THREADS) k_rectilinear(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, int libm_only) {
+    __shared__ double tab_smem[ATM_FIELDS * ATM_CELLS];
+#pragma unroll 4
+    for (int i = threadIdx.x; i < ATM_FIELDS * ATM_CELLS; i += RECT_THREADS) tab_smem[i] = B.atm_cells[i];
+    __syncthreads();
+    const GSource gs{(unsigned)__cvta_generic_to_shared(tab_smem), B.atm_pieces, B.n_atm_pieces};
+    const int wl = S.x1 - S.x0;
+    const int xl = blockIdx.x * RECT_THREADS + threadIdx.x, y = blockIdx.y;
+    const bool active = xl < wl;
+    const int xx = min(xl, wl - 1);
+    const size_t pixel = (size_t)y * wl + xx;
+    double elevation, direction;
+    get_ray_params(S, S.x0 + xx, y, &elevation, &direction);
+    double cc[8];
+    direction_calc(S, to_degrees(direction), cc);  // params.model.coords_at_dist_calc(position, direction.to_degrees())
+    const double alt = *B.obs_alt;
+    const double radius = S.radius;
+    const double d = FLAT ? S.step : S.step / radius;
+    const double hd = 0.5 * d, d6 = d / 6.0;
+    const double shift = FLAT ? ATM_BASE : radius + ATM_BASE;
+    // env.cast_ray_stepper(alt, elevation, straight_rays)
+    Stepper line;
+    stepper_init(line, FLAT, radius, alt, elevation);
+    double a = line.a, b = line.b;
+    PathBase bE = path_base<FLAT>(gs.tab, shift, a), bM = path_base<FLAT>(gs.tab, shift, fma(hd, b, a)), bN = path_base<FLAT>(gs.tab, shift, fma(d, b, a));
+    const double d15 = 1.5 * d, d2 = 2.0 * d;
+
+    PixelState st;
+    init_pixel(st);
+    int consumed = 0;
+    // point 0: the observer's state over the terrain under it
+    double lat0, lon0;
+    V3 fpos0{0.0, 0.0, 0.0};
+    walk_coords(S, cc, 0.0, &lat0, &lon0, &fpos0);
+    double elev0 = elev_or_zero(B.terrain, lat0, lon0);
+    unsigned long long mask0 = OBJECTS ? objects_close(S, B, fpos0, lat0, lon0) : 0ull;
+    double ray0 = alt, len0 = 0.0;
+    RayState prev{0.0, alt};
+    if (!(0.0 > S.max_distance || alt < -1000.0)) {
+#pragma unroll 1
+        for (int k = 1; k < S.n_x; ++k) {
+            // self.ray.next(): state k
+            double x1, h1;
+            if (S.straight) {
+                const RayState nw = stepper_next(line, S.atm, FLAT, 1, radius, S.step);
+                x1 = nw.x, h1 = nw.h;
+            } else {
+                double a_new, b_new;
+                bool ok = false;
+                if (!libm_only) {
+                    ok = rk4_step_shared<FLAT>(d, hd, d6, a, b, bE, bM, bN, &a_new, &b_new) || a != a || b != b;
+                    bE = bN;
+                    bM = path_base<FLAT>(gs.tab, shift, fma(d15, b, a));
+                    bN = path_base<FLAT>(gs.tab, shift, fma(d2, b, a));
+                }
+                if (!ok) {
+                    if (libm_only) rk4_step<FLAT, 2>(S.atm, gs, radius, d, hd, d6, a, b, &a_new, &b_new);
+                    else rk4_step<FLAT, 1>(S.atm, gs, radius, d, hd, d6, a, b, &a_new, &b_new);
+                }
+                a = a_new, b = b_new;
+                x1 = B.path_x[k];
+                h1 = FLAT ? a : a - radius;
+            }
+            const double len1 = len0 + calc_dist(FLAT, radius, prev, RayState{x1, h1});
+            // the point exists unless it is past max_distance or below -1000 m (rectilinear.rs:175-177)
+            if (x1 > S.max_distance || h1 < -1000.0) break;
+            consumed = k;
+            double lat1, lon1;
+            V3 fpos1{0.0, 0.0, 0.0};
+            walk_coords(S, cc, x1, &lat1, &lon1, &fpos1);
+            const double elev1 = elev_or_zero(B.terrain, lat1, lon1);
+            const unsigned long long mask1 = OBJECTS ? objects_close(S, B, fpos1, lat1, lon1) : 0ull;
+            const double diff1 = ray0 - elev0, diff2 = h1 - elev1;
+            if (diff1 * diff2 < 0.0 || (OBJECTS && (mask0 | mask1))) {
+                const StepEnds e{lat0, lon0, elev0, ray0, prev.x, len0, lat1, lon1, elev1, h1, x1, len1, mask0 | mask1};
+                const bool finish = process_ends<OBJECTS, false>(S, B, O, e, k, pixel, st, [&](V3* n0, V3* n1) {
+                    const SampleTrig t0 = sample_trig(S, fpos0, lat0, lon0), t1 = sample_trig(S, fpos1, lat1, lon1);
+                    *n0 = find_normal(S, B.terrain, lat0, lon0, t0.sinlat, t0.coslat, t0.sinlon, t0.coslon);
+                    *n1 = find_normal(S, B.terrain, lat1, lon1, t1.sinlat, t1.coslat, t1.sinlon, t1.coslon);
+                });
+                if (finish) break;
+            }
+            lat0 = lat1, lon0 = lon1, elev0 = elev1, mask0 = mask1, fpos0 = fpos1;
+            ray0 = h1, len0 = len1;
+            prev = RayState{x1, h1};
+        }
+    }
+    write_pixel<false>(S, B, O, pixel, active, st, consumed);
+    // points the stream produced (states integrated + 1), the Rectilinear generator's count of path steps
+    unsigned long long pts = active && !(0.0 > S.max_distance || alt < -1000.0) ? (unsigned long long)consumed + 1ull : 0ull;
+    for (int o = 16; o > 0; o >>= 1) pts += __shfl_xor_sync(FULL, pts, o);
+    if ((threadIdx.x & 31) == 0 && pts) atomicAdd(B.counters + CNT_PATH_STEPS, pts);
 }
 
 // ---------------------------------------------------------------------------------------------

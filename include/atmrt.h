@@ -50,6 +50,10 @@ typedef enum atmrt_earth_model {
     ATMRT_EARTH_OBSERVER_AE = 4             /* ObserverAe{proj_radius}: radius = proj_radius            */
 } atmrt_earth_model;
 
+/* GeneratorDef (generator/mod.rs:72-78): Fast (generators/fast.rs: separable caches) or Rectilinear
+ * (generators/rectilinear.rs: one ray and one azimuth walk per pixel of a rectilinear projection). */
+typedef enum atmrt_generator { ATMRT_GENERATOR_FAST = 0, ATMRT_GENERATOR_RECTILINEAR = 1 } atmrt_generator;
+
 /* Altitude (generator/params.rs:17-30) */
 typedef enum atmrt_altitude_kind { ATMRT_ALT_ABSOLUTE = 0, ATMRT_ALT_RELATIVE = 1 } atmrt_altitude_kind;
 typedef struct atmrt_altitude {
@@ -104,7 +108,7 @@ typedef struct atmrt_params {
     double simple_max_distance; /* Coloring::Simple.max_distance = frame.max_distance */
     /* view.fog_distance: Option<f64> */
     int32_t fog_enabled;
-    int32_t _pad0;
+    int32_t generator; /* atmrt_generator: output.generator (params.rs:387-392) */
     double fog_distance;
     /* output (params.rs:394-413); x0..x1 is the column block this context renders
      * (x0 = 0, x1 = width for a single GPU). */

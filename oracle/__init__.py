@@ -147,6 +147,13 @@ def as_cartesian(earth_model, radius, lat, lon, elev, ellipsoid_b=0.0):
     return out
 
 
+def ray_params(params, x, y):
+    """RectilinearGenerator::get_ray_params: (elevation, direction) of a pixel in degrees."""
+    out = np.empty(2)
+    lib().oracle_ray_params(C.byref(params), int(x), int(y), _p(out))
+    return out[0], out[1]
+
+
 def light_dir(earth_model, radius, lat, lon, direction, zenith_deg, light_dir_deg):
     out = np.empty(3)
     lib().oracle_light_dir(int(earth_model), C.c_double(radius), C.c_double(lat), C.c_double(lon), C.c_double(direction),

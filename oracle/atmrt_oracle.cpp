@@ -871,10 +871,19 @@ TracingState interpolate(const TracingState& a, const TracingState& b, double pr
     return r;
 }
 
-// get_single_pixel, utils.rs:201-289. Returns zip iterations consumed.
-int get_single_pixel(const Scene& s, const std::vector<TerrainData>& terr, const std::vector<PathElem>& path,
-                     std::vector<TracePoint>* result, uint64_t* step_overflows) {
-    size_t n = std::min(terr.size(), path.size());
+// The stream get_single_pixel consumes: the Fast generator zips two caches (fast.rs:56-64), the Rectilinear
+// generator walks its own PathIterator per pixel (rectilinear.rs:112-186).
+struct ZipSource {
+    const std::vector<TerrainData>& terr;
+    const std::vector<PathElem>& path;
+    bool has(size_t k) const { return k < terr.size() && k < path.size(); }
+};
+
+// get_single_pixel, utils.rs:201-289. Returns iterations consumed.
+template <class Source>
+int get_single_pixel(const Scene& s, Source& src, std::vector<TracePoint>* result, uint64_t* step_overflows) {
+    auto& terr = src.terr;
+    auto& path = src.path;
     auto make = [&](size_t k, bool first) {
         TracingState t;
         t.lat = terr[k].lat;
@@ -891,7 +900,7 @@ int get_single_pixel(const Scene& s, const std::vector<TerrainData>& terr, const
     std::vector<Collision> coll;
     std::vector<std::pair<double, TracePoint>> step_result;
     int consumed = 0;
-    for (size_t k = 1; k < n; ++k) {
+    for (size_t k = 1; src.has(k); ++k) {
         consumed = (int)k;
         // old_tracing_state is always (terr[k-1], path[k-1]) -- with dist/path_len forced to 0.0 for
         // k-1 == 0 (utils.rs:207-208) -- so it is rebuilt on demand instead of being cloned per step.
@@ -939,6 +948,70 @@ int get_single_pixel(const Scene& s, const std::vector<TerrainData>& terr, const
     }
     return consumed;
 }
+
+// ------------------------------------------------------------------------------------------
+// Rectilinear generator: generators/rectilinear.rs
+// ------------------------------------------------------------------------------------------
+struct RayParams {
+    double elevation, direction;  // radians
+};
+
+// RectilinearGenerator::get_ray_params, rectilinear.rs:80-105. nalgebra's Matrix4::from_euler_angles(roll,
+// pitch, yaw) is Rz(yaw) Ry(pitch) Rx(roll); its product with a vector accumulates column by column.
+RayParams get_ray_params(const atmrt_params& p, int x, int y) {
+    double width = (double)p.width;
+    double xf = (double)(int16_t)((int16_t)x - (int16_t)p.width / 2);
+    double yf = (double)(int16_t)((int16_t)y - (int16_t)p.height / 2);
+    double z = width / 2.0 / std::tan(to_radians(p.fov) / 2.0);
+    double roll = 0.0, pitch = -to_radians(p.tilt), yaw = to_radians(p.direction);
+    double sr = std::sin(roll), cr = std::cos(roll), sp = std::sin(pitch), cp = std::cos(pitch), sy = std::sin(yaw), cy = std::cos(yaw);
+    double m[3][3] = {{cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr},
+                      {sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr},
+                      {-sp, cp * sr, cp * cr}};
+    double v[3] = {z, xf, -yf};  // [forward, right, up]
+    double d[3];
+    for (int i = 0; i < 3; ++i) d[i] = (m[i][0] * v[0] + m[i][1] * v[1]) + m[i][2] * v[2];
+    double n = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    for (int i = 0; i < 3; ++i) d[i] = d[i] / n;
+    return {std::asin(d[2]), std::atan2(d[1], d[0])};
+}
+
+// PathIterator (rectilinear.rs:112-186) as a lazily materialised stream: point k is the stepper's state k
+// with the terrain under it; the stream ends at the first state past max_distance or below -1000 m.
+struct PathIteratorSource {
+    const Scene& s;
+    Stepper ray;
+    DirCalc dist_calc;
+    RayState ray_state;
+    double path_length = 0.0;
+    bool exhausted = false;
+    std::vector<TerrainData> terr;
+    std::vector<PathElem> path;
+
+    PathIteratorSource(const Scene& scene, RayParams rp)
+        : s(scene),
+          ray(&scene.env, altitude_abs(scene.p.altitude, scene.terrain, scene.p.latitude, scene.p.longitude), rp.elevation, scene.p.straight_rays != 0),
+          dist_calc(coords_at_dist_calc(scene.model, scene.p.latitude, scene.p.longitude, to_degrees(rp.direction))) {
+        ray.set_step_size(scene.p.simulation_step);
+        ray_state = {0.0, altitude_abs(scene.p.altitude, scene.terrain, scene.p.latitude, scene.p.longitude), 0.0};
+    }
+    bool next() {  // Iterator::next, rectilinear.rs:173-185
+        PathElem elem{ray_state.x, ray_state.h, path_length};
+        if (elem.dist > s.p.max_distance || elem.elev < -1000.0) return false;
+        double lat, lon;
+        coords_at_dist(dist_calc, elem.dist, &lat, &lon);
+        terr.push_back(terrain_data_from(s, lat, lon));
+        path.push_back(elem);
+        RayState nw = ray.next();
+        path_length += calc_dist(s.env, ray_state, nw);
+        ray_state = nw;
+        return true;
+    }
+    bool has(size_t k) {
+        while (!exhausted && terr.size() <= k) exhausted = !next();
+        return k < terr.size();
+    }
+};
 
 // ------------------------------------------------------------------------------------------
 // Colouring: coloring/shading.rs, coloring/simple.rs ; compositing: renderer/mod.rs:367-414
@@ -1133,23 +1206,36 @@ int oracle_render(const atmrt_params* p, const atmrt_tile_desc* tiles, int ntile
     if (stride_y < 1) stride_y = 1;
     const int x0 = p->x0, x1 = p->x1, H = p->height;
     const int cols = (x1 - x0 + stride_x - 1) / stride_x, rows = (H + stride_y - 1) / stride_y;
+    const bool rectilinear = p->generator == ATMRT_GENERATOR_RECTILINEAR;
     double t0 = now_s();
     std::vector<std::vector<TerrainData>> terrain_cache(cols);
+    if (!rectilinear) {
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int c = 0; c < cols; ++c) terrain_cache[c] = gen_terrain_cache(s, get_ray_dir(*p, x0 + c * stride_x));
+        for (int c = 0; c < cols; ++c) terrain_cache[c] = gen_terrain_cache(s, get_ray_dir(*p, x0 + c * stride_x));
+    }
     double t1 = now_s();
     std::vector<std::vector<PathElem>> path_cache(rows);
+    if (!rectilinear) {
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int r = 0; r < rows; ++r) path_cache[r] = gen_path_cache(s, get_ray_elev(*p, r * stride_y));
+        for (int r = 0; r < rows; ++r) path_cache[r] = gen_path_cache(s, get_ray_elev(*p, r * stride_y));
+    }
     double t2 = now_s();
     uint64_t ray_steps = 0, ntp = 0, nhit = 0, overflows = 0, path_steps = 0;
-    for (int r = 0; r < rows; ++r) path_steps += path_cache[r].size() - 1;
-#pragma omp parallel for schedule(dynamic, 16) collapse(2) reduction(+ : ray_steps, ntp, nhit, overflows)
+    for (int r = 0; r < rows && !rectilinear; ++r) path_steps += path_cache[r].size() - 1;
+#pragma omp parallel for schedule(dynamic, 16) collapse(2) reduction(+ : ray_steps, ntp, nhit, overflows, path_steps)
     for (int r = 0; r < rows; ++r) {
         for (int c = 0; c < cols; ++c) {
             std::vector<TracePoint> tps;
             uint64_t ov = 0;
-            int consumed = get_single_pixel(s, terrain_cache[c], path_cache[r], &tps, &ov);
+            int consumed;
+            if (rectilinear) {  // RectilinearGenerator::gen_pixel, rectilinear.rs:107-124
+                PathIteratorSource it(s, get_ray_params(*p, x0 + c * stride_x, r * stride_y));
+                consumed = get_single_pixel(s, it, &tps, &ov);
+                path_steps += it.path.size();
+            } else {
+                ZipSource zip{terrain_cache[c], path_cache[r]};
+                consumed = get_single_pixel(s, zip, &tps, &ov);
+            }
             size_t idx = (size_t)r * cols + c;
             ray_steps += (uint64_t)consumed;
             ntp += tps.size();
@@ -1190,7 +1276,7 @@ int oracle_render(const atmrt_params* p, const atmrt_tile_desc* tiles, int ntile
         stats->trace_points = ntp;
         stats->pixels_hit = nhit;
         stats->step_overflows = overflows;
-        stats->n_terrain = cols ? (int)terrain_cache[0].size() : 0;
+        stats->n_terrain = cols && !rectilinear ? (int)terrain_cache[0].size() : 0;
         stats->terrain_samples = (uint64_t)cols * (uint64_t)stats->n_terrain;
         stats->path_steps = path_steps;
         int mx = 0;
@@ -1309,6 +1395,13 @@ int oracle_ray_path(const atmrt_atmosphere_def* def, double wavelength, int flat
         x[i] = s.x;
         h[i] = s.h;
     }
+    return 0;
+}
+
+// RectilinearGenerator::get_ray_params (rectilinear.rs:80-105): elevation and direction of a pixel, degrees
+int oracle_ray_params(const atmrt_params* p, int x, int y, double* out2) {
+    RayParams r = get_ray_params(*p, x, y);
+    out2[0] = to_degrees(r.elevation), out2[1] = to_degrees(r.direction);
     return 0;
 }
 

@@ -514,3 +514,47 @@ def test_rays_leaving_the_atmosphere_model(ctx, oracle_lib):
     np.testing.assert_allclose(g["dist"], w["dist"][:n], rtol=1e-14)
     ok = ~np.isnan(g["elev"])
     np.testing.assert_allclose(g["elev"][ok], w["elev"][:n][ok], rtol=1e-9, atol=PATH_ATOL)
+
+
+# ---------------------------------------------------------------------------------------------
+# the Rectilinear generator
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,scale", [("c1", 0.12), ("c2", 0.04), ("c3_flat", 0.03), ("c4", 0.04), ("c3_wgs84", 0.02), ("c3_azeq", 0.02)])
+def test_rectilinear_generator_matches_oracle(ctx, oracle_lib, name, scale):
+    """generators/rectilinear.rs: one ray and one azimuth walk per pixel of a rectilinear projection."""
+    p, terrain, objects, textures = scene(name, scale)
+    p.generator = abi.GENERATOR_RECTILINEAR
+    p.tilt = -1.5  # look slightly down so that most of the frame hits the terrain
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects(objects, textures)
+    got = ctx.render()
+    want = oracle_lib.render(p, terrain.tiles, objects, textures)
+    rep = compare_render(got, want, "rect-" + name, finish_moves_frac=0.01 if objects else 0.002)
+    gs, ws = got["stats"], want["stats"]
+    assert gs["pixels_hit"] > 0.3 * p.width * p.height
+    moved = rep["silhouette_flips"] + rep["finish_step_moves"]
+    if moved == 0:
+        assert gs["ray_steps"] == ws["ray_steps"] and gs["trace_points"] == ws["trace_points"] and gs["path_steps"] == ws["path_steps"]
+        np.testing.assert_array_equal(got["steps"], want["steps"])
+    # the caches of the Fast generator do not exist here
+    with pytest.raises(runtime.AtmrtError):
+        ctx.path(0)
+
+
+def test_rectilinear_centre_pixel_is_the_fast_generators(ctx):
+    """The centre pixel of both projections is the same ray along the same azimuth."""
+    p, terrain, _, _ = scene("c2", 0.05)
+    p.tilt = -2.0
+    ctx.set_terrain(terrain)
+    ctx.set_objects([])
+    ctx.set_params(p)
+    fast = ctx.render()
+    p.generator = abi.GENERATOR_RECTILINEAR
+    ctx.set_params(p)
+    rect = ctx.render()
+    cy, cx = p.height // 2, p.width // 2
+    f, r = fast["meta"][cy, cx], rect["meta"][cy, cx]
+    for key in ("lat", "lon", "elevation", "distance"):
+        assert abs(f[key] - r[key]) <= 1e-6 * max(1.0, abs(f[key])), key
+    assert abs(int(fast["steps"][cy, cx]) - int(rect["steps"][cy, cx])) <= 1
