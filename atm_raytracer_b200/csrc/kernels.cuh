@@ -1042,7 +1042,7 @@ __device__ __forceinline__ void get_ray_params(const DevScene& S, int x, int y, 
 constexpr int RECT_THREADS = 128;
 
 template <bool FLAT, bool OBJECTS>
-__global__ void __launch_bounds__(RECT_THREADS) k_rectilinear(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, int libm_only) {
+__global__ void __launch_bounds__(RECT_THREADS, 4) k_rectilinear(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, int libm_only) {
     __shared__ double tab_smem[ATM_FIELDS * ATM_CELLS];
 #pragma unroll 4
     for (int i = threadIdx.x; i < ATM_FIELDS * ATM_CELLS; i += RECT_THREADS) tab_smem[i] = B.atm_cells[i];

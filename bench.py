@@ -50,15 +50,18 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=1.0, help="image scale (1.0 = the BASELINE size; anything else is a dry run)")
     ap.add_argument("--march-mode", type=int, default=0, help="0 product default, 1 brute force (every step), 2 hierarchical march always")
     ap.add_argument("--cpu-stride", type=int, default=0, help="column/row stride of the bounded CPU sample (0 = auto)")
+    ap.add_argument("--generator", default="Fast", choices=["Fast", "Rectilinear"],
+                    help="output.generator of the workload (diagnosis; the BASELINE configs use the default Fast generator)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
-def build_workload(name, scale, with_posts):
+def build_workload(name, scale, with_posts, generator="Fast"):
     from atm_raytracer_b200 import config, runtime, scenes
 
     cfg, grid = scenes.make_scene(name, scale=scale)
+    cfg["output"]["generator"] = generator
     params = config.into_params(cfg)
     objects, textures = config.lower_objects(cfg)
     lat0, lon0, nlat, nlon = grid
@@ -81,8 +84,9 @@ def describe(name, params, terrain, extra=None):
                     f"{'straight' if params.straight_rays else 'refracted (US-76)'} rays, "
                     f"{'FlatDistorted' if params.earth_model == 1 else 'Spherical R=%g km' % (params.radius / 1e3)}, "
                     f"{len(terrain.tiles)} synthetic DTED L1 tiles, max_distance {params.max_distance / 1e3:g} km, step {params.simulation_step:g} m",
-        "generator": "Fast",
-        "l2_policy": "inputs larger than L2 (profile caches >> 126 MB are rewritten and re-read every step)",
+        "generator": "Rectilinear" if params.generator == 1 else "Fast",
+        "l2_policy": "inputs larger than L2 (profile caches >> 126 MB are rewritten and re-read every step)" if params.generator == 0
+                     else "L2 flushed by the render itself only when the terrain exceeds it; the Rectilinear generator keeps no caches",
     }
     d.update(extra or {})
     return d
@@ -176,6 +180,8 @@ def auto_stride(params):
     for s in (1, 2, 4, 8, 16, 32, 64, 128):
         cols = (params.x1 - params.x0) / s
         est = cols * n_t * 2.5e-6 / cores + (cols * params.height / s) * n_t * 2.0e-9 / cores
+        if params.generator == 1:  # Rectilinear: one RK4 step + one TerrainData per ray step (~0.7 us per step per core measured)
+            est = (cols * params.height / s) * n_t * 0.7e-6 / cores
         if est < 12.0:
             return s
     return 128
@@ -185,7 +191,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg, params, terrain, objects, textures = build_workload(args.workload, args.scale, True)
+    cfg, params, terrain, objects, textures = build_workload(args.workload, args.scale, True, args.generator)
     stride = args.cpu_stride or auto_stride(params)
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_sample(params, terrain, objects, textures, stride * 2)
@@ -237,7 +243,7 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    cfg, params, terrain, objects, textures = build_workload(args.workload, args.scale, rank == 0)
+    cfg, params, terrain, objects, textures = build_workload(args.workload, args.scale, rank == 0, args.generator)
     my = parallel.shard_params(params, rank, world)
     wl, H, W = my.x1 - my.x0, params.height, params.width
 
@@ -351,7 +357,9 @@ def run_b200(args):
     units = {"terrain": wl * n_t, "paths": st["path_steps"] / world if world > 1 else st["path_steps"],
              "march": st["ray_steps"] / world}
     stage_ms = {"terrain": ms_a, "paths": ms_b, "march": ms_c}
-    if args.march_mode == 0 and params.terrain_alpha == 1.0 and not objects:
+    if params.generator == 1:
+        STAGE_UNITS["march"] = ("k_rectilinear", "ray steps")  # one kernel: stepper + walk + tap + get_single_pixel per pixel
+    elif args.march_mode == 0 and params.terrain_alpha == 1.0 and not objects:
         STAGE_UNITS["march"] = ("k_sweep+k_sweep_shade", "ray steps")  # opaque terrain, no objects: the horizon sweep
     dom = max(stage_ms, key=stage_ms.get)
     roofs = {k: roofline(k, stage_ms[k], units[k], params, fp, args) for k in stage_ms}
@@ -424,6 +432,9 @@ def ncu_traffic(kernel, args):
 def fp64_instr_per_unit(stage, params):
     # DESIGN.md, "Kernels and rooflines": arithmetic the reference performs per unit, transcendentals
     # costed at the instruction count of CUDA's f64 libm paths.
+    if stage == "march" and params.generator == 1:
+        # Rectilinear: every ray step is one RK4 step + one TerrainData::from_lat_lon + the sign test
+        return (25.0 if params.straight_rays else 2600.0) + (1500.0 if params.earth_model == 0 else 700.0) + 3.0
     if stage == "march":
         return 3.0  # 1 DADD (diff), 1 DMUL (product), 1 DSETP (sign test) per ray step (utils.rs:220-222)
     if stage == "paths":
@@ -432,6 +443,8 @@ def fp64_instr_per_unit(stage, params):
 
 
 def hbm_bytes_per_unit(stage, params):
+    if stage == "march" and params.generator == 1:
+        return 40.0  # five bilinear taps of 4 i16 posts per ray step as the reference computes it (8 B here: normals at hits only)
     if stage == "march":
         return 8.0 * (1.0 / params.height + 1.0 / max(1, params.x1 - params.x0))
     if stage == "paths":
