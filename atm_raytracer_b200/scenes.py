@@ -61,6 +61,11 @@ EARTH_VARIANTS = {
 
 
 def make_scene(name, scale=1.0):
+    if name.startswith("rect_"):  # the same scene through the Rectilinear generator, looking slightly down
+        c, grid = make_scene(name[5:], scale)
+        c["output"]["generator"] = "Rectilinear"
+        c["view"]["frame"]["tilt"] = -1.5
+        return c, grid
     c = _base()
     out, view = c["output"], c["view"]
 

@@ -18,7 +18,9 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-CASES = {"c1": 0.075, "c2": 0.025, "c3_flat": 0.0125, "c3_sph": 0.0125, "c4": 0.025}
+CASES = {"c1": 0.075, "c2": 0.025, "c3_flat": 0.0125, "c3_sph": 0.0125, "c4": 0.025,
+         # the other earth models and the Rectilinear generator
+         "c3_wgs84": 0.0125, "c3_azeq": 0.0125, "c4_obsae": 0.02, "rect_c2": 0.02, "rect_c4": 0.02}
 
 
 def tiles_digest(terrain):
@@ -32,7 +34,10 @@ def main():
     import oracle
     from conftest import scene
 
+    only = sys.argv[1:]
     for name, scale in CASES.items():
+        if only and name not in only:
+            continue
         p, terrain, objects, textures = scene(name, scale)
         r = oracle.render(p, terrain.tiles, objects, textures, max_points=12)
         cols = [0, p.width // 2, p.width - 1]

@@ -10,7 +10,7 @@ import pytest
 from conftest import scene
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CASES = ["c1", "c2", "c3_flat", "c3_sph", "c4"]
+CASES = ["c1", "c2", "c3_flat", "c3_sph", "c4", "c3_wgs84", "c3_azeq", "c4_obsae", "rect_c2", "rect_c4"]
 
 
 def load(name):
