@@ -59,6 +59,8 @@ def test_cuda_matches_golden(ctx, name):
     got = ctx.render()
     want = {"rgb": g["rgb"], "meta": g["meta"], "steps": g["steps"]}
     compare_render(got, want, f"golden-{name}", finish_moves_frac=0.01 if objects else 0.001)
+    if name.startswith("rect_"):  # the Rectilinear generator keeps no caches to probe
+        return
     for i, x in enumerate(g["cols"]):
         t = ctx.terrain_profile(int(x))
         np.testing.assert_allclose(t["lat"], g["t_lat"][i], rtol=1e-13)
