@@ -1341,7 +1341,7 @@ __global__ void __launch_bounds__(32 * SHADE_COLS, 2) k_sweep_shade(const __grid
     s_meta[lane][w * 4 + 0] = st.m_lat, s_meta[lane][w * 4 + 1] = st.m_lon, s_meta[lane][w * 4 + 2] = st.m_elev, s_meta[lane][w * 4 + 3] = st.m_dist;
     s_steps[lane][w] = consumed;
     count_pixel(B, active, st, consumed);
-    __syncthreads();
+    const bool all_cols = __syncthreads_and(col_ok ? 1 : 0) != 0;  // also the barrier between staging and write-out
     const int rows = min(32, S.height - y0);
     // Write-out with the lanes along x: thread t handles pixel (row t / 16, column t % 16) of the tile -- its
     // 32 bytes of metadata as two 16-byte stores, so a warp writes two 512-byte row segments -- and, for the
@@ -1357,9 +1357,7 @@ __global__ void __launch_bounds__(32 * SHADE_COLS, 2) k_sweep_shade(const __grid
         if (O.steps && live) O.steps[(size_t)(y0 + r) * wl + c0 + c] = s_steps[r][c];
     }
     if (O.rgb) {
-        bool whole = c0 + SHADE_COLS <= wl && (wl & 3) == 0;  // every row segment of the tile is 48 aligned bytes
-        for (int c = 0; c < SHADE_COLS; ++c) whole = whole && !s_skip[c];
-        if (whole) {
+        if (all_cols && (wl & 3) == 0) {  // every row segment of the tile is 48 aligned bytes
             constexpr int WORDS = SHADE_COLS * 3 / 4;
             if ((int)threadIdx.x < rows * WORDS) {
                 const int r = threadIdx.x / WORDS, q = threadIdx.x % WORDS;
