@@ -3,6 +3,7 @@
 // One context per GPU. A render is three stages on two streams (terrain profile || ray paths, then
 // the march); all buffers live in HBM and are reused between renders. There is no CPU fallback:
 // without a CUDA device every entry point fails with ATMRT_ERR_NO_DEVICE / ATMRT_ERR_CUDA.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -69,6 +70,9 @@ struct atmrt_ctx {
     int path_k_far = 0;
     std::vector<double> atm_cells;  // g(h) table of the ray-path stage, [ATM_FIELDS][ATM_CELLS]
     std::vector<DevGPiece> atm_pieces;  // its cells that hold the start of a temperature function
+    std::vector<double> atm_bnd;           // sorted altitudes where g is not smooth: the starts of the temperature functions, the table's ends
+    std::vector<unsigned char> atm_first;  // per table cell: index of the first of them at or above the cell's lower edge
+    DevBuf d_atm_aux;
     int atm_cells_served = 0;
     bool atm_table_valid = false;
     atmrt_atmosphere_def atm_table_def{};
@@ -576,6 +580,7 @@ int prepare_render(atmrt_ctx* ctx) {
     (void)h;
     e |= ensure(ctx, ctx->d_obs, f8);
     e |= ensure(ctx, ctx->d_atm_cells, f8 * ATM_FIELDS * ATM_CELLS + sizeof(DevGPiece) * ATM_MAX_PIECES);
+    e |= ensure(ctx, ctx->d_atm_aux, f8 * ATM_MAX_BND + ATM_CELLS);
     e |= ensure(ctx, ctx->d_sweep_flags, 16);
     if (!rect) {
         e |= ensure(ctx, ctx->d_sweep_col, wl);
@@ -584,6 +589,22 @@ int prepare_render(atmrt_ctx* ctx) {
     // the g(h) table depends on the atmosphere and the wavelength only: rebuilt when they change
     if (!ctx->atm_table_valid || memcmp(&ctx->atm_table_def, &p.atmosphere, sizeof(p.atmosphere)) != 0 || ctx->atm_table_wavelength != p.wavelength) {
         build_g_table(S.atm, p.wavelength, ctx->atm_cells, ctx->atm_pieces, &ctx->atm_cells_served);
+        {  // where a macro step of the ray-path stage must not reach across (kernels.cuh: k_ray_paths_macro)
+            std::vector<double>& bnd = ctx->atm_bnd;
+            bnd.clear();
+            bnd.push_back(ATM_BASE - 0.5 * ATM_CELL);
+            bnd.push_back(ATM_BASE + (ATM_CELLS - 0.5) * ATM_CELL);
+            for (int i = 1; i < S.atm.n; ++i) bnd.push_back(S.atm.layer[i].start);
+            std::sort(bnd.begin(), bnd.end());
+            bnd.resize(ATM_MAX_BND, std::numeric_limits<double>::infinity());
+            ctx->atm_first.assign(ATM_CELLS, 0);
+            for (int j = 0; j < ATM_CELLS; ++j) {
+                const double lower = ATM_BASE + ((double)j - 0.5) * ATM_CELL;
+                int t = 0;
+                while (bnd[t] < lower) ++t;
+                ctx->atm_first[j] = (unsigned char)t;
+            }
+        }
         ctx->atm_table_def = p.atmosphere;
         ctx->atm_table_wavelength = p.wavelength;
         ctx->atm_table_valid = true;
@@ -618,6 +639,8 @@ int prepare_render(atmrt_ctx* ctx) {
     B.atm_cells = (const double*)ctx->d_atm_cells.p;
     B.atm_pieces = (const DevGPiece*)((const char*)ctx->d_atm_cells.p + f8 * ATM_FIELDS * ATM_CELLS);
     B.n_atm_pieces = (int)ctx->atm_pieces.size();
+    B.atm_bnd = (const double*)ctx->d_atm_aux.p;
+    B.atm_first = (const unsigned char*)ctx->d_atm_aux.p + f8 * ATM_MAX_BND;
     B.sweep_flags = (unsigned*)ctx->d_sweep_flags.p;
     B.sweep_col = (unsigned char*)ctx->d_sweep_col.p;
     B.sweep_hit = (int*)ctx->d_sweep_hit.p;
@@ -632,6 +655,8 @@ int upload_scene_inputs(atmrt_ctx* ctx, cudaStream_t s) {
     if (!ctx->atm_pieces.empty())
         CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->d_atm_cells.p + sizeof(double) * ATM_FIELDS * ATM_CELLS, ctx->atm_pieces.data(),
                                       sizeof(DevGPiece) * ctx->atm_pieces.size(), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_atm_aux.p, ctx->atm_bnd.data(), sizeof(double) * ATM_MAX_BND, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->d_atm_aux.p + sizeof(double) * ATM_MAX_BND, ctx->atm_first.data(), ATM_CELLS, cudaMemcpyHostToDevice, s));
     if (S.nobjects > 0) {
         std::vector<DevObject> host(S.nobjects);
         for (int i = 0; i < S.nobjects; ++i) {
@@ -737,10 +762,12 @@ int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main) {
             k_ray_paths_straight<<<(h + 127) / 128, 128, 0, ctx->s_b>>>(S, B);
         } else if (S.flat) {
             if (ctx->path_mode == 1) k_ray_paths<true, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
-            else k_ray_paths<true, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
+            else if (ctx->path_mode == 2) k_ray_paths<true, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
+            else k_ray_paths_macro<true><<<(h + 2 * PATH_ROWS - 1) / (2 * PATH_ROWS), 64, 0, ctx->s_b>>>(S, B);
         } else {
             if (ctx->path_mode == 1) k_ray_paths<false, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
-            else k_ray_paths<false, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
+            else if (ctx->path_mode == 2) k_ray_paths<false, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
+            else k_ray_paths_macro<false><<<(h + 2 * PATH_ROWS - 1) / (2 * PATH_ROWS), 64, 0, ctx->s_b>>>(S, B);
         }
         ctx->launches++;
     }
@@ -916,7 +943,7 @@ void atmrt_destroy(atmrt_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_objects_in, &ctx->d_objects, &ctx->d_dist, &ctx->d_colcalc, &ctx->d_tlat, &ctx->d_tlon, &ctx->d_telev,
                       &ctx->d_tclose, &ctx->d_pdist, &ctx->d_pelev, &ctx->d_plen, &ctx->d_pn,
                       &ctx->d_tmin1, &ctx->d_tmax1, &ctx->d_tmin2, &ctx->d_tmax2, &ctx->d_tmin3, &ctx->d_tmax3, &ctx->d_close1, &ctx->d_close2, &ctx->d_close3, &ctx->d_rmin1, &ctx->d_rmin3, &ctx->d_rmax3,
-                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_sweep_flags, &ctx->d_sweep_col, &ctx->d_sweep_hit, &ctx->d_stage, &ctx->d_rgb, &ctx->d_meta,
+                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_sweep_flags, &ctx->d_sweep_col, &ctx->d_sweep_hit, &ctx->d_stage, &ctx->d_atm_aux, &ctx->d_rgb, &ctx->d_meta,
                       &ctx->d_steps, &ctx->d_points, &ctx->d_counts, &ctx->d_probe_a, &ctx->d_probe_b, &ctx->d_probe_c, &ctx->d_probe_d};
     for (DevBuf* b : bufs) release(*b);
     for (DevBuf& b : ctx->textures) release(b);
@@ -1101,7 +1128,7 @@ int atmrt_set_march_mode(atmrt_ctx* ctx, int mode) {
 // Tuning hook for Stage B: image rows integrated per warp (1..32).
 int atmrt_set_path_mode(atmrt_ctx* ctx, int mode) {
     if (!ctx) return ATMRT_ERR_INVALID;
-    ctx->path_mode = mode == 1 ? 1 : 0;
+    ctx->path_mode = mode == 1 || mode == 2 ? mode : 0;
     return 0;
 }
 

@@ -76,6 +76,8 @@ struct DevBuffers {
     const double* atm_cells;  // g(h) table of the ray-path stage (device_paths.cuh): [ATM_FIELDS][ATM_CELLS]
     const DevGPiece* atm_pieces;  // its cells that hold the start of a temperature function, piecewise
     int n_atm_pieces;
+    const double* atm_bnd;           // sorted altitudes where g is not smooth (k_ray_paths_macro), +inf padded
+    const unsigned char* atm_first;  // per table cell: index of the first of them at or above the cell's lower edge
 };
 
 enum Counter { CNT_RAY_STEPS = 0, CNT_TRACE_POINTS, CNT_PIXELS_HIT, CNT_OVERFLOWS, CNT_PATH_STEPS, CNT_COUNT };
@@ -507,6 +509,154 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
     }
 #undef ATMRT_PATH_OUTPUTS
     if (writer) {
+        B.p_n[y] = n;
+        atomicAdd(B.counters + CNT_PATH_STEPS, (unsigned long long)(n - 1));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage B with macro steps. The ray equation is smooth wherever g(h) is -- everywhere except at the starts
+// of the temperature functions, where g jumps -- and there classical RK4 with a 25 m step is converged far
+// below f64 resolution of the path: integrating the same equation with ONE RK4 step of 8 x 25 m lands on the
+// same state to 3e-11 m (scratch measurement in DESIGN.md section 4.B; the local error of the long step is
+// 1e-16 m), and the seven states in between follow from the cubic Hermite interpolant of the two ends (error
+// < 1e-12 m). At a start of a temperature function the reference's result DOES depend on how its 25 m steps
+// straddle the jump (by millimetres), so there the kernel takes the reference's own single steps: a macro
+// step is taken only when no start lies in the altitude span it covers (exact test against the sorted
+// starts), single steps otherwise. The chain is 8x shorter where it matters, and the eight states of a
+// macro step are eight independent outputs: a warp is 4 rows x 8 sub-lanes (lane = 4 j + row), every
+// sub-lane integrates the row's macro step redundantly (identical values, no exchange), evaluates ITS
+// state from the interpolant, its calc_dist segment, takes part in a prefix sum for path_length and stores
+// its cache entry -- the warp's stores are 256 contiguous bytes per plane.
+// ---------------------------------------------------------------------------------------------
+constexpr int MACRO = 8;
+constexpr int ATM_MAX_BND = ATMRT_MAX_ATM_FUNCTIONS + 4;
+
+template <bool FLAT>
+__global__ void __launch_bounds__(64) k_ray_paths_macro(const __grid_constant__ DevScene S, DevBuffers B) {
+    __shared__ double tab_smem[ATM_FIELDS * ATM_CELLS];
+    __shared__ double s_bnd[ATM_MAX_BND];          // sorted altitudes where g is not smooth (+inf padded)
+    __shared__ unsigned char s_first[ATM_CELLS];   // per cell: index of the first of them at or above the cell's lower edge
+#pragma unroll 4
+    for (int i = threadIdx.x; i < ATM_FIELDS * ATM_CELLS; i += 64) tab_smem[i] = B.atm_cells[i];
+    for (int i = threadIdx.x; i < ATM_CELLS; i += 64) s_first[i] = B.atm_first[i];
+    if (threadIdx.x < ATM_MAX_BND) s_bnd[threadIdx.x] = B.atm_bnd[threadIdx.x];
+    __syncthreads();
+    const GSource gs{(unsigned)__cvta_generic_to_shared(tab_smem), B.atm_pieces, B.n_atm_pieces};
+    const int lane = threadIdx.x & 31, rr = lane & 3, j = lane >> 2;
+    const int y_raw = (blockIdx.x * 2 + (threadIdx.x >> 5)) * PATH_ROWS + rr;
+    const int y = min(y_raw, S.height - 1);
+    const bool writer = y_raw < S.height;
+    const double alt = *B.obs_alt;
+    const double radius = S.radius, off = FLAT ? 0.0 : radius;
+    const double d = FLAT ? S.step : S.step / radius;
+    const double hd = 0.5 * d, d6 = d / 6.0;
+    const double D = (double)MACRO * d, hD = 0.5 * D, D6 = D / 6.0;
+    const double shift = FLAT ? ATM_BASE : radius + ATM_BASE;
+    const double d15 = 1.5 * d, d2 = 2.0 * d;
+    const int n_t = S.n_t, k_far = S.path_k_far;
+    double* const o_elev = B.p_elev + path_index(n_t, 0, y);
+    double* const o_len = B.p_len + path_index(n_t, 0, y);
+    const double* __restrict__ dxr = B.path_dxr;
+    // the cubic Hermite basis at this sub-lane's state, s = (j + 1) / 8
+    const double sj = (double)(j + 1) * (1.0 / MACRO);
+    const double h01 = sj * sj * (3.0 - 2.0 * sj), h10 = sj * (sj - 1.0) * (sj - 1.0), h11 = sj * sj * (sj - 1.0);
+    const unsigned rowbits = 0x11111111u << rr;  // this row's sub-lanes in a ballot
+
+    double a = FLAT ? alt : radius + alt;
+    double b = FLAT ? tan(to_radians(get_ray_elev(S, y))) : a * tan(to_radians(get_ray_elev(S, y)));
+    PathBase bE{0.0, 0.0, 0.0, 0.0}, bM = bE, bN = bE;
+    bool bases_valid = false;
+    // element 0: (alt, 0)
+    if (writer && j == 0) o_elev[0] = alt, o_len[0] = 0.0;
+    double h_e = alt;           // altitude of element e
+    double path_length = 0.0;   // of element e
+    bool done_c = false;        // an element <= e - 1 is past max_distance or below -1000 m (utils.rs:167-170)
+    bool trig_e = alt < -1000.0 || 0 >= k_far;  // ... element e is
+    int n = 1;
+    int e = 0;
+#pragma unroll 1
+    while (e < n_t - 1) {
+        if (__all_sync(FULL, done_c)) break;
+        const bool still = done_c || a != a;  // complete (it stops moving) or NaN (NaN in, NaN out): nothing to integrate
+        const bool idle = __all_sync(FULL, still);
+        // may this step be a macro step? no start of a temperature function in the altitudes it spans
+        bool macro = e + MACRO <= n_t - 1;
+        if (macro && !idle) {
+            const double a_end = fma(D, b, a);
+            const double lo = fmin(a, a_end) - off - 1.0, hi = fmax(a, a_end) - off + 1.0;
+            const int cell = min(max((int)floor((lo - (ATM_BASE - 0.5 * ATM_CELL)) * (1.0 / ATM_CELL)), 0), ATM_CELLS - 1);
+            int t = s_first[cell];
+            while (s_bnd[t] < lo) ++t;
+            const bool unsafe = !still && !(s_bnd[t] > hi);  // (NaN spans are not safe either)
+            macro = !__any_sync(FULL, unsafe);
+        }
+        double a1 = a, b1 = b;
+        if (macro && !idle) {
+            const bool ok = rk4_step<FLAT, 0>(S.atm, gs, radius, D, hD, D6, a, b, &a1, &b1) || still;
+            macro = __all_sync(FULL, ok);  // a cell the table does not serve: the reference's single steps handle it
+        }
+        int m;
+        bool valid;
+        double a_q;  // this sub-lane's state
+        if (macro) {
+            m = MACRO;
+            valid = true;
+            a_q = j == MACRO - 1 ? a1 : a + fma(h01, a1 - a, D * fma(h10, b, h11 * b1));
+            if (still) a_q = a, a1 = a, b1 = b;
+            bases_valid = false;
+        } else {
+            m = 1;
+            valid = j == 0;
+            if (!bases_valid) {
+                bE = path_base<FLAT>(gs.tab, shift, a), bM = path_base<FLAT>(gs.tab, shift, fma(hd, b, a)), bN = path_base<FLAT>(gs.tab, shift, fma(d, b, a));
+                bases_valid = true;
+            }
+            const bool ok = rk4_step_shared<FLAT>(d, hd, d6, a, b, bE, bM, bN, &a1, &b1) || still;
+            bE = bN;
+            bM = path_base<FLAT>(gs.tab, shift, fma(d15, b, a));
+            bN = path_base<FLAT>(gs.tab, shift, fma(d2, b, a));
+            if (!ok) rk4_step<FLAT, 1>(S.atm, gs, radius, d, hd, d6, a, b, &a1, &b1);  // rare: an altitude the table does not serve
+            if (still) a1 = a, b1 = b;
+            a_q = a1;
+        }
+        // this sub-lane's element q = e + j + 1: calc_dist from the element before it, path_length by prefix sum
+        const int q = min(e + j + 1, n_t - 1);
+        const double h_q = FLAT ? a_q : a_q - radius;
+        const double h_up = __shfl_up_sync(FULL, h_q, 4);
+        const double h_p = j == 0 ? h_e : h_up;
+        double dx = dxr[q];
+        if (!FLAT) dx = dx * ((h_q + h_p) * 0.5 + radius);
+        const double dh = h_q - h_p;
+        double acc = valid ? sqrt_nr(dx * dx + dh * dh) : 0.0;
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(FULL, acc, o);
+            if (lane >= o) acc += up;
+        }
+        const double len_q = path_length + acc;
+        // termination: element q is kept unless an element <= q - 2 is past max_distance or below -1000 m
+        const bool trig_q = valid && (q >= k_far || h_q < -1000.0);
+        const unsigned trig = (__ballot_sync(FULL, trig_q) & rowbits) >> rr;  // bit 4 j' = sub-lane j'
+        const bool earlier = done_c || (j >= 1 && trig_e) || (j >= 2 && (trig & ((1u << (4 * (j - 1))) - 1u)) != 0u);
+        const bool emit = valid && writer && !earlier;
+        stg_if(o_elev + (size_t)q * PATH_ROWS, h_q, emit);
+        stg_if(o_len + (size_t)q * PATH_ROWS, len_q, emit);
+        n = emit ? q + 1 : n;
+        // carry to element e + m
+        const int last = rr + 4 * (m - 1);
+        const unsigned before_last = m == 1 ? 0u : (trig & ((1u << (4 * (m - 1))) - 1u));
+        done_c = done_c || trig_e || before_last != 0u;
+        trig_e = ((trig >> (4 * (m - 1))) & 1u) != 0u;
+        path_length = __shfl_sync(FULL, len_q, last);
+        h_e = __shfl_sync(FULL, h_q, last);
+        a = a1, b = b1;
+        e += m;
+    }
+    n = max(n, __shfl_xor_sync(FULL, n, 4));
+    n = max(n, __shfl_xor_sync(FULL, n, 8));
+    n = max(n, __shfl_xor_sync(FULL, n, 16));
+    if (writer && j == 0) {
         B.p_n[y] = n;
         atomicAdd(B.counters + CNT_PATH_STEPS, (unsigned long long)(n - 1));
     }

@@ -236,8 +236,10 @@ int atmrt_render_trace(atmrt_ctx* ctx, atmrt_trace_point* points, int32_t* count
  * step like the reference loop (validation); 2 = hierarchical march always (validation of the sweep).
  * All three produce identical images. */
 int atmrt_set_march_mode(atmrt_ctx* ctx, int mode);
-/* Ray-path stage: 0 (default) g(h) from the table with libm for unserved altitudes, 1 every evaluation
- * through libm, op for op the oracle's arithmetic (validation). */
+/* Ray-path stage: 0 (default) g(h) from the table, macro steps of 8 steps where g is smooth and the
+ * reference's single steps across the starts of the temperature functions; 1 every evaluation through
+ * libm, op for op the oracle's arithmetic, single steps (validation); 2 the table, single steps only
+ * (validation of the macro steps). */
 int atmrt_set_path_mode(atmrt_ctx* ctx, int mode);
 /* Tuning hook for the ray-path stage: image rows integrated per warp (1..32, default 32). */
 int atmrt_set_rows_per_warp(atmrt_ctx* ctx, int rows);
