@@ -763,11 +763,11 @@ int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main) {
         } else if (S.flat) {
             if (ctx->path_mode == 1) k_ray_paths<true, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
             else if (ctx->path_mode == 2) k_ray_paths<true, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
-            else k_ray_paths_macro<true><<<(h + 2 * PATH_ROWS - 1) / (2 * PATH_ROWS), 64, 0, ctx->s_b>>>(S, B);
+            else k_ray_paths_macro<true><<<(h + MACRO_THREADS / 32 * MACRO_ROWS - 1) / (MACRO_THREADS / 32 * MACRO_ROWS), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
         } else {
             if (ctx->path_mode == 1) k_ray_paths<false, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
             else if (ctx->path_mode == 2) k_ray_paths<false, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
-            else k_ray_paths_macro<false><<<(h + 2 * PATH_ROWS - 1) / (2 * PATH_ROWS), 64, 0, ctx->s_b>>>(S, B);
+            else k_ray_paths_macro<false><<<(h + MACRO_THREADS / 32 * MACRO_ROWS - 1) / (MACRO_THREADS / 32 * MACRO_ROWS), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
         }
         ctx->launches++;
     }

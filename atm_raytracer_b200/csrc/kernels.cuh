@@ -517,34 +517,36 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
 // ---------------------------------------------------------------------------------------------
 // Stage B with macro steps. The ray equation is smooth wherever g(h) is -- everywhere except at the starts
 // of the temperature functions, where g jumps -- and there classical RK4 with a 25 m step is converged far
-// below f64 resolution of the path: integrating the same equation with ONE RK4 step of 8 x 25 m lands on the
-// same state to 3e-11 m (scratch measurement in DESIGN.md section 4.B; the local error of the long step is
-// 1e-16 m), and the seven states in between follow from the cubic Hermite interpolant of the two ends (error
-// < 1e-12 m). At a start of a temperature function the reference's result DOES depend on how its 25 m steps
+// below f64 resolution of the path: integrating the same equation with ONE RK4 step of 16 x 25 m lands on the
+// same state to 4e-11 m for near-horizontal rays and 2e-9 m at 44 degrees (extended-precision measurement in
+// DESIGN.md section 4.B), and the fifteen states in between follow from the cubic Hermite interpolant of the
+// two ends (error < 2e-11 m). At a start of a temperature function the reference's result DOES depend on how its 25 m steps
 // straddle the jump (by millimetres), so there the kernel takes the reference's own single steps: a macro
 // step is taken only when no start lies in the altitude span it covers (exact test against the sorted
-// starts), single steps otherwise. The chain is 8x shorter where it matters, and the eight states of a
-// macro step are eight independent outputs: a warp is 4 rows x 8 sub-lanes (lane = 4 j + row), every
+// starts), single steps otherwise. The chain is 16x shorter where it matters, and the sixteen states of a
+// macro step are sixteen independent outputs: a warp is 2 rows x 16 sub-lanes (lane = 2 j + row), every
 // sub-lane integrates the row's macro step redundantly (identical values, no exchange), evaluates ITS
 // state from the interpolant, its calc_dist segment, takes part in a prefix sum for path_length and stores
-// its cache entry -- the warp's stores are 256 contiguous bytes per plane.
+// its cache entry.
 // ---------------------------------------------------------------------------------------------
-constexpr int MACRO = 8;
+constexpr int MACRO = 16;              // steps per macro step
+constexpr int MACRO_ROWS = 32 / MACRO;  // rows per warp
+constexpr int MACRO_THREADS = 128;      // 4 warps share one copy of the table: H / 8 blocks, all resident at once
 constexpr int ATM_MAX_BND = ATMRT_MAX_ATM_FUNCTIONS + 4;
 
 template <bool FLAT>
-__global__ void __launch_bounds__(64) k_ray_paths_macro(const __grid_constant__ DevScene S, DevBuffers B) {
+__global__ void __launch_bounds__(MACRO_THREADS) k_ray_paths_macro(const __grid_constant__ DevScene S, DevBuffers B) {
     __shared__ double tab_smem[ATM_FIELDS * ATM_CELLS];
     __shared__ double s_bnd[ATM_MAX_BND];          // sorted altitudes where g is not smooth (+inf padded)
     __shared__ unsigned char s_first[ATM_CELLS];   // per cell: index of the first of them at or above the cell's lower edge
 #pragma unroll 4
-    for (int i = threadIdx.x; i < ATM_FIELDS * ATM_CELLS; i += 64) tab_smem[i] = B.atm_cells[i];
-    for (int i = threadIdx.x; i < ATM_CELLS; i += 64) s_first[i] = B.atm_first[i];
+    for (int i = threadIdx.x; i < ATM_FIELDS * ATM_CELLS; i += MACRO_THREADS) tab_smem[i] = B.atm_cells[i];
+    for (int i = threadIdx.x; i < ATM_CELLS; i += MACRO_THREADS) s_first[i] = B.atm_first[i];
     if (threadIdx.x < ATM_MAX_BND) s_bnd[threadIdx.x] = B.atm_bnd[threadIdx.x];
     __syncthreads();
     const GSource gs{(unsigned)__cvta_generic_to_shared(tab_smem), B.atm_pieces, B.n_atm_pieces};
-    const int lane = threadIdx.x & 31, rr = lane & 3, j = lane >> 2;
-    const int y_raw = (blockIdx.x * 2 + (threadIdx.x >> 5)) * PATH_ROWS + rr;
+    const int lane = threadIdx.x & 31, rr = lane % MACRO_ROWS, j = lane / MACRO_ROWS;
+    const int y_raw = (blockIdx.x * (MACRO_THREADS / 32) + (threadIdx.x >> 5)) * MACRO_ROWS + rr;
     const int y = min(y_raw, S.height - 1);
     const bool writer = y_raw < S.height;
     const double alt = *B.obs_alt;
@@ -558,10 +560,11 @@ __global__ void __launch_bounds__(64) k_ray_paths_macro(const __grid_constant__ 
     double* const o_elev = B.p_elev + path_index(n_t, 0, y);
     double* const o_len = B.p_len + path_index(n_t, 0, y);
     const double* __restrict__ dxr = B.path_dxr;
-    // the cubic Hermite basis at this sub-lane's state, s = (j + 1) / 8
+    // the cubic Hermite basis at this sub-lane's state, s = (j + 1) / MACRO
     const double sj = (double)(j + 1) * (1.0 / MACRO);
     const double h01 = sj * sj * (3.0 - 2.0 * sj), h10 = sj * (sj - 1.0) * (sj - 1.0), h11 = sj * sj * (sj - 1.0);
-    const unsigned rowbits = 0x11111111u << rr;  // this row's sub-lanes in a ballot
+    unsigned rowbits = 0u;  // this row's sub-lanes in a ballot
+    for (int t = 0; t < MACRO; ++t) rowbits |= 1u << (t * MACRO_ROWS + rr);
 
     double a = FLAT ? alt : radius + alt;
     double b = FLAT ? tan(to_radians(get_ray_elev(S, y))) : a * tan(to_radians(get_ray_elev(S, y)));
@@ -623,39 +626,37 @@ __global__ void __launch_bounds__(64) k_ray_paths_macro(const __grid_constant__ 
         // this sub-lane's element q = e + j + 1: calc_dist from the element before it, path_length by prefix sum
         const int q = min(e + j + 1, n_t - 1);
         const double h_q = FLAT ? a_q : a_q - radius;
-        const double h_up = __shfl_up_sync(FULL, h_q, 4);
+        const double h_up = __shfl_up_sync(FULL, h_q, MACRO_ROWS);
         const double h_p = j == 0 ? h_e : h_up;
         double dx = dxr[q];
         if (!FLAT) dx = dx * ((h_q + h_p) * 0.5 + radius);
         const double dh = h_q - h_p;
         double acc = valid ? sqrt_nr(dx * dx + dh * dh) : 0.0;
 #pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
+        for (int o = MACRO_ROWS; o < 32; o <<= 1) {
             const double up = __shfl_up_sync(FULL, acc, o);
             if (lane >= o) acc += up;
         }
         const double len_q = path_length + acc;
         // termination: element q is kept unless an element <= q - 2 is past max_distance or below -1000 m
         const bool trig_q = valid && (q >= k_far || h_q < -1000.0);
-        const unsigned trig = (__ballot_sync(FULL, trig_q) & rowbits) >> rr;  // bit 4 j' = sub-lane j'
-        const bool earlier = done_c || (j >= 1 && trig_e) || (j >= 2 && (trig & ((1u << (4 * (j - 1))) - 1u)) != 0u);
+        const unsigned trig = (__ballot_sync(FULL, trig_q) & rowbits) >> rr;  // bit MACRO_ROWS j' = sub-lane j'
+        const bool earlier = done_c || (j >= 1 && trig_e) || (j >= 2 && (trig & ((1u << (MACRO_ROWS * (j - 1))) - 1u)) != 0u);
         const bool emit = valid && writer && !earlier;
         stg_if(o_elev + (size_t)q * PATH_ROWS, h_q, emit);
         stg_if(o_len + (size_t)q * PATH_ROWS, len_q, emit);
         n = emit ? q + 1 : n;
         // carry to element e + m
-        const int last = rr + 4 * (m - 1);
-        const unsigned before_last = m == 1 ? 0u : (trig & ((1u << (4 * (m - 1))) - 1u));
+        const int last = rr + MACRO_ROWS * (m - 1);
+        const unsigned before_last = m == 1 ? 0u : (trig & ((1u << (MACRO_ROWS * (m - 1))) - 1u));
         done_c = done_c || trig_e || before_last != 0u;
-        trig_e = ((trig >> (4 * (m - 1))) & 1u) != 0u;
+        trig_e = ((trig >> (MACRO_ROWS * (m - 1))) & 1u) != 0u;
         path_length = __shfl_sync(FULL, len_q, last);
         h_e = __shfl_sync(FULL, h_q, last);
         a = a1, b = b1;
         e += m;
     }
-    n = max(n, __shfl_xor_sync(FULL, n, 4));
-    n = max(n, __shfl_xor_sync(FULL, n, 8));
-    n = max(n, __shfl_xor_sync(FULL, n, 16));
+    for (int o = MACRO_ROWS; o < 32; o <<= 1) n = max(n, __shfl_xor_sync(FULL, n, o));
     if (writer && j == 0) {
         B.p_n[y] = n;
         atomicAdd(B.counters + CNT_PATH_STEPS, (unsigned long long)(n - 1));

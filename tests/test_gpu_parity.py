@@ -149,9 +149,9 @@ def test_path_modes_agree(ctx, oracle_lib, name):
         np.testing.assert_array_equal(np.isnan(a["elev"]), np.isnan(b["elev"]))
         ok = ~np.isnan(a["elev"])
         worst = max(worst, float(np.abs(a["elev"][ok] - b["elev"][ok]).max()))
-        np.testing.assert_allclose(a["path_length"][ok], b["path_length"][ok], rtol=1e-13, atol=1e-8)
+        np.testing.assert_allclose(a["path_length"][ok], b["path_length"][ok], rtol=1e-11, atol=1e-8)  # a sum of thousands of segments
         np.testing.assert_allclose(a["elev"], c["elev"], rtol=1e-9, atol=PATH_ATOL)
-        np.testing.assert_allclose(a["path_length"], c["path_length"], rtol=1e-11, atol=1e-9)
+        np.testing.assert_allclose(a["path_length"], c["path_length"], rtol=1e-11, atol=1e-7)  # segments of altitudes that carry the ulp of r (9e-10 m)
     # macro steps vs single steps: tens of nanometres -- the rounding of r (ulp 9e-10 m) accumulated over thousands
     # of single steps, a hundred times below the noise floor of the reference's own evaluation (PATH_ATOL)
     assert worst < 2e-7, worst
