@@ -790,7 +790,8 @@ int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main) {
     // Stage A on s_a
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->a0, ctx->s_a));
     k_column_setup<<<(wl + 127) / 128, 128, 0, ctx->s_a>>>(S, B);
-    k_terrain_profile<<<dim3((S.n_t + 127) / 128, wl), 128, 0, ctx->s_a>>>(S, ctx->terrain, B, 0);
+    if (S.earth.walker == WALK_SPHERICAL) k_terrain_profile<WALK_SPHERICAL><<<dim3((S.n_t + 127) / 128, wl), 128, 0, ctx->s_a>>>(S, ctx->terrain, B, 0);
+    else k_terrain_profile<-1><<<dim3((S.n_t + 127) / 128, wl), 128, 0, ctx->s_a>>>(S, ctx->terrain, B, 0);
     ctx->launches += 2;
     auto terrain_pyramids = [&](cudaStream_t st, int only_if_not_swept) {
         const long long warps = (long long)wl * S.n2;
@@ -816,7 +817,8 @@ int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main) {
         // next was measured and is slower: 8.9 ms -> 9.8 / 10.5 ms with 2 / 4 chunks at c5 -- the sweep's long
         // columns leave each smaller grid with a longer tail.)
         k_sweep<<<(wl + SWEEP_THREADS / 32 - 1) / (SWEEP_THREADS / 32), SWEEP_THREADS, 0, main>>>(S, B, 0, wl);
-        k_sweep_shade<<<dim3((h + 31) / 32, (wl + SHADE_COLS - 1) / SHADE_COLS), 32 * SHADE_COLS, 0, main>>>(S, B, O, 0);
+        if (S.earth.walker == WALK_SPHERICAL) k_sweep_shade<WALK_SPHERICAL><<<dim3((h + 31) / 32, (wl + SHADE_COLS - 1) / SHADE_COLS), 32 * SHADE_COLS, 0, main>>>(S, B, O, 0);
+        else k_sweep_shade<-1><<<dim3((h + 31) / 32, (wl + SHADE_COLS - 1) / SHADE_COLS), 32 * SHADE_COLS, 0, main>>>(S, B, O, 0);
         ctx->launches += 2;
         // fallbacks, no-ops unless the device-side checks ask for them: pyramids + hierarchical march of the
         // whole image (rays cross), brute-force march of flagged columns

@@ -30,11 +30,11 @@
 //     from the previous state; g and 1/r at the stages are the values at those points with a first-order
 //     correction (neglected term < 1e-12 relative). The lookups leave the critical path; what remains on
 //     it is the chain of the four slope updates.
-//  4. One lane per row, one warp per block: 32 adjacent rows (8 row groups of the tiled cache) step
-//     together, H / 32 warps spread over the SMs; the stage leaves the FP64 pipe almost idle for the
-//     terrain stage that runs beside it. A lone warp issues one instruction every ~2.3 cycles (ncu), so
-//     the step is also trimmed in instructions: PathElem::dist and calc_dist's dx / R do not depend on
-//     the row and come from two host tables.
+//  4. Where g is smooth sixteen steps are taken as ONE RK4 step and the states in between come from the
+//     cubic Hermite interpolant of its ends, on sixteen sub-lanes (kernels.cuh: k_ray_paths_macro); across
+//     the starts of the temperature functions, where g jumps and the reference's result depends on how its
+//     steps straddle the jump, the kernel takes the reference's single steps (rk4_step_shared). PathElem::dist
+//     and calc_dist's dx / R do not depend on the row and come from two host tables.
 #pragma once
 
 #include "device_atm.cuh"

@@ -217,11 +217,20 @@ __device__ __forceinline__ EllipsoidCalc column_ellipsoid_calc(const DevScene& S
     return e;
 }
 
+// The walker of a kernel instantiation: W >= 0 fixes it at compile time (the hot kernels are instantiated for
+// the spherical walker, so that the common case carries none of the other models' code), W < 0 reads the scene.
+template <int W>
+__device__ __forceinline__ int walker_of(const DevScene& S) {
+    return W >= 0 ? W : S.earth.walker;
+}
+
 // find_normal, utils.rs:15-40: central differences +-15 m north/south and east/west on the terrain, walked
 // with the model's own DirectionalCalc from (lat, lon) at azimuths 0 and 90 degrees.
 // A pure function of (lat, lon); sin/cos of both are passed in because the callers have them.
+template <int W = -1>
 __device__ __forceinline__ V3 find_normal(const DevScene& S, const DevTerrain& T, double lat, double lon, double sinlat, double coslat,
                                           double sinlon, double coslon) {
+    const int walker = walker_of<W>(S);
     double n_lat, n_lon, s_lat, s_lon, e_lat, e_lon, w_lat, w_lon;
     Dirs D;  // world_directions(lat, lon)
     if (S.earth.flat_dirs) {
@@ -231,7 +240,7 @@ __device__ __forceinline__ V3 find_normal(const DevScene& S, const DevTerrain& T
     } else {
         D = spherical_directions_sc(sinlat, coslat, sinlon, coslon);
     }
-    if (S.earth.walker == WALK_FLDS) {
+    if (walker == WALK_FLDS) {
         // FlDsCalc::new((lat, lon), 0.0 / 90.0).coords_at_dist(+-DIFF)
         n_lat = lat + 1.0 * NORMAL_DIFF / DEGREE_DISTANCE;
         n_lon = lon + 0.0 * NORMAL_DIFF / DEGREE_DISTANCE / coslat;
@@ -241,7 +250,7 @@ __device__ __forceinline__ V3 find_normal(const DevScene& S, const DevTerrain& T
         e_lon = lon + SIN_90 * NORMAL_DIFF / DEGREE_DISTANCE / coslat;
         w_lat = lat + COS_90 * -NORMAL_DIFF / DEGREE_DISTANCE;
         w_lon = lon + SIN_90 * -NORMAL_DIFF / DEGREE_DISTANCE / coslat;
-    } else if (S.earth.walker == WALK_AZEQ) {
+    } else if (walker == WALK_AZEQ) {
         // AzEqCalc::new(north cos(az) + east sin(az), as_cartesian(lat, lon, 0)).coords_at_dist(+-DIFF), mod.rs:116-125
         const double r = (90.0 - lat) * DEGREE_DISTANCE;
         const V3 pos{r * coslon, r * sinlon, 0.0};
@@ -251,7 +260,7 @@ __device__ __forceinline__ V3 find_normal(const DevScene& S, const DevTerrain& T
         azeq_walk(pos, dir_ns, -NORMAL_DIFF, &s_lat, &s_lon);
         azeq_walk(pos, dir_ew, NORMAL_DIFF, &e_lat, &e_lon);
         azeq_walk(pos, dir_ew, -NORMAL_DIFF, &w_lat, &w_lon);
-    } else if (S.earth.walker == WALK_ELLIPSOID) {
+    } else if (walker == WALK_ELLIPSOID) {
         // EllipsoidCalc::new(a, b, (lat, lon), 0.0 / 90.0).coords_at_dist(+-DIFF)
         const EllipsoidCalc ns = ellipsoid_calc(S.earth, lat, lon, 0.0), ew = ellipsoid_calc(S.earth, lat, lon, 90.0);
         ellipsoid_walk(S.earth, ns, NORMAL_DIFF, &n_lat, &n_lon);
@@ -312,10 +321,11 @@ struct SampleTrig {
 // cos(lat) sin(lon) to the rounding of the walk (|fpos| = 1 +- 2e-16), so they are recovered without four
 // more libm calls. Near the poles (cos lat < 0.05) the division loses bits: evaluate them from the angles
 // as the reference does.
+template <int W = -1>
 __device__ __forceinline__ SampleTrig sample_trig(const DevScene& S, V3 fpos, double lat, double lon) {
     SampleTrig t;
     const double c2 = fpos.x * fpos.x + fpos.y * fpos.y;
-    if (S.earth.walker == WALK_SPHERICAL && c2 > 0.0025) {
+    if (walker_of<W>(S) == WALK_SPHERICAL && c2 > 0.0025) {
         t.sinlat = fpos.z;
         t.coslat = sqrt(c2);
         const double ic = 1.0 / t.coslat;
@@ -336,15 +346,17 @@ __device__ __forceinline__ V3 walk_fpos(const DevScene& S, const double* __restr
 
 // DirectionalCalc::coords_at_dist of the walker lowered into cc (direction_calc). fpos: the unit vector of the
 // sample for the spherical walker (sample_trig reads the sample's sines and cosines off it), else untouched.
+template <int W = -1>
 __device__ __forceinline__ void walk_coords(const DevScene& S, const double* __restrict__ cc, double d, double* lat, double* lon, V3* fpos) {
-    if (S.earth.walker == WALK_FLDS) {  // FlDsCalc::coords_at_dist, directional_calc.rs:41-47
+    const int walker = walker_of<W>(S);
+    if (walker == WALK_FLDS) {  // FlDsCalc::coords_at_dist, directional_calc.rs:41-47
         double d_lat = cc[0] * d / DEGREE_DISTANCE;
         double d_lon = cc[1] * d / DEGREE_DISTANCE / cc[2];
         *lat = S.lat0 + d_lat;
         *lon = S.lon0 + d_lon;
-    } else if (S.earth.walker == WALK_AZEQ) {  // AzEqCalc::coords_at_dist, directional_calc.rs:20-27
+    } else if (walker == WALK_AZEQ) {  // AzEqCalc::coords_at_dist, directional_calc.rs:20-27
         azeq_walk(V3{cc[3], cc[4], cc[5]}, V3{cc[0], cc[1], cc[2]}, d, lat, lon);
-    } else if (S.earth.walker == WALK_ELLIPSOID) {  // EllipsoidCalc::coords_at_dist, directional_calc.rs:139-184
+    } else if (walker == WALK_ELLIPSOID) {  // EllipsoidCalc::coords_at_dist, directional_calc.rs:139-184
         ellipsoid_walk(S.earth, column_ellipsoid_calc(S, cc), d, lat, lon);
     } else {  // SphericalCalc::coords_at_dist, directional_calc.rs:71-86
         *fpos = walk_fpos(S, cc, d);
@@ -366,6 +378,7 @@ __device__ __forceinline__ unsigned long long objects_close(const DevScene& S, c
     return mask;
 }
 
+template <int W>
 __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__ DevScene S, DevTerrain T, DevBuffers B, int col0) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     int xl = col0 + blockIdx.y;  // the render is issued in column chunks (atmrt_lib.cu:launch_render)
@@ -374,7 +387,7 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
     const double* cc = B.colcalc + (size_t)xl * 8;
     double lat, lon;
     V3 fpos{0.0, 0.0, 0.0};
-    walk_coords(S, cc, d, &lat, &lon, &fpos);
+    walk_coords<W>(S, cc, d, &lat, &lon, &fpos);
     double elev = elev_or_zero(T, lat, lon);
     size_t idx = (size_t)xl * S.n_pad + k;
     B.t_lat[idx] = lat;
@@ -386,11 +399,12 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
 
 // TerrainData::normal of sample k of column xl (find_normal at the sample's coordinates, utils.rs:84):
 // the coordinates come from the cache, the unit vector of the walk is recomputed (one sincos).
+template <int W = -1>
 __device__ __forceinline__ V3 sample_normal(const DevScene& S, const DevTerrain& T, const DevBuffers& B, int xl, int k, double lat, double lon) {
     V3 fpos{0.0, 0.0, 0.0};
-    if (S.earth.walker == WALK_SPHERICAL) fpos = walk_fpos(S, B.colcalc + (size_t)xl * 8, B.dist_k[k]);
-    const SampleTrig t = sample_trig(S, fpos, lat, lon);
-    return find_normal(S, T, lat, lon, t.sinlat, t.coslat, t.sinlon, t.coslon);
+    if (walker_of<W>(S) == WALK_SPHERICAL) fpos = walk_fpos(S, B.colcalc + (size_t)xl * 8, B.dist_k[k]);
+    const SampleTrig t = sample_trig<W>(S, fpos, lat, lon);
+    return find_normal<W>(S, T, lat, lon, t.sinlat, t.coslat, t.sinlon, t.coslon);
 }
 
 // The normals of one column (probe: atmrt_get_terrain_profile), [k][3].
@@ -1421,6 +1435,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(const __grid_constant__
 // row-major [y][x] image and metadata are stored as contiguous row segments.
 constexpr int SHADE_COLS = 16;
 
+template <int W>
 __global__ void __launch_bounds__(32 * SHADE_COLS, 2) k_sweep_shade(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, int col0) {
     if (B.sweep_flags[0] != 0) return;
     __shared__ double s_meta[32][SHADE_COLS * 4];
@@ -1470,7 +1485,7 @@ __global__ void __launch_bounds__(32 * SHADE_COLS, 2) k_sweep_shade(const __grid
                 if (mine) {
                     const int smp = ks - (second ? 1 : 0);
                     const size_t ti = (size_t)xx * S.n_pad + smp;
-                    const V3 n = sample_normal(S, B.terrain, B, xx, smp, B.t_lat[ti], B.t_lon[ti]);
+                    const V3 n = sample_normal<W>(S, B.terrain, B, xx, smp, B.t_lat[ti], B.t_lon[ti]);
                     s_nrm[w][item][0] = n.x, s_nrm[w][item][1] = n.y, s_nrm[w][item][2] = n.z;
                 }
             }
