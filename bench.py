@@ -35,7 +35,7 @@ METRIC = "panorama pixels/s"
 # reference arithmetic each stage restates, not from the SASS.
 STAGE_UNITS = {
     "terrain": ("k_terrain_profile", "terrain samples"),
-    "paths": ("k_ray_paths", "path steps"),
+    "paths": ("k_ray_paths_macro", "path steps"),
     "march": ("k_march", "ray steps"),
 }
 
@@ -384,7 +384,7 @@ def run_b200(args):
         "e2e_with_meta": e2e_meta,
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roof,
-        "roofline_stages": {k: {f: v[f] for f in ("kernel", "achieved", "peak", "frac", "unit", "launch_ms", "units_per_launch", "traffic")}
+        "roofline_stages": {k: {f: v[f] for f in ("kernel", "achieved", "peak", "frac", "unit", "launch_ms", "units_per_launch", "traffic", "ncu")}
                             for k, v in roofs.items()},
         "cpu_baseline": cpu,
         "fp64_peak_measured": fp,
@@ -411,11 +411,29 @@ def roofline(stage, ms, units, params, fp, args):
     return {
         "kernel": STAGE_UNITS[stage][0], "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "G FP64 instr/s",
         "frac": achieved / peak if peak else None, "traffic": ncu_traffic(STAGE_UNITS[stage][0], args),
+        "ncu": ncu_counters(STAGE_UNITS[stage][0], args),
+        "note": "achieved counts the FP64 instructions of the REFERENCE's algorithm per unit (DESIGN.md section 4); the kernels execute "
+                "fewer (deferred normals, g(h) table and macro steps, horizon sweep), so frac > 1 means less work than the reference's "
+                "algorithm, not a faster pipe -- the pipe utilisations measured by ncu are under `ncu`",
         "units_per_launch": units, "unit_name": STAGE_UNITS[stage][1], "fp64_instr_per_unit": per_unit, "launch_ms": ms,
         "peak_source": "measured live (atmrt_fp64_peak: 8 independent DFMA chains/thread); MEASURED_PEAKS.json has no FP64 entry",
         "hbm": {"algorithmic_bytes_per_unit": bytes_unit, "achieved_gbs": bytes_unit * units / (ms * 1e-3) / 1e9 if ms > 0 else 0.0,
                 "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs"},
     }
+
+
+def ncu_counters(kernel, args):
+    """Pipe utilisations of `kernel` (or of each kernel of a `a+b` pair) from the committed ncu --set full capture
+    (profiles/ncu_summary.json): what the hardware counters say next to the algorithmic `achieved`."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+        if args.gpus != 1 or args.scale != 1.0:
+            return None
+        got = {k: table.get(f"{args.workload}:{k}") for k in kernel.split("+")}
+        got = {k: v for k, v in got.items() if v}
+        return got or None
+    except Exception:
+        return None
 
 
 def ncu_traffic(kernel, args):
@@ -448,7 +466,7 @@ def hbm_bytes_per_unit(stage, params):
     if stage == "march":
         return 8.0 * (1.0 / params.height + 1.0 / max(1, params.x1 - params.x0))
     if stage == "paths":
-        return 24.0
+        return 24.0  # PathElem{dist, elev, path_length} per step as the reference stores it (16 B here: dist is row-independent)
     return 48.0 + 40.0  # six f64 outputs + five bilinear taps of 4 i16 posts
 
 
