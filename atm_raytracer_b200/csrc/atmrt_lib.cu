@@ -33,6 +33,7 @@ struct atmrt_ctx {
     int device = 0;
     std::string err;
     cudaStream_t s_a = nullptr, s_b = nullptr, s_main = nullptr;
+    cudaEvent_t ev_band[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_prep = nullptr, ev_a = nullptr, ev_b = nullptr;
     // Stage timing: one set of events per render since the last harvest (atmrt_stage_times), so a
     // whole timed region of asynchronous renders can be averaged without synchronising inside it.
@@ -93,6 +94,8 @@ struct atmrt_ctx {
 };
 
 namespace {
+
+constexpr int SHADE_BANDS = 8;  // row bands of the shading when the image goes straight to host memory
 
 int fail(atmrt_ctx* ctx, int code, const std::string& msg) {
     if (ctx)
@@ -684,6 +687,12 @@ struct RenderTargets {
     atmrt_trace_point* points = nullptr;
     int* counts = nullptr;
     int max_points = 0;
+    // host destinations (atmrt_render): when the horizon sweep serves the image, the shading is launched in
+    // row bands and every finished band travels to the host while the next one is shaded
+    unsigned char* host_rgb = nullptr;
+    atmrt_meta* host_meta = nullptr;
+    int* host_steps = nullptr;
+    bool host_copied = false;  // out: the bands were copied (valid unless a device-side fallback ran afterwards)
 };
 
 // Launch the whole render on (s_a || s_b) -> main. Asynchronous.
@@ -702,7 +711,7 @@ int next_stage_events(atmrt_ctx* ctx, atmrt_ctx::StageEvents** out) {
     return 0;
 }
 
-int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main) {
+int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
     const DevScene& S = ctx->scene;
     const DevBuffers& B = ctx->buf;
     const int wl = S.x1 - S.x0, h = S.height;
@@ -817,9 +826,31 @@ int launch_render(atmrt_ctx* ctx, const RenderTargets& rt, cudaStream_t main) {
         // next was measured and is slower: 8.9 ms -> 9.8 / 10.5 ms with 2 / 4 chunks at c5 -- the sweep's long
         // columns leave each smaller grid with a longer tail.)
         k_sweep<<<(wl + SWEEP_THREADS / 32 - 1) / (SWEEP_THREADS / 32), SWEEP_THREADS, 0, main>>>(S, B, 0, wl);
-        if (S.earth.walker == WALK_SPHERICAL) k_sweep_shade<WALK_SPHERICAL><<<dim3((h + 31) / 32, (wl + SHADE_COLS - 1) / SHADE_COLS), 32 * SHADE_COLS, 0, main>>>(S, B, O, 0);
-        else k_sweep_shade<-1><<<dim3((h + 31) / 32, (wl + SHADE_COLS - 1) / SHADE_COLS), 32 * SHADE_COLS, 0, main>>>(S, B, O, 0);
-        ctx->launches += 2;
+        ctx->launches++;
+        const bool to_host = rt.host_rgb || rt.host_meta || rt.host_steps;
+        const int nbands = to_host && h >= 256 ? SHADE_BANDS : 1;
+        const int band_rows = ((h + nbands - 1) / nbands + 31) / 32 * 32;
+        int bi = 0;
+        for (int r0 = 0; r0 < h; r0 += band_rows, ++bi) {
+            const int r1 = std::min(h, r0 + band_rows);
+            const dim3 sgrid((r1 - r0 + 31) / 32, (wl + SHADE_COLS - 1) / SHADE_COLS);
+            if (S.earth.walker == WALK_SPHERICAL) k_sweep_shade<WALK_SPHERICAL><<<sgrid, 32 * SHADE_COLS, 0, main>>>(S, B, O, 0, r0);
+            else k_sweep_shade<-1><<<sgrid, 32 * SHADE_COLS, 0, main>>>(S, B, O, 0, r0);
+            ctx->launches++;
+            if (to_host) {  // the finished band goes to the host on the (idle) stage-A stream while the next band is shaded
+                const size_t p0 = (size_t)r0 * wl, np = (size_t)(r1 - r0) * wl;
+                CUDA_TRY(ctx, cudaEventRecord(ctx->ev_band[bi], main));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_a, ctx->ev_band[bi], 0));
+                if (rt.host_rgb) CUDA_TRY(ctx, cudaMemcpyAsync(rt.host_rgb + p0 * 3, rt.rgb + p0 * 3, np * 3, cudaMemcpyDeviceToHost, ctx->s_a));
+                if (rt.host_meta) CUDA_TRY(ctx, cudaMemcpyAsync(rt.host_meta + p0, rt.meta + p0, np * sizeof(atmrt_meta), cudaMemcpyDeviceToHost, ctx->s_a));
+                if (rt.host_steps) CUDA_TRY(ctx, cudaMemcpyAsync(rt.host_steps + p0, rt.steps + p0, np * sizeof(int), cudaMemcpyDeviceToHost, ctx->s_a));
+            }
+        }
+        if (to_host) {
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->s_a));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_a, 0));
+            rt.host_copied = true;
+        }
         // fallbacks, no-ops unless the device-side checks ask for them: pyramids + hierarchical march of the
         // whole image (rays cross), brute-force march of flagged columns
         terrain_pyramids(main, 1);
@@ -928,6 +959,7 @@ int atmrt_create(int device, atmrt_ctx** out) {
               cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking) == cudaSuccess;
     cudaEvent_t* evs[] = {&ctx->ev_prep, &ctx->ev_a, &ctx->ev_b};
     for (cudaEvent_t* ev : evs) ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
+    for (cudaEvent_t& ev : ctx->ev_band) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
     cudaEvent_t* tevs[] = {&ctx->t_0, &ctx->t_1};
     for (cudaEvent_t* ev : tevs) ok = ok && cudaEventCreate(ev) == cudaSuccess;
     if (!ok) {
@@ -952,6 +984,8 @@ void atmrt_destroy(atmrt_ctx* ctx) {
     if (ctx->terrain_owned) cudaFree(ctx->terrain_owned);
     cudaEvent_t evs[] = {ctx->ev_prep, ctx->ev_a, ctx->ev_b, ctx->t_0, ctx->t_1};
     for (cudaEvent_t ev : evs)
+        if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->ev_band)
         if (ev) cudaEventDestroy(ev);
     for (atmrt_ctx::StageEvents& e : ctx->ring) {
         cudaEvent_t all[] = {e.a0, e.a1, e.b0, e.b1, e.c0, e.c1, e.t0, e.t1};
@@ -1171,13 +1205,23 @@ int atmrt_render(atmrt_ctx* ctx, uint8_t* rgb, atmrt_meta* meta, int32_t* steps,
     rt.rgb = rgb ? (unsigned char*)ctx->d_rgb.p : nullptr;
     rt.meta = meta ? (atmrt_meta*)ctx->d_meta.p : nullptr;
     rt.steps = steps ? (int*)ctx->d_steps.p : nullptr;
+    rt.host_rgb = rgb, rt.host_meta = meta, rt.host_steps = steps;
     cudaStream_t main = ctx->s_main;
     rc = launch_render(ctx, rt, main);
     if (rc) return rc;
-    if (rgb) CUDA_TRY(ctx, cudaMemcpyAsync(rgb, ctx->d_rgb.p, npix * 3, cudaMemcpyDeviceToHost, main));
-    if (meta) CUDA_TRY(ctx, cudaMemcpyAsync(meta, ctx->d_meta.p, npix * sizeof(atmrt_meta), cudaMemcpyDeviceToHost, main));
-    if (steps) CUDA_TRY(ctx, cudaMemcpyAsync(steps, ctx->d_steps.p, npix * sizeof(int), cudaMemcpyDeviceToHost, main));
-    CUDA_TRY(ctx, cudaStreamSynchronize(main));
+    bool copy_all = !rt.host_copied;
+    if (rt.host_copied) {  // bands went out behind the horizon sweep: valid unless a device-side fallback repainted pixels afterwards
+        unsigned flags[2] = {0, 0};
+        CUDA_TRY(ctx, cudaMemcpyAsync(flags, ctx->d_sweep_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, main));
+        CUDA_TRY(ctx, cudaStreamSynchronize(main));
+        copy_all = flags[0] != 0 || flags[1] != 0;
+    }
+    if (copy_all) {
+        if (rgb) CUDA_TRY(ctx, cudaMemcpyAsync(rgb, ctx->d_rgb.p, npix * 3, cudaMemcpyDeviceToHost, main));
+        if (meta) CUDA_TRY(ctx, cudaMemcpyAsync(meta, ctx->d_meta.p, npix * sizeof(atmrt_meta), cudaMemcpyDeviceToHost, main));
+        if (steps) CUDA_TRY(ctx, cudaMemcpyAsync(steps, ctx->d_steps.p, npix * sizeof(int), cudaMemcpyDeviceToHost, main));
+        CUDA_TRY(ctx, cudaStreamSynchronize(main));
+    }
     return collect_stats(ctx, stats);
 }
 

@@ -1436,7 +1436,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(const __grid_constant__
 constexpr int SHADE_COLS = 16;
 
 template <int W>
-__global__ void __launch_bounds__(32 * SHADE_COLS, 2) k_sweep_shade(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, int col0) {
+__global__ void __launch_bounds__(32 * SHADE_COLS, 2) k_sweep_shade(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, int col0, int row0) {
     if (B.sweep_flags[0] != 0) return;
     __shared__ double s_meta[32][SHADE_COLS * 4];
     __shared__ __align__(16) unsigned char s_rgb[32][SHADE_COLS * 3];
@@ -1445,7 +1445,7 @@ __global__ void __launch_bounds__(32 * SHADE_COLS, 2) k_sweep_shade(const __grid
     __shared__ double s_nrm[SHADE_COLS][64][3];
     const int wl = S.x1 - S.x0;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int c0 = col0 + blockIdx.y * SHADE_COLS, y0 = blockIdx.x * 32;  // col0: a multiple of SHADE_COLS
+    const int c0 = col0 + blockIdx.y * SHADE_COLS, y0 = row0 + blockIdx.x * 32;  // col0: a multiple of SHADE_COLS; row0: of 32 (row bands)
     const int xl = c0 + w, y = y0 + lane;
     const bool col_ok = xl < wl && B.sweep_col[xl] == 0;  // flagged columns belong to the brute-force march
     const bool active = col_ok && y < S.height;

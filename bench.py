@@ -309,7 +309,16 @@ def run_b200(args):
             pinned = [torch.from_numpy(p).pin_memory() for _, p in terrain.tiles]
             terrain_pinned = runtime.Terrain([(d, t_.numpy()) for (d, _), t_ in zip(terrain.tiles, pinned)])
 
+        host_rgb_np = host_rgb.numpy() if rank == 0 else None
+        host_meta_np = host_meta.numpy() if rank == 0 else None
+
         def e2e_step(with_meta):
+            if world == 1:
+                # one GPU: the library's host-buffer call (atmrt_render) -- the image leaves in row bands while
+                # the remaining bands are still being shaded
+                ctx.pack_terrain(terrain_pinned, packed.data_ptr())  # H2D + retile
+                ctx.render(rgb=True, meta=with_meta, steps=False, out={"rgb": host_rgb_np, "meta": host_meta_np})
+                return
             if rank == 0:
                 ctx.pack_terrain(terrain_pinned, packed.data_ptr())  # H2D + retile
             parallel.broadcast_terrain(packed)
@@ -338,8 +347,9 @@ def run_b200(args):
             dt = tt.item()
             return {"value": W * H / dt, "unit": "pixels/s", "h2d_bytes_per_step": int(terrain.bytes),
                     "d2h_bytes_per_step": int(W * H * 3 + (W * H * 32 if with_meta else 0)), "ms_per_step": dt * 1e3, "steps": e2e_steps,
-                    "api": "Context.pack_terrain (H2D + retile) + broadcast + render_device + gather_columns + D2H of rgb"
-                           + (" and per-pixel metadata" if with_meta else "")}
+                    "api": ("Context.pack_terrain (H2D + retile) + Context.render (atmrt_render: host buffers out, rgb"
+                            if world == 1 else "Context.pack_terrain (H2D + retile) + broadcast + render_device + gather_columns + D2H of rgb")
+                           + (" and per-pixel metadata" if with_meta else "") + (")" if world == 1 else "")}
 
         wants_meta = bool(cfg["output"].get("file_metadata"))
         e2e_meta = e2e_time(True)
