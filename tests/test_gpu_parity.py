@@ -568,3 +568,78 @@ def test_rectilinear_centre_pixel_is_the_fast_generators(ctx):
     for key in ("lat", "lon", "elevation", "distance"):
         assert abs(f[key] - r[key]) <= 1e-6 * max(1.0, abs(f[key])), key
     assert abs(int(fast["steps"][cy, cx]) - int(rect["steps"][cy, cx])) <= 1
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 5 at its FULL size (16384 x 4096, 64 tiles, 16000 samples per ray): properties that need no oracle
+# ---------------------------------------------------------------------------------------------
+def test_full_size_c5_properties(ctx):
+    """The oracle cannot render 67 M pixels in test time; at full size the render is held to properties:
+    idempotence (two renders are the same bytes), the horizon sweep equals the hierarchical march bit for
+    bit on a column block (two independent implementations of get_single_pixel), the step accounting of the
+    two agrees, a column block rendered alone equals the same columns of the whole image (what the 8-GPU
+    sharding relies on), and the image is what a panorama must be (sky above, terrain below, every metadata
+    distance within max_distance and increasing upwards in a column on the whole)."""
+    p, terrain, _, _ = scene("c5", 1.0)
+    assert (p.width, p.height) == (16384, 4096)
+    ctx.set_terrain(terrain)
+    ctx.set_objects([])
+    ctx.set_params(p)
+    ctx.set_march_mode(0)
+    a = ctx.render(steps=True)
+    b = ctx.render(steps=True)
+    np.testing.assert_array_equal(a["rgb"], b["rgb"])
+    np.testing.assert_array_equal(a["steps"], b["steps"])
+    assert a["stats"]["ray_steps"] == b["stats"]["ray_steps"] == int(a["steps"].astype(np.int64).sum())
+    hit = ~np.isnan(a["meta"]["distance"])
+    assert a["stats"]["pixels_hit"] == int(hit.sum())
+    assert 0.3 < hit.mean() < 0.7
+    assert not hit[:64].any() and hit[-64:].all()  # 45 degrees up is sky, 45 degrees down is ground
+    d = a["meta"]["distance"]
+    assert np.nanmax(d) <= p.max_distance and np.nanmin(d) > 0.0
+    # in a column the hit distance grows from the bottom row upwards, except where a nearer ridge hides farther ground
+    col = d[:, 1234]
+    v = col[~np.isnan(col)]
+    assert (np.diff(v) <= 0).mean() > 0.99
+    # a column block on its own (x0, x1) and through the general march
+    q = abi.Params.from_buffer_copy(p)
+    q.x0, q.x1 = 6144, 6144 + 512
+    ctx.set_params(q)
+    blk = ctx.render(steps=True)
+    np.testing.assert_array_equal(blk["rgb"], a["rgb"][:, 6144:6144 + 512])
+    np.testing.assert_array_equal(blk["steps"], a["steps"][:, 6144:6144 + 512])
+    ctx.set_march_mode(2)
+    try:
+        hier = ctx.render(steps=True)
+    finally:
+        ctx.set_march_mode(0)
+    np.testing.assert_array_equal(hier["rgb"], blk["rgb"])
+    np.testing.assert_array_equal(hier["steps"], blk["steps"])
+    for f in ("lat", "lon", "elevation", "distance"):
+        np.testing.assert_array_equal(hier["meta"][f], blk["meta"][f])
+    assert hier["stats"]["ray_steps"] == blk["stats"]["ray_steps"]
+
+
+def test_empty_and_ragged_terrain_renders(ctx, oracle_lib):
+    """Edge inputs: no tiles at all (every sample is sea level, get_elev -> None -> 0: utils.rs:86), and a ragged
+    set -- one tile missing from the 2 x 2 block and one tile of another resolution (601 longitude lines)."""
+    p, terrain, _, _ = scene("c2", 0.08)
+    p.tilt = -0.5
+    ctx.set_objects([])
+    empty = runtime.Terrain([])
+    ctx.set_terrain(empty)
+    ctx.set_params(p)
+    got = ctx.render()
+    want = oracle_lib.render(p, empty.tiles)
+    compare_render(got, want, "empty-terrain")
+    hit = ~np.isnan(got["meta"]["distance"])
+    assert hit.any() and (got["meta"]["elevation"][hit] == 0.0).all()  # the sea, up to the horizon
+    tiles = list(terrain.tiles)
+    (d, posts) = tiles[1]
+    coarse = np.ascontiguousarray(posts[::2, :])  # every other longitude line: 601 x 1201
+    ragged = runtime.Terrain([tiles[0], (runtime.Terrain.desc(d.lat0, d.lon0, coarse), coarse), tiles[3]])
+    ctx.set_terrain(ragged)
+    ctx.set_params(p)
+    got = ctx.render()
+    want = oracle_lib.render(p, ragged.tiles)
+    compare_render(got, want, "ragged-terrain")
