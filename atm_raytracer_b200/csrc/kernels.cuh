@@ -1433,10 +1433,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(const __grid_constant__
 // one column (adjacent rows hit adjacent steps, so the cache reads of a warp share sectors), the
 // results are staged in shared memory and written with the lanes running along x, so that the
 // row-major [y][x] image and metadata are stored as contiguous row segments.
-constexpr int SHADE_COLS = 16;
+constexpr int SHADE_COLS = 8;
 
 template <int W>
-__global__ void __launch_bounds__(32 * SHADE_COLS, 2) k_sweep_shade(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, int col0, int row0) {
+__global__ void __launch_bounds__(32 * SHADE_COLS, 3) k_sweep_shade(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, int col0, int row0) {
     if (B.sweep_flags[0] != 0) return;
     __shared__ double s_meta[32][SHADE_COLS * 4];
     __shared__ __align__(16) unsigned char s_rgb[32][SHADE_COLS * 3];
