@@ -1355,12 +1355,20 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(const __grid_constant__
     static_assert(SWEEP_ROWS == PATH_ROWS, "the sweep reads one row group of the path cache per 32-byte load");
     int k = 1;  // first step the current row may still cross at
     // groups of SWEEP_ROWS rows (local row 0 is the top one), bottom group first, rows bottom-up inside
-    for (int g = (S.height - 1) / SWEEP_ROWS; g >= 0 && !flagged; --g) {
+    bool finished = false;
+    for (int g = (S.height - 1) / SWEEP_ROWS; g >= 0 && !flagged && !finished; --g) {
         const int ybase = g * SWEEP_ROWS;
         int r = min(SWEEP_ROWS - 1, S.height - 1 - ybase);
         const int4 len = *reinterpret_cast<const int4*>(B.p_n + ybase);  // p_n is padded to h_pad entries
         const int n0 = min(S.n_t, len.x), n1 = min(S.n_t, len.y), n2 = min(S.n_t, len.z), n3 = min(S.n_t, len.w);
         while (r >= 0 && !flagged) {
+            if (k >= S.n_t) {
+                // The walk has reached the end of the caches: the first row that sees only sky scanned to the end,
+                // and no row above it can cross any more (no path is longer than n_t). All of them at once.
+                for (int yy = ybase + r - lane; yy >= 0; yy -= 32) hit[yy] = 0;
+                finished = true;
+                break;
+            }
             int nlim = r == 3 ? n3 : (r == 2 ? n2 : (r == 1 ? n1 : n0));
             if (k >= nlim) {  // this row's path ends without a sign change
                 if (lane == 0) hit[ybase + r] = 0;
