@@ -67,6 +67,9 @@ struct atmrt_ctx {
     int march_mode = 0;
     int rows_per_warp = 32;
     std::vector<double> dist_k;
+    std::vector<double> walk_sc;  // (sin, cos)(dist_k / radius), cached
+    int walk_sc_n = -1;
+    double walk_sc_step = 0.0, walk_sc_radius = 0.0;
     std::vector<double> path_x;  // [2][n_t]: x of path element k (the same for every row), and (x_k - x_{k-1}) / R
     int path_k_far = 0;
     std::vector<double> atm_cells;  // g(h) table of the ray-path stage, [ATM_FIELDS][ATM_CELLS]
@@ -512,6 +515,22 @@ int prepare_render(atmrt_ctx* ctx) {
     for (double d = 0.0; d < p.max_distance; d += p.simulation_step) ctx->dist_k.push_back(d);
     const int n_t = (int)ctx->dist_k.size();
     S.n_t = n_t;
+    // SphericalCalc::coords_at_dist's sin / cos of dist / radius (directional_calc.rs:72-76) do not depend on the
+    // column: tabulated behind dist_k (at an even offset: they are read as double2), once per (n_t, step, radius)
+    const size_t sc_off = ((size_t)n_t + 1) & ~(size_t)1;
+    S.n_sc_off = (int)sc_off;
+    ctx->dist_k.resize(sc_off + (size_t)2 * n_t, 0.0);
+    if (p.earth_model == ATMRT_EARTH_SPHERICAL || p.earth_model == ATMRT_EARTH_OBSERVER_AE) {
+        if (ctx->walk_sc_n != n_t || ctx->walk_sc_step != p.simulation_step || ctx->walk_sc_radius != p.radius) {
+            ctx->walk_sc.resize((size_t)2 * n_t);
+            for (int k = 0; k < n_t; ++k) {
+                const double ang = ctx->dist_k[k] / p.radius;
+                ctx->walk_sc[2 * k] = std::sin(ang), ctx->walk_sc[2 * k + 1] = std::cos(ang);
+            }
+            ctx->walk_sc_n = n_t, ctx->walk_sc_step = p.simulation_step, ctx->walk_sc_radius = p.radius;
+        }
+        std::copy(ctx->walk_sc.begin(), ctx->walk_sc.end(), ctx->dist_k.begin() + sc_off);
+    }
     {
         // PathElem::dist does not depend on the row: the stepper's independent variable advances by the same
         // step for every ray (phi += step / R, x = phi * R; flat and straight rays: x += step). The same
@@ -549,7 +568,7 @@ int prepare_render(atmrt_ctx* ctx) {
     int e = 0;
     const bool rect = p.generator == ATMRT_GENERATOR_RECTILINEAR;  // one ray and one walk per pixel: no caches
     S.generator = p.generator;
-    e |= ensure(ctx, ctx->d_dist, f8 * n_t);
+    e |= ensure(ctx, ctx->d_dist, f8 * (3 * n_t + 2));  // dist_k, then (sin, cos)(dist_k / R)
     e |= ensure(ctx, ctx->d_pdist, f8 * 2 * S.n_x);
     if (!rect) {
     e |= ensure(ctx, ctx->d_colcalc, f8 * 8 * wl);
@@ -620,6 +639,7 @@ int prepare_render(atmrt_ctx* ctx) {
     DevBuffers& B = ctx->buf;
     B = DevBuffers{};
     B.dist_k = (const double*)ctx->d_dist.p;
+    B.walk_sc = S.earth.walker == WALK_SPHERICAL ? (const double2*)((const double*)ctx->d_dist.p + S.n_sc_off) : nullptr;
     B.colcalc = (double*)ctx->d_colcalc.p;
     B.t_lat = (double*)ctx->d_tlat.p, B.t_lon = (double*)ctx->d_tlon.p, B.t_elev = (double*)ctx->d_telev.p;
     B.terrain = ctx->terrain;
@@ -652,7 +672,7 @@ int prepare_render(atmrt_ctx* ctx) {
 
 int upload_scene_inputs(atmrt_ctx* ctx, cudaStream_t s) {
     const DevScene& S = ctx->scene;
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dist.p, ctx->dist_k.data(), sizeof(double) * S.n_t, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dist.p, ctx->dist_k.data(), sizeof(double) * ctx->dist_k.size(), cudaMemcpyHostToDevice, s));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pdist.p, ctx->path_x.data(), sizeof(double) * 2 * S.n_x, cudaMemcpyHostToDevice, s));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_atm_cells.p, ctx->atm_cells.data(), sizeof(double) * ATM_FIELDS * ATM_CELLS, cudaMemcpyHostToDevice, s));
     if (!ctx->atm_pieces.empty())

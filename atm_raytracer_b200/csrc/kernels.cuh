@@ -39,6 +39,7 @@ struct DevScene {
     int width, height, x0, x1;
     int generator;  // atmrt_generator
     int n_x;     // entries of path_x / path_dxr (n_t + 2)
+    int n_sc_off;  // offset of walk_sc behind dist_k
     int n_t;     // terrain samples per column (N_t)
     int path_k_far;  // first path element with dist > max_distance (n_t if none): the row-independent half of utils.rs:167
     int n_pad;   // row stride of the [column][k] and [row][k] caches
@@ -57,6 +58,7 @@ struct DevBuffers {
     double* colcalc;       // [wl][8]: spherical {dir.xyz, pos.xyz}; flat {cos_az, sin_az, cos_lat0}
     // Stage A cache, [wl][n_pad]
     DevTerrain terrain;  // the packed terrain (the march samples it for the deferred normals)
+    const double2* walk_sc;  // [n_t]: (sin, cos)(dist_k / R) of the spherical walker, host libm like the reference; nullptr otherwise
     double *t_lat, *t_lon, *t_elev;
     unsigned long long* t_close;
     // Stage B cache, step-major [n_t][h_pad]
@@ -338,16 +340,24 @@ __device__ __forceinline__ SampleTrig sample_trig(const DevScene& S, V3 fpos, do
 }
 
 // SphericalCalc::coords_at_dist (directional_calc.rs:71-86) up to the unit vector of the sample.
-__device__ __forceinline__ V3 walk_fpos(const DevScene& S, const double* __restrict__ cc, double d) {
+// `sc`: sin and cos of d / R when the caller has them (the Fast generator's distances are the same for every
+// column, so the host tabulates sin/cos(dist_k / R) once: DevBuffers::walk_sc), else nullptr.
+__device__ __forceinline__ V3 walk_fpos(const DevScene& S, const double* __restrict__ cc, double d, const double2* sc = nullptr) {
     double sinang, cosang;
-    sincos(d / S.earth.radius, &sinang, &cosang);
+    if (sc) {
+        const double2 v = *sc;
+        sinang = v.x, cosang = v.y;
+    } else {
+        sincos(d / S.earth.radius, &sinang, &cosang);
+    }
     return V3{cc[3], cc[4], cc[5]} * cosang + V3{cc[0], cc[1], cc[2]} * sinang;
 }
 
 // DirectionalCalc::coords_at_dist of the walker lowered into cc (direction_calc). fpos: the unit vector of the
 // sample for the spherical walker (sample_trig reads the sample's sines and cosines off it), else untouched.
 template <int W = -1>
-__device__ __forceinline__ void walk_coords(const DevScene& S, const double* __restrict__ cc, double d, double* lat, double* lon, V3* fpos) {
+__device__ __forceinline__ void walk_coords(const DevScene& S, const double* __restrict__ cc, double d, double* lat, double* lon, V3* fpos,
+                                            const double2* sc = nullptr) {
     const int walker = walker_of<W>(S);
     if (walker == WALK_FLDS) {  // FlDsCalc::coords_at_dist, directional_calc.rs:41-47
         double d_lat = cc[0] * d / DEGREE_DISTANCE;
@@ -359,7 +369,7 @@ __device__ __forceinline__ void walk_coords(const DevScene& S, const double* __r
     } else if (walker == WALK_ELLIPSOID) {  // EllipsoidCalc::coords_at_dist, directional_calc.rs:139-184
         ellipsoid_walk(S.earth, column_ellipsoid_calc(S, cc), d, lat, lon);
     } else {  // SphericalCalc::coords_at_dist, directional_calc.rs:71-86
-        *fpos = walk_fpos(S, cc, d);
+        *fpos = walk_fpos(S, cc, d, sc);
         *lat = to_degrees(asin(fpos->z));
         *lon = to_degrees(atan2(fpos->y, fpos->x));
     }
@@ -387,7 +397,7 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
     const double* cc = B.colcalc + (size_t)xl * 8;
     double lat, lon;
     V3 fpos{0.0, 0.0, 0.0};
-    walk_coords<W>(S, cc, d, &lat, &lon, &fpos);
+    walk_coords<W>(S, cc, d, &lat, &lon, &fpos, B.walk_sc ? B.walk_sc + k : nullptr);
     double elev = elev_or_zero(T, lat, lon);
     size_t idx = (size_t)xl * S.n_pad + k;
     B.t_lat[idx] = lat;
@@ -402,7 +412,7 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
 template <int W = -1>
 __device__ __forceinline__ V3 sample_normal(const DevScene& S, const DevTerrain& T, const DevBuffers& B, int xl, int k, double lat, double lon) {
     V3 fpos{0.0, 0.0, 0.0};
-    if (walker_of<W>(S) == WALK_SPHERICAL) fpos = walk_fpos(S, B.colcalc + (size_t)xl * 8, B.dist_k[k]);
+    if (walker_of<W>(S) == WALK_SPHERICAL) fpos = walk_fpos(S, B.colcalc + (size_t)xl * 8, B.dist_k[k], B.walk_sc ? B.walk_sc + k : nullptr);
     const SampleTrig t = sample_trig<W>(S, fpos, lat, lon);
     return find_normal<W>(S, T, lat, lon, t.sinlat, t.coslat, t.sinlon, t.coslon);
 }
