@@ -1454,7 +1454,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(const __grid_constant__
 constexpr int SHADE_COLS = 8;
 
 template <int W>
-__global__ void __launch_bounds__(32 * SHADE_COLS, 3) k_sweep_shade(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, int col0, int row0) {
+__global__ void __launch_bounds__(32 * SHADE_COLS, 4) k_sweep_shade(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, int col0, int row0) {
     if (B.sweep_flags[0] != 0) return;
     __shared__ double s_meta[32][SHADE_COLS * 4];
     __shared__ __align__(16) unsigned char s_rgb[32][SHADE_COLS * 3];
