@@ -715,6 +715,19 @@ struct RenderTargets {
     bool host_copied = false;  // out: the bands were copied (valid unless a device-side fallback ran afterwards)
 };
 
+// The ray-path stage with macro steps: as many simulation steps per macro step as keep it within
+// MACRO_MAX_METRES (16 at 25 or 50 m; fewer for coarser simulation steps, none above 400 m).
+template <bool FLAT>
+void launch_macro_paths(atmrt_ctx* ctx, const DevScene& S, const DevBuffers& B, int h) {
+    const int warps = MACRO_THREADS / 32;
+    auto blocks = [&](int m) { return (h + warps * (32 / m) - 1) / (warps * (32 / m)); };
+    if (16.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 16><<<blocks(16), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
+    else if (8.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 8><<<blocks(8), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
+    else if (4.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 4><<<blocks(4), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
+    else if (2.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 2><<<blocks(2), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
+    else k_ray_paths<FLAT, false><<<(h + 31) / 32, 32, 0, ctx->s_b>>>(S, B);
+}
+
 // Launch the whole render on (s_a || s_b) -> main. Asynchronous.
 int next_stage_events(atmrt_ctx* ctx, atmrt_ctx::StageEvents** out) {
     if (ctx->ring_used == ctx->ring.size()) {
@@ -792,11 +805,11 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         } else if (S.flat) {
             if (ctx->path_mode == 1) k_ray_paths<true, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
             else if (ctx->path_mode == 2) k_ray_paths<true, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
-            else k_ray_paths_macro<true><<<(h + MACRO_THREADS / 32 * MACRO_ROWS - 1) / (MACRO_THREADS / 32 * MACRO_ROWS), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
+            else launch_macro_paths<true>(ctx, S, B, h);
         } else {
             if (ctx->path_mode == 1) k_ray_paths<false, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
             else if (ctx->path_mode == 2) k_ray_paths<false, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
-            else k_ray_paths_macro<false><<<(h + MACRO_THREADS / 32 * MACRO_ROWS - 1) / (MACRO_THREADS / 32 * MACRO_ROWS), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
+            else launch_macro_paths<false>(ctx, S, B, h);
         }
         ctx->launches++;
     }

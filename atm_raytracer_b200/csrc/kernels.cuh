@@ -553,12 +553,11 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
 // state from the interpolant, its calc_dist segment, takes part in a prefix sum for path_length and stores
 // its cache entry.
 // ---------------------------------------------------------------------------------------------
-constexpr int MACRO = 16;              // steps per macro step
-constexpr int MACRO_ROWS = 32 / MACRO;  // rows per warp
-constexpr int MACRO_THREADS = 128;      // 4 warps share one copy of the table: H / 8 blocks, all resident at once
+constexpr int MACRO_THREADS = 128;  // 4 warps share one copy of the table
+constexpr double MACRO_MAX_METRES = 800.0;  // longest macro step: 16 x 50 m (truncation error < 3e-8 m, section 4.B); longer simulation steps get fewer per macro step
 constexpr int ATM_MAX_BND = ATMRT_MAX_ATM_FUNCTIONS + 4;
 
-template <bool FLAT>
+template <bool FLAT, int MACRO>  // MACRO steps per macro step (16, 8, 4 or 2), 32 / MACRO rows per warp
 __global__ void __launch_bounds__(MACRO_THREADS) k_ray_paths_macro(const __grid_constant__ DevScene S, DevBuffers B) {
     __shared__ double tab_smem[ATM_FIELDS * ATM_CELLS];
     __shared__ double s_bnd[ATM_MAX_BND];          // sorted altitudes where g is not smooth (+inf padded)
@@ -568,6 +567,7 @@ __global__ void __launch_bounds__(MACRO_THREADS) k_ray_paths_macro(const __grid_
     for (int i = threadIdx.x; i < ATM_CELLS; i += MACRO_THREADS) s_first[i] = B.atm_first[i];
     if (threadIdx.x < ATM_MAX_BND) s_bnd[threadIdx.x] = B.atm_bnd[threadIdx.x];
     __syncthreads();
+    constexpr int MACRO_ROWS = 32 / MACRO;
     const GSource gs{(unsigned)__cvta_generic_to_shared(tab_smem), B.atm_pieces, B.n_atm_pieces};
     const int lane = threadIdx.x & 31, rr = lane % MACRO_ROWS, j = lane / MACRO_ROWS;
     const int y_raw = (blockIdx.x * (MACRO_THREADS / 32) + (threadIdx.x >> 5)) * MACRO_ROWS + rr;

@@ -121,14 +121,16 @@ def test_path_cache_matches_oracle(ctx, oracle_lib, name):
         np.testing.assert_allclose(got["path_length"], want["path_length"][:n], rtol=1e-12, atol=1e-9)
 
 
-@pytest.mark.parametrize("name", ["c2", "c3_flat", "c5"])
-def test_path_modes_agree(ctx, oracle_lib, name):
+@pytest.mark.parametrize("name,step", [("c2", None), ("c3_flat", None), ("c5", None), ("c2", 100.0), ("c2", 200.0), ("c3_flat", 400.0), ("c2", 1000.0)])
+def test_path_modes_agree(ctx, oracle_lib, name, step):
     """The ray-path stage three ways: g(h) from the table with macro steps where g is smooth (default), the
     table with the reference's single steps everywhere (mode 2), and every g(h) through libm -- the oracle's
     arithmetic op for op (mode 1). The macro steps reproduce the single steps to nanometres (RK4 at 25 m is
     converged far below that where g is smooth; across the starts of the temperature functions both take
     the same single steps); libm agrees within the noise floor of the reference's own evaluation."""
     p, terrain, _, _ = scene(name, 0.05 if name != "c5" else 0.0125)
+    if step is not None:  # coarser simulation steps get shorter macro steps: 8, 4, 2 steps, none above 400 m
+        p.simulation_step = step
     ctx.set_terrain(terrain)
     ctx.set_params(p)
     ctx.set_objects([])
