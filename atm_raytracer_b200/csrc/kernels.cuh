@@ -1026,7 +1026,7 @@ __device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers
     });
 }
 
-constexpr int MARCH_THREADS = 128;
+constexpr int MARCH_THREADS = 64;
 
 __device__ __forceinline__ void init_pixel(PixelState& st) {
     st.result = Rgb8{{0, 0, 0}};
@@ -1172,7 +1172,7 @@ __device__ __forceinline__ void march_column(const DevScene& S, const DevBuffers
 // grid = (rows / MARCH_THREADS, columns per pass): a block walks the columns blockIdx.y, blockIdx.y +
 // gridDim.y, ... so that the fallback launches behind the horizon sweep can use a small grid.
 template <bool OBJECTS, bool BRUTE, bool TRACE>
-__global__ void __launch_bounds__(MARCH_THREADS, 8) k_march(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, int when) {
+__global__ void __launch_bounds__(MARCH_THREADS, 16) k_march(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, int when) {
     if (when == MARCH_IF_NOT_SWEPT && B.sweep_flags[0] == 0) return;
     if (when == MARCH_FLAGGED_COLUMNS && (B.sweep_flags[0] != 0 || B.sweep_flags[1] == 0)) return;
     const int wl = S.x1 - S.x0;
