@@ -65,7 +65,6 @@ struct atmrt_ctx {
     DevBuffers buf{};
     bool rendered = false;
     int march_mode = 0;
-    int rows_per_warp = 32;
     std::vector<double> dist_k;
     std::vector<double> walk_sc;  // (sin, cos)(dist_k / radius), cached
     int walk_sc_n = -1;
@@ -1194,16 +1193,9 @@ int atmrt_set_march_mode(atmrt_ctx* ctx, int mode) {
     return 0;
 }
 
-// Tuning hook for Stage B: image rows integrated per warp (1..32).
 int atmrt_set_path_mode(atmrt_ctx* ctx, int mode) {
     if (!ctx) return ATMRT_ERR_INVALID;
     ctx->path_mode = mode == 1 || mode == 2 ? mode : 0;
-    return 0;
-}
-
-int atmrt_set_rows_per_warp(atmrt_ctx* ctx, int rows) {
-    if (!ctx || rows < 1 || rows > 32) return fail(ctx, ATMRT_ERR_INVALID, "rows per warp must be 1..32");
-    ctx->rows_per_warp = rows;  // kept for ABI stability: the 3-lanes-per-row stepper fixes 10 rows per warp
     return 0;
 }
 
@@ -1439,6 +1431,26 @@ int atmrt_refraction_probe(atmrt_ctx* ctx, const double* h, int n, int with_piec
     CUDA_TRY(ctx, cudaGetLastError());
     if (g_table) CUDA_TRY(ctx, cudaMemcpyAsync(g_table, ctx->d_probe_b.p, bytes, cudaMemcpyDeviceToHost, s));
     if (g_libm) CUDA_TRY(ctx, cudaMemcpyAsync(g_libm, ctx->d_probe_c.p, bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int atmrt_pixel_angles(atmrt_ctx* ctx, double* elevation_angle, double* azimuth) {
+    if (!ctx) return ATMRT_ERR_INVALID;
+    if (!ctx->has_params) return fail(ctx, ATMRT_ERR_STATE, "pixel_angles before set_params");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const atmrt_params& p = ctx->params;
+    DevScene S{};  // only the frame and the image geometry are read
+    S.direction = p.direction, S.tilt = p.tilt, S.fov = p.fov;
+    S.width = p.width, S.height = p.height, S.x0 = p.x0, S.x1 = p.x1, S.generator = p.generator;
+    const size_t wl = (size_t)(p.x1 - p.x0), bytes = sizeof(double) * wl * (size_t)p.height;
+    if ((elevation_angle && ensure(ctx, ctx->d_probe_a, bytes)) || (azimuth && ensure(ctx, ctx->d_probe_b, bytes))) return ATMRT_ERR_CUDA;
+    cudaStream_t s = ctx->s_main;
+    k_pixel_angles<<<dim3((unsigned)((wl + 127) / 128), (unsigned)p.height), 128, 0, s>>>(S, elevation_angle ? (double*)ctx->d_probe_a.p : nullptr,
+                                                                                        azimuth ? (double*)ctx->d_probe_b.p : nullptr);
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (elevation_angle) CUDA_TRY(ctx, cudaMemcpyAsync(elevation_angle, ctx->d_probe_a.p, bytes, cudaMemcpyDeviceToHost, s));
+    if (azimuth) CUDA_TRY(ctx, cudaMemcpyAsync(azimuth, ctx->d_probe_b.p, bytes, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     return 0;
 }

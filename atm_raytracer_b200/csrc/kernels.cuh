@@ -1214,6 +1214,29 @@ __device__ __forceinline__ void get_ray_params(const DevScene& S, int x, int y, 
     *direction = atan2(d[1], d[0]);
 }
 
+// ResultPixel.elevation_angle / azimuth of every pixel of the column block ([H][x1 - x0] each; either may be
+// null). Fast generator, fast.rs:67-76: get_ray_elev(y) and get_ray_dir(x) wrapped ONCE into [0, 360);
+// Rectilinear generator, rectilinear.rs:78-116: the pixel's own (elevation, direction).to_degrees(), not wrapped.
+__global__ void __launch_bounds__(128) k_pixel_angles(const __grid_constant__ DevScene S, double* __restrict__ elevation_angle,
+                                                      double* __restrict__ azimuth) {
+    const int wl = S.x1 - S.x0;
+    const int xl = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (xl >= wl) return;
+    double el, az;
+    if (S.generator == ATMRT_GENERATOR_RECTILINEAR) {
+        get_ray_params(S, S.x0 + xl, y, &el, &az);
+        el = to_degrees(el), az = to_degrees(az);
+    } else {
+        el = get_ray_elev(S, y);
+        az = get_ray_dir(S, S.x0 + xl);
+        if (az < 0.0) az += 360.0;
+        else if (az >= 360.0) az -= 360.0;
+    }
+    const size_t pixel = (size_t)y * wl + xl;
+    if (elevation_angle) elevation_angle[pixel] = el;
+    if (azimuth) azimuth[pixel] = az;
+}
+
 constexpr int RECT_THREADS = 128;
 
 template <bool FLAT, bool OBJECTS>

@@ -50,8 +50,8 @@ def _load():
         "atmrt_render_device": (C.c_int, [vp, vp, vp, vp, P(abi.Stats), vp]),
         "atmrt_stage_times": (C.c_int, [vp, P(abi.StageMs)]),
         "atmrt_render_trace": (C.c_int, [vp, vp, vp, C.c_int]),
+        "atmrt_pixel_angles": (C.c_int, [vp, vp, vp]),
         "atmrt_set_march_mode": (C.c_int, [vp, C.c_int]),
-        "atmrt_set_rows_per_warp": (C.c_int, [vp, C.c_int]),
         "atmrt_get_terrain_profile": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, P(C.c_int)]),
         "atmrt_get_path": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, P(C.c_int)]),
         "atmrt_atmosphere_probe": (C.c_int, [vp, vp, C.c_int, vp, vp, vp]),
@@ -97,64 +97,7 @@ def refraction_table(atmosphere, wavelength):
     return cells, base.value, ch.value, served.value, npieces.value
 
 
-class Terrain:
-    """Decoded DTED tiles on the host (``Terrain``, terrain/mod.rs:55-126).
-
-    ``tiles`` is a list of ``(abi.TileDesc, int16 ndarray [nlon][nlat])``. Decoding is done by the
-    C++ host library (``libatmrt_host.so``: atmrt_host_read_dted) or by the caller.
-    """
-
-    def __init__(self, tiles=None):
-        self.tiles = list(tiles or [])
-
-    @staticmethod
-    def desc(lat0, lon0, posts, lat_interval=None, lon_interval=None):
-        nlon, nlat = posts.shape
-        d = abi.TileDesc()
-        d.lat0, d.lon0 = int(lat0), int(lon0)  # `as i16` truncation of the header origin
-        d.nlon, d.nlat = int(nlon), int(nlat)
-        d.min_lat, d.min_lon = float(lat0), float(lon0)
-        d.lat_interval = 3600.0 / (nlat - 1) if lat_interval is None else float(lat_interval)
-        d.lon_interval = 3600.0 / (nlon - 1) if lon_interval is None else float(lon_interval)
-        return d
-
-    @classmethod
-    def from_arrays(cls, items):
-        """items: iterable of (lat0, lon0, posts[nlon][nlat])."""
-        out = []
-        for lat0, lon0, posts in items:
-            posts = np.ascontiguousarray(posts, dtype=np.int16)
-            out.append((cls.desc(lat0, lon0, posts), posts))
-        return cls(out)
-
-    @classmethod
-    def from_folder(cls, folder):
-        """``Terrain::from_folder`` (terrain/mod.rs:66-83): every entry must be a DTED file."""
-        from . import host
-
-        tiles = []
-        names = sorted(os.listdir(folder))
-        for name in names:
-            tiles.append(host.read_dted(os.path.join(folder, name)))
-        print(f"Detected {len(names)} terrain files")
-        return cls(tiles)
-
-    def c_arrays(self):
-        n = len(self.tiles)
-        descs = (abi.TileDesc * max(n, 1))()
-        ptrs = (C.c_void_p * max(n, 1))()
-        for i, (d, posts) in enumerate(self.tiles):
-            descs[i] = d
-            ptrs[i] = None if posts is None else posts.ctypes.data  # None: descriptor-only terrain (non-root ranks)
-        return descs, ptrs, n
-
-    def descriptors_only(self):
-        """The same tile table without the posts (what a non-root rank needs to bind a broadcast copy)."""
-        return Terrain([(d, None) for d, _ in self.tiles])
-
-    @property
-    def bytes(self):
-        return sum(int(d.nlon) * int(d.nlat) * 2 for d, _ in self.tiles)
+from .terrain import Terrain  # noqa: E402,F401  (re-exported: runtime.Terrain)
 
 
 class Context:
@@ -241,9 +184,6 @@ class Context:
     def set_march_mode(self, mode):
         self._check(lib.atmrt_set_march_mode(self._h, int(mode)))
 
-    def set_rows_per_warp(self, rows):
-        self._check(lib.atmrt_set_rows_per_warp(self._h, int(rows)))
-
     # ---- render ----
     def shape(self):
         p = self.params
@@ -289,6 +229,13 @@ class Context:
         cnt = np.zeros((h, w), dtype=np.int32)
         self._check(lib.atmrt_render_trace(self._h, _ptr(pts), _ptr(cnt), int(max_points)))
         return pts, cnt
+
+    def pixel_angles(self):
+        """ResultPixel.elevation_angle / azimuth of every pixel of the column block, [H][x1-x0] each (degrees)."""
+        h, w = self.shape()
+        el, az = np.empty((h, w)), np.empty((h, w))
+        self._check(lib.atmrt_pixel_angles(self._h, _ptr(el), _ptr(az)))
+        return el, az
 
     # ---- probes ----
     def terrain_profile(self, x):

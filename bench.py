@@ -58,7 +58,8 @@ def parse_args():
 
 
 def build_workload(name, scale, with_posts, generator="Fast"):
-    from atm_raytracer_b200 import config, runtime, scenes
+    from atm_raytracer_b200 import config, scenes
+    from atm_raytracer_b200.terrain import Terrain  # no native library behind it: the reference arm never loads the CUDA .so
 
     cfg, grid = scenes.make_scene(name, scale=scale)
     cfg["output"]["generator"] = generator
@@ -71,10 +72,10 @@ def build_workload(name, scale, with_posts, generator="Fast"):
 
         with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
             posts = list(ex.map(lambda k: synth.make_tile(k[0], k[1], 1), keys))
-        terrain = runtime.Terrain.from_arrays([(k[0], k[1], p) for k, p in zip(keys, posts)])
+        terrain = Terrain.from_arrays([(k[0], k[1], p) for k, p in zip(keys, posts)])
     else:
         shape = np.empty((1201, 1201), np.int16)
-        terrain = runtime.Terrain([(runtime.Terrain.desc(k[0], k[1], shape), None) for k in keys])
+        terrain = Terrain([(Terrain.desc(k[0], k[1], shape), None) for k in keys])
     return cfg, params, terrain, objects, textures
 
 
@@ -157,6 +158,7 @@ def cpu_sample(params, terrain, objects, textures, stride):
     """One bounded CPU sample; returns (pixels/s of the full job, ray-steps/s, description, timing)."""
     import oracle
 
+    oracle.use_native()  # the `baseline` build of the port (-O3 -march=native, compiled on this host), as BASELINE.md states
     # all host cores, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for every rank)
     threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     r = oracle.render(params, terrain.tiles, objects, textures, stride_x=stride, stride_y=stride, meta=True, steps=False, threads=threads)
@@ -170,6 +172,7 @@ def cpu_sample(params, terrain, objects, textures, stride):
     desc = (f"every {stride}th column and row ({r['rgb'].shape[1]}x{r['rgb'].shape[0]} px), all three stages; "
             f"stage times extrapolated to the full image (terrain x{stride}, paths x{stride}, pixels x{stride * stride}); "
             f"sample took {tm['s_total']:.2f} s")
+    desc += f"; oracle build: {oracle.BUILD}"
     return pixels / t_full, steps_full / t_full, desc, tm, threads
 
 
@@ -235,7 +238,6 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():

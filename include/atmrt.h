@@ -228,6 +228,11 @@ int atmrt_render_device(atmrt_ctx* ctx, void* rgb_dev, void* meta_dev, void* ste
 /* Harvest the per-stage CUDA-event timings of every render issued since the last call (the renders
  * themselves stay asynchronous); synchronises the device. */
 int atmrt_stage_times(atmrt_ctx* ctx, atmrt_stage_ms* out);
+/* ResultPixel.elevation_angle and ResultPixel.azimuth (generators/mod.rs:14-19) of every pixel of the column
+ * block, degrees, host buffers [H][x1-x0] each (either may be NULL). Fast generator (fast.rs:67-76):
+ * get_ray_elev(y), and get_ray_dir(x) wrapped once into [0, 360); Rectilinear generator (rectilinear.rs:78-116):
+ * the pixel's own elevation / direction, not wrapped. Needs set_params only. */
+int atmrt_pixel_angles(atmrt_ctx* ctx, double* elevation_angle, double* azimuth);
 /* Full trace-point lists (ResultPixel.trace_points) for small images: points[H][x1-x0][max_points],
  * counts[H][x1-x0] (true count, may exceed max_points). Host buffers. */
 int atmrt_render_trace(atmrt_ctx* ctx, atmrt_trace_point* points, int32_t* counts, int max_points);
@@ -241,8 +246,6 @@ int atmrt_set_march_mode(atmrt_ctx* ctx, int mode);
  * libm, op for op the oracle's arithmetic, single steps (validation); 2 the table, single steps only
  * (validation of the macro steps). */
 int atmrt_set_path_mode(atmrt_ctx* ctx, int mode);
-/* Tuning hook for the ray-path stage: image rows integrated per warp (1..32, default 32). */
-int atmrt_set_rows_per_warp(atmrt_ctx* ctx, int rows);
 
 /* ---- probes (the reference's TSV dumpers: elev_profile.rs:43-64, ray_path.rs:65-103,
  *      atm_printer.rs:35-46) ------------------------------------------------------------ */

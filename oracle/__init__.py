@@ -35,6 +35,32 @@ class Timing(C.Structure):
 
 
 _lib = None
+BUILD = "-O2 -ffp-contract=off (portable: liboracle.so)"
+NATIVE_LIB_PATH = os.path.join(_HERE, "liboracle_native.so")
+
+
+def use_native():
+    """Switch this process to the `baseline` build of the same source (-O3 -march=native, oracle/Makefile), compiled
+    here and now for this host's cores -- what bench.py's CPU legs time. Falls back to the portable build (and says
+    so in BUILD) when the compiler is not available. Must be called before the first use of lib()."""
+    global _lib, BUILD
+    if _lib is not None and BUILD.startswith("-O3"):
+        return BUILD
+    try:
+        subprocess.check_call(["make", "-C", _HERE, "-B", "-s", "baseline"], stdout=subprocess.DEVNULL)
+        _lib = _bind(C.CDLL(NATIVE_LIB_PATH))
+        BUILD = "-O3 -march=native -ffp-contract=off (liboracle_native.so, built on this host)"
+    except Exception as e:  # noqa: BLE001
+        BUILD = f"-O2 -ffp-contract=off (portable liboracle.so; native build failed: {type(e).__name__})"
+    return BUILD
+
+
+def _bind(L):
+    L.oracle_air_index.restype = C.c_double
+    L.oracle_air_index.argtypes = [C.c_double] * 4
+    L.oracle_num_threads.restype = C.c_int
+    L.oracle_set_num_threads.argtypes = [C.c_int]
+    return L
 
 
 def lib():
@@ -213,6 +239,14 @@ def ray_angles(params):
     d, e = np.empty(params.width), np.empty(params.height)
     lib().oracle_ray_angles(C.byref(params), _p(d), _p(e))
     return d, e
+
+
+def pixel_angles(params):
+    """ResultPixel.elevation_angle / azimuth, [H][x1-x0] each (fast.rs:67-76, rectilinear.rs:78-116)."""
+    shape = (params.height, params.x1 - params.x0)
+    el, az = np.empty(shape), np.empty(shape)
+    lib().oracle_pixel_angles(C.byref(params), _p(el), _p(az))
+    return el, az
 
 
 def check_collision(obj, texture, obj_alt_abs, earth_model, radius, p1, p2):

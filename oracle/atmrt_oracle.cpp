@@ -1440,6 +1440,31 @@ int oracle_ray_angles(const atmrt_params* p, double* dir /*[W]*/, double* elev /
     return 0;
 }
 
+// ResultPixel.elevation_angle / azimuth of every pixel of the column block, [H][x1-x0] each.
+// Fast generator (fast.rs:67-76): elevation_angle = get_ray_elev(y); azimuth = get_ray_dir(x) wrapped ONCE into
+// [0, 360) (`if azimuth < 0.0 { += 360.0 } else if azimuth >= 360.0 { -= 360.0 }`).
+// Rectilinear generator (rectilinear.rs:78-116): the pixel's own (elevation, direction).to_degrees(), not wrapped.
+int oracle_pixel_angles(const atmrt_params* p, double* elevation_angle, double* azimuth) {
+    const int wl = p->x1 - p->x0;
+    for (int y = 0; y < p->height; ++y) {
+        for (int c = 0; c < wl; ++c) {
+            double el, az;
+            if (p->generator == ATMRT_GENERATOR_RECTILINEAR) {
+                const RayParams r = get_ray_params(*p, p->x0 + c, y);
+                el = to_degrees(r.elevation), az = to_degrees(r.direction);
+            } else {
+                el = get_ray_elev(*p, y);
+                az = get_ray_dir(*p, p->x0 + c);
+                if (az < 0.0) az += 360.0;
+                else if (az >= 360.0) az -= 360.0;
+            }
+            if (elevation_angle) elevation_angle[(size_t)y * wl + c] = el;
+            if (azimuth) azimuth[(size_t)y * wl + c] = az;
+        }
+    }
+    return 0;
+}
+
 // Object::check_collision for one segment; returns number of collisions (<= 8 written)
 int oracle_check_collision(const atmrt_object* obj, const uint8_t* texture, double obj_alt_abs, int earth_model,
                            double radius, const double* p1 /*lat,lon,elev*/, const double* p2, double* props,

@@ -430,6 +430,36 @@ def test_column_shards_equal_full_render(ctx):
     assert sum(r["stats"]["ray_steps"] for r in parts) == full["stats"]["ray_steps"]
 
 
+@pytest.mark.parametrize("name,direction,fov,rect", [("c5", 0.0, 360.0, False), ("c2", 355.0, 30.0, False), ("c2", -170.0, 40.0, False), ("c2", 20.0, 10.0, True)])
+def test_pixel_angles_match_oracle(ctx, oracle_lib, name, direction, fov, rect):
+    """ResultPixel.elevation_angle / azimuth (fast.rs:67-76: azimuth wrapped once into [0, 360); rectilinear.rs:78-116:
+    the pixel's own angles): integer pixel arithmetic and two multiplications, so bit-identical for the Fast generator."""
+    p, terrain, _, _ = scene(name, 0.02 if name == "c5" else 0.1)
+    p.direction, p.fov = direction, fov
+    if rect:
+        p.generator = abi.GENERATOR_RECTILINEAR
+        p.tilt = -3.0
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    el, az = ctx.pixel_angles()
+    wel, waz = oracle_lib.pixel_angles(p)
+    if rect:
+        np.testing.assert_allclose(el, wel, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(az, waz, rtol=0, atol=1e-12)
+    else:
+        np.testing.assert_array_equal(el, wel)
+        np.testing.assert_array_equal(az, waz)
+        assert az.min() >= 0.0 and az.max() < 360.0
+        assert (np.diff(el[:, 0]) < 0).all()  # row 0 is the top of the image
+    # a column block reports its own columns
+    q = abi.Params.from_buffer_copy(p)
+    q.x0, q.x1 = p.width // 4, p.width // 2
+    ctx.set_params(q)
+    el2, az2 = ctx.pixel_angles()
+    np.testing.assert_array_equal(az2, az[:, q.x0:q.x1])
+    np.testing.assert_array_equal(el2, el[:, q.x0:q.x1])
+
+
 def test_fog_simple_colouring_and_relative_altitude(ctx, oracle_lib):
     p, terrain, objects, textures = scene("c2", 0.1)
     p.coloring = abi.COLORING_SIMPLE
@@ -461,19 +491,62 @@ def test_rays_leaving_coverage_see_sea_level(ctx, oracle_lib):
 # ---------------------------------------------------------------------------------------------
 # full BASELINE sizes, checked through size-independent properties
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name,stride", [("c2", 12), ("c4", 15)])
+def _strided(got, stride):
+    return {"rgb": got["rgb"][::stride, ::stride], "meta": got["meta"][::stride, ::stride], "steps": got["steps"][::stride, ::stride]}
+
+
+# Every BASELINE.json config at its real size (c1 640x480 in full; the others on every stride-th row and column,
+# which the oracle renders in seconds); c5 (16384 x 4096) has its own test below.
+@pytest.mark.parametrize("name,stride", [("c1", 1), ("c2", 12), ("c3_flat", 12), ("c3_sph", 12), ("c4", 15)])
 def test_full_size_render_against_strided_oracle(ctx, oracle_lib, name, stride):
     """The full-size GPU image, sub-sampled, must equal the oracle run on exactly those pixels."""
     p, terrain, objects, textures = scene(name, 1.0)
+    assert (p.width, p.height) == {"c1": (640, 480), "c2": (1920, 1080), "c3_flat": (3840, 1080), "c3_sph": (3840, 1080), "c4": (1920, 1080)}[name]
     ctx.set_terrain(terrain)
     ctx.set_params(p)
     ctx.set_objects(objects, textures)
     got = ctx.render()
     want = oracle_lib.render(p, terrain.tiles, objects, textures, stride_x=stride, stride_y=stride)
-    sub = {"rgb": got["rgb"][::stride, ::stride], "meta": got["meta"][::stride, ::stride], "steps": got["steps"][::stride, ::stride]}
-    compare_render(sub, want, f"{name}-full/{stride}", finish_moves_frac=0.01 if objects else 0.001)
+    sub = _strided(got, stride)
+    rep = compare_render(sub, want, f"{name}-full/{stride}", finish_moves_frac=0.01 if objects else 0.001)
     st = got["stats"]
     assert st["pixels_hit"] > 0 and st["ray_steps"] <= p.width * p.height * (st["n_terrain"] - 1)
+    if stride == 1:  # the whole image was compared: the step accounting must agree up to the counted moves
+        moved = rep["silhouette_flips"] + rep["finish_step_moves"]
+        assert abs(st["ray_steps"] - want["stats"]["ray_steps"]) <= moved * st["n_terrain"]
+
+
+@pytest.mark.parametrize("path_mode", [0, 1])
+def test_full_size_c5_against_strided_oracle(ctx, oracle_lib, path_mode):
+    """BASELINE config 5 -- the configuration the benchmark is quoted on -- at its FULL size (16384 x 4096, 64 tiles,
+    16000 samples per ray) against the oracle on every 64th row and column (256 x 64 pixels, each one the oracle's
+    full-length march). Twice: with the default ray-path stage (g(h) table + macro steps) and with path_mode 1,
+    where every refractive-index evaluation goes through libm, op for op the oracle's arithmetic."""
+    stride = 64
+    p, terrain, _, _ = scene("c5", 1.0)
+    assert (p.width, p.height) == (16384, 4096)
+    ctx.set_terrain(terrain)
+    ctx.set_objects([])
+    ctx.set_params(p)
+    ctx.set_march_mode(0)
+    ctx.set_path_mode(path_mode)
+    try:
+        got = ctx.render()
+    finally:
+        ctx.set_path_mode(0)
+    want = oracle_lib.render(p, terrain.tiles, stride_x=stride, stride_y=stride)
+    sub = _strided(got, stride)
+    rep = compare_render(sub, want, f"c5-full/{stride}-path_mode{path_mode}")
+    if rep["silhouette_flips"] + rep["finish_step_moves"] == 0:  # `steps` = zip iterations consumed per pixel
+        np.testing.assert_array_equal(sub["steps"], want["steps"])
+    assert 0.3 < float((~np.isnan(sub["meta"]["distance"])).mean()) < 0.7
+    # the rows the oracle integrated: the path caches agree within the noise floor of the reference's own evaluation
+    for y in (0, 2048 - 64, 2048, 2048 + 64, 4032):
+        g, w = ctx.path(y), oracle_lib.path_cache(p, terrain.tiles, y)
+        n = len(g["dist"])
+        ok = ~np.isnan(g["elev"])
+        np.testing.assert_array_equal(ok, ~np.isnan(w["elev"][:n]))
+        np.testing.assert_allclose(g["elev"][ok], w["elev"][:n][ok], rtol=1e-9, atol=PATH_ATOL)
 
 
 def test_errors_are_reported_not_swallowed(ctx):

@@ -410,6 +410,29 @@ def test_pixel_angles_i16_centring(oracle_lib):
     assert e[240] == 1.0 and e[0] == 1.0 - ((-240 / 480) * 30.0) / (641 / 480)
 
 
+def test_result_pixel_angles_wrap_once(oracle_lib):
+    """ResultPixel.azimuth is get_ray_dir(x) wrapped ONCE into [0, 360) (fast.rs:67-72); elevation_angle = get_ray_elev(y)."""
+    p = abi.Params()
+    p.width, p.height, p.x0, p.x1 = 640, 480, 0, 640
+    p.fov, p.direction, p.tilt = 30.0, 350.0, 1.0
+    el, az = oracle_lib.pixel_angles(p)
+    d, e = oracle_lib.ray_angles(p)
+    assert az[0, 0] == 335.0 and az[5, 320] == 350.0
+    assert az[0, 639] == d[639] - 360.0 and 0.0 <= az.min() and az.max() < 360.0  # 364.95... wraps down
+    np.testing.assert_array_equal(el[:, 17], e)
+    p.direction = -10.0
+    _, az = oracle_lib.pixel_angles(p)
+    assert az[0, 0] == 335.0 and az[0, 320] == 350.0 and az[0, 639] == -10.0 + (319 / 640) * 30.0
+    p.direction = 730.0  # wrapped once only, like the reference
+    _, az = oracle_lib.pixel_angles(p)
+    assert az[0, 320] == 370.0
+    # Rectilinear: the pixel's own angles (rectilinear.rs:78-116); the centre pixel looks along (tilt, direction)
+    p.direction, p.tilt, p.generator = 20.0, -3.0, abi.GENERATOR_RECTILINEAR
+    el, az = oracle_lib.pixel_angles(p)
+    assert abs(el[240, 320] + 3.0) < 1e-12 and abs(az[240, 320] - 20.0) < 1e-12
+    assert az[240, 0] < 20.0 - 14.0 and el[0, 320] > 0.0
+
+
 def test_horizon_on_a_smooth_sphere(oracle_lib):
     """Straight rays over sea-level (no tiles => elevation 0): a pixel row hits iff its ray dips
     below the geometric horizon, and the hit distance follows the sphere intersection."""
