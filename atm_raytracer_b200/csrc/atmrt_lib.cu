@@ -83,6 +83,9 @@ struct atmrt_ctx {
     int path_mode = 0;  // 0: g(h) from the table, 1: every evaluation through libm (validation)
     DevBuf d_atm_cells;
     DevBuf d_sweep_flags, d_sweep_col, d_sweep_hit;
+    DevBuf d_rgb_t, d_partial;  // fused stage C: column-major colour scratch, per-(column, band) counters
+    int sweep_bands = 0;        // 0: chosen per render (launch_render)
+    bool stage_c_legacy = false;
     DevBuf d_stage;  // raw posts of pack_terrain on their way to the tiled layout
     bool sweep_enabled = true;
     DevBuf d_dist, d_colcalc, d_tlat, d_tlon, d_telev, d_tclose;
@@ -853,7 +856,24 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->c0, main));
     MarchOut O{rt.rgb, rt.meta, rt.steps, rt.points, rt.counts, rt.max_points};
     const dim3 grid((h + MARCH_THREADS - 1) / MARCH_THREADS, wl);
-    if (sweep) {
+    if (sweep && !ctx->stage_c_legacy) {
+        // Fused sweep + shading, one warp per (column, row band). Enough bands that the grid holds about three times
+        // the warps the GPU keeps resident (a column block of an 8-GPU frame is 2048 columns wide), none below 128 rows.
+        int bands = ctx->sweep_bands;
+        if (bands <= 0) bands = (int)std::min<long long>(std::max<long long>(1, ((long long)ctx->num_sms * 96 + wl - 1) / wl), std::max(1, h / 128));
+        const int band_rows = ((h + bands - 1) / bands + 31) / 32 * 32;
+        bands = (h + band_rows - 1) / band_rows;
+        if (rt.rgb && (rc = ensure(ctx, ctx->d_rgb_t, (size_t)wl * S.h_pad * 3))) return rc;
+        if ((rc = ensure(ctx, ctx->d_partial, sizeof(unsigned long long) * 2 * (size_t)wl * bands))) return rc;
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_sweep_col.p, 0, (size_t)wl, main));
+        FusedOut F{rt.rgb ? (unsigned char*)ctx->d_rgb_t.p : nullptr, (unsigned long long*)ctx->d_partial.p, band_rows, bands};
+        const dim3 fgrid((wl + FUSED_WARPS - 1) / FUSED_WARPS, bands);
+        if (S.earth.walker == WALK_SPHERICAL) k_sweep_fused<WALK_SPHERICAL><<<fgrid, 32 * FUSED_WARPS, 0, main>>>(S, B, O, F, 0, wl);
+        else k_sweep_fused<-1><<<fgrid, 32 * FUSED_WARPS, 0, main>>>(S, B, O, F, 0, wl);
+        if (rt.rgb) k_rgb_rows<<<dim3((wl + 31) / 32, (h + 31) / 32), 256, 0, main>>>(F.rgb_t, rt.rgb, wl, h, S.h_pad, B.sweep_flags);
+        k_sweep_counters<<<(wl + 127) / 128, 128, 0, main>>>(B, F.partial, wl, bands);
+        ctx->launches += rt.rgb ? 3 : 2;
+    } else if (sweep) {
         // (Splitting the image into column chunks so that the shading of one chunk overlaps the sweep of the
         // next was measured and is slower: 8.9 ms -> 9.8 / 10.5 ms with 2 / 4 chunks at c5 -- the sweep's long
         // columns leave each smaller grid with a longer tail.)
@@ -883,6 +903,8 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
             CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_a, 0));
             rt.host_copied = true;
         }
+    }
+    if (sweep) {
         // fallbacks, no-ops unless the device-side checks ask for them: pyramids + hierarchical march of the
         // whole image (rays cross), brute-force march of flagged columns
         terrain_pyramids(main, 1);
@@ -998,6 +1020,8 @@ int atmrt_create(int device, atmrt_ctx** out) {
         delete ctx;
         return fail(nullptr, ATMRT_ERR_CUDA, "stream/event creation failed");
     }
+    if (const char* e = getenv("ATMRT_SWEEP_BANDS")) ctx->sweep_bands = atoi(e);  // tuning (scratch/): row bands per column of the fused stage C
+    if (const char* e = getenv("ATMRT_STAGE_C")) ctx->stage_c_legacy = std::string(e) == "legacy";
     *out = ctx;
     return 0;
 }
@@ -1009,7 +1033,7 @@ void atmrt_destroy(atmrt_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_objects_in, &ctx->d_objects, &ctx->d_dist, &ctx->d_colcalc, &ctx->d_tlat, &ctx->d_tlon, &ctx->d_telev,
                       &ctx->d_tclose, &ctx->d_pdist, &ctx->d_pelev, &ctx->d_plen, &ctx->d_pn,
                       &ctx->d_tmin1, &ctx->d_tmax1, &ctx->d_tmin2, &ctx->d_tmax2, &ctx->d_tmin3, &ctx->d_tmax3, &ctx->d_close1, &ctx->d_close2, &ctx->d_close3, &ctx->d_rmin1, &ctx->d_rmin3, &ctx->d_rmax3,
-                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_sweep_flags, &ctx->d_sweep_col, &ctx->d_sweep_hit, &ctx->d_stage, &ctx->d_atm_aux, &ctx->d_rgb, &ctx->d_meta,
+                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_sweep_flags, &ctx->d_sweep_col, &ctx->d_sweep_hit, &ctx->d_rgb_t, &ctx->d_partial, &ctx->d_stage, &ctx->d_atm_aux, &ctx->d_rgb, &ctx->d_meta,
                       &ctx->d_steps, &ctx->d_points, &ctx->d_counts, &ctx->d_probe_a, &ctx->d_probe_b, &ctx->d_probe_c, &ctx->d_probe_d};
     for (DevBuf* b : bufs) release(*b);
     for (DevBuf& b : ctx->textures) release(b);

@@ -38,6 +38,11 @@ struct DevShade {
     int _pad2;
 };
 
+// x / 255.0 and the palette's x / (thr_b - thr_a): IEEE divisions by a constant, evaluated as div_by (device_math.cuh:
+// Markstein's correctly rounded quotient from RN(1/b), 3 instructions) -- the same bits as the division the reference
+// performs, without its slow-path bookkeeping.
+__device__ __forceinline__ double over_255(double x) { return div_by(x, 255.0, 1.0 / 255.0); }
+
 struct Collision {
     double prop;
     V3 normal;
@@ -59,10 +64,10 @@ __device__ inline void texture_get_pixel(const DevObject& o, double x, double y,
     int iy1 = (int)y1, iy2 = (int)y2;
     double px = x - x1, py = y - y1;
     for (int c = 0; c < 4; ++c) {
-        double p00 = (double)o.tex[((size_t)iy1 * o.tex_w + ix1) * 4 + c] / 255.0;
-        double p01 = (double)o.tex[((size_t)iy2 * o.tex_w + ix1) * 4 + c] / 255.0;
-        double p10 = (double)o.tex[((size_t)iy1 * o.tex_w + ix2) * 4 + c] / 255.0;
-        double p11 = (double)o.tex[((size_t)iy2 * o.tex_w + ix2) * 4 + c] / 255.0;
+        double p00 = over_255((double)o.tex[((size_t)iy1 * o.tex_w + ix1) * 4 + c]);
+        double p01 = over_255((double)o.tex[((size_t)iy2 * o.tex_w + ix1) * 4 + c]);
+        double p10 = over_255((double)o.tex[((size_t)iy1 * o.tex_w + ix2) * 4 + c]);
+        double p11 = over_255((double)o.tex[((size_t)iy2 * o.tex_w + ix2) * 4 + c]);
         double v = p00 * (1.0 - px) * (1.0 - py) + p01 * (1.0 - px) * py + p10 * px * (1.0 - py) + p11 * px * py;
         out[c] = as_u8(v * 255.0);
     }
@@ -150,13 +155,14 @@ __device__ inline int billboard_collision(const DevObject& o, V3 pos1, V3 pos2, 
     y = y / o.height;
     unsigned char px[4];
     texture_get_pixel(o, x, y, px);
-    results[0] = {prop, front, Color4{(double)px[0] / 255.0, (double)px[1] / 255.0, (double)px[2] / 255.0, (double)px[3] / 255.0}};
+    results[0] = {prop, front, Color4{over_255((double)px[0]), over_255((double)px[1]), over_255((double)px[2]), over_255((double)px[3])}};
     return 1;
 }
 
 // ---- colouring -------------------------------------------------------------------------------
 __device__ inline V3 elev_to_color(int palette, double elev) {  // shading.rs:30-83
-    double thr1 = 300.0, thr2, thr3 = 1800.0, thr4 = 3000.0;
+    const double thr1 = 300.0, thr3 = 1800.0, thr4 = 3000.0;
+    double thr2;
     V3 c0, c1, c2, c3;
     if (palette == ATMRT_PALETTE_LEGACY) {
         thr2 = 1200.0;
@@ -171,17 +177,18 @@ __device__ inline V3 elev_to_color(int palette, double elev) {  // shading.rs:30
         c2 = {0.41, 0.52, 0.4};
         c3 = {0.85, 0.92, 0.95};
     }
+    const bool legacy = palette == ATMRT_PALETTE_LEGACY;
     if (elev < thr1) return c0;
-    if (elev < thr2) {
-        double prop = (elev - thr1) / (thr2 - thr1);
+    if (elev < thr2) {  // (elev - thr1) / (thr2 - thr1)
+        double prop = legacy ? div_by(elev - thr1, 900.0, 1.0 / 900.0) : div_by(elev - thr1, 700.0, 1.0 / 700.0);
         return c1 * prop + c0 * (1.0 - prop);
     }
-    if (elev < thr3) {
-        double prop = (elev - thr2) / (thr3 - thr2);
+    if (elev < thr3) {  // (elev - thr2) / (thr3 - thr2)
+        double prop = legacy ? div_by(elev - thr2, 600.0, 1.0 / 600.0) : div_by(elev - thr2, 800.0, 1.0 / 800.0);
         return c2 * prop + c1 * (1.0 - prop);
     }
-    if (elev < thr4) {
-        double prop = (elev - thr3) / (thr4 - thr3);
+    if (elev < thr4) {  // (elev - thr3) / (thr4 - thr3)
+        double prop = div_by(elev - thr3, 1200.0, 1.0 / 1200.0);
         return c3 * prop + c2 * (1.0 - prop);
     }
     return c3;
@@ -253,7 +260,7 @@ __device__ inline Rgb8 apply_fog(double fog_dist, double pixel_dist, Rgb8 color)
 __device__ inline Rgb8 add_rgb(Rgb8 rgb1, Rgb8 rgb2, double a) {  // renderer/mod.rs:378-383
     Rgb8 out;
     for (int i = 0; i < 3; ++i) {
-        double c1 = (double)rgb1.c[i] / 255.0, c2 = (double)rgb2.c[i] / 255.0;
+        double c1 = over_255((double)rgb1.c[i]), c2 = over_255((double)rgb2.c[i]);
         out.c[i] = as_u8((c1 + c2 * a) * 255.0);
     }
     return out;

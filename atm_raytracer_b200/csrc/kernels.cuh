@@ -1581,6 +1581,340 @@ __global__ void __launch_bounds__(32 * SHADE_COLS, 4) k_sweep_shade(const __grid
 }
 
 // ---------------------------------------------------------------------------------------------
+// Stage C for opaque terrain without objects, fused: the horizon sweep AND the shading of the pixels it
+// resolves, one warp per (column, row band).
+//
+// The sweep of one column is a staircase walk through (row, step) whose every window load depends on the row
+// resolved before it: a latency chain. The shading of the resolved pixels (two deferred terrain normals,
+// interpolation, colouring, metadata) is independent arithmetic. In one kernel the schedulers fill the sweep's
+// load stalls of some warps with the shading of others, the first-hit plane (`sweep_hit`) never goes to memory,
+// and sky pixels cost one store loop instead of a shading pass. A column is cut into row bands so that the
+// grid stays large when the columns are sharded over several GPUs: by the monotonicity the sweep rests on, the
+// walk of a band starts at the first-hit step of the row just below it, which the band finds by scanning that
+// ONE row from step 1 (the same cells test the same products, so the band sees exactly the state the single
+// walk would hand it).
+//
+// Resolved pixels are queued in the lanes -- entry j of a batch in lane 31 - j, so that lanes ascend with the row
+// as in a warp of 32 adjacent rows -- and shaded 29 to 32 at a time between two row groups. The colour goes to a
+// column-major scratch image (a warp's 32 rows are 96 contiguous bytes there; the row-major image would take one
+// 1-byte sector write per pixel and channel) which k_rgb_rows transposes; the 32-byte metadata records are whole
+// sectors and go straight to the row-major plane.
+// ---------------------------------------------------------------------------------------------
+constexpr int FUSED_WARPS = 4;  // adjacent columns of one band share a block (and the path windows in L1)
+#ifndef FUSED_MIN_BLOCKS
+#define FUSED_MIN_BLOCKS 6
+#endif
+
+struct FusedOut {
+    unsigned char* rgb_t;         // [wl][h_pad][3] column-major scratch (null: no colour wanted)
+    unsigned long long* partial;  // [wl][bands][2]: ray steps, pixels hit -- summed over the unflagged columns by k_sweep_counters
+    int band_rows;                // rows per band (a multiple of SWEEP_ROWS)
+    int bands;
+};
+
+template <int W>
+__global__ void __launch_bounds__(32 * FUSED_WARPS, FUSED_MIN_BLOCKS) k_sweep_fused(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, FusedOut F, int col0, int col1) {
+    if (B.sweep_flags[0] != 0) return;
+    __shared__ double s_nrm[FUSED_WARPS][64][3];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int xl = col0 + blockIdx.x * FUSED_WARPS + w;
+    if (xl >= col1) return;
+    const int wl = S.x1 - S.x0;
+    // bands are numbered from the top of the image; blockIdx.y = 0 is the bottom band (the walk's first, and the
+    // busiest: every one of its rows hits), so that the long warps are scheduled first
+    const int band = F.bands - 1 - (int)blockIdx.y;
+    const int y_lo = band * F.band_rows;
+    const int y_hi = min(S.height, y_lo + F.band_rows) - 1;
+    const double* __restrict__ te = B.t_elev + (size_t)xl * S.n_pad;
+    const double* __restrict__ pe = B.p_elev;
+    const int n_t = S.n_t, k_last = n_t - 1;
+    static_assert(SWEEP_ROWS == PATH_ROWS && SWEEP_ROWS == 4, "the sweep reads one row group of the path cache per 32-byte load");
+    bool flagged = !(pe[0] - te[0] > 0.0);  // every ray starts at the observer altitude (element 0 of every row)
+    unsigned long long acc_steps = 0ull;
+    unsigned acc_hits = 0u;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const Rgb8 sky{{S.shade.def_color[0], S.shade.def_color[1], S.shade.def_color[2]}};
+
+    // one pixel of this column: colour to the scratch image, metadata and step count to the row-major planes
+    auto store_pixel = [&](int y, Rgb8 px, double m0, double m1, double m2, double m3, int consumed) {
+        if (F.rgb_t) {
+            unsigned char* o = F.rgb_t + ((size_t)xl * S.h_pad + y) * 3;
+            o[0] = px.c[0], o[1] = px.c[1], o[2] = px.c[2];
+        }
+        const size_t pixel = (size_t)y * wl + xl;
+        if (O.meta) {
+            double2* out = reinterpret_cast<double2*>(O.meta + pixel);
+            out[0] = make_double2(m0, m1);
+            out[1] = make_double2(m2, m3);
+        }
+        if (O.steps) O.steps[pixel] = consumed;
+    };
+
+    // ---- where the walk enters this band: the first-hit step of the row just below it --------------------
+    int k = 1;  // first step the current row may still cross at
+    if (y_hi + 1 < S.height && !flagged) {
+        const int yb = y_hi + 1;
+        const int nlim = min(n_t, B.p_n[yb]);
+        bool odd = false, found = false;
+        while (k < nlim) {
+            const int kk = min(k + lane, k_last);
+            const double cur = pe[path_index(n_t, kk, yb)], t_cur = te[kk];
+            double prv = __shfl_up_sync(FULL, cur, 1), t_prv = __shfl_up_sync(FULL, t_cur, 1);
+            if (lane == 0) prv = pe[path_index(n_t, k - 1, yb)], t_prv = te[k - 1];
+            const double d1 = prv - t_prv, d2 = cur - t_cur;
+            const bool in = k + lane < nlim;
+            const unsigned hits = __ballot_sync(FULL, in && d1 > 0.0 && d1 * d2 < 0.0);  // the reference's product test (utils.rs:222), from above
+            const bool oddcell = in && (d2 == 0.0 || (d1 * d2 < 0.0 && !(d1 > 0.0)));
+            odd = odd || (oddcell && (hits == 0 || lane < __ffs(hits) - 1));
+            if (hits) {
+                k += __ffs(hits) - 1;
+                found = true;
+                break;
+            }
+            k += 32;
+        }
+        if (!found) k = max(nlim, 1);  // its path ends without a sign change: the rows above go on from there
+        if (__any_sync(FULL, odd)) flagged = true;
+    }
+
+    // ---- the queue of resolved pixels and its shading ------------------------------------------------------
+    int qy = 0, qk = 0, qn = 0;  // this lane's entry (row, first-hit step or 0), entries queued
+    auto push = [&](int y, int kh) {
+        if (lane == 31 - qn) qy = y, qk = kh;
+        ++qn;
+    };
+    auto flush = [&]() {
+        const bool valid = lane >= 32 - qn;
+        const int yy = __shfl_sync(FULL, qy, 31);  // a queued row for the idle lanes to shadow
+        const int y = valid ? qy : yy;
+        const int kh = valid ? qk : 0;
+        const bool hit = kh > 0;
+        const int nlim = min(n_t, B.p_n[y]);
+        // The terrain normals of the two samples that bracket each hit (TerrainData::normal, deferred from stage A:
+        // sample_normal). The rows of a batch hit a handful of distinct samples -- foreground rows share one step,
+        // rows on a slope hit consecutive steps, and sample k - 1 of one run of rows is sample k of the next -- so
+        // each distinct sample is evaluated once: the first lane of every run of equal k owns sample k, and sample
+        // k - 1 unless the next run owns it as its k; the owned samples are numbered, dealt to the lanes 32 at a
+        // time, and read back through shared memory.
+        V3 nrm[2] = {V3{0.0, 0.0, 0.0}, V3{0.0, 0.0, 0.0}};
+        {
+            const int k_up = __shfl_up_sync(FULL, kh, 1);
+            const bool lead = hit && (lane == 0 || k_up != kh);
+            const unsigned mask1 = __ballot_sync(FULL, lead);
+            if (mask1) {  // warp-uniform
+                const int leader = 31 - __clz(mask1 & (0xffffffffu >> (31 - lane)));         // of this lane's run (when it hit)
+                const unsigned later = leader >= 31 || leader < 0 ? 0u : (mask1 & (0xfffffffeu << leader));
+                const int next = later ? __ffs(later) - 1 : -1;                               // leader of the next run
+                const int k_next = __shfl_sync(FULL, kh, next < 0 ? 0 : next);
+                const bool own0 = lead && !(next >= 0 && k_next == kh - 1);
+                const unsigned mask0 = __ballot_sync(FULL, own0);
+                const int n1cnt = __popc(mask1), total = n1cnt + __popc(mask0);
+                __syncwarp();
+                for (int base = 0; base < total; base += 32) {
+                    const int item = base + lane;
+                    const bool mine = item < total, second = item >= n1cnt;
+                    const unsigned src = mine ? __fns(second ? mask0 : mask1, 0, (second ? item - n1cnt : item) + 1) : 0u;
+                    const int ks = __shfl_sync(FULL, kh, src & 31);
+                    if (mine) {
+                        const int smp = ks - (second ? 1 : 0);
+                        const size_t ti = (size_t)xl * S.n_pad + smp;
+                        const V3 n = sample_normal<W>(S, B.terrain, B, xl, smp, B.t_lat[ti], B.t_lon[ti]);
+                        s_nrm[w][item][0] = n.x, s_nrm[w][item][1] = n.y, s_nrm[w][item][2] = n.z;
+                    }
+                }
+                __syncwarp();
+                if (hit) {
+                    const int i1 = __popc(mask1 & ((1u << leader) - 1u));
+                    const int i0 = ((mask0 >> leader) & 1u) ? n1cnt + __popc(mask0 & ((1u << leader) - 1u)) : i1 + 1;
+                    nrm[0] = V3{s_nrm[w][i0][0], s_nrm[w][i0][1], s_nrm[w][i0][2]};
+                    nrm[1] = V3{s_nrm[w][i1][0], s_nrm[w][i1][1], s_nrm[w][i1][2]};
+                }
+            }
+        }
+        // get_single_pixel's hit (utils.rs:220-236) and draw_image (renderer/mod.rs:395-411) for ONE opaque trace point:
+        // with terrain_alpha == 1 the compositing is  result = add([0,0,0], c, 1.0 * 1.0)  and then
+        // add(result, default, 0.0), and ((0/255 + c/255 * 1) * 255) as u8 == c, ((c/255 + d/255 * 0) * 255) as u8 == c
+        // for all 256 values of c (tests/test_oracle_known_answers.py: test_identity_requantisation_all_values), so the
+        // pixel IS the (fogged) colour of its trace point; a pixel without one is add([0,0,0], default, 1.0) == default.
+        Rgb8 px = sky;
+        double m_lat = qnan, m_lon = qnan, m_elev = qnan, m_dist = qnan;
+        int consumed = nlim > 0 ? nlim - 1 : 0;
+        if (hit) {
+            const size_t ti = (size_t)xl * S.n_pad + kh;
+            const size_t p1 = path_index(n_t, kh, y), p0 = p1 - PATH_ROWS;
+            const double lat0 = B.t_lat[ti - 1], lon0 = B.t_lon[ti - 1], elev0 = B.t_elev[ti - 1];
+            const double lat1 = B.t_lat[ti], lon1 = B.t_lon[ti], elev1 = B.t_elev[ti];
+            const double ray0 = pe[p0], ray1 = pe[p1];
+            const double dist0 = B.path_x[kh - 1], dist1 = B.path_x[kh];  // path_x[0] = 0
+            const double len0 = kh - 1 == 0 ? 0.0 : B.p_len[p0], len1 = B.p_len[p1];
+            const double diff1 = ray0 - elev0, diff2 = ray1 - elev1;
+            const double prop = diff1 / (diff1 - diff2);
+            // TracingState::interpolate, utils.rs:108-125
+            m_lat = lat0 + (lat1 - lat0) * prop, m_lon = lon0 + (lon1 - lon0) * prop;
+            m_dist = dist0 + (dist1 - dist0) * prop, m_elev = elev0 + (elev1 - elev0) * prop;
+            const double plen = len0 + (len1 - len0) * prop;
+            const V3 normal = nrm[0] + (nrm[1] - nrm[0]) * prop;
+            px = color_for_pixel(S.shade, true, m_elev, m_dist, normal, Color4{0.0, 0.0, 0.0, 1.0});
+            if (S.shade.fog_enabled) px = apply_fog(S.shade.fog_distance, plen, px);
+            consumed = kh;
+        }
+        if (valid) store_pixel(y, px, m_lat, m_lon, m_elev, m_dist, consumed);
+        acc_steps += valid ? (unsigned long long)consumed : 0ull;
+        acc_hits += valid && hit ? 1u : 0u;
+        qn = 0;
+    };
+
+    // ---- the walk: groups of SWEEP_ROWS rows (local row 0 is the top one), bottom group first, rows bottom-up ----
+    bool finished = false;
+    for (int g = y_hi / SWEEP_ROWS;; --g) {
+        // (one more turn after the last group, to shade what is still queued: `flush` is expanded in ONE place)
+        const bool walking = g * SWEEP_ROWS >= y_lo && !flagged && !finished;
+        const int ybase = max(g, 0) * SWEEP_ROWS;
+        int r = walking ? min(SWEEP_ROWS - 1, y_hi - ybase) : -1;
+        const int4 len = *reinterpret_cast<const int4*>(B.p_n + ybase);  // p_n is padded to h_pad entries
+        const int n0 = min(n_t, len.x), n1 = min(n_t, len.y), n2 = min(n_t, len.z), n3 = min(n_t, len.w);
+        while (r >= 0 && !flagged) {
+            if (k >= n_t) {
+                // The walk has reached the end of the caches: the first row that sees only sky scanned to the end,
+                // and no row above it can cross any more (no path is longer than n_t). All of them at once.
+                for (int yy = ybase + r - lane; yy >= y_lo; yy -= 32) {
+                    const int nl = min(n_t, B.p_n[yy]);
+                    const int consumed = nl > 0 ? nl - 1 : 0;
+                    store_pixel(yy, sky, qnan, qnan, qnan, qnan, consumed);
+                    acc_steps += (unsigned long long)consumed;
+                }
+                finished = true;
+                break;
+            }
+            int nlim = r == 3 ? n3 : (r == 2 ? n2 : (r == 1 ? n1 : n0));
+            if (k >= nlim) {  // this row's path ends without a sign change
+                push(ybase + r, 0);
+                --r;
+                continue;
+            }
+            // the window: steps k + lane for all rows of the group; the "before" side comes from the lane below
+            const int kk = min(k + lane, k_last);
+            const double4 cur = *reinterpret_cast<const double4*>(pe + path_index(n_t, kk, ybase));
+            const double t_cur = te[kk];
+            double4 prv;
+            prv.x = __shfl_up_sync(FULL, cur.x, 1), prv.y = __shfl_up_sync(FULL, cur.y, 1);
+            prv.z = __shfl_up_sync(FULL, cur.z, 1), prv.w = __shfl_up_sync(FULL, cur.w, 1);
+            double t_prv = __shfl_up_sync(FULL, t_cur, 1);
+            if (lane == 0) {
+                prv = *reinterpret_cast<const double4*>(pe + path_index(n_t, k - 1, ybase));
+                t_prv = te[k - 1];
+            }
+            int lo = 0;        // lanes below `lo` are steps the current row cannot cross at any more
+            bool odd = false;  // an exact zero or an exit from below among the cells of this window
+            // Resolve rows from the registers while the window serves them. A crossing from above
+            // (d1 > 0 > d2, utils.rs:220-222) at the first such lane >= lo is the row's hit; the row above
+            // continues from that lane.
+#define ATMRT_FUSED_ROW(C, R, NABOVE)                                                                        \
+    {                                                                                                        \
+        const double d1 = prv.C - t_prv, d2 = cur.C - t_cur;                                                 \
+        const bool in = k + lane < nlim, cross = d1 * d2 < 0.0; /* utils.rs:222 */                           \
+        const bool oddcell = in && lane >= lo && (d2 == 0.0 || (cross && !(d1 > 0.0)));                      \
+        const unsigned hits = __ballot_sync(FULL, in && lane >= lo && d1 > 0.0 && cross);                    \
+        odd = odd || (oddcell && (hits == 0 || lane < __ffs(hits) - 1)); /* only cells the row visits */     \
+        if (hits == 0) {                                                                                     \
+            if (k + 32 >= nlim) { /* the row ends inside the window: no hit; the row above goes on from there */ \
+                push(ybase + R, 0);                                                                          \
+                r = R - 1;                                                                                   \
+                k = nlim;                                                                                    \
+            } else {                                                                                         \
+                r = R;                                                                                       \
+                k += 32;                                                                                     \
+            }                                                                                                \
+            lo = 0;                                                                                          \
+            goto fused_window_done;                                                                          \
+        }                                                                                                    \
+        lo = __ffs(hits) - 1;                                                                                \
+        push(ybase + R, k + lo);                                                                             \
+        r = R - 1;                                                                                           \
+        nlim = NABOVE;                                                                                       \
+    }
+            switch (r) {
+                case 3: ATMRT_FUSED_ROW(w, 3, n2)
+                case 2: ATMRT_FUSED_ROW(z, 2, n1)
+                case 1: ATMRT_FUSED_ROW(y, 1, n0)
+                default: ATMRT_FUSED_ROW(x, 0, n0)
+            }
+#undef ATMRT_FUSED_ROW
+        fused_window_done:
+            // An odd cell among those a row visits before its hit (an exact zero of ray - terrain, or an exit
+            // from below: a ray that started under the surface) sends the column to the general march.
+            if (__any_sync(FULL, odd)) flagged = true;
+            k += lo;  // the next window starts at the last hit
+        }
+        // between two row groups: the next group's (up to four) entries always fit
+        if (qn > 32 - SWEEP_ROWS || (!walking && qn > 0)) flush();
+        if (!walking) break;
+    }
+    if (flagged && lane == 0) {
+        B.sweep_col[xl] = 1;                 // (zeroed before the launch; every band that flags writes the same 1)
+        atomicOr(B.sweep_flags + 1, 1u);     // some column needs the brute-force march
+    }
+    for (int o = 16; o > 0; o >>= 1) acc_steps += __shfl_xor_sync(FULL, acc_steps, o);
+    acc_hits = __reduce_add_sync(FULL, acc_hits);
+    if (lane == 0) {
+        unsigned long long* out = F.partial + ((size_t)xl * F.bands + band) * 2;
+        out[0] = acc_steps, out[1] = (unsigned long long)acc_hits;
+    }
+}
+
+// The render counters of the swept columns: the partial sums of the bands of every column the sweep did NOT hand
+// to the brute-force march (that march counts its own pixels). One thread per column.
+__global__ void __launch_bounds__(128) k_sweep_counters(DevBuffers B, const unsigned long long* __restrict__ partial, int wl, int bands) {
+    if (B.sweep_flags[0] != 0) return;
+    const int xl = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long steps = 0ull, hits = 0ull;
+    if (xl < wl && B.sweep_col[xl] == 0) {
+        for (int b = 0; b < bands; ++b) steps += partial[((size_t)xl * bands + b) * 2], hits += partial[((size_t)xl * bands + b) * 2 + 1];
+    }
+    for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(FULL, steps, o), hits += __shfl_xor_sync(FULL, hits, o);
+    if ((threadIdx.x & 31) == 0) {
+        if (steps) atomicAdd(B.counters + CNT_RAY_STEPS, steps);
+        if (hits) atomicAdd(B.counters + CNT_TRACE_POINTS, hits), atomicAdd(B.counters + CNT_PIXELS_HIT, hits);
+    }
+}
+
+// Column-major colour scratch [wl][h_pad][3] -> the row-major image [h][wl][3]. A block moves a tile of 32 columns x
+// 32 rows through shared memory: 96 contiguous bytes per column in, 96 contiguous bytes per row out.
+__global__ void __launch_bounds__(256) k_rgb_rows(const unsigned char* __restrict__ rgb_t, unsigned char* __restrict__ rgb, int wl, int h, int h_pad,
+                                                 const unsigned* __restrict__ sweep_flags) {
+    if (sweep_flags[0] != 0) return;
+    __shared__ unsigned tile[32][25];  // [column][24 words = 32 rows x 3 bytes] (+1: bank spread)
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    for (int c = ty; c < 32; c += 8) {
+        if (tx < 24 && c0 + c < wl) tile[c][tx] = *reinterpret_cast<const unsigned*>(rgb_t + ((size_t)(c0 + c) * h_pad + y0) * 3 + 4 * tx);
+    }
+    __syncthreads();
+    const unsigned char* tb = reinterpret_cast<const unsigned char*>(&tile[0][0]);
+    const bool words = (wl & 3) == 0 && c0 + 32 <= wl;  // every row segment of the tile is 96 aligned bytes
+    for (int r = ty; r < 32; r += 8) {
+        if (y0 + r >= h) continue;
+        unsigned char* out = rgb + ((size_t)(y0 + r) * wl + c0) * 3;
+        if (words) {
+            if (tx < 24) {
+                unsigned v = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int b = 4 * tx + q, c = b / 3, ch = b - 3 * c;
+                    v |= (unsigned)tb[c * 100 + r * 3 + ch] << (8 * q);
+                }
+                reinterpret_cast<unsigned*>(out)[tx] = v;
+            }
+        } else {
+            for (int b = tx; b < 96; b += 32) {
+                const int c = b / 3, ch = b - 3 * c;
+                if (c0 + c < wl) out[b] = tb[c * 100 + r * 3 + ch];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // FP64 pipe micro-benchmark (the roofline denominator for this path: MEASURED_PEAKS.json has no
 // FP64 figure). 8 independent DFMA (or DADD) chains per thread.
 // ---------------------------------------------------------------------------------------------
