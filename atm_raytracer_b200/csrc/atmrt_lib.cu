@@ -83,9 +83,11 @@ struct atmrt_ctx {
     int path_mode = 0;  // 0: g(h) from the table, 1: every evaluation through libm (validation)
     DevBuf d_atm_cells;
     DevBuf d_sweep_flags, d_sweep_col, d_sweep_hit;
-    DevBuf d_rgb_t, d_partial;  // fused stage C: column-major colour scratch, per-(column, band) counters
-    int sweep_bands = 0;        // 0: chosen per render (launch_render)
+    DevBuf d_anchor;  // walk anchors of stage A, [wl][n_anchor]
+    bool walk_anchors = true;
+    DevBuf d_list, d_count, d_normals;  // stage C: the distinct hit samples of every column and their normals
     bool stage_c_legacy = false;
+    int sweep_min_blocks = 10;
     DevBuf d_stage;  // raw posts of pack_terrain on their way to the tiled layout
     bool sweep_enabled = true;
     DevBuf d_dist, d_colcalc, d_tlat, d_tlon, d_telev, d_tclose;
@@ -564,6 +566,15 @@ int prepare_render(atmrt_ctx* ctx) {
     S.n2 = (S.n1 + 31) / 32;
     S.h_pad = (p.height + 31) / 32 * 32;
     S.nobjects = (int)ctx->objects.size();
+    // Walk anchors of stage A (kernels.cuh: anchored_lat_lon): a power of two of samples per anchor whose half span
+    // stays below 2.5e-3 rad of arc (1024 samples at 25 m, 512 at 50 m); none for coarse steps or other walkers.
+    S.anchor_shift = 0, S.n_anchor = 0;
+    if (S.earth.walker == WALK_SPHERICAL && ctx->walk_anchors && p.generator == ATMRT_GENERATOR_FAST) {
+        const double max_samples = 5.0e-3 * p.radius / p.simulation_step;
+        int shift = 0;
+        while (shift < 10 && (double)(2 << shift) <= max_samples) ++shift;
+        if (shift >= 6) S.anchor_shift = shift, S.n_anchor = (n_t + (1 << shift) - 1) >> shift;
+    }
 
     const size_t wl = (size_t)(p.x1 - p.x0), h = (size_t)p.height, np = (size_t)S.n_pad;
     const size_t f8 = sizeof(double);
@@ -574,6 +585,7 @@ int prepare_render(atmrt_ctx* ctx) {
     e |= ensure(ctx, ctx->d_pdist, f8 * 2 * S.n_x);
     if (!rect) {
     e |= ensure(ctx, ctx->d_colcalc, f8 * 8 * wl);
+    if (S.n_anchor > 0) e |= ensure(ctx, ctx->d_anchor, sizeof(WalkAnchor) * wl * (size_t)S.n_anchor);
     e |= ensure(ctx, ctx->d_tlat, f8 * wl * np);
     e |= ensure(ctx, ctx->d_tlon, f8 * wl * np);
     e |= ensure(ctx, ctx->d_telev, f8 * wl * np);
@@ -643,6 +655,7 @@ int prepare_render(atmrt_ctx* ctx) {
     B.dist_k = (const double*)ctx->d_dist.p;
     B.walk_sc = S.earth.walker == WALK_SPHERICAL ? (const double2*)((const double*)ctx->d_dist.p + S.n_sc_off) : nullptr;
     B.colcalc = (double*)ctx->d_colcalc.p;
+    B.walk_anchor = S.n_anchor > 0 ? (WalkAnchor*)ctx->d_anchor.p : nullptr;
     B.t_lat = (double*)ctx->d_tlat.p, B.t_lon = (double*)ctx->d_tlon.p, B.t_elev = (double*)ctx->d_telev.p;
     B.terrain = ctx->terrain;
     B.t_close = S.nobjects > 0 ? (unsigned long long*)ctx->d_tclose.p : nullptr;
@@ -834,6 +847,10 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
     // Stage A on s_a
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->a0, ctx->s_a));
     k_column_setup<<<(wl + 127) / 128, 128, 0, ctx->s_a>>>(S, B);
+    if (S.n_anchor > 0) {
+        k_walk_anchors<<<dim3((S.n_anchor + 127) / 128, wl), 128, 0, ctx->s_a>>>(S, B);
+        ctx->launches++;
+    }
     if (S.earth.walker == WALK_SPHERICAL) k_terrain_profile<WALK_SPHERICAL><<<dim3((S.n_t + 127) / 128, wl), 128, 0, ctx->s_a>>>(S, ctx->terrain, B, 0);
     else k_terrain_profile<-1><<<dim3((S.n_t + 127) / 128, wl), 128, 0, ctx->s_a>>>(S, ctx->terrain, B, 0);
     ctx->launches += 2;
@@ -857,22 +874,44 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
     MarchOut O{rt.rgb, rt.meta, rt.steps, rt.points, rt.counts, rt.max_points};
     const dim3 grid((h + MARCH_THREADS - 1) / MARCH_THREADS, wl);
     if (sweep && !ctx->stage_c_legacy) {
-        // Fused sweep + shading, one warp per (column, row band). Enough bands that the grid holds about three times
-        // the warps the GPU keeps resident (a column block of an 8-GPU frame is 2048 columns wide), none below 128 rows.
-        int bands = ctx->sweep_bands;
-        if (bands <= 0) bands = (int)std::min<long long>(std::max<long long>(1, ((long long)ctx->num_sms * 96 + wl - 1) / wl), std::max(1, h / 128));
-        const int band_rows = ((h + bands - 1) / bands + 31) / 32 * 32;
-        bands = (h + band_rows - 1) / band_rows;
-        if (rt.rgb && (rc = ensure(ctx, ctx->d_rgb_t, (size_t)wl * S.h_pad * 3))) return rc;
-        if ((rc = ensure(ctx, ctx->d_partial, sizeof(unsigned long long) * 2 * (size_t)wl * bands))) return rc;
-        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_sweep_col.p, 0, (size_t)wl, main));
-        FusedOut F{rt.rgb ? (unsigned char*)ctx->d_rgb_t.p : nullptr, (unsigned long long*)ctx->d_partial.p, band_rows, bands};
-        const dim3 fgrid((wl + FUSED_WARPS - 1) / FUSED_WARPS, bands);
-        if (S.earth.walker == WALK_SPHERICAL) k_sweep_fused<WALK_SPHERICAL><<<fgrid, 32 * FUSED_WARPS, 0, main>>>(S, B, O, F, 0, wl);
-        else k_sweep_fused<-1><<<fgrid, 32 * FUSED_WARPS, 0, main>>>(S, B, O, F, 0, wl);
-        if (rt.rgb) k_rgb_rows<<<dim3((wl + 31) / 32, (h + 31) / 32), 256, 0, main>>>(F.rgb_t, rt.rgb, wl, h, S.h_pad, B.sweep_flags);
-        k_sweep_counters<<<(wl + 127) / 128, 128, 0, main>>>(B, F.partial, wl, bands);
-        ctx->launches += rt.rgb ? 3 : 2;
+        // Bit-mask sweep -> normals of the distinct hit samples -> row-major shading (kernels.cuh).
+        SweepLists L{};
+        L.cap = std::min(2 * S.h_pad, S.n_pad);
+        if ((rc = ensure(ctx, ctx->d_list, sizeof(int) * (size_t)wl * L.cap))) return rc;
+        if ((rc = ensure(ctx, ctx->d_count, sizeof(int) * (size_t)wl))) return rc;
+        if ((rc = ensure(ctx, ctx->d_normals, sizeof(double) * 3 * (size_t)wl * L.cap))) return rc;
+        L.list = (int*)ctx->d_list.p, L.count = (int*)ctx->d_count.p, L.normals = (double*)ctx->d_normals.p;
+        const int sgrid = (wl + BITS_WARPS - 1) / BITS_WARPS;
+        if (ctx->sweep_min_blocks == 16) k_sweep_bits<16><<<sgrid, 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl);
+        else if (ctx->sweep_min_blocks == 12) k_sweep_bits<12><<<sgrid, 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl);
+        else k_sweep_bits<10><<<sgrid, 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl);
+        // enough blocks per column that a narrow column block (one of eight GPUs) still fills the machine
+        const int parts = std::max(1, std::min(8, (ctx->num_sms * 16 + wl - 1) / wl));
+        if (S.earth.walker == WALK_SPHERICAL) k_hit_normals<WALK_SPHERICAL><<<wl * parts, 128, 0, main>>>(S, B, L, parts);
+        else k_hit_normals<-1><<<wl * parts, 128, 0, main>>>(S, B, L, parts);
+        ctx->launches += 2;
+        const bool to_host = rt.host_rgb || rt.host_meta || rt.host_steps;
+        const int nbands = to_host && h >= 256 ? SHADE_BANDS : 1;
+        const int band_rows = ((h + nbands - 1) / nbands + 31) / 32 * 32;
+        int bi = 0;
+        for (int r0 = 0; r0 < h; r0 += band_rows, ++bi) {
+            const int r1 = std::min(h, r0 + band_rows);
+            k_shade_tiles<<<dim3((r1 - r0 + 31) / 32, (wl + TILE_COLS - 1) / TILE_COLS), 32 * TILE_COLS, 0, main>>>(S, B, O, L, r0);
+            ctx->launches++;
+            if (to_host) {  // the finished band goes to the host on the (idle) stage-A stream while the next band is shaded
+                const size_t p0 = (size_t)r0 * wl, np = (size_t)(r1 - r0) * wl;
+                CUDA_TRY(ctx, cudaEventRecord(ctx->ev_band[bi], main));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_a, ctx->ev_band[bi], 0));
+                if (rt.host_rgb) CUDA_TRY(ctx, cudaMemcpyAsync(rt.host_rgb + p0 * 3, rt.rgb + p0 * 3, np * 3, cudaMemcpyDeviceToHost, ctx->s_a));
+                if (rt.host_meta) CUDA_TRY(ctx, cudaMemcpyAsync(rt.host_meta + p0, rt.meta + p0, np * sizeof(atmrt_meta), cudaMemcpyDeviceToHost, ctx->s_a));
+                if (rt.host_steps) CUDA_TRY(ctx, cudaMemcpyAsync(rt.host_steps + p0, rt.steps + p0, np * sizeof(int), cudaMemcpyDeviceToHost, ctx->s_a));
+            }
+        }
+        if (to_host) {
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->s_a));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_a, 0));
+            rt.host_copied = true;
+        }
     } else if (sweep) {
         // (Splitting the image into column chunks so that the shading of one chunk overlaps the sweep of the
         // next was measured and is slower: 8.9 ms -> 9.8 / 10.5 ms with 2 / 4 chunks at c5 -- the sweep's long
@@ -1020,7 +1059,8 @@ int atmrt_create(int device, atmrt_ctx** out) {
         delete ctx;
         return fail(nullptr, ATMRT_ERR_CUDA, "stream/event creation failed");
     }
-    if (const char* e = getenv("ATMRT_SWEEP_BANDS")) ctx->sweep_bands = atoi(e);  // tuning (scratch/): row bands per column of the fused stage C
+    if (const char* e = getenv("ATMRT_WALK_ANCHORS")) ctx->walk_anchors = atoi(e) != 0;
+    if (const char* e = getenv("ATMRT_SWEEP_MB")) ctx->sweep_min_blocks = atoi(e);
     if (const char* e = getenv("ATMRT_STAGE_C")) ctx->stage_c_legacy = std::string(e) == "legacy";
     *out = ctx;
     return 0;
@@ -1033,7 +1073,7 @@ void atmrt_destroy(atmrt_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_objects_in, &ctx->d_objects, &ctx->d_dist, &ctx->d_colcalc, &ctx->d_tlat, &ctx->d_tlon, &ctx->d_telev,
                       &ctx->d_tclose, &ctx->d_pdist, &ctx->d_pelev, &ctx->d_plen, &ctx->d_pn,
                       &ctx->d_tmin1, &ctx->d_tmax1, &ctx->d_tmin2, &ctx->d_tmax2, &ctx->d_tmin3, &ctx->d_tmax3, &ctx->d_close1, &ctx->d_close2, &ctx->d_close3, &ctx->d_rmin1, &ctx->d_rmin3, &ctx->d_rmax3,
-                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_sweep_flags, &ctx->d_sweep_col, &ctx->d_sweep_hit, &ctx->d_rgb_t, &ctx->d_partial, &ctx->d_stage, &ctx->d_atm_aux, &ctx->d_rgb, &ctx->d_meta,
+                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_sweep_flags, &ctx->d_sweep_col, &ctx->d_sweep_hit, &ctx->d_list, &ctx->d_count, &ctx->d_normals, &ctx->d_anchor, &ctx->d_stage, &ctx->d_atm_aux, &ctx->d_rgb, &ctx->d_meta,
                       &ctx->d_steps, &ctx->d_points, &ctx->d_counts, &ctx->d_probe_a, &ctx->d_probe_b, &ctx->d_probe_c, &ctx->d_probe_d};
     for (DevBuf* b : bufs) release(*b);
     for (DevBuf& b : ctx->textures) release(b);
@@ -1475,6 +1515,77 @@ int atmrt_pixel_angles(atmrt_ctx* ctx, double* elevation_angle, double* azimuth)
     CUDA_TRY(ctx, cudaGetLastError());
     if (elevation_angle) CUDA_TRY(ctx, cudaMemcpyAsync(elevation_angle, ctx->d_probe_a.p, bytes, cudaMemcpyDeviceToHost, s));
     if (azimuth) CUDA_TRY(ctx, cudaMemcpyAsync(azimuth, ctx->d_probe_b.p, bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int atmrt_ray_paths(atmrt_ctx* ctx, double start_h, const double* angles_deg, int n, double ray_step, int nsteps, double* x, double* h) {
+    if (!ctx || !angles_deg || n < 0 || nsteps < 0 || !(ray_step > 0.0)) return fail(ctx, ATMRT_ERR_INVALID, "ray_paths: bad argument");
+    if (!ctx->has_params) return fail(ctx, ATMRT_ERR_STATE, "ray_paths before set_params");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const atmrt_params& p = ctx->params;
+    DevScene S{};
+    int rc = lower_atmosphere(ctx, p.atmosphere, p.wavelength, &S.atm);
+    if (rc) return rc;
+    // EarthModel::to_shape (earth_model/mod.rs:95-112), as prepare_render lowers it
+    S.flat = p.earth_model == ATMRT_EARTH_FLAT_DISTORTED || p.earth_model == ATMRT_EARTH_AZIMUTHAL_EQUIDISTANT || p.earth_model == ATMRT_EARTH_OBSERVER_AE;
+    S.radius = p.earth_model == ATMRT_EARTH_ELLIPSOID ? (2.0 * p.radius + p.ellipsoid_b) / 3.0 : p.radius;
+    // RayState::x: the stepper's own running sum (phi += step / R, x = phi * R; flat: x += step), the same for every ray
+    if (x) {
+        const double d = S.flat ? ray_step : ray_step / S.radius;
+        double t = 0.0;
+        for (int k = 0; k < nsteps; ++k) {
+            t += d;
+            x[k] = S.flat ? t : t * S.radius;
+        }
+    }
+    if (n == 0 || nsteps == 0 || !h) return 0;
+    std::vector<double> cells;
+    std::vector<DevGPiece> pieces;
+    build_g_table(S.atm, p.wavelength, cells, pieces, nullptr);
+    const size_t cell_bytes = sizeof(double) * cells.size(), out_bytes = sizeof(double) * (size_t)n * nsteps;
+    if (ensure(ctx, ctx->d_probe_a, sizeof(double) * (size_t)n) || ensure(ctx, ctx->d_probe_b, out_bytes) ||
+        ensure(ctx, ctx->d_probe_d, cell_bytes + sizeof(DevGPiece) * ATM_MAX_PIECES))
+        return ATMRT_ERR_CUDA;
+    cudaStream_t s = ctx->s_main;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_probe_a.p, angles_deg, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_probe_d.p, cells.data(), cell_bytes, cudaMemcpyHostToDevice, s));
+    if (!pieces.empty())
+        CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->d_probe_d.p + cell_bytes, pieces.data(), sizeof(DevGPiece) * pieces.size(), cudaMemcpyHostToDevice, s));
+    DevBuffers B{};
+    B.atm_cells = (const double*)ctx->d_probe_d.p;
+    B.atm_pieces = (const DevGPiece*)((const char*)ctx->d_probe_d.p + cell_bytes);
+    B.n_atm_pieces = (int)pieces.size();
+    const int libm = ctx->path_mode == 1 ? 1 : 0;
+    if (S.flat)
+        k_ray_path_probe<true><<<(n + 127) / 128, 128, 0, s>>>(S, B, start_h, (const double*)ctx->d_probe_a.p, n, ray_step, nsteps, libm, (double*)ctx->d_probe_b.p);
+    else
+        k_ray_path_probe<false><<<(n + 127) / 128, 128, 0, s>>>(S, B, start_h, (const double*)ctx->d_probe_a.p, n, ray_step, nsteps, libm, (double*)ctx->d_probe_b.p);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->d_probe_b.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int atmrt_elev_profile(atmrt_ctx* ctx, double azimuth, const double* dist, int n, double* lat, double* lon, double* elev) {
+    if (!ctx || !dist || !elev || n < 0) return fail(ctx, ATMRT_ERR_INVALID, "elev_profile: bad argument");
+    if (!ctx->has_terrain) return fail(ctx, ATMRT_ERR_STATE, "elev_profile before set_terrain");
+    if (!ctx->has_params) return fail(ctx, ATMRT_ERR_STATE, "elev_profile before set_params");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return 0;
+    int rc = prepare_render(ctx);  // lowers the earth model into ctx->scene (and sizes the render buffers)
+    if (rc) return rc;
+    const size_t bytes = sizeof(double) * (size_t)n;
+    if (ensure(ctx, ctx->d_probe_a, bytes) || ensure(ctx, ctx->d_probe_b, bytes) || ensure(ctx, ctx->d_probe_c, bytes) || ensure(ctx, ctx->d_probe_d, bytes))
+        return ATMRT_ERR_CUDA;
+    cudaStream_t s = ctx->s_main;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_probe_a.p, dist, bytes, cudaMemcpyHostToDevice, s));
+    k_elev_profile<<<(n + 127) / 128, 128, 0, s>>>(ctx->scene, ctx->terrain, azimuth, (const double*)ctx->d_probe_a.p, n, (double*)ctx->d_probe_b.p,
+                                                   (double*)ctx->d_probe_c.p, (double*)ctx->d_probe_d.p);
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (lat) CUDA_TRY(ctx, cudaMemcpyAsync(lat, ctx->d_probe_b.p, bytes, cudaMemcpyDeviceToHost, s));
+    if (lon) CUDA_TRY(ctx, cudaMemcpyAsync(lon, ctx->d_probe_c.p, bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(elev, ctx->d_probe_d.p, bytes, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     return 0;
 }

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "atmrt_host.h"
+#include "../../../include/atmrt_fmt.h"
 
 namespace atmrt_host {
 extern std::string g_error;
@@ -639,6 +640,41 @@ static bool write_metadata(const std::string& path, const atmrt_params& p, const
     return gzclose(f) == Z_OK && ok;
 }
 
+// Terrain::from_folder (terrain/mod.rs:66-83): every entry of the folder must be a terrain file; decoded on the host.
+struct HostTerrain {
+    std::vector<atmrt_tile_desc> descs;
+    std::vector<std::vector<int16_t>> posts;
+    std::vector<const int16_t*> ptrs() const {
+        std::vector<const int16_t*> p;
+        for (const auto& v : posts) p.push_back(v.data());
+        return p;
+    }
+};
+
+static HostTerrain load_terrain_folder(const std::string& folder) {
+    HostTerrain t;
+    DIR* dir = opendir(folder.c_str());
+    if (!dir) throw std::runtime_error("Error opening the terrain data directory " + folder);
+    std::vector<std::string> names;
+    while (dirent* e = readdir(dir)) {
+        std::string n = e->d_name;
+        if (n != "." && n != "..") names.push_back(n);
+    }
+    closedir(dir);
+    std::sort(names.begin(), names.end());
+    for (const std::string& n : names) {
+        std::string path = folder + "/" + n;
+        atmrt_tile_desc d{};
+        if (atmrt_host_read_dted(path.c_str(), &d, nullptr, 0) != 0) throw std::runtime_error("Could not buffer terrain file " + path);
+        std::vector<int16_t> buf((size_t)d.nlon * d.nlat);
+        if (atmrt_host_read_dted(path.c_str(), &d, buf.data(), buf.size()) != 0) throw std::runtime_error(g_error);
+        t.descs.push_back(d);
+        t.posts.push_back(std::move(buf));
+    }
+    printf("Detected %zu terrain files\n", names.size());
+    return t;
+}
+
 }  // namespace atmrt_host
 
 using namespace atmrt_host;
@@ -650,28 +686,7 @@ extern "C" int atmrt_host_gen(int argc, const char* const* argv) {
     try {
         Config c = read_config(argc, argv);
         printf("%.3f: Using terrain data directory: \"%s\"\n", t(), c.terrain_folder.c_str());
-        // Terrain::from_folder (terrain/mod.rs:66-83): every entry must be a terrain file
-        std::vector<atmrt_tile_desc> descs;
-        std::vector<std::vector<int16_t>> posts;
-        DIR* dir = opendir(c.terrain_folder.c_str());
-        if (!dir) throw std::runtime_error("Error opening the terrain data directory " + c.terrain_folder);
-        std::vector<std::string> names;
-        while (dirent* e = readdir(dir)) {
-            std::string n = e->d_name;
-            if (n != "." && n != "..") names.push_back(n);
-        }
-        closedir(dir);
-        std::sort(names.begin(), names.end());
-        for (const std::string& n : names) {
-            std::string path = c.terrain_folder + "/" + n;
-            atmrt_tile_desc d{};
-            if (atmrt_host_read_dted(path.c_str(), &d, nullptr, 0) != 0) throw std::runtime_error("Could not buffer terrain file " + path);
-            std::vector<int16_t> buf((size_t)d.nlon * d.nlat);
-            if (atmrt_host_read_dted(path.c_str(), &d, buf.data(), buf.size()) != 0) throw std::runtime_error(g_error);
-            descs.push_back(d);
-            posts.push_back(std::move(buf));
-        }
-        printf("Detected %zu terrain files\n", names.size());
+        HostTerrain terrain = load_terrain_folder(c.terrain_folder);
 
         atmrt_params p = into_params(c);
         std::vector<atmrt_object> objects;
@@ -695,9 +710,7 @@ extern "C" int atmrt_host_gen(int argc, const char* const* argv) {
             if (rc != 0) throw std::runtime_error(std::string(what) + ": " + atmrt_last_error(ctx));
         };
         check(atmrt_create(0, &ctx), "atmrt_create");
-        std::vector<const int16_t*> post_ptrs;
-        for (auto& v : posts) post_ptrs.push_back(v.data());
-        check(atmrt_set_terrain(ctx, descs.data(), (int)descs.size(), post_ptrs.data()), "atmrt_set_terrain");
+        check(atmrt_set_terrain(ctx, terrain.descs.data(), (int)terrain.descs.size(), terrain.ptrs().data()), "atmrt_set_terrain");
         check(atmrt_set_params(ctx, &p), "atmrt_set_params");
         check(atmrt_set_objects(ctx, objects.data(), (int)objects.size(), tex_ptrs.data()), "atmrt_set_objects");
         printf("%.3f: Generating terrain cache...\n%.3f: Generating path cache...\n%.3f: Calculating pixels...\n", t(), t(), t());
@@ -743,5 +756,199 @@ extern "C" int atmrt_host_parse_config(int argc, const char* const* argv, atmrt_
         return 0;
     } catch (const std::exception& e) {
         return fail(ATMRT_ERR_INVALID, e.what());
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The reference's three text dumpers: the same flags, the same text layout (`{}` of an f64 is
+// atmrt_fmt_f64), the numbers from the device through the C-ABI probes. `parse_config(filename)` (params.rs:678-692)
+// reads the YAML only -- these subcommands take no `gen` flags.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct DumpArgs {
+    std::string input;
+    std::map<std::string, std::string> val;
+    std::map<std::string, bool> flag;
+};
+
+// clap's AllowLeadingHyphen: a value may start with '-' (negative numbers)
+DumpArgs parse_dump_args(int argc, const char* const* argv, const std::map<std::string, std::string>& takes,
+                         const std::map<std::string, std::string>& flags) {
+    DumpArgs a;
+    for (int i = 0; i < argc; ++i) {
+        const std::string s = argv[i];
+        auto t = takes.find(s);
+        if (t != takes.end()) {
+            if (i + 1 >= argc) throw std::runtime_error("missing value for " + s);
+            a.val[t->second] = argv[++i];
+            continue;
+        }
+        auto f = flags.find(s);
+        if (f != flags.end()) {
+            a.flag[f->second] = true;
+            continue;
+        }
+        if (a.input.empty() && (s.empty() || s[0] != '-')) {
+            a.input = s;
+            continue;
+        }
+        throw std::runtime_error("unknown argument " + s);
+    }
+    if (a.input.empty()) throw std::runtime_error("please provide an input file");
+    return a;
+}
+
+double dump_num(const DumpArgs& a, const char* key, double def, const char* what) {
+    auto it = a.val.find(key);
+    if (it == a.val.end()) return def;
+    char* end = nullptr;
+    const double v = strtod(it->second.c_str(), &end);
+    if (end == it->second.c_str() || *end != '\0') throw std::runtime_error(std::string("please provide a valid ") + what);
+    return v;
+}
+
+Config parse_config_file(const std::string& filename) {  // params.rs:678-692
+    Config c;
+    c.atmosphere = us_76();
+    apply_yaml(parse_yaml(read_file(filename)), &c);
+    return c;
+}
+
+struct Ctx {  // a context that is destroyed on every exit path
+    atmrt_ctx* h = nullptr;
+    ~Ctx() {
+        if (h) atmrt_destroy(h);
+    }
+    void check(int rc, const char* what) const {
+        if (rc != 0) throw std::runtime_error(std::string(what) + ": " + atmrt_last_error(h));
+    }
+};
+
+int dump_fail(const std::exception& e) {
+    fail(ATMRT_ERR_INVALID, e.what());
+    fprintf(stderr, "ERROR: %s\n", e.what());  // main.rs:36-38
+    return 1;
+}
+
+}  // namespace
+
+// output-ray-paths (ray_path.rs:6-106): h(x) of refracted rays cast at a range of elevation angles.
+extern "C" int atmrt_host_output_ray_paths(int argc, const char* const* argv) {
+    try {
+        const DumpArgs a = parse_dump_args(argc, argv,
+                                           {{"-h", "height"}, {"--height", "height"}, {"-a", "min_angle"}, {"--min-ang", "min_angle"},
+                                            {"-b", "max_angle"}, {"--max-ang", "max_angle"}, {"-s", "angle_step"}, {"--angle-step", "angle_step"},
+                                            {"-r", "ray_step"}, {"--ray-step", "ray_step"}, {"-c", "cutoff_dist"}, {"--cutoff-dist", "cutoff_dist"},
+                                            {"-o", "output_step"}, {"--output-step", "output_step"}},
+                                           {});
+        const double height = dump_num(a, "height", 2.0, "observer height");
+        const double min_ang = dump_num(a, "min_angle", -1.0, "minimum altitude"), max_ang = dump_num(a, "max_angle", 1.0, "maximum altitude");
+        const double step = dump_num(a, "angle_step", 0.1, "step size"), ray_step = dump_num(a, "ray_step", 50.0, "ray step size");
+        const double cutoff = dump_num(a, "cutoff_dist", 10000.0, "cutoff distance"), output_step = dump_num(a, "output_step", 50.0, "output step");
+        if (!(step > 0.0)) throw std::runtime_error("step must be positive");
+        if (!(ray_step > 0.0)) throw std::runtime_error("ray step must be positive");
+        const Config c = parse_config_file(a.input);
+        const atmrt_params p = into_params(c);
+        // the angles: `ang += step` from min_ang while ang <= max_ang (ray_path.rs:65-94)
+        std::vector<double> angles;
+        for (double ang = min_ang; ang <= max_ang; ang += step) {
+            fprintf(stderr, "Elevation angle %s (min=%s, max=%s)\n", atmrt_fmt_f64(ang).c_str(), atmrt_fmt_f64(min_ang).c_str(), atmrt_fmt_f64(max_ang).c_str());
+            angles.push_back(ang);
+        }
+        Ctx ctx;
+        ctx.check(atmrt_create(0, &ctx.h), "atmrt_create");
+        ctx.check(atmrt_set_params(ctx.h, &p), "atmrt_set_params");
+        // every ray is stepped until x >= cutoff (ray_path.rs:88-90); x is the same running sum for every ray
+        int nsteps = 0;
+        std::vector<double> x;
+        for (int cap = 1024;; cap *= 2) {
+            x.assign((size_t)cap, 0.0);
+            const double none = 0.0;  // (no rays in this call: only RayState::x is wanted)
+            ctx.check(atmrt_ray_paths(ctx.h, height, &none, 0, ray_step, cap, x.data(), nullptr), "atmrt_ray_paths");
+            int k = 0;
+            while (k < cap && !(x[(size_t)k] >= cutoff)) ++k;
+            if (k < cap) {
+                nsteps = k + 1;
+                break;
+            }
+            if (cap > (1 << 26)) throw std::runtime_error("cutoff distance / ray step too large");
+        }
+        x.resize((size_t)nsteps);
+        std::vector<double> h((size_t)angles.size() * nsteps);
+        if (!angles.empty())
+            ctx.check(atmrt_ray_paths(ctx.h, height, angles.data(), (int)angles.size(), ray_step, nsteps, x.data(), h.data()), "atmrt_ray_paths");
+        // a state is output when an output_step boundary falls within ray_step / 2 of it (ray_path.rs:80-87)
+        std::vector<int> keep;
+        for (int k = 0; k < nsteps; ++k)
+            if (std::floor((x[(size_t)k] - ray_step / 2.0) / output_step) != std::floor((x[(size_t)k] + ray_step / 2.0) / output_step)) keep.push_back(k);
+        std::string out;
+        for (size_t i = 0; i <= keep.size(); ++i) {
+            out += atmrt_fmt_f64(i == 0 ? 0.0 : x[(size_t)keep[i - 1]]) + "\t";
+            for (size_t r = 0; r < angles.size(); ++r) out += atmrt_fmt_f64(i == 0 ? height : h[r * nsteps + (size_t)keep[i - 1]]) + "\t";
+            out += "\n";
+        }
+        fwrite(out.data(), 1, out.size(), stdout);
+        return 0;
+    } catch (const std::exception& e) {
+        return dump_fail(e);
+    }
+}
+
+// output-elev-profile (elev_profile.rs:9-67): terrain elevation against distance along one azimuth from the observer.
+extern "C" int atmrt_host_output_elev_profile(int argc, const char* const* argv) {
+    try {
+        const DumpArgs a = parse_dump_args(argc, argv,
+                                           {{"-a", "azim"}, {"--azim", "azim"}, {"-s", "step"}, {"--step", "step"}, {"-c", "cutoff_dist"}, {"--cutoff-dist", "cutoff_dist"}}, {});
+        const double azim = dump_num(a, "azim", 0.0, "azimuth"), step = dump_num(a, "step", 50.0, "step size");
+        const double cutoff = dump_num(a, "cutoff_dist", 10000.0, "cutoff distance");
+        if (!(step > 0.0)) throw std::runtime_error("step must be positive");
+        const Config c = parse_config_file(a.input);
+        const HostTerrain terrain = load_terrain_folder(c.terrain_folder);
+        const atmrt_params p = into_params(c);
+        std::vector<double> xs;
+        for (double x = 0.0; x <= cutoff; x += step) xs.push_back(x);  // elev_profile.rs:53-60
+        Ctx ctx;
+        ctx.check(atmrt_create(0, &ctx.h), "atmrt_create");
+        ctx.check(atmrt_set_terrain(ctx.h, terrain.descs.data(), (int)terrain.descs.size(), terrain.ptrs().data()), "atmrt_set_terrain");
+        ctx.check(atmrt_set_params(ctx.h, &p), "atmrt_set_params");
+        std::vector<double> elev(xs.size());
+        ctx.check(atmrt_elev_profile(ctx.h, azim, xs.data(), (int)xs.size(), nullptr, nullptr, elev.data()), "atmrt_elev_profile");
+        std::string out;
+        for (size_t i = 0; i < xs.size(); ++i) out += atmrt_fmt_f64(xs[i]) + "\t" + atmrt_fmt_f64(elev[i]) + "\n";
+        fwrite(out.data(), 1, out.size(), stdout);
+        return 0;
+    } catch (const std::exception& e) {
+        return dump_fail(e);
+    }
+}
+
+// output-atm (atm_printer.rs:6-49): temperature, pressure and relative humidity against altitude.
+extern "C" int atmrt_host_output_atm(int argc, const char* const* argv) {
+    try {
+        const DumpArgs a = parse_dump_args(argc, argv,
+                                           {{"-a", "min_altitude"}, {"--min-alt", "min_altitude"}, {"-b", "max_altitude"}, {"--max-alt", "max_altitude"}, {"-s", "step"}, {"--step", "step"}},
+                                           {{"-c", "celsius"}, {"--celsius", "celsius"}});
+        const double min_alt = dump_num(a, "min_altitude", 0.0, "minimum altitude"), max_alt = dump_num(a, "max_altitude", 1000.0, "maximum altitude");
+        const double step = dump_num(a, "step", 0.2, "step size");
+        const bool celsius = a.flag.count("celsius") != 0;
+        if (!(step > 0.0)) throw std::runtime_error("step must be positive");  // (the reference would loop forever)
+        const Config c = parse_config_file(a.input);
+        const atmrt_params p = into_params(c);
+        std::vector<double> alts;
+        for (double alt = min_alt; alt <= max_alt; alt += step) alts.push_back(alt);  // atm_printer.rs:35-46
+        Ctx ctx;
+        ctx.check(atmrt_create(0, &ctx.h), "atmrt_create");
+        ctx.check(atmrt_set_params(ctx.h, &p), "atmrt_set_params");
+        std::vector<double> t(alts.size()), pr(alts.size());
+        ctx.check(atmrt_atmosphere_probe(ctx.h, alts.data(), (int)alts.size(), t.data(), pr.data(), nullptr), "atmrt_atmosphere_probe");
+        std::string out;
+        for (size_t i = 0; i < alts.size(); ++i)
+            out += atmrt_fmt_f64(alts[i]) + " " + atmrt_fmt_f64(t[i] - (celsius ? 273.15 : 0.0)) + " " + atmrt_fmt_f64(pr[i]) + " " +
+                   atmrt_fmt_f64(c.atmosphere.humidity) + "\n";
+        fwrite(out.data(), 1, out.size(), stdout);
+        return 0;
+    } catch (const std::exception& e) {
+        return dump_fail(e);
     }
 }

@@ -48,10 +48,13 @@ struct DevScene {
     int n2;      // level-2 chunks  = ceil(n1 / 32)
     int h_pad;   // row stride of the step-major [k][row] path cache and of the node-major path pyramids
     int nobjects;
-    int _pad;
+    int anchor_shift;  // log2 of the samples per walk anchor (k_terrain_profile), 0: no anchors
+    int n_anchor, _pad;  // anchors per column
     DevAtmosphere atm;
     DevShade shade;
 };
+
+struct WalkAnchor;
 
 struct DevBuffers {
     const double* dist_k;  // [n_t] accumulated `distance += step` (utils.rs:191-196), host-computed
@@ -59,6 +62,7 @@ struct DevBuffers {
     // Stage A cache, [wl][n_pad]
     DevTerrain terrain;  // the packed terrain (the march samples it for the deferred normals)
     const double2* walk_sc;  // [n_t]: (sin, cos)(dist_k / R) of the spherical walker, host libm like the reference; nullptr otherwise
+    WalkAnchor* walk_anchor;  // [wl][n_anchor]: see anchored_lat_lon; nullptr: every sample through asin / atan2
     double *t_lat, *t_lon, *t_elev;
     unsigned long long* t_close;
     // Stage B cache, step-major [n_t][h_pad]
@@ -132,6 +136,37 @@ __global__ void __launch_bounds__(128) k_refraction_probe(const __grid_constant_
     if (i >= n) return;
     g_tab[i] = pieces ? g_fallback(tab, pieces, npieces, S.atm, h[i]) : g_table(tab, h[i] - ATM_BASE);
     g_ref[i] = g_libm(S.atm, h[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Probes behind the reference's text dumpers.
+// ---------------------------------------------------------------------------------------------
+// ray_path.rs:65-91: env.cast_ray_stepper(height, ang.to_radians(), false), set_step_size(ray_step), nsteps x next().
+// One thread per ray. libm_only: PathStepper::next op for op (device_atm.cuh: stepper_next); else the ray-path stage's
+// step with g(h) from the table, its pieces, then libm (device_paths.cuh: rk4_step<FLAT, 1>).
+template <bool FLAT>
+__global__ void __launch_bounds__(128) k_ray_path_probe(const __grid_constant__ DevScene S, DevBuffers B, double start_h, const double* __restrict__ ang_deg,
+                                                        int n, double step, int nsteps, int libm_only, double* __restrict__ h_out) {
+    __shared__ double tab_smem[ATM_FIELDS * ATM_CELLS];
+    for (int i = threadIdx.x; i < ATM_FIELDS * ATM_CELLS; i += blockDim.x) tab_smem[i] = B.atm_cells[i];
+    __syncthreads();
+    const GSource gs{(unsigned)__cvta_generic_to_shared(tab_smem), B.atm_pieces, B.n_atm_pieces};
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Stepper st;
+    stepper_init(st, FLAT, S.radius, start_h, to_radians(ang_deg[i]));
+    const double d = FLAT ? step : step / S.radius, hd = 0.5 * d, d6 = d / 6.0;
+    double* out = h_out + (size_t)i * nsteps;
+    for (int k = 0; k < nsteps; ++k) {
+        if (libm_only) {
+            out[k] = stepper_next(st, S.atm, FLAT, 0, S.radius, step).h;
+        } else {
+            double a_new, b_new;
+            rk4_step<FLAT, 1>(S.atm, gs, S.radius, d, hd, d6, st.a, st.b, &a_new, &b_new);
+            st.a = a_new, st.b = b_new;
+            out[k] = FLAT ? st.a : st.a - S.radius;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -375,6 +410,40 @@ __device__ __forceinline__ void walk_coords(const DevScene& S, const double* __r
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Latitude and longitude of a great-circle sample from an ANCHOR sample of the same column.
+// SphericalCalc::coords_at_dist (directional_calc.rs:71-86) ends in lat = asin(z), lon = atan2(y, x) of the unit
+// vector f = (x, y, z) -- two of the slowest f64 libm calls, 40 % of stage A's instructions. Neighbouring samples
+// of a column differ by 4e-6 rad, so with (lat_a, lon_a) of an anchor sample a few kilometres away (libm, once per
+// 512 or 1024 samples: k_walk_anchors) the sample's angles follow from exact identities with SMALL arguments:
+//     sin(lat - lat_a) = z cos(lat_a) - c sin(lat_a),                 c = sqrt(x^2 + y^2) = cos(lat)
+//     tan(lon - lon_a) = (y cos(lon_a) - x sin(lon_a)) / (x cos(lon_a) + y sin(lon_a))
+// and asin / atan of an argument below 1e-2 are four / five terms of their series (truncation < 1e-22 rad). The
+// rounding errors are absolute ones of ~1e-16 rad on values of order 1 -- what the 1-2 ulp of the libm calls amount to
+// (CUDA's and glibc's differ from each other by as much). Returns false (the caller uses asin / atan2) near the
+// poles, across the antimeridian and when an argument is not small.
+// ---------------------------------------------------------------------------------------------
+struct WalkAnchor {
+    double lat, lon;  // radians
+    double sinlat, coslat, sinlon, coslon;
+};
+
+__device__ __forceinline__ bool anchored_lat_lon(const WalkAnchor& a, V3 f, double* lat_deg, double* lon_deg) {
+    const double c = sqrt_nr(fma(f.x, f.x, f.y * f.y));
+    const double u = fma(f.z, a.coslat, -(c * a.sinlat));    // sin(lat - lat_a)
+    const double p = fma(f.y, a.coslon, -(f.x * a.sinlon));  // c sin(lon - lon_a)
+    const double q = fma(f.x, a.coslon, f.y * a.sinlon);     // c cos(lon - lon_a)
+    const double t = p * rcp_nr(q);
+    const double u2 = u * u, t2 = t * t;
+    // asin u = u + u^3/6 + 3 u^5/40 + 5 u^7/112 + ...;  atan t = t - t^3/3 + t^5/5 - t^7/7 + t^9/9 - ...
+    const double dlat = fma(u * u2, fma(u2, fma(u2, 5.0 / 112.0, 3.0 / 40.0), 1.0 / 6.0), u);
+    const double dlon = fma(-(t * t2), fma(t2, fma(t2, fma(t2, -1.0 / 9.0, 1.0 / 7.0), -1.0 / 5.0), 1.0 / 3.0), t);
+    const double lon = a.lon + dlon;
+    *lat_deg = to_degrees(a.lat + dlat);
+    *lon_deg = to_degrees(lon);
+    return c > 0.05 && q > 0.0 && fabs(t) < 1.0e-2 && fabs(u) < 1.0e-2 && fabs(lon) < 3.1;  // (false for NaN)
+}
+
 // TerrainData::objects_close (utils.rs:76-82): Object::is_close, frustum.rs:103-114 / billboard.rs:68-78
 __device__ __forceinline__ unsigned long long objects_close(const DevScene& S, const DevBuffers& B, V3 fpos, double lat, double lon) {
     const SampleTrig t = sample_trig(S, fpos, lat, lon);
@@ -388,6 +457,19 @@ __device__ __forceinline__ unsigned long long objects_close(const DevScene& S, c
     return mask;
 }
 
+// The anchors of every column: sample (b << shift) + (1 << shift) / 2 of block b, through libm. One thread per anchor.
+__global__ void __launch_bounds__(128) k_walk_anchors(const __grid_constant__ DevScene S, DevBuffers B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, xl = blockIdx.y;
+    if (b >= S.n_anchor) return;
+    const int ka = min((b << S.anchor_shift) + (1 << S.anchor_shift) / 2, S.n_t - 1);
+    const V3 f = walk_fpos(S, B.colcalc + (size_t)xl * 8, B.dist_k[ka], B.walk_sc + ka);
+    WalkAnchor a;
+    a.lat = asin(f.z), a.lon = atan2(f.y, f.x);
+    sincos(a.lat, &a.sinlat, &a.coslat);
+    sincos(a.lon, &a.sinlon, &a.coslon);
+    B.walk_anchor[(size_t)xl * S.n_anchor + b] = a;
+}
+
 template <int W>
 __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__ DevScene S, DevTerrain T, DevBuffers B, int col0) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -397,7 +479,12 @@ __global__ void __launch_bounds__(128) k_terrain_profile(const __grid_constant__
     const double* cc = B.colcalc + (size_t)xl * 8;
     double lat, lon;
     V3 fpos{0.0, 0.0, 0.0};
-    walk_coords<W>(S, cc, d, &lat, &lon, &fpos, B.walk_sc ? B.walk_sc + k : nullptr);
+    bool done = false;
+    if (W == WALK_SPHERICAL && B.walk_anchor) {  // asin / atan2 of the walk's unit vector through the column's anchors
+        fpos = walk_fpos(S, cc, d, B.walk_sc + k);
+        done = anchored_lat_lon(B.walk_anchor[(size_t)xl * S.n_anchor + (k >> S.anchor_shift)], fpos, &lat, &lon);
+    }
+    if (!done) walk_coords<W>(S, cc, d, &lat, &lon, &fpos, B.walk_sc ? B.walk_sc + k : nullptr);
     double elev = elev_or_zero(T, lat, lon);
     size_t idx = (size_t)xl * S.n_pad + k;
     B.t_lat[idx] = lat;
@@ -424,6 +511,22 @@ __global__ void __launch_bounds__(128) k_profile_normals(const __grid_constant__
     const size_t idx = (size_t)xl * S.n_pad + k;
     const V3 n = sample_normal(S, T, B, xl, k, B.t_lat[idx], B.t_lon[idx]);
     out[3 * k] = n.x, out[3 * k + 1] = n.y, out[3 * k + 2] = n.z;
+}
+
+// elev_profile.rs:43-60: params.model.coords_at_dist_calc((lat0, lon0), azimuth).coords_at_dist(x) and
+// terrain.get_elev(..).unwrap_or(0.0) at n distances -- the walker of stage A without its anchors or tables.
+__global__ void __launch_bounds__(128) k_elev_profile(const __grid_constant__ DevScene S, DevTerrain T, double azimuth, const double* __restrict__ dist, int n,
+                                                      double* __restrict__ lat, double* __restrict__ lon, double* __restrict__ elev) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double cc[8];
+    direction_calc(S, azimuth, cc);
+    double la, lo;
+    V3 fpos{0.0, 0.0, 0.0};
+    walk_coords(S, cc, dist[i], &la, &lo, &fpos);
+    if (lat) lat[i] = la;
+    if (lon) lon[i] = lo;
+    elev[i] = elev_or_zero(T, la, lo);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1581,336 +1684,274 @@ __global__ void __launch_bounds__(32 * SHADE_COLS, 4) k_sweep_shade(const __grid
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stage C for opaque terrain without objects, fused: the horizon sweep AND the shading of the pixels it
-// resolves, one warp per (column, row band).
+// Stage C for opaque terrain without objects, three kernels (the product path; k_sweep / k_sweep_shade above are its
+// first version, kept behind ATMRT_STAGE_C=legacy while this one is being measured):
 //
-// The sweep of one column is a staircase walk through (row, step) whose every window load depends on the row
-// resolved before it: a latency chain. The shading of the resolved pixels (two deferred terrain normals,
-// interpolation, colouring, metadata) is independent arithmetic. In one kernel the schedulers fill the sweep's
-// load stalls of some warps with the shading of others, the first-hit plane (`sweep_hit`) never goes to memory,
-// and sky pixels cost one store loop instead of a shading pass. A column is cut into row bands so that the
-// grid stays large when the columns are sharded over several GPUs: by the monotonicity the sweep rests on, the
-// walk of a band starts at the first-hit step of the row just below it, which the band finds by scanning that
-// ONE row from step 1 (the same cells test the same products, so the band sees exactly the state the single
-// walk would hand it).
-//
-// Resolved pixels are queued in the lanes -- entry j of a batch in lane 31 - j, so that lanes ascend with the row
-// as in a warp of 32 adjacent rows -- and shaded 29 to 32 at a time between two row groups. The colour goes to a
-// column-major scratch image (a warp's 32 rows are 96 contiguous bytes there; the row-major image would take one
-// 1-byte sector write per pixel and channel) which k_rgb_rows transposes; the 32-byte metadata records are whole
-// sectors and go straight to the row-major plane.
+//   k_sweep_bits   the horizon sweep with the sign tests of a whole window taken as warp votes: the lanes hold 32
+//                  consecutive steps of a group of four rows, three ballots per row (ray above / below / exactly on the
+//                  terrain) turn the window into bit masks, and every row of the group is then resolved by a handful of
+//                  warp-uniform integer operations -- the first set bit of (above << 1) & below is the reference's first
+//                  d1 * d2 < 0 seen from above (utils.rs:220-222). Per column it also lists the DISTINCT terrain samples
+//                  its hits touch (sample k - 1 and k of every first-hit step k, in ascending order): the hit plane
+//                  stores, per pixel, the position of its k in that list.
+//   k_hit_normals  TerrainData::normal (find_normal, utils.rs:15-40) of every listed sample, one thread per sample: the
+//                  deferred normals at full lanes, each distinct sample once (rows in the foreground share steps).
+//   k_shade_tiles  interpolation, colouring and the metadata of the pixels; warps along the rows of one column (shared
+//                  sectors in every cache), written row-major through shared memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int FUSED_WARPS = 4;  // adjacent columns of one band share a block (and the path windows in L1)
-#ifndef FUSED_MIN_BLOCKS
-#define FUSED_MIN_BLOCKS 6
-#endif
+constexpr int BITS_WARPS = 4;  // adjacent columns share a block (and the path windows in L1)
 
-struct FusedOut {
-    unsigned char* rgb_t;         // [wl][h_pad][3] column-major scratch (null: no colour wanted)
-    unsigned long long* partial;  // [wl][bands][2]: ray steps, pixels hit -- summed over the unflagged columns by k_sweep_counters
-    int band_rows;                // rows per band (a multiple of SWEEP_ROWS)
-    int bands;
+struct SweepLists {
+    int* list;        // [wl][cap]: the distinct samples of the column's hits, ascending; list[s - 1] == list[s] - 1 for every slot s a pixel refers to
+    int* count;       // [wl]
+    double* normals;  // [wl][cap][3]
+    int cap;
 };
 
-template <int W>
-__global__ void __launch_bounds__(32 * FUSED_WARPS, FUSED_MIN_BLOCKS) k_sweep_fused(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, FusedOut F, int col0, int col1) {
+// predicated global stores (no branch): the sweep's control flow is warp-uniform, only lane 0 writes
+__device__ __forceinline__ void st_if_s32(int* p, int v, bool ok) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.global.s32 [%1], %2;\n\t}" ::"r"((unsigned)ok), "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_if_v4s32(int* p, int a, int b, int c, int d, bool ok) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.global.v4.s32 [%1], {%2, %3, %4, %5};\n\t}" ::"r"((unsigned)ok), "l"(p), "r"(a), "r"(b),
+                 "r"(c), "r"(d)
+                 : "memory");
+}
+
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(32 * BITS_WARPS, MIN_BLOCKS) k_sweep_bits(const __grid_constant__ DevScene S, DevBuffers B, SweepLists L, int col0, int col1) {
     if (B.sweep_flags[0] != 0) return;
-    __shared__ double s_nrm[FUSED_WARPS][64][3];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int xl = col0 + blockIdx.x * FUSED_WARPS + w;
+    const int lane = threadIdx.x & 31;
+    const bool lane0 = lane == 0;
+    const int xl = col0 + blockIdx.x * BITS_WARPS + (threadIdx.x >> 5);
     if (xl >= col1) return;
-    const int wl = S.x1 - S.x0;
-    // bands are numbered from the top of the image; blockIdx.y = 0 is the bottom band (the walk's first, and the
-    // busiest: every one of its rows hits), so that the long warps are scheduled first
-    const int band = F.bands - 1 - (int)blockIdx.y;
-    const int y_lo = band * F.band_rows;
-    const int y_hi = min(S.height, y_lo + F.band_rows) - 1;
     const double* __restrict__ te = B.t_elev + (size_t)xl * S.n_pad;
     const double* __restrict__ pe = B.p_elev;
+    int* __restrict__ hit = B.sweep_hit + (size_t)xl * S.h_pad;  // per pixel: 1 + the slot of its first-hit step in the list (0: no hit)
+    int* __restrict__ list = L.list + (size_t)xl * L.cap;
     const int n_t = S.n_t, k_last = n_t - 1;
     static_assert(SWEEP_ROWS == PATH_ROWS && SWEEP_ROWS == 4, "the sweep reads one row group of the path cache per 32-byte load");
     bool flagged = !(pe[0] - te[0] > 0.0);  // every ray starts at the observer altitude (element 0 of every row)
-    unsigned long long acc_steps = 0ull;
-    unsigned acc_hits = 0u;
-    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    const Rgb8 sky{{S.shade.def_color[0], S.shade.def_color[1], S.shade.def_color[2]}};
-
-    // one pixel of this column: colour to the scratch image, metadata and step count to the row-major planes
-    auto store_pixel = [&](int y, Rgb8 px, double m0, double m1, double m2, double m3, int consumed) {
-        if (F.rgb_t) {
-            unsigned char* o = F.rgb_t + ((size_t)xl * S.h_pad + y) * 3;
-            o[0] = px.c[0], o[1] = px.c[1], o[2] = px.c[2];
-        }
-        const size_t pixel = (size_t)y * wl + xl;
-        if (O.meta) {
-            double2* out = reinterpret_cast<double2*>(O.meta + pixel);
-            out[0] = make_double2(m0, m1);
-            out[1] = make_double2(m2, m3);
-        }
-        if (O.steps) O.steps[pixel] = consumed;
-    };
-
-    // ---- where the walk enters this band: the first-hit step of the row just below it --------------------
-    int k = 1;  // first step the current row may still cross at
-    if (y_hi + 1 < S.height && !flagged) {
-        const int yb = y_hi + 1;
-        const int nlim = min(n_t, B.p_n[yb]);
-        bool odd = false, found = false;
-        while (k < nlim) {
-            const int kk = min(k + lane, k_last);
-            const double cur = pe[path_index(n_t, kk, yb)], t_cur = te[kk];
-            double prv = __shfl_up_sync(FULL, cur, 1), t_prv = __shfl_up_sync(FULL, t_cur, 1);
-            if (lane == 0) prv = pe[path_index(n_t, k - 1, yb)], t_prv = te[k - 1];
-            const double d1 = prv - t_prv, d2 = cur - t_cur;
-            const bool in = k + lane < nlim;
-            const unsigned hits = __ballot_sync(FULL, in && d1 > 0.0 && d1 * d2 < 0.0);  // the reference's product test (utils.rs:222), from above
-            const bool oddcell = in && (d2 == 0.0 || (d1 * d2 < 0.0 && !(d1 > 0.0)));
-            odd = odd || (oddcell && (hits == 0 || lane < __ffs(hits) - 1));
-            if (hits) {
-                k += __ffs(hits) - 1;
-                found = true;
-                break;
-            }
-            k += 32;
-        }
-        if (!found) k = max(nlim, 1);  // its path ends without a sign change: the rows above go on from there
-        if (__any_sync(FULL, odd)) flagged = true;
+    // The window: lane j holds step kb + j; lane 0 is the "before" side of the first step a row may cross at, so a
+    // window serves the steps kb + 1 .. kb + 31 and advances by 31. `lo`: the current row may cross at lanes >= lo only
+    // (kb + lo is the first-hit step of the row below it, or where that row's path ended).
+    int kb = 0, lo = 1;
+    int* lp = list;   // end of the list
+    int last = -1;    // its last entry: the step of the latest hit
+    unsigned bad = 0u;  // odd cells met so far
+    double t_cur;
+    double4 cur;
+    unsigned m4;  // this lane's step: the rows of the group whose ray is below the terrain there (bit R = row R)
+    bool finished = false;  // the walk reached the end of the caches: every row above sees only sky
+#define ATMRT_BITS_WINDOW(YBASE)                                                                                  \
+    {                                                                                                            \
+        cur = *reinterpret_cast<const double4*>(pe + path_index(n_t, min(kb + lane, k_last), YBASE));            \
+        m4 = (cur.x - t_cur < 0.0 ? 1u : 0u) | (cur.y - t_cur < 0.0 ? 2u : 0u) | (cur.z - t_cur < 0.0 ? 4u : 0u) | \
+             (cur.w - t_cur < 0.0 ? 8u : 0u);                                                                    \
     }
-
-    // ---- the queue of resolved pixels and its shading ------------------------------------------------------
-    int qy = 0, qk = 0, qn = 0;  // this lane's entry (row, first-hit step or 0), entries queued
-    auto push = [&](int y, int kh) {
-        if (lane == 31 - qn) qy = y, qk = kh;
-        ++qn;
-    };
-    auto flush = [&]() {
-        const bool valid = lane >= 32 - qn;
-        const int yy = __shfl_sync(FULL, qy, 31);  // a queued row for the idle lanes to shadow
-        const int y = valid ? qy : yy;
-        const int kh = valid ? qk : 0;
-        const bool hit = kh > 0;
-        const int nlim = min(n_t, B.p_n[y]);
-        // The terrain normals of the two samples that bracket each hit (TerrainData::normal, deferred from stage A:
-        // sample_normal). The rows of a batch hit a handful of distinct samples -- foreground rows share one step,
-        // rows on a slope hit consecutive steps, and sample k - 1 of one run of rows is sample k of the next -- so
-        // each distinct sample is evaluated once: the first lane of every run of equal k owns sample k, and sample
-        // k - 1 unless the next run owns it as its k; the owned samples are numbered, dealt to the lanes 32 at a
-        // time, and read back through shared memory.
-        V3 nrm[2] = {V3{0.0, 0.0, 0.0}, V3{0.0, 0.0, 0.0}};
-        {
-            const int k_up = __shfl_up_sync(FULL, kh, 1);
-            const bool lead = hit && (lane == 0 || k_up != kh);
-            const unsigned mask1 = __ballot_sync(FULL, lead);
-            if (mask1) {  // warp-uniform
-                const int leader = 31 - __clz(mask1 & (0xffffffffu >> (31 - lane)));         // of this lane's run (when it hit)
-                const unsigned later = leader >= 31 || leader < 0 ? 0u : (mask1 & (0xfffffffeu << leader));
-                const int next = later ? __ffs(later) - 1 : -1;                               // leader of the next run
-                const int k_next = __shfl_sync(FULL, kh, next < 0 ? 0 : next);
-                const bool own0 = lead && !(next >= 0 && k_next == kh - 1);
-                const unsigned mask0 = __ballot_sync(FULL, own0);
-                const int n1cnt = __popc(mask1), total = n1cnt + __popc(mask0);
-                __syncwarp();
-                for (int base = 0; base < total; base += 32) {
-                    const int item = base + lane;
-                    const bool mine = item < total, second = item >= n1cnt;
-                    const unsigned src = mine ? __fns(second ? mask0 : mask1, 0, (second ? item - n1cnt : item) + 1) : 0u;
-                    const int ks = __shfl_sync(FULL, kh, src & 31);
-                    if (mine) {
-                        const int smp = ks - (second ? 1 : 0);
-                        const size_t ti = (size_t)xl * S.n_pad + smp;
-                        const V3 n = sample_normal<W>(S, B.terrain, B, xl, smp, B.t_lat[ti], B.t_lon[ti]);
-                        s_nrm[w][item][0] = n.x, s_nrm[w][item][1] = n.y, s_nrm[w][item][2] = n.z;
-                    }
-                }
-                __syncwarp();
-                if (hit) {
-                    const int i1 = __popc(mask1 & ((1u << leader) - 1u));
-                    const int i0 = ((mask0 >> leader) & 1u) ? n1cnt + __popc(mask0 & ((1u << leader) - 1u)) : i1 + 1;
-                    nrm[0] = V3{s_nrm[w][i0][0], s_nrm[w][i0][1], s_nrm[w][i0][2]};
-                    nrm[1] = V3{s_nrm[w][i1][0], s_nrm[w][i1][1], s_nrm[w][i1][2]};
-                }
-            }
-        }
-        // get_single_pixel's hit (utils.rs:220-236) and draw_image (renderer/mod.rs:395-411) for ONE opaque trace point:
-        // with terrain_alpha == 1 the compositing is  result = add([0,0,0], c, 1.0 * 1.0)  and then
-        // add(result, default, 0.0), and ((0/255 + c/255 * 1) * 255) as u8 == c, ((c/255 + d/255 * 0) * 255) as u8 == c
-        // for all 256 values of c (tests/test_oracle_known_answers.py: test_identity_requantisation_all_values), so the
-        // pixel IS the (fogged) colour of its trace point; a pixel without one is add([0,0,0], default, 1.0) == default.
-        Rgb8 px = sky;
-        double m_lat = qnan, m_lon = qnan, m_elev = qnan, m_dist = qnan;
-        int consumed = nlim > 0 ? nlim - 1 : 0;
-        if (hit) {
-            const size_t ti = (size_t)xl * S.n_pad + kh;
-            const size_t p1 = path_index(n_t, kh, y), p0 = p1 - PATH_ROWS;
-            const double lat0 = B.t_lat[ti - 1], lon0 = B.t_lon[ti - 1], elev0 = B.t_elev[ti - 1];
-            const double lat1 = B.t_lat[ti], lon1 = B.t_lon[ti], elev1 = B.t_elev[ti];
-            const double ray0 = pe[p0], ray1 = pe[p1];
-            const double dist0 = B.path_x[kh - 1], dist1 = B.path_x[kh];  // path_x[0] = 0
-            const double len0 = kh - 1 == 0 ? 0.0 : B.p_len[p0], len1 = B.p_len[p1];
-            const double diff1 = ray0 - elev0, diff2 = ray1 - elev1;
-            const double prop = diff1 / (diff1 - diff2);
-            // TracingState::interpolate, utils.rs:108-125
-            m_lat = lat0 + (lat1 - lat0) * prop, m_lon = lon0 + (lon1 - lon0) * prop;
-            m_dist = dist0 + (dist1 - dist0) * prop, m_elev = elev0 + (elev1 - elev0) * prop;
-            const double plen = len0 + (len1 - len0) * prop;
-            const V3 normal = nrm[0] + (nrm[1] - nrm[0]) * prop;
-            px = color_for_pixel(S.shade, true, m_elev, m_dist, normal, Color4{0.0, 0.0, 0.0, 1.0});
-            if (S.shade.fog_enabled) px = apply_fog(S.shade.fog_distance, plen, px);
-            consumed = kh;
-        }
-        if (valid) store_pixel(y, px, m_lat, m_lon, m_elev, m_dist, consumed);
-        acc_steps += valid ? (unsigned long long)consumed : 0ull;
-        acc_hits += valid && hit ? 1u : 0u;
-        qn = 0;
-    };
-
-    // ---- the walk: groups of SWEEP_ROWS rows (local row 0 is the top one), bottom group first, rows bottom-up ----
-    bool finished = false;
-    for (int g = y_hi / SWEEP_ROWS;; --g) {
-        // (one more turn after the last group, to shade what is still queued: `flush` is expanded in ONE place)
-        const bool walking = g * SWEEP_ROWS >= y_lo && !flagged && !finished;
-        const int ybase = max(g, 0) * SWEEP_ROWS;
-        int r = walking ? min(SWEEP_ROWS - 1, y_hi - ybase) : -1;
+    t_cur = te[min(lane, k_last)];
+    for (int g = (S.height - 1) / SWEEP_ROWS; g >= 0 && bad == 0u && !flagged && !finished; --g) {
+        const int ybase = g * SWEEP_ROWS;
+        const int rmax = min(SWEEP_ROWS - 1, S.height - 1 - ybase);
         const int4 len = *reinterpret_cast<const int4*>(B.p_n + ybase);  // p_n is padded to h_pad entries
-        const int n0 = min(n_t, len.x), n1 = min(n_t, len.y), n2 = min(n_t, len.z), n3 = min(n_t, len.w);
-        while (r >= 0 && !flagged) {
-            if (k >= n_t) {
-                // The walk has reached the end of the caches: the first row that sees only sky scanned to the end,
-                // and no row above it can cross any more (no path is longer than n_t). All of them at once.
-                for (int yy = ybase + r - lane; yy >= y_lo; yy -= 32) {
-                    const int nl = min(n_t, B.p_n[yy]);
-                    const int consumed = nl > 0 ? nl - 1 : 0;
-                    store_pixel(yy, sky, qnan, qnan, qnan, qnan, consumed);
-                    acc_steps += (unsigned long long)consumed;
-                }
-                finished = true;
-                break;
-            }
-            int nlim = r == 3 ? n3 : (r == 2 ? n2 : (r == 1 ? n1 : n0));
-            if (k >= nlim) {  // this row's path ends without a sign change
-                push(ybase + r, 0);
-                --r;
-                continue;
-            }
-            // the window: steps k + lane for all rows of the group; the "before" side comes from the lane below
-            const int kk = min(k + lane, k_last);
-            const double4 cur = *reinterpret_cast<const double4*>(pe + path_index(n_t, kk, ybase));
-            const double t_cur = te[kk];
-            double4 prv;
-            prv.x = __shfl_up_sync(FULL, cur.x, 1), prv.y = __shfl_up_sync(FULL, cur.y, 1);
-            prv.z = __shfl_up_sync(FULL, cur.z, 1), prv.w = __shfl_up_sync(FULL, cur.w, 1);
-            double t_prv = __shfl_up_sync(FULL, t_cur, 1);
-            if (lane == 0) {
-                prv = *reinterpret_cast<const double4*>(pe + path_index(n_t, k - 1, ybase));
-                t_prv = te[k - 1];
-            }
-            int lo = 0;        // lanes below `lo` are steps the current row cannot cross at any more
-            bool odd = false;  // an exact zero or an exit from below among the cells of this window
-            // Resolve rows from the registers while the window serves them. A crossing from above
-            // (d1 > 0 > d2, utils.rs:220-222) at the first such lane >= lo is the row's hit; the row above
-            // continues from that lane.
-#define ATMRT_FUSED_ROW(C, R, NABOVE)                                                                        \
-    {                                                                                                        \
-        const double d1 = prv.C - t_prv, d2 = cur.C - t_cur;                                                 \
-        const bool in = k + lane < nlim, cross = d1 * d2 < 0.0; /* utils.rs:222 */                           \
-        const bool oddcell = in && lane >= lo && (d2 == 0.0 || (cross && !(d1 > 0.0)));                      \
-        const unsigned hits = __ballot_sync(FULL, in && lane >= lo && d1 > 0.0 && cross);                    \
-        odd = odd || (oddcell && (hits == 0 || lane < __ffs(hits) - 1)); /* only cells the row visits */     \
-        if (hits == 0) {                                                                                     \
-            if (k + 32 >= nlim) { /* the row ends inside the window: no hit; the row above goes on from there */ \
-                push(ybase + R, 0);                                                                          \
-                r = R - 1;                                                                                   \
-                k = nlim;                                                                                    \
-            } else {                                                                                         \
-                r = R;                                                                                       \
-                k += 32;                                                                                     \
-            }                                                                                                \
-            lo = 0;                                                                                          \
-            goto fused_window_done;                                                                          \
-        }                                                                                                    \
-        lo = __ffs(hits) - 1;                                                                                \
-        push(ybase + R, k + lo);                                                                             \
-        r = R - 1;                                                                                           \
-        nlim = NABOVE;                                                                                       \
+        ATMRT_BITS_WINDOW(ybase)
+        // Rows that cross at the very step the row below them hit at need no search: where that row crossed from above,
+        // every ray above it was above the terrain one step earlier too (the rays do not cross: k_path_check), so such
+        // a row hits there iff it is below the terrain at that step -- one bit of m4 at the hit's lane.
+        unsigned same = lo < 32 && kb + lo == last ? __shfl_sync(FULL, m4, lo & 31) : 0u;
+        int h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+        // One row: walk the windows until the row crosses from above (its hit), its path ends (no hit; the row above
+        // goes on from there: a path never outlives the one above it, k_path_check) or the caches end (sky).
+#define ATMRT_BITS_ROW(C, R, LEN, HOUT)                                                                          \
+    if (R <= rmax) {                                                                                             \
+        if ((same >> R) & 1u) {                                                                                  \
+            HOUT = (int)(lp - list); /* the same step, the same slot */                                          \
+        } else {                                                                                                 \
+            const int nlim = min(n_t, LEN);                                                                      \
+            same = 0u;                                                                                           \
+            for (;;) {                                                                                           \
+                if (kb + lo >= nlim) {                                                                           \
+                    finished = finished || kb + lo >= n_t;                                                       \
+                    break;                                                                                       \
+                }                                                                                                \
+                if (lo < 32) {                                                                                   \
+                    const double d = cur.C - t_cur; /* ray - terrain at step kb + lane */                        \
+                    const unsigned above = __ballot_sync(FULL, d > 0.0), below = __ballot_sync(FULL, d < 0.0);   \
+                    const unsigned zero = __ballot_sync(FULL, d == 0.0);                                         \
+                    const int span = nlim - kb; /* lanes below `span` are steps of this row's path */           \
+                    const unsigned visit = (span >= 32 ? FULL : (1u << span) - 1u) & (FULL << lo);               \
+                    const unsigned entry = (above << 1) & below & visit; /* d1 > 0 > d2: utils.rs:220-222, from above */ \
+                    /* an exit from below (the ray started under the surface) or an exact zero among the cells the  \
+                       row visits before its hit sends the column to the general march */                        \
+                    const unsigned odd = (((below << 1) & above) | zero) & visit;                                \
+                    if (entry) {                                                                                 \
+                        const int hl = __ffs(entry) - 1, kh = kb + hl;                                           \
+                        bad |= odd & ((1u << hl) - 1u);                                                          \
+                        /* the distinct samples of the hits: kh - 1 and kh, appended unless they are the last entries */ \
+                        const bool new1 = last != kh, new0 = new1 && last != kh - 1;                             \
+                        st_if_s32(lp, kh - 1, lane0 && new0);                                                    \
+                        lp += new0 ? 1 : 0;                                                                      \
+                        st_if_s32(lp, kh, lane0 && new1);                                                        \
+                        lp += new1 ? 1 : 0;                                                                      \
+                        last = kh;                                                                               \
+                        HOUT = (int)(lp - list); /* 1 + slot of kh */                                            \
+                        lo = hl;                 /* the row above continues from the same step */                \
+                        same = __shfl_sync(FULL, m4, hl);                                                        \
+                        break;                                                                                   \
+                    }                                                                                            \
+                    bad |= odd;                                                                                  \
+                    if (kb + 32 >= nlim) { /* the row ends inside the window */                                  \
+                        lo = nlim - kb;                                                                          \
+                        break;                                                                                   \
+                    }                                                                                            \
+                    kb += 31, lo = 1;                                                                            \
+                } else { /* the row below ended on the last step of this window: move on (kb + lo is unchanged) */ \
+                    kb += 31, lo -= 31;                                                                          \
+                }                                                                                                \
+                t_cur = te[min(kb + lane, k_last)];                                                              \
+                ATMRT_BITS_WINDOW(ybase)                                                                         \
+            }                                                                                                    \
+        }                                                                                                        \
     }
-            switch (r) {
-                case 3: ATMRT_FUSED_ROW(w, 3, n2)
-                case 2: ATMRT_FUSED_ROW(z, 2, n1)
-                case 1: ATMRT_FUSED_ROW(y, 1, n0)
-                default: ATMRT_FUSED_ROW(x, 0, n0)
-            }
-#undef ATMRT_FUSED_ROW
-        fused_window_done:
-            // An odd cell among those a row visits before its hit (an exact zero of ray - terrain, or an exit
-            // from below: a ray that started under the surface) sends the column to the general march.
-            if (__any_sync(FULL, odd)) flagged = true;
-            k += lo;  // the next window starts at the last hit
+        ATMRT_BITS_ROW(w, 3, len.w, h3)
+        ATMRT_BITS_ROW(z, 2, len.z, h2)
+        ATMRT_BITS_ROW(y, 1, len.y, h1)
+        ATMRT_BITS_ROW(x, 0, len.x, h0)
+#undef ATMRT_BITS_ROW
+        st_if_v4s32(hit + ybase, h0, h1, h2, h3, lane0);  // (the plane is padded to h_pad rows)
+        if (finished) {
+            // The first row that sees only sky scanned to the end, and no row above it can cross any more (no path is
+            // longer than n_t). All of them at once.
+            for (int yy = ybase - 1 - lane; yy >= 0; yy -= 32) hit[yy] = 0;
         }
-        // between two row groups: the next group's (up to four) entries always fit
-        if (qn > 32 - SWEEP_ROWS || (!walking && qn > 0)) flush();
-        if (!walking) break;
     }
-    if (flagged && lane == 0) {
-        B.sweep_col[xl] = 1;                 // (zeroed before the launch; every band that flags writes the same 1)
-        atomicOr(B.sweep_flags + 1, 1u);     // some column needs the brute-force march
-    }
-    for (int o = 16; o > 0; o >>= 1) acc_steps += __shfl_xor_sync(FULL, acc_steps, o);
-    acc_hits = __reduce_add_sync(FULL, acc_hits);
-    if (lane == 0) {
-        unsigned long long* out = F.partial + ((size_t)xl * F.bands + band) * 2;
-        out[0] = acc_steps, out[1] = (unsigned long long)acc_hits;
+#undef ATMRT_BITS_WINDOW
+    flagged = flagged || bad != 0u;
+    if (lane0) {
+        L.count[xl] = (int)(lp - list);
+        B.sweep_col[xl] = flagged ? 1 : 0;
+        if (flagged) atomicOr(B.sweep_flags + 1, 1u);  // some column needs the brute-force march
     }
 }
 
-// The render counters of the swept columns: the partial sums of the bands of every column the sweep did NOT hand
-// to the brute-force march (that march counts its own pixels). One thread per column.
-__global__ void __launch_bounds__(128) k_sweep_counters(DevBuffers B, const unsigned long long* __restrict__ partial, int wl, int bands) {
+// TerrainData::normal of the listed samples (sample_normal: find_normal at the sample's cached coordinates).
+template <int W>
+__global__ void __launch_bounds__(128) k_hit_normals(const __grid_constant__ DevScene S, DevBuffers B, SweepLists L, int parts) {
     if (B.sweep_flags[0] != 0) return;
-    const int xl = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long steps = 0ull, hits = 0ull;
-    if (xl < wl && B.sweep_col[xl] == 0) {
-        for (int b = 0; b < bands; ++b) steps += partial[((size_t)xl * bands + b) * 2], hits += partial[((size_t)xl * bands + b) * 2 + 1];
-    }
-    for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(FULL, steps, o), hits += __shfl_xor_sync(FULL, hits, o);
-    if ((threadIdx.x & 31) == 0) {
-        if (steps) atomicAdd(B.counters + CNT_RAY_STEPS, steps);
-        if (hits) atomicAdd(B.counters + CNT_TRACE_POINTS, hits), atomicAdd(B.counters + CNT_PIXELS_HIT, hits);
+    const int xl = blockIdx.x / parts, part = blockIdx.x % parts;
+    if (B.sweep_col[xl] != 0) return;  // flagged columns belong to the brute-force march
+    const int cnt = L.count[xl];
+    const int* __restrict__ list = L.list + (size_t)xl * L.cap;
+    double* __restrict__ out = L.normals + (size_t)xl * L.cap * 3;
+    for (int s = part * 128 + threadIdx.x; s < cnt; s += parts * 128) {
+        const int smp = list[s];
+        const size_t ti = (size_t)xl * S.n_pad + smp;
+        const V3 n = sample_normal<W>(S, B.terrain, B, xl, smp, B.t_lat[ti], B.t_lon[ti]);
+        out[3 * s] = n.x, out[3 * s + 1] = n.y, out[3 * s + 2] = n.z;
     }
 }
 
-// Column-major colour scratch [wl][h_pad][3] -> the row-major image [h][wl][3]. A block moves a tile of 32 columns x
-// 32 rows through shared memory: 96 contiguous bytes per column in, 96 contiguous bytes per row out.
-__global__ void __launch_bounds__(256) k_rgb_rows(const unsigned char* __restrict__ rgb_t, unsigned char* __restrict__ rgb, int wl, int h, int h_pad,
-                                                 const unsigned* __restrict__ sweep_flags) {
-    if (sweep_flags[0] != 0) return;
-    __shared__ unsigned tile[32][25];  // [column][24 words = 32 rows x 3 bytes] (+1: bank spread)
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int c0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
-    for (int c = ty; c < 32; c += 8) {
-        if (tx < 24 && c0 + c < wl) tile[c][tx] = *reinterpret_cast<const unsigned*>(rgb_t + ((size_t)(c0 + c) * h_pad + y0) * 3 + 4 * tx);
+// get_single_pixel's hit (utils.rs:220-236) and draw_image (renderer/mod.rs:395-411) of the swept pixels. A block is a
+// tile of 32 rows x TILE_COLS columns: each warp shades 32 adjacent rows of ONE column -- adjacent rows hit adjacent
+// steps and adjacent list slots, so the reads of the hit plane, the list, the normals and both caches share sectors --
+// and the results are staged in shared memory and written with the lanes running along x, so that the row-major image
+// and metadata are stored as contiguous row segments.
+// With terrain_alpha == 1 the compositing of ONE opaque trace point is  result = add([0,0,0], c, 1.0 * 1.0)  and then
+// add(result, default, 0.0), and ((0/255 + c/255 * 1) * 255) as u8 == c, ((c/255 + d/255 * 0) * 255) as u8 == c for all
+// 256 values of c (tests/test_oracle_known_answers.py: test_identity_requantisation_all_values): the pixel IS the
+// (fogged) colour of its trace point, and a pixel without one is add([0,0,0], default, 1.0) == default.
+constexpr int TILE_COLS = 8;
+
+__global__ void __launch_bounds__(32 * TILE_COLS, 4) k_shade_tiles(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, SweepLists L, int row0) {
+    if (B.sweep_flags[0] != 0) return;
+    __shared__ double s_meta[32][TILE_COLS * 4];
+    __shared__ __align__(16) unsigned char s_rgb[32][TILE_COLS * 3];
+    __shared__ int s_steps[32][TILE_COLS];
+    __shared__ unsigned char s_skip[TILE_COLS];
+    __shared__ unsigned long long s_cnt[TILE_COLS];
+    __shared__ unsigned s_hits[TILE_COLS];
+    const int wl = S.x1 - S.x0, n_t = S.n_t;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c0 = blockIdx.y * TILE_COLS, y0 = row0 + blockIdx.x * 32;  // row0: a multiple of 32 (row bands)
+    const int xl = c0 + w, y = y0 + lane;
+    const bool col_ok = xl < wl && B.sweep_col[min(xl, wl - 1)] == 0;  // flagged columns belong to the brute-force march
+    const bool active = col_ok && y < S.height;
+    if (lane == 0) s_skip[w] = col_ok ? 0 : 1;
+    const int xx = min(xl, wl - 1), yy = min(y, S.height - 1);
+    const int nlim = min(n_t, B.p_n[yy]);
+    const int slot1 = active ? B.sweep_hit[(size_t)xx * S.h_pad + yy] : 0;
+    const bool hit = slot1 > 0;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    Rgb8 px{{S.shade.def_color[0], S.shade.def_color[1], S.shade.def_color[2]}};
+    double m_lat = qnan, m_lon = qnan, m_elev = qnan, m_dist = qnan;
+    int consumed = nlim > 0 ? nlim - 1 : 0;
+    if (hit) {
+        const int s = slot1 - 1;
+        const int kh = L.list[(size_t)xx * L.cap + s];
+        const double* __restrict__ nr = L.normals + ((size_t)xx * L.cap + s - 1) * 3;  // slots s - 1, s: samples kh - 1, kh
+        const V3 n0{nr[0], nr[1], nr[2]}, n1{nr[3], nr[4], nr[5]};
+        const size_t ti = (size_t)xx * S.n_pad + kh;
+        const size_t p1 = path_index(n_t, kh, yy), p0 = p1 - PATH_ROWS;
+        const double lat0 = B.t_lat[ti - 1], lon0 = B.t_lon[ti - 1], elev0 = B.t_elev[ti - 1];
+        const double lat1 = B.t_lat[ti], lon1 = B.t_lon[ti], elev1 = B.t_elev[ti];
+        const double ray0 = B.p_elev[p0], ray1 = B.p_elev[p1];
+        const double dist0 = B.path_x[kh - 1], dist1 = B.path_x[kh];  // path_x[0] = 0
+        const double len0 = kh - 1 == 0 ? 0.0 : B.p_len[p0], len1 = B.p_len[p1];
+        const double diff1 = ray0 - elev0, diff2 = ray1 - elev1;
+        const double prop = diff1 / (diff1 - diff2);
+        // TracingState::interpolate, utils.rs:108-125
+        m_lat = lat0 + (lat1 - lat0) * prop, m_lon = lon0 + (lon1 - lon0) * prop;
+        m_dist = dist0 + (dist1 - dist0) * prop, m_elev = elev0 + (elev1 - elev0) * prop;
+        const double plen = len0 + (len1 - len0) * prop;
+        const V3 normal = n0 + (n1 - n0) * prop;
+        px = color_for_pixel(S.shade, true, m_elev, m_dist, normal, Color4{0.0, 0.0, 0.0, 1.0});
+        if (S.shade.fog_enabled) px = apply_fog(S.shade.fog_distance, plen, px);
+        consumed = kh;
     }
-    __syncthreads();
-    const unsigned char* tb = reinterpret_cast<const unsigned char*>(&tile[0][0]);
-    const bool words = (wl & 3) == 0 && c0 + 32 <= wl;  // every row segment of the tile is 96 aligned bytes
-    for (int r = ty; r < 32; r += 8) {
-        if (y0 + r >= h) continue;
-        unsigned char* out = rgb + ((size_t)(y0 + r) * wl + c0) * 3;
-        if (words) {
-            if (tx < 24) {
-                unsigned v = 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int b = 4 * tx + q, c = b / 3, ch = b - 3 * c;
-                    v |= (unsigned)tb[c * 100 + r * 3 + ch] << (8 * q);
-                }
-                reinterpret_cast<unsigned*>(out)[tx] = v;
+    s_rgb[lane][w * 3 + 0] = px.c[0], s_rgb[lane][w * 3 + 1] = px.c[1], s_rgb[lane][w * 3 + 2] = px.c[2];
+    s_meta[lane][w * 4 + 0] = m_lat, s_meta[lane][w * 4 + 1] = m_lon, s_meta[lane][w * 4 + 2] = m_elev, s_meta[lane][w * 4 + 3] = m_dist;
+    s_steps[lane][w] = consumed;
+    {  // render counters: one atomic set per block
+        unsigned long long steps = active ? (unsigned long long)consumed : 0ull;
+        for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(FULL, steps, o);
+        const unsigned hits = __popc(__ballot_sync(FULL, active && hit));
+        if (lane == 0) s_cnt[w] = steps, s_hits[w] = hits;
+    }
+    const bool all_cols = __syncthreads_and(col_ok ? 1 : 0) != 0;  // also the barrier between staging and write-out
+    const int rows = min(32, S.height - y0);
+    // Write-out with the lanes along x: thread t handles pixel (row t / TILE_COLS, column t % TILE_COLS) of the tile -- its
+    // 32 bytes of metadata as two 16-byte stores -- and, for the colour, word t of the tile's 32 x 6 four-byte words
+    // when the row segments are word-aligned.
+    {
+        const int r = threadIdx.x / TILE_COLS, c = threadIdx.x % TILE_COLS;
+        const bool live = r < rows && c0 + c < wl && !s_skip[c];
+        if (O.meta && live) {
+            double2* out = reinterpret_cast<double2*>(O.meta + (size_t)(y0 + r) * wl + c0 + c);
+            out[0] = make_double2(s_meta[r][c * 4 + 0], s_meta[r][c * 4 + 1]);
+            out[1] = make_double2(s_meta[r][c * 4 + 2], s_meta[r][c * 4 + 3]);
+        }
+        if (O.steps && live) O.steps[(size_t)(y0 + r) * wl + c0 + c] = s_steps[r][c];
+    }
+    if (O.rgb) {
+        if (all_cols && (wl & 3) == 0) {  // every row segment of the tile is 24 aligned bytes
+            constexpr int WORDS = TILE_COLS * 3 / 4;
+            if ((int)threadIdx.x < rows * WORDS) {
+                const int r = threadIdx.x / WORDS, q = threadIdx.x % WORDS;
+                const unsigned v = *reinterpret_cast<const unsigned*>(&s_rgb[r][q * 4]);
+                *reinterpret_cast<unsigned*>(O.rgb + ((size_t)(y0 + r) * wl + c0) * 3 + q * 4) = v;
             }
         } else {
-            for (int b = tx; b < 96; b += 32) {
-                const int c = b / 3, ch = b - 3 * c;
-                if (c0 + c < wl) out[b] = tb[c * 100 + r * 3 + ch];
+            for (int e = threadIdx.x; e < rows * TILE_COLS * 3; e += 32 * TILE_COLS) {
+                const int r = e / (TILE_COLS * 3), q = e % (TILE_COLS * 3), c = q / 3;
+                if (c0 + c < wl && !s_skip[c]) O.rgb[((size_t)(y0 + r) * wl + c0) * 3 + q] = s_rgb[r][q];
             }
         }
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long st = 0ull, ht = 0ull;
+        for (int i = 0; i < TILE_COLS; ++i) st += s_cnt[i], ht += s_hits[i];
+        if (st) atomicAdd(B.counters + CNT_RAY_STEPS, st);
+        if (ht) atomicAdd(B.counters + CNT_TRACE_POINTS, ht), atomicAdd(B.counters + CNT_PIXELS_HIT, ht);
     }
 }
 

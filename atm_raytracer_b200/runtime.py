@@ -55,6 +55,8 @@ def _load():
         "atmrt_get_terrain_profile": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, P(C.c_int)]),
         "atmrt_get_path": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, P(C.c_int)]),
         "atmrt_atmosphere_probe": (C.c_int, [vp, vp, C.c_int, vp, vp, vp]),
+        "atmrt_ray_paths": (C.c_int, [vp, C.c_double, vp, C.c_int, C.c_double, C.c_int, vp, vp]),
+        "atmrt_elev_profile": (C.c_int, [vp, C.c_double, vp, C.c_int, vp, vp, vp]),
         "atmrt_refraction_probe": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, P(C.c_int)]),
         "atmrt_set_path_mode": (C.c_int, [vp, C.c_int]),
         "atmrt_refraction_table": (C.c_int, [vp, C.c_double, vp, C.c_int, P(C.c_int), P(C.c_int), P(C.c_double), P(C.c_double), P(C.c_int), P(C.c_int)]),
@@ -255,6 +257,20 @@ class Context:
         dist, elev, plen = np.empty(m), np.empty(m), np.empty(m)
         self._check(lib.atmrt_get_path(self._h, y, m, _ptr(dist), _ptr(elev), _ptr(plen), C.byref(n)))
         return {"dist": dist, "elev": elev, "path_length": plen}
+
+    def ray_paths(self, start_h, angles_deg, ray_step, nsteps):
+        """The stepper behind `output-ray-paths`: (x[nsteps], h[n_angles][nsteps])."""
+        a = np.ascontiguousarray(angles_deg, dtype=np.float64)
+        x, h = np.empty(nsteps), np.empty((a.size, nsteps))
+        self._check(lib.atmrt_ray_paths(self._h, float(start_h), _ptr(a), a.size, float(ray_step), int(nsteps), _ptr(x), _ptr(h)))
+        return x, h
+
+    def elev_profile(self, azimuth, dist):
+        """The sampler behind `output-elev-profile`: (lat, lon, elev) at the given distances along `azimuth`."""
+        d = np.ascontiguousarray(dist, dtype=np.float64)
+        lat, lon, elev = np.empty_like(d), np.empty_like(d), np.empty_like(d)
+        self._check(lib.atmrt_elev_profile(self._h, float(azimuth), _ptr(d), d.size, _ptr(lat), _ptr(lon), _ptr(elev)))
+        return lat, lon, elev
 
     def atmosphere_probe(self, h):
         h = np.ascontiguousarray(h, dtype=np.float64)

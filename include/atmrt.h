@@ -255,6 +255,17 @@ int atmrt_get_terrain_profile(atmrt_ctx* ctx, int x, int capacity, double* lat, 
 /* Stage-B cache of row y (gen_path_cache, utils.rs:136-174). */
 int atmrt_get_path(atmrt_ctx* ctx, int y, int capacity, double* dist, double* elev,
                    double* path_length, int* n);
+/* The stepper behind `output-ray-paths` (ray_path.rs:65-91): n rays cast from altitude start_h at the given elevation
+ * angles (degrees), ALWAYS refracted (cast_ray_stepper(h, ang, false)) on the shape the configured earth model lowers
+ * to (to_shape), step size ray_step, nsteps calls of next(): x[nsteps] (RayState::x, the same for every ray) and
+ * h[n][nsteps] (RayState::h). The ray-path stage's own step (g(h) table, pieces, libm), or with atmrt_set_path_mode(1)
+ * PathStepper::next op for op. Host buffers; needs set_params only. */
+int atmrt_ray_paths(atmrt_ctx* ctx, double start_h, const double* angles_deg, int n, double ray_step, int nsteps,
+                    double* x, double* h);
+/* The sampler behind `output-elev-profile` (elev_profile.rs:43-60): coords_at_dist_calc((lat0, lon0), azimuth)
+ * .coords_at_dist(dist[i]) and Terrain::get_elev(..).unwrap_or(0.0). lat / lon may be NULL. */
+int atmrt_elev_profile(atmrt_ctx* ctx, double azimuth, const double* dist, int n, double* lat, double* lon,
+                       double* elev);
 /* Atmosphere::temperature / pressure and Environment::n at n altitudes, on the device. */
 int atmrt_atmosphere_probe(atmrt_ctx* ctx, const double* h, int n, double* temperature,
                            double* pressure, double* refractive_index);

@@ -249,6 +249,38 @@ def pixel_angles(params):
     return el, az
 
 
+def _read_text(fn, *args):
+    import tempfile
+
+    with tempfile.NamedTemporaryFile(suffix=".tsv") as tmp:
+        rc = fn(*args, os.fsencode(tmp.name))
+        if rc != 0:
+            raise RuntimeError(f"oracle dumper failed: {rc}")
+        return open(tmp.name, "rb").read().decode()
+
+
+def output_ray_paths(params, height=2.0, min_ang=-1.0, max_ang=1.0, step=0.1, ray_step=50.0, cutoff=10000.0, output_step=50.0):
+    """The stdout of `output-ray-paths` (ray_path.rs) for a Params."""
+    L = lib()
+    L.oracle_output_ray_paths.argtypes = [C.c_void_p] + [C.c_double] * 7 + [C.c_char_p]
+    return _read_text(L.oracle_output_ray_paths, C.byref(params), height, min_ang, max_ang, step, ray_step, cutoff, output_step)
+
+
+def output_elev_profile(params, tiles, azim=0.0, step=50.0, cutoff=10000.0):
+    """The stdout of `output-elev-profile` (elev_profile.rs), Terrain::from_folder's line included."""
+    L = lib()
+    descs, ptrs, n = _tiles(tiles)
+    L.oracle_output_elev_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_char_p]
+    return _read_text(L.oracle_output_elev_profile, C.byref(params), descs, n, ptrs, azim, step, cutoff)
+
+
+def output_atm(adef, min_alt=0.0, max_alt=1000.0, step=0.2, celsius=False):
+    """The stdout of `output-atm` (atm_printer.rs)."""
+    L = lib()
+    L.oracle_output_atm.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_char_p]
+    return _read_text(L.oracle_output_atm, C.byref(adef), min_alt, max_alt, step, int(bool(celsius)))
+
+
 def check_collision(obj, texture, obj_alt_abs, earth_model, radius, p1, p2):
     p1 = np.ascontiguousarray(p1, np.float64)
     p2 = np.ascontiguousarray(p2, np.float64)

@@ -37,6 +37,7 @@
 #endif
 
 #include "../include/atmrt.h"
+#include "../include/atmrt_fmt.h"
 
 namespace {
 
@@ -1462,6 +1463,81 @@ int oracle_pixel_angles(const atmrt_params* p, double* elevation_angle, double* 
             if (azimuth) azimuth[(size_t)y * wl + c] = az;
         }
     }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The three text dumpers, restated (the reference's only text windows onto the external crates: a real binary's
+// stdout can be diffed against these files). `{}` of an f64 is atmrt_fmt_f64 (include/atmrt_fmt.h). Each writes the
+// text the reference prints to stdout into `path` and returns 0.
+// ---------------------------------------------------------------------------------------------
+// ray_path.rs:6-106 (`output-ray-paths`): rays are always refracted (cast_ray_stepper(height, ang, false), :71).
+int oracle_output_ray_paths(const atmrt_params* p, double height, double min_ang, double max_ang, double step, double ray_step, double cutoff,
+                            double output_step, const char* path) {
+    if (!(step > 0.0)) return ATMRT_ERR_INVALID;  // assert!(step > 0.0), :53
+    Environment env{};
+    if (!atmosphere_from_def(p->atmosphere, &env.atm)) return ATMRT_ERR_INVALID;
+    const EarthModel model{p->earth_model, p->radius, p->ellipsoid_b};
+    env.flat = shape_flat(model), env.radius = shape_radius(model), env.wavelength = p->wavelength;
+    std::vector<std::vector<double>> rays;
+    std::vector<double> xs{0.0};
+    for (double ang = min_ang; ang <= max_ang; ang += step) {  // :65-94
+        Stepper stepper(&env, height, to_radians(ang), false);
+        stepper.set_step_size(ray_step);
+        std::vector<double> ray{height};
+        for (;;) {
+            const RayState st = stepper.next();
+            if (std::floor((st.x - ray_step / 2.0) / output_step) != std::floor((st.x + ray_step / 2.0) / output_step)) {
+                if (ang == min_ang) xs.push_back(st.x);
+                ray.push_back(st.h);
+            }
+            if (st.x >= cutoff) break;
+        }
+        rays.push_back(ray);
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) return ATMRT_ERR_IO;
+    for (size_t i = 0; i < xs.size(); ++i) {  // :97-103
+        fprintf(f, "%s\t", atmrt_fmt_f64(xs[i]).c_str());
+        for (const auto& ray : rays) fprintf(f, "%s\t", atmrt_fmt_f64(ray[i]).c_str());
+        fprintf(f, "\n");
+    }
+    fclose(f);
+    return 0;
+}
+
+// elev_profile.rs:9-67 (`output-elev-profile`); Terrain::from_folder's "Detected N terrain files" line (terrain/mod.rs:80)
+// goes to the same stdout first.
+int oracle_output_elev_profile(const atmrt_params* p, const atmrt_tile_desc* tiles, int ntiles, const int16_t* const* posts, double azim,
+                               double step, double cutoff, const char* path) {
+    if (!(step > 0.0)) return ATMRT_ERR_INVALID;
+    const Terrain terrain = make_terrain(tiles, ntiles, posts);
+    const EarthModel model{p->earth_model, p->radius, p->ellipsoid_b};
+    const DirCalc calc = coords_at_dist_calc(model, p->latitude, p->longitude, azim);
+    FILE* f = fopen(path, "wb");
+    if (!f) return ATMRT_ERR_IO;
+    fprintf(f, "Detected %d terrain files\n", ntiles);
+    for (double x = 0.0; x <= cutoff; x += step) {  // :53-64
+        double lat, lon, elev = 0.0;
+        coords_at_dist(calc, x, &lat, &lon);
+        if (!terrain_get_elev(terrain, lat, lon, &elev)) elev = 0.0;
+        fprintf(f, "%s\t%s\n", atmrt_fmt_f64(x).c_str(), atmrt_fmt_f64(elev).c_str());
+    }
+    fclose(f);
+    return 0;
+}
+
+// atm_printer.rs:6-49 (`output-atm`)
+int oracle_output_atm(const atmrt_atmosphere_def* def, double min_alt, double max_alt, double step, int celsius, const char* path) {
+    if (!(step > 0.0)) return ATMRT_ERR_INVALID;
+    Atmosphere atm;
+    if (!atmosphere_from_def(*def, &atm)) return ATMRT_ERR_INVALID;
+    FILE* f = fopen(path, "wb");
+    if (!f) return ATMRT_ERR_IO;
+    for (double alt = min_alt; alt <= max_alt; alt += step)  // :35-46
+        fprintf(f, "%s %s %s %s\n", atmrt_fmt_f64(alt).c_str(), atmrt_fmt_f64(atm_temperature(atm, alt) - (celsius ? 273.15 : 0.0)).c_str(),
+                atmrt_fmt_f64(atm_pressure(atm, alt)).c_str(), atmrt_fmt_f64(atm.humidity).c_str());
+    fclose(f);
     return 0;
 }
 

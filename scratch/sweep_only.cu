@@ -1,5 +1,5 @@
 // compile-only probe: ptxas -v of the fused stage-C kernel without the rest of the library
 #include "../atm_raytracer_b200/csrc/kernels.cuh"
 namespace atmrt {
-template __global__ void k_sweep_fused<0>(const __grid_constant__ DevScene, DevBuffers, MarchOut, FusedOut, int, int);
+template __global__ void k_sweep_bits<10>(const __grid_constant__ DevScene, DevBuffers, SweepLists, int, int);
 }
