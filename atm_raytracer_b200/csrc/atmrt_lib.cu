@@ -8,8 +8,11 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <mutex>
+#include <set>
 #include <string>
 #include <functional>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -21,6 +24,8 @@ static_assert(sizeof(DevScene) < 4000, "DevScene must fit the kernel parameter s
 namespace {
 
 std::string g_create_error;
+std::mutex g_pageable_mutex;
+std::set<void*> g_pageable;  // atmrt_host_alloc blocks that are ordinary (not page-locked) memory
 
 struct DevBuf {
     void* p = nullptr;
@@ -85,9 +90,9 @@ struct atmrt_ctx {
     DevBuf d_sweep_flags, d_sweep_col, d_sweep_hit;
     DevBuf d_anchor;  // walk anchors of stage A, [wl][n_anchor]
     bool walk_anchors = true;
+    DevBuf d_rec_ab, d_rec_em, d_rec_n;  // stage B: the steps of the chain (k_ray_chain -> k_ray_elements)
     DevBuf d_list, d_count, d_normals;  // stage C: the distinct hit samples of every column and their normals
-    bool stage_c_legacy = false;
-    int sweep_min_blocks = 10;
+    int sweep_bands = 0;                // 0: chosen per render (launch_render)
     DevBuf d_stage;  // raw posts of pack_terrain on their way to the tiled layout
     bool sweep_enabled = true;
     DevBuf d_dist, d_colcalc, d_tlat, d_tlon, d_telev, d_tclose;
@@ -727,20 +732,51 @@ struct RenderTargets {
     unsigned char* host_rgb = nullptr;
     atmrt_meta* host_meta = nullptr;
     int* host_steps = nullptr;
+    // the host image may be wider than this context's column block (a shard of a multi-GPU frame written in place):
+    // `host_width` pixels per host row (0: the block's own width), the block starts at column `host_x0` of it
+    int host_width = 0, host_x0 = 0;
     bool host_copied = false;  // out: the bands were copied (valid unless a device-side fallback ran afterwards)
 };
 
-// The ray-path stage with macro steps: as many simulation steps per macro step as keep it within
-// MACRO_MAX_METRES (16 at 25 or 50 m; fewer for coarser simulation steps, none above 400 m).
+// Rows [r0, r1) of the column block from the device planes to the host image (row-major; the block may be a
+// sub-rectangle of a wider host image): strided 2-D copies, asynchronous on `st` when the host memory is pinned.
+int copy_rows_to_host(atmrt_ctx* ctx, const RenderTargets& rt, int wl, int r0, int r1, cudaStream_t st) {
+    const size_t hw = rt.host_width > 0 ? (size_t)rt.host_width : (size_t)wl;
+    const size_t src = (size_t)r0 * wl, dst = (size_t)r0 * hw + (size_t)rt.host_x0;
+    const size_t rows = (size_t)(r1 - r0);
+    if (rt.host_rgb)
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(rt.host_rgb + dst * 3, hw * 3, rt.rgb + src * 3, (size_t)wl * 3, (size_t)wl * 3, rows, cudaMemcpyDeviceToHost, st));
+    if (rt.host_meta)
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(rt.host_meta + dst, hw * sizeof(atmrt_meta), rt.meta + src, (size_t)wl * sizeof(atmrt_meta), (size_t)wl * sizeof(atmrt_meta),
+                                        rows, cudaMemcpyDeviceToHost, st));
+    if (rt.host_steps)
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(rt.host_steps + dst, hw * sizeof(int), rt.steps + src, (size_t)wl * sizeof(int), (size_t)wl * sizeof(int), rows,
+                                        cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+// The ray-path stage with macro steps, as chain + elements (kernels.cuh): as many simulation steps per macro step as keep
+// it within MACRO_MAX_METRES (16 at 25 or 50 m; fewer for coarser simulation steps, none above 400 m).
 template <bool FLAT>
-void launch_macro_paths(atmrt_ctx* ctx, const DevScene& S, const DevBuffers& B, int h) {
-    const int warps = MACRO_THREADS / 32;
-    auto blocks = [&](int m) { return (h + warps * (32 / m) - 1) / (warps * (32 / m)); };
-    if (16.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 16><<<blocks(16), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
-    else if (8.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 8><<<blocks(8), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
-    else if (4.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 4><<<blocks(4), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
-    else if (2.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 2><<<blocks(2), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
-    else k_ray_paths<FLAT, false><<<(h + 31) / 32, 32, 0, ctx->s_b>>>(S, B);
+int launch_macro_paths(atmrt_ctx* ctx, const DevScene& S, const DevBuffers& B, int h) {
+    int macro_steps = 0;
+    for (int m : {16, 8, 4, 2})
+        if (macro_steps == 0 && (double)m * S.step <= MACRO_MAX_METRES) macro_steps = m;
+    if (macro_steps == 0) {
+        k_ray_paths<FLAT, false><<<(h + 31) / 32, 32, 0, ctx->s_b>>>(S, B);
+        return 0;
+    }
+    PathRecords R{};
+    R.cap = S.n_t + 1;
+    int rc = ensure(ctx, ctx->d_rec_ab, sizeof(double2) * (size_t)h * R.cap);
+    if (!rc) rc = ensure(ctx, ctx->d_rec_em, sizeof(int2) * (size_t)h * R.cap);
+    if (!rc) rc = ensure(ctx, ctx->d_rec_n, sizeof(int) * (size_t)h);
+    if (rc) return rc;
+    R.ab = (double2*)ctx->d_rec_ab.p, R.em = (int2*)ctx->d_rec_em.p, R.n = (int*)ctx->d_rec_n.p;
+    k_ray_chain<FLAT><<<(h + CHAIN_THREADS - 1) / CHAIN_THREADS, CHAIN_THREADS, 0, ctx->s_b>>>(S, B, R, macro_steps);
+    k_ray_elements<FLAT><<<h, ELEM_THREADS, 0, ctx->s_b>>>(S, B, R);
+    ctx->launches++;
+    return 0;
 }
 
 // Launch the whole render on (s_a || s_b) -> main. Asynchronous.
@@ -820,11 +856,11 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         } else if (S.flat) {
             if (ctx->path_mode == 1) k_ray_paths<true, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
             else if (ctx->path_mode == 2) k_ray_paths<true, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
-            else launch_macro_paths<true>(ctx, S, B, h);
+            else if ((rc = launch_macro_paths<true>(ctx, S, B, h))) return rc;
         } else {
             if (ctx->path_mode == 1) k_ray_paths<false, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
             else if (ctx->path_mode == 2) k_ray_paths<false, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
-            else launch_macro_paths<false>(ctx, S, B, h);
+            else if ((rc = launch_macro_paths<false>(ctx, S, B, h))) return rc;
         }
         ctx->launches++;
     }
@@ -873,22 +909,28 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->c0, main));
     MarchOut O{rt.rgb, rt.meta, rt.steps, rt.points, rt.counts, rt.max_points};
     const dim3 grid((h + MARCH_THREADS - 1) / MARCH_THREADS, wl);
-    if (sweep && !ctx->stage_c_legacy) {
+    if (sweep) {
         // Bit-mask sweep -> normals of the distinct hit samples -> row-major shading (kernels.cuh).
+        // Row bands: one walk per column unless the column block is so narrow that its walks could not fill a fraction of
+        // the machine. (Measured at config 5: a band costs the scan of one whole row, +0.9 ms per extra band on the full
+        // panorama and +0.1 ms on a 2048-column block of an 8-GPU frame; bands pay below ~1000 columns.)
         SweepLists L{};
-        L.cap = std::min(2 * S.h_pad, S.n_pad);
-        if ((rc = ensure(ctx, ctx->d_list, sizeof(int) * (size_t)wl * L.cap))) return rc;
-        if ((rc = ensure(ctx, ctx->d_count, sizeof(int) * (size_t)wl))) return rc;
-        if ((rc = ensure(ctx, ctx->d_normals, sizeof(double) * 3 * (size_t)wl * L.cap))) return rc;
+        int bands = ctx->sweep_bands > 0 ? ctx->sweep_bands : (int)(((long long)ctx->num_sms * 8) / std::max(wl, 1));
+        bands = std::max(1, std::min(bands, std::max(1, h / 128)));
+        L.band_rows = ((h + bands - 1) / bands + 31) / 32 * 32;
+        L.bands = (h + L.band_rows - 1) / L.band_rows;
+        L.cap = std::min(2 * L.band_rows + 2, S.n_pad);
+        const size_t segs = (size_t)wl * L.bands;
+        if ((rc = ensure(ctx, ctx->d_list, sizeof(int) * segs * L.cap))) return rc;
+        if ((rc = ensure(ctx, ctx->d_count, sizeof(int) * segs))) return rc;
+        if ((rc = ensure(ctx, ctx->d_normals, sizeof(double) * 3 * segs * L.cap))) return rc;
         L.list = (int*)ctx->d_list.p, L.count = (int*)ctx->d_count.p, L.normals = (double*)ctx->d_normals.p;
-        const int sgrid = (wl + BITS_WARPS - 1) / BITS_WARPS;
-        if (ctx->sweep_min_blocks == 16) k_sweep_bits<16><<<sgrid, 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl);
-        else if (ctx->sweep_min_blocks == 12) k_sweep_bits<12><<<sgrid, 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl);
-        else k_sweep_bits<10><<<sgrid, 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl);
-        // enough blocks per column that a narrow column block (one of eight GPUs) still fills the machine
-        const int parts = std::max(1, std::min(8, (ctx->num_sms * 16 + wl - 1) / wl));
-        if (S.earth.walker == WALK_SPHERICAL) k_hit_normals<WALK_SPHERICAL><<<wl * parts, 128, 0, main>>>(S, B, L, parts);
-        else k_hit_normals<-1><<<wl * parts, 128, 0, main>>>(S, B, L, parts);
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_sweep_col.p, 0, (size_t)wl, main));
+        k_sweep_bits<<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, L.bands), 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl);
+        // enough blocks per (column, band) that a narrow column block still fills the machine
+        const int parts = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)ctx->num_sms * 16 + segs - 1) / segs));
+        if (S.earth.walker == WALK_SPHERICAL) k_hit_normals<WALK_SPHERICAL><<<(unsigned)(segs * parts), 128, 0, main>>>(S, B, L, parts);
+        else k_hit_normals<-1><<<(unsigned)(segs * parts), 128, 0, main>>>(S, B, L, parts);
         ctx->launches += 2;
         const bool to_host = rt.host_rgb || rt.host_meta || rt.host_steps;
         const int nbands = to_host && h >= 256 ? SHADE_BANDS : 1;
@@ -899,42 +941,9 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
             k_shade_tiles<<<dim3((r1 - r0 + 31) / 32, (wl + TILE_COLS - 1) / TILE_COLS), 32 * TILE_COLS, 0, main>>>(S, B, O, L, r0);
             ctx->launches++;
             if (to_host) {  // the finished band goes to the host on the (idle) stage-A stream while the next band is shaded
-                const size_t p0 = (size_t)r0 * wl, np = (size_t)(r1 - r0) * wl;
                 CUDA_TRY(ctx, cudaEventRecord(ctx->ev_band[bi], main));
                 CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_a, ctx->ev_band[bi], 0));
-                if (rt.host_rgb) CUDA_TRY(ctx, cudaMemcpyAsync(rt.host_rgb + p0 * 3, rt.rgb + p0 * 3, np * 3, cudaMemcpyDeviceToHost, ctx->s_a));
-                if (rt.host_meta) CUDA_TRY(ctx, cudaMemcpyAsync(rt.host_meta + p0, rt.meta + p0, np * sizeof(atmrt_meta), cudaMemcpyDeviceToHost, ctx->s_a));
-                if (rt.host_steps) CUDA_TRY(ctx, cudaMemcpyAsync(rt.host_steps + p0, rt.steps + p0, np * sizeof(int), cudaMemcpyDeviceToHost, ctx->s_a));
-            }
-        }
-        if (to_host) {
-            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->s_a));
-            CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_a, 0));
-            rt.host_copied = true;
-        }
-    } else if (sweep) {
-        // (Splitting the image into column chunks so that the shading of one chunk overlaps the sweep of the
-        // next was measured and is slower: 8.9 ms -> 9.8 / 10.5 ms with 2 / 4 chunks at c5 -- the sweep's long
-        // columns leave each smaller grid with a longer tail.)
-        k_sweep<<<(wl + SWEEP_THREADS / 32 - 1) / (SWEEP_THREADS / 32), SWEEP_THREADS, 0, main>>>(S, B, 0, wl);
-        ctx->launches++;
-        const bool to_host = rt.host_rgb || rt.host_meta || rt.host_steps;
-        const int nbands = to_host && h >= 256 ? SHADE_BANDS : 1;
-        const int band_rows = ((h + nbands - 1) / nbands + 31) / 32 * 32;
-        int bi = 0;
-        for (int r0 = 0; r0 < h; r0 += band_rows, ++bi) {
-            const int r1 = std::min(h, r0 + band_rows);
-            const dim3 sgrid((r1 - r0 + 31) / 32, (wl + SHADE_COLS - 1) / SHADE_COLS);
-            if (S.earth.walker == WALK_SPHERICAL) k_sweep_shade<WALK_SPHERICAL><<<sgrid, 32 * SHADE_COLS, 0, main>>>(S, B, O, 0, r0);
-            else k_sweep_shade<-1><<<sgrid, 32 * SHADE_COLS, 0, main>>>(S, B, O, 0, r0);
-            ctx->launches++;
-            if (to_host) {  // the finished band goes to the host on the (idle) stage-A stream while the next band is shaded
-                const size_t p0 = (size_t)r0 * wl, np = (size_t)(r1 - r0) * wl;
-                CUDA_TRY(ctx, cudaEventRecord(ctx->ev_band[bi], main));
-                CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_a, ctx->ev_band[bi], 0));
-                if (rt.host_rgb) CUDA_TRY(ctx, cudaMemcpyAsync(rt.host_rgb + p0 * 3, rt.rgb + p0 * 3, np * 3, cudaMemcpyDeviceToHost, ctx->s_a));
-                if (rt.host_meta) CUDA_TRY(ctx, cudaMemcpyAsync(rt.host_meta + p0, rt.meta + p0, np * sizeof(atmrt_meta), cudaMemcpyDeviceToHost, ctx->s_a));
-                if (rt.host_steps) CUDA_TRY(ctx, cudaMemcpyAsync(rt.host_steps + p0, rt.steps + p0, np * sizeof(int), cudaMemcpyDeviceToHost, ctx->s_a));
+                if ((rc = copy_rows_to_host(ctx, rt, wl, r0, r1, ctx->s_a))) return rc;
             }
         }
         if (to_host) {
@@ -1005,6 +1014,37 @@ int collect_stats(atmrt_ctx* ctx, atmrt_stats* stats) {
 
 }  // namespace
 
+// ---- multi-GPU group (atmrt_group_*): state and helpers ------------------------------------------
+struct atmrt_group {
+    std::vector<atmrt_ctx*> ctx;
+    std::string err;
+    atmrt_params params{};
+    bool has_params = false;
+    std::vector<void*> packed;  // per GPU: the packed terrain (owned)
+    size_t packed_cap = 0;
+    std::vector<cudaEvent_t> ev_slice;  // per GPU: its slice is retiled
+};
+
+static int gfail(atmrt_group* g, int code, const std::string& msg) {
+    if (g) g->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+// run fn(i) for every context on its own host thread; the first failure wins
+template <class F>
+static int group_parallel(atmrt_group* g, F fn) {
+    const int n = (int)g->ctx.size();
+    std::vector<int> rc(n, 0);
+    std::vector<std::thread> th;
+    for (int i = 1; i < n; ++i) th.emplace_back([&, i] { rc[i] = fn(i); });
+    rc[0] = fn(0);
+    for (auto& t : th) t.join();
+    for (int i = 0; i < n; ++i)
+        if (rc[i]) return gfail(g, rc[i], "GPU " + std::to_string(g->ctx[i]->device) + ": " + g->ctx[i]->err);
+    return 0;
+}
+
 // =============================================================================================
 // C ABI
 // =============================================================================================
@@ -1059,9 +1099,6 @@ int atmrt_create(int device, atmrt_ctx** out) {
         delete ctx;
         return fail(nullptr, ATMRT_ERR_CUDA, "stream/event creation failed");
     }
-    if (const char* e = getenv("ATMRT_WALK_ANCHORS")) ctx->walk_anchors = atoi(e) != 0;
-    if (const char* e = getenv("ATMRT_SWEEP_MB")) ctx->sweep_min_blocks = atoi(e);
-    if (const char* e = getenv("ATMRT_STAGE_C")) ctx->stage_c_legacy = std::string(e) == "legacy";
     *out = ctx;
     return 0;
 }
@@ -1073,7 +1110,7 @@ void atmrt_destroy(atmrt_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_objects_in, &ctx->d_objects, &ctx->d_dist, &ctx->d_colcalc, &ctx->d_tlat, &ctx->d_tlon, &ctx->d_telev,
                       &ctx->d_tclose, &ctx->d_pdist, &ctx->d_pelev, &ctx->d_plen, &ctx->d_pn,
                       &ctx->d_tmin1, &ctx->d_tmax1, &ctx->d_tmin2, &ctx->d_tmax2, &ctx->d_tmin3, &ctx->d_tmax3, &ctx->d_close1, &ctx->d_close2, &ctx->d_close3, &ctx->d_rmin1, &ctx->d_rmin3, &ctx->d_rmax3,
-                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_sweep_flags, &ctx->d_sweep_col, &ctx->d_sweep_hit, &ctx->d_list, &ctx->d_count, &ctx->d_normals, &ctx->d_anchor, &ctx->d_stage, &ctx->d_atm_aux, &ctx->d_rgb, &ctx->d_meta,
+                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_sweep_flags, &ctx->d_sweep_col, &ctx->d_sweep_hit, &ctx->d_list, &ctx->d_count, &ctx->d_normals, &ctx->d_anchor, &ctx->d_rec_ab, &ctx->d_rec_em, &ctx->d_rec_n, &ctx->d_stage, &ctx->d_atm_aux, &ctx->d_rgb, &ctx->d_meta,
                       &ctx->d_steps, &ctx->d_points, &ctx->d_counts, &ctx->d_probe_a, &ctx->d_probe_b, &ctx->d_probe_c, &ctx->d_probe_d};
     for (DevBuf* b : bufs) release(*b);
     for (DevBuf& b : ctx->textures) release(b);
@@ -1257,6 +1294,12 @@ int atmrt_set_march_mode(atmrt_ctx* ctx, int mode) {
     return 0;
 }
 
+int atmrt_set_sweep_bands(atmrt_ctx* ctx, int bands) {
+    if (!ctx || bands < 0) return fail(ctx, ATMRT_ERR_INVALID, "sweep bands must be >= 0 (0: automatic)");
+    ctx->sweep_bands = bands;
+    return 0;
+}
+
 int atmrt_set_path_mode(atmrt_ctx* ctx, int mode) {
     if (!ctx) return ATMRT_ERR_INVALID;
     ctx->path_mode = mode == 1 || mode == 2 ? mode : 0;
@@ -1280,13 +1323,15 @@ int atmrt_render_device(atmrt_ctx* ctx, void* rgb_dev, void* meta_dev, void* ste
     return 0;
 }
 
-int atmrt_render(atmrt_ctx* ctx, uint8_t* rgb, atmrt_meta* meta, int32_t* steps, atmrt_stats* stats) {
-    if (!ctx) return ATMRT_ERR_INVALID;
+// Render this context's column block into host memory; the block may be a sub-rectangle of a wider host image
+// (host_width pixels per row, starting at column host_x0). Synchronous.
+static int render_to_host(atmrt_ctx* ctx, uint8_t* rgb, atmrt_meta* meta, int32_t* steps, int host_width, int host_x0, atmrt_stats* stats) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     int rc = prepare_render(ctx);
     if (rc) return rc;
     const DevScene& S = ctx->scene;
-    const size_t npix = (size_t)(S.x1 - S.x0) * S.height;
+    const int wl = S.x1 - S.x0;
+    const size_t npix = (size_t)wl * S.height;
     if (rgb && (rc = ensure(ctx, ctx->d_rgb, npix * 3))) return rc;
     if (meta && (rc = ensure(ctx, ctx->d_meta, npix * sizeof(atmrt_meta)))) return rc;
     if (steps && (rc = ensure(ctx, ctx->d_steps, npix * sizeof(int)))) return rc;
@@ -1295,6 +1340,7 @@ int atmrt_render(atmrt_ctx* ctx, uint8_t* rgb, atmrt_meta* meta, int32_t* steps,
     rt.meta = meta ? (atmrt_meta*)ctx->d_meta.p : nullptr;
     rt.steps = steps ? (int*)ctx->d_steps.p : nullptr;
     rt.host_rgb = rgb, rt.host_meta = meta, rt.host_steps = steps;
+    rt.host_width = host_width, rt.host_x0 = host_x0;
     cudaStream_t main = ctx->s_main;
     rc = launch_render(ctx, rt, main);
     if (rc) return rc;
@@ -1306,12 +1352,15 @@ int atmrt_render(atmrt_ctx* ctx, uint8_t* rgb, atmrt_meta* meta, int32_t* steps,
         copy_all = flags[0] != 0 || flags[1] != 0;
     }
     if (copy_all) {
-        if (rgb) CUDA_TRY(ctx, cudaMemcpyAsync(rgb, ctx->d_rgb.p, npix * 3, cudaMemcpyDeviceToHost, main));
-        if (meta) CUDA_TRY(ctx, cudaMemcpyAsync(meta, ctx->d_meta.p, npix * sizeof(atmrt_meta), cudaMemcpyDeviceToHost, main));
-        if (steps) CUDA_TRY(ctx, cudaMemcpyAsync(steps, ctx->d_steps.p, npix * sizeof(int), cudaMemcpyDeviceToHost, main));
+        if ((rc = copy_rows_to_host(ctx, rt, wl, 0, S.height, main))) return rc;
         CUDA_TRY(ctx, cudaStreamSynchronize(main));
     }
     return collect_stats(ctx, stats);
+}
+
+int atmrt_render(atmrt_ctx* ctx, uint8_t* rgb, atmrt_meta* meta, int32_t* steps, atmrt_stats* stats) {
+    if (!ctx) return ATMRT_ERR_INVALID;
+    return render_to_host(ctx, rgb, meta, steps, 0, 0, stats);
 }
 
 int atmrt_render_trace(atmrt_ctx* ctx, atmrt_trace_point* points, int32_t* counts, int max_points) {
@@ -1627,6 +1676,206 @@ int atmrt_fp64_peak(atmrt_ctx* ctx, double* gflops, double* dadd_ginstr) {
     if (gflops) *gflops = best[0] * 2.0;
     if (dadd_ginstr) *dadd_ginstr = best[1];
     return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU: one panorama over the GPUs of a box, in ONE process. The panorama shards by contiguous column blocks
+// (pixels are independent: fast.rs:52-92), one context per GPU, one host thread per context. Terrain: every GPU
+// uploads and retiles a contiguous SLICE of the tiles over its own PCIe link and pulls the other slices from its peers
+// over NVLink (cudaMemcpyPeerAsync), so the host-to-device traffic of the frame is one copy of the terrain, not one per
+// GPU. Image: every GPU copies its finished row bands straight into its columns of the host's row-major image (strided
+// 2-D copies over its own PCIe link); nothing funnels through one GPU. No collective in the march.
+// ---------------------------------------------------------------------------------------------
+int atmrt_group_create(const int* devices, int n, atmrt_group** out) {
+    if (!out || n < 1 || n > 64) return gfail(nullptr, ATMRT_ERR_INVALID, "group_create: bad argument");
+    *out = nullptr;
+    atmrt_group* g = new atmrt_group();
+    for (int i = 0; i < n; ++i) {
+        atmrt_ctx* c = nullptr;
+        const int rc = atmrt_create(devices ? devices[i] : i, &c);
+        if (rc) {
+            for (atmrt_ctx* x : g->ctx) atmrt_destroy(x);
+            delete g;
+            return rc;  // (g_create_error is set)
+        }
+        g->ctx.push_back(c);
+    }
+    // peer access both ways between every pair (NVLink / NVSwitch on a B200 box); without it the peer copies are staged
+    for (int i = 0; i < n; ++i) {
+        cudaSetDevice(g->ctx[i]->device);
+        for (int j = 0; j < n; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, g->ctx[i]->device, g->ctx[j]->device);
+            if (can) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(g->ctx[j]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            }
+        }
+        cudaEvent_t ev = nullptr;
+        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        g->ev_slice.push_back(ev);
+    }
+    g->packed.assign(n, nullptr);
+    *out = g;
+    return 0;
+}
+
+void atmrt_group_destroy(atmrt_group* g) {
+    if (!g) return;
+    for (size_t i = 0; i < g->ctx.size(); ++i) {
+        cudaSetDevice(g->ctx[i]->device);
+        cudaDeviceSynchronize();
+        if (g->packed[i]) cudaFree(g->packed[i]);
+        if (g->ev_slice[i]) cudaEventDestroy(g->ev_slice[i]);
+        atmrt_destroy(g->ctx[i]);
+    }
+    delete g;
+}
+
+const char* atmrt_group_last_error(const atmrt_group* g) { return g ? g->err.c_str() : g_create_error.c_str(); }
+int atmrt_group_size(const atmrt_group* g) { return g ? (int)g->ctx.size() : 0; }
+
+int atmrt_group_column_block(const atmrt_group* g, int width, int i, int* x0, int* x1) {
+    if (!g || i < 0 || i >= (int)g->ctx.size() || !x0 || !x1) return ATMRT_ERR_INVALID;
+    const long long n = (long long)g->ctx.size();
+    *x0 = (int)((long long)i * width / n), *x1 = (int)((long long)(i + 1) * width / n);
+    return 0;
+}
+
+int atmrt_group_set_terrain(atmrt_group* g, const atmrt_tile_desc* tiles, int ntiles, const int16_t* const* posts) {
+    if (!g || ntiles < 0 || (ntiles > 0 && (!tiles || !posts))) return gfail(g, ATMRT_ERR_INVALID, "group_set_terrain: bad argument");
+    const int n = (int)g->ctx.size();
+    TerrainLayout L;
+    int rc = make_layout(g->ctx[0], tiles, ntiles, &L);
+    if (rc) return gfail(g, rc, g->ctx[0]->err);
+    // contiguous slices of tiles per GPU: slice i = tiles [i T / n, (i + 1) T / n), one contiguous range of packed posts
+    auto first_tile = [&](int i) { return (int)((long long)i * ntiles / n); };
+    auto post_byte = [&](int t) { return L.off_posts + sizeof(int16_t) * (size_t)(t < ntiles ? L.tiles[t].post_offset : (long long)((L.total - L.off_posts) / sizeof(int16_t))); };
+    rc = group_parallel(g, [&](int i) -> int {
+        atmrt_ctx* ctx = g->ctx[i];
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        if (!g->packed[i] || g->packed_cap < L.total) {
+            if (g->packed[i]) CUDA_TRY(ctx, cudaFree(g->packed[i]));
+            g->packed[i] = nullptr;
+            CUDA_TRY(ctx, cudaMalloc(&g->packed[i], L.total));
+        }
+        char* base = (char*)g->packed[i];
+        cudaStream_t s = ctx->s_main;
+        const int t0 = first_tile(i), t1 = first_tile(i + 1);
+        if (ntiles > 0) CUDA_TRY(ctx, cudaMemcpyAsync(base + L.off_tiles, L.tiles.data(), sizeof(DevTile) * ntiles, cudaMemcpyHostToDevice, s));
+        if (!L.lookup.empty()) CUDA_TRY(ctx, cudaMemcpyAsync(base + L.off_lookup, L.lookup.data(), sizeof(int) * L.lookup.size(), cudaMemcpyHostToDevice, s));
+        std::vector<size_t> offs(t1 - t0 + 1, 0);
+        for (int t = t0; t < t1; ++t) offs[t - t0 + 1] = offs[t - t0] + align_up(sizeof(int16_t) * (size_t)tiles[t].nlon * tiles[t].nlat, 256);
+        int e = ensure(ctx, ctx->d_stage, std::max<size_t>(offs[t1 - t0], 256));
+        if (e) return e;
+        if (t1 > t0) CUDA_TRY(ctx, cudaMemsetAsync(base + post_byte(t0), 0, post_byte(t1) - post_byte(t0), s));  // the padding of the edge micro-tiles
+        for (int t = t0; t < t1; ++t)
+            CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->d_stage.p + offs[t - t0], posts[t], sizeof(int16_t) * (size_t)tiles[t].nlon * tiles[t].nlat, cudaMemcpyHostToDevice, s));
+        for (int t = t0; t < t1; ++t) {
+            const size_t np = (size_t)tiles[t].nlon * tiles[t].nlat;
+            k_retile<<<(unsigned)((np + 255) / 256), 256, 0, s>>>((const int16_t*)((const char*)ctx->d_stage.p + offs[t - t0]), (int16_t*)(base + L.off_posts), L.tiles[t]);
+        }
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaEventRecord(g->ev_slice[i], s));
+        return 0;
+    });
+    if (rc) return rc;
+    g->packed_cap = std::max(g->packed_cap, L.total);
+    // all-gather of the slices over the peer links: every GPU pulls the slices it does not own
+    rc = group_parallel(g, [&](int i) -> int {
+        atmrt_ctx* ctx = g->ctx[i];
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        cudaStream_t s = ctx->s_main;
+        for (int k = 1; k < n; ++k) {
+            const int o = (i + k) % n;  // staggered: no two GPUs start on the same peer
+            const size_t b0 = post_byte(first_tile(o)), b1 = post_byte(first_tile(o + 1));
+            if (b1 <= b0) continue;
+            CUDA_TRY(ctx, cudaStreamWaitEvent(s, g->ev_slice[o], 0));
+            CUDA_TRY(ctx, cudaMemcpyPeerAsync((char*)g->packed[i] + b0, ctx->device, (const char*)g->packed[o] + b0, g->ctx[o]->device, b1 - b0, s));
+        }
+        CUDA_TRY(ctx, cudaStreamSynchronize(s));
+        return atmrt_bind_terrain(ctx, tiles, ntiles, g->packed[i]);
+    });
+    return rc;
+}
+
+int atmrt_group_set_params(atmrt_group* g, const atmrt_params* params) {
+    if (!g || !params) return gfail(g, ATMRT_ERR_INVALID, "group_set_params: NULL argument");
+    if (params->width < (int)g->ctx.size()) return gfail(g, ATMRT_ERR_INVALID, "group_set_params: fewer columns than GPUs");
+    for (size_t i = 0; i < g->ctx.size(); ++i) {
+        atmrt_params p = *params;  // the group shards [0, width): x0 / x1 of the argument are ignored
+        atmrt_group_column_block(g, params->width, (int)i, &p.x0, &p.x1);
+        const int rc = atmrt_set_params(g->ctx[i], &p);
+        if (rc) return gfail(g, rc, g->ctx[i]->err);
+    }
+    g->params = *params;
+    g->has_params = true;
+    return 0;
+}
+
+int atmrt_group_set_objects(atmrt_group* g, const atmrt_object* objects, int nobjects, const uint8_t* const* rgba_textures) {
+    if (!g) return ATMRT_ERR_INVALID;
+    for (atmrt_ctx* c : g->ctx) {
+        const int rc = atmrt_set_objects(c, objects, nobjects, rgba_textures);
+        if (rc) return gfail(g, rc, c->err);
+    }
+    return 0;
+}
+
+int atmrt_group_render(atmrt_group* g, uint8_t* rgb, atmrt_meta* meta, int32_t* steps, atmrt_stats* stats) {
+    if (!g) return ATMRT_ERR_INVALID;
+    if (!g->has_params) return gfail(g, ATMRT_ERR_STATE, "group_render before group_set_params");
+    const int n = (int)g->ctx.size(), W = g->params.width;
+    std::vector<atmrt_stats> st(n);
+    const int rc = group_parallel(g, [&](int i) -> int {
+        int x0 = 0, x1 = 0;
+        atmrt_group_column_block(g, W, i, &x0, &x1);
+        return render_to_host(g->ctx[i], rgb, meta, steps, W, x0, &st[i]);
+    });
+    if (rc) return rc;
+    if (stats) {
+        *stats = st[0];
+        for (int i = 1; i < n; ++i) {
+            stats->ray_steps += st[i].ray_steps, stats->trace_points += st[i].trace_points, stats->pixels_hit += st[i].pixels_hit;
+            stats->step_overflows += st[i].step_overflows, stats->terrain_samples += st[i].terrain_samples;
+            stats->kernel_launches += st[i].kernel_launches;
+            stats->n_path_max = std::max(stats->n_path_max, st[i].n_path_max);
+            stats->ms_terrain = std::max(stats->ms_terrain, st[i].ms_terrain), stats->ms_paths = std::max(stats->ms_paths, st[i].ms_paths);
+            stats->ms_march = std::max(stats->ms_march, st[i].ms_march), stats->ms_total = std::max(stats->ms_total, st[i].ms_total);
+        }
+    }
+    return 0;
+}
+
+// Page-locked host memory visible to every GPU (cudaHostAllocPortable): the copies of a render into it are asynchronous
+// and run at the full rate of each GPU's own PCIe link.
+void* atmrt_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, std::max<size_t>(bytes, 1), cudaHostAllocPortable) == cudaSuccess) return p;
+    cudaGetLastError();
+    // no device (or no page-locked memory left): ordinary memory -- the copies then run staged and synchronous
+    p = malloc(std::max<size_t>(bytes, 1));
+    if (p) {
+        std::lock_guard<std::mutex> lock(g_pageable_mutex);
+        g_pageable.insert(p);
+    }
+    return p;
+}
+void atmrt_host_free(void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lock(g_pageable_mutex);
+        auto it = g_pageable.find(p);
+        if (it != g_pageable.end()) {
+            g_pageable.erase(it);
+            free(p);
+            return;
+        }
+    }
+    cudaFreeHost(p);
 }
 
 }  // extern "C"

@@ -300,6 +300,7 @@ struct Config {
     double simulation_step = 50.0;
     std::string file = "./output.png", file_metadata;
     int width = 640, height = 480;
+    int gpus = 1;  // --gpus N (not a flag of the reference): column blocks over N GPUs of this box
 };
 
 static atmrt_atmosphere_def us_76() {  // AtmosphereDef::us_76() (params.rs:453)
@@ -530,7 +531,7 @@ static Config read_config(int argc, const char* const* argv) {
         {"-g", "lon"}, {"--lon", "lon"}, {"-a", "alt"}, {"--alt", "alt"}, {"-e", "elev"}, {"--elev", "elev"}, {"-d", "dir"},
         {"--dir", "dir"}, {"-f", "fov"}, {"--fov", "fov"}, {"-i", "tilt"}, {"--tilt", "tilt"}, {"-m", "maxdist"},
         {"--maxdist", "maxdist"}, {"--step", "step"}, {"-R", "radius"}, {"--radius", "radius"}, {"--output", "output"},
-        {"--output-meta", "output-meta"}, {"-w", "width"}, {"--width", "width"}, {"-h", "height"}, {"--height", "height"}};
+        {"--output-meta", "output-meta"}, {"-w", "width"}, {"--width", "width"}, {"-h", "height"}, {"--height", "height"}, {"--gpus", "gpus"}};
     const std::map<std::string, std::string> flags = {{"--flat", "flat"}, {"-s", "straight"}, {"--straight", "straight"}};
     for (int i = 0; i < argc; ++i) {
         std::string a = argv[i];
@@ -568,6 +569,10 @@ static Config read_config(int argc, const char* const* argv) {
     if (flag.count("flat")) c.earth_model = ATMRT_EARTH_FLAT_DISTORTED;
     if (val.count("radius")) c.earth_model = ATMRT_EARTH_SPHERICAL, c.radius = d("radius") * 1e3;  // km (params.rs:764-767)
     if (flag.count("straight")) c.straight_rays = true;
+    if (val.count("gpus")) {
+        c.gpus = atoi(val["gpus"].c_str());
+        if (c.gpus < 1) throw std::runtime_error("--gpus must be at least 1");
+    }
     return c;
 }
 
@@ -621,7 +626,7 @@ static atmrt_params into_params(const Config& c) {
     return p;
 }
 
-static bool write_metadata(const std::string& path, const atmrt_params& p, const std::vector<atmrt_meta>& meta) {
+static bool write_metadata(const std::string& path, const atmrt_params& p, const atmrt_meta* meta, size_t npix) {
     // Own sidecar format (the reference's gzip(bincode(AllData)) depends on serde layouts of external
     // crates -- SURVEY section 8 f2): gzip of "ATMRTMETA1\n", i32 width, i32 height, then
     // width*height records of 4 little-endian f64 (lat, lon, elevation, distance; NaN = no hit).
@@ -630,8 +635,8 @@ static bool write_metadata(const std::string& path, const atmrt_params& p, const
     const char magic[] = "ATMRTMETA1\n";
     int32_t wh[2] = {p.width, p.height};
     bool ok = gzwrite(f, magic, sizeof(magic) - 1) > 0 && gzwrite(f, wh, sizeof wh) > 0;
-    const char* data = (const char*)meta.data();
-    size_t left = meta.size() * sizeof(atmrt_meta);
+    const char* data = (const char*)meta;
+    size_t left = npix * sizeof(atmrt_meta);
     while (ok && left > 0) {
         unsigned chunk = (unsigned)std::min<size_t>(left, 1u << 30);
         ok = gzwrite(f, data, chunk) == (int)chunk;
@@ -643,12 +648,15 @@ static bool write_metadata(const std::string& path, const atmrt_params& p, const
 // Terrain::from_folder (terrain/mod.rs:66-83): every entry of the folder must be a terrain file; decoded on the host.
 struct HostTerrain {
     std::vector<atmrt_tile_desc> descs;
-    std::vector<std::vector<int16_t>> posts;
-    std::vector<const int16_t*> ptrs() const {
-        std::vector<const int16_t*> p;
-        for (const auto& v : posts) p.push_back(v.data());
-        return p;
+    std::vector<int16_t*> posts;  // page-locked (atmrt_host_alloc): every GPU uploads its slice at the full rate of its link
+    HostTerrain() = default;
+    HostTerrain(const HostTerrain&) = delete;
+    HostTerrain& operator=(const HostTerrain&) = delete;
+    HostTerrain(HostTerrain&& o) noexcept : descs(std::move(o.descs)), posts(std::move(o.posts)) { o.posts.clear(); }
+    ~HostTerrain() {
+        for (int16_t* p : posts) atmrt_host_free(p);
     }
+    std::vector<const int16_t*> ptrs() const { return std::vector<const int16_t*>(posts.begin(), posts.end()); }
 };
 
 static HostTerrain load_terrain_folder(const std::string& folder) {
@@ -666,10 +674,12 @@ static HostTerrain load_terrain_folder(const std::string& folder) {
         std::string path = folder + "/" + n;
         atmrt_tile_desc d{};
         if (atmrt_host_read_dted(path.c_str(), &d, nullptr, 0) != 0) throw std::runtime_error("Could not buffer terrain file " + path);
-        std::vector<int16_t> buf((size_t)d.nlon * d.nlat);
-        if (atmrt_host_read_dted(path.c_str(), &d, buf.data(), buf.size()) != 0) throw std::runtime_error(g_error);
+        const size_t np = (size_t)d.nlon * d.nlat;
+        int16_t* buf = (int16_t*)atmrt_host_alloc(np * sizeof(int16_t));
+        if (!buf) throw std::runtime_error("cannot allocate page-locked memory for " + path);
         t.descs.push_back(d);
-        t.posts.push_back(std::move(buf));
+        t.posts.push_back(buf);
+        if (atmrt_host_read_dted(path.c_str(), &d, buf, np) != 0) throw std::runtime_error(g_error);
     }
     printf("Detected %zu terrain files\n", names.size());
     return t;
@@ -682,7 +692,9 @@ using namespace atmrt_host;
 extern "C" int atmrt_host_gen(int argc, const char* const* argv) {
     const auto start = std::chrono::steady_clock::now();
     auto t = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count(); };
-    atmrt_ctx* ctx = nullptr;
+    atmrt_group* group = nullptr;
+    uint8_t* rgb = nullptr;
+    atmrt_meta* meta = nullptr;
     try {
         Config c = read_config(argc, argv);
         printf("%.3f: Using terrain data directory: \"%s\"\n", t(), c.terrain_folder.c_str());
@@ -706,32 +718,36 @@ extern "C" int atmrt_host_gen(int argc, const char* const* argv) {
             objects.push_back(o);
         }
 
+        // One context per GPU, the panorama in column blocks (a group of one is the single-GPU render).
         auto check = [&](int rc, const char* what) {
-            if (rc != 0) throw std::runtime_error(std::string(what) + ": " + atmrt_last_error(ctx));
+            if (rc != 0) throw std::runtime_error(std::string(what) + ": " + atmrt_group_last_error(group));
         };
-        check(atmrt_create(0, &ctx), "atmrt_create");
-        check(atmrt_set_terrain(ctx, terrain.descs.data(), (int)terrain.descs.size(), terrain.ptrs().data()), "atmrt_set_terrain");
-        check(atmrt_set_params(ctx, &p), "atmrt_set_params");
-        check(atmrt_set_objects(ctx, objects.data(), (int)objects.size(), tex_ptrs.data()), "atmrt_set_objects");
+        check(atmrt_group_create(nullptr, c.gpus, &group), "atmrt_group_create");
+        check(atmrt_group_set_terrain(group, terrain.descs.data(), (int)terrain.descs.size(), terrain.ptrs().data()), "atmrt_group_set_terrain");
+        check(atmrt_group_set_params(group, &p), "atmrt_group_set_params");
+        check(atmrt_group_set_objects(group, objects.data(), (int)objects.size(), tex_ptrs.data()), "atmrt_group_set_objects");
         printf("%.3f: Generating terrain cache...\n%.3f: Generating path cache...\n%.3f: Calculating pixels...\n", t(), t(), t());
-        std::vector<uint8_t> rgb((size_t)p.width * p.height * 3);
-        std::vector<atmrt_meta> meta;
-        if (!c.file_metadata.empty()) meta.resize((size_t)p.width * p.height);
+        const size_t npix = (size_t)p.width * p.height;
+        rgb = (uint8_t*)atmrt_host_alloc(npix * 3);
+        if (!c.file_metadata.empty()) meta = (atmrt_meta*)atmrt_host_alloc(npix * sizeof(atmrt_meta));
+        if (!rgb || (!c.file_metadata.empty() && !meta)) throw std::runtime_error("cannot allocate page-locked memory for the image");
         atmrt_stats st{};
-        check(atmrt_render(ctx, rgb.data(), meta.empty() ? nullptr : meta.data(), nullptr, &st), "atmrt_render");
+        check(atmrt_group_render(group, rgb, meta, nullptr, &st), "atmrt_group_render");
         printf("%.3f: Done calculating (terrain %.2f ms, paths %.2f ms, march %.2f ms on the GPU; %llu ray steps, %llu pixels hit)\n", t(),
                st.ms_terrain, st.ms_paths, st.ms_march, (unsigned long long)st.ray_steps, (unsigned long long)st.pixels_hit);
         printf("%.3f: Outputting image...\n", t());
-        if (atmrt_host_write_png(c.file.c_str(), rgb.data(), p.width, p.height, 3) != 0) throw std::runtime_error(g_error);
+        if (atmrt_host_write_png(c.file.c_str(), rgb, p.width, p.height, 3) != 0) throw std::runtime_error(g_error);
         if (!c.file_metadata.empty()) {
             printf("%.3f: Outputting metadata...\n", t());
-            if (!write_metadata(c.file_metadata, p, meta)) throw std::runtime_error("cannot write " + c.file_metadata);
+            if (!write_metadata(c.file_metadata, p, meta, npix)) throw std::runtime_error("cannot write " + c.file_metadata);
         }
         printf("%.3f: Done.\n", t());
-        atmrt_destroy(ctx);
+        atmrt_host_free(rgb), atmrt_host_free(meta);
+        atmrt_group_destroy(group);
         return 0;
     } catch (const std::exception& e) {
-        if (ctx) atmrt_destroy(ctx);
+        atmrt_host_free(rgb), atmrt_host_free(meta);
+        if (group) atmrt_group_destroy(group);
         fail(ATMRT_ERR_INVALID, e.what());
         fprintf(stderr, "ERROR: %s\n", e.what());  // main.rs:36-38
         return 1;

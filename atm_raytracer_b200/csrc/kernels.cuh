@@ -642,149 +642,208 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stage B with macro steps. The ray equation is smooth wherever g(h) is -- everywhere except at the starts
-// of the temperature functions, where g jumps -- and there classical RK4 with a 25 m step is converged far
-// below f64 resolution of the path: integrating the same equation with ONE RK4 step of 16 x 25 m lands on the
-// same state to 4e-11 m for near-horizontal rays and 2e-9 m at 44 degrees (extended-precision measurement in
-// DESIGN.md section 4.B), and the fifteen states in between follow from the cubic Hermite interpolant of the
-// two ends (error < 2e-11 m). At a start of a temperature function the reference's result DOES depend on how its 25 m steps
-// straddle the jump (by millimetres), so there the kernel takes the reference's own single steps: a macro
-// step is taken only when no start lies in the altitude span it covers (exact test against the sorted
-// starts), single steps otherwise. The chain is 16x shorter where it matters, and the sixteen states of a
-// macro step are sixteen independent outputs: a warp is 2 rows x 16 sub-lanes (lane = 2 j + row), every
-// sub-lane integrates the row's macro step redundantly (identical values, no exchange), evaluates ITS
-// state from the interpolant, its calc_dist segment, takes part in a prefix sum for path_length and stores
-// its cache entry.
+// Macro steps. The ray equation is smooth wherever g(h) is -- everywhere except at the starts of the temperature
+// functions, where g jumps -- and there classical RK4 with a 25 m step is converged far below f64 resolution of the path:
+// integrating the same equation with ONE RK4 step of 16 x 25 m lands on the same state to 4e-11 m for near-horizontal
+// rays and 2e-9 m at 44 degrees (extended-precision measurement in DESIGN.md section 4.B), and the fifteen states in
+// between follow from the cubic Hermite interpolant of the two ends (error < 2e-11 m). At a start of a temperature
+// function the reference's result DOES depend on how its 25 m steps straddle the jump (by millimetres), so there the
+// stage takes the reference's own single steps: a macro step is taken only when no start lies in the altitude span it
+// covers (exact test against the sorted starts), single steps otherwise.
 // ---------------------------------------------------------------------------------------------
-constexpr int MACRO_THREADS = 128;  // 4 warps share one copy of the table
 constexpr double MACRO_MAX_METRES = 800.0;  // longest macro step: 16 x 50 m (truncation error < 3e-8 m, section 4.B); longer simulation steps get fewer per macro step
 constexpr int ATM_MAX_BND = ATMRT_MAX_ATM_FUNCTIONS + 4;
 
-template <bool FLAT, int MACRO>  // MACRO steps per macro step (16, 8, 4 or 2), 32 / MACRO rows per warp
-__global__ void __launch_bounds__(MACRO_THREADS) k_ray_paths_macro(const __grid_constant__ DevScene S, DevBuffers B) {
+// ---------------------------------------------------------------------------------------------
+// Stage B in two kernels: the CHAIN and the ELEMENTS.
+//
+// What is serial in a ray path is the integration of its state -- four dependent lookups of g per RK4 step. What
+// k_ray_paths_macro does besides (the sixteen states of a macro step from the cubic Hermite interpolant, their calc_dist
+// segments with a square root each, the prefix sum for path_length, the termination rule, the stores) is a second chain
+// of about the same length that a single in-order warp can only run AFTER the first, macro step after macro step. Here
+// the two are separate kernels:
+//   k_ray_chain     one lane per row integrates nothing but the state: per step the macro / single decision (per ROW,
+//                   not per pair of rows), one RK4 step of 16 x step or of step, and a 24-byte record {a, b, e, m} of the
+//                   state the step starts from. The stage's latency chain, a third as long.
+//   k_ray_elements  one block per row turns the records into the cache: every element of every step is independent
+//                   (Hermite state, segment length from the element before it), then one scan along the row for
+//                   path_length and one minimum for the termination rule (utils.rs:167-170). Throughput work that shares
+//                   the machine with stage A.
+// The arithmetic of a step is k_ray_paths_macro's (rk4_step<FLAT, 0> on the table; pieces, then libm where the table does
+// not serve), except that single steps take four lookups instead of rk4_step_shared's two corrected ones (1e-12
+// relative) and that path_length is summed in scan order (1e-13 relative).
+// ---------------------------------------------------------------------------------------------
+struct PathRecords {
+    double2* ab;  // [h][cap]: the state (r, dr/dphi) or (h, dh/dx) a step starts from; entry n is the state after the last step
+    int2* em;     // [h][cap]: first element of the step (its state is `ab`), elements in it: 16 / 8 / 4 / 2 or 1; negative: the row is frozen (complete or NaN)
+    int* n;       // [h]: steps recorded
+    int cap;
+};
+
+constexpr int CHAIN_THREADS = 64;
+
+template <bool FLAT>
+__global__ void __launch_bounds__(CHAIN_THREADS) k_ray_chain(const __grid_constant__ DevScene S, DevBuffers B, PathRecords R, int macro_steps) {
     __shared__ double tab_smem[ATM_FIELDS * ATM_CELLS];
     __shared__ double s_bnd[ATM_MAX_BND];          // sorted altitudes where g is not smooth (+inf padded)
     __shared__ unsigned char s_first[ATM_CELLS];   // per cell: index of the first of them at or above the cell's lower edge
 #pragma unroll 4
-    for (int i = threadIdx.x; i < ATM_FIELDS * ATM_CELLS; i += MACRO_THREADS) tab_smem[i] = B.atm_cells[i];
-    for (int i = threadIdx.x; i < ATM_CELLS; i += MACRO_THREADS) s_first[i] = B.atm_first[i];
+    for (int i = threadIdx.x; i < ATM_FIELDS * ATM_CELLS; i += CHAIN_THREADS) tab_smem[i] = B.atm_cells[i];
+    for (int i = threadIdx.x; i < ATM_CELLS; i += CHAIN_THREADS) s_first[i] = B.atm_first[i];
     if (threadIdx.x < ATM_MAX_BND) s_bnd[threadIdx.x] = B.atm_bnd[threadIdx.x];
     __syncthreads();
-    constexpr int MACRO_ROWS = 32 / MACRO;
     const GSource gs{(unsigned)__cvta_generic_to_shared(tab_smem), B.atm_pieces, B.n_atm_pieces};
-    const int lane = threadIdx.x & 31, rr = lane % MACRO_ROWS, j = lane / MACRO_ROWS;
-    const int y_raw = (blockIdx.x * (MACRO_THREADS / 32) + (threadIdx.x >> 5)) * MACRO_ROWS + rr;
+    const int y_raw = blockIdx.x * CHAIN_THREADS + threadIdx.x;
     const int y = min(y_raw, S.height - 1);
     const bool writer = y_raw < S.height;
     const double alt = *B.obs_alt;
     const double radius = S.radius, off = FLAT ? 0.0 : radius;
     const double d = FLAT ? S.step : S.step / radius;
-    const double hd = 0.5 * d, d6 = d / 6.0;
-    const double D = (double)MACRO * d, hD = 0.5 * D, D6 = D / 6.0;
-    const double shift = FLAT ? ATM_BASE : radius + ATM_BASE;
-    const double d15 = 1.5 * d, d2 = 2.0 * d;
+    const double D = (double)macro_steps * d;
+    const int n_t = S.n_t, k_far = S.path_k_far;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double2* __restrict__ rab = R.ab + (size_t)y * R.cap;
+    int2* __restrict__ rem = R.em + (size_t)y * R.cap;
+
+    double a = FLAT ? alt : radius + alt;
+    double b = FLAT ? tan(to_radians(get_ray_elev(S, y))) : a * tan(to_radians(get_ray_elev(S, y)));
+    double Lb = inf, Ub = -inf;  // the starts of temperature functions that bracket the current altitude (none in between); empty at first
+    bool trig_end = alt < -1000.0 || 0 >= k_far;  // the element the state sits on is past max_distance or below -1000 m
+    bool done = false;                            // ... an element before it is: the cache needs nothing beyond this element
+    int e = 0, ns = 0;
+#pragma unroll 1
+    while (__any_sync(FULL, e < n_t - 1 && !done)) {
+        const bool active = e < n_t - 1 && !done;
+        const bool nan = a != a;  // NaN in, NaN out: nothing to integrate, the elements are NaN
+        // may this step be a macro step? room for it, and no start of a temperature function in the altitudes it spans
+        // (the exact test of k_ray_paths_macro against the sorted starts, through a bracket that is renewed when left)
+        bool macro = e + macro_steps <= n_t - 1;
+        {
+            const double a_end = fma(D, b, a);
+            const double lo = fmin(a, a_end) - off - 1.0, hi = fmax(a, a_end) - off + 1.0;
+            if (active && !nan && !(lo > Lb && hi < Ub)) {
+                const double h0 = a - off;
+                const int cell = min(max((int)floor((h0 - (ATM_BASE - 0.5 * ATM_CELL)) * (1.0 / ATM_CELL)), 0), ATM_CELLS - 1);
+                int t = s_first[cell];
+                while (t > 0 && s_bnd[t - 1] > h0) --t;
+                while (s_bnd[t] <= h0) ++t;  // first start above the altitude (+inf padded)
+                Ub = s_bnd[t], Lb = t > 0 ? s_bnd[t - 1] : -inf;
+            }
+            macro = macro && (nan || (lo > Lb && hi < Ub));
+        }
+        const double step = macro ? D : d;
+        double a1 = a, b1 = b;
+        if (active && !nan) {
+            bool ok = rk4_step<FLAT, 0>(S.atm, gs, radius, step, 0.5 * step, step / 6.0, a, b, &a1, &b1);
+            if (!ok && macro) {  // a cell the table does not serve: the reference's single steps handle it
+                macro = false;
+                ok = rk4_step<FLAT, 0>(S.atm, gs, radius, d, 0.5 * d, d / 6.0, a, b, &a1, &b1);
+            }
+            if (!ok) rk4_step<FLAT, 1>(S.atm, gs, radius, d, 0.5 * d, d / 6.0, a, b, &a1, &b1);  // rare: pieces, then libm
+        }
+        const int m = macro ? macro_steps : 1;
+        if (active && writer) {
+            rab[ns] = make_double2(a, b);
+            rem[ns] = make_int2(e, nan ? -m : m);
+        }
+        if (active) {
+            ++ns;
+            // Termination (utils.rs:167-170): element q is kept unless an element <= q - 2 is past max_distance or
+            // below -1000 m. The chain knows the END elements of its steps: once one of them is past the rule, one more
+            // step supplies every element the cache can keep (k_ray_elements applies the rule to every element).
+            done = trig_end;
+            a = a1, b = b1, e += m;
+            const double h_end = FLAT ? a : a - radius;
+            trig_end = e >= k_far || h_end < -1000.0;
+        }
+    }
+    if (writer) {
+        rab[ns] = make_double2(a, b);  // the state after the last step
+        rem[ns] = make_int2(e, 0);
+        R.n[y] = ns;
+    }
+}
+
+constexpr int ELEM_THREADS = 256;
+
+template <bool FLAT>
+__global__ void __launch_bounds__(ELEM_THREADS) k_ray_elements(const __grid_constant__ DevScene S, DevBuffers B, PathRecords R) {
+    __shared__ int s_trig;        // first element past max_distance or below -1000 m
+    __shared__ double s_warp[ELEM_THREADS / 32];
+    __shared__ double s_carry;
+    const int y = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, j = tid & 15;
+    const double alt = *B.obs_alt;
+    const double radius = S.radius;
+    const double d = FLAT ? S.step : S.step / radius;
     const int n_t = S.n_t, k_far = S.path_k_far;
     double* const o_elev = B.p_elev + path_index(n_t, 0, y);
     double* const o_len = B.p_len + path_index(n_t, 0, y);
     const double* __restrict__ dxr = B.path_dxr;
-    // the cubic Hermite basis at this sub-lane's state, s = (j + 1) / MACRO
-    const double sj = (double)(j + 1) * (1.0 / MACRO);
-    const double h01 = sj * sj * (3.0 - 2.0 * sj), h10 = sj * (sj - 1.0) * (sj - 1.0), h11 = sj * sj * (sj - 1.0);
-    unsigned rowbits = 0u;  // this row's sub-lanes in a ballot
-    for (int t = 0; t < MACRO; ++t) rowbits |= 1u << (t * MACRO_ROWS + rr);
-
-    double a = FLAT ? alt : radius + alt;
-    double b = FLAT ? tan(to_radians(get_ray_elev(S, y))) : a * tan(to_radians(get_ray_elev(S, y)));
-    PathBase bE{0.0, 0.0, 0.0, 0.0}, bM = bE, bN = bE;
-    bool bases_valid = false;
-    // element 0: (alt, 0)
-    if (writer && j == 0) o_elev[0] = alt, o_len[0] = 0.0;
-    double h_e = alt;           // altitude of element e
-    double path_length = 0.0;   // of element e
-    bool done_c = false;        // an element <= e - 1 is past max_distance or below -1000 m (utils.rs:167-170)
-    bool trig_e = alt < -1000.0 || 0 >= k_far;  // ... element e is
-    int n = 1;
-    int e = 0;
-#pragma unroll 1
-    while (e < n_t - 1) {
-        if (__all_sync(FULL, done_c)) break;
-        const bool still = done_c || a != a;  // complete (it stops moving) or NaN (NaN in, NaN out): nothing to integrate
-        const bool idle = __all_sync(FULL, still);
-        // may this step be a macro step? no start of a temperature function in the altitudes it spans
-        bool macro = e + MACRO <= n_t - 1;
-        if (macro && !idle) {
-            const double a_end = fma(D, b, a);
-            const double lo = fmin(a, a_end) - off - 1.0, hi = fmax(a, a_end) - off + 1.0;
-            const int cell = min(max((int)floor((lo - (ATM_BASE - 0.5 * ATM_CELL)) * (1.0 / ATM_CELL)), 0), ATM_CELLS - 1);
-            int t = s_first[cell];
-            while (s_bnd[t] < lo) ++t;
-            const bool unsafe = !still && !(s_bnd[t] > hi);  // (NaN spans are not safe either)
-            macro = !__any_sync(FULL, unsafe);
-        }
-        double a1 = a, b1 = b;
-        if (macro && !idle) {
-            const bool ok = rk4_step<FLAT, 0>(S.atm, gs, radius, D, hD, D6, a, b, &a1, &b1) || still;
-            macro = __all_sync(FULL, ok);  // a cell the table does not serve: the reference's single steps handle it
-        }
-        int m;
-        bool valid;
-        double a_q;  // this sub-lane's state
-        if (macro) {
-            m = MACRO;
-            valid = true;
-            a_q = j == MACRO - 1 ? a1 : a + fma(h01, a1 - a, D * fma(h10, b, h11 * b1));
-            if (still) a_q = a, a1 = a, b1 = b;
-            bases_valid = false;
-        } else {
-            m = 1;
-            valid = j == 0;
-            if (!bases_valid) {
-                bE = path_base<FLAT>(gs.tab, shift, a), bM = path_base<FLAT>(gs.tab, shift, fma(hd, b, a)), bN = path_base<FLAT>(gs.tab, shift, fma(d, b, a));
-                bases_valid = true;
-            }
-            const bool ok = rk4_step_shared<FLAT>(d, hd, d6, a, b, bE, bM, bN, &a1, &b1) || still;
-            bE = bN;
-            bM = path_base<FLAT>(gs.tab, shift, fma(d15, b, a));
-            bN = path_base<FLAT>(gs.tab, shift, fma(d2, b, a));
-            if (!ok) rk4_step<FLAT, 1>(S.atm, gs, radius, d, hd, d6, a, b, &a1, &b1);  // rare: an altitude the table does not serve
-            if (still) a1 = a, b1 = b;
-            a_q = a1;
-        }
-        // this sub-lane's element q = e + j + 1: calc_dist from the element before it, path_length by prefix sum
-        const int q = min(e + j + 1, n_t - 1);
+    const double2* __restrict__ rab = R.ab + (size_t)y * R.cap;
+    const int2* __restrict__ rem = R.em + (size_t)y * R.cap;
+    const int nrec = R.n[y];
+    if (tid == 0) {
+        s_trig = alt < -1000.0 || 0 >= k_far ? 0 : n_t;
+        s_carry = 0.0;
+        o_elev[0] = alt, o_len[0] = 0.0;  // element 0: (alt, 0)
+    }
+    __syncthreads();
+    // ---- the elements: 16 threads per step; element q = e + j + 1 from the interpolant of the step's two ends ----
+    int first_trig = n_t;
+    for (int base = 0; base < nrec; base += ELEM_THREADS / 16) {
+        const int sidx = base + tid / 16;
+        const bool have = sidx < nrec;
+        const int2 em = have ? rem[sidx] : make_int2(0, 0);
+        const int m = abs(em.y);
+        const bool frozen = em.y < 0, mine = have && j < m;
+        const double2 s0 = rab[have ? sidx : 0], s1 = rab[have ? sidx + 1 : 0];
+        const double a = s0.x, b = s0.y, a1 = s1.x, b1 = s1.y;
+        // the cubic Hermite basis at this thread's state, s = (j + 1) / m (the last state of a step is its end)
+        const double sj = (double)(j + 1) / (double)max(m, 1);
+        const double h01 = sj * sj * (3.0 - 2.0 * sj), h10 = sj * (sj - 1.0) * (sj - 1.0), h11 = sj * sj * (sj - 1.0);
+        const double Dm = (double)m * d;
+        double a_q = j == m - 1 ? a1 : a + fma(h01, a1 - a, Dm * fma(h10, b, h11 * b1));
+        if (frozen) a_q = a;
+        const int q = min(em.x + j + 1, n_t - 1);
         const double h_q = FLAT ? a_q : a_q - radius;
-        const double h_up = __shfl_up_sync(FULL, h_q, MACRO_ROWS);
-        const double h_p = j == 0 ? h_e : h_up;
+        const double h_up = __shfl_up_sync(FULL, h_q, 1);
+        const double h_p = j == 0 ? (FLAT ? a : a - radius) : h_up;  // the element before it: the step's start, or the neighbour's
         double dx = dxr[q];
         if (!FLAT) dx = dx * ((h_q + h_p) * 0.5 + radius);
         const double dh = h_q - h_p;
-        double acc = valid ? sqrt_nr(dx * dx + dh * dh) : 0.0;
-#pragma unroll
-        for (int o = MACRO_ROWS; o < 32; o <<= 1) {
-            const double up = __shfl_up_sync(FULL, acc, o);
-            if (lane >= o) acc += up;
+        const double seg = sqrt_nr(dx * dx + dh * dh);
+        if (mine) {
+            o_elev[(size_t)q * PATH_ROWS] = h_q;
+            o_len[(size_t)q * PATH_ROWS] = seg;  // (its calc_dist segment; path_length after the scan below)
+            if (q >= k_far || h_q < -1000.0) first_trig = min(first_trig, q);
         }
-        const double len_q = path_length + acc;
-        // termination: element q is kept unless an element <= q - 2 is past max_distance or below -1000 m
-        const bool trig_q = valid && (q >= k_far || h_q < -1000.0);
-        const unsigned trig = (__ballot_sync(FULL, trig_q) & rowbits) >> rr;  // bit MACRO_ROWS j' = sub-lane j'
-        const bool earlier = done_c || (j >= 1 && trig_e) || (j >= 2 && (trig & ((1u << (MACRO_ROWS * (j - 1))) - 1u)) != 0u);
-        const bool emit = valid && writer && !earlier;
-        stg_if(o_elev + (size_t)q * PATH_ROWS, h_q, emit);
-        stg_if(o_len + (size_t)q * PATH_ROWS, len_q, emit);
-        n = emit ? q + 1 : n;
-        // carry to element e + m
-        const int last = rr + MACRO_ROWS * (m - 1);
-        const unsigned before_last = m == 1 ? 0u : (trig & ((1u << (MACRO_ROWS * (m - 1))) - 1u));
-        done_c = done_c || trig_e || before_last != 0u;
-        trig_e = ((trig >> (MACRO_ROWS * (m - 1))) & 1u) != 0u;
-        path_length = __shfl_sync(FULL, len_q, last);
-        h_e = __shfl_sync(FULL, h_q, last);
-        a = a1, b = b1;
-        e += m;
     }
-    for (int o = MACRO_ROWS; o < 32; o <<= 1) n = max(n, __shfl_xor_sync(FULL, n, o));
-    if (writer && j == 0) {
+    for (int o = 16; o > 0; o >>= 1) first_trig = min(first_trig, __shfl_xor_sync(FULL, first_trig, o));
+    if (lane == 0 && first_trig < n_t) atomicMin(&s_trig, first_trig);
+    __syncthreads();
+    // elements 0 .. n - 1 are kept: everything the chain produced, up to the element after the first one past the rule
+    const int n_all = nrec > 0 ? rem[nrec].x + 1 : 1;
+    const int n = min(n_all, s_trig < n_t ? s_trig + 2 : n_t);
+    // ---- path_length: the running sum of the segments along the row ----
+    for (int base = 1; base < n; base += ELEM_THREADS) {
+        const int q = base + tid;
+        double v = q < n ? o_len[(size_t)q * PATH_ROWS] : 0.0;
+        for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(FULL, v, o);
+            if (lane >= o) v += up;
+        }
+        if (lane == 31) s_warp[tid >> 5] = v;
+        __syncthreads();
+        double pre = s_carry;
+        for (int w = 0; w < (tid >> 5); ++w) pre += s_warp[w];
+        v += pre;
+        if (q < n) o_len[(size_t)q * PATH_ROWS] = v;
+        __syncthreads();
+        if (tid == ELEM_THREADS - 1) s_carry = v;
+        __syncthreads();
+    }
+    if (tid == 0) {
         B.p_n[y] = n;
         atomicAdd(B.counters + CNT_PATH_STEPS, (unsigned long long)(n - 1));
     }
@@ -1470,222 +1529,10 @@ __global__ void __launch_bounds__(256) k_path_check(const double* __restrict__ e
     if (__any_sync(FULL, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, 1u);
 }
 
-constexpr int SWEEP_THREADS = 128;  // one warp per column
-constexpr int SWEEP_ROWS = 4;       // rows resolved per window from one 32-byte load per lane
-
-// One warp per column. The lanes hold a window of 32 consecutive steps (lane l: step k + l) for a group of
-// SWEEP_ROWS adjacent rows at once -- the path cache is [k][row], so the rows of a group are one 32-byte
-// sector per step. The rows of the group are resolved bottom-up from those registers: row y's first event
-// in the window decides it, and the row above continues from the same step. The window advances only when
-// the lowest unresolved row has no event in it.
-__global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(const __grid_constant__ DevScene S, DevBuffers B, int col0, int col1) {
-    if (B.sweep_flags[0] != 0) return;
-    const int lane = threadIdx.x & 31;
-    const int xl = col0 + blockIdx.x * (SWEEP_THREADS / 32) + (threadIdx.x >> 5);  // the image is swept in column chunks
-    if (xl >= col1) return;
-    const double* __restrict__ te = B.t_elev + (size_t)xl * S.n_pad;
-    const double* __restrict__ pe = B.p_elev;
-    int* __restrict__ hit = B.sweep_hit + (size_t)xl * S.h_pad;
-    bool flagged = !(pe[0] - te[0] > 0.0);  // every ray starts at the observer altitude (element 0 of every row)
-    const int k_last = S.n_t - 1;
-    static_assert(SWEEP_ROWS == PATH_ROWS, "the sweep reads one row group of the path cache per 32-byte load");
-    int k = 1;  // first step the current row may still cross at
-    // groups of SWEEP_ROWS rows (local row 0 is the top one), bottom group first, rows bottom-up inside
-    bool finished = false;
-    for (int g = (S.height - 1) / SWEEP_ROWS; g >= 0 && !flagged && !finished; --g) {
-        const int ybase = g * SWEEP_ROWS;
-        int r = min(SWEEP_ROWS - 1, S.height - 1 - ybase);
-        const int4 len = *reinterpret_cast<const int4*>(B.p_n + ybase);  // p_n is padded to h_pad entries
-        const int n0 = min(S.n_t, len.x), n1 = min(S.n_t, len.y), n2 = min(S.n_t, len.z), n3 = min(S.n_t, len.w);
-        while (r >= 0 && !flagged) {
-            if (k >= S.n_t) {
-                // The walk has reached the end of the caches: the first row that sees only sky scanned to the end,
-                // and no row above it can cross any more (no path is longer than n_t). All of them at once.
-                for (int yy = ybase + r - lane; yy >= 0; yy -= 32) hit[yy] = 0;
-                finished = true;
-                break;
-            }
-            int nlim = r == 3 ? n3 : (r == 2 ? n2 : (r == 1 ? n1 : n0));
-            if (k >= nlim) {  // this row's path ends without a sign change
-                if (lane == 0) hit[ybase + r] = 0;
-                --r;
-                continue;
-            }
-            // the window: steps k + lane for all rows of the group; the "before" side comes from the lane below
-            const int kk = min(k + lane, k_last);
-            const double4 cur = *reinterpret_cast<const double4*>(pe + path_index(S.n_t, kk, ybase));
-            const double t_cur = te[kk];
-            double4 prv;
-            prv.x = __shfl_up_sync(FULL, cur.x, 1), prv.y = __shfl_up_sync(FULL, cur.y, 1);
-            prv.z = __shfl_up_sync(FULL, cur.z, 1), prv.w = __shfl_up_sync(FULL, cur.w, 1);
-            double t_prv = __shfl_up_sync(FULL, t_cur, 1);
-            if (lane == 0) {
-                prv = *reinterpret_cast<const double4*>(pe + path_index(S.n_t, k - 1, ybase));
-                t_prv = te[k - 1];
-            }
-            int lo = 0;        // lanes below `lo` are steps the current row cannot cross at any more
-            bool odd = false;  // an exact zero or an exit from below among the cells of this window
-            // Resolve rows from the registers while the window serves them. A crossing from above
-            // (d1 > 0 > d2, utils.rs:220-222) at the first such lane >= lo is the row's hit; the row above
-            // continues from that lane.
-#define ATMRT_SWEEP_ROW(C, R, NABOVE)                                                                        \
-    {                                                                                                        \
-        const double d1 = prv.C - t_prv, d2 = cur.C - t_cur;                                                 \
-        const bool in = k + lane < nlim;                                                                     \
-        const bool oddcell = in && lane >= lo && (d2 == 0.0 || (d1 * d2 < 0.0 && !(d1 > 0.0)));              \
-        const unsigned hits = __ballot_sync(FULL, in && lane >= lo && d1 > 0.0 && d2 < 0.0);                 \
-        odd = odd || (oddcell && (hits == 0 || lane < __ffs(hits) - 1)); /* only cells the row visits */     \
-        if (hits == 0) {                                                                                     \
-            if (k + 32 >= nlim) { /* the row ends inside the window: no hit; the row above goes on from there */ \
-                if (lane == 0) hit[ybase + R] = 0;                                                           \
-                r = R - 1;                                                                                   \
-                k = nlim;                                                                                    \
-            } else {                                                                                         \
-                r = R;                                                                                       \
-                k += 32;                                                                                     \
-            }                                                                                                \
-            lo = 0;                                                                                          \
-            goto window_done;                                                                                \
-        }                                                                                                    \
-        lo = __ffs(hits) - 1;                                                                                \
-        if (lane == 0) hit[ybase + R] = k + lo;                                                              \
-        r = R - 1;                                                                                           \
-        nlim = NABOVE;                                                                                       \
-    }
-            switch (r) {
-                case 3: ATMRT_SWEEP_ROW(w, 3, n2)
-                case 2: ATMRT_SWEEP_ROW(z, 2, n1)
-                case 1: ATMRT_SWEEP_ROW(y, 1, n0)
-                default: ATMRT_SWEEP_ROW(x, 0, n0)
-            }
-#undef ATMRT_SWEEP_ROW
-        window_done:
-            // An odd cell among those a row visits before its hit (an exact zero of ray - terrain, or an exit
-            // from below: a ray that started under the surface) sends the column to the general march.
-            if (__any_sync(FULL, odd)) flagged = true;
-            k += lo;  // the next window starts at the last hit
-        }
-    }
-    if (lane == 0) {
-        B.sweep_col[xl] = flagged ? 1 : 0;
-        if (flagged) atomicOr(B.sweep_flags + 1, 1u);  // some column needs the brute-force march
-    }
-}
-
-// Colour, composite and write the pixels of the swept columns (get_single_pixel's hit processing +
-// draw_image). A block is a tile of 32 rows x SHADE_COLS columns: each warp shades 32 adjacent rows of
-// one column (adjacent rows hit adjacent steps, so the cache reads of a warp share sectors), the
-// results are staged in shared memory and written with the lanes running along x, so that the
-// row-major [y][x] image and metadata are stored as contiguous row segments.
-constexpr int SHADE_COLS = 8;
-
-template <int W>
-__global__ void __launch_bounds__(32 * SHADE_COLS, 4) k_sweep_shade(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, int col0, int row0) {
-    if (B.sweep_flags[0] != 0) return;
-    __shared__ double s_meta[32][SHADE_COLS * 4];
-    __shared__ __align__(16) unsigned char s_rgb[32][SHADE_COLS * 3];
-    __shared__ int s_steps[32][SHADE_COLS];
-    __shared__ unsigned char s_skip[SHADE_COLS];
-    __shared__ double s_nrm[SHADE_COLS][64][3];
-    const int wl = S.x1 - S.x0;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int c0 = col0 + blockIdx.y * SHADE_COLS, y0 = row0 + blockIdx.x * 32;  // col0: a multiple of SHADE_COLS; row0: of 32 (row bands)
-    const int xl = c0 + w, y = y0 + lane;
-    const bool col_ok = xl < wl && B.sweep_col[xl] == 0;  // flagged columns belong to the brute-force march
-    const bool active = col_ok && y < S.height;
-    if (lane == 0) s_skip[w] = col_ok ? 0 : 1;
-    const int xx = min(xl, wl - 1), yy = min(y, S.height - 1);
-    const size_t pixel = (size_t)yy * wl + xx;
-    const int nlim = min(S.n_t, B.p_n[yy]);
-    PixelState st;
-    init_pixel(st);
-    int consumed = nlim > 0 ? nlim - 1 : 0;
-    const int k = active ? B.sweep_hit[(size_t)xx * S.h_pad + yy] : 0;
-    const bool hit = k > 0;
-    // The terrain normals of the two samples that bracket each hit (TerrainData::normal, deferred from stage
-    // A: sample_normal). The 32 rows of the warp hit a handful of distinct samples -- the foreground rows
-    // share one step, rows on a slope hit consecutive steps, and sample k - 1 of one row is sample k of the
-    // next run -- so each distinct sample is evaluated once: the first lane of every run of equal k owns
-    // sample k, and sample k - 1 unless the next run owns it as its k; the owned samples are numbered,
-    // dealt to the lanes 32 at a time, and read back through shared memory.
-    V3 nrm[2] = {V3{0.0, 0.0, 0.0}, V3{0.0, 0.0, 0.0}};
-    {
-        const int k_up = __shfl_up_sync(FULL, k, 1);
-        const bool lead = hit && (lane == 0 || k_up != k);
-        const unsigned mask1 = __ballot_sync(FULL, lead);
-        if (mask1) {  // warp-uniform
-            const int leader = 31 - __clz(mask1 & (0xffffffffu >> (31 - lane)));         // of this lane's run (when it hit)
-            const unsigned later = leader >= 31 || leader < 0 ? 0u : (mask1 & (0xfffffffeu << leader));
-            const int next = later ? __ffs(later) - 1 : -1;                               // leader of the next run
-            const int k_next = __shfl_sync(FULL, k, next < 0 ? 0 : next);
-            const bool own0 = lead && !(next >= 0 && k_next == k - 1);
-            const unsigned mask0 = __ballot_sync(FULL, own0);
-            const int n1cnt = __popc(mask1), total = n1cnt + __popc(mask0);
-            for (int base = 0; base < total; base += 32) {
-                const int item = base + lane;
-                const bool mine = item < total, second = item >= n1cnt;
-                const unsigned src = mine ? __fns(second ? mask0 : mask1, 0, (second ? item - n1cnt : item) + 1) : 0u;
-                const int ks = __shfl_sync(FULL, k, src & 31);
-                if (mine) {
-                    const int smp = ks - (second ? 1 : 0);
-                    const size_t ti = (size_t)xx * S.n_pad + smp;
-                    const V3 n = sample_normal<W>(S, B.terrain, B, xx, smp, B.t_lat[ti], B.t_lon[ti]);
-                    s_nrm[w][item][0] = n.x, s_nrm[w][item][1] = n.y, s_nrm[w][item][2] = n.z;
-                }
-            }
-            __syncwarp();
-            if (hit) {
-                const int i1 = __popc(mask1 & ((1u << leader) - 1u));
-                const int i0 = ((mask0 >> leader) & 1u) ? n1cnt + __popc(mask0 & ((1u << leader) - 1u)) : i1 + 1;
-                nrm[0] = V3{s_nrm[w][i0][0], s_nrm[w][i0][1], s_nrm[w][i0][2]};
-                nrm[1] = V3{s_nrm[w][i1][0], s_nrm[w][i1][1], s_nrm[w][i1][2]};
-            }
-        }
-    }
-    if (hit) {
-        process_step<false, false>(S, B, O, xx, yy, k, pixel, st, nrm);
-        consumed = k;
-    }
-    const Rgb8 px = final_color(S, st);
-    s_rgb[lane][w * 3 + 0] = px.c[0], s_rgb[lane][w * 3 + 1] = px.c[1], s_rgb[lane][w * 3 + 2] = px.c[2];
-    s_meta[lane][w * 4 + 0] = st.m_lat, s_meta[lane][w * 4 + 1] = st.m_lon, s_meta[lane][w * 4 + 2] = st.m_elev, s_meta[lane][w * 4 + 3] = st.m_dist;
-    s_steps[lane][w] = consumed;
-    count_pixel(B, active, st, consumed);
-    const bool all_cols = __syncthreads_and(col_ok ? 1 : 0) != 0;  // also the barrier between staging and write-out
-    const int rows = min(32, S.height - y0);
-    // Write-out with the lanes along x: thread t handles pixel (row t / 16, column t % 16) of the tile -- its
-    // 32 bytes of metadata as two 16-byte stores, so a warp writes two 512-byte row segments -- and, for the
-    // colour, word t of the tile's 32 x 12 four-byte words when the row segments are word-aligned.
-    {
-        const int r = threadIdx.x / SHADE_COLS, c = threadIdx.x % SHADE_COLS;
-        const bool live = r < rows && c0 + c < wl && !s_skip[c];
-        if (O.meta && live) {
-            double2* out = reinterpret_cast<double2*>(O.meta + (size_t)(y0 + r) * wl + c0 + c);
-            out[0] = make_double2(s_meta[r][c * 4 + 0], s_meta[r][c * 4 + 1]);
-            out[1] = make_double2(s_meta[r][c * 4 + 2], s_meta[r][c * 4 + 3]);
-        }
-        if (O.steps && live) O.steps[(size_t)(y0 + r) * wl + c0 + c] = s_steps[r][c];
-    }
-    if (O.rgb) {
-        if (all_cols && (wl & 3) == 0) {  // every row segment of the tile is 48 aligned bytes
-            constexpr int WORDS = SHADE_COLS * 3 / 4;
-            if ((int)threadIdx.x < rows * WORDS) {
-                const int r = threadIdx.x / WORDS, q = threadIdx.x % WORDS;
-                const unsigned v = *reinterpret_cast<const unsigned*>(&s_rgb[r][q * 4]);
-                *reinterpret_cast<unsigned*>(O.rgb + ((size_t)(y0 + r) * wl + c0) * 3 + q * 4) = v;
-            }
-        } else {
-            for (int e = threadIdx.x; e < rows * SHADE_COLS * 3; e += 32 * SHADE_COLS) {
-                const int r = e / (SHADE_COLS * 3), q = e % (SHADE_COLS * 3), c = q / 3;
-                if (c0 + c < wl && !s_skip[c]) O.rgb[((size_t)(y0 + r) * wl + c0) * 3 + q] = s_rgb[r][q];
-            }
-        }
-    }
-}
+constexpr int SWEEP_ROWS = 4;  // rows resolved per window from one 32-byte load per lane
 
 // ---------------------------------------------------------------------------------------------
-// Stage C for opaque terrain without objects, three kernels (the product path; k_sweep / k_sweep_shade above are its
-// first version, kept behind ATMRT_STAGE_C=legacy while this one is being measured):
+// Stage C for opaque terrain without objects, three kernels:
 //
 //   k_sweep_bits   the horizon sweep with the sign tests of a whole window taken as warp votes: the lanes hold 32
 //                  consecutive steps of a group of four rows, three ballots per row (ray above / below / exactly on the
@@ -1702,10 +1549,12 @@ __global__ void __launch_bounds__(32 * SHADE_COLS, 4) k_sweep_shade(const __grid
 constexpr int BITS_WARPS = 4;  // adjacent columns share a block (and the path windows in L1)
 
 struct SweepLists {
-    int* list;        // [wl][cap]: the distinct samples of the column's hits, ascending; list[s - 1] == list[s] - 1 for every slot s a pixel refers to
-    int* count;       // [wl]
-    double* normals;  // [wl][cap][3]
-    int cap;
+    int* list;        // [wl][bands][cap]: the distinct samples of a band's hits, ascending; list[s - 1] == list[s] - 1 for every slot s a pixel refers to
+    int* count;       // [wl][bands]
+    double* normals;  // [wl][bands][cap][3]
+    int cap;          // entries per (column, band)
+    int bands;        // a column is swept in row bands, numbered from the top of the image ...
+    int band_rows;    // ... of this many rows (a multiple of 32)
 };
 
 // predicated global stores (no branch): the sweep's control flow is warp-uniform, only lane 0 writes
@@ -1718,43 +1567,90 @@ __device__ __forceinline__ void st_if_v4s32(int* p, int a, int b, int c, int d, 
                  : "memory");
 }
 
-template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(32 * BITS_WARPS, MIN_BLOCKS) k_sweep_bits(const __grid_constant__ DevScene S, DevBuffers B, SweepLists L, int col0, int col1) {
+__global__ void __launch_bounds__(32 * BITS_WARPS, 8) k_sweep_bits(const __grid_constant__ DevScene S, DevBuffers B, SweepLists L, int col0, int col1) {
     if (B.sweep_flags[0] != 0) return;
     const int lane = threadIdx.x & 31;
     const bool lane0 = lane == 0;
     const int xl = col0 + blockIdx.x * BITS_WARPS + (threadIdx.x >> 5);
     if (xl >= col1) return;
+    // The walk of a column is one dependent chain; cut into row bands it is several shorter ones, which is what keeps a
+    // narrow column block (one of eight GPUs) busy. By the monotonicity the sweep rests on, the walk enters a band in the
+    // state the row just below the band leaves behind -- its first-hit step, or the end of its path -- which the band
+    // finds by scanning that ONE row from step 1: the same cells, the same tests. blockIdx.y = 0 is the bottom band.
+    const int band = L.bands - 1 - (int)blockIdx.y;
+    const int y_lo = band * L.band_rows, y_hi = min(S.height, y_lo + L.band_rows) - 1;
     const double* __restrict__ te = B.t_elev + (size_t)xl * S.n_pad;
-    const double* __restrict__ pe = B.p_elev;
-    int* __restrict__ hit = B.sweep_hit + (size_t)xl * S.h_pad;  // per pixel: 1 + the slot of its first-hit step in the list (0: no hit)
-    int* __restrict__ list = L.list + (size_t)xl * L.cap;
+    int* __restrict__ hit = B.sweep_hit + (size_t)xl * S.h_pad;  // per pixel: 1 + the slot of its first-hit step in the band's list (0: no hit)
+    int* const list = L.list + ((size_t)xl * L.bands + band) * L.cap;
     const int n_t = S.n_t, k_last = n_t - 1;
     static_assert(SWEEP_ROWS == PATH_ROWS && SWEEP_ROWS == 4, "the sweep reads one row group of the path cache per 32-byte load");
-    bool flagged = !(pe[0] - te[0] > 0.0);  // every ray starts at the observer altitude (element 0 of every row)
+    bool flagged = !(B.p_elev[0] - te[0] > 0.0);  // every ray starts at the observer altitude (element 0 of every row)
     // The window: lane j holds step kb + j; lane 0 is the "before" side of the first step a row may cross at, so a
     // window serves the steps kb + 1 .. kb + 31 and advances by 31. `lo`: the current row may cross at lanes >= lo only
     // (kb + lo is the first-hit step of the row below it, or where that row's path ended).
     int kb = 0, lo = 1;
-    int* lp = list;   // end of the list
-    int last = -1;    // its last entry: the step of the latest hit
+    int* lp = list;     // end of the list ...
+    int cnt = 0;        // ... and its length
+    int last = -1;      // its last entry: the step of the latest hit
     unsigned bad = 0u;  // odd cells met so far
-    double t_cur;
-    double4 cur;
-    unsigned m4;  // this lane's step: the rows of the group whose ray is below the terrain there (bit R = row R)
+    unsigned m4;        // this lane's step: the rows of the group whose ray is below the terrain there (bit R = row R)
     bool finished = false;  // the walk reached the end of the caches: every row above sees only sky
-#define ATMRT_BITS_WINDOW(YBASE)                                                                                  \
-    {                                                                                                            \
-        cur = *reinterpret_cast<const double4*>(pe + path_index(n_t, min(kb + lane, k_last), YBASE));            \
-        m4 = (cur.x - t_cur < 0.0 ? 1u : 0u) | (cur.y - t_cur < 0.0 ? 2u : 0u) | (cur.z - t_cur < 0.0 ? 4u : 0u) | \
-             (cur.w - t_cur < 0.0 ? 8u : 0u);                                                                    \
+    const size_t gstride = (size_t)n_t * PATH_ROWS;  // one row group of the path cache
+    if (y_hi + 1 < S.height && !flagged) {
+        // ---- entering the band: the row below it, four windows at a time ----
+        const int yb = y_hi + 1, nlim = min(n_t, B.p_n[yb]);
+        const double* pr = B.p_elev + path_index(n_t, 0, yb);
+        unsigned entry = 0u;
+        for (;;) {
+            unsigned stop = 0u, oddf = 0u, ent[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int kw = kb + 31 * w, kk = min(kw + lane, k_last);
+                const double dw = pr[(size_t)kk * PATH_ROWS] - te[kk];
+                const unsigned ab = __ballot_sync(FULL, dw > 0.0), be = __ballot_sync(FULL, dw < 0.0), ze = __ballot_sync(FULL, dw == 0.0);
+                const int sp = nlim - kw;
+                const unsigned vis = (sp >= 32 ? FULL : sp <= 0 ? 0u : (1u << sp) - 1u) & ~1u;
+                ent[w] = (ab << 1) & be & vis;
+                const unsigned od = (((be << 1) & ab) | ze) & vis;
+                stop |= ent[w] != 0u || kw + 32 >= nlim ? 1u << w : 0u;
+                // odd cells the row visits: all of a window without a crossing, those before the crossing otherwise
+                oddf |= (ent[w] ? od & ((1u << (__ffs(ent[w]) - 1)) - 1u) : od) != 0u ? 1u << w : 0u;
+            }
+            const int nskip = stop ? __ffs(stop) - 1 : 4;     // windows passed without an event
+            bad |= oddf & (stop ? (2u << nskip) - 1u : 0xfu);  // ... and the one that holds the event, up to it
+            kb += 31 * nskip;
+            if (stop) {
+                entry = nskip == 0 ? ent[0] : nskip == 1 ? ent[1] : nskip == 2 ? ent[2] : ent[3];
+                break;
+            }
+        }
+        if (entry) {  // the row below hits at step kb + hl: the band's rows go on from there
+            const int hl = __ffs(entry) - 1, kh = kb + hl;
+            st_if_s32(lp, kh - 1, lane0);
+            st_if_s32(lp + 1, kh, lane0);
+            lp += 2, cnt = 2, last = kh, lo = hl;
+        } else {  // its path ends without a sign change (or it sees only sky: kb + lo == n_t)
+            kb = ((nlim - 1) / 31) * 31, lo = nlim - kb;
+        }
     }
-    t_cur = te[min(lane, k_last)];
-    for (int g = (S.height - 1) / SWEEP_ROWS; g >= 0 && bad == 0u && !flagged && !finished; --g) {
+    const int g_top = y_hi / SWEEP_ROWS;
+    const double* pg = B.p_elev + (size_t)g_top * gstride;          // this group's rows, [k][row % 4]
+    const int* pn = B.p_n + g_top * SWEEP_ROWS;
+    int kk4 = min(kb + lane, k_last) * PATH_ROWS;                   // this lane's step of the window, as an offset into pg
+    double t_cur = te[min(kb + lane, k_last)];
+    double4 cur = *reinterpret_cast<const double4*>(pg + kk4);
+    double4 nxt = cur;  // the window of the NEXT group at the same steps, loaded one group ahead (the walk's latency chain)
+    int nxt_kb = -1;
+#define ATMRT_BITS_M4()                                                                                              \
+    m4 = (cur.x - t_cur < 0.0 ? 1u : 0u) | (cur.y - t_cur < 0.0 ? 2u : 0u) | (cur.z - t_cur < 0.0 ? 4u : 0u) |       \
+         (cur.w - t_cur < 0.0 ? 8u : 0u);
+    for (int g = g_top; g * SWEEP_ROWS >= y_lo && bad == 0u && !flagged && !finished; --g, pg -= gstride, pn -= SWEEP_ROWS) {
         const int ybase = g * SWEEP_ROWS;
-        const int rmax = min(SWEEP_ROWS - 1, S.height - 1 - ybase);
-        const int4 len = *reinterpret_cast<const int4*>(B.p_n + ybase);  // p_n is padded to h_pad entries
-        ATMRT_BITS_WINDOW(ybase)
+        const int rmax = min(SWEEP_ROWS - 1, y_hi - ybase);
+        const int4 len = *reinterpret_cast<const int4*>(pn);  // p_n is padded to h_pad entries
+        if (g != g_top) cur = nxt_kb == kb ? nxt : *reinterpret_cast<const double4*>(pg + kk4);
+        if (ybase > y_lo) nxt = *reinterpret_cast<const double4*>(pg - gstride + kk4), nxt_kb = kb;
+        ATMRT_BITS_M4()
         // Rows that cross at the very step the row below them hit at need no search: where that row crossed from above,
         // every ray above it was above the terrain one step earlier too (the rays do not cross: k_path_check), so such
         // a row hits there iff it is below the terrain at that step -- one bit of m4 at the hit's lane.
@@ -1765,9 +1661,10 @@ __global__ void __launch_bounds__(32 * BITS_WARPS, MIN_BLOCKS) k_sweep_bits(cons
 #define ATMRT_BITS_ROW(C, R, LEN, HOUT)                                                                          \
     if (R <= rmax) {                                                                                             \
         if ((same >> R) & 1u) {                                                                                  \
-            HOUT = (int)(lp - list); /* the same step, the same slot */                                          \
+            HOUT = cnt; /* the same step, the same slot */                                                       \
         } else {                                                                                                 \
             const int nlim = min(n_t, LEN);                                                                      \
+            int adv = 0; /* windows this row has moved on without a hit */                                       \
             same = 0u;                                                                                           \
             for (;;) {                                                                                           \
                 if (kb + lo >= nlim) {                                                                           \
@@ -1790,12 +1687,12 @@ __global__ void __launch_bounds__(32 * BITS_WARPS, MIN_BLOCKS) k_sweep_bits(cons
                         /* the distinct samples of the hits: kh - 1 and kh, appended unless they are the last entries */ \
                         const bool new1 = last != kh, new0 = new1 && last != kh - 1;                             \
                         st_if_s32(lp, kh - 1, lane0 && new0);                                                    \
-                        lp += new0 ? 1 : 0;                                                                      \
+                        lp += new0 ? 1 : 0, cnt += new0 ? 1 : 0;                                                 \
                         st_if_s32(lp, kh, lane0 && new1);                                                        \
-                        lp += new1 ? 1 : 0;                                                                      \
+                        lp += new1 ? 1 : 0, cnt += new1 ? 1 : 0;                                                 \
                         last = kh;                                                                               \
-                        HOUT = (int)(lp - list); /* 1 + slot of kh */                                            \
-                        lo = hl;                 /* the row above continues from the same step */                \
+                        HOUT = cnt; /* 1 + slot of kh */                                                         \
+                        lo = hl;    /* the row above continues from the same step */                             \
                         same = __shfl_sync(FULL, m4, hl);                                                        \
                         break;                                                                                   \
                     }                                                                                            \
@@ -1805,11 +1702,35 @@ __global__ void __launch_bounds__(32 * BITS_WARPS, MIN_BLOCKS) k_sweep_bits(cons
                         break;                                                                                   \
                     }                                                                                            \
                     kb += 31, lo = 1;                                                                            \
+                    /* Far field: a row crosses many windows without a hit. From its second empty window on, four    \
+                       windows of THIS row at once -- four loads in flight instead of a chain of four -- and on past  \
+                       them while none holds a crossing or the end of the row's path; the window that does is then  \
+                       taken up as usual. */                                                                     \
+                    if (adv++ > 0) for (;;) {                                                                    \
+                        unsigned stop = 0u, oddf = 0u;                                                           \
+                        _Pragma("unroll") for (int w = 0; w < 4; ++w) {                                          \
+                            const int kw = kb + 31 * w, kk = min(kw + lane, k_last);                             \
+                            const double dw = pg[(size_t)kk * PATH_ROWS + R] - te[kk];                           \
+                            const unsigned ab = __ballot_sync(FULL, dw > 0.0), be = __ballot_sync(FULL, dw < 0.0); \
+                            const unsigned ze = __ballot_sync(FULL, dw == 0.0);                                  \
+                            const int sp = nlim - kw;                                                            \
+                            const unsigned vis = (sp >= 32 ? FULL : sp <= 0 ? 0u : (1u << sp) - 1u) & ~1u;       \
+                            const bool here = ((ab << 1) & be & vis) != 0u || kw + 32 >= nlim;                   \
+                            stop |= here ? 1u << w : 0u;                                                         \
+                            oddf |= ((((be << 1) & ab) | ze) & vis) != 0u ? 1u << w : 0u;                        \
+                        }                                                                                        \
+                        const int nskip = stop ? __ffs(stop) - 1 : 4; /* whole windows without an event */       \
+                        bad |= oddf & ((1u << nskip) - 1u);                                                      \
+                        kb += 31 * nskip;                                                                        \
+                        if (stop) break;                                                                         \
+                    }                                                                                            \
                 } else { /* the row below ended on the last step of this window: move on (kb + lo is unchanged) */ \
                     kb += 31, lo -= 31;                                                                          \
                 }                                                                                                \
+                kk4 = min(kb + lane, k_last) * PATH_ROWS;                                                        \
                 t_cur = te[min(kb + lane, k_last)];                                                              \
-                ATMRT_BITS_WINDOW(ybase)                                                                         \
+                cur = *reinterpret_cast<const double4*>(pg + kk4);                                               \
+                ATMRT_BITS_M4()                                                                                  \
             }                                                                                                    \
         }                                                                                                        \
     }
@@ -1822,15 +1743,17 @@ __global__ void __launch_bounds__(32 * BITS_WARPS, MIN_BLOCKS) k_sweep_bits(cons
         if (finished) {
             // The first row that sees only sky scanned to the end, and no row above it can cross any more (no path is
             // longer than n_t). All of them at once.
-            for (int yy = ybase - 1 - lane; yy >= 0; yy -= 32) hit[yy] = 0;
+            for (int yy = ybase - 1 - lane; yy >= y_lo; yy -= 32) hit[yy] = 0;
         }
     }
-#undef ATMRT_BITS_WINDOW
+#undef ATMRT_BITS_M4
     flagged = flagged || bad != 0u;
     if (lane0) {
-        L.count[xl] = (int)(lp - list);
-        B.sweep_col[xl] = flagged ? 1 : 0;
-        if (flagged) atomicOr(B.sweep_flags + 1, 1u);  // some column needs the brute-force march
+        L.count[(size_t)xl * L.bands + band] = cnt;
+        if (flagged) {
+            B.sweep_col[xl] = 1;              // (zeroed before the launch; every band that flags writes the same 1)
+            atomicOr(B.sweep_flags + 1, 1u);  // some column needs the brute-force march
+        }
     }
 }
 
@@ -1838,11 +1761,12 @@ __global__ void __launch_bounds__(32 * BITS_WARPS, MIN_BLOCKS) k_sweep_bits(cons
 template <int W>
 __global__ void __launch_bounds__(128) k_hit_normals(const __grid_constant__ DevScene S, DevBuffers B, SweepLists L, int parts) {
     if (B.sweep_flags[0] != 0) return;
-    const int xl = blockIdx.x / parts, part = blockIdx.x % parts;
+    const int seg = blockIdx.x / parts, part = blockIdx.x % parts;  // seg = column * bands + band
+    const int xl = seg / L.bands;
     if (B.sweep_col[xl] != 0) return;  // flagged columns belong to the brute-force march
-    const int cnt = L.count[xl];
-    const int* __restrict__ list = L.list + (size_t)xl * L.cap;
-    double* __restrict__ out = L.normals + (size_t)xl * L.cap * 3;
+    const int cnt = L.count[seg];
+    const int* __restrict__ list = L.list + (size_t)seg * L.cap;
+    double* __restrict__ out = L.normals + (size_t)seg * L.cap * 3;
     for (int s = part * 128 + threadIdx.x; s < cnt; s += parts * 128) {
         const int smp = list[s];
         const size_t ti = (size_t)xl * S.n_pad + smp;
@@ -1887,8 +1811,9 @@ __global__ void __launch_bounds__(32 * TILE_COLS, 4) k_shade_tiles(const __grid_
     int consumed = nlim > 0 ? nlim - 1 : 0;
     if (hit) {
         const int s = slot1 - 1;
-        const int kh = L.list[(size_t)xx * L.cap + s];
-        const double* __restrict__ nr = L.normals + ((size_t)xx * L.cap + s - 1) * 3;  // slots s - 1, s: samples kh - 1, kh
+        const size_t seg = ((size_t)xx * L.bands + yy / L.band_rows) * L.cap;  // the lists of this pixel's band
+        const int kh = L.list[seg + s];
+        const double* __restrict__ nr = L.normals + (seg + s - 1) * 3;  // slots s - 1, s: samples kh - 1, kh
         const V3 n0{nr[0], nr[1], nr[2]}, n1{nr[3], nr[4], nr[5]};
         const size_t ti = (size_t)xx * S.n_pad + kh;
         const size_t p1 = path_index(n_t, kh, yy), p0 = p1 - PATH_ROWS;

@@ -52,6 +52,7 @@ def _load():
         "atmrt_render_trace": (C.c_int, [vp, vp, vp, C.c_int]),
         "atmrt_pixel_angles": (C.c_int, [vp, vp, vp]),
         "atmrt_set_march_mode": (C.c_int, [vp, C.c_int]),
+        "atmrt_set_sweep_bands": (C.c_int, [vp, C.c_int]),
         "atmrt_get_terrain_profile": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, P(C.c_int)]),
         "atmrt_get_path": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, P(C.c_int)]),
         "atmrt_atmosphere_probe": (C.c_int, [vp, vp, C.c_int, vp, vp, vp]),
@@ -62,6 +63,17 @@ def _load():
         "atmrt_refraction_table": (C.c_int, [vp, C.c_double, vp, C.c_int, P(C.c_int), P(C.c_int), P(C.c_double), P(C.c_double), P(C.c_int), P(C.c_int)]),
         "atmrt_observer_altitude": (C.c_int, [vp, P(C.c_double)]),
         "atmrt_fp64_peak": (C.c_int, [vp, P(C.c_double), P(C.c_double)]),
+        "atmrt_group_create": (C.c_int, [P(C.c_int), C.c_int, P(vp)]),
+        "atmrt_group_destroy": (None, [vp]),
+        "atmrt_group_last_error": (C.c_char_p, [vp]),
+        "atmrt_group_size": (C.c_int, [vp]),
+        "atmrt_group_column_block": (C.c_int, [vp, C.c_int, C.c_int, P(C.c_int), P(C.c_int)]),
+        "atmrt_group_set_terrain": (C.c_int, [vp, P(abi.TileDesc), C.c_int, P(vp)]),
+        "atmrt_group_set_params": (C.c_int, [vp, P(abi.Params)]),
+        "atmrt_group_set_objects": (C.c_int, [vp, P(abi.Object), C.c_int, P(vp)]),
+        "atmrt_group_render": (C.c_int, [vp, vp, vp, vp, P(abi.Stats)]),
+        "atmrt_host_alloc": (vp, [C.c_size_t]),
+        "atmrt_host_free": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
@@ -183,6 +195,9 @@ class Context:
                 ptrs[i] = t.ctypes.data
         self._check(lib.atmrt_set_objects(self._h, arr, n, ptrs))
 
+    def set_sweep_bands(self, bands):
+        self._check(lib.atmrt_set_sweep_bands(self._h, int(bands)))
+
     def set_march_mode(self, mode):
         self._check(lib.atmrt_set_march_mode(self._h, int(mode)))
 
@@ -298,6 +313,102 @@ class Context:
         a, b = C.c_double(), C.c_double()
         self._check(lib.atmrt_fp64_peak(self._h, C.byref(a), C.byref(b)))
         return {"dfma_gflops": a.value, "dadd_ginstr": b.value}
+
+
+def host_array(shape, dtype):
+    """A numpy array in page-locked host memory visible to every GPU (atmrt_host_alloc); freed with the array."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = lib.atmrt_host_alloc(max(n, 1))
+    if not p:
+        raise MemoryError("atmrt_host_alloc failed")
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            lib.atmrt_host_free(self.ptr)
+
+    buf = (C.c_char * max(n, 1)).from_address(p)
+    buf._owner = _Owner(p)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+class Group:
+    """One panorama over several GPUs of this box in ONE process (``atmrt_group``): column blocks, one context and one
+    host thread per GPU; terrain uploaded in slices and all-gathered over the peer links; every GPU writes its block
+    straight into the host's row-major image over its own PCIe link."""
+
+    def __init__(self, n, devices=None):
+        h = C.c_void_p()
+        dev = None if devices is None else (C.c_int * n)(*devices)
+        rc = lib.atmrt_group_create(dev, int(n), C.byref(h))
+        if rc != 0:
+            raise AtmrtError(rc, (lib.atmrt_group_last_error(None) or b"").decode())
+        self._h = h
+        self.n = n
+        self.params = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.atmrt_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise AtmrtError(rc, (lib.atmrt_group_last_error(self._h) or b"").decode())
+
+    def column_block(self, width, i):
+        a, b = C.c_int(), C.c_int()
+        self._check(lib.atmrt_group_column_block(self._h, int(width), int(i), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_terrain(self, terrain):
+        descs, ptrs, n = terrain.c_arrays()
+        self._check(lib.atmrt_group_set_terrain(self._h, descs, n, ptrs))
+
+    def set_params(self, params):
+        self._check(lib.atmrt_group_set_params(self._h, C.byref(params)))
+        self.params = params
+
+    def set_objects(self, objects, textures=None):
+        n = len(objects)
+        arr = (abi.Object * max(n, 1))()
+        ptrs = (C.c_void_p * max(n, 1))()
+        keep = []
+        for i, o in enumerate(objects):
+            arr[i] = o
+            t = None if textures is None else textures[i]
+            if t is not None:
+                t = np.ascontiguousarray(t, dtype=np.uint8)
+                keep.append(t)
+                ptrs[i] = t.ctypes.data
+        self._check(lib.atmrt_group_set_objects(self._h, arr, n, ptrs))
+
+    def render(self, rgb=True, meta=True, steps=True, out=None):
+        """The full image (all column blocks) in host memory; ``out`` may carry preallocated arrays (host_array)."""
+        p = self.params
+        h, w = p.height, p.width
+        out = out or {}
+        a_rgb = out.get("rgb") if rgb else None
+        a_meta = out.get("meta") if meta else None
+        a_steps = out.get("steps") if steps else None
+        if rgb and a_rgb is None:
+            a_rgb = host_array((h, w, 3), np.uint8)
+        if meta and a_meta is None:
+            a_meta = host_array((h, w), META_DTYPE)
+        if steps and a_steps is None:
+            a_steps = host_array((h, w), np.int32)
+        st = abi.Stats()
+        self._check(lib.atmrt_group_render(self._h, _ptr(a_rgb), _ptr(a_meta), _ptr(a_steps), C.byref(st)))
+        return {"rgb": a_rgb, "meta": a_meta, "steps": a_steps, "stats": st.as_dict()}
 
 
 class FastGenerator:

@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--cpu-stride", type=int, default=0, help="column/row stride of the bounded CPU sample (0 = auto)")
     ap.add_argument("--generator", default="Fast", choices=["Fast", "Rectilinear"],
                     help="output.generator of the workload (diagnosis; the BASELINE configs use the default Fast generator)")
+    ap.add_argument("--emulate-ranks", type=int, default=0,
+                    help="diagnosis on ONE GPU: render only rank 0's column block of an N-rank frame (what each GPU of an N-GPU run does, without the exchange)")
+    ap.add_argument("--sweep-bands", type=int, default=0, help="row bands of the horizon sweep (0 = automatic; tuning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -247,10 +250,13 @@ def run_b200(args):
 
     cfg, params, terrain, objects, textures = build_workload(args.workload, args.scale, rank == 0, args.generator)
     my = parallel.shard_params(params, rank, world)
+    if args.emulate_ranks > 1 and world == 1:
+        my = parallel.shard_params(params, 0, args.emulate_ranks)
     wl, H, W = my.x1 - my.x0, params.height, params.width
 
     ctx = runtime.Context(local)
     ctx.set_march_mode(args.march_mode)
+    ctx.set_sweep_bands(args.sweep_bands)
     # terrain: rank 0 uploads + retiles, everyone receives the packed copy over NCCL (once, untimed)
     nbytes = ctx.packed_bytes(terrain)
     packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -303,61 +309,54 @@ def run_b200(args):
     # broadcast, render, gather to rank 0, image (and, when the workload says --output-meta, the
     # per-pixel metadata) back to host memory. Reported twice: as the workload's CLI line produces it
     # (`e2e`) and with the 32 B/pixel metadata always read back (`e2e_with_meta`).
-    e2e = e2e_meta = None
+    e2e = e2e_meta = e2e_gen = None
     if not args.no_e2e:
-        host_rgb = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
-        host_meta = torch.empty((H, W, 4), dtype=torch.float64).pin_memory() if rank == 0 else None
-        if rank == 0:  # decoded tiles staged in pinned memory, as a host that just decoded them would hold them
-            pinned = [torch.from_numpy(p).pin_memory() for _, p in terrain.tiles]
-            terrain_pinned = runtime.Terrain([(d, t_.numpy()) for (d, _), t_ in zip(terrain.tiles, pinned)])
-
-        host_rgb_np = host_rgb.numpy() if rank == 0 else None
-        host_meta_np = host_meta.numpy() if rank == 0 else None
-
-        def e2e_step(with_meta):
-            if world == 1:
-                # one GPU: the library's host-buffer call (atmrt_render) -- the image leaves in row bands while
-                # the remaining bands are still being shaded
-                ctx.pack_terrain(terrain_pinned, packed.data_ptr())  # H2D + retile
-                ctx.render(rgb=True, meta=with_meta, steps=False, out={"rgb": host_rgb_np, "meta": host_meta_np})
-                return
-            if rank == 0:
-                ctx.pack_terrain(terrain_pinned, packed.data_ptr())  # H2D + retile
-            parallel.broadcast_terrain(packed)
-            ctx.render_device(rgb.data_ptr(), meta.data_ptr(), 0, stream)
-            full_rgb = parallel.gather_columns(rgb, W)
-            if rank == 0:
-                host_rgb.copy_(full_rgb, non_blocking=True)
-            if with_meta:
-                full_meta = parallel.gather_columns(meta, W)
-                if rank == 0:
-                    host_meta.copy_(full_meta, non_blocking=True)
-            torch.cuda.synchronize()
-
-        def e2e_time(with_meta):
-            e2e_steps = max(1, min(args.steps, 3))
-            e2e_step(with_meta)
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                e2e_step(with_meta)
-            barrier()
-            dt = (time.perf_counter() - t0) / e2e_steps
-            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = tt.item()
-            return {"value": W * H / dt, "unit": "pixels/s", "h2d_bytes_per_step": int(terrain.bytes),
-                    "d2h_bytes_per_step": int(W * H * 3 + (W * H * 32 if with_meta else 0)), "ms_per_step": dt * 1e3, "steps": e2e_steps,
-                    "api": ("Context.pack_terrain (H2D + retile) + Context.render (atmrt_render: host buffers out, rgb"
-                            if world == 1 else "Context.pack_terrain (H2D + retile) + broadcast + render_device + gather_columns + D2H of rgb")
-                           + (" and per-pixel metadata" if with_meta else "") + (")" if world == 1 else "")}
-
-        wants_meta = bool(cfg["output"].get("file_metadata"))
-        e2e_meta = e2e_time(True)
-        e2e = e2e_meta if wants_meta else e2e_time(False)
+        # What `atm-raytracer gen --gpus N` does between the decoded tiles and the image: ONE process drives the N GPUs of
+        # the box through the library's group API (atmrt_group_*: one context and one host thread per GPU). Every step
+        # uploads the decoded DTED tiles from page-locked host memory -- each GPU a slice over its own PCIe link, the
+        # slices all-gathered over NVLink -- retiles, renders the column blocks and lands every block in the host's
+        # row-major image (and metadata) over each GPU's own link. Under torchrun rank 0 is that process; the other
+        # ranks stand by at the barrier with their GPUs idle.
+        del rgb, meta
+        torch.cuda.empty_cache()
+        barrier()
         if rank == 0:
-            assert host_rgb.numpy().any()
+            group = runtime.Group(world)
+            tiles_pinned = []
+            for d, posts in terrain.tiles:
+                a = runtime.host_array(posts.shape, np.int16)
+                a[...] = posts
+                tiles_pinned.append((d, a))
+            terrain_pinned = runtime.Terrain(tiles_pinned)
+            group.set_params(params)
+            group.set_objects(objects, textures)
+            host = {"rgb": runtime.host_array((H, W, 3), np.uint8), "meta": runtime.host_array((H, W), runtime.META_DTYPE)}
+
+            def e2e_time(with_meta):
+                e2e_steps = max(1, min(args.steps, 3))
+
+                def one():
+                    group.set_terrain(terrain_pinned)  # H2D of the decoded tiles (sliced) + retile + all-gather
+                    group.render(rgb=True, meta=with_meta, steps=False, out=host)
+
+                one()
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    one()
+                dt = (time.perf_counter() - t0) / e2e_steps
+                return {"value": W * H / dt, "unit": "pixels/s", "h2d_bytes_per_step": int(terrain.bytes),
+                        "d2h_bytes_per_step": int(W * H * 3 + (W * H * 32 if with_meta else 0)), "ms_per_step": dt * 1e3, "steps": e2e_steps,
+                        "api": f"atmrt_group_set_terrain + atmrt_group_render on {world} GPU(s) from one process (the path of `atm-raytracer gen --gpus {world}`): "
+                               "decoded tiles in page-locked host memory in, rgb" + (" and per-pixel metadata" if with_meta else "") + " in page-locked host memory out"}
+
+            wants_meta = bool(cfg["output"].get("file_metadata"))
+            e2e_meta = e2e_time(True)
+            e2e = e2e_meta if wants_meta else e2e_time(False)
+            assert host["rgb"].any()
+            group.close()
+            if world == 1:
+                e2e_gen = time_gen_executable()
+        barrier()
 
     if rank != 0:
         if world > 1:
@@ -394,6 +393,7 @@ def run_b200(args):
         "clocks": clocks.summary(),
         "e2e": e2e,
         "e2e_with_meta": e2e_meta,
+        "e2e_gen": e2e_gen,
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roof,
         "roofline_stages": {k: {f: v[f] for f in ("kernel", "achieved", "peak", "frac", "unit", "launch_ms", "units_per_launch", "traffic", "ncu")}
@@ -405,6 +405,37 @@ def run_b200(args):
     emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_gen_executable():
+    """Wall time of the `atm-raytracer gen` executable on BASELINE config 2 (1920x1080, 2x2 DTED tiles on disk, with
+    --output-meta): process start, CUDA initialisation, DTED decode, upload, render, PNG encode and the metadata sidecar --
+    everything SURVEY section 8d(ii) counts as end-to-end `gen`. The executable's own stage stamps are reported next to it."""
+    import re
+    import subprocess
+    import tempfile
+
+    from atm_raytracer_b200 import host, synth
+
+    with tempfile.TemporaryDirectory() as tmp:
+        folder = os.path.join(tmp, "terrain")
+        os.mkdir(folder)
+        synth.write_tile_grid(folder, 45, 5, 2, 2, level=1)
+        png, dat = os.path.join(tmp, "out.png"), os.path.join(tmp, "out.dat")
+        argv = [host.EXECUTABLE, "gen", "-t", folder, "-l", "45.05", "-g", "6.0", "-a", "1800", "-d", "0", "-f", "10", "-m", "200", "--step", "50",
+                "-w", "1920", "-h", "1080", "--output", png, "--output-meta", dat]
+        best, stamps = None, {}
+        for _ in range(2):
+            t0 = time.perf_counter()
+            r = subprocess.run(argv, capture_output=True, text=True)
+            dt = time.perf_counter() - t0
+            if r.returncode != 0:
+                return {"error": r.stderr.strip()[-300:]}
+            if best is None or dt < best:
+                best = dt
+                stamps = {m.group(2).strip(" ."): float(m.group(1)) for m in re.finditer(r"^([0-9.]+): ([A-Za-z ]+)", r.stdout, re.M)}
+        return {"workload": "c2 via `atm-raytracer gen` (CLI flags, DTED L1 files on disk -> PNG + metadata sidecar)", "wall_s": best,
+                "pixels_per_s": 1920 * 1080 / best, "stage_stamps_s": stamps, "png_bytes": os.path.getsize(png), "meta_bytes": os.path.getsize(dat)}
 
 
 def roofline(stage, ms, units, params, fp, args):

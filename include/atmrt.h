@@ -241,6 +241,10 @@ int atmrt_render_trace(atmrt_ctx* ctx, atmrt_trace_point* points, int32_t* count
  * step like the reference loop (validation); 2 = hierarchical march always (validation of the sweep).
  * All three produce identical images. */
 int atmrt_set_march_mode(atmrt_ctx* ctx, int mode);
+/* Horizon sweep: the number of row bands a column is walked in (0 = automatic: enough bands that a narrow column
+ * block still fills the GPU; clamped to bands of at least 128 rows). Every value gives the same image (tuning and
+ * validation hook). */
+int atmrt_set_sweep_bands(atmrt_ctx* ctx, int bands);
 /* Ray-path stage: 0 (default) g(h) from the table, macro steps of 8 steps where g is smooth and the
  * reference's single steps across the starts of the temperature functions; 1 every evaluation through
  * libm, op for op the oracle's arithmetic, single steps (validation); 2 the table, single steps only
@@ -286,6 +290,26 @@ int atmrt_refraction_table(const atmrt_atmosphere_def* def, double wavelength, d
 int atmrt_observer_altitude(atmrt_ctx* ctx, double* alt);
 /* FP64 FMA throughput micro-benchmark (roofline denominator): returns GFLOP/s (2 flop per FMA). */
 int atmrt_fp64_peak(atmrt_ctx* ctx, double* gflops, double* dadd_ginstr);
+
+/* ---- one panorama over the GPUs of a box, in one process (generator/mod.rs:47-99 on several GPUs) ----------------
+ * The panorama shards by contiguous column blocks [i W / n, (i + 1) W / n), one context per GPU and one host thread per
+ * context. group_set_terrain uploads and retiles a slice of the tiles on every GPU and all-gathers the slices over the
+ * peer links (NVLink); group_render writes every GPU's block straight into the row-major host buffers of the FULL image
+ * (rgb[H][W][3], meta[H][W], steps[H][W]; any may be NULL), each GPU over its own PCIe link -- allocate them with
+ * atmrt_host_alloc for asynchronous copies. x0 / x1 of the params are ignored. */
+typedef struct atmrt_group atmrt_group;
+int atmrt_group_create(const int* devices /* NULL: 0..n-1 */, int n, atmrt_group** out);
+void atmrt_group_destroy(atmrt_group* g);
+const char* atmrt_group_last_error(const atmrt_group* g); /* g may be NULL: last create() error */
+int atmrt_group_size(const atmrt_group* g);
+int atmrt_group_column_block(const atmrt_group* g, int width, int i, int* x0, int* x1);
+int atmrt_group_set_terrain(atmrt_group* g, const atmrt_tile_desc* tiles, int ntiles, const int16_t* const* posts);
+int atmrt_group_set_params(atmrt_group* g, const atmrt_params* params);
+int atmrt_group_set_objects(atmrt_group* g, const atmrt_object* objects, int nobjects, const uint8_t* const* rgba_textures);
+int atmrt_group_render(atmrt_group* g, uint8_t* rgb, atmrt_meta* meta, int32_t* steps, atmrt_stats* stats);
+/* Page-locked host memory visible to every GPU (the host image / metadata / decoded tiles). */
+void* atmrt_host_alloc(size_t bytes);
+void atmrt_host_free(void* p);
 
 #ifdef __cplusplus
 }

@@ -346,6 +346,31 @@ def test_march_variants_are_bit_identical(ctx, name, scale):
     assert out[0]["stats"]["pixels_hit"] > 0
 
 
+@pytest.mark.parametrize("name,scale", [("c2", 0.5), ("c3_flat", 0.25), ("c1", 1.0)])
+def test_sweep_row_bands_are_bit_identical(ctx, name, scale):
+    """The horizon sweep walks a column in row bands (what keeps a narrow column block of an 8-GPU frame busy): a band
+    enters the walk in the state the row below it leaves behind, found by scanning that one row. Any number of bands
+    must give the image of the single walk -- and of the brute-force march, bit for bit."""
+    p, terrain, _, _ = scene(name, scale)
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects([])
+    out = {}
+    try:
+        ctx.set_march_mode(1)
+        brute = ctx.render()
+        ctx.set_march_mode(0)
+        for bands in (1, 2, 3, 64):  # (64: clamped to bands of 128 rows)
+            ctx.set_sweep_bands(bands)
+            out[bands] = ctx.render()
+    finally:
+        ctx.set_sweep_bands(0)
+        ctx.set_march_mode(0)
+    for bands, r in out.items():
+        _same_render(r, brute)
+    assert brute["stats"]["pixels_hit"] > 0.2 * p.width * p.height
+
+
 def test_sweep_falls_back_when_rays_cross(ctx, oracle_lib):
     """A strong temperature inversion (duct) bends rays back down and makes neighbouring rays cross: the
     path cache is no longer monotone in the row, k_path_check says so on the device and the general
@@ -458,6 +483,38 @@ def test_pixel_angles_match_oracle(ctx, oracle_lib, name, direction, fov, rect):
     el2, az2 = ctx.pixel_angles()
     np.testing.assert_array_equal(az2, az[:, q.x0:q.x1])
     np.testing.assert_array_equal(el2, el[:, q.x0:q.x1])
+
+
+@pytest.mark.parametrize("name,scale,n", [("c4", 0.1, 3), ("c2", 0.25, 2), ("c1", 0.5, 1)])
+def test_group_of_contexts_equals_single_render(ctx, name, scale, n):
+    """atmrt_group_* (one process, one context and one host thread per GPU; here all of them on GPU 0): the tiles are
+    uploaded in slices and all-gathered with peer copies, every context renders its column block and writes it straight
+    into the full row-major host image. The result must be the single-context render, byte for byte."""
+    p, terrain, objects, textures = scene(name, scale)
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects(objects, textures)
+    want = ctx.render()
+    g = runtime.Group(n, devices=[0] * n)
+    try:
+        assert [g.column_block(p.width, i) for i in range(n)] == [(i * p.width // n, (i + 1) * p.width // n) for i in range(n)]
+        g.set_terrain(terrain)
+        g.set_params(p)
+        g.set_objects(objects, textures)
+        got = g.render()
+        again = g.render(steps=False, meta=False)  # a second frame on the same group; terrain re-uploaded in between
+        g.set_terrain(terrain)
+        third = g.render(steps=False, meta=False)
+    finally:
+        g.close()
+    np.testing.assert_array_equal(got["rgb"], want["rgb"])
+    np.testing.assert_array_equal(got["steps"], want["steps"])
+    for f in ("lat", "lon", "elevation", "distance"):
+        np.testing.assert_array_equal(got["meta"][f], want["meta"][f])
+    for f in ("ray_steps", "trace_points", "pixels_hit"):
+        assert got["stats"][f] == want["stats"][f]
+    np.testing.assert_array_equal(again["rgb"], want["rgb"])
+    np.testing.assert_array_equal(third["rgb"], want["rgb"])
 
 
 def test_fog_simple_colouring_and_relative_altitude(ctx, oracle_lib):
