@@ -144,6 +144,13 @@ class StageMs(C.Structure):
                 ("renders", C.c_int32), ("_pad", C.c_int32)]
 
 
+KERNEL_COUNT = 8
+
+
+class KernelMs(C.Structure):
+    _fields_ = [("ms", C.c_double * KERNEL_COUNT), ("renders_with", C.c_int32 * KERNEL_COUNT), ("renders", C.c_int32), ("_pad", C.c_int32)]
+
+
 def us_76() -> AtmosphereDef:
     """``AtmosphereDef::us_76()`` of the external atm-refraction crate (params.rs:453): US Standard
     Atmosphere 1976 temperature layers up to 84.852 km, sea-level fixed points 288.15 K / 101325 Pa."""

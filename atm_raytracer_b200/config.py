@@ -257,7 +257,9 @@ def lower_objects(cfg, cwd="."):
         o.longitude = float(pos.get("longitude", 0.0))
         o.altitude = _altitude(pos.get("altitude", {"Relative": 1.0}))
         kind, val = _tagged(node["shape"], "shape")
-        col = node.get("color", {"r": 1.0, "g": 1.0, "b": 1.0})
+        if "color" not in node:  # `color` has no serde default (object/mod.rs:158-163): the reference rejects the config
+            raise ConfigError("object needs a color")
+        col = node["color"]
         o.color[0], o.color[1], o.color[2] = float(col["r"]), float(col["g"]), float(col["b"])
         o.color[3] = float(col.get("a", 1.0))
         tex = None

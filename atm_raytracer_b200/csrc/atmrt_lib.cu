@@ -44,9 +44,12 @@ struct atmrt_ctx {
     // whole timed region of asynchronous renders can be averaged without synchronising inside it.
     struct StageEvents {
         cudaEvent_t a0, a1, b0, b1, c0, c1, t0, t1;
+        cudaEvent_t k0[ATMRT_KERNEL_COUNT], k1[ATMRT_KERNEL_COUNT];  // around the hot kernels (atmrt_kernel_times)
+        unsigned kmask;                                             // which of them this render launched
     };
+    static constexpr size_t RING = 64;  // renders kept for the averages: the oldest is overwritten
     std::vector<StageEvents> ring;
-    size_t ring_used = 0;
+    size_t ring_next = 0, ring_used = 0;
     cudaEvent_t t_0 = nullptr, t_1 = nullptr;  // fp64 micro-benchmark
     int num_sms = 148;
 
@@ -758,7 +761,7 @@ int copy_rows_to_host(atmrt_ctx* ctx, const RenderTargets& rt, int wl, int r0, i
 // The ray-path stage with macro steps, as chain + elements (kernels.cuh): as many simulation steps per macro step as keep
 // it within MACRO_MAX_METRES (16 at 25 or 50 m; fewer for coarser simulation steps, none above 400 m).
 template <bool FLAT>
-int launch_macro_paths(atmrt_ctx* ctx, const DevScene& S, const DevBuffers& B, int h) {
+int launch_macro_paths(atmrt_ctx* ctx, const DevScene& S, const DevBuffers& B, int h, atmrt_ctx::StageEvents* E) {
     int macro_steps = 0;
     for (int m : {16, 8, 4, 2})
         if (macro_steps == 0 && (double)m * S.step <= MACRO_MAX_METRES) macro_steps = m;
@@ -773,27 +776,44 @@ int launch_macro_paths(atmrt_ctx* ctx, const DevScene& S, const DevBuffers& B, i
     if (!rc) rc = ensure(ctx, ctx->d_rec_n, sizeof(int) * (size_t)h);
     if (rc) return rc;
     R.ab = (double2*)ctx->d_rec_ab.p, R.em = (int2*)ctx->d_rec_em.p, R.n = (int*)ctx->d_rec_n.p;
+    CUDA_TRY(ctx, cudaEventRecord(E->k0[ATMRT_KERNEL_RAY_CHAIN], ctx->s_b));
     k_ray_chain<FLAT><<<(h + CHAIN_THREADS - 1) / CHAIN_THREADS, CHAIN_THREADS, 0, ctx->s_b>>>(S, B, R, macro_steps);
+    CUDA_TRY(ctx, cudaEventRecord(E->k1[ATMRT_KERNEL_RAY_CHAIN], ctx->s_b));
+    CUDA_TRY(ctx, cudaEventRecord(E->k0[ATMRT_KERNEL_RAY_ELEMENTS], ctx->s_b));
     k_ray_elements<FLAT><<<h, ELEM_THREADS, 0, ctx->s_b>>>(S, B, R);
+    CUDA_TRY(ctx, cudaEventRecord(E->k1[ATMRT_KERNEL_RAY_ELEMENTS], ctx->s_b));
+    E->kmask |= 1u << ATMRT_KERNEL_RAY_CHAIN | 1u << ATMRT_KERNEL_RAY_ELEMENTS;
     ctx->launches++;
     return 0;
 }
 
 // Launch the whole render on (s_a || s_b) -> main. Asynchronous.
 int next_stage_events(atmrt_ctx* ctx, atmrt_ctx::StageEvents** out) {
-    if (ctx->ring_used == ctx->ring.size()) {
-        if (ctx->ring.size() >= 4096) {  // nobody is harvesting: recycle
-            ctx->ring_used = 0;
-        } else {
-            atmrt_ctx::StageEvents e{};
-            cudaEvent_t* evs[] = {&e.a0, &e.a1, &e.b0, &e.b1, &e.c0, &e.c1, &e.t0, &e.t1};
-            for (cudaEvent_t* ev : evs) CUDA_TRY(ctx, cudaEventCreate(ev));
-            ctx->ring.push_back(e);
+    if (ctx->ring.size() < atmrt_ctx::RING) {
+        atmrt_ctx::StageEvents e{};
+        cudaEvent_t* evs[] = {&e.a0, &e.a1, &e.b0, &e.b1, &e.c0, &e.c1, &e.t0, &e.t1};
+        for (cudaEvent_t* ev : evs) CUDA_TRY(ctx, cudaEventCreate(ev));
+        for (int i = 0; i < ATMRT_KERNEL_COUNT; ++i) {
+            CUDA_TRY(ctx, cudaEventCreate(&e.k0[i]));
+            CUDA_TRY(ctx, cudaEventCreate(&e.k1[i]));
         }
+        ctx->ring.push_back(e);
     }
-    *out = &ctx->ring[ctx->ring_used++];
+    atmrt_ctx::StageEvents* E = &ctx->ring[ctx->ring_next % atmrt_ctx::RING];
+    E->kmask = 0u;
+    ctx->ring_next++;
+    ctx->ring_used = std::min(ctx->ring_used + 1, atmrt_ctx::RING);
+    *out = E;
     return 0;
 }
+
+// events around one hot kernel (or one group of launches of it) of this render
+#define KT_BEGIN(id, st)                                     \
+    {                                                        \
+        CUDA_TRY(ctx, cudaEventRecord(E->k0[id], st));       \
+        E->kmask |= 1u << (id);                              \
+    }
+#define KT_END(id, st) CUDA_TRY(ctx, cudaEventRecord(E->k1[id], st));
 
 int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
     const DevScene& S = ctx->scene;
@@ -820,6 +840,7 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         for (cudaEvent_t ev : marks) CUDA_TRY(ctx, cudaEventRecord(ev, main));
         const dim3 grid((wl + RECT_THREADS - 1) / RECT_THREADS, h);
         const int libm = ctx->path_mode == 1 ? 1 : 0;
+        KT_BEGIN(ATMRT_KERNEL_RECTILINEAR, main)
         if (S.flat) {
             if (S.nobjects > 0) k_rectilinear<true, true><<<grid, RECT_THREADS, 0, main>>>(S, B, O, libm);
             else k_rectilinear<true, false><<<grid, RECT_THREADS, 0, main>>>(S, B, O, libm);
@@ -827,6 +848,7 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
             if (S.nobjects > 0) k_rectilinear<false, true><<<grid, RECT_THREADS, 0, main>>>(S, B, O, libm);
             else k_rectilinear<false, false><<<grid, RECT_THREADS, 0, main>>>(S, B, O, libm);
         }
+        KT_END(ATMRT_KERNEL_RECTILINEAR, main)
         ctx->launches++;
         CUDA_TRY(ctx, cudaEventRecord(E->c1, main));
         CUDA_TRY(ctx, cudaEventRecord(E->t1, main));
@@ -856,11 +878,11 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         } else if (S.flat) {
             if (ctx->path_mode == 1) k_ray_paths<true, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
             else if (ctx->path_mode == 2) k_ray_paths<true, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
-            else if ((rc = launch_macro_paths<true>(ctx, S, B, h))) return rc;
+            else if ((rc = launch_macro_paths<true>(ctx, S, B, h, E))) return rc;
         } else {
             if (ctx->path_mode == 1) k_ray_paths<false, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
             else if (ctx->path_mode == 2) k_ray_paths<false, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
-            else if ((rc = launch_macro_paths<false>(ctx, S, B, h))) return rc;
+            else if ((rc = launch_macro_paths<false>(ctx, S, B, h, E))) return rc;
         }
         ctx->launches++;
     }
@@ -887,8 +909,10 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         k_walk_anchors<<<dim3((S.n_anchor + 127) / 128, wl), 128, 0, ctx->s_a>>>(S, B);
         ctx->launches++;
     }
+    KT_BEGIN(ATMRT_KERNEL_TERRAIN_PROFILE, ctx->s_a)
     if (S.earth.walker == WALK_SPHERICAL) k_terrain_profile<WALK_SPHERICAL><<<dim3((S.n_t + 127) / 128, wl), 128, 0, ctx->s_a>>>(S, ctx->terrain, B, 0);
     else k_terrain_profile<-1><<<dim3((S.n_t + 127) / 128, wl), 128, 0, ctx->s_a>>>(S, ctx->terrain, B, 0);
+    KT_END(ATMRT_KERNEL_TERRAIN_PROFILE, ctx->s_a)
     ctx->launches += 2;
     auto terrain_pyramids = [&](cudaStream_t st, int only_if_not_swept) {
         const long long warps = (long long)wl * S.n2;
@@ -926,12 +950,17 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         if ((rc = ensure(ctx, ctx->d_normals, sizeof(double) * 3 * segs * L.cap))) return rc;
         L.list = (int*)ctx->d_list.p, L.count = (int*)ctx->d_count.p, L.normals = (double*)ctx->d_normals.p;
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_sweep_col.p, 0, (size_t)wl, main));
+        KT_BEGIN(ATMRT_KERNEL_SWEEP, main)
         k_sweep_bits<<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, L.bands), 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl);
+        KT_END(ATMRT_KERNEL_SWEEP, main)
         // enough blocks per (column, band) that a narrow column block still fills the machine
         const int parts = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)ctx->num_sms * 16 + segs - 1) / segs));
+        KT_BEGIN(ATMRT_KERNEL_HIT_NORMALS, main)
         if (S.earth.walker == WALK_SPHERICAL) k_hit_normals<WALK_SPHERICAL><<<(unsigned)(segs * parts), 128, 0, main>>>(S, B, L, parts);
         else k_hit_normals<-1><<<(unsigned)(segs * parts), 128, 0, main>>>(S, B, L, parts);
+        KT_END(ATMRT_KERNEL_HIT_NORMALS, main)
         ctx->launches += 2;
+        KT_BEGIN(ATMRT_KERNEL_SHADE, main)
         const bool to_host = rt.host_rgb || rt.host_meta || rt.host_steps;
         const int nbands = to_host && h >= 256 ? SHADE_BANDS : 1;
         const int band_rows = ((h + nbands - 1) / nbands + 31) / 32 * 32;
@@ -946,6 +975,7 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
                 if ((rc = copy_rows_to_host(ctx, rt, wl, r0, r1, ctx->s_a))) return rc;
             }
         }
+        KT_END(ATMRT_KERNEL_SHADE, main)
         if (to_host) {
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->s_a));
             CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_a, 0));
@@ -962,6 +992,7 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         k_march<false, true, false><<<fgrid, MARCH_THREADS, 0, main>>>(S, B, O, MARCH_FLAGGED_COLUMNS);
         ctx->launches += 2;
     } else {
+        KT_BEGIN(ATMRT_KERNEL_MARCH, main)
 #define ATMRT_LAUNCH_MARCH(OB, BR, TR) k_march<OB, BR, TR><<<grid, MARCH_THREADS, 0, main>>>(S, B, O, MARCH_ALWAYS)
         if (objs) {
             if (brute) { if (trace) ATMRT_LAUNCH_MARCH(true, true, true); else ATMRT_LAUNCH_MARCH(true, true, false); }
@@ -971,6 +1002,7 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
             else       { if (trace) ATMRT_LAUNCH_MARCH(false, false, true); else ATMRT_LAUNCH_MARCH(false, false, false); }
         }
 #undef ATMRT_LAUNCH_MARCH
+        KT_END(ATMRT_KERNEL_MARCH, main)
         ctx->launches++;
     }
     if (timed) {
@@ -1002,7 +1034,7 @@ int collect_stats(atmrt_ctx* ctx, atmrt_stats* stats) {
     for (int v : pn) mx = std::max(mx, v);
     stats->n_path_max = mx;
     if (ctx->ring_used > 0) {
-        const atmrt_ctx::StageEvents& E = ctx->ring[ctx->ring_used - 1];
+        const atmrt_ctx::StageEvents& E = ctx->ring[(ctx->ring_next - 1) % atmrt_ctx::RING];
         cudaEventElapsedTime(&stats->ms_terrain, E.a0, E.a1);
         cudaEventElapsedTime(&stats->ms_paths, E.b0, E.b1);
         cudaEventElapsedTime(&stats->ms_march, E.c0, E.c1);
@@ -1056,7 +1088,7 @@ int atmrt_abi_version(void) { return ATMRT_ABI_VERSION; }
 int atmrt_abi_sizes(size_t* out, int n) {
     const size_t v[] = {sizeof(atmrt_altitude), sizeof(atmrt_atmosphere_def), sizeof(atmrt_params), sizeof(atmrt_tile_desc),
                         sizeof(atmrt_object),   sizeof(atmrt_meta),           sizeof(atmrt_trace_point), sizeof(atmrt_stats),
-                        sizeof(atmrt_stage_ms)};
+                        sizeof(atmrt_stage_ms), sizeof(atmrt_kernel_ms)};
     const int m = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < n && i < m; ++i) out[i] = v[i];
     return m;
@@ -1124,6 +1156,10 @@ void atmrt_destroy(atmrt_ctx* ctx) {
         cudaEvent_t all[] = {e.a0, e.a1, e.b0, e.b1, e.c0, e.c1, e.t0, e.t1};
         for (cudaEvent_t ev : all)
             if (ev) cudaEventDestroy(ev);
+        for (int i = 0; i < ATMRT_KERNEL_COUNT; ++i) {
+            if (e.k0[i]) cudaEventDestroy(e.k0[i]);
+            if (e.k1[i]) cudaEventDestroy(e.k1[i]);
+        }
     }
     if (ctx->s_a) cudaStreamDestroy(ctx->s_a);
     if (ctx->s_b) cudaStreamDestroy(ctx->s_b);
@@ -1448,8 +1484,8 @@ int atmrt_stage_times(atmrt_ctx* ctx, atmrt_stage_ms* out) {
     CUDA_TRY(ctx, cudaDeviceSynchronize());
     memset(out, 0, sizeof(*out));
     double a = 0, b = 0, c = 0, t = 0;
-    for (size_t i = 0; i < ctx->ring_used; ++i) {
-        const atmrt_ctx::StageEvents& E = ctx->ring[i];
+    for (size_t i = 0; i < ctx->ring_used; ++i) {  // the most recent renders (at most RING of them)
+        const atmrt_ctx::StageEvents& E = ctx->ring[(ctx->ring_next - 1 - i) % atmrt_ctx::RING];
         float ms = 0.f;
         CUDA_TRY(ctx, cudaEventElapsedTime(&ms, E.a0, E.a1));
         a += ms;
@@ -1466,6 +1502,33 @@ int atmrt_stage_times(atmrt_ctx* ctx, atmrt_stage_ms* out) {
         out->ms_terrain = a / n, out->ms_paths = b / n, out->ms_march = c / n, out->ms_total = t / n;
     }
     ctx->ring_used = 0;
+    return 0;
+}
+
+const char* atmrt_kernel_name(int i) {
+    static const char* names[ATMRT_KERNEL_COUNT] = {"k_terrain_profile", "k_ray_chain", "k_ray_elements", "k_sweep_bits",
+                                                    "k_hit_normals",     "k_shade_tiles", "k_march",      "k_rectilinear"};
+    return i >= 0 && i < ATMRT_KERNEL_COUNT ? names[i] : "";
+}
+
+int atmrt_kernel_times(atmrt_ctx* ctx, atmrt_kernel_ms* out) {
+    if (!ctx || !out) return fail(ctx, ATMRT_ERR_INVALID, "kernel_times: NULL argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    memset(out, 0, sizeof(*out));
+    for (size_t i = 0; i < ctx->ring_used; ++i) {
+        const atmrt_ctx::StageEvents& E = ctx->ring[(ctx->ring_next - 1 - i) % atmrt_ctx::RING];
+        for (int k = 0; k < ATMRT_KERNEL_COUNT; ++k) {
+            if (!(E.kmask >> k & 1u)) continue;
+            float ms = 0.f;
+            CUDA_TRY(ctx, cudaEventElapsedTime(&ms, E.k0[k], E.k1[k]));
+            out->ms[k] += ms;
+            out->renders_with[k] += 1;
+        }
+    }
+    for (int k = 0; k < ATMRT_KERNEL_COUNT; ++k)
+        if (out->renders_with[k] > 0) out->ms[k] /= (double)out->renders_with[k];
+    out->renders = (int32_t)ctx->ring_used;
     return 0;
 }
 
@@ -1845,6 +1908,25 @@ int atmrt_group_render(atmrt_group* g, uint8_t* rgb, atmrt_meta* meta, int32_t* 
             stats->n_path_max = std::max(stats->n_path_max, st[i].n_path_max);
             stats->ms_terrain = std::max(stats->ms_terrain, st[i].ms_terrain), stats->ms_paths = std::max(stats->ms_paths, st[i].ms_paths);
             stats->ms_march = std::max(stats->ms_march, st[i].ms_march), stats->ms_total = std::max(stats->ms_total, st[i].ms_total);
+        }
+    }
+    return 0;
+}
+
+int atmrt_group_pixel_angles(atmrt_group* g, double* elevation_angle, double* azimuth) {
+    if (!g) return ATMRT_ERR_INVALID;
+    if (!g->has_params) return gfail(g, ATMRT_ERR_STATE, "group_pixel_angles before group_set_params");
+    const int W = g->params.width, H = g->params.height;
+    for (size_t i = 0; i < g->ctx.size(); ++i) {
+        int x0 = 0, x1 = 0;
+        atmrt_group_column_block(g, W, (int)i, &x0, &x1);
+        const size_t wl = (size_t)(x1 - x0);
+        std::vector<double> el(elevation_angle ? wl * H : 0), az(azimuth ? wl * H : 0);
+        const int rc = atmrt_pixel_angles(g->ctx[i], elevation_angle ? el.data() : nullptr, azimuth ? az.data() : nullptr);
+        if (rc) return gfail(g, rc, g->ctx[i]->err);
+        for (int y = 0; y < H; ++y) {
+            if (elevation_angle) memcpy(elevation_angle + (size_t)y * W + x0, el.data() + (size_t)y * wl, sizeof(double) * wl);
+            if (azimuth) memcpy(azimuth + (size_t)y * W + x0, az.data() + (size_t)y * wl, sizeof(double) * wl);
         }
     }
     return 0;

@@ -370,6 +370,7 @@ static void apply_yaml(const Node& doc, Config* c) {
                 if (!pos || !shape) throw std::runtime_error("object needs position and shape");
                 parse_position(*pos, &co.o.latitude, &co.o.longitude, &co.o.altitude);
                 co.o.color[0] = co.o.color[1] = co.o.color[2] = co.o.color[3] = 1.0;
+                if (!on.get("color")) throw std::runtime_error("object needs a color");  // `color` has no serde default (object/mod.rs:158-163)
                 if (const Node* col = on.get("color")) {
                     co.o.color[0] = num(*col, "r", 1.0), co.o.color[1] = num(*col, "g", 1.0), co.o.color[2] = num(*col, "b", 1.0);
                     co.o.color[3] = num(*col, "a", 1.0);  // default_alpha, object/mod.rs:147-156
@@ -506,6 +507,9 @@ static void apply_yaml(const Node& doc, Config* c) {
         for (const char* k : {"ticks", "vertical_ticks"})
             if (const Node* t = out->get(k))
                 if (t->kind == Node::Seq && !t->seq.empty()) fprintf(stderr, "warning: output.%s is ignored (overlays are out of scope)\n", k);
+        for (const char* k : {"show_eye_level", "show_flat_horizon"})
+            if (const Node* t = out->get(k))
+                if (t->kind == Node::Scalar && t->as_bool(k)) fprintf(stderr, "warning: output.%s is ignored (overlays are out of scope)\n", k);
     }
 }
 
@@ -626,22 +630,30 @@ static atmrt_params into_params(const Config& c) {
     return p;
 }
 
-static bool write_metadata(const std::string& path, const atmrt_params& p, const atmrt_meta* meta, size_t npix) {
-    // Own sidecar format (the reference's gzip(bincode(AllData)) depends on serde layouts of external
-    // crates -- SURVEY section 8 f2): gzip of "ATMRTMETA1\n", i32 width, i32 height, then
-    // width*height records of 4 little-endian f64 (lat, lon, elevation, distance; NaN = no hit).
+static bool write_metadata(const std::string& path, const atmrt_params& p, const atmrt_meta* meta, size_t npix, const std::vector<double>& elevation_angle,
+                           const std::vector<double>& azimuth) {
+    // NOT the reference's file: generator/mod.rs:26-45 writes gzip(bincode(AllData{params, result})), and `params` holds
+    // atm_refraction's lowered Atmosphere and Environment, whose serde layout lives in an un-vendored crate (SURVEY section
+    // 8 f2) -- `view` cannot read what is written here. Own documented sidecar, version 2: gzip of
+    //   "ATMRTMETA2\n", i32 width, i32 height, i32 generator (0 Fast, 1 Rectilinear), i32 0,
+    //   ResultPixel.elevation_angle: Fast f64[height] (one per row), Rectilinear f64[height][width]
+    //   ResultPixel.azimuth:         Fast f64[width] (one per column, wrapped into [0, 360)), Rectilinear f64[height][width]
+    //   width * height records of 4 little-endian f64: lat, lon, elevation, distance of the FIRST trace point (NaN = none)
     gzFile f = gzopen(path.c_str(), "wb6");
     if (!f) return false;
-    const char magic[] = "ATMRTMETA1\n";
-    int32_t wh[2] = {p.width, p.height};
-    bool ok = gzwrite(f, magic, sizeof(magic) - 1) > 0 && gzwrite(f, wh, sizeof wh) > 0;
-    const char* data = (const char*)meta;
-    size_t left = npix * sizeof(atmrt_meta);
-    while (ok && left > 0) {
-        unsigned chunk = (unsigned)std::min<size_t>(left, 1u << 30);
-        ok = gzwrite(f, data, chunk) == (int)chunk;
-        data += chunk, left -= chunk;
-    }
+    const char magic[] = "ATMRTMETA2\n";
+    int32_t hdr[4] = {p.width, p.height, p.generator, 0};
+    bool ok = gzwrite(f, magic, sizeof(magic) - 1) > 0 && gzwrite(f, hdr, sizeof hdr) > 0;
+    auto put = [&](const char* data, size_t left) {
+        while (ok && left > 0) {
+            unsigned chunk = (unsigned)std::min<size_t>(left, 1u << 30);
+            ok = gzwrite(f, data, chunk) == (int)chunk;
+            data += chunk, left -= chunk;
+        }
+    };
+    put((const char*)elevation_angle.data(), elevation_angle.size() * sizeof(double));
+    put((const char*)azimuth.data(), azimuth.size() * sizeof(double));
+    put((const char*)meta, npix * sizeof(atmrt_meta));
     return gzclose(f) == Z_OK && ok;
 }
 
@@ -739,7 +751,17 @@ extern "C" int atmrt_host_gen(int argc, const char* const* argv) {
         if (atmrt_host_write_png(c.file.c_str(), rgb, p.width, p.height, 3) != 0) throw std::runtime_error(g_error);
         if (!c.file_metadata.empty()) {
             printf("%.3f: Outputting metadata...\n", t());
-            if (!write_metadata(c.file_metadata, p, meta, npix)) throw std::runtime_error("cannot write " + c.file_metadata);
+            // ResultPixel.elevation_angle / azimuth (fast.rs:67-76, rectilinear.rs:78-116)
+            std::vector<double> el(npix), az(npix);
+            check(atmrt_group_pixel_angles(group, el.data(), az.data()), "atmrt_group_pixel_angles");
+            if (p.generator == ATMRT_GENERATOR_FAST) {  // separable: one elevation per row, one azimuth per column
+                std::vector<double> el_rows((size_t)p.height), az_cols(az.begin(), az.begin() + p.width);
+                for (int y = 0; y < p.height; ++y) el_rows[(size_t)y] = el[(size_t)y * p.width];
+                el.swap(el_rows), az.swap(az_cols);
+            }
+            fprintf(stderr, "note: %s is this host's own sidecar layout (ATMRTMETA2), not the reference's bincode container: `view` cannot read it\n",
+                    c.file_metadata.c_str());
+            if (!write_metadata(c.file_metadata, p, meta, npix, el, az)) throw std::runtime_error("cannot write " + c.file_metadata);
         }
         printf("%.3f: Done.\n", t());
         atmrt_host_free(rgb), atmrt_host_free(meta);

@@ -49,6 +49,8 @@ def _load():
         "atmrt_render": (C.c_int, [vp, vp, vp, vp, P(abi.Stats)]),
         "atmrt_render_device": (C.c_int, [vp, vp, vp, vp, P(abi.Stats), vp]),
         "atmrt_stage_times": (C.c_int, [vp, P(abi.StageMs)]),
+        "atmrt_kernel_times": (C.c_int, [vp, P(abi.KernelMs)]),
+        "atmrt_kernel_name": (C.c_char_p, [C.c_int]),
         "atmrt_render_trace": (C.c_int, [vp, vp, vp, C.c_int]),
         "atmrt_pixel_angles": (C.c_int, [vp, vp, vp]),
         "atmrt_set_march_mode": (C.c_int, [vp, C.c_int]),
@@ -72,6 +74,7 @@ def _load():
         "atmrt_group_set_params": (C.c_int, [vp, P(abi.Params)]),
         "atmrt_group_set_objects": (C.c_int, [vp, P(abi.Object), C.c_int, P(vp)]),
         "atmrt_group_render": (C.c_int, [vp, vp, vp, vp, P(abi.Stats)]),
+        "atmrt_group_pixel_angles": (C.c_int, [vp, vp, vp]),
         "atmrt_host_alloc": (vp, [C.c_size_t]),
         "atmrt_host_free": (None, [vp]),
     }
@@ -240,6 +243,13 @@ class Context:
         self._check(lib.atmrt_stage_times(self._h, C.byref(st)))
         return {k: getattr(st, k) for k, _ in abi.StageMs._fields_ if not k.startswith("_")}
 
+    def kernel_times(self):
+        """Average device time of each hot kernel over the renders since the last stage_times() call:
+        {kernel name: ms} for the kernels those renders launched (synchronises; does not reset the averages)."""
+        k = abi.KernelMs()
+        self._check(lib.atmrt_kernel_times(self._h, C.byref(k)))
+        return {lib.atmrt_kernel_name(i).decode(): k.ms[i] for i in range(abi.KERNEL_COUNT) if k.renders_with[i] > 0}
+
     def render_trace(self, max_points=8):
         h, w = self.shape()
         pts = np.zeros((h, w, max(max_points, 1)), dtype=TRACE_DTYPE)
@@ -391,6 +401,13 @@ class Group:
                 keep.append(t)
                 ptrs[i] = t.ctypes.data
         self._check(lib.atmrt_group_set_objects(self._h, arr, n, ptrs))
+
+    def pixel_angles(self):
+        """ResultPixel.elevation_angle / azimuth of the whole image, [H][W] each."""
+        p = self.params
+        el, az = np.empty((p.height, p.width)), np.empty((p.height, p.width))
+        self._check(lib.atmrt_group_pixel_angles(self._h, _ptr(el), _ptr(az)))
+        return el, az
 
     def render(self, rgb=True, meta=True, steps=True, out=None):
         """The full image (all column blocks) in host memory; ``out`` may carry preallocated arrays (host_array)."""

@@ -292,6 +292,7 @@ def run_b200(args):
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1) / args.steps
+    kernel_ms = ctx.kernel_times()  # per hot kernel, CUDA events on the stream it is launched on, averaged over the timed steps
     stage = ctx.stage_times()
     t = torch.tensor([ms, stage["ms_terrain"], stage["ms_paths"], stage["ms_march"]], dtype=torch.float64, device=dev)
     if world > 1:
@@ -364,17 +365,28 @@ def run_b200(args):
         return
 
     # ---- roofline of the dominant kernel -------------------------------------------------------
+    # EXECUTED work against the measured peaks: FP64-pipe instructions of one launch (counted on the SASS page of the
+    # committed ncu capture of these very sources) / the live duration of that launch, against the live DFMA issue rate;
+    # DRAM bytes of one launch (same capture) / live duration against MEASURED_PEAKS.json's copy bandwidth. What the
+    # REFERENCE would execute for the same units is reported separately, as `algorithmic`.
     n_t = st["n_terrain"]
-    units = {"terrain": wl * n_t, "paths": st["path_steps"] / world if world > 1 else st["path_steps"],
-             "march": st["ray_steps"] / world}
+    units = {"terrain": wl * n_t, "paths": st["path_steps"] / world if world > 1 else st["path_steps"], "march": st["ray_steps"] / world}
+    roofs = {k: kernel_roofline(k, v, fp, args, world) for k, v in kernel_ms.items()}
+    dom = max(kernel_ms, key=kernel_ms.get)
+    roof = dict(roofs[dom])
+    stage_of = {"k_terrain_profile": "terrain", "k_ray_chain": "paths", "k_ray_elements": "paths", "k_sweep_bits": "march", "k_hit_normals": "march",
+                "k_shade_tiles": "march", "k_march": "march", "k_rectilinear": "march"}
     stage_ms = {"terrain": ms_a, "paths": ms_b, "march": ms_c}
-    if params.generator == 1:
-        STAGE_UNITS["march"] = ("k_rectilinear", "ray steps")  # one kernel: stepper + walk + tap + get_single_pixel per pixel
-    elif args.march_mode == 0 and params.terrain_alpha == 1.0 and not objects:
-        STAGE_UNITS["march"] = ("k_sweep+k_sweep_shade", "ray steps")  # opaque terrain, no objects: the horizon sweep
-    dom = max(stage_ms, key=stage_ms.get)
-    roofs = {k: roofline(k, stage_ms[k], units[k], params, fp, args) for k in stage_ms}
-    roof = roofs[dom]
+    algorithmic = {}
+    for sname, t_ms in stage_ms.items():
+        per_unit = fp64_instr_per_unit(sname, params)
+        rate = per_unit * units[sname] / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
+        peak = (fp or {}).get("dfma_gflops", 0.0) / 2.0
+        algorithmic[sname] = {"reference_fp64_instr_per_unit": per_unit, "units_per_step": units[sname], "unit_name": STAGE_UNITS[sname][1],
+                              "reference_equivalent_ginstr_per_s": rate, "algorithmic_speedup": rate / peak if peak else None,
+                              "hbm_algorithmic_bytes_per_unit": hbm_bytes_per_unit(sname, params)}
+    roof["stage"] = stage_of.get(dom)
+    roof["algorithmic"] = algorithmic.get(stage_of.get(dom))
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -396,8 +408,9 @@ def run_b200(args):
         "e2e_gen": e2e_gen,
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roof,
-        "roofline_stages": {k: {f: v[f] for f in ("kernel", "achieved", "peak", "frac", "unit", "launch_ms", "units_per_launch", "traffic", "ncu")}
-                            for k, v in roofs.items()},
+        "roofline_kernels": roofs,
+        "algorithmic": algorithmic,
+        "kernel_ms": kernel_ms,
         "cpu_baseline": cpu,
         "fp64_peak_measured": fp,
         "pixels_hit": st["pixels_hit"], "step_overflows": st["step_overflows"],
@@ -438,56 +451,58 @@ def time_gen_executable():
                 "pixels_per_s": 1920 * 1080 / best, "stage_stamps_s": stamps, "png_bytes": os.path.getsize(png), "meta_bytes": os.path.getsize(dat)}
 
 
-def roofline(stage, ms, units, params, fp, args):
-    """FP64-pipe roofline of the dominant kernel. `achieved` = algorithmic FP64 instructions per launch
-    (per-unit figure from DESIGN.md x units per launch) / measured launch duration; `peak` = the DFMA
-    issue rate measured live by atmrt_fp64_peak (MEASURED_PEAKS.json has no FP64 figure)."""
-    per_unit = fp64_instr_per_unit(stage, params)
-    peak = (fp or {}).get("dfma_gflops", 0.0) / 2.0  # G FP64 instr/s
-    achieved = per_unit * units / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+def _source_sha():
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    try:
+        from source_sha import source_sha
+
+        return source_sha()
+    except Exception:
+        return None
+
+
+def kernel_roofline(kernel, ms, fp, args, world):
+    """`roofline` of one kernel. `bound` is the FP64 pipe: the path is f64 arithmetic on data that is read once (SURVEY
+    section 8d), no dense contraction. achieved = executed FP64-pipe thread instructions per launch / live launch duration;
+    peak = the DFMA issue rate measured live (atmrt_fp64_peak; MEASURED_PEAKS.json has no FP64 entry); frac = achieved /
+    peak. The executed counts come from profiles/ncu_summary.json and are used only when that capture was taken from the
+    sources this run executes (source_sha) on this workload at N = 1; otherwise frac is null and the entry says why."""
     hbm_peak = 6548.2
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    bytes_unit = hbm_bytes_per_unit(stage, params)
-    return {
-        "kernel": STAGE_UNITS[stage][0], "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "G FP64 instr/s",
-        "frac": achieved / peak if peak else None, "traffic": ncu_traffic(STAGE_UNITS[stage][0], args),
-        "ncu": ncu_counters(STAGE_UNITS[stage][0], args),
-        "note": "achieved counts the FP64 instructions of the REFERENCE's algorithm per unit (DESIGN.md section 4); the kernels execute "
-                "fewer (deferred normals, g(h) table and macro steps, horizon sweep), so frac > 1 means less work than the reference's "
-                "algorithm, not a faster pipe -- the pipe utilisations measured by ncu are under `ncu`",
-        "units_per_launch": units, "unit_name": STAGE_UNITS[stage][1], "fp64_instr_per_unit": per_unit, "launch_ms": ms,
-        "peak_source": "measured live (atmrt_fp64_peak: 8 independent DFMA chains/thread); MEASURED_PEAKS.json has no FP64 entry",
-        "hbm": {"algorithmic_bytes_per_unit": bytes_unit, "achieved_gbs": bytes_unit * units / (ms * 1e-3) / 1e9 if ms > 0 else 0.0,
-                "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs"},
-    }
-
-
-def ncu_counters(kernel, args):
-    """Pipe utilisations of `kernel` (or of each kernel of a `a+b` pair) from the committed ncu --set full capture
-    (profiles/ncu_summary.json): what the hardware counters say next to the algorithmic `achieved`."""
+    peak = (fp or {}).get("dfma_gflops", 0.0) / 2.0  # G FP64 thread instr/s
+    out = {"kernel": kernel, "bound": "fp64", "launch_ms": ms, "peak": peak, "unit": "G FP64 thread instr/s", "achieved": None, "frac": None, "traffic": None,
+           "peak_source": "measured live (atmrt_fp64_peak: 8 independent DFMA chains per thread); MEASURED_PEAKS.json has no FP64 entry",
+           "hbm": {"peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs", "achieved_gbs": None, "frac": None}}
     try:
         table = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
-        if args.gpus != 1 or args.scale != 1.0:
-            return None
-        got = {k: table.get(f"{args.workload}:{k}") for k in kernel.split("+")}
-        got = {k: v for k, v in got.items() if v}
-        return got or None
     except Exception:
-        return None
-
-
-def ncu_traffic(kernel, args):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` on this workload, from the
-    committed ncu --set full capture (profiles/traffic.json); None when no capture matches."""
-    try:
-        table = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        e = table.get(f"{args.workload}:{kernel}") if args.gpus == 1 and args.scale == 1.0 else None
-        return None if e is None else {"bytes": e["dram_bytes"], "source": e["source"]}
-    except Exception:
-        return None
+        table = {}
+    e = table.get(f"{args.workload}:{kernel}")
+    sha = _source_sha()
+    if e is None or args.scale != 1.0 or world != 1 or args.emulate_ranks > 1 or args.generator != "Fast":
+        out["note"] = "no ncu capture of this kernel for this workload / shard under profiles/"
+        return out
+    if e.get("source_sha") != sha:
+        out["note"] = f"profiles/ncu_summary.json was captured from other sources (sha {e.get('source_sha')}, running {sha}): executed counts withheld"
+        out["stale_ncu"] = {k: e.get(k) for k in ("gpu_time_ms", "fp64_pipe_pct", "issue_active_pct", "source")}
+        return out
+    fp64_thread = e["fp64_warp_instructions"] * 32.0
+    dram = e["dram_read_bytes"] + e["dram_write_bytes"]
+    out["achieved"] = fp64_thread / (ms * 1e-3) / 1e9 if ms > 0 else None
+    out["frac"] = out["achieved"] / peak if peak and out["achieved"] is not None else None
+    out["traffic"] = dram
+    out["hbm"].update(achieved_gbs=dram / (ms * 1e-3) / 1e9 if ms > 0 else None)
+    out["hbm"]["frac"] = out["hbm"]["achieved_gbs"] / hbm_peak if out["hbm"]["achieved_gbs"] else None
+    out["issue"] = {"warp_instructions_per_launch": e["warp_instructions"],
+                    "achieved_g_warp_instr_per_s": e["warp_instructions"] / (ms * 1e-3) / 1e9 if ms > 0 else None}
+    out["ncu"] = {k: e.get(k) for k in ("gpu_time_ms", "fp64_pipe_pct", "issue_active_pct", "warps_active_pct", "dram_throughput_pct", "registers",
+                                        "top_stalls_warps_per_issue_cycle", "source", "source_sha")}
+    out["note"] = ("frac = FP64-pipe instructions this kernel EXECUTES per launch (SASS page of the ncu capture of these sources) / live launch "
+                   "duration / live DFMA issue rate; `ncu.fp64_pipe_pct` is the hardware counter of the same capture (kernel alone, cold cache)")
+    return out
 
 
 def fp64_instr_per_unit(stage, params):

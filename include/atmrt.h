@@ -182,12 +182,32 @@ typedef struct atmrt_stage_ms {
     int32_t _pad;
 } atmrt_stage_ms;
 
+/* Device time of the hot kernels, averaged over the renders since the previous atmrt_stage_times() call (CUDA events on
+ * the stream each kernel is launched on). A kernel a render did not launch does not count for it. */
+enum {
+    ATMRT_KERNEL_TERRAIN_PROFILE = 0, /* stage A */
+    ATMRT_KERNEL_RAY_CHAIN = 1,       /* stage B: the integration chain */
+    ATMRT_KERNEL_RAY_ELEMENTS = 2,    /* stage B: the cache elements of the recorded steps */
+    ATMRT_KERNEL_SWEEP = 3,           /* stage C, opaque terrain without objects: the horizon sweep */
+    ATMRT_KERNEL_HIT_NORMALS = 4,     /* ... normals of the distinct hit samples */
+    ATMRT_KERNEL_SHADE = 5,           /* ... shading of the pixels (all row bands) */
+    ATMRT_KERNEL_MARCH = 6,           /* stage C, general march */
+    ATMRT_KERNEL_RECTILINEAR = 7,     /* the Rectilinear generator */
+    ATMRT_KERNEL_COUNT = 8
+};
+typedef struct atmrt_kernel_ms {
+    double ms[ATMRT_KERNEL_COUNT];
+    int32_t renders_with[ATMRT_KERNEL_COUNT]; /* renders that launched the kernel */
+    int32_t renders;
+    int32_t _pad;
+} atmrt_kernel_ms;
+
 typedef struct atmrt_ctx atmrt_ctx;
 
 /* ---- lifecycle -------------------------------------------------------------------------- */
 int atmrt_abi_version(void);
 /* sizeof() of the ABI structs in declaration order (altitude, atmosphere_def, params, tile_desc,
- * object, meta, trace_point, stats, stage_ms); returns how many there are. For binding self-checks. */
+ * object, meta, trace_point, stats, stage_ms, kernel_ms); returns how many there are. For binding self-checks. */
 int atmrt_abi_sizes(size_t* out, int n);
 int atmrt_create(int device, atmrt_ctx** out);
 void atmrt_destroy(atmrt_ctx* ctx);
@@ -233,6 +253,9 @@ int atmrt_stage_times(atmrt_ctx* ctx, atmrt_stage_ms* out);
  * get_ray_elev(y), and get_ray_dir(x) wrapped once into [0, 360); Rectilinear generator (rectilinear.rs:78-116):
  * the pixel's own elevation / direction, not wrapped. Needs set_params only. */
 int atmrt_pixel_angles(atmrt_ctx* ctx, double* elevation_angle, double* azimuth);
+/* Per-kernel device times of the same renders (does not reset the averages; call it before atmrt_stage_times). */
+int atmrt_kernel_times(atmrt_ctx* ctx, atmrt_kernel_ms* out);
+const char* atmrt_kernel_name(int i); /* "k_terrain_profile", ... for i in [0, ATMRT_KERNEL_COUNT) */
 /* Full trace-point lists (ResultPixel.trace_points) for small images: points[H][x1-x0][max_points],
  * counts[H][x1-x0] (true count, may exceed max_points). Host buffers. */
 int atmrt_render_trace(atmrt_ctx* ctx, atmrt_trace_point* points, int32_t* counts, int max_points);
@@ -307,6 +330,8 @@ int atmrt_group_set_terrain(atmrt_group* g, const atmrt_tile_desc* tiles, int nt
 int atmrt_group_set_params(atmrt_group* g, const atmrt_params* params);
 int atmrt_group_set_objects(atmrt_group* g, const atmrt_object* objects, int nobjects, const uint8_t* const* rgba_textures);
 int atmrt_group_render(atmrt_group* g, uint8_t* rgb, atmrt_meta* meta, int32_t* steps, atmrt_stats* stats);
+/* atmrt_pixel_angles of the whole image: [H][W] each, either may be NULL. */
+int atmrt_group_pixel_angles(atmrt_group* g, double* elevation_angle, double* azimuth);
 /* Page-locked host memory visible to every GPU (the host image / metadata / decoded tiles). */
 void* atmrt_host_alloc(size_t bytes);
 void atmrt_host_free(void* p);

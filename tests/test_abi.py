@@ -35,7 +35,7 @@ def test_host_library_exports_every_declared_symbol():
 def test_struct_sizes_match_the_header():
     out = (C.c_size_t * 16)()
     n = runtime.lib.atmrt_abi_sizes(out, 16)
-    mirror = [abi.Altitude, abi.AtmosphereDef, abi.Params, abi.TileDesc, abi.Object, abi.Meta, abi.TracePoint, abi.Stats, abi.StageMs]
+    mirror = [abi.Altitude, abi.AtmosphereDef, abi.Params, abi.TileDesc, abi.Object, abi.Meta, abi.TracePoint, abi.Stats, abi.StageMs, abi.KernelMs]
     assert n == len(mirror)
     assert [out[i] for i in range(n)] == [C.sizeof(m) for m in mirror]
     assert runtime.lib.atmrt_abi_version() == 1

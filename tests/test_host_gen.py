@@ -177,9 +177,15 @@ def test_gen_executable_end_to_end(tmp_path, ctx):
     img = host.read_png(str(png))[..., :3]
     assert img.shape == (120, 200, 3)
     raw = gzip.decompress(dat.read_bytes())
-    assert raw.startswith(b"ATMRTMETA1\n")
-    w, h = np.frombuffer(raw, "<i4", 2, 11)
-    meta = np.frombuffer(raw, runtime.META_DTYPE, offset=19).reshape(h, w)
+    # the host's own sidecar (NOT the reference's bincode container, and it says so): ATMRTMETA2
+    assert raw.startswith(b"ATMRTMETA2\n") and "not the reference's bincode container" in r.stderr
+    w, h, generator, _ = np.frombuffer(raw, "<i4", 4, 11)
+    assert (w, h, generator) == (200, 120, 0)
+    off = 11 + 16
+    el = np.frombuffer(raw, "<f8", h, off)         # ResultPixel.elevation_angle, one per row (Fast generator)
+    az = np.frombuffer(raw, "<f8", w, off + 8 * h)  # ResultPixel.azimuth, one per column, wrapped into [0, 360)
+    meta = np.frombuffer(raw, runtime.META_DTYPE, offset=off + 8 * (h + w)).reshape(h, w)
+    assert el[h // 2] == -2.0 and (np.diff(el) < 0).all() and az[w // 2] == 80.0 and (np.diff(az) > 0).all()
     # the same render through the Python mirror of the host
     cfg = config.read_config(argv)
     terrain = runtime.Terrain.from_folder(str(folder))
