@@ -144,7 +144,7 @@ class StageMs(C.Structure):
                 ("renders", C.c_int32), ("_pad", C.c_int32)]
 
 
-KERNEL_COUNT = 8
+KERNEL_COUNT = 7
 
 
 class KernelMs(C.Structure):

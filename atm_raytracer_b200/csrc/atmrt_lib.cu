@@ -93,7 +93,6 @@ struct atmrt_ctx {
     DevBuf d_sweep_flags, d_sweep_col, d_sweep_hit;
     DevBuf d_anchor;  // walk anchors of stage A, [wl][n_anchor]
     bool walk_anchors = true;
-    DevBuf d_rec_ab, d_rec_em, d_rec_n;  // stage B: the steps of the chain (k_ray_chain -> k_ray_elements)
     DevBuf d_list, d_count, d_normals;  // stage C: the distinct hit samples of every column and their normals
     int sweep_bands = 0;                // 0: chosen per render (launch_render)
     DevBuf d_stage;  // raw posts of pack_terrain on their way to the tiled layout
@@ -758,32 +757,20 @@ int copy_rows_to_host(atmrt_ctx* ctx, const RenderTargets& rt, int wl, int r0, i
     return 0;
 }
 
-// The ray-path stage with macro steps, as chain + elements (kernels.cuh): as many simulation steps per macro step as keep
-// it within MACRO_MAX_METRES (16 at 25 or 50 m; fewer for coarser simulation steps, none above 400 m).
+// The ray-path stage with macro steps: as many simulation steps per macro step as keep it within
+// MACRO_MAX_METRES (16 at 25 or 50 m; fewer for coarser simulation steps, none above 400 m).
 template <bool FLAT>
 int launch_macro_paths(atmrt_ctx* ctx, const DevScene& S, const DevBuffers& B, int h, atmrt_ctx::StageEvents* E) {
-    int macro_steps = 0;
-    for (int m : {16, 8, 4, 2})
-        if (macro_steps == 0 && (double)m * S.step <= MACRO_MAX_METRES) macro_steps = m;
-    if (macro_steps == 0) {
-        k_ray_paths<FLAT, false><<<(h + 31) / 32, 32, 0, ctx->s_b>>>(S, B);
-        return 0;
-    }
-    PathRecords R{};
-    R.cap = S.n_t + 1;
-    int rc = ensure(ctx, ctx->d_rec_ab, sizeof(double2) * (size_t)h * R.cap);
-    if (!rc) rc = ensure(ctx, ctx->d_rec_em, sizeof(int2) * (size_t)h * R.cap);
-    if (!rc) rc = ensure(ctx, ctx->d_rec_n, sizeof(int) * (size_t)h);
-    if (rc) return rc;
-    R.ab = (double2*)ctx->d_rec_ab.p, R.em = (int2*)ctx->d_rec_em.p, R.n = (int*)ctx->d_rec_n.p;
-    CUDA_TRY(ctx, cudaEventRecord(E->k0[ATMRT_KERNEL_RAY_CHAIN], ctx->s_b));
-    k_ray_chain<FLAT><<<(h + CHAIN_THREADS - 1) / CHAIN_THREADS, CHAIN_THREADS, 0, ctx->s_b>>>(S, B, R, macro_steps);
-    CUDA_TRY(ctx, cudaEventRecord(E->k1[ATMRT_KERNEL_RAY_CHAIN], ctx->s_b));
-    CUDA_TRY(ctx, cudaEventRecord(E->k0[ATMRT_KERNEL_RAY_ELEMENTS], ctx->s_b));
-    k_ray_elements<FLAT><<<h, ELEM_THREADS, 0, ctx->s_b>>>(S, B, R);
-    CUDA_TRY(ctx, cudaEventRecord(E->k1[ATMRT_KERNEL_RAY_ELEMENTS], ctx->s_b));
-    E->kmask |= 1u << ATMRT_KERNEL_RAY_CHAIN | 1u << ATMRT_KERNEL_RAY_ELEMENTS;
-    ctx->launches++;
+    const int warps = MACRO_THREADS / 32;
+    auto blocks = [&](int m) { return (h + warps * (32 / m) - 1) / (warps * (32 / m)); };
+    CUDA_TRY(ctx, cudaEventRecord(E->k0[ATMRT_KERNEL_RAY_PATHS], ctx->s_b));
+    if (16.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 16><<<blocks(16), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
+    else if (8.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 8><<<blocks(8), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
+    else if (4.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 4><<<blocks(4), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
+    else if (2.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 2><<<blocks(2), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
+    else k_ray_paths<FLAT, false><<<(h + 31) / 32, 32, 0, ctx->s_b>>>(S, B);
+    CUDA_TRY(ctx, cudaEventRecord(E->k1[ATMRT_KERNEL_RAY_PATHS], ctx->s_b));
+    E->kmask |= 1u << ATMRT_KERNEL_RAY_PATHS;
     return 0;
 }
 
@@ -1142,7 +1129,7 @@ void atmrt_destroy(atmrt_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_objects_in, &ctx->d_objects, &ctx->d_dist, &ctx->d_colcalc, &ctx->d_tlat, &ctx->d_tlon, &ctx->d_telev,
                       &ctx->d_tclose, &ctx->d_pdist, &ctx->d_pelev, &ctx->d_plen, &ctx->d_pn,
                       &ctx->d_tmin1, &ctx->d_tmax1, &ctx->d_tmin2, &ctx->d_tmax2, &ctx->d_tmin3, &ctx->d_tmax3, &ctx->d_close1, &ctx->d_close2, &ctx->d_close3, &ctx->d_rmin1, &ctx->d_rmin3, &ctx->d_rmax3,
-                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_sweep_flags, &ctx->d_sweep_col, &ctx->d_sweep_hit, &ctx->d_list, &ctx->d_count, &ctx->d_normals, &ctx->d_anchor, &ctx->d_rec_ab, &ctx->d_rec_em, &ctx->d_rec_n, &ctx->d_stage, &ctx->d_atm_aux, &ctx->d_rgb, &ctx->d_meta,
+                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_sweep_flags, &ctx->d_sweep_col, &ctx->d_sweep_hit, &ctx->d_list, &ctx->d_count, &ctx->d_normals, &ctx->d_anchor, &ctx->d_stage, &ctx->d_atm_aux, &ctx->d_rgb, &ctx->d_meta,
                       &ctx->d_steps, &ctx->d_points, &ctx->d_counts, &ctx->d_probe_a, &ctx->d_probe_b, &ctx->d_probe_c, &ctx->d_probe_d};
     for (DevBuf* b : bufs) release(*b);
     for (DevBuf& b : ctx->textures) release(b);
@@ -1506,8 +1493,8 @@ int atmrt_stage_times(atmrt_ctx* ctx, atmrt_stage_ms* out) {
 }
 
 const char* atmrt_kernel_name(int i) {
-    static const char* names[ATMRT_KERNEL_COUNT] = {"k_terrain_profile", "k_ray_chain", "k_ray_elements", "k_sweep_bits",
-                                                    "k_hit_normals",     "k_shade_tiles", "k_march",      "k_rectilinear"};
+    static const char* names[ATMRT_KERNEL_COUNT] = {"k_terrain_profile", "k_ray_paths_macro", "k_sweep_bits", "k_hit_normals",
+                                                    "k_shade_tiles",     "k_march",           "k_rectilinear"};
     return i >= 0 && i < ATMRT_KERNEL_COUNT ? names[i] : "";
 }
 

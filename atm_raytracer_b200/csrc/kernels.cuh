@@ -642,208 +642,151 @@ __global__ void __launch_bounds__(32) k_ray_paths(const __grid_constant__ DevSce
 }
 
 // ---------------------------------------------------------------------------------------------
-// Macro steps. The ray equation is smooth wherever g(h) is -- everywhere except at the starts of the temperature
-// functions, where g jumps -- and there classical RK4 with a 25 m step is converged far below f64 resolution of the path:
-// integrating the same equation with ONE RK4 step of 16 x 25 m lands on the same state to 4e-11 m for near-horizontal
-// rays and 2e-9 m at 44 degrees (extended-precision measurement in DESIGN.md section 4.B), and the fifteen states in
-// between follow from the cubic Hermite interpolant of the two ends (error < 2e-11 m). At a start of a temperature
-// function the reference's result DOES depend on how its 25 m steps straddle the jump (by millimetres), so there the
-// stage takes the reference's own single steps: a macro step is taken only when no start lies in the altitude span it
-// covers (exact test against the sorted starts), single steps otherwise.
+// Stage B with macro steps. The ray equation is smooth wherever g(h) is -- everywhere except at the starts
+// of the temperature functions, where g jumps -- and there classical RK4 with a 25 m step is converged far
+// below f64 resolution of the path: integrating the same equation with ONE RK4 step of 16 x 25 m lands on the
+// same state to 4e-11 m for near-horizontal rays and 2e-9 m at 44 degrees (extended-precision measurement in
+// DESIGN.md section 4.B), and the fifteen states in between follow from the cubic Hermite interpolant of the
+// two ends (error < 2e-11 m). At a start of a temperature function the reference's result DOES depend on how its 25 m steps
+// straddle the jump (by millimetres), so there the kernel takes the reference's own single steps: a macro
+// step is taken only when no start lies in the altitude span it covers (exact test against the sorted
+// starts), single steps otherwise. The chain is 16x shorter where it matters, and the sixteen states of a
+// macro step are sixteen independent outputs: a warp is 2 rows x 16 sub-lanes (lane = 2 j + row), every
+// sub-lane integrates the row's macro step redundantly (identical values, no exchange), evaluates ITS
+// state from the interpolant, its calc_dist segment, takes part in a prefix sum for path_length and stores
+// its cache entry.
 // ---------------------------------------------------------------------------------------------
+constexpr int MACRO_THREADS = 128;  // 4 warps share one copy of the table
 constexpr double MACRO_MAX_METRES = 800.0;  // longest macro step: 16 x 50 m (truncation error < 3e-8 m, section 4.B); longer simulation steps get fewer per macro step
 constexpr int ATM_MAX_BND = ATMRT_MAX_ATM_FUNCTIONS + 4;
 
-// ---------------------------------------------------------------------------------------------
-// Stage B in two kernels: the CHAIN and the ELEMENTS.
-//
-// What is serial in a ray path is the integration of its state -- four dependent lookups of g per RK4 step. What
-// k_ray_paths_macro does besides (the sixteen states of a macro step from the cubic Hermite interpolant, their calc_dist
-// segments with a square root each, the prefix sum for path_length, the termination rule, the stores) is a second chain
-// of about the same length that a single in-order warp can only run AFTER the first, macro step after macro step. Here
-// the two are separate kernels:
-//   k_ray_chain     one lane per row integrates nothing but the state: per step the macro / single decision (per ROW,
-//                   not per pair of rows), one RK4 step of 16 x step or of step, and a 24-byte record {a, b, e, m} of the
-//                   state the step starts from. The stage's latency chain, a third as long.
-//   k_ray_elements  one block per row turns the records into the cache: every element of every step is independent
-//                   (Hermite state, segment length from the element before it), then one scan along the row for
-//                   path_length and one minimum for the termination rule (utils.rs:167-170). Throughput work that shares
-//                   the machine with stage A.
-// The arithmetic of a step is k_ray_paths_macro's (rk4_step<FLAT, 0> on the table; pieces, then libm where the table does
-// not serve), except that single steps take four lookups instead of rk4_step_shared's two corrected ones (1e-12
-// relative) and that path_length is summed in scan order (1e-13 relative).
-// ---------------------------------------------------------------------------------------------
-struct PathRecords {
-    double2* ab;  // [h][cap]: the state (r, dr/dphi) or (h, dh/dx) a step starts from; entry n is the state after the last step
-    int2* em;     // [h][cap]: first element of the step (its state is `ab`), elements in it: 16 / 8 / 4 / 2 or 1; negative: the row is frozen (complete or NaN)
-    int* n;       // [h]: steps recorded
-    int cap;
-};
-
-constexpr int CHAIN_THREADS = 64;
-
-template <bool FLAT>
-__global__ void __launch_bounds__(CHAIN_THREADS) k_ray_chain(const __grid_constant__ DevScene S, DevBuffers B, PathRecords R, int macro_steps) {
+template <bool FLAT, int MACRO>  // MACRO steps per macro step (16, 8, 4 or 2), 32 / MACRO rows per warp
+__global__ void __launch_bounds__(MACRO_THREADS) k_ray_paths_macro(const __grid_constant__ DevScene S, DevBuffers B) {
     __shared__ double tab_smem[ATM_FIELDS * ATM_CELLS];
     __shared__ double s_bnd[ATM_MAX_BND];          // sorted altitudes where g is not smooth (+inf padded)
     __shared__ unsigned char s_first[ATM_CELLS];   // per cell: index of the first of them at or above the cell's lower edge
 #pragma unroll 4
-    for (int i = threadIdx.x; i < ATM_FIELDS * ATM_CELLS; i += CHAIN_THREADS) tab_smem[i] = B.atm_cells[i];
-    for (int i = threadIdx.x; i < ATM_CELLS; i += CHAIN_THREADS) s_first[i] = B.atm_first[i];
+    for (int i = threadIdx.x; i < ATM_FIELDS * ATM_CELLS; i += MACRO_THREADS) tab_smem[i] = B.atm_cells[i];
+    for (int i = threadIdx.x; i < ATM_CELLS; i += MACRO_THREADS) s_first[i] = B.atm_first[i];
     if (threadIdx.x < ATM_MAX_BND) s_bnd[threadIdx.x] = B.atm_bnd[threadIdx.x];
     __syncthreads();
+    constexpr int MACRO_ROWS = 32 / MACRO;
     const GSource gs{(unsigned)__cvta_generic_to_shared(tab_smem), B.atm_pieces, B.n_atm_pieces};
-    const int y_raw = blockIdx.x * CHAIN_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, rr = lane % MACRO_ROWS, j = lane / MACRO_ROWS;
+    const int y_raw = (blockIdx.x * (MACRO_THREADS / 32) + (threadIdx.x >> 5)) * MACRO_ROWS + rr;
     const int y = min(y_raw, S.height - 1);
     const bool writer = y_raw < S.height;
     const double alt = *B.obs_alt;
     const double radius = S.radius, off = FLAT ? 0.0 : radius;
     const double d = FLAT ? S.step : S.step / radius;
-    const double D = (double)macro_steps * d;
-    const int n_t = S.n_t, k_far = S.path_k_far;
-    const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    double2* __restrict__ rab = R.ab + (size_t)y * R.cap;
-    int2* __restrict__ rem = R.em + (size_t)y * R.cap;
-
-    double a = FLAT ? alt : radius + alt;
-    double b = FLAT ? tan(to_radians(get_ray_elev(S, y))) : a * tan(to_radians(get_ray_elev(S, y)));
-    double Lb = inf, Ub = -inf;  // the starts of temperature functions that bracket the current altitude (none in between); empty at first
-    bool trig_end = alt < -1000.0 || 0 >= k_far;  // the element the state sits on is past max_distance or below -1000 m
-    bool done = false;                            // ... an element before it is: the cache needs nothing beyond this element
-    int e = 0, ns = 0;
-#pragma unroll 1
-    while (__any_sync(FULL, e < n_t - 1 && !done)) {
-        const bool active = e < n_t - 1 && !done;
-        const bool nan = a != a;  // NaN in, NaN out: nothing to integrate, the elements are NaN
-        // may this step be a macro step? room for it, and no start of a temperature function in the altitudes it spans
-        // (the exact test of k_ray_paths_macro against the sorted starts, through a bracket that is renewed when left)
-        bool macro = e + macro_steps <= n_t - 1;
-        {
-            const double a_end = fma(D, b, a);
-            const double lo = fmin(a, a_end) - off - 1.0, hi = fmax(a, a_end) - off + 1.0;
-            if (active && !nan && !(lo > Lb && hi < Ub)) {
-                const double h0 = a - off;
-                const int cell = min(max((int)floor((h0 - (ATM_BASE - 0.5 * ATM_CELL)) * (1.0 / ATM_CELL)), 0), ATM_CELLS - 1);
-                int t = s_first[cell];
-                while (t > 0 && s_bnd[t - 1] > h0) --t;
-                while (s_bnd[t] <= h0) ++t;  // first start above the altitude (+inf padded)
-                Ub = s_bnd[t], Lb = t > 0 ? s_bnd[t - 1] : -inf;
-            }
-            macro = macro && (nan || (lo > Lb && hi < Ub));
-        }
-        const double step = macro ? D : d;
-        double a1 = a, b1 = b;
-        if (active && !nan) {
-            bool ok = rk4_step<FLAT, 0>(S.atm, gs, radius, step, 0.5 * step, step / 6.0, a, b, &a1, &b1);
-            if (!ok && macro) {  // a cell the table does not serve: the reference's single steps handle it
-                macro = false;
-                ok = rk4_step<FLAT, 0>(S.atm, gs, radius, d, 0.5 * d, d / 6.0, a, b, &a1, &b1);
-            }
-            if (!ok) rk4_step<FLAT, 1>(S.atm, gs, radius, d, 0.5 * d, d / 6.0, a, b, &a1, &b1);  // rare: pieces, then libm
-        }
-        const int m = macro ? macro_steps : 1;
-        if (active && writer) {
-            rab[ns] = make_double2(a, b);
-            rem[ns] = make_int2(e, nan ? -m : m);
-        }
-        if (active) {
-            ++ns;
-            // Termination (utils.rs:167-170): element q is kept unless an element <= q - 2 is past max_distance or
-            // below -1000 m. The chain knows the END elements of its steps: once one of them is past the rule, one more
-            // step supplies every element the cache can keep (k_ray_elements applies the rule to every element).
-            done = trig_end;
-            a = a1, b = b1, e += m;
-            const double h_end = FLAT ? a : a - radius;
-            trig_end = e >= k_far || h_end < -1000.0;
-        }
-    }
-    if (writer) {
-        rab[ns] = make_double2(a, b);  // the state after the last step
-        rem[ns] = make_int2(e, 0);
-        R.n[y] = ns;
-    }
-}
-
-constexpr int ELEM_THREADS = 256;
-
-template <bool FLAT>
-__global__ void __launch_bounds__(ELEM_THREADS) k_ray_elements(const __grid_constant__ DevScene S, DevBuffers B, PathRecords R) {
-    __shared__ int s_trig;        // first element past max_distance or below -1000 m
-    __shared__ double s_warp[ELEM_THREADS / 32];
-    __shared__ double s_carry;
-    const int y = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, j = tid & 15;
-    const double alt = *B.obs_alt;
-    const double radius = S.radius;
-    const double d = FLAT ? S.step : S.step / radius;
+    const double hd = 0.5 * d, d6 = d / 6.0;
+    const double D = (double)MACRO * d, hD = 0.5 * D, D6 = D / 6.0;
+    const double shift = FLAT ? ATM_BASE : radius + ATM_BASE;
+    const double d15 = 1.5 * d, d2 = 2.0 * d;
     const int n_t = S.n_t, k_far = S.path_k_far;
     double* const o_elev = B.p_elev + path_index(n_t, 0, y);
     double* const o_len = B.p_len + path_index(n_t, 0, y);
     const double* __restrict__ dxr = B.path_dxr;
-    const double2* __restrict__ rab = R.ab + (size_t)y * R.cap;
-    const int2* __restrict__ rem = R.em + (size_t)y * R.cap;
-    const int nrec = R.n[y];
-    if (tid == 0) {
-        s_trig = alt < -1000.0 || 0 >= k_far ? 0 : n_t;
-        s_carry = 0.0;
-        o_elev[0] = alt, o_len[0] = 0.0;  // element 0: (alt, 0)
-    }
-    __syncthreads();
-    // ---- the elements: 16 threads per step; element q = e + j + 1 from the interpolant of the step's two ends ----
-    int first_trig = n_t;
-    for (int base = 0; base < nrec; base += ELEM_THREADS / 16) {
-        const int sidx = base + tid / 16;
-        const bool have = sidx < nrec;
-        const int2 em = have ? rem[sidx] : make_int2(0, 0);
-        const int m = abs(em.y);
-        const bool frozen = em.y < 0, mine = have && j < m;
-        const double2 s0 = rab[have ? sidx : 0], s1 = rab[have ? sidx + 1 : 0];
-        const double a = s0.x, b = s0.y, a1 = s1.x, b1 = s1.y;
-        // the cubic Hermite basis at this thread's state, s = (j + 1) / m (the last state of a step is its end)
-        const double sj = (double)(j + 1) / (double)max(m, 1);
-        const double h01 = sj * sj * (3.0 - 2.0 * sj), h10 = sj * (sj - 1.0) * (sj - 1.0), h11 = sj * sj * (sj - 1.0);
-        const double Dm = (double)m * d;
-        double a_q = j == m - 1 ? a1 : a + fma(h01, a1 - a, Dm * fma(h10, b, h11 * b1));
-        if (frozen) a_q = a;
-        const int q = min(em.x + j + 1, n_t - 1);
+    // the cubic Hermite basis at this sub-lane's state, s = (j + 1) / MACRO
+    const double sj = (double)(j + 1) * (1.0 / MACRO);
+    const double h01 = sj * sj * (3.0 - 2.0 * sj), h10 = sj * (sj - 1.0) * (sj - 1.0), h11 = sj * sj * (sj - 1.0);
+    unsigned rowbits = 0u;  // this row's sub-lanes in a ballot
+    for (int t = 0; t < MACRO; ++t) rowbits |= 1u << (t * MACRO_ROWS + rr);
+
+    double a = FLAT ? alt : radius + alt;
+    double b = FLAT ? tan(to_radians(get_ray_elev(S, y))) : a * tan(to_radians(get_ray_elev(S, y)));
+    PathBase bE{0.0, 0.0, 0.0, 0.0}, bM = bE, bN = bE;
+    bool bases_valid = false;
+    // element 0: (alt, 0)
+    if (writer && j == 0) o_elev[0] = alt, o_len[0] = 0.0;
+    double h_e = alt;           // altitude of element e
+    double path_length = 0.0;   // of element e
+    bool done_c = false;        // an element <= e - 1 is past max_distance or below -1000 m (utils.rs:167-170)
+    bool trig_e = alt < -1000.0 || 0 >= k_far;  // ... element e is
+    int n = 1;
+    int e = 0;
+    double dx_q = dxr[min(j + 1, n_t - 1)];
+#pragma unroll 1
+    while (e < n_t - 1) {
+        if (__all_sync(FULL, done_c)) break;
+        const bool still = done_c || a != a;  // complete (it stops moving) or NaN (NaN in, NaN out): nothing to integrate
+        const bool idle = __all_sync(FULL, still);
+        // may this step be a macro step? no start of a temperature function in the altitudes it spans
+        bool macro = e + MACRO <= n_t - 1;
+        if (macro && !idle) {
+            const double a_end = fma(D, b, a);
+            const double lo = fmin(a, a_end) - off - 1.0, hi = fmax(a, a_end) - off + 1.0;
+            const int cell = min(max((int)floor((lo - (ATM_BASE - 0.5 * ATM_CELL)) * (1.0 / ATM_CELL)), 0), ATM_CELLS - 1);
+            int t = s_first[cell];
+            while (s_bnd[t] < lo) ++t;
+            const bool unsafe = !still && !(s_bnd[t] > hi);  // (NaN spans are not safe either)
+            macro = !__any_sync(FULL, unsafe);
+        }
+        double a1 = a, b1 = b;
+        if (macro && !idle) {
+            const bool ok = rk4_step<FLAT, 0>(S.atm, gs, radius, D, hD, D6, a, b, &a1, &b1) || still;
+            macro = __all_sync(FULL, ok);  // a cell the table does not serve: the reference's single steps handle it
+        }
+        int m;
+        bool valid;
+        double a_q;  // this sub-lane's state
+        if (macro) {
+            m = MACRO;
+            valid = true;
+            a_q = j == MACRO - 1 ? a1 : a + fma(h01, a1 - a, D * fma(h10, b, h11 * b1));
+            if (still) a_q = a, a1 = a, b1 = b;
+            bases_valid = false;
+        } else {
+            m = 1;
+            valid = j == 0;
+            if (!bases_valid) {
+                bE = path_base<FLAT>(gs.tab, shift, a), bM = path_base<FLAT>(gs.tab, shift, fma(hd, b, a)), bN = path_base<FLAT>(gs.tab, shift, fma(d, b, a));
+                bases_valid = true;
+            }
+            const bool ok = rk4_step_shared<FLAT>(d, hd, d6, a, b, bE, bM, bN, &a1, &b1) || still;
+            bE = bN;
+            bM = path_base<FLAT>(gs.tab, shift, fma(d15, b, a));
+            bN = path_base<FLAT>(gs.tab, shift, fma(d2, b, a));
+            if (!ok) rk4_step<FLAT, 1>(S.atm, gs, radius, d, hd, d6, a, b, &a1, &b1);  // rare: an altitude the table does not serve
+            if (still) a1 = a, b1 = b;
+            a_q = a1;
+        }
+        // this sub-lane's element q = e + j + 1: calc_dist from the element before it, path_length by prefix sum
+        const int q = min(e + j + 1, n_t - 1);
         const double h_q = FLAT ? a_q : a_q - radius;
-        const double h_up = __shfl_up_sync(FULL, h_q, 1);
-        const double h_p = j == 0 ? (FLAT ? a : a - radius) : h_up;  // the element before it: the step's start, or the neighbour's
-        double dx = dxr[q];
+        const double h_up = __shfl_up_sync(FULL, h_q, MACRO_ROWS);
+        const double h_p = j == 0 ? h_e : h_up;
+        double dx = dx_q;  // dxr[q], loaded one iteration ahead: off the chain
         if (!FLAT) dx = dx * ((h_q + h_p) * 0.5 + radius);
         const double dh = h_q - h_p;
-        const double seg = sqrt_nr(dx * dx + dh * dh);
-        if (mine) {
-            o_elev[(size_t)q * PATH_ROWS] = h_q;
-            o_len[(size_t)q * PATH_ROWS] = seg;  // (its calc_dist segment; path_length after the scan below)
-            if (q >= k_far || h_q < -1000.0) first_trig = min(first_trig, q);
+        double acc = valid ? sqrt_nr(dx * dx + dh * dh) : 0.0;
+#pragma unroll
+        for (int o = MACRO_ROWS; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(FULL, acc, o);
+            if (lane >= o) acc += up;
         }
+        const double len_q = path_length + acc;
+        // termination: element q is kept unless an element <= q - 2 is past max_distance or below -1000 m
+        const bool trig_q = valid && (q >= k_far || h_q < -1000.0);
+        const unsigned trig = (__ballot_sync(FULL, trig_q) & rowbits) >> rr;  // bit MACRO_ROWS j' = sub-lane j'
+        const bool earlier = done_c || (j >= 1 && trig_e) || (j >= 2 && (trig & ((1u << (MACRO_ROWS * (j - 1))) - 1u)) != 0u);
+        const bool emit = valid && writer && !earlier;
+        stg_if(o_elev + (size_t)q * PATH_ROWS, h_q, emit);
+        stg_if(o_len + (size_t)q * PATH_ROWS, len_q, emit);
+        n = emit ? q + 1 : n;
+        // carry to element e + m
+        const int last = rr + MACRO_ROWS * (m - 1);
+        const unsigned before_last = m == 1 ? 0u : (trig & ((1u << (MACRO_ROWS * (m - 1))) - 1u));
+        done_c = done_c || trig_e || before_last != 0u;
+        trig_e = ((trig >> (MACRO_ROWS * (m - 1))) & 1u) != 0u;
+        path_length = __shfl_sync(FULL, len_q, last);
+        h_e = __shfl_sync(FULL, h_q, last);
+        a = a1, b = b1;
+        e += m;
+        dx_q = dxr[min(e + j + 1, n_t - 1)];  // this sub-lane's element of the next iteration, whichever kind of step it takes
     }
-    for (int o = 16; o > 0; o >>= 1) first_trig = min(first_trig, __shfl_xor_sync(FULL, first_trig, o));
-    if (lane == 0 && first_trig < n_t) atomicMin(&s_trig, first_trig);
-    __syncthreads();
-    // elements 0 .. n - 1 are kept: everything the chain produced, up to the element after the first one past the rule
-    const int n_all = nrec > 0 ? rem[nrec].x + 1 : 1;
-    const int n = min(n_all, s_trig < n_t ? s_trig + 2 : n_t);
-    // ---- path_length: the running sum of the segments along the row ----
-    for (int base = 1; base < n; base += ELEM_THREADS) {
-        const int q = base + tid;
-        double v = q < n ? o_len[(size_t)q * PATH_ROWS] : 0.0;
-        for (int o = 1; o < 32; o <<= 1) {
-            const double up = __shfl_up_sync(FULL, v, o);
-            if (lane >= o) v += up;
-        }
-        if (lane == 31) s_warp[tid >> 5] = v;
-        __syncthreads();
-        double pre = s_carry;
-        for (int w = 0; w < (tid >> 5); ++w) pre += s_warp[w];
-        v += pre;
-        if (q < n) o_len[(size_t)q * PATH_ROWS] = v;
-        __syncthreads();
-        if (tid == ELEM_THREADS - 1) s_carry = v;
-        __syncthreads();
-    }
-    if (tid == 0) {
+    for (int o = MACRO_ROWS; o < 32; o <<= 1) n = max(n, __shfl_xor_sync(FULL, n, o));
+    if (writer && j == 0) {
         B.p_n[y] = n;
         atomicAdd(B.counters + CNT_PATH_STEPS, (unsigned long long)(n - 1));
     }

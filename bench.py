@@ -374,7 +374,7 @@ def run_b200(args):
     roofs = {k: kernel_roofline(k, v, fp, args, world) for k, v in kernel_ms.items()}
     dom = max(kernel_ms, key=kernel_ms.get)
     roof = dict(roofs[dom])
-    stage_of = {"k_terrain_profile": "terrain", "k_ray_chain": "paths", "k_ray_elements": "paths", "k_sweep_bits": "march", "k_hit_normals": "march",
+    stage_of = {"k_terrain_profile": "terrain", "k_ray_paths_macro": "paths", "k_sweep_bits": "march", "k_hit_normals": "march",
                 "k_shade_tiles": "march", "k_march": "march", "k_rectilinear": "march"}
     stage_ms = {"terrain": ms_a, "paths": ms_b, "march": ms_c}
     algorithmic = {}

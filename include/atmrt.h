@@ -186,14 +186,13 @@ typedef struct atmrt_stage_ms {
  * the stream each kernel is launched on). A kernel a render did not launch does not count for it. */
 enum {
     ATMRT_KERNEL_TERRAIN_PROFILE = 0, /* stage A */
-    ATMRT_KERNEL_RAY_CHAIN = 1,       /* stage B: the integration chain */
-    ATMRT_KERNEL_RAY_ELEMENTS = 2,    /* stage B: the cache elements of the recorded steps */
-    ATMRT_KERNEL_SWEEP = 3,           /* stage C, opaque terrain without objects: the horizon sweep */
-    ATMRT_KERNEL_HIT_NORMALS = 4,     /* ... normals of the distinct hit samples */
-    ATMRT_KERNEL_SHADE = 5,           /* ... shading of the pixels (all row bands) */
-    ATMRT_KERNEL_MARCH = 6,           /* stage C, general march */
-    ATMRT_KERNEL_RECTILINEAR = 7,     /* the Rectilinear generator */
-    ATMRT_KERNEL_COUNT = 8
+    ATMRT_KERNEL_RAY_PATHS = 1,       /* stage B (refracted rays, macro steps) */
+    ATMRT_KERNEL_SWEEP = 2,           /* stage C, opaque terrain without objects: the horizon sweep */
+    ATMRT_KERNEL_HIT_NORMALS = 3,     /* ... normals of the distinct hit samples */
+    ATMRT_KERNEL_SHADE = 4,           /* ... shading of the pixels (all row bands) */
+    ATMRT_KERNEL_MARCH = 5,           /* stage C, general march */
+    ATMRT_KERNEL_RECTILINEAR = 6,     /* the Rectilinear generator */
+    ATMRT_KERNEL_COUNT = 7
 };
 typedef struct atmrt_kernel_ms {
     double ms[ATMRT_KERNEL_COUNT];
