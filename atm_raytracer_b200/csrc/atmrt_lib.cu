@@ -1209,6 +1209,23 @@ int atmrt_bind_terrain(atmrt_ctx* ctx, const atmrt_tile_desc* tiles, int ntiles,
     ctx->terrain.lat_min = L.lat_min, ctx->terrain.lon_min = L.lon_min;
     ctx->terrain.nlat_tiles = L.nlat_tiles, ctx->terrain.nlon_tiles = L.nlon_tiles;
     ctx->terrain.ntiles = ntiles;
+    {  // a regular terrain (device_math.cuh): every tile is exactly its one-degree cell on one common grid
+        DevTerrain& T = ctx->terrain;
+        T.regular = ntiles > 0 ? 1 : 0;
+        for (int i = 0; i < ntiles && T.regular; ++i) {
+            const atmrt_tile_desc& d = tiles[i];
+            const DevTile& t = L.tiles[i];
+            if (d.nlat != tiles[0].nlat || d.nlon != tiles[0].nlon || d.lat_interval != tiles[0].lat_interval || d.lon_interval != tiles[0].lon_interval ||
+                d.min_lat != (double)d.lat0 || d.min_lon != (double)d.lon0 || t.max_lat != d.min_lat + 1.0 || t.max_lon != d.min_lon + 1.0 ||
+                d.lat0 < -32768 || d.lat0 > 32767 || d.lon0 < -32768 || d.lon0 > 32767)
+                T.regular = 0;
+        }
+        if (T.regular) {
+            T.r_nlat = L.tiles[0].nlat, T.r_nlon = L.tiles[0].nlon, T.r_mt_lat = L.tiles[0].mt_lat;
+            T.r_lat_interval = L.tiles[0].lat_interval, T.r_lon_interval = L.tiles[0].lon_interval;
+            T.r_inv_lat_interval = L.tiles[0].inv_lat_interval, T.r_inv_lon_interval = L.tiles[0].inv_lon_interval;
+        }
+    }
     ctx->has_terrain = true;
     ctx->rendered = false;
     return 0;

@@ -77,6 +77,12 @@ struct DevTerrain {
     const int16_t* posts;
     int lat_min, lon_min, nlat_tiles, nlon_tiles;
     int ntiles;
+    // A REGULAR terrain -- every tile covers exactly its one-degree cell [lat0, lat0 + 1] x [lon0, lon0 + 1] with the
+    // same grid (what a folder of DTED files of one level is): the descriptor of a tile is then known without loading
+    // it (only its offset in the packed posts differs) and a sample is always inside the tile its floor selects.
+    int regular;
+    int r_nlat, r_nlon, r_mt_lat;
+    double r_lat_interval, r_lon_interval, r_inv_lat_interval, r_inv_lon_interval;
 };
 
 __device__ __forceinline__ long long post_index(const DevTile& t, int ilon, int ilat) {
@@ -91,7 +97,19 @@ __device__ __forceinline__ double div_by(double a, double b, double y) {
     return fma(fma(-b, q, a), y, q);
 }
 
-// DtedData::get_elev (external; bilinear form witnessed by terrain/geotiff.rs:61-100)
+// The bilinear form of DtedData::get_elev (external; witnessed by terrain/geotiff.rs:61-100) on the 2 x 2 posts whose
+// lower-left one is (lon_int, lat_int) of the tile whose posts start at `off`. The four indices of the micro-tiled
+// layout follow from the first: +1 / +8 inside an 8 x 8 micro-tile, a step into the next micro-tile at its edge.
+__device__ __forceinline__ double bilinear_posts(const int16_t* __restrict__ p, long long off, int mt_lat, int lon_int, int lat_int, double lon_frac, double lat_frac) {
+    const long long i00 = off + ((long long)((lon_int >> 3) * mt_lat + (lat_int >> 3)) << 6) + ((lon_int & 7) << 3) + (lat_int & 7);
+    const int dlat = (lat_int & 7) == 7 ? 57 : 1;                 // next micro-tile along latitude: + 64 - 7
+    const int dlon = (lon_int & 7) == 7 ? mt_lat * 64 - 56 : 8;   // next micro-tile along longitude: + 64 mt_lat - 7 * 8
+    const double e00 = (double)__ldg(p + i00), e01 = (double)__ldg(p + i00 + dlat);
+    const double e10 = (double)__ldg(p + i00 + dlon), e11 = (double)__ldg(p + i00 + dlon + dlat);
+    return e00 * (1.0 - lon_frac) * (1.0 - lat_frac) + e01 * (1.0 - lon_frac) * lat_frac + e10 * lon_frac * (1.0 - lat_frac) + e11 * lon_frac * lat_frac;
+}
+
+// DtedData::get_elev
 __device__ __forceinline__ bool tile_get_elev(const DevTerrain& T, const DevTile& t, double lat, double lon, double* out) {
     if (lat < t.min_lat || lat > t.max_lat || lon < t.min_lon || lon > t.max_lon) return false;
     double plat = div_by((lat - t.min_lat) * 3600.0, t.lat_interval, t.inv_lat_interval);
@@ -106,23 +124,36 @@ __device__ __forceinline__ bool tile_get_elev(const DevTerrain& T, const DevTile
         lon_int -= 1;
         lon_frac += 1.0;
     }
-    const int16_t* p = T.posts;
-    double e00 = (double)__ldg(p + post_index(t, lon_int, lat_int));
-    double e01 = (double)__ldg(p + post_index(t, lon_int, lat_int + 1));
-    double e10 = (double)__ldg(p + post_index(t, lon_int + 1, lat_int));
-    double e11 = (double)__ldg(p + post_index(t, lon_int + 1, lat_int + 1));
-    *out = e00 * (1.0 - lon_frac) * (1.0 - lat_frac) + e01 * (1.0 - lon_frac) * lat_frac +
-           e10 * lon_frac * (1.0 - lat_frac) + e11 * lon_frac * lat_frac;
+    *out = bilinear_posts(T.posts, t.post_offset, t.mt_lat, lon_int, lat_int, lon_frac, lat_frac);
     return true;
 }
 
 // Terrain::get_elev, terrain/mod.rs:120-126
 __device__ __forceinline__ bool terrain_get_elev(const DevTerrain& T, double latitude, double longitude, double* out) {
-    int klat = as_i16(floor(latitude)) - T.lat_min;
-    int klon = as_i16(floor(longitude)) - T.lon_min;
+    const double flat = floor(latitude), flon = floor(longitude);
+    int klat = as_i16(flat) - T.lat_min;
+    int klon = as_i16(flon) - T.lon_min;
     if (klat < 0 || klat >= T.nlat_tiles || klon < 0 || klon >= T.nlon_tiles) return false;
     int ti = __ldg(T.lookup + klat * T.nlon_tiles + klon);
     if (ti < 0) return false;
+    if (T.regular && flat == (double)(klat + T.lat_min) && flon == (double)(klon + T.lon_min)) {  // (not a saturated or NaN key)
+        // tile_get_elev with the descriptor of a regular tile: min = the floor (its key), max = min + 1, so the bounds
+        // hold by construction; the same operations on the same values otherwise
+        const double plat = div_by((latitude - flat) * 3600.0, T.r_lat_interval, T.r_inv_lat_interval);
+        const double plon = div_by((longitude - flon) * 3600.0, T.r_lon_interval, T.r_inv_lon_interval);
+        int lat_int = (int)plat, lon_int = (int)plon;
+        double lat_frac = plat - (double)lat_int, lon_frac = plon - (double)lon_int;
+        if (lat_int == T.r_nlat - 1) {
+            lat_int -= 1;
+            lat_frac += 1.0;
+        }
+        if (lon_int == T.r_nlon - 1) {
+            lon_int -= 1;
+            lon_frac += 1.0;
+        }
+        *out = bilinear_posts(T.posts, __ldg(&T.tiles[ti].post_offset), T.r_mt_lat, lon_int, lat_int, lon_frac, lat_frac);
+        return true;
+    }
     return tile_get_elev(T, T.tiles[ti], latitude, longitude, out);
 }
 __device__ __forceinline__ double elev_or_zero(const DevTerrain& T, double lat, double lon) {  // .unwrap_or(0.0)

@@ -1702,7 +1702,7 @@ __global__ void __launch_bounds__(32 * BITS_WARPS, 8) k_sweep_bits(const __grid_
 
 // TerrainData::normal of the listed samples (sample_normal: find_normal at the sample's cached coordinates).
 template <int W>
-__global__ void __launch_bounds__(128) k_hit_normals(const __grid_constant__ DevScene S, DevBuffers B, SweepLists L, int parts) {
+__global__ void __launch_bounds__(128, 8) k_hit_normals(const __grid_constant__ DevScene S, DevBuffers B, SweepLists L, int parts) {
     if (B.sweep_flags[0] != 0) return;
     const int seg = blockIdx.x / parts, part = blockIdx.x % parts;  // seg = column * bands + band
     const int xl = seg / L.bands;
