@@ -6,6 +6,9 @@ Field order and types must match the header exactly; ``tests/test_abi.py`` check
 import ctypes as C
 
 MAX_ATM_FUNCTIONS = 16
+MAX_SPLINE_POINTS = 64
+FUNCTION_LINEAR, FUNCTION_SPLINE = 0, 1
+SPLINE_NATURAL, SPLINE_DERIVATIVES, SPLINE_SECOND_DERIVATIVES = 0, 1, 2
 MAX_OBJECTS = 64
 MAX_STEP_POINTS = 16
 
@@ -30,9 +33,15 @@ class AtmosphereDef(C.Structure):
         ("temperature", C.c_double),
         ("humidity", C.c_double),
         ("n_functions", C.c_int32),
-        ("_pad", C.c_int32),
+        ("n_spline_points", C.c_int32),
         ("fn_start_altitude", C.c_double * MAX_ATM_FUNCTIONS),
         ("fn_gradient", C.c_double * MAX_ATM_FUNCTIONS),
+        ("fn_kind", C.c_int32 * MAX_ATM_FUNCTIONS),
+        ("fn_boundary", C.c_int32 * MAX_ATM_FUNCTIONS),
+        ("fn_boundary_values", (C.c_double * 2) * MAX_ATM_FUNCTIONS),
+        ("fn_first_point", C.c_int32 * MAX_ATM_FUNCTIONS),
+        ("fn_n_points", C.c_int32 * MAX_ATM_FUNCTIONS),
+        ("spline_points", (C.c_double * 2) * MAX_SPLINE_POINTS),
     ]
 
 

@@ -225,17 +225,44 @@ def atmosphere_def(node):
     if len(fns) > abi.MAX_ATM_FUNCTIONS:
         raise ConfigError("too many temperature functions")
     a.n_functions = len(fns)
+    n_points = 0
     for i, (start, fn) in enumerate(fns):
         kind, val = _tagged(fn, "temperature function")
-        if kind != "Linear":
-            raise ConfigError("Spline temperature functions are not supported by the device path yet")
         a.fn_start_altitude[i] = 0.0 if start is None else start
-        a.fn_gradient[i] = float(val["gradient"])
+        if kind == "Linear":
+            a.fn_kind[i] = abi.FUNCTION_LINEAR
+            a.fn_gradient[i] = float(val["gradient"])
+        elif kind == "Spline":
+            a.fn_kind[i] = abi.FUNCTION_SPLINE
+            bc, bc_val = _tagged(val.get("boundary_condition", "Natural"), "boundary_condition")
+            try:
+                a.fn_boundary[i] = {"Natural": abi.SPLINE_NATURAL, "Derivatives": abi.SPLINE_DERIVATIVES,
+                                    "SecondDerivatives": abi.SPLINE_SECOND_DERIVATIVES}[bc]
+            except KeyError:
+                raise ConfigError(f"unknown Spline boundary condition {bc!r}") from None
+            if bc != "Natural":
+                if bc_val is None or len(bc_val) != 2:
+                    raise ConfigError(f"{bc} needs two numbers")
+                a.fn_boundary_values[i][0], a.fn_boundary_values[i][1] = float(bc_val[0]), float(bc_val[1])
+            points = val.get("points") or []
+            if len(points) < 2:
+                raise ConfigError("a Spline needs at least two points")
+            if n_points + len(points) > abi.MAX_SPLINE_POINTS:
+                raise ConfigError("too many Spline points")
+            a.fn_first_point[i], a.fn_n_points[i] = n_points, len(points)
+            for alt, temp in points:
+                a.spline_points[n_points][0], a.spline_points[n_points][1] = float(alt), float(temp)
+                n_points += 1
+        else:
+            raise ConfigError(f"unknown temperature function {kind!r}")
+    a.n_spline_points = n_points
     tfp = node.get("temperature_fixed_point")
-    if tfp is None:
-        raise ConfigError("temperature_fixed_point is required when every function is Linear")
-    a.temperature_altitude = float(tfp["altitude"])
-    a.temperature = float(tfp["temperature"])
+    if n_points == 0:
+        if tfp is None:
+            raise ConfigError("temperature_fixed_point is required when every function is Linear")
+    if tfp is not None:  # README.md:318-323: with a Spline present it "shouldn't be present"; it is then ignored
+        a.temperature_altitude = float(tfp["altitude"])
+        a.temperature = float(tfp["temperature"])
     return a
 
 

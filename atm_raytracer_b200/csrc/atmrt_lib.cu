@@ -201,13 +201,58 @@ int make_layout(atmrt_ctx* ctx, const atmrt_tile_desc* descs, int n, TerrainLayo
 // ---- atmosphere lowering (Atmosphere::from_def; host libm, same as the reference's CPU lowering) --
 constexpr double ATM_G = 9.80665, ATM_M = 0.0289644, ATM_R = 8.31432;  // R* of US Standard Atmosphere 1976
 
-double host_layer_temperature(const DevAtmLayer& l, double h) { return l.t_ref + l.gradient * (h - l.h_ref); }
+double host_cubic_temperature(const DevAtmLayer& l, double h) {
+    const double x = h - l.x0;
+    return std::fma(std::fma(std::fma(l.c3, x, l.c2), x, l.c1), x, l.c0);
+}
+double host_layer_temperature(const DevAtmLayer& l, double h) {
+    if (l.cubic) return host_cubic_temperature(l, h);
+    return l.t_ref + l.gradient * (h - l.h_ref);
+}
+// device_atm.cuh: cubic_inverse_integral
+double host_cubic_inverse_integral(const DevAtmLayer& l, double h) {
+    const double gx[4] = ATMRT_GL8_X, gw[4] = ATMRT_GL8_W;
+    const double half = 0.5 * (h - l.h_ref), mid = 0.5 * (h + l.h_ref);
+    double acc = 0.0;
+    for (int i = 3; i >= 0; --i) acc += gw[i] / host_cubic_temperature(l, mid - half * gx[i]);
+    for (int i = 0; i < 4; ++i) acc += gw[i] / host_cubic_temperature(l, mid + half * gx[i]);
+    return acc * half;
+}
 double host_layer_pressure(const DevAtmLayer& l, double h) {
+    if (l.cubic) return l.p_ref * std::exp(-ATM_G * ATM_M / ATM_R * host_cubic_inverse_integral(l, h));
     if (l.gradient != 0.0) {
         double t = host_layer_temperature(l, h);
         return l.p_ref * std::pow(t / l.t_ref, -ATM_G * ATM_M / (ATM_R * l.gradient));
     }
     return l.p_ref * std::exp(-ATM_G * ATM_M * (h - l.h_ref) / (ATM_R * l.t_ref));
+}
+
+// Second derivatives M[i] of the cubic spline through (x[i], y[i]) under one of the reference's three boundary
+// conditions (README.md:303-309), by the Thomas algorithm on the usual tridiagonal system
+//   h[i-1] M[i-1] + 2 (h[i-1] + h[i]) M[i] + h[i] M[i+1] = 6 ((y[i+1] - y[i]) / h[i] - (y[i] - y[i-1]) / h[i-1]).
+void spline_second_derivatives(const std::vector<double>& x, const std::vector<double>& y, int boundary, double a, double b, std::vector<double>& M) {
+    const int m = (int)x.size();
+    std::vector<double> sub(m, 0.0), diag(m, 1.0), sup(m, 0.0), rhs(m, 0.0);
+    for (int i = 1; i + 1 < m; ++i) {
+        const double h0 = x[i] - x[i - 1], h1 = x[i + 1] - x[i];
+        sub[i] = h0, diag[i] = 2.0 * (h0 + h1), sup[i] = h1;
+        rhs[i] = 6.0 * ((y[i + 1] - y[i]) / h1 - (y[i] - y[i - 1]) / h0);
+    }
+    if (boundary == ATMRT_SPLINE_DERIVATIVES) {
+        const double h0 = x[1] - x[0], hl = x[m - 1] - x[m - 2];
+        diag[0] = 2.0 * h0, sup[0] = h0, rhs[0] = 6.0 * ((y[1] - y[0]) / h0 - a);
+        sub[m - 1] = hl, diag[m - 1] = 2.0 * hl, rhs[m - 1] = 6.0 * (b - (y[m - 1] - y[m - 2]) / hl);
+    } else if (boundary == ATMRT_SPLINE_SECOND_DERIVATIVES) {
+        rhs[0] = a, rhs[m - 1] = b;
+    }
+    for (int i = 1; i < m; ++i) {
+        const double w = sub[i] / diag[i - 1];
+        diag[i] -= w * sup[i - 1];
+        rhs[i] -= w * rhs[i - 1];
+    }
+    M.assign(m, 0.0);
+    M[m - 1] = rhs[m - 1] / diag[m - 1];
+    for (int i = m - 2; i >= 0; --i) M[i] = (rhs[i] - sup[i] * M[i + 1]) / diag[i];
 }
 
 // ---- the g(h) table of the ray-path stage (device_paths.cuh) -----------------------------------
@@ -228,9 +273,20 @@ long double ld_n_minus_1(const LdAtmosphere& A, long double h) {
         if (h >= (long double)a.layer[i].start) idx = i;
     if (A.forced_layer >= 0) idx = A.forced_layer;  // that temperature function's law, continued past its boundaries
     const DevAtmLayer& l = a.layer[idx];
-    const long double t = (long double)l.t_ref + (long double)l.gradient * (h - (long double)l.h_ref);
+    auto cubic_t = [&](long double hh) {
+        const long double x = hh - (long double)l.x0;
+        return (long double)l.c0 + x * ((long double)l.c1 + x * ((long double)l.c2 + x * (long double)l.c3));
+    };
+    const long double t = l.cubic ? cubic_t(h) : (long double)l.t_ref + (long double)l.gradient * (h - (long double)l.h_ref);
     long double p;
-    if (l.gradient != 0.0)
+    if (l.cubic) {  // the same 8-point rule as cubic_inverse_integral, as a function of real numbers
+        static const long double gx[4] = {0.1834346424956498049394761L, 0.5255324099163289858177390L, 0.7966664774136267395915539L, 0.9602898564975362316835609L};
+        static const long double gw[4] = {0.3626837833783619829651504L, 0.3137066458778872873379622L, 0.2223810344533744705443560L, 0.1012285362903762591525314L};
+        const long double half = 0.5L * (h - (long double)l.h_ref), mid = 0.5L * (h + (long double)l.h_ref);
+        long double acc = 0.0L;
+        for (int i = 0; i < 4; ++i) acc += gw[i] / cubic_t(mid - half * gx[i]) + gw[i] / cubic_t(mid + half * gx[i]);
+        p = (long double)l.p_ref * expl(-(long double)ATM_G * ATM_M / (long double)ATM_R * acc * half);
+    } else if (l.gradient != 0.0)
         p = (long double)l.p_ref * powl(t / (long double)l.t_ref, -(long double)ATM_G * ATM_M / ((long double)ATM_R * l.gradient));
     else
         p = (long double)l.p_ref * expl(-(long double)ATM_G * ATM_M * (h - (long double)l.h_ref) / ((long double)ATM_R * l.t_ref));
@@ -367,69 +423,98 @@ void build_g_table(const DevAtmosphere& a, double wavelength, std::vector<double
 }
 
 int lower_atmosphere(atmrt_ctx* ctx, const atmrt_atmosphere_def& def, double wavelength, DevAtmosphere* out) {
-    const int n = def.n_functions;
-    if (n < 1 || n > ATMRT_MAX_ATM_FUNCTIONS) return fail(ctx, ATMRT_ERR_INVALID, "atmosphere: n_functions out of range");
+    const int nf = def.n_functions;
+    const double inf = std::numeric_limits<double>::infinity();
+    if (nf < 1 || nf > ATMRT_MAX_ATM_FUNCTIONS) return fail(ctx, ATMRT_ERR_INVALID, "atmosphere: n_functions out of range");
     DevAtmosphere a{};
-    a.n = n;
     a.humidity = def.humidity;
-    for (int i = 0; i < n; ++i) {
-        a.layer[i].start = i == 0 ? -std::numeric_limits<double>::infinity() : def.fn_start_altitude[i];
-        a.layer[i].gradient = def.fn_gradient[i];
-        if (i >= 2 && !(def.fn_start_altitude[i] > def.fn_start_altitude[i - 1]))
+    // One layer per Linear function, one per segment of a Spline function that reaches into the function's range
+    // [its start, the next function's start); the end segments continue the spline beyond its points.
+    bool any_spline = false;
+    int n = 0;
+    for (int f = 0; f < nf; ++f) {
+        if (f >= 2 && !(def.fn_start_altitude[f] > def.fn_start_altitude[f - 1]))
             return fail(ctx, ATMRT_ERR_INVALID, "atmosphere: function altitudes must increase");
+        const double fs = f == 0 ? -inf : def.fn_start_altitude[f], fe = f + 1 < nf ? def.fn_start_altitude[f + 1] : inf;
+        if (def.fn_kind[f] == ATMRT_FUNCTION_LINEAR) {
+            if (n >= ATM_MAX_LAYERS) return fail(ctx, ATMRT_ERR_INVALID, "atmosphere: more than 32 functions and spline segments");
+            a.layer[n].start = fs;
+            a.layer[n].gradient = def.fn_gradient[f];
+            ++n;
+            continue;
+        }
+        if (def.fn_kind[f] != ATMRT_FUNCTION_SPLINE) return fail(ctx, ATMRT_ERR_INVALID, "atmosphere: unknown temperature function kind");
+        any_spline = true;
+        const int first = def.fn_first_point[f], m = def.fn_n_points[f];
+        if (m < 2 || first < 0 || first + m > def.n_spline_points || def.n_spline_points > ATMRT_MAX_SPLINE_POINTS)
+            return fail(ctx, ATMRT_ERR_INVALID, "atmosphere: a Spline needs at least two points inside spline_points");
+        if (def.fn_boundary[f] < ATMRT_SPLINE_NATURAL || def.fn_boundary[f] > ATMRT_SPLINE_SECOND_DERIVATIVES)
+            return fail(ctx, ATMRT_ERR_INVALID, "atmosphere: unknown Spline boundary condition");
+        std::vector<double> x(m), y(m), M;
+        for (int i = 0; i < m; ++i) {
+            x[i] = def.spline_points[first + i][0], y[i] = def.spline_points[first + i][1];
+            if (i > 0 && !(x[i] > x[i - 1])) return fail(ctx, ATMRT_ERR_INVALID, "atmosphere: Spline point altitudes must increase");
+        }
+        spline_second_derivatives(x, y, def.fn_boundary[f], def.fn_boundary_values[f][0], def.fn_boundary_values[f][1], M);
+        for (int i = 0; i + 1 < m; ++i) {
+            const double lo = i == 0 ? -inf : x[i], hi = i + 2 == m ? inf : x[i + 1];
+            if (!(hi > fs) || !(lo < fe)) continue;  // the segment lies outside the function's range
+            if (n >= ATM_MAX_LAYERS) return fail(ctx, ATMRT_ERR_INVALID, "atmosphere: more than 32 functions and spline segments");
+            const double h = x[i + 1] - x[i];
+            DevAtmLayer& l = a.layer[n++];
+            l.start = std::max(fs, lo);
+            l.cubic = 1;
+            l.x0 = x[i];
+            l.c0 = y[i];
+            l.c1 = (y[i + 1] - y[i]) / h - h * (2.0 * M[i] + M[i + 1]) / 6.0;
+            l.c2 = 0.5 * M[i];
+            l.c3 = (M[i + 1] - M[i]) / (6.0 * h);
+        }
     }
+    a.n = n;
     auto find = [&](double h) {
         int idx = 0;
         for (int i = 1; i < n; ++i)
             if (h >= a.layer[i].start) idx = i;
         return idx;
     };
-    // boundary temperatures by continuity from the temperature fixed point
-    std::vector<double> tb(n, 0.0);
-    const int jt = find(def.temperature_altitude);
-    {
-        double ha = def.temperature_altitude, ta = def.temperature;
-        for (int i = jt; i + 1 < n; ++i) {
-            double t = ta + a.layer[i].gradient * (a.layer[i + 1].start - ha);
-            tb[i + 1] = t;
-            ha = a.layer[i + 1].start;
-            ta = t;
-        }
-        ha = def.temperature_altitude, ta = def.temperature;
-        for (int i = jt; i >= 1; --i) {
-            double t = ta + a.layer[i].gradient * (a.layer[i].start - ha);
-            tb[i] = t;
-            ha = a.layer[i].start;
-            ta = t;
-        }
+    // Temperatures of the Linear layers: anchored at (ha[i], ta[i]) by continuity with a neighbour whose temperature
+    // is known -- the layer holding the temperature fixed point when every function is Linear, the Spline segments
+    // otherwise. Above a known layer the anchor is the lower boundary, below it the upper one.
+    std::vector<double> ha(n, 0.0), ta(n, 0.0);
+    std::vector<char> known(n, 0);
+    auto temp_in = [&](int i, double h) { return a.layer[i].cubic ? host_cubic_temperature(a.layer[i], h) : ta[i] + a.layer[i].gradient * (h - ha[i]); };
+    if (any_spline) {
+        for (int i = 0; i < n; ++i) known[i] = (char)a.layer[i].cubic;
+    } else {
+        const int jt = find(def.temperature_altitude);
+        ha[jt] = def.temperature_altitude, ta[jt] = def.temperature, known[jt] = 1;
     }
-    auto temp_at = [&](double h) {
-        int i = find(h);
-        if (i == jt) return def.temperature + a.layer[i].gradient * (h - def.temperature_altitude);
-        if (i > jt) return tb[i] + a.layer[i].gradient * (h - a.layer[i].start);
-        return tb[i + 1] + a.layer[i].gradient * (h - a.layer[i + 1].start);
-    };
+    for (int i = 0; i + 1 < n; ++i)  // upwards
+        if (known[i] && !known[i + 1]) ha[i + 1] = a.layer[i + 1].start, ta[i + 1] = temp_in(i, a.layer[i + 1].start), known[i + 1] = 1;
+    for (int i = n - 1; i >= 1; --i)  // downwards
+        if (known[i] && !known[i - 1]) ha[i - 1] = a.layer[i].start, ta[i - 1] = temp_in(i, a.layer[i].start), known[i - 1] = 1;
     // reference point per layer: the pressure fixed point in its layer, the lower boundary above it,
     // the upper boundary below it; pressures propagate hydrostatically from the fixed point.
     const int jp = find(def.pressure_altitude);
     a.layer[jp].h_ref = def.pressure_altitude;
-    a.layer[jp].t_ref = temp_at(def.pressure_altitude);
+    a.layer[jp].t_ref = temp_in(jp, def.pressure_altitude);
     a.layer[jp].p_ref = def.pressure;
     for (int i = jp + 1; i < n; ++i) {
         a.layer[i].h_ref = a.layer[i].start;
-        a.layer[i].t_ref = tb[i];
+        a.layer[i].t_ref = temp_in(i, a.layer[i].start);
         a.layer[i].p_ref = host_layer_pressure(a.layer[i - 1], a.layer[i].start);
     }
     for (int i = jp - 1; i >= 0; --i) {
         a.layer[i].h_ref = a.layer[i + 1].start;
-        a.layer[i].t_ref = tb[i + 1];
+        a.layer[i].t_ref = temp_in(i, a.layer[i + 1].start);
         a.layer[i].p_ref = host_layer_pressure(a.layer[i + 1], a.layer[i + 1].start);
     }
     for (int i = 0; i < n; ++i) {
         DevAtmLayer& l = a.layer[i];
         l.gm = -ATM_G * ATM_M;
         l.rt = ATM_R * l.t_ref;
-        l.expo = l.gradient != 0.0 ? -ATM_G * ATM_M / (ATM_R * l.gradient) : 0.0;
+        l.expo = l.cubic ? -ATM_G * ATM_M / ATM_R : l.gradient != 0.0 ? -ATM_G * ATM_M / (ATM_R * l.gradient) : 0.0;
     }
     // Ciddor (1996) wavelength-only terms; 450 ppm CO2.
     const double w0 = 295.235, w1 = 2.6422, w2 = -0.032380, w3 = 0.004028;

@@ -12,22 +12,27 @@
 
 namespace atmrt {
 
-// One temperature function of the atmosphere after host lowering (Atmosphere::from_def): a
-// reference altitude with known temperature and pressure, and the hydrostatic exponent.
+// One law of the atmosphere after host lowering (Atmosphere::from_def): a Linear temperature function, or one
+// segment of a Spline temperature function (its end segments continued to the function's boundaries), with a
+// reference altitude of known temperature and pressure.
+constexpr int ATM_MAX_LAYERS = 32;  // Linear functions + Spline segments of one atmosphere
 struct DevAtmLayer {
     double start;     // lower boundary (-inf for layer 0)
     double h_ref, t_ref, p_ref;
-    double gradient;  // K/m
-    double expo;      // gradient != 0: -g*M/(R*gradient)
+    double gradient;  // K/m (Linear)
+    double expo;      // Linear, gradient != 0: -g*M/(R*gradient); cubic: -g*M/R
     double gm;        // -g*M
     double rt;        // R*t_ref (isothermal layers)
+    double x0, c0, c1, c2, c3;  // cubic: T = c0 + x (c1 + x (c2 + x c3)), x = h - x0
+    int cubic;
+    int _pad;
 };
 
 struct DevAtmosphere {
     int n;
     int _pad;
     double humidity;
-    DevAtmLayer layer[ATMRT_MAX_ATM_FUNCTIONS];
+    DevAtmLayer layer[ATM_MAX_LAYERS];
     // Ciddor terms that depend only on the wavelength (lowered on the host with + - * / only).
     double r_axs, r_vs, m_a, rho_axs;
     double k_dry;  // m_a r_axs / (R rho_axs)
@@ -40,19 +45,45 @@ __device__ __forceinline__ int atm_layer_index(const DevAtmosphere& a, double h)
     return idx;
 }
 
+// Gauss-Legendre, 8 points on [-1, 1]: nodes +-GL8_X[i], weights GL8_W[i].
+#define ATMRT_GL8_X {0.1834346424956498049394761, 0.5255324099163289858177390, 0.7966664774136267395915539, 0.9602898564975362316835609}
+#define ATMRT_GL8_W {0.3626837833783619829651504, 0.3137066458778872873379622, 0.2223810344533744705443560, 0.1012285362903762591525314}
+
+__device__ __forceinline__ double cubic_temperature(const DevAtmLayer& l, double h) {
+    const double x = h - l.x0;
+    return fma(fma(fma(l.c3, x, l.c2), x, l.c1), x, l.c0);
+}
+
 __device__ __forceinline__ double layer_temperature(const DevAtmLayer& l, double h) {
+    if (l.cubic) return cubic_temperature(l, h);
     return l.t_ref + l.gradient * (h - l.h_ref);
 }
 
+// Integral of dh / T over [h_ref, h] inside one Spline segment: the 8-point rule, nodes taken in ascending order
+// (oracle: cubic_inverse_integral).
+__device__ __noinline__ double cubic_inverse_integral(const DevAtmLayer& l, double h) {
+    const double gx[4] = ATMRT_GL8_X, gw[4] = ATMRT_GL8_W;
+    const double half = 0.5 * (h - l.h_ref), mid = 0.5 * (h + l.h_ref);
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 3; i >= 0; --i) acc += gw[i] / cubic_temperature(l, mid - half * gx[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc += gw[i] / cubic_temperature(l, mid + half * gx[i]);
+    return acc * half;
+}
+
 // Hydrostatic pressure inside one layer: p_ref (T/T_ref)^expo for a linear temperature function,
-// p_ref exp(-g M (h - h_ref) / (R T_ref)) for an isothermal one. pow() is evaluated as
+// p_ref exp(-g M (h - h_ref) / (R T_ref)) for an isothermal one, p_ref exp(-g M / R * integral of dh / T) for a
+// Spline segment. pow() is evaluated as
 // exp(expo * log(x)) because this sits on the serial critical path of the ray stepper (pow costs 740
 // dependent cycles on B200, log + exp 430): for x in [0.5, 1.5] and |expo| < 40 that stays within
 // ~3 ulp of the correctly rounded power -- far below the half-ulp-of-n noise (4e-7 relative in
 // dn/dh) that the reference's finite-difference derivative carries anyway.
 __device__ __forceinline__ double layer_pressure(const DevAtmLayer& l, double h, double t) {
     double arg;
-    if (l.gradient != 0.0)
+    if (l.cubic)
+        arg = l.expo * cubic_inverse_integral(l, h);
+    else if (l.gradient != 0.0)
         arg = l.expo * log(t / l.t_ref);
     else
         arg = l.gm * (h - l.h_ref) / l.rt;

@@ -217,6 +217,11 @@ struct BlockParser {
                     lines[pos].indent = child;
                     lines[pos].text = rest;
                     n.seq.push_back(block(child));
+                } else if (rest.rfind("- ", 0) == 0) {
+                    // "- - value" starts a nested list whose other items follow at the column of the inner dash
+                    lines[pos].indent = child;
+                    lines[pos].text = rest;
+                    n.seq.push_back(block(child));
                 } else {
                     ++pos;
                     n.seq.push_back(parse_inline(rest));
@@ -457,13 +462,44 @@ static void apply_yaml(const Node& doc, Config* c) {
                 std::string tag;
                 const Node* body;
                 tagged(*fns[i].second, "temperature function", &tag, &body);
-                if (tag != "Linear") throw std::runtime_error("Spline temperature functions are not supported by the device path yet");
                 a.fn_start_altitude[i] = fns[i].first;
-                a.fn_gradient[i] = num(*body, "gradient", 0.0);
+                if (tag == "Linear") {
+                    a.fn_kind[i] = ATMRT_FUNCTION_LINEAR;
+                    a.fn_gradient[i] = num(*body, "gradient", 0.0);
+                    continue;
+                }
+                if (tag != "Spline") throw std::runtime_error("unknown temperature function '" + tag + "'");
+                a.fn_kind[i] = ATMRT_FUNCTION_SPLINE;
+                a.fn_boundary[i] = ATMRT_SPLINE_NATURAL;
+                if (const Node* bc = body->get("boundary_condition")) {
+                    std::string bc_tag;
+                    const Node* bc_body;
+                    tagged(*bc, "boundary_condition", &bc_tag, &bc_body);
+                    if (bc_tag == "Derivatives")
+                        a.fn_boundary[i] = ATMRT_SPLINE_DERIVATIVES;
+                    else if (bc_tag == "SecondDerivatives")
+                        a.fn_boundary[i] = ATMRT_SPLINE_SECOND_DERIVATIVES;
+                    else if (bc_tag != "Natural")
+                        throw std::runtime_error("unknown Spline boundary condition '" + bc_tag + "'");
+                    if (bc_tag != "Natural") {
+                        if (bc_body->kind != Node::Seq || bc_body->seq.size() != 2) throw std::runtime_error(bc_tag + " needs two numbers");
+                        a.fn_boundary_values[i][0] = bc_body->seq[0].as_double(bc_tag), a.fn_boundary_values[i][1] = bc_body->seq[1].as_double(bc_tag);
+                    }
+                }
+                const Node* pts = body->get("points");
+                if (!pts || pts->kind != Node::Seq || pts->seq.size() < 2) throw std::runtime_error("a Spline needs at least two points");
+                if (a.n_spline_points + (int)pts->seq.size() > ATMRT_MAX_SPLINE_POINTS) throw std::runtime_error("too many Spline points");
+                a.fn_first_point[i] = a.n_spline_points, a.fn_n_points[i] = (int)pts->seq.size();
+                for (const Node& pt : pts->seq) {
+                    if (pt.kind != Node::Seq || pt.seq.size() != 2) throw std::runtime_error("a Spline point is a pair (altitude, temperature)");
+                    a.spline_points[a.n_spline_points][0] = pt.seq[0].as_double("Spline point altitude");
+                    a.spline_points[a.n_spline_points][1] = pt.seq[1].as_double("Spline point temperature");
+                    ++a.n_spline_points;
+                }
             }
             const Node* tfp = atm->get("temperature_fixed_point");
-            if (!tfp) throw std::runtime_error("temperature_fixed_point is required when every function is Linear");
-            a.temperature_altitude = num(*tfp, "altitude", 0.0), a.temperature = num(*tfp, "temperature", 288.15);
+            if (!tfp && a.n_spline_points == 0) throw std::runtime_error("temperature_fixed_point is required when every function is Linear");
+            if (tfp) a.temperature_altitude = num(*tfp, "altitude", 0.0), a.temperature = num(*tfp, "temperature", 288.15);  // ignored beside a Spline (README.md:318-323)
             c->atmosphere = a;
         }
     }

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ATMRT_ABI_VERSION 1
+#define ATMRT_ABI_VERSION 2
 #define ATMRT_MAX_ATM_FUNCTIONS 16 /* temperature functions in an atmosphere definition */
 #define ATMRT_MAX_OBJECTS 64       /* objects_close is a 64-bit mask per terrain sample  */
 #define ATMRT_MAX_STEP_POINTS 16   /* trace points produced by ONE march step (overflow is counted) */
@@ -68,8 +68,17 @@ typedef enum atmrt_palette { ATMRT_PALETTE_LEGACY = 0, ATMRT_PALETTE_IMPROVED = 
 
 /* AtmosphereDef of the external `atm-refraction` crate as the reference's YAML exposes it
  * (README.md:281-323). Function 0 is `first_temperature_function` (valid from -infinity);
- * function i>0 starts at fn_start_altitude[i]. Only `Linear{gradient}` functions are supported on
- * the device in this round (Spline -> ATMRT_ERR_INVALID). */
+ * function i>0 starts at fn_start_altitude[i]. A function is `Linear{gradient}` or
+ * `Spline{boundary_condition, points}`: a cubic spline through its (altitude, temperature) points with a
+ * Natural / Derivatives[a, b] / SecondDerivatives[a, b] boundary condition, continued by its end cubics where its
+ * altitude range reaches beyond the points. Temperatures: a Spline is absolute; a Linear function is continuous with
+ * its neighbour towards the nearest Spline, or -- when every function is Linear -- towards the temperature fixed
+ * point (ignored when a Spline is present, as the README prescribes). Pressure is hydrostatic from the pressure fixed
+ * point; inside a Spline function the integral of dh / T is taken with an 8-point Gauss-Legendre rule per spline
+ * segment (the crate's own quadrature is not known here). */
+#define ATMRT_MAX_SPLINE_POINTS 64 /* points of all Spline functions of one atmosphere together */
+typedef enum atmrt_function_kind { ATMRT_FUNCTION_LINEAR = 0, ATMRT_FUNCTION_SPLINE = 1 } atmrt_function_kind;
+typedef enum atmrt_spline_boundary { ATMRT_SPLINE_NATURAL = 0, ATMRT_SPLINE_DERIVATIVES = 1, ATMRT_SPLINE_SECOND_DERIVATIVES = 2 } atmrt_spline_boundary;
 typedef struct atmrt_atmosphere_def {
     double pressure_altitude; /* pressure fixed point */
     double pressure;          /* Pa */
@@ -77,9 +86,15 @@ typedef struct atmrt_atmosphere_def {
     double temperature;          /* K */
     double humidity;             /* relative humidity 0..1, constant with altitude (default 0) */
     int32_t n_functions;         /* >= 1 */
-    int32_t _pad;
+    int32_t n_spline_points;     /* entries of spline_points in use */
     double fn_start_altitude[ATMRT_MAX_ATM_FUNCTIONS]; /* [0] unused */
-    double fn_gradient[ATMRT_MAX_ATM_FUNCTIONS];       /* K per metre */
+    double fn_gradient[ATMRT_MAX_ATM_FUNCTIONS];       /* Linear: K per metre */
+    int32_t fn_kind[ATMRT_MAX_ATM_FUNCTIONS];          /* atmrt_function_kind */
+    int32_t fn_boundary[ATMRT_MAX_ATM_FUNCTIONS];      /* Spline: atmrt_spline_boundary */
+    double fn_boundary_values[ATMRT_MAX_ATM_FUNCTIONS][2]; /* Spline: [a, b] of Derivatives / SecondDerivatives */
+    int32_t fn_first_point[ATMRT_MAX_ATM_FUNCTIONS];   /* Spline: its points are spline_points[first .. first + n) */
+    int32_t fn_n_points[ATMRT_MAX_ATM_FUNCTIONS];      /* Spline: >= 2, altitudes strictly increasing */
+    double spline_points[ATMRT_MAX_SPLINE_POINTS][2];  /* (altitude m, temperature K) */
 } atmrt_atmosphere_def;
 
 /* Flat POD image of the reference's `Params` (generator/params.rs:496-505). */

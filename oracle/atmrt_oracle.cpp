@@ -363,11 +363,15 @@ struct AtmLayer {
     double start;   // lower boundary (-inf for layer 0)
     double h_ref, t_ref, p_ref;
     double gradient;
+    // One segment of a Spline temperature function: T = k[0] + k[1] x + k[2] x^2 + k[3] x^3, x = h - origin.
+    bool spline_segment;
+    double origin, k[4];
 };
 
+constexpr int ORACLE_MAX_LAYERS = 32;  // Linear functions + Spline segments
 struct Atmosphere {
     int n;
-    AtmLayer layer[ATMRT_MAX_ATM_FUNCTIONS];
+    AtmLayer layer[ORACLE_MAX_LAYERS];
     double humidity;
 };
 
@@ -378,9 +382,31 @@ int atm_layer_index(const Atmosphere& a, double h) {
     return idx;
 }
 
-double layer_temperature(const AtmLayer& l, double h) { return l.t_ref + l.gradient * (h - l.h_ref); }
+double segment_temperature(const AtmLayer& l, double h) {
+    const double x = h - l.origin;
+    return std::fma(std::fma(std::fma(l.k[3], x, l.k[2]), x, l.k[1]), x, l.k[0]);
+}
+
+double layer_temperature(const AtmLayer& l, double h) {
+    if (l.spline_segment) return segment_temperature(l, h);
+    return l.t_ref + l.gradient * (h - l.h_ref);
+}
+
+// Integral of dh / T from the segment's reference altitude to h with the 8-point Gauss-Legendre rule (include/atmrt.h:
+// the documented quadrature of the hydrostatic integral inside a Spline function), nodes visited in ascending order.
+double cubic_inverse_integral(const AtmLayer& l, double h) {
+    static const double node[8] = {-0.9602898564975362316835609, -0.7966664774136267395915539, -0.5255324099163289858177390, -0.1834346424956498049394761,
+                                   0.1834346424956498049394761,  0.5255324099163289858177390,  0.7966664774136267395915539,  0.9602898564975362316835609};
+    static const double weight[8] = {0.1012285362903762591525314, 0.2223810344533744705443560, 0.3137066458778872873379622, 0.3626837833783619829651504,
+                                     0.3626837833783619829651504, 0.3137066458778872873379622, 0.2223810344533744705443560, 0.1012285362903762591525314};
+    const double half = 0.5 * (h - l.h_ref), mid = 0.5 * (h + l.h_ref);
+    double sum = 0.0;
+    for (int i = 0; i < 8; ++i) sum += weight[i] / segment_temperature(l, mid + half * node[i]);
+    return sum * half;
+}
 
 double layer_pressure(const AtmLayer& l, double h) {
+    if (l.spline_segment) return l.p_ref * std::exp(-ATM_G * ATM_M / ATM_R * cubic_inverse_integral(l, h));
     if (l.gradient != 0.0) {
         double t = layer_temperature(l, h);
         return l.p_ref * std::pow(t / l.t_ref, -ATM_G * ATM_M / (ATM_R * l.gradient));
@@ -388,10 +414,122 @@ double layer_pressure(const AtmLayer& l, double h) {
     return l.p_ref * std::exp(-ATM_G * ATM_M * (h - l.h_ref) / (ATM_R * l.t_ref));
 }
 
-// Atmosphere::from_def for Linear-only definitions.
+// Atmosphere::from_def with at least one Spline function (README.md:296-323). The spline's second derivatives come
+// from the classical forward-elimination / back-substitution recurrence (decomposition factors `u`, as in the textbook
+// routine), the cubic of segment i is then
+//   T = y_i + x ((y_{i+1} - y_i) / d - d (2 z_i + z_{i+1}) / 6) + x^2 z_i / 2 + x^3 (z_{i+1} - z_i) / (6 d),  d = x_{i+1} - x_i.
+bool atmosphere_with_splines(const atmrt_atmosphere_def& def, Atmosphere* out) {
+    const double inf = std::numeric_limits<double>::infinity();
+    Atmosphere a{};
+    a.humidity = def.humidity;
+    int n = 0;
+    for (int f = 0; f < def.n_functions; ++f) {
+        if (f >= 2 && !(def.fn_start_altitude[f] > def.fn_start_altitude[f - 1])) return false;
+        const double from = f == 0 ? -inf : def.fn_start_altitude[f];
+        const double to = f + 1 < def.n_functions ? def.fn_start_altitude[f + 1] : inf;
+        if (def.fn_kind[f] == ATMRT_FUNCTION_LINEAR) {
+            if (n == ORACLE_MAX_LAYERS) return false;
+            a.layer[n].start = from;
+            a.layer[n].gradient = def.fn_gradient[f];
+            ++n;
+            continue;
+        }
+        if (def.fn_kind[f] != ATMRT_FUNCTION_SPLINE) return false;
+        const int m = def.fn_n_points[f], p0 = def.fn_first_point[f];
+        if (m < 2 || p0 < 0 || p0 + m > def.n_spline_points || def.n_spline_points > ATMRT_MAX_SPLINE_POINTS) return false;
+        const double (*pt)[2] = def.spline_points + p0;
+        for (int i = 1; i < m; ++i)
+            if (!(pt[i][0] > pt[i - 1][0])) return false;
+        std::vector<double> z(m, 0.0), u(m, 0.0);
+        const int bc = def.fn_boundary[f];
+        const double bc0 = def.fn_boundary_values[f][0], bc1 = def.fn_boundary_values[f][1];
+        // row 0: z_0 = -1/2 z_1 + u_0 (Derivatives) or z_0 = value (Natural: 0)
+        if (bc == ATMRT_SPLINE_DERIVATIVES) {
+            z[0] = -0.5;
+            u[0] = (3.0 / (pt[1][0] - pt[0][0])) * ((pt[1][1] - pt[0][1]) / (pt[1][0] - pt[0][0]) - bc0);
+        } else if (bc == ATMRT_SPLINE_SECOND_DERIVATIVES) {
+            u[0] = bc0;
+        } else if (bc != ATMRT_SPLINE_NATURAL) {
+            return false;
+        }
+        for (int i = 1; i + 1 < m; ++i) {
+            const double sig = (pt[i][0] - pt[i - 1][0]) / (pt[i + 1][0] - pt[i - 1][0]);
+            const double piv = sig * z[i - 1] + 2.0;
+            z[i] = (sig - 1.0) / piv;
+            const double dd = (pt[i + 1][1] - pt[i][1]) / (pt[i + 1][0] - pt[i][0]) - (pt[i][1] - pt[i - 1][1]) / (pt[i][0] - pt[i - 1][0]);
+            u[i] = (6.0 * dd / (pt[i + 1][0] - pt[i - 1][0]) - sig * u[i - 1]) / piv;
+        }
+        double qn = 0.0, un = 0.0;  // last row: z_{m-1} = (un - qn u_{m-2}) / (qn z_{m-2} + 1)
+        if (bc == ATMRT_SPLINE_DERIVATIVES) {
+            const double d = pt[m - 1][0] - pt[m - 2][0];
+            qn = 0.5;
+            un = (3.0 / d) * (bc1 - (pt[m - 1][1] - pt[m - 2][1]) / d);
+        } else if (bc == ATMRT_SPLINE_SECOND_DERIVATIVES) {
+            un = bc1;
+        }
+        z[m - 1] = (un - qn * u[m - 2]) / (qn * z[m - 2] + 1.0);
+        for (int i = m - 2; i >= 0; --i) z[i] = z[i] * z[i + 1] + u[i];
+        for (int i = 0; i + 1 < m; ++i) {
+            const double lo = i == 0 ? -inf : pt[i][0], hi = i + 2 == m ? inf : pt[i + 1][0];
+            if (hi <= from || lo >= to) continue;
+            if (n == ORACLE_MAX_LAYERS) return false;
+            const double d = pt[i + 1][0] - pt[i][0];
+            AtmLayer& l = a.layer[n++];
+            l.start = lo > from ? lo : from;
+            l.spline_segment = true;
+            l.origin = pt[i][0];
+            l.k[0] = pt[i][1];
+            l.k[1] = (pt[i + 1][1] - pt[i][1]) / d - d * (2.0 * z[i] + z[i + 1]) / 6.0;
+            l.k[2] = z[i] / 2.0;
+            l.k[3] = (z[i + 1] - z[i]) / (6.0 * d);
+        }
+    }
+    a.n = n;
+    // Linear layers take their temperature from the nearest Spline by continuity: sweep up, then down.
+    // A Linear layer is written as T = t_fix + gradient (h - h_fix); keep (h_fix, t_fix) in (h_ref, t_ref) for now.
+    std::vector<bool> have(n);
+    for (int i = 0; i < n; ++i) have[i] = a.layer[i].spline_segment;
+    for (int i = 1; i < n; ++i)
+        if (!have[i] && have[i - 1]) {
+            a.layer[i].h_ref = a.layer[i].start;
+            a.layer[i].t_ref = layer_temperature(a.layer[i - 1], a.layer[i].start);
+            have[i] = true;
+        }
+    for (int i = n - 2; i >= 0; --i)
+        if (!have[i] && have[i + 1]) {
+            a.layer[i].h_ref = a.layer[i + 1].start;
+            a.layer[i].t_ref = layer_temperature(a.layer[i + 1], a.layer[i + 1].start);
+            have[i] = true;
+        }
+    // Pressure reference points, outwards from the pressure fixed point (as in the Linear-only lowering below).
+    int jp = 0;
+    for (int i = 1; i < n; ++i)
+        if (def.pressure_altitude >= a.layer[i].start) jp = i;
+    auto move_reference = [&](AtmLayer& l, double h) {  // after this, (h_ref, t_ref) is the pressure reference point
+        const double t = layer_temperature(l, h);
+        l.h_ref = h;
+        l.t_ref = t;
+    };
+    move_reference(a.layer[jp], def.pressure_altitude);
+    a.layer[jp].p_ref = def.pressure;
+    for (int i = jp + 1; i < n; ++i) {
+        move_reference(a.layer[i], a.layer[i].start);
+        a.layer[i].p_ref = layer_pressure(a.layer[i - 1], a.layer[i].start);
+    }
+    for (int i = jp - 1; i >= 0; --i) {
+        move_reference(a.layer[i], a.layer[i + 1].start);
+        a.layer[i].p_ref = layer_pressure(a.layer[i + 1], a.layer[i + 1].start);
+    }
+    *out = a;
+    return true;
+}
+
+// Atmosphere::from_def.
 bool atmosphere_from_def(const atmrt_atmosphere_def& def, Atmosphere* out) {
     int n = def.n_functions;
     if (n < 1 || n > ATMRT_MAX_ATM_FUNCTIONS) return false;
+    for (int i = 0; i < n; ++i)
+        if (def.fn_kind[i] != ATMRT_FUNCTION_LINEAR) return atmosphere_with_splines(def, out);
     Atmosphere a{};
     a.n = n;
     a.humidity = def.humidity;

@@ -38,7 +38,7 @@ def test_struct_sizes_match_the_header():
     mirror = [abi.Altitude, abi.AtmosphereDef, abi.Params, abi.TileDesc, abi.Object, abi.Meta, abi.TracePoint, abi.Stats, abi.StageMs, abi.KernelMs]
     assert n == len(mirror)
     assert [out[i] for i in range(n)] == [C.sizeof(m) for m in mirror]
-    assert runtime.lib.atmrt_abi_version() == 1
+    assert runtime.lib.atmrt_abi_version() == 2
 
 
 def test_packed_terrain_size_needs_no_gpu():

@@ -107,6 +107,9 @@ def test_custom_atmosphere_and_scope_errors(tmp_path):
     a = config.into_params(cfg).atmosphere
     assert a.n_functions == 2 and a.fn_gradient[0] == 0.01 and a.fn_start_altitude[1] == 300.0 and a.temperature == 283.0
     cfg["atmosphere"]["first_temperature_function"] = {"Spline": {"points": [[0, 288.0], [100, 287.0]], "boundary_condition": "Natural"}}
+    a = config.into_params(cfg).atmosphere
+    assert a.fn_kind[0] == abi.FUNCTION_SPLINE and a.fn_boundary[0] == abi.SPLINE_NATURAL and a.n_spline_points == 2
+    cfg["atmosphere"]["first_temperature_function"] = {"Spline": {"points": [[0, 288.0]]}}
     with pytest.raises(config.ConfigError):
         config.into_params(cfg)
     # every EarthModel of the reference lowers (earth_model/mod.rs:19-28); the parameterless ones as the reference lowers them

@@ -73,7 +73,7 @@ def _fields(s, skip=()):
         if isinstance(v, C.Structure):
             out[name] = _fields(v)
         elif isinstance(v, C.Array):
-            out[name] = list(v)
+            out[name] = [list(x) if isinstance(x, C.Array) else x for x in v]
         else:
             out[name] = v
     return out
@@ -94,7 +94,43 @@ def _same_params(a, b):
     assert fa == fb
 
 
-@pytest.mark.parametrize("text", [YAML, BLOCK_YAML], ids=["flow", "block"])
+# The README's own Spline example (README.md:296-316: nested block lists), and the compact spellings of the same
+SPLINE_YAML = """
+atmosphere:
+    pressure:
+        altitude: 0.0
+        pressure: 101325
+    first_temperature_function:
+        Linear:
+            gradient: -0.0065
+    next_functions:
+        - altitude: 100.0
+          function:
+            Spline:
+                boundary_condition:
+                    Derivatives:
+                        - -0.0065
+                        - 0.0
+                points:
+                    -
+                        - 100.0
+                        - 288.0
+                    -
+                        - 110.0
+                        - 285.0
+                    - - 120.0
+                      - 291.0
+        - altitude: 400.0
+          function:
+            Spline:
+                boundary_condition: Natural
+                points: [[400.0, 290.0], [600.0, 288.0], [1000.0, 286.0]]
+        - altitude: 1000.0
+          function: {Spline: {boundary_condition: {SecondDerivatives: [1.0e-6, 0.0]}, points: [[1000.0, 286.0], [3000.0, 270.0]]}}
+"""
+
+
+@pytest.mark.parametrize("text", [YAML, BLOCK_YAML, SPLINE_YAML], ids=["flow", "block", "spline"])
 def test_cpp_yaml_parser_matches_pyyaml(tmp_path, text):
     f = tmp_path / "c.yaml"
     f.write_text(text)
