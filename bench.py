@@ -242,11 +242,19 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    # host-side rendezvous for the end-to-end leg: a rank waiting in an NCCL barrier keeps a spinning kernel on its
+    # GPU, which the one process that drives all N GPUs there would have to time-slice with
+    standby_group = dist.new_group(backend="gloo") if world > 1 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def standby():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=standby_group)
 
     cfg, params, terrain, objects, textures = build_workload(args.workload, args.scale, rank == 0, args.generator)
     my = parallel.shard_params(params, rank, world)
@@ -317,10 +325,11 @@ def run_b200(args):
         # uploads the decoded DTED tiles from page-locked host memory -- each GPU a slice over its own PCIe link, the
         # slices all-gathered over NVLink -- retiles, renders the column blocks and lands every block in the host's
         # row-major image (and metadata) over each GPU's own link. Under torchrun rank 0 is that process; the other
-        # ranks stand by at the barrier with their GPUs idle.
+        # ranks stand by at a host-side (gloo) barrier with their GPUs idle.
         del rgb, meta
         torch.cuda.empty_cache()
         barrier()
+        standby()
         if rank == 0:
             group = runtime.Group(world)
             tiles_pinned = []
@@ -357,7 +366,7 @@ def run_b200(args):
             group.close()
             if world == 1:
                 e2e_gen = time_gen_executable()
-        barrier()
+        standby()
 
     if rank != 0:
         if world > 1:
