@@ -90,7 +90,7 @@ struct atmrt_ctx {
     double atm_table_wavelength = 0.0;
     int path_mode = 0;  // 0: g(h) from the table, 1: every evaluation through libm (validation)
     DevBuf d_atm_cells;
-    DevBuf d_sweep_flags, d_sweep_col, d_sweep_hit;
+    DevBuf d_sweep_flags, d_sweep_col, d_sweep_hit, d_cross;
     DevBuf d_anchor;  // walk anchors of stage A, [wl][n_anchor]
     bool walk_anchors = true;
     DevBuf d_list, d_count, d_normals;  // stage C: the distinct hit samples of every column and their normals
@@ -936,6 +936,9 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
     const bool trace = rt.points != nullptr || rt.counts != nullptr;
     const bool brute = ctx->march_mode == 1, objs = S.nobjects > 0;
     const bool sweep = ctx->sweep_enabled && !objs && !trace && !brute && ctx->params.terrain_alpha == 1.0;
+    // Translucent terrain and / or objects: the crossing march (kernels.cuh) under the same device-side check, with the
+    // hierarchical march behind it.
+    const bool cross = ctx->sweep_enabled && !sweep && !trace && !brute;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_sweep_flags.p, 0, 16, main));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_prep, main));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_a, ctx->ev_prep, 0));
@@ -965,7 +968,7 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
                                                           only_if_not_swept ? B.sweep_flags : nullptr);
         ctx->launches += 2;
     };
-    if (sweep) {
+    if (sweep || cross) {
         k_path_check<<<dim3((h + 255) / 256, (S.n_t + 63) / 64), 256, 0, ctx->s_b>>>(B.p_elev, B.p_n, h, S.h_pad, S.n_t, B.sweep_flags);
         ctx->launches++;
     } else {
@@ -995,7 +998,7 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
                                                         only_if_not_swept ? B.sweep_flags : nullptr);
         ctx->launches += 2;
     };
-    if (!sweep) terrain_pyramids(ctx->s_a, 0);
+    if (!sweep && !cross) terrain_pyramids(ctx->s_a, 0);
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->a1, ctx->s_a));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->s_a));
 
@@ -1063,6 +1066,21 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         k_march<false, false, false><<<fgrid, MARCH_THREADS, 0, main>>>(S, B, O, MARCH_IF_NOT_SWEPT);
         k_march<false, true, false><<<fgrid, MARCH_THREADS, 0, main>>>(S, B, O, MARCH_FLAGGED_COLUMNS);
         ctx->launches += 2;
+    } else if (cross) {
+        if ((rc = ensure(ctx, ctx->d_cross, sizeof(unsigned short) * (size_t)wl * S.n_pad))) return rc;
+        unsigned short* thresholds = (unsigned short*)ctx->d_cross.p;
+        const int bands = (h + CROSS_BAND - 1) / CROSS_BAND;
+        KT_BEGIN(ATMRT_KERNEL_MARCH, main)
+        k_thresholds<<<dim3((S.n_t + 127) / 128, wl), 128, 0, main>>>(S, B, thresholds, objs ? 1 : 0);
+        if (objs) k_cross_march<true><<<dim3((bands + CROSS_WARPS - 1) / CROSS_WARPS, wl), 32 * CROSS_WARPS, 0, main>>>(S, B, O, thresholds);
+        else k_cross_march<false><<<dim3((bands + CROSS_WARPS - 1) / CROSS_WARPS, wl), 32 * CROSS_WARPS, 0, main>>>(S, B, O, thresholds);
+        // the fallback, a no-op unless the rays of this render cross
+        terrain_pyramids(main, 1);
+        path_pyramids(main, 1);
+        if (objs) k_march<true, false, false><<<dim3(grid.x, std::min(wl, 64)), MARCH_THREADS, 0, main>>>(S, B, O, MARCH_IF_NOT_SWEPT);
+        else k_march<false, false, false><<<dim3(grid.x, std::min(wl, 64)), MARCH_THREADS, 0, main>>>(S, B, O, MARCH_IF_NOT_SWEPT);
+        KT_END(ATMRT_KERNEL_MARCH, main)
+        ctx->launches += 3;
     } else {
         KT_BEGIN(ATMRT_KERNEL_MARCH, main)
 #define ATMRT_LAUNCH_MARCH(OB, BR, TR) k_march<OB, BR, TR><<<grid, MARCH_THREADS, 0, main>>>(S, B, O, MARCH_ALWAYS)
@@ -1214,7 +1232,7 @@ void atmrt_destroy(atmrt_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_objects_in, &ctx->d_objects, &ctx->d_dist, &ctx->d_colcalc, &ctx->d_tlat, &ctx->d_tlon, &ctx->d_telev,
                       &ctx->d_tclose, &ctx->d_pdist, &ctx->d_pelev, &ctx->d_plen, &ctx->d_pn,
                       &ctx->d_tmin1, &ctx->d_tmax1, &ctx->d_tmin2, &ctx->d_tmax2, &ctx->d_tmin3, &ctx->d_tmax3, &ctx->d_close1, &ctx->d_close2, &ctx->d_close3, &ctx->d_rmin1, &ctx->d_rmin3, &ctx->d_rmax3,
-                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_sweep_flags, &ctx->d_sweep_col, &ctx->d_sweep_hit, &ctx->d_list, &ctx->d_count, &ctx->d_normals, &ctx->d_anchor, &ctx->d_stage, &ctx->d_atm_aux, &ctx->d_rgb, &ctx->d_meta,
+                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_sweep_flags, &ctx->d_sweep_col, &ctx->d_sweep_hit, &ctx->d_cross, &ctx->d_list, &ctx->d_count, &ctx->d_normals, &ctx->d_anchor, &ctx->d_stage, &ctx->d_atm_aux, &ctx->d_rgb, &ctx->d_meta,
                       &ctx->d_steps, &ctx->d_points, &ctx->d_counts, &ctx->d_probe_a, &ctx->d_probe_b, &ctx->d_probe_c, &ctx->d_probe_d};
     for (DevBuf* b : bufs) release(*b);
     for (DevBuf& b : ctx->textures) release(b);

@@ -1288,6 +1288,151 @@ __global__ void __launch_bounds__(MARCH_THREADS, 16) k_march(const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
+// Stage C, general case (translucent terrain and / or objects), when the rays of the render do not cross: the
+// crossing march.
+//
+// get_single_pixel (utils.rs:201-289) looks at every step of every ray, and acts at the steps where
+// diff1 * diff2 < 0 or an object is close. When the rays of a column are ordered -- r[k][y] >= r[k][y+1], a NaN
+// ray only above a finite one, an upper ray at least as long as a lower one: what k_path_check verifies on the
+// path cache of THIS render -- "the ray is above the terrain at step k" is a monotone predicate of the row, so
+// one number per terrain sample describes a whole column of pixels at that step: Y[x][k], how many rows (from the
+// top) have r - t > 0 (or NaN). A pixel (x, y) can only have a sign change at step k if y lies between Y[x][k-1]
+// and Y[x][k]; the steps with a close object concern every row.
+//
+//   k_thresholds    one thread per terrain sample: Y[x][k] by bisection over the rows that are still alive
+//                   at step k, and the flag "an object is close at step k - 1 or k".
+//   k_cross_march   one warp per (column, band of CROSS_BAND rows) walks the thresholds of its column in windows
+//                   of 32 steps and queues the (step, row) pairs of its band in step order; whenever 32 are
+//                   queued the lanes take one each and run the reference's step on it (process_step: the exact
+//                   product test, interpolation, normals, objects, stable sort, compositing) on the pixel's
+//                   state, which lives in shared memory. Pairs of the same row inside one batch run in queue
+//                   order. The candidates are a superset of the reference's events (an exact zero or a NaN on
+//                   one side changes the predicate without being an event; process_step tests the product), so
+//                   the result is the general march's, pixel for pixel.
+//
+// Both return at once when k_path_check found crossing rays; the general march then runs behind them.
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned CROSS_CLOSE = 0x8000u;  // Y holds a row count <= 32767 (atmrt_set_params limits the height)
+constexpr int CROSS_BAND = 64;             // rows per warp
+constexpr int CROSS_WARPS = 4;
+constexpr int CROSS_QUEUE = 128;           // >= 31 + CROSS_BAND, a power of two
+
+__global__ void __launch_bounds__(128) k_thresholds(const __grid_constant__ DevScene S, DevBuffers B, unsigned short* __restrict__ thresholds,
+                                                    int objects) {
+    if (B.sweep_flags[0] != 0) return;
+    const int k = blockIdx.x * 128 + threadIdx.x, xl = blockIdx.y;
+    if (k >= S.n_t) return;
+    // rows alive at step k: p_n[y] > k, and p_n does not increase with y
+    int lo = 0, hi = S.height;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (B.p_n[mid] > k) lo = mid + 1;
+        else hi = mid;
+    }
+    const size_t ti = (size_t)xl * S.n_pad + k;
+    const double t = B.t_elev[ti];
+    hi = lo, lo = 0;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const double d = B.p_elev[path_index(S.n_t, k, mid)] - t;
+        if (!(d <= 0.0)) lo = mid + 1;
+        else hi = mid;
+    }
+    unsigned v = (unsigned)lo;
+    if (objects && k >= 1 && (B.t_close[ti - 1] | B.t_close[ti]) != 0) v |= CROSS_CLOSE;
+    thresholds[ti] = (unsigned short)v;
+}
+
+struct CrossPixel {
+    PixelState st;
+    int nlim;    // steps of the ray inside the terrain profile
+    int done_k;  // the step the pixel finished at, -1 while it is live
+};
+
+template <bool OBJECTS>
+__global__ void __launch_bounds__(32 * CROSS_WARPS) k_cross_march(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O,
+                                                                  const unsigned short* __restrict__ thresholds) {
+    if (B.sweep_flags[0] != 0) return;
+    __shared__ CrossPixel pix_smem[CROSS_WARPS][CROSS_BAND];
+    __shared__ int queue_smem[CROSS_WARPS][CROSS_QUEUE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int xl = blockIdx.y, wl = S.x1 - S.x0;
+    const int b0 = (blockIdx.x * CROSS_WARPS + warp) * CROSS_BAND;
+    if (b0 >= S.height) return;
+    const int b1 = min(b0 + CROSS_BAND, S.height);
+    CrossPixel* pix = pix_smem[warp];
+    int* queue = queue_smem[warp];
+    int nmax = 0;
+    for (int r = lane; r < CROSS_BAND; r += 32) {
+        CrossPixel& c = pix[r];
+        init_pixel(c.st);
+        c.nlim = b0 + r < b1 ? min(S.n_t, B.p_n[b0 + r]) : 0;
+        c.done_k = -1;
+        nmax = max(nmax, c.nlim);
+    }
+    nmax = __reduce_max_sync(FULL, nmax);  // the band's longest ray
+    __syncwarp();
+    const unsigned short* Y = thresholds + (size_t)xl * S.n_pad;
+    int head = 0, tail = 0;  // queue positions (monotone; the slot is position & (CROSS_QUEUE - 1))
+
+    // the lanes take one queued pair each; pairs of one row run in queue order
+    auto run_batch = [&](int n) {
+        const bool have = lane < n;
+        const int ev = have ? queue[(head + lane) & (CROSS_QUEUE - 1)] : -1 - lane;
+        const int r = ev & (CROSS_BAND - 1), k = ev >> 6;
+        const unsigned same = __match_any_sync(FULL, have ? r : -1 - lane);
+        const int rank = __popc(same & ((1u << lane) - 1u));
+        const int rounds = __reduce_max_sync(FULL, have ? rank : 0);
+        for (int round = 0; round <= rounds; ++round) {
+            if (have && rank == round) {
+                CrossPixel& c = pix[r];
+                if (c.done_k < 0 && k < c.nlim) {
+                    const int y = b0 + r;
+                    PixelState st = c.st;
+                    if (process_step<OBJECTS, false>(S, B, O, xl, y, k, (size_t)y * wl + xl, st)) c.done_k = k;
+                    c.st = st;
+                }
+            }
+            __syncwarp();
+        }
+        head += n;
+    };
+
+    static_assert(CROSS_BAND == 64, "a queued pair is (step << 6) | row of the band");
+    unsigned prev = Y[0] & 0x7fffu;  // Y[kb - 1] of the window
+    for (int kb = 1; kb < nmax; kb += 32) {
+        const int k = kb + lane;
+        const unsigned v = k < nmax ? Y[k] : 0u;
+        unsigned before = __shfl_up_sync(FULL, v, 1);
+        if (lane == 0) before = prev;
+        prev = __shfl_sync(FULL, v, 31);
+        const int yk = (int)(v & 0x7fffu), yp = (int)(before & 0x7fffu);
+        int first = max(min(yk, yp), b0), last = min(max(yk, yp), b1);  // rows [first, last) changed sides
+        if (OBJECTS && (v & CROSS_CLOSE)) first = b0, last = b1;
+        if (k >= nmax) last = first;
+        unsigned any = __ballot_sync(FULL, last > first);
+        while (any) {
+            const int j = __ffs(any) - 1;
+            any &= any - 1;
+            const int f = __shfl_sync(FULL, first, j), n = __shfl_sync(FULL, last, j) - f, kk = kb + j;
+            for (int i = lane; i < n; i += 32) queue[(tail + i) & (CROSS_QUEUE - 1)] = (kk << 6) | (f + i - b0);
+            tail += n;
+            __syncwarp();
+            while (tail - head >= 32) run_batch(32);
+        }
+    }
+    if (tail > head) run_batch(tail - head);
+
+    for (int r = lane; r < CROSS_BAND; r += 32) {  // all lanes: write_pixel votes
+        const CrossPixel& c = pix[r];
+        const bool active = b0 + r < b1;
+        const int y = active ? b0 + r : b1 - 1;
+        const int consumed = c.done_k >= 0 ? c.done_k : (c.nlim > 0 ? c.nlim - 1 : 0);
+        write_pixel<false>(S, B, O, (size_t)y * wl + xl, active, c.st, consumed);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // The Rectilinear generator (generators/rectilinear.rs): a rectilinear projection, so every pixel has its
 // own elevation AND azimuth -- one ray integration and one azimuth walk per pixel, nothing to cache. One
 // thread per pixel runs the reference's PathIterator (rectilinear.rs:112-186) fused with get_single_pixel:
