@@ -90,7 +90,7 @@ struct atmrt_ctx {
     double atm_table_wavelength = 0.0;
     int path_mode = 0;  // 0: g(h) from the table, 1: every evaluation through libm (validation)
     DevBuf d_atm_cells;
-    DevBuf d_sweep_flags, d_sweep_col, d_sweep_hit, d_cross;
+    DevBuf d_sweep_flags, d_sweep_col, d_sweep_hit, d_cross, d_cross_trig;
     DevBuf d_anchor;  // walk anchors of stage A, [wl][n_anchor]
     bool walk_anchors = true;
     DevBuf d_list, d_count, d_normals;  // stage C: the distinct hit samples of every column and their normals
@@ -1067,13 +1067,25 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         k_march<false, true, false><<<fgrid, MARCH_THREADS, 0, main>>>(S, B, O, MARCH_FLAGGED_COLUMNS);
         ctx->launches += 2;
     } else if (cross) {
-        if ((rc = ensure(ctx, ctx->d_cross, sizeof(unsigned short) * (size_t)wl * S.n_pad))) return rc;
+        const size_t samples = (size_t)wl * S.n_pad;
+        if ((rc = ensure(ctx, ctx->d_cross, sizeof(unsigned short) * samples))) return rc;
         unsigned short* thresholds = (unsigned short*)ctx->d_cross.p;
+        unsigned short* trig_slot = nullptr;
+        double* trig = nullptr;
+        int* trig_count = nullptr;
+        if (objs) {  // per column: slot of every sample next to a close object | its four sines and cosines | the slot counter
+            const size_t off_trig = align_up(sizeof(unsigned short) * samples, 256), off_count = off_trig + sizeof(double) * 4 * CROSS_TRIG_CAP * (size_t)wl;
+            if ((rc = ensure(ctx, ctx->d_cross_trig, off_count + sizeof(int) * (size_t)wl))) return rc;
+            trig_slot = (unsigned short*)ctx->d_cross_trig.p;
+            trig = (double*)((char*)ctx->d_cross_trig.p + off_trig);
+            trig_count = (int*)((char*)ctx->d_cross_trig.p + off_count);
+            CUDA_TRY(ctx, cudaMemsetAsync(trig_count, 0, sizeof(int) * (size_t)wl, main));
+        }
         const int bands = (h + CROSS_BAND - 1) / CROSS_BAND;
         KT_BEGIN(ATMRT_KERNEL_MARCH, main)
-        k_thresholds<<<dim3((S.n_t + 127) / 128, wl), 128, 0, main>>>(S, B, thresholds, objs ? 1 : 0);
-        if (objs) k_cross_march<true><<<dim3((bands + CROSS_WARPS - 1) / CROSS_WARPS, wl), 32 * CROSS_WARPS, 0, main>>>(S, B, O, thresholds);
-        else k_cross_march<false><<<dim3((bands + CROSS_WARPS - 1) / CROSS_WARPS, wl), 32 * CROSS_WARPS, 0, main>>>(S, B, O, thresholds);
+        k_thresholds<<<dim3((S.n_t + 127) / 128, wl), 128, 0, main>>>(S, B, thresholds, objs ? 1 : 0, trig_slot, trig, trig_count);
+        if (objs) k_cross_march<true><<<dim3((bands + CROSS_WARPS - 1) / CROSS_WARPS, wl), 32 * CROSS_WARPS, 0, main>>>(S, B, O, thresholds, trig_slot, trig);
+        else k_cross_march<false><<<dim3((bands + CROSS_WARPS - 1) / CROSS_WARPS, wl), 32 * CROSS_WARPS, 0, main>>>(S, B, O, thresholds, nullptr, nullptr);
         // the fallback, a no-op unless the rays of this render cross
         terrain_pyramids(main, 1);
         path_pyramids(main, 1);
@@ -1232,7 +1244,7 @@ void atmrt_destroy(atmrt_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_objects_in, &ctx->d_objects, &ctx->d_dist, &ctx->d_colcalc, &ctx->d_tlat, &ctx->d_tlon, &ctx->d_telev,
                       &ctx->d_tclose, &ctx->d_pdist, &ctx->d_pelev, &ctx->d_plen, &ctx->d_pn,
                       &ctx->d_tmin1, &ctx->d_tmax1, &ctx->d_tmin2, &ctx->d_tmax2, &ctx->d_tmin3, &ctx->d_tmax3, &ctx->d_close1, &ctx->d_close2, &ctx->d_close3, &ctx->d_rmin1, &ctx->d_rmin3, &ctx->d_rmax3,
-                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_sweep_flags, &ctx->d_sweep_col, &ctx->d_sweep_hit, &ctx->d_cross, &ctx->d_list, &ctx->d_count, &ctx->d_normals, &ctx->d_anchor, &ctx->d_stage, &ctx->d_atm_aux, &ctx->d_rgb, &ctx->d_meta,
+                      &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_sweep_flags, &ctx->d_sweep_col, &ctx->d_sweep_hit, &ctx->d_cross, &ctx->d_cross_trig, &ctx->d_list, &ctx->d_count, &ctx->d_normals, &ctx->d_anchor, &ctx->d_stage, &ctx->d_atm_aux, &ctx->d_rgb, &ctx->d_meta,
                       &ctx->d_steps, &ctx->d_points, &ctx->d_counts, &ctx->d_probe_a, &ctx->d_probe_b, &ctx->d_probe_c, &ctx->d_probe_d};
     for (DevBuf* b : bufs) release(*b);
     for (DevBuf& b : ctx->textures) release(b);

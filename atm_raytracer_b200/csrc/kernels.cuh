@@ -973,6 +973,10 @@ struct PixelState {
     double m_lat, m_lon, m_elev, m_dist;
 };
 
+// Crossing march (below): per column, the samples next to a close object keep sin / cos of their latitude and longitude
+constexpr unsigned CROSS_NO_SLOT = 0xffffu;
+constexpr int CROSS_TRIG_CAP = 1024;  // cached samples per column; the rest evaluates sincos in place
+
 struct MarchOut {
     unsigned char* rgb;          // [h][wl][3]
     atmrt_meta* meta;            // [h][wl]
@@ -1014,6 +1018,8 @@ struct StepEnds {
     double lat0, lon0, elev0, ray0, dist0, len0;
     double lat1, lon1, elev1, ray1, dist1, len1;
     unsigned long long mask;  // objects_close of either end
+    const double* trig0 = nullptr;  // sin lat, cos lat, sin lon, cos lon of the end (k_thresholds), or null
+    const double* trig1 = nullptr;
 };
 
 // One step that holds an event (utils.rs:220-285). `normals(&n0, &n1)` yields TerrainData::normal of the two
@@ -1058,8 +1064,9 @@ __device__ __forceinline__ bool process_ends(const DevScene& S, const DevBuffers
     }
     unsigned long long mask = e.mask;
     if (mask) {
-        V3 pos1 = as_cartesian(S.earth, lat0, lon0, ray0);
-        V3 pos2 = as_cartesian(S.earth, lat1, lon1, ray1);
+        // (the sines and cosines are the sample's, the same for every row: the crossing march caches them)
+        V3 pos1 = e.trig0 ? as_cartesian_sc(S.earth, lat0, ray0, e.trig0[0], e.trig0[1], e.trig0[2], e.trig0[3]) : as_cartesian(S.earth, lat0, lon0, ray0);
+        V3 pos2 = e.trig1 ? as_cartesian_sc(S.earth, lat1, ray1, e.trig1[0], e.trig1[1], e.trig1[2], e.trig1[3]) : as_cartesian(S.earth, lat1, lon1, ray1);
         // The reference walks a HashSet (arbitrary order); index order here. Only exact `prop` ties
         // could tell the difference (stable sort below).
         while (mask) {
@@ -1112,7 +1119,8 @@ __device__ __forceinline__ bool process_ends(const DevScene& S, const DevBuffers
 // The Fast generator's step k of pixel (xl, y): the ends come from the two caches (fast.rs:56-64).
 template <bool OBJECTS, bool TRACE>
 __device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers& B, const MarchOut& O, int xl, int y, int k,
-                                             size_t pixel, PixelState& st, const V3* normals = nullptr) {
+                                             size_t pixel, PixelState& st, const V3* normals = nullptr, const unsigned short* trig_slot = nullptr,
+                                             const double* trig = nullptr) {
     const size_t ti = (size_t)xl * S.n_pad + k;
     const size_t p1 = path_index(S.n_t, k, y), p0 = p1 - PATH_ROWS;
     StepEnds e;
@@ -1122,6 +1130,11 @@ __device__ __forceinline__ bool process_step(const DevScene& S, const DevBuffers
     e.dist0 = B.path_x[k - 1], e.dist1 = B.path_x[k];  // path_x[0] = 0
     e.len0 = k - 1 == 0 ? 0.0 : B.p_len[p0], e.len1 = B.p_len[p1];
     e.mask = OBJECTS ? (B.t_close[ti - 1] | B.t_close[ti]) : 0ull;
+    if (OBJECTS && trig_slot && e.mask) {
+        const unsigned s0 = trig_slot[ti - 1], s1 = trig_slot[ti];
+        if (s0 != CROSS_NO_SLOT) e.trig0 = trig + ((size_t)xl * CROSS_TRIG_CAP + s0) * 4;
+        if (s1 != CROSS_NO_SLOT) e.trig1 = trig + ((size_t)xl * CROSS_TRIG_CAP + s1) * 4;
+    }
     return process_ends<OBJECTS, TRACE>(S, B, O, e, k, pixel, st, [&](V3* n0, V3* n1) {
         if (normals) {
             *n0 = normals[0], *n1 = normals[1];
@@ -1302,13 +1315,16 @@ __global__ void __launch_bounds__(MARCH_THREADS, 16) k_march(const __grid_consta
 //   k_thresholds    one thread per terrain sample: Y[x][k] by bisection over the rows that are still alive
 //                   at step k, and the flag "an object is close at step k - 1 or k".
 //   k_cross_march   one warp per (column, band of CROSS_BAND rows) walks the thresholds of its column in windows
-//                   of 32 steps and queues the (step, row) pairs of its band in step order; whenever 32 are
-//                   queued the lanes take one each and run the reference's step on it (process_step: the exact
-//                   product test, interpolation, normals, objects, stable sort, compositing) on the pixel's
-//                   state, which lives in shared memory. Pairs of the same row inside one batch run in queue
-//                   order. The candidates are a superset of the reference's events (an exact zero or a NaN on
-//                   one side changes the predicate without being an event; process_step tests the product), so
-//                   the result is the general march's, pixel for pixel.
+//                   of 32 steps and lists the (step, row) pairs of its band in step order. Thirty-two at a time
+//                   the pairs are filtered -- the ray is still live, and either its row changed sides or one of
+//                   the close objects is within reach of the ray's segment (object_out_of_reach: an exact
+//                   rejection, most rows of a step next to an object pass it by) -- and whenever 32 survivors
+//                   are queued the lanes take one each and run the reference's step on it (process_step: the
+//                   exact product test, interpolation, normals, objects, stable sort, compositing) on the
+//                   pixel's state, which lives in shared memory. Pairs of the same row inside one batch run in
+//                   queue order. The survivors are a superset of the reference's events (an exact zero or a
+//                   NaN on one side changes the predicate without being an event; process_step tests the
+//                   product), so the result is the general march's, pixel for pixel.
 //
 // Both return at once when k_path_check found crossing rays; the general march then runs behind them.
 // ---------------------------------------------------------------------------------------------
@@ -1318,7 +1334,8 @@ constexpr int CROSS_WARPS = 4;
 constexpr int CROSS_QUEUE = 128;           // >= 31 + CROSS_BAND, a power of two
 
 __global__ void __launch_bounds__(128) k_thresholds(const __grid_constant__ DevScene S, DevBuffers B, unsigned short* __restrict__ thresholds,
-                                                    int objects) {
+                                                    int objects, unsigned short* __restrict__ trig_slot, double* __restrict__ trig,
+                                                    int* __restrict__ trig_count) {
     if (B.sweep_flags[0] != 0) return;
     const int k = blockIdx.x * 128 + threadIdx.x, xl = blockIdx.y;
     if (k >= S.n_t) return;
@@ -1339,7 +1356,23 @@ __global__ void __launch_bounds__(128) k_thresholds(const __grid_constant__ DevS
         else hi = mid;
     }
     unsigned v = (unsigned)lo;
-    if (objects && k >= 1 && (B.t_close[ti - 1] | B.t_close[ti]) != 0) v |= CROSS_CLOSE;
+    if (objects) {
+        const unsigned long long here = B.t_close[ti], before = k >= 1 ? B.t_close[ti - 1] : 0ull, after = k + 1 < S.n_t ? B.t_close[ti + 1] : 0ull;
+        if (k >= 1 && (before | here) != 0) v |= CROSS_CLOSE;
+        unsigned slot = CROSS_NO_SLOT;
+        if ((before | here | after) != 0) {  // an end of a step with a close object: as_cartesian's sines and cosines (mod.rs:59-93)
+            const int got = atomicAdd(trig_count + xl, 1);
+            if (got < CROSS_TRIG_CAP) {
+                double* t4 = trig + ((size_t)xl * CROSS_TRIG_CAP + got) * 4;
+                double sinlat = 0.0, coslat = 1.0, sinlon, coslon;
+                sincos(to_radians(B.t_lon[ti]), &sinlon, &coslon);
+                if (!S.earth.flat_dirs) sincos(to_radians(B.t_lat[ti]), &sinlat, &coslat);
+                t4[0] = sinlat, t4[1] = coslat, t4[2] = sinlon, t4[3] = coslon;
+                slot = (unsigned)got;
+            }
+        }
+        trig_slot[ti] = (unsigned short)slot;
+    }
     thresholds[ti] = (unsigned short)v;
 }
 
@@ -1349,19 +1382,38 @@ struct CrossPixel {
     int done_k;  // the step the pixel finished at, -1 while it is live
 };
 
+// Can the segment pos1 -> pos2 touch object o at all? Every point Frustum / Billboard::check_collision returns lies
+// between the planes h = 0 and h = height along the object's axis and within max(r1, r2) (half the width) of it. The
+// height is linear along the segment and the distance to the axis cannot drop below the nearer end's by more than
+// the segment's length, so a segment with both ends beyond one plane, or with both ends farther from the axis than
+// that, yields no collision. The 1 mm margins are a million times the rounding of these dot products (coordinates
+// of 6.4e6 m, 1e-16 relative). NaN compares false: never rejected.
+__device__ __forceinline__ bool object_out_of_reach(const DevObject& o, V3 pos1, V3 pos2, double seg_len) {
+    const double margin = 1.0e-3;
+    const V3 p1 = pos1 - o.pos, p2 = pos2 - o.pos;
+    const double h1 = dot(p1, o.up), h2 = dot(p2, o.up);
+    if (fmax(h1, h2) < -margin || fmin(h1, h2) > o.height + margin) return true;
+    const double reach = (o.kind == ATMRT_OBJECT_FRUSTUM ? fmax(o.r1, o.r2) : 0.5 * o.width) + seg_len + margin;
+    const double q1 = dot(p1, p1) - h1 * h1, q2 = dot(p2, p2) - h2 * h2;  // squared distances to the axis
+    return fmin(q1, q2) > reach * reach;
+}
+
 template <bool OBJECTS>
-__global__ void __launch_bounds__(32 * CROSS_WARPS) k_cross_march(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O,
-                                                                  const unsigned short* __restrict__ thresholds) {
+__global__ void __launch_bounds__(32 * CROSS_WARPS, 6) k_cross_march(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O,
+                                                                     const unsigned short* __restrict__ thresholds,
+                                                                     const unsigned short* __restrict__ trig_slot, const double* __restrict__ trig) {
     if (B.sweep_flags[0] != 0) return;
     __shared__ CrossPixel pix_smem[CROSS_WARPS][CROSS_BAND];
-    __shared__ int queue_smem[CROSS_WARPS][CROSS_QUEUE];
+    __shared__ int queue_smem[CROSS_WARPS][2][CROSS_QUEUE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int xl = blockIdx.y, wl = S.x1 - S.x0;
     const int b0 = (blockIdx.x * CROSS_WARPS + warp) * CROSS_BAND;
     if (b0 >= S.height) return;
     const int b1 = min(b0 + CROSS_BAND, S.height);
     CrossPixel* pix = pix_smem[warp];
-    int* queue = queue_smem[warp];
+    // candidates: every (step, row) the thresholds name; survivors: those that can have an effect, in the same order
+    int* cand = queue_smem[warp][0];
+    int* queue = queue_smem[warp][1];
     int nmax = 0;
     for (int r = lane; r < CROSS_BAND; r += 32) {
         CrossPixel& c = pix[r];
@@ -1373,55 +1425,115 @@ __global__ void __launch_bounds__(32 * CROSS_WARPS) k_cross_march(const __grid_c
     nmax = __reduce_max_sync(FULL, nmax);  // the band's longest ray
     __syncwarp();
     const unsigned short* Y = thresholds + (size_t)xl * S.n_pad;
-    int head = 0, tail = 0;  // queue positions (monotone; the slot is position & (CROSS_QUEUE - 1))
-
-    // the lanes take one queued pair each; pairs of one row run in queue order
-    auto run_batch = [&](int n) {
-        const bool have = lane < n;
-        const int ev = have ? queue[(head + lane) & (CROSS_QUEUE - 1)] : -1 - lane;
-        const int r = ev & (CROSS_BAND - 1), k = ev >> 6;
-        const unsigned same = __match_any_sync(FULL, have ? r : -1 - lane);
-        const int rank = __popc(same & ((1u << lane) - 1u));
-        const int rounds = __reduce_max_sync(FULL, have ? rank : 0);
-        for (int round = 0; round <= rounds; ++round) {
-            if (have && rank == round) {
-                CrossPixel& c = pix[r];
-                if (c.done_k < 0 && k < c.nlim) {
-                    const int y = b0 + r;
-                    PixelState st = c.st;
-                    if (process_step<OBJECTS, false>(S, B, O, xl, y, k, (size_t)y * wl + xl, st)) c.done_k = k;
-                    c.st = st;
-                }
-            }
-            __syncwarp();
-        }
-        head += n;
-    };
-
-    static_assert(CROSS_BAND == 64, "a queued pair is (step << 6) | row of the band");
+    const size_t tbase = (size_t)xl * S.n_pad;
+    int head = 0, tail = 0, chead = 0, ctail = 0;  // queue positions (monotone; the slot is position & (CROSS_QUEUE - 1))
+    static_assert(CROSS_BAND == 64, "a queued pair is (step << 7) | (sign change possible << 6) | row of the band");
     unsigned prev = Y[0] & 0x7fffu;  // Y[kb - 1] of the window
-    for (int kb = 1; kb < nmax; kb += 32) {
-        const int k = kb + lane;
-        const unsigned v = k < nmax ? Y[k] : 0u;
-        unsigned before = __shfl_up_sync(FULL, v, 1);
-        if (lane == 0) before = prev;
-        prev = __shfl_sync(FULL, v, 31);
-        const int yk = (int)(v & 0x7fffu), yp = (int)(before & 0x7fffu);
-        int first = max(min(yk, yp), b0), last = min(max(yk, yp), b1);  // rows [first, last) changed sides
-        if (OBJECTS && (v & CROSS_CLOSE)) first = b0, last = b1;
-        if (k >= nmax) last = first;
-        unsigned any = __ballot_sync(FULL, last > first);
-        while (any) {
+    int kb = 1 - 32, first = 0, last = 0, t_first = 0, t_last = 0;
+    unsigned any = 0;  // steps of the window that still have rows to queue
+    bool windows_left = true;
+
+    for (;;) {
+        if (tail - head >= 32 || (tail > head && !windows_left && ctail == chead)) {
+            // ---- the lanes take one surviving pair each and run the reference's step; pairs of one row run in queue order ----
+            const int n = min(32, tail - head);
+            const bool have = lane < n;
+            const int ev = have ? queue[(head + lane) & (CROSS_QUEUE - 1)] : -1 - lane;
+            const int r = ev & (CROSS_BAND - 1), k = ev >> 7;
+            const unsigned same = __match_any_sync(FULL, have ? r : -1 - lane);
+            const int rank = __popc(same & ((1u << lane) - 1u));
+            const int rounds = __reduce_max_sync(FULL, have ? rank : 0);
+            for (int round = 0; round <= rounds; ++round) {
+                if (have && rank == round) {
+                    CrossPixel& c = pix[r];
+                    if (c.done_k < 0 && k < c.nlim) {
+                        const int y = b0 + r;
+                        PixelState st = c.st;
+                        if (process_step<OBJECTS, false>(S, B, O, xl, y, k, (size_t)y * wl + xl, st, nullptr, trig_slot, trig)) c.done_k = k;
+                        c.st = st;
+                    }
+                }
+                __syncwarp();
+            }
+            head += n;
+            continue;
+        }
+        // ---- more candidates: the next steps of the window, the next window ----
+        while (ctail - chead < 32 && windows_left) {
+            if (!any) {  // next window: lane j looks at step kb + j
+                kb += 32;
+                if (kb >= nmax) {
+                    windows_left = false;
+                    break;
+                }
+                const int k = kb + lane;
+                const unsigned v = k < nmax ? Y[k] : 0u;
+                unsigned before = __shfl_up_sync(FULL, v, 1);
+                if (lane == 0) before = prev;
+                prev = __shfl_sync(FULL, v, 31);
+                const int yk = (int)(v & 0x7fffu), yp = (int)(before & 0x7fffu);
+                t_first = max(min(yk, yp), b0), t_last = min(max(yk, yp), b1);  // rows [t_first, t_last) changed sides
+                first = t_first, last = t_last;
+                if (OBJECTS && (v & CROSS_CLOSE)) first = b0, last = b1;
+                if (k >= nmax) last = first;
+                any = __ballot_sync(FULL, last > first);
+                continue;
+            }
             const int j = __ffs(any) - 1;
             any &= any - 1;
             const int f = __shfl_sync(FULL, first, j), n = __shfl_sync(FULL, last, j) - f, kk = kb + j;
-            for (int i = lane; i < n; i += 32) queue[(tail + i) & (CROSS_QUEUE - 1)] = (kk << 6) | (f + i - b0);
-            tail += n;
+            const int tf = __shfl_sync(FULL, t_first, j), tl = __shfl_sync(FULL, t_last, j);
+            for (int i = lane; i < n; i += 32) {
+                const int row = f + i;
+                cand[(ctail + i) & (CROSS_QUEUE - 1)] = (kk << 7) | (row >= tf && row < tl ? 64 : 0) | (row - b0);
+            }
+            ctail += n;
             __syncwarp();
-            while (tail - head >= 32) run_batch(32);
+        }
+        if (ctail == chead) {
+            if (tail == head) break;
+            continue;  // flush the survivors
+        }
+        // ---- which candidates can have an effect? a live ray, and a possible sign change or an object within reach ----
+        {
+            const int n = min(32, ctail - chead);
+            bool keep = false;
+            int ev = 0;
+            if (lane < n) {
+                ev = cand[(chead + lane) & (CROSS_QUEUE - 1)];
+                const int r = ev & (CROSS_BAND - 1), k = ev >> 7;
+                const CrossPixel& c = pix[r];
+                if (c.done_k < 0 && k < c.nlim) {
+                    keep = true;
+                    if (OBJECTS && !(ev & 64)) {
+                        const size_t ti = tbase + k;
+                        const unsigned s0 = trig_slot[ti - 1], s1 = trig_slot[ti];
+                        if (s0 != CROSS_NO_SLOT && s1 != CROSS_NO_SLOT) {
+                            const double* q0 = trig + ((size_t)xl * CROSS_TRIG_CAP + s0) * 4;
+                            const double* q1 = trig + ((size_t)xl * CROSS_TRIG_CAP + s1) * 4;
+                            const size_t p1 = path_index(S.n_t, k, b0 + r);
+                            const V3 pos1 = as_cartesian_sc(S.earth, B.t_lat[ti - 1], B.p_elev[p1 - PATH_ROWS], q0[0], q0[1], q0[2], q0[3]);
+                            const V3 pos2 = as_cartesian_sc(S.earth, B.t_lat[ti], B.p_elev[p1], q1[0], q1[1], q1[2], q1[3]);
+                            const V3 w = pos2 - pos1;
+                            const double seg_len = sqrt(dot(w, w));
+                            unsigned long long mask = B.t_close[ti - 1] | B.t_close[ti];
+                            keep = false;
+                            while (mask && !keep) {
+                                const int oi = __ffsll((long long)mask) - 1;
+                                mask &= mask - 1;
+                                keep = !object_out_of_reach(B.objects[oi], pos1, pos2, seg_len);
+                            }
+                        }
+                    }
+                }
+            }
+            const unsigned kept = __ballot_sync(FULL, keep);
+            if (keep) queue[(tail + __popc(kept & ((1u << lane) - 1u))) & (CROSS_QUEUE - 1)] = ev;
+            tail += __popc(kept);
+            chead += n;
+            __syncwarp();
         }
     }
-    if (tail > head) run_batch(tail - head);
 
     for (int r = lane; r < CROSS_BAND; r += 32) {  // all lanes: write_pixel votes
         const CrossPixel& c = pix[r];

@@ -1,5 +1,6 @@
 # Where k_march's time goes on c4: variants of the scene, timed with the library's own per-kernel events.
-import sys, numpy as np
+import os, sys, numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from atm_raytracer_b200 import runtime, config, scenes
 
 def run(label, alpha=None, with_objects=True, march_mode=0, reps=4):
@@ -15,8 +16,9 @@ def run(label, alpha=None, with_objects=True, march_mode=0, reps=4):
     print(label, {k: round(v, 3) for k, v in kt.items()}, "trace_points", st["trace_points"], "ray_steps", st["ray_steps"], flush=True)
     c.close()
 
-run("c4 as is            ")
-run("c4 no objects a=.5  ", with_objects=False, march_mode=2)
-run("c4 objects a=1      ", alpha=1.0, march_mode=2)
-run("c4 no objects a=1 m2", alpha=1.0, with_objects=False, march_mode=2)
+for mode in (0, 2):
+    print("march mode", mode, "(0: crossing march, 2: hierarchical march)")
+    run("c4 as is            ", march_mode=mode)
+    run("c4 no objects a=.5  ", with_objects=False, march_mode=mode)
+    run("c4 objects a=1      ", alpha=1.0, march_mode=mode)
 run("c4 brute            ", march_mode=1)

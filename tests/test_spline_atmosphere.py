@@ -250,11 +250,11 @@ def test_ray_paths_through_a_spline_inversion(ctx, oracle_lib, flat):
 
 @pytest.mark.gpu
 def test_gen_executable_accepts_the_readme_atmosphere(tmp_path):
-    """`atm-raytracer output-atm -c <README atmosphere>` through the C++ host's own YAML reader."""
+    """`atm-raytracer output-atm <README atmosphere>` through the C++ host's own YAML reader (`-c` is --celsius there)."""
     cfg = tmp_path / "atm.yaml"
     cfg.write_text(README_YAML)
     exe = ROOT / "atm_raytracer_b200" / "atm-raytracer"
-    out = subprocess.run([str(exe), "output-atm", "-c", str(cfg), "--min-alt", "100", "--max-alt", "120", "--step", "10"],
+    out = subprocess.run([str(exe), "output-atm", str(cfg), "--min-alt", "100", "--max-alt", "120", "--step", "10"],
                          capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     rows = [line.split() for line in out.stdout.strip().splitlines() if line and line[0].isdigit()]
