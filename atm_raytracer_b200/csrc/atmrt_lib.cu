@@ -1068,8 +1068,12 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         ctx->launches += 2;
     } else if (cross) {
         const size_t samples = (size_t)wl * S.n_pad;
-        if ((rc = ensure(ctx, ctx->d_cross, sizeof(unsigned short) * samples))) return rc;
+        // thresholds [column][n_pad] | per window of 32 steps: min, max of the thresholds [column][n1_pad] each
+        const size_t off_win = align_up(sizeof(unsigned short) * samples, 256), win_bytes = align_up(sizeof(unsigned short) * (size_t)wl * S.n1_pad, 256);
+        if ((rc = ensure(ctx, ctx->d_cross, off_win + 2 * win_bytes))) return rc;
         unsigned short* thresholds = (unsigned short*)ctx->d_cross.p;
+        unsigned short* window_min = (unsigned short*)((char*)ctx->d_cross.p + off_win);
+        unsigned short* window_max = (unsigned short*)((char*)ctx->d_cross.p + off_win + win_bytes);
         unsigned short* trig_slot = nullptr;
         double* trig = nullptr;
         int* trig_count = nullptr;
@@ -1083,9 +1087,9 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         }
         const int bands = (h + CROSS_BAND - 1) / CROSS_BAND;
         KT_BEGIN(ATMRT_KERNEL_MARCH, main)
-        k_thresholds<<<dim3((S.n_t + 127) / 128, wl), 128, 0, main>>>(S, B, thresholds, objs ? 1 : 0, trig_slot, trig, trig_count);
-        if (objs) k_cross_march<true><<<dim3((bands + CROSS_WARPS - 1) / CROSS_WARPS, wl), 32 * CROSS_WARPS, 0, main>>>(S, B, O, thresholds, trig_slot, trig);
-        else k_cross_march<false><<<dim3((bands + CROSS_WARPS - 1) / CROSS_WARPS, wl), 32 * CROSS_WARPS, 0, main>>>(S, B, O, thresholds, nullptr, nullptr);
+        k_thresholds<<<dim3((S.n_t + 127) / 128, wl), 128, 0, main>>>(S, B, thresholds, window_min, window_max, objs ? 1 : 0, trig_slot, trig, trig_count);
+        if (objs) k_cross_march<true><<<dim3((wl + CROSS_WARPS - 1) / CROSS_WARPS, bands), 32 * CROSS_WARPS, 0, main>>>(S, B, O, thresholds, window_min, window_max, trig_slot, trig);
+        else k_cross_march<false><<<dim3((wl + CROSS_WARPS - 1) / CROSS_WARPS, bands), 32 * CROSS_WARPS, 0, main>>>(S, B, O, thresholds, window_min, window_max, nullptr, nullptr);
         // the fallback, a no-op unless the rays of this render cross
         terrain_pyramids(main, 1);
         path_pyramids(main, 1);

@@ -1313,9 +1313,10 @@ __global__ void __launch_bounds__(MARCH_THREADS, 16) k_march(const __grid_consta
 // and Y[x][k]; the steps with a close object concern every row.
 //
 //   k_thresholds    one thread per terrain sample: Y[x][k] by bisection over the rows that are still alive
-//                   at step k, and the flag "an object is close at step k - 1 or k".
-//   k_cross_march   one warp per (column, band of CROSS_BAND rows) walks the thresholds of its column in windows
-//                   of 32 steps and lists the (step, row) pairs of its band in step order. Thirty-two at a time
+//                   at step k, and the flag "an object is close at step k - 1 or k"; per window of 32 steps the
+//                   range of the thresholds (a band skips the windows that cannot concern it).
+//   k_cross_march   one warp per (column, band of CROSS_BAND rows) walks the windows of its column that concern it
+//                   and lists the (step, row) pairs of its band in step order. Thirty-two at a time
 //                   the pairs are filtered -- the ray is still live, and either its row changed sides or one of
 //                   the close objects is within reach of the ray's segment (object_out_of_reach: an exact
 //                   rejection, most rows of a step next to an object pass it by) -- and whenever 32 survivors
@@ -1331,49 +1332,61 @@ __global__ void __launch_bounds__(MARCH_THREADS, 16) k_march(const __grid_consta
 constexpr unsigned CROSS_CLOSE = 0x8000u;  // Y holds a row count <= 32767 (atmrt_set_params limits the height)
 constexpr int CROSS_BAND = 64;             // rows per warp
 constexpr int CROSS_WARPS = 4;
-constexpr int CROSS_QUEUE = 128;           // >= 31 + CROSS_BAND, a power of two
+constexpr int CROSS_QUEUE = 64;            // >= 31 + 32, a power of two
 
 __global__ void __launch_bounds__(128) k_thresholds(const __grid_constant__ DevScene S, DevBuffers B, unsigned short* __restrict__ thresholds,
-                                                    int objects, unsigned short* __restrict__ trig_slot, double* __restrict__ trig,
-                                                    int* __restrict__ trig_count) {
+                                                    unsigned short* __restrict__ window_min, unsigned short* __restrict__ window_max, int objects,
+                                                    unsigned short* __restrict__ trig_slot, double* __restrict__ trig, int* __restrict__ trig_count) {
     if (B.sweep_flags[0] != 0) return;
     const int k = blockIdx.x * 128 + threadIdx.x, xl = blockIdx.y;
-    if (k >= S.n_t) return;
-    // rows alive at step k: p_n[y] > k, and p_n does not increase with y
-    int lo = 0, hi = S.height;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (B.p_n[mid] > k) lo = mid + 1;
-        else hi = mid;
-    }
-    const size_t ti = (size_t)xl * S.n_pad + k;
-    const double t = B.t_elev[ti];
-    hi = lo, lo = 0;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        const double d = B.p_elev[path_index(S.n_t, k, mid)] - t;
-        if (!(d <= 0.0)) lo = mid + 1;
-        else hi = mid;
-    }
-    unsigned v = (unsigned)lo;
-    if (objects) {
-        const unsigned long long here = B.t_close[ti], before = k >= 1 ? B.t_close[ti - 1] : 0ull, after = k + 1 < S.n_t ? B.t_close[ti + 1] : 0ull;
-        if (k >= 1 && (before | here) != 0) v |= CROSS_CLOSE;
-        unsigned slot = CROSS_NO_SLOT;
-        if ((before | here | after) != 0) {  // an end of a step with a close object: as_cartesian's sines and cosines (mod.rs:59-93)
-            const int got = atomicAdd(trig_count + xl, 1);
-            if (got < CROSS_TRIG_CAP) {
-                double* t4 = trig + ((size_t)xl * CROSS_TRIG_CAP + got) * 4;
-                double sinlat = 0.0, coslat = 1.0, sinlon, coslon;
-                sincos(to_radians(B.t_lon[ti]), &sinlon, &coslon);
-                if (!S.earth.flat_dirs) sincos(to_radians(B.t_lat[ti]), &sinlat, &coslat);
-                t4[0] = sinlat, t4[1] = coslat, t4[2] = sinlon, t4[3] = coslon;
-                slot = (unsigned)got;
-            }
+    const bool valid = k < S.n_t;
+    unsigned v = 0;
+    if (valid) {
+        // rows alive at step k: p_n[y] > k, and p_n does not increase with y
+        int lo = 0, hi = S.height;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (B.p_n[mid] > k) lo = mid + 1;
+            else hi = mid;
         }
-        trig_slot[ti] = (unsigned short)slot;
+        const size_t ti = (size_t)xl * S.n_pad + k;
+        const double t = B.t_elev[ti];
+        hi = lo, lo = 0;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const double d = B.p_elev[path_index(S.n_t, k, mid)] - t;
+            if (!(d <= 0.0)) lo = mid + 1;
+            else hi = mid;
+        }
+        v = (unsigned)lo;
+        if (objects) {
+            const unsigned long long here = B.t_close[ti], before = k >= 1 ? B.t_close[ti - 1] : 0ull, after = k + 1 < S.n_t ? B.t_close[ti + 1] : 0ull;
+            if (k >= 1 && (before | here) != 0) v |= CROSS_CLOSE;
+            unsigned slot = CROSS_NO_SLOT;
+            if ((before | here | after) != 0) {  // an end of a step with a close object: as_cartesian's sines and cosines (mod.rs:59-93)
+                const int got = atomicAdd(trig_count + xl, 1);
+                if (got < CROSS_TRIG_CAP) {
+                    double* t4 = trig + ((size_t)xl * CROSS_TRIG_CAP + got) * 4;
+                    double sinlat = 0.0, coslat = 1.0, sinlon, coslon;
+                    sincos(to_radians(B.t_lon[ti]), &sinlon, &coslon);
+                    if (!S.earth.flat_dirs) sincos(to_radians(B.t_lat[ti]), &sinlat, &coslat);
+                    t4[0] = sinlat, t4[1] = coslat, t4[2] = sinlon, t4[3] = coslon;
+                    slot = (unsigned)got;
+                }
+            }
+            trig_slot[ti] = (unsigned short)slot;
+        }
+        thresholds[ti] = (unsigned short)v;
     }
-    thresholds[ti] = (unsigned short)v;
+    // the window of 32 steps this warp covers: the range of its thresholds, and whether an object is close in it
+    const unsigned y = v & 0x7fffu;
+    const unsigned lo_y = __reduce_min_sync(FULL, valid ? y : 0x7fffu), hi_y = __reduce_max_sync(FULL, valid ? y : 0u);
+    const bool close = __any_sync(FULL, (v & CROSS_CLOSE) != 0);
+    if ((threadIdx.x & 31) == 0 && valid) {
+        const size_t wi = (size_t)xl * S.n1_pad + (k >> 5);
+        window_min[wi] = (unsigned short)lo_y;
+        window_max[wi] = (unsigned short)(hi_y | (close ? CROSS_CLOSE : 0u));
+    }
 }
 
 struct CrossPixel {
@@ -1401,19 +1414,20 @@ __device__ __forceinline__ bool object_out_of_reach(const DevObject& o, V3 pos1,
 template <bool OBJECTS>
 __global__ void __launch_bounds__(32 * CROSS_WARPS, 6) k_cross_march(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O,
                                                                      const unsigned short* __restrict__ thresholds,
+                                                                     const unsigned short* __restrict__ window_min,
+                                                                     const unsigned short* __restrict__ window_max,
                                                                      const unsigned short* __restrict__ trig_slot, const double* __restrict__ trig) {
     if (B.sweep_flags[0] != 0) return;
     __shared__ CrossPixel pix_smem[CROSS_WARPS][CROSS_BAND];
-    __shared__ int queue_smem[CROSS_WARPS][2][CROSS_QUEUE];
+    __shared__ int queue_smem[CROSS_WARPS][CROSS_QUEUE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int xl = blockIdx.y, wl = S.x1 - S.x0;
-    const int b0 = (blockIdx.x * CROSS_WARPS + warp) * CROSS_BAND;
-    if (b0 >= S.height) return;
+    // the warps of a block: the same band of adjacent columns (alike in work, and they read the same rows of the path cache)
+    const int wl = S.x1 - S.x0, xl = blockIdx.x * CROSS_WARPS + warp;
+    const int b0 = blockIdx.y * CROSS_BAND;
+    if (xl >= wl) return;
     const int b1 = min(b0 + CROSS_BAND, S.height);
     CrossPixel* pix = pix_smem[warp];
-    // candidates: every (step, row) the thresholds name; survivors: those that can have an effect, in the same order
-    int* cand = queue_smem[warp][0];
-    int* queue = queue_smem[warp][1];
+    int* queue = queue_smem[warp];  // the (step, row) pairs that can have an effect, in step order
     int nmax = 0;
     for (int r = lane; r < CROSS_BAND; r += 32) {
         CrossPixel& c = pix[r];
@@ -1424,22 +1438,26 @@ __global__ void __launch_bounds__(32 * CROSS_WARPS, 6) k_cross_march(const __gri
     }
     nmax = __reduce_max_sync(FULL, nmax);  // the band's longest ray
     __syncwarp();
-    const unsigned short* Y = thresholds + (size_t)xl * S.n_pad;
-    const size_t tbase = (size_t)xl * S.n_pad;
-    int head = 0, tail = 0, chead = 0, ctail = 0;  // queue positions (monotone; the slot is position & (CROSS_QUEUE - 1))
-    static_assert(CROSS_BAND == 64, "a queued pair is (step << 7) | (sign change possible << 6) | row of the band");
-    unsigned prev = Y[0] & 0x7fffu;  // Y[kb - 1] of the window
-    int kb = 1 - 32, first = 0, last = 0, t_first = 0, t_last = 0;
-    unsigned any = 0;  // steps of the window that still have rows to queue
-    bool windows_left = true;
+    const size_t tbase = (size_t)xl * S.n_pad, wbase = (size_t)xl * S.n1_pad;
+    const unsigned short* Y = thresholds + tbase;
+    const int nwin = (nmax + 31) >> 5;
+    int head = 0, tail = 0;  // queue positions (monotone; the slot is position & (CROSS_QUEUE - 1))
+    static_assert(CROSS_BAND == 64, "a queued pair is (step << 6) | row of the band");
+    // the enumeration, outermost first: 32 windows at a time (w0, wmask) -> one window (kb; per lane the rows
+    // [first, last) of step kb + lane, [t_first, t_last) of them because the row changed sides; `any`: the steps that
+    // have rows) -> one step (cur_k and its rows cur_f + [cur_i, cur_n))
+    int w0 = -32, kb = 0, first = 0, last = 0, t_first = 0, t_last = 0;
+    unsigned wmask = 0, any = 0;
+    int cur_k = 0, cur_f = 0, cur_n = 0, cur_i = 0, cur_tf = 0, cur_tl = 0;
+    bool enumerated = false;
 
     for (;;) {
-        if (tail - head >= 32 || (tail > head && !windows_left && ctail == chead)) {
-            // ---- the lanes take one surviving pair each and run the reference's step; pairs of one row run in queue order ----
+        if (tail - head >= 32 || (tail > head && enumerated)) {
+            // ---- the lanes take one queued pair each and run the reference's step; pairs of one row run in queue order ----
             const int n = min(32, tail - head);
             const bool have = lane < n;
             const int ev = have ? queue[(head + lane) & (CROSS_QUEUE - 1)] : -1 - lane;
-            const int r = ev & (CROSS_BAND - 1), k = ev >> 7;
+            const int r = ev & (CROSS_BAND - 1), k = ev >> 6;
             const unsigned same = __match_any_sync(FULL, have ? r : -1 - lane);
             const int rank = __popc(same & ((1u << lane) - 1u));
             const int rounds = __reduce_max_sync(FULL, have ? rank : 0);
@@ -1458,60 +1476,65 @@ __global__ void __launch_bounds__(32 * CROSS_WARPS, 6) k_cross_march(const __gri
             head += n;
             continue;
         }
-        // ---- more candidates: the next steps of the window, the next window ----
-        while (ctail - chead < 32 && windows_left) {
-            if (!any) {  // next window: lane j looks at step kb + j
-                kb += 32;
-                if (kb >= nmax) {
-                    windows_left = false;
-                    break;
+        if (enumerated) break;
+        if (cur_i >= cur_n) {  // the next step that has rows
+            if (!any) {        // ... in the next window that can have any
+                if (!wmask) {
+                    w0 += 32;
+                    if (w0 >= nwin) {
+                        enumerated = true;
+                        continue;
+                    }
+                    // a window matters to the band if its thresholds (and the one before its first step: the window before
+                    // it is included) reach into the band, or an object is close somewhere in it
+                    const int w = w0 + lane;
+                    bool matters = false;
+                    if (w < nwin) {
+                        const unsigned hi_w = window_max[wbase + w], lo_w = window_min[wbase + w];
+                        const unsigned hi_p = w > 0 ? window_max[wbase + w - 1] : hi_w, lo_p = w > 0 ? window_min[wbase + w - 1] : lo_w;
+                        matters = (OBJECTS && (hi_w & CROSS_CLOSE)) ||
+                                  ((int)min(lo_w, lo_p) < b1 && (int)(max(hi_w, hi_p) & 0x7fffu) > b0);
+                    }
+                    wmask = __ballot_sync(FULL, matters);
+                    continue;
                 }
+                kb = (w0 + __ffs(wmask) - 1) << 5;
+                wmask &= wmask - 1;
                 const int k = kb + lane;
-                const unsigned v = k < nmax ? Y[k] : 0u;
+                const bool in = k >= 1 && k < nmax;
+                const unsigned v = in ? Y[k] : 0u;
                 unsigned before = __shfl_up_sync(FULL, v, 1);
-                if (lane == 0) before = prev;
-                prev = __shfl_sync(FULL, v, 31);
+                if (lane == 0 && in) before = Y[k - 1];
                 const int yk = (int)(v & 0x7fffu), yp = (int)(before & 0x7fffu);
                 t_first = max(min(yk, yp), b0), t_last = min(max(yk, yp), b1);  // rows [t_first, t_last) changed sides
                 first = t_first, last = t_last;
                 if (OBJECTS && (v & CROSS_CLOSE)) first = b0, last = b1;
-                if (k >= nmax) last = first;
+                if (!in) last = first;
                 any = __ballot_sync(FULL, last > first);
                 continue;
             }
             const int j = __ffs(any) - 1;
             any &= any - 1;
-            const int f = __shfl_sync(FULL, first, j), n = __shfl_sync(FULL, last, j) - f, kk = kb + j;
-            const int tf = __shfl_sync(FULL, t_first, j), tl = __shfl_sync(FULL, t_last, j);
-            for (int i = lane; i < n; i += 32) {
-                const int row = f + i;
-                cand[(ctail + i) & (CROSS_QUEUE - 1)] = (kk << 7) | (row >= tf && row < tl ? 64 : 0) | (row - b0);
-            }
-            ctail += n;
-            __syncwarp();
+            cur_k = kb + j, cur_i = 0;
+            cur_f = __shfl_sync(FULL, first, j), cur_n = __shfl_sync(FULL, last, j) - cur_f;
+            cur_tf = __shfl_sync(FULL, t_first, j), cur_tl = __shfl_sync(FULL, t_last, j);
+            continue;
         }
-        if (ctail == chead) {
-            if (tail == head) break;
-            continue;  // flush the survivors
-        }
-        // ---- which candidates can have an effect? a live ray, and a possible sign change or an object within reach ----
+        // ---- the next 32 rows of the step: which can have an effect? a live ray, and a possible sign change or an object within reach ----
         {
-            const int n = min(32, ctail - chead);
+            const int row = cur_f + cur_i + lane, k = cur_k;
             bool keep = false;
-            int ev = 0;
-            if (lane < n) {
-                ev = cand[(chead + lane) & (CROSS_QUEUE - 1)];
-                const int r = ev & (CROSS_BAND - 1), k = ev >> 7;
-                const CrossPixel& c = pix[r];
+            if (cur_i + lane < cur_n) {
+                const CrossPixel& c = pix[row - b0];
                 if (c.done_k < 0 && k < c.nlim) {
                     keep = true;
-                    if (OBJECTS && !(ev & 64)) {
+                    if (OBJECTS && !(row >= cur_tf && row < cur_tl)) {
                         const size_t ti = tbase + k;
                         const unsigned s0 = trig_slot[ti - 1], s1 = trig_slot[ti];
                         if (s0 != CROSS_NO_SLOT && s1 != CROSS_NO_SLOT) {
                             const double* q0 = trig + ((size_t)xl * CROSS_TRIG_CAP + s0) * 4;
                             const double* q1 = trig + ((size_t)xl * CROSS_TRIG_CAP + s1) * 4;
-                            const size_t p1 = path_index(S.n_t, k, b0 + r);
+                            const size_t p1 = path_index(S.n_t, k, row);
                             const V3 pos1 = as_cartesian_sc(S.earth, B.t_lat[ti - 1], B.p_elev[p1 - PATH_ROWS], q0[0], q0[1], q0[2], q0[3]);
                             const V3 pos2 = as_cartesian_sc(S.earth, B.t_lat[ti], B.p_elev[p1], q1[0], q1[1], q1[2], q1[3]);
                             const V3 w = pos2 - pos1;
@@ -1528,9 +1551,9 @@ __global__ void __launch_bounds__(32 * CROSS_WARPS, 6) k_cross_march(const __gri
                 }
             }
             const unsigned kept = __ballot_sync(FULL, keep);
-            if (keep) queue[(tail + __popc(kept & ((1u << lane) - 1u))) & (CROSS_QUEUE - 1)] = ev;
+            if (keep) queue[(tail + __popc(kept & ((1u << lane) - 1u))) & (CROSS_QUEUE - 1)] = (k << 6) | (row - b0);
             tail += __popc(kept);
-            chead += n;
+            cur_i += 32;
             __syncwarp();
         }
     }
