@@ -15,7 +15,7 @@ MAX_STEP_POINTS = 16
 EARTH_SPHERICAL, EARTH_FLAT_DISTORTED, EARTH_ELLIPSOID, EARTH_AZIMUTHAL_EQUIDISTANT, EARTH_OBSERVER_AE = 0, 1, 2, 3, 4
 FLAT_FAMILY = (EARTH_FLAT_DISTORTED, EARTH_AZIMUTHAL_EQUIDISTANT, EARTH_OBSERVER_AE)  # the world is the azimuthal-equidistant plane
 ALT_ABSOLUTE, ALT_RELATIVE = 0, 1
-GENERATOR_FAST, GENERATOR_RECTILINEAR = 0, 1
+GENERATOR_FAST, GENERATOR_RECTILINEAR, GENERATOR_INTERPOLATING_RECTILINEAR = 0, 1, 2
 COLORING_SIMPLE, COLORING_SHADING = 0, 1
 PALETTE_LEGACY, PALETTE_IMPROVED = 0, 1
 OBJECT_FRUSTUM, OBJECT_BILLBOARD = 0, 1

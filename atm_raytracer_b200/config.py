@@ -354,8 +354,10 @@ def into_params(cfg, x0=None, x1=None):
         p.generator = abi.GENERATOR_FAST
     elif gen == "Rectilinear":
         p.generator = abi.GENERATOR_RECTILINEAR
+    elif gen == "InterpolatingRectilinear":
+        p.generator = abi.GENERATOR_INTERPOLATING_RECTILINEAR
     else:
-        raise ConfigError(f"generator {gen} is outside the hot-path scope (SURVEY section 8 f1)")
+        raise ConfigError(f"unknown generator {gen!r}")
     p.x0 = 0 if x0 is None else int(x0)
     p.x1 = p.width if x1 is None else int(x1)
     return p

@@ -19,7 +19,7 @@
 
 using namespace atmrt;
 
-static_assert(sizeof(DevScene) < 4000, "DevScene must fit the kernel parameter space");
+static_assert(sizeof(DevScene) < 8000, "DevScene must fit the kernel parameter space (32764 bytes on sm_70+ with CUDA >= 12.1)");
 
 namespace {
 
@@ -97,6 +97,13 @@ struct atmrt_ctx {
     int sweep_bands = 0;                // 0: chosen per render (launch_render)
     DevBuf d_stage;  // raw posts of pack_terrain on their way to the tiled layout
     bool sweep_enabled = true;
+    // InterpolatingRectilinear generator: the grid's angle tables (device) while its Fast render is prepared, its trace lists,
+    // the statistics of that render
+    const double* grid_row_elev = nullptr;
+    const double* grid_col_dir = nullptr;
+    DevBuf d_interp, d_grid_angles, d_grid_points, d_grid_counts;
+    atmrt_stats grid_stats{};
+    int grid_overflows = 0;
     DevBuf d_dist, d_colcalc, d_tlat, d_tlon, d_telev, d_tclose;
     DevBuf d_pdist, d_pelev, d_plen, d_pn;
     DevBuf d_tmin1, d_tmax1, d_tmin2, d_tmax2, d_tmin3, d_tmax3, d_close1, d_close2, d_close3;
@@ -544,7 +551,8 @@ int validate_params(atmrt_ctx* ctx, const atmrt_params& p) {
         return fail(ctx, ATMRT_ERR_INVALID, "radius (Spherical radius, Ellipsoid a, ObserverAe proj_radius) must be positive");
     if (p.earth_model == ATMRT_EARTH_ELLIPSOID && !(p.ellipsoid_b > 0.0)) return fail(ctx, ATMRT_ERR_INVALID, "ellipsoid_b must be positive");
     if (p.coloring != ATMRT_COLORING_SIMPLE && p.coloring != ATMRT_COLORING_SHADING) return fail(ctx, ATMRT_ERR_INVALID, "unknown coloring");
-    if (p.generator != ATMRT_GENERATOR_FAST && p.generator != ATMRT_GENERATOR_RECTILINEAR) return fail(ctx, ATMRT_ERR_INVALID, "unknown generator");
+    if (p.generator != ATMRT_GENERATOR_FAST && p.generator != ATMRT_GENERATOR_RECTILINEAR && p.generator != ATMRT_GENERATOR_INTERPOLATING_RECTILINEAR)
+        return fail(ctx, ATMRT_ERR_INVALID, "unknown generator");
     return 0;
 }
 
@@ -671,8 +679,11 @@ int prepare_render(atmrt_ctx* ctx) {
     const size_t wl = (size_t)(p.x1 - p.x0), h = (size_t)p.height, np = (size_t)S.n_pad;
     const size_t f8 = sizeof(double);
     int e = 0;
-    const bool rect = p.generator == ATMRT_GENERATOR_RECTILINEAR;  // one ray and one walk per pixel: no caches
+    // Rectilinear: one ray and one walk per pixel, no caches; InterpolatingRectilinear: the caches belong to its grid,
+    // which is prepared as a Fast render of its own (launch_interpolating)
+    const bool rect = p.generator != ATMRT_GENERATOR_FAST;
     S.generator = p.generator;
+    S.row_elev_deg = ctx->grid_row_elev, S.col_dir_deg = ctx->grid_col_dir;
     e |= ensure(ctx, ctx->d_dist, f8 * (3 * n_t + 2));  // dist_k, then (sin, cos)(dist_k / R)
     e |= ensure(ctx, ctx->d_pdist, f8 * 2 * S.n_x);
     if (!rect) {
@@ -887,7 +898,11 @@ int next_stage_events(atmrt_ctx* ctx, atmrt_ctx::StageEvents** out) {
     }
 #define KT_END(id, st) CUDA_TRY(ctx, cudaEventRecord(E->k1[id], st));
 
+int launch_interpolating(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main);
+int collect_stats(atmrt_ctx* ctx, atmrt_stats* stats);
+
 int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
+    if (ctx->scene.generator == ATMRT_GENERATOR_INTERPOLATING_RECTILINEAR) return launch_interpolating(ctx, rt, main);
     const DevScene& S = ctx->scene;
     const DevBuffers& B = ctx->buf;
     const int wl = S.x1 - S.x0, h = S.height;
@@ -1120,12 +1135,113 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
     return 0;
 }
 
+// FovData::min_elev_step / min_dir_step (interpolating_rectilinear.rs:432-521) of the image `S` describes, in radians
+int interpolating_steps(atmrt_ctx* ctx, const DevScene& S, cudaStream_t main, double* elev_step, double* dir_step) {
+    int rc = ensure(ctx, ctx->d_interp, 64);
+    if (rc) return rc;
+    const double two_pi = 360.0 * (PI / 180.0);
+    unsigned long long init[2];
+    memcpy(&init[0], &two_pi, 8), init[1] = init[0];
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_interp.p, init, sizeof(init), cudaMemcpyHostToDevice, main));
+    k_interp_steps<<<dim3((S.width + 127) / 128, S.height), 128, 0, main>>>(S, (unsigned long long*)ctx->d_interp.p);
+    CUDA_TRY(ctx, cudaGetLastError());
+    double mins[2];
+    CUDA_TRY(ctx, cudaMemcpyAsync(mins, ctx->d_interp.p, sizeof(mins), cudaMemcpyDeviceToHost, main));
+    CUDA_TRY(ctx, cudaStreamSynchronize(main));
+    const double scale = 1.5;
+    *elev_step = mins[0] * scale, *dir_step = mins[1] * scale;
+    return 0;
+}
+
+// InterpolatingRectilinearGenerator::generate (interpolating_rectilinear.rs:121-170). The reference fills its caches
+// lazily, grid point by grid point; here the grid that covers the column block is one Fast render with explicit angle
+// tables that keeps its trace lists on the device, and one kernel blends them into the image.
+int launch_interpolating(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
+    const atmrt_params image_params = ctx->params;
+    const DevScene S = ctx->scene;  // the image: frame, size, column block, shading
+    const int wl = S.x1 - S.x0, h = S.height;
+    double elev_step, dir_step;
+    int rc = interpolating_steps(ctx, S, main, &elev_step, &dir_step);
+    if (rc) return rc;
+    if (!(elev_step > 0.0) || !(dir_step > 0.0)) return fail(ctx, ATMRT_ERR_INVALID, "InterpolatingRectilinear: the field of view yields no grid step");
+    // the grid points the column block reads: floor(angle / step) and the next one, per pixel (FovData::cache_coords, :185-204)
+    int range[4] = {INT_MAX, -INT_MAX, INT_MAX, -INT_MAX};
+    int* d_range = (int*)((char*)ctx->d_interp.p + 16);
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_range, range, sizeof(range), cudaMemcpyHostToDevice, main));
+    k_interp_range<<<dim3((wl + 127) / 128, h), 128, 0, main>>>(S, elev_step, dir_step, d_range);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(range, d_range, sizeof(range), cudaMemcpyDeviceToHost, main));
+    CUDA_TRY(ctx, cudaStreamSynchronize(main));
+    const long long rows = (long long)range[1] + 1 - range[0] + 1, cols = (long long)range[3] + 1 - range[2] + 1;
+    if (rows < 2 || cols < 2 || rows > 32767 || cols > 32767) return fail(ctx, ATMRT_ERR_INVALID, "InterpolatingRectilinear: the grid does not fit 32767 x 32767 points");
+    InterpGrid G{};
+    G.elev_step = elev_step, G.dir_step = dir_step;
+    G.elev_top = range[1] + 1, G.dir_left = range[2];
+    G.rows = (int)rows, G.cols = (int)cols, G.max_points = INTERP_MAX_POINTS;
+    // Cache::get_path_cache / get_terrain_cache, :46-84: index * step, in degrees; rows from the highest elevation down
+    std::vector<double> angles((size_t)(rows + cols));
+    for (int j = 0; j < G.rows; ++j) angles[(size_t)j] = to_degrees((double)(G.elev_top - j) * elev_step);
+    for (int i = 0; i < G.cols; ++i) angles[(size_t)G.rows + i] = to_degrees((double)(G.dir_left + i) * dir_step);
+    if ((rc = ensure(ctx, ctx->d_grid_angles, sizeof(double) * angles.size()))) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_grid_angles.p, angles.data(), sizeof(double) * angles.size(), cudaMemcpyHostToDevice, main));
+    CUDA_TRY(ctx, cudaStreamSynchronize(main));  // `angles` is pageable
+    const size_t npoints = (size_t)rows * (size_t)cols;
+    if ((rc = ensure(ctx, ctx->d_grid_points, npoints * sizeof(atmrt_trace_point) * INTERP_MAX_POINTS))) return rc;
+    if ((rc = ensure(ctx, ctx->d_grid_counts, npoints * sizeof(int)))) return rc;
+
+    // ---- the grid: a Fast render of rows x cols pixels with these angles, trace lists kept ----
+    atmrt_params grid_params = image_params;
+    grid_params.generator = ATMRT_GENERATOR_FAST;
+    grid_params.width = G.cols, grid_params.height = G.rows, grid_params.x0 = 0, grid_params.x1 = G.cols;
+    ctx->params = grid_params;
+    ctx->grid_row_elev = (const double*)ctx->d_grid_angles.p;
+    ctx->grid_col_dir = (const double*)ctx->d_grid_angles.p + G.rows;
+    rc = prepare_render(ctx);
+    if (!rc) {
+        RenderTargets grid;
+        grid.points = (atmrt_trace_point*)ctx->d_grid_points.p;
+        grid.counts = (int*)ctx->d_grid_counts.p;
+        grid.max_points = INTERP_MAX_POINTS;
+        rc = launch_render(ctx, grid, main);
+    }
+    if (!rc) rc = collect_stats(ctx, &ctx->grid_stats);  // (synchronises) ray steps, path steps, terrain samples are the grid's
+    const int grid_launches = ctx->launches;
+    ctx->params = image_params;
+    ctx->grid_row_elev = ctx->grid_col_dir = nullptr;
+    ctx->scene = S;
+    if (rc) return rc;
+
+    // ---- the image: blend the four grid pixels around every pixel's own ray, colour and composite ----
+    G.points = (const atmrt_trace_point*)ctx->d_grid_points.p;
+    G.counts = (const int*)ctx->d_grid_counts.p;
+    const DevBuffers& B = ctx->buf;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 8 * CNT_COUNT, main));
+    MarchOut O{rt.rgb, rt.meta, rt.steps, rt.points, rt.counts, rt.max_points};
+    const dim3 grid_dim((wl + 127) / 128, h);
+    if (rt.points || rt.counts) k_interp_blend<true><<<grid_dim, 128, 0, main>>>(S, B, O, G);
+    else k_interp_blend<false><<<grid_dim, 128, 0, main>>>(S, B, O, G);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches = grid_launches + 3;
+    ctx->rendered = true;
+    return 0;
+}
+
 int collect_stats(atmrt_ctx* ctx, atmrt_stats* stats) {
     if (!stats) return 0;
     const DevScene& S = ctx->scene;
     unsigned long long c[CNT_COUNT];
     CUDA_TRY(ctx, cudaMemcpy(c, ctx->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost));
     std::vector<int> pn(S.height, 0);
+    if (S.generator == ATMRT_GENERATOR_INTERPOLATING_RECTILINEAR) {
+        // the marches are the grid's; trace points and hit pixels are the blended image's; a grid pixel with more trace
+        // points than the blend keeps counts as an overflow of every image pixel that reads it
+        *stats = ctx->grid_stats;
+        stats->trace_points = c[CNT_TRACE_POINTS];
+        stats->pixels_hit = c[CNT_PIXELS_HIT];
+        stats->step_overflows = ctx->grid_stats.step_overflows + c[CNT_OVERFLOWS];
+        stats->kernel_launches = ctx->launches;
+        return 0;
+    }
     const bool rect = S.generator == ATMRT_GENERATOR_RECTILINEAR;  // no path cache
     if (!rect) CUDA_TRY(ctx, cudaMemcpy(pn.data(), ctx->d_pn.p, sizeof(int) * S.height, cudaMemcpyDeviceToHost));
     memset(stats, 0, sizeof(*stats));
@@ -1249,7 +1365,7 @@ void atmrt_destroy(atmrt_ctx* ctx) {
                       &ctx->d_tclose, &ctx->d_pdist, &ctx->d_pelev, &ctx->d_plen, &ctx->d_pn,
                       &ctx->d_tmin1, &ctx->d_tmax1, &ctx->d_tmin2, &ctx->d_tmax2, &ctx->d_tmin3, &ctx->d_tmax3, &ctx->d_close1, &ctx->d_close2, &ctx->d_close3, &ctx->d_rmin1, &ctx->d_rmin3, &ctx->d_rmax3,
                       &ctx->d_rmax1, &ctx->d_rmin2, &ctx->d_rmax2, &ctx->d_obs, &ctx->d_counters, &ctx->d_atm_cells, &ctx->d_sweep_flags, &ctx->d_sweep_col, &ctx->d_sweep_hit, &ctx->d_cross, &ctx->d_cross_trig, &ctx->d_list, &ctx->d_count, &ctx->d_normals, &ctx->d_anchor, &ctx->d_stage, &ctx->d_atm_aux, &ctx->d_rgb, &ctx->d_meta,
-                      &ctx->d_steps, &ctx->d_points, &ctx->d_counts, &ctx->d_probe_a, &ctx->d_probe_b, &ctx->d_probe_c, &ctx->d_probe_d};
+                      &ctx->d_steps, &ctx->d_points, &ctx->d_counts, &ctx->d_interp, &ctx->d_grid_angles, &ctx->d_grid_points, &ctx->d_grid_counts, &ctx->d_probe_a, &ctx->d_probe_b, &ctx->d_probe_c, &ctx->d_probe_d};
     for (DevBuf* b : bufs) release(*b);
     for (DevBuf& b : ctx->textures) release(b);
     if (ctx->terrain_owned) cudaFree(ctx->terrain_owned);
@@ -1745,6 +1861,13 @@ int atmrt_pixel_angles(atmrt_ctx* ctx, double* elevation_angle, double* azimuth)
     const size_t wl = (size_t)(p.x1 - p.x0), bytes = sizeof(double) * wl * (size_t)p.height;
     if ((elevation_angle && ensure(ctx, ctx->d_probe_a, bytes)) || (azimuth && ensure(ctx, ctx->d_probe_b, bytes))) return ATMRT_ERR_CUDA;
     cudaStream_t s = ctx->s_main;
+    if (p.generator == ATMRT_GENERATOR_INTERPOLATING_RECTILINEAR) {
+        double elev_step, dir_step;
+        int rc = interpolating_steps(ctx, S, s, &elev_step, &dir_step);
+        if (rc) return rc;
+        k_interp_angles<<<dim3((unsigned)((wl + 127) / 128), (unsigned)p.height), 128, 0, s>>>(S, elev_step, dir_step, elevation_angle ? (double*)ctx->d_probe_a.p : nullptr,
+                                                                                             azimuth ? (double*)ctx->d_probe_b.p : nullptr);
+    } else
     k_pixel_angles<<<dim3((unsigned)((wl + 127) / 128), (unsigned)p.height), 128, 0, s>>>(S, elevation_angle ? (double*)ctx->d_probe_a.p : nullptr,
                                                                                         azimuth ? (double*)ctx->d_probe_b.p : nullptr);
     CUDA_TRY(ctx, cudaGetLastError());

@@ -538,7 +538,8 @@ static void apply_yaml(const Node& doc, Config* c) {
         {
             if (g->scalar == "Fast") c->generator = ATMRT_GENERATOR_FAST;
             else if (g->scalar == "Rectilinear") c->generator = ATMRT_GENERATOR_RECTILINEAR;
-            else throw std::runtime_error("generator " + g->scalar + " is outside the device path (Fast, Rectilinear)");
+            else if (g->scalar == "InterpolatingRectilinear") c->generator = ATMRT_GENERATOR_INTERPOLATING_RECTILINEAR;
+            else throw std::runtime_error("unknown generator " + g->scalar + " (Fast, Rectilinear, InterpolatingRectilinear)");
         }
         for (const char* k : {"ticks", "vertical_ticks"})
             if (const Node* t = out->get(k))

@@ -38,6 +38,10 @@ struct DevScene {
     int earth_model, straight, flat;
     int width, height, x0, x1;
     int generator;  // atmrt_generator
+    // explicit ray angles in degrees instead of the image's (the grid of the InterpolatingRectilinear generator): one
+    // elevation per row, one direction per column; null for the image's own
+    const double* row_elev_deg;
+    const double* col_dir_deg;
     int n_x;     // entries of path_x / path_dxr (n_t + 2)
     int n_sc_off;  // offset of walk_sc behind dist_k
     int n_t;     // terrain samples per column (N_t)
@@ -196,11 +200,13 @@ __global__ void k_prepare_scene(const __grid_constant__ DevScene S, DevTerrain T
 
 // get_ray_dir / get_ray_elev, generators/fast.rs:111-125 (pixel centring goes through i16)
 __device__ __forceinline__ double get_ray_dir(const DevScene& S, int x) {
+    if (S.col_dir_deg) return S.col_dir_deg[x];
     double width = (double)S.width;
     double xx = (double)(short)((short)x - (short)S.width / 2) / width;
     return S.direction + xx * S.fov;
 }
 __device__ __forceinline__ double get_ray_elev(const DevScene& S, int y) {
+    if (S.row_elev_deg) return S.row_elev_deg[y];
     double width = (double)S.width, height = (double)S.height;
     double aspect = width / height;
     double yy = (double)(short)((short)y - (short)S.height / 2) / height;
@@ -1620,6 +1626,231 @@ __global__ void __launch_bounds__(128) k_pixel_angles(const __grid_constant__ De
     const size_t pixel = (size_t)y * wl + xl;
     if (elevation_angle) elevation_angle[pixel] = el;
     if (azimuth) azimuth[pixel] = az;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The InterpolatingRectilinear generator (generators/interpolating_rectilinear.rs): the rectilinear image's rays,
+// served from a regular grid in (elevation, direction) whose points are Fast-generator pixels. The grid itself is an
+// ordinary Fast render with explicit angle tables (DevScene::row_elev_deg / col_dir_deg) that keeps its trace lists;
+// these kernels find the grid's steps and extent and blend the lists.
+// ---------------------------------------------------------------------------------------------
+struct InterpGrid {
+    double elev_step, dir_step;  // FovData::min_elev_step / min_dir_step (radians)
+    int elev_top;                // elevation index of grid row 0 (rows run downwards, like an image)
+    int dir_left;                // direction index of grid column 0
+    int rows, cols;
+    int max_points;              // trace points kept per grid pixel
+    const atmrt_trace_point* points;  // [rows][cols][max_points]
+    const int* counts;                // [rows][cols], the true counts
+};
+
+// gen_fov_data, interpolating_rectilinear.rs:432-521: the smallest |difference| of elevation between vertical neighbours
+// and of direction between horizontal neighbours over the WHOLE image, each difference raised to fov / width / 3. The
+// differences are positive doubles: their bit patterns order like the values. mins[0], mins[1] start at 2 pi.
+__global__ void __launch_bounds__(128) k_interp_steps(const __grid_constant__ DevScene S, unsigned long long* __restrict__ mins) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    double d_elev = 1.0e300, d_dir = 1.0e300;
+    if (x < S.width) {
+        const double two_pi = 360.0 * (PI / 180.0), min_diff = to_radians(S.fov) / (double)S.width / 3.0;
+        double el, az, el2, az2;
+        get_ray_params(S, x, y, &el, &az);
+        if (y >= 1) {
+            get_ray_params(S, x, y - 1, &el2, &az2);
+            d_elev = fmax(fabs(el - el2), min_diff);  // (`if diff < min_diff { diff = min_diff }`; a NaN difference is never the minimum)
+            if (!(d_elev == d_elev)) d_elev = 1.0e300;
+        }
+        if (x >= 1) {
+            get_ray_params(S, x - 1, y, &el2, &az2);
+            double diff = fabs(az - az2);
+            if (diff > two_pi) diff -= two_pi;
+            d_dir = fmax(diff, min_diff);
+            if (!(d_dir == d_dir)) d_dir = 1.0e300;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        d_elev = fmin(d_elev, __shfl_xor_sync(FULL, d_elev, o));
+        d_dir = fmin(d_dir, __shfl_xor_sync(FULL, d_dir, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(mins + 0, (unsigned long long)__double_as_longlong(d_elev));
+        atomicMin(mins + 1, (unsigned long long)__double_as_longlong(d_dir));
+    }
+}
+
+// FovData::cache_coords, :185-204, of one pixel
+struct InterpCorner {
+    int elev_index, dir_index;
+    double rem_elev, rem_dir;
+};
+__device__ __forceinline__ InterpCorner interp_corner(const DevScene& S, double elev_step, double dir_step, int x, int y) {
+    double el, az;
+    get_ray_params(S, x, y, &el, &az);
+    const double ef = el / elev_step, df = az / dir_step;
+    InterpCorner c;
+    c.elev_index = (int)floor(ef), c.dir_index = (int)floor(df);
+    c.rem_elev = ef - (double)c.elev_index, c.rem_dir = df - (double)c.dir_index;
+    return c;
+}
+
+// the index ranges the column block needs: range = {min elev, max elev, min dir, max dir} (starting at +-INT_MAX)
+__global__ void __launch_bounds__(128) k_interp_range(const __grid_constant__ DevScene S, double elev_step, double dir_step, int* __restrict__ range) {
+    const int xl = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    int e_lo = INT_MAX, e_hi = -INT_MAX, d_lo = INT_MAX, d_hi = -INT_MAX;
+    if (xl < S.x1 - S.x0) {
+        const InterpCorner c = interp_corner(S, elev_step, dir_step, S.x0 + xl, y);
+        e_lo = e_hi = c.elev_index, d_lo = d_hi = c.dir_index;
+    }
+    e_lo = __reduce_min_sync(FULL, e_lo), e_hi = __reduce_max_sync(FULL, e_hi);
+    d_lo = __reduce_min_sync(FULL, d_lo), d_hi = __reduce_max_sync(FULL, d_hi);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(range + 0, e_lo), atomicMax(range + 1, e_hi);
+        atomicMin(range + 2, d_lo), atomicMax(range + 3, d_hi);
+    }
+}
+
+// TracePoint::interpolate / PixelColor::interpolate (generators/mod.rs:32-80): self * (1 - coeff) + other * coeff
+struct BlendPoint {
+    double lat, lon, distance, elevation, path_length;
+    V3 normal;
+    Color4 color;
+    bool is_terrain;
+    int step;
+};
+__device__ __forceinline__ BlendPoint load_point(const atmrt_trace_point& t) {
+    return {t.lat, t.lon, t.distance, t.elevation, t.path_length, V3{t.normal[0], t.normal[1], t.normal[2]},
+            Color4{t.color[0], t.color[1], t.color[2], t.color[3]}, t.is_terrain != 0, t.step};
+}
+__device__ __forceinline__ BlendPoint blend(const BlendPoint& a, const BlendPoint& b, double coeff) {
+    const double ca = 1.0 - coeff;
+    BlendPoint r;
+    r.lat = a.lat * ca + b.lat * coeff, r.lon = a.lon * ca + b.lon * coeff, r.distance = a.distance * ca + b.distance * coeff;
+    r.elevation = a.elevation * ca + b.elevation * coeff, r.path_length = a.path_length * ca + b.path_length * coeff;
+    r.normal = a.normal * ca + b.normal * coeff;
+    r.is_terrain = a.is_terrain || b.is_terrain;
+    if (a.is_terrain && b.is_terrain) r.color = Color4{0.0, 0.0, 0.0, a.color.a * ca + b.color.a * coeff};
+    else if (!a.is_terrain && !b.is_terrain)
+        r.color = Color4{a.color.r * ca + b.color.r * coeff, a.color.g * ca + b.color.g * coeff, a.color.b * ca + b.color.b * coeff, a.color.a * ca + b.color.a * coeff};
+    else r.color = Color4{0.0, 0.0, 0.0, a.is_terrain ? a.color.a : b.color.a};
+    r.step = a.step;
+    return r;
+}
+
+// interpolate_trace_points, :274-345: `e[i]` the group's point of grid pixel SEQUENCE[i] = (elev + i / 2, dir + i % 2)
+__device__ inline bool blend_group(const atmrt_trace_point* const e[4], double re, double rd, BlendPoint* out) {
+    const int have = (e[0] ? 1 : 0) | (e[1] ? 2 : 0) | (e[2] ? 4 : 0) | (e[3] ? 8 : 0);
+    int a = -1, b = -1, c = -1;  // the points in the order the rule takes them
+    double r_elev = re, r_dir = rd;
+    int rule;  // 1: single, 2: two adjacent, 3: two diagonal, 4: three, 5: four
+    switch (have) {
+        case 1: rule = 1, a = 0; if (!(re < 0.5 && rd < 0.5)) return false; break;
+        case 2: rule = 1, a = 1; if (!(re < 0.5 && rd >= 0.5)) return false; break;
+        case 4: rule = 1, a = 2; if (!(re >= 0.5 && rd < 0.5)) return false; break;
+        case 8: rule = 1, a = 3; if (!(re >= 0.5 && rd >= 0.5)) return false; break;
+        case 1 | 2: rule = 2, a = 0, b = 1; break;
+        case 1 | 4: rule = 2, a = 0, b = 2, r_elev = rd, r_dir = re; break;
+        case 1 | 8: rule = 3, a = 0, b = 3; break;
+        case 2 | 4: rule = 3, a = 1, b = 2, r_dir = 1.0 - rd; break;
+        case 2 | 8: rule = 2, a = 1, b = 3, r_elev = 1.0 - rd, r_dir = re; break;
+        case 4 | 8: rule = 2, a = 2, b = 3, r_elev = 1.0 - re; break;
+        case 1 | 2 | 4: rule = 4, a = 0, b = 1, c = 2; break;
+        case 1 | 2 | 8: rule = 4, a = 1, b = 0, c = 3, r_dir = 1.0 - rd; break;
+        case 1 | 4 | 8: rule = 4, a = 0, b = 3, c = 2, r_elev = 1.0 - re; break;
+        case 2 | 4 | 8: rule = 4, a = 3, b = 2, c = 1, r_elev = 1.0 - re, r_dir = 1.0 - rd; break;
+        case 15: rule = 5; break;
+        default: return false;
+    }
+    if (rule == 1) {
+        *out = load_point(*e[a]);
+    } else if (rule == 2) {  // interpolate_two_adjacent
+        if (r_elev >= 0.5) return false;
+        *out = blend(load_point(*e[a]), load_point(*e[b]), r_dir);
+    } else if (rule == 3) {  // interpolate_two_diagonal
+        if ((r_elev >= 0.5 && r_dir < 0.5) || (r_elev < 0.5 && r_dir >= 0.5)) return false;
+        const double coeff = r_elev * r_dir / (r_elev * r_dir + (1.0 - r_elev) * (1.0 - r_dir));
+        *out = blend(load_point(*e[a]), load_point(*e[b]), coeff);
+    } else if (rule == 4) {  // interpolate_three
+        if (r_elev >= 0.5 && r_dir >= 0.5) return false;
+        const double sum = 1.0 - r_elev + r_elev * (1.0 - r_dir);
+        *out = blend(blend(load_point(*e[a]), load_point(*e[b]), r_dir), load_point(*e[c]), r_elev * (1.0 - r_dir) / sum);
+    } else {  // interpolate_four
+        *out = blend(blend(load_point(*e[0]), load_point(*e[1]), rd), blend(load_point(*e[2]), load_point(*e[3]), rd), re);
+    }
+    return true;
+}
+
+constexpr int INTERP_MAX_POINTS = 8;  // trace points kept per grid pixel (a grid pixel with more is counted in step_overflows)
+
+// interpolate (:394-419) + draw_image for one image pixel: group the trace points of the four grid pixels
+// (collect_trace_points, :213-243: a point joins the FIRST group holding a point of its class closer than one simulation
+// step in distance, else opens one; a later point of the same grid pixel replaces the earlier one in the group's slot),
+// blend every group and composite the results in group order.
+template <bool TRACE>
+__global__ void __launch_bounds__(128) k_interp_blend(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, InterpGrid G) {
+    const int wl = S.x1 - S.x0;
+    const int xl = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const bool active = xl < wl;
+    const int xx = min(xl, wl - 1);
+    const size_t pixel = (size_t)y * wl + xx;
+    const InterpCorner c = interp_corner(S, G.elev_step, G.dir_step, S.x0 + xx, y);
+    PixelState st;
+    init_pixel(st);
+    signed char group_of[4][INTERP_MAX_POINTS];  // the group of every point of the four lists
+    const atmrt_trace_point* list[4];
+    int n[4], ngroups = 0;
+    bool overflow = false;
+    for (int q = 0; q < 4; ++q) {
+        const int row = G.elev_top - (c.elev_index + q / 2), col = c.dir_index + q % 2 - G.dir_left;
+        const bool inside = row >= 0 && row < G.rows && col >= 0 && col < G.cols;  // (always, for the block the grid was made for)
+        const size_t g = inside ? (size_t)row * G.cols + col : 0;
+        list[q] = G.points + g * G.max_points;
+        const int cnt = inside ? G.counts[g] : 0;
+        overflow |= cnt > G.max_points;
+        n[q] = min(min(cnt, G.max_points), INTERP_MAX_POINTS);
+    }
+    for (int q = 0; q < 4; ++q)
+        for (int i = 0; i < n[q]; ++i) {
+            const double dist = list[q][i].distance;
+            const int cls = list[q][i].is_terrain;
+            int g = ngroups;  // the first group (in order of creation) that holds a close point of the same class
+            for (int q2 = 0; q2 <= q; ++q2)
+                for (int i2 = 0; i2 < (q2 == q ? i : n[q2]); ++i2)
+                    if (group_of[q2][i2] < g && fabs(dist - list[q2][i2].distance) < S.step && cls == list[q2][i2].is_terrain) g = group_of[q2][i2];
+            if (g == ngroups) ++ngroups;
+            group_of[q][i] = (signed char)g;
+        }
+    for (int g = 0; g < ngroups; ++g) {
+        const atmrt_trace_point* e[4] = {nullptr, nullptr, nullptr, nullptr};
+        for (int q = 0; q < 4; ++q)
+            for (int i = 0; i < n[q]; ++i)
+                if (group_of[q][i] == g) e[q] = list[q] + i;  // match_sequence, :245-266: the last one wins the slot
+        BlendPoint p;
+        if (blend_group(e, c.rem_elev, c.rem_dir, &p))
+            emit_point<TRACE>(S, O, pixel, p.step, st, p.is_terrain, p.lat, p.lon, p.distance, p.elevation, p.path_length, p.normal, p.color);
+    }
+    if (overflow) st.overflows += 1;
+    write_pixel<TRACE>(S, B, O, pixel, active, st, 0);
+}
+
+// ResultPixel.elevation_angle / azimuth of the blended pixel (interpolate, :405-417): the four grid pixels' angles (azimuth
+// wrapped once into [0, 360), Cache::get_pixel :97-103) weighted with the remainders
+__global__ void __launch_bounds__(128) k_interp_angles(const __grid_constant__ DevScene S, double elev_step, double dir_step, double* __restrict__ elevation_angle,
+                                                       double* __restrict__ azimuth) {
+    const int wl = S.x1 - S.x0;
+    const int xl = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (xl >= wl) return;
+    const InterpCorner c = interp_corner(S, elev_step, dir_step, S.x0 + xl, y);
+    double e4[4], a4[4];
+    for (int q = 0; q < 4; ++q) {
+        e4[q] = to_degrees((double)(c.elev_index + q / 2) * elev_step);
+        double a = to_degrees((double)(c.dir_index + q % 2) * dir_step);
+        if (a < 0.0) a += 360.0;
+        else if (a >= 360.0) a -= 360.0;
+        a4[q] = a;
+    }
+    const double re = c.rem_elev, rd = c.rem_dir;
+    const size_t pixel = (size_t)y * wl + xl;
+    if (elevation_angle) elevation_angle[pixel] = e4[0] * (1.0 - re) * (1.0 - rd) + e4[1] * (1.0 - re) * rd + e4[2] * re * (1.0 - rd) + e4[3] * re * rd;
+    if (azimuth) azimuth[pixel] = a4[0] * (1.0 - re) * (1.0 - rd) + a4[1] * (1.0 - re) * rd + a4[2] * re * (1.0 - rd) + a4[3] * re * rd;
 }
 
 constexpr int RECT_THREADS = 128;

@@ -52,7 +52,7 @@ typedef enum atmrt_earth_model {
 
 /* GeneratorDef (generator/mod.rs:72-78): Fast (generators/fast.rs: separable caches) or Rectilinear
  * (generators/rectilinear.rs: one ray and one azimuth walk per pixel of a rectilinear projection). */
-typedef enum atmrt_generator { ATMRT_GENERATOR_FAST = 0, ATMRT_GENERATOR_RECTILINEAR = 1 } atmrt_generator;
+typedef enum atmrt_generator { ATMRT_GENERATOR_FAST = 0, ATMRT_GENERATOR_RECTILINEAR = 1, ATMRT_GENERATOR_INTERPOLATING_RECTILINEAR = 2 } atmrt_generator;
 
 /* Altitude (generator/params.rs:17-30) */
 typedef enum atmrt_altitude_kind { ATMRT_ALT_ABSOLUTE = 0, ATMRT_ALT_RELATIVE = 1 } atmrt_altitude_kind;

@@ -1153,6 +1153,142 @@ struct PathIteratorSource {
 };
 
 // ------------------------------------------------------------------------------------------
+// InterpolatingRectilinear generator: generators/interpolating_rectilinear.rs. A regular grid in (elevation,
+// direction) -- steps = 1.5 x the smallest angular distance between neighbouring pixels of the rectilinear image
+// (gen_fov_data, :432-521) -- whose points are Fast-generator pixels (one path cache per elevation index, one
+// terrain cache per direction index, get_single_pixel on the pair, :86-117); an image pixel blends the trace points
+// of the four grid points around its own ray (interpolate, :394-419).
+// ------------------------------------------------------------------------------------------
+struct FovData {
+    double min_elev_step, min_dir_step;
+};
+
+// gen_fov_data, interpolating_rectilinear.rs:432-521 (over the WHOLE image, whatever column block is rendered)
+FovData gen_fov_data(const atmrt_params& p, const std::vector<RayParams>& table) {
+    const int W = p.width, H = p.height;
+    const double two_pi = 360.0 * (PI / 180.0), min_diff = p.fov * (PI / 180.0) / (double)W / 3.0, scale = 1.5;
+    double min_elev = std::numeric_limits<double>::infinity(), min_dir = std::numeric_limits<double>::infinity();
+    for (int x = 0; x < W; ++x) {
+        double m = two_pi, last = table[x].elevation;
+        for (int y = 1; y < H; ++y) {
+            const double next = table[(size_t)y * W + x].elevation;
+            double diff = std::fabs(next - last);
+            if (diff < min_diff) diff = min_diff;
+            if (diff < m) m = diff;
+            last = next;
+        }
+        min_elev = std::fmin(min_elev, m);
+    }
+    for (int y = 0; y < H; ++y) {
+        double m = two_pi, last = table[(size_t)y * W].direction;
+        for (int x = 1; x < W; ++x) {
+            const double next = table[(size_t)y * W + x].direction;
+            double diff = std::fabs(next - last);
+            if (diff > two_pi) diff -= two_pi;
+            if (diff < min_diff) diff = min_diff;
+            if (diff < m) m = diff;
+            last = next;
+        }
+        min_dir = std::fmin(min_dir, m);
+    }
+    return {min_elev * scale, min_dir * scale};
+}
+
+// PixelColor::same_class / TracePoint::interpolate (generators/mod.rs:32-80): self * (1 - coeff) + other * coeff
+TracePoint blend(const TracePoint& a, const TracePoint& b, double coeff) {
+    auto mix = [&](double u, double v) { return u * (1.0 - coeff) + v * coeff; };
+    TracePoint r;
+    r.lat = mix(a.lat, b.lat), r.lon = mix(a.lon, b.lon), r.distance = mix(a.distance, b.distance);
+    r.elevation = mix(a.elevation, b.elevation), r.path_length = mix(a.path_length, b.path_length);
+    r.normal = a.normal * (1.0 - coeff) + b.normal * coeff;
+    r.is_terrain = a.is_terrain || b.is_terrain;  // a mixed pair is Terrain (it does not occur: groups hold one class)
+    if (a.is_terrain && b.is_terrain) r.color = Color{0, 0, 0, mix(a.color.a, b.color.a)};
+    else if (!a.is_terrain && !b.is_terrain) r.color = Color{mix(a.color.r, b.color.r), mix(a.color.g, b.color.g), mix(a.color.b, b.color.b), mix(a.color.a, b.color.a)};
+    else r.color = Color{0, 0, 0, a.is_terrain ? a.color.a : b.color.a};
+    r.step = a.step;
+    return r;
+}
+
+// interpolate_trace_points, :274-345: slot i = SEQUENCE[i] = (elev + i / 2, dir + i % 2). False: the group yields nothing.
+bool blend_group(const TracePoint* e[4], double re, double rd, TracePoint* out) {
+    const int have = (e[0] ? 1 : 0) | (e[1] ? 2 : 0) | (e[2] ? 4 : 0) | (e[3] ? 8 : 0);
+    auto two_adjacent = [&](const TracePoint& a, const TracePoint& b, double r_elev, double r_dir) {
+        if (r_elev >= 0.5) return false;
+        *out = blend(a, b, r_dir);
+        return true;
+    };
+    auto two_diagonal = [&](const TracePoint& a, const TracePoint& b, double r_elev, double r_dir) {
+        if ((r_elev >= 0.5 && r_dir < 0.5) || (r_elev < 0.5 && r_dir >= 0.5)) return false;
+        const double coeff = r_elev * r_dir / (r_elev * r_dir + (1.0 - r_elev) * (1.0 - r_dir));
+        *out = blend(a, b, coeff);
+        return true;
+    };
+    auto three = [&](const TracePoint& a, const TracePoint& b, const TracePoint& c, double r_elev, double r_dir) {
+        if (r_elev >= 0.5 && r_dir >= 0.5) return false;
+        const double sum = 1.0 - r_elev + r_elev * (1.0 - r_dir);
+        *out = blend(blend(a, b, r_dir), c, r_elev * (1.0 - r_dir) / sum);
+        return true;
+    };
+    auto single = [&](const TracePoint& a, bool cond) {
+        if (!cond) return false;
+        *out = a;
+        return true;
+    };
+    switch (have) {
+        case 0: return false;
+        case 1: return single(*e[0], re < 0.5 && rd < 0.5);
+        case 2: return single(*e[1], re < 0.5 && rd >= 0.5);
+        case 4: return single(*e[2], re >= 0.5 && rd < 0.5);
+        case 8: return single(*e[3], re >= 0.5 && rd >= 0.5);
+        case 1 | 2: return two_adjacent(*e[0], *e[1], re, rd);
+        case 1 | 4: return two_adjacent(*e[0], *e[2], rd, re);
+        case 1 | 8: return two_diagonal(*e[0], *e[3], re, rd);
+        case 2 | 4: return two_diagonal(*e[1], *e[2], re, 1.0 - rd);
+        case 2 | 8: return two_adjacent(*e[1], *e[3], 1.0 - rd, re);
+        case 4 | 8: return two_adjacent(*e[2], *e[3], 1.0 - re, rd);
+        case 1 | 2 | 4: return three(*e[0], *e[1], *e[2], re, rd);
+        case 1 | 2 | 8: return three(*e[1], *e[0], *e[3], re, 1.0 - rd);
+        case 1 | 4 | 8: return three(*e[0], *e[3], *e[2], 1.0 - re, rd);
+        case 2 | 4 | 8: return three(*e[3], *e[2], *e[1], 1.0 - re, 1.0 - rd);
+        default: *out = blend(blend(*e[0], *e[1], rd), blend(*e[2], *e[3], rd), re); return true;
+    }
+}
+
+// interpolate, :394-419 with collect_trace_points, :213-243: a trace point joins the FIRST group that holds a point of its
+// class closer than one simulation step in distance, else it opens a group; a later point of the same grid pixel replaces
+// an earlier one in the group's slot (match_sequence, :245-266).
+std::vector<TracePoint> blend_pixels(const std::vector<TracePoint>* px[4], double re, double rd, double step_size) {
+    struct Member {
+        int slot;
+        const TracePoint* tp;
+    };
+    std::vector<std::vector<Member>> groups;
+    for (int slot = 0; slot < 4; ++slot)
+        for (const TracePoint& tp : *px[slot]) {
+            size_t g = 0;
+            for (; g < groups.size(); ++g) {
+                bool close = false;
+                for (const Member& m : groups[g])
+                    if (std::fabs(tp.distance - m.tp->distance) < step_size && tp.is_terrain == m.tp->is_terrain) {
+                        close = true;
+                        break;
+                    }
+                if (close) break;
+            }
+            if (g == groups.size()) groups.emplace_back();
+            groups[g].push_back({slot, &tp});
+        }
+    std::vector<TracePoint> out;
+    for (const auto& grp : groups) {
+        const TracePoint* e[4] = {nullptr, nullptr, nullptr, nullptr};
+        for (const Member& m : grp) e[m.slot] = m.tp;
+        TracePoint tp;
+        if (blend_group(e, re, rd, &tp)) out.push_back(tp);
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------
 // Colouring: coloring/shading.rs, coloring/simple.rs ; compositing: renderer/mod.rs:367-414
 // ------------------------------------------------------------------------------------------
 struct Rgb8 {
@@ -1335,6 +1471,125 @@ struct oracle_timing {
 // block [x0,x1), optionally on a row/column sub-sample (every `stride_x`-th column and
 // `stride_y`-th row, used for the bounded CPU baseline). Buffers are [rows][cols] of the sampled
 // grid: rows = ceil(H/stride_y), cols = ceil((x1-x0)/stride_x).
+// InterpolatingRectilinearGenerator::generate (interpolating_rectilinear.rs:121-170) + draw_image, for the pixels
+// (x0 + c * stride_x, r * stride_y). The reference fills its three caches lazily; here the grid points the pixels
+// need are listed first and evaluated in parallel. `steps` is 0 for every pixel: a blended pixel has no march of its own.
+static int render_interpolating(const Scene& s, int stride_x, int stride_y, uint8_t* rgb, atmrt_meta* meta, int32_t* steps, int32_t* counts,
+                                atmrt_trace_point* points, int max_points, atmrt_stats* stats, oracle_timing* timing) {
+    const atmrt_params& p = s.p;
+    const int W = p.width, H = p.height, x0 = p.x0, x1 = p.x1;
+    const int cols = (x1 - x0 + stride_x - 1) / stride_x, rows = (H + stride_y - 1) / stride_y;
+    const double t0 = now_s();
+    std::vector<RayParams> table((size_t)W * H);
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) table[(size_t)y * W + x] = get_ray_params(p, x, y);
+    const FovData fov = gen_fov_data(p, table);
+    // FovData::cache_coords, :185-204
+    struct Corner {
+        int elev_index, dir_index;
+        double rem_elev, rem_dir;
+    };
+    std::vector<Corner> corner((size_t)rows * cols);
+    std::vector<int> elev_ids, dir_ids;
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) {
+            const RayParams rp = table[(size_t)(r * stride_y) * W + (x0 + c * stride_x)];
+            const double ef = rp.elevation / fov.min_elev_step, df = rp.direction / fov.min_dir_step;
+            Corner k;
+            k.elev_index = (int)std::floor(ef), k.dir_index = (int)std::floor(df);
+            k.rem_elev = ef - (double)k.elev_index, k.rem_dir = df - (double)k.dir_index;
+            corner[(size_t)r * cols + c] = k;
+            elev_ids.push_back(k.elev_index), elev_ids.push_back(k.elev_index + 1);
+            dir_ids.push_back(k.dir_index), dir_ids.push_back(k.dir_index + 1);
+        }
+    auto unique = [](std::vector<int>& v) {
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+    };
+    unique(elev_ids), unique(dir_ids);
+    auto pos = [](const std::vector<int>& v, int id) { return (size_t)(std::lower_bound(v.begin(), v.end(), id) - v.begin()); };
+    // Cache::get_path_cache / get_terrain_cache, :46-84: index * step, to degrees
+    std::vector<std::vector<PathElem>> paths(elev_ids.size());
+    std::vector<std::vector<TerrainData>> terrains(dir_ids.size());
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t i = 0; i < dir_ids.size(); ++i) terrains[i] = gen_terrain_cache(s, to_degrees((double)dir_ids[i] * fov.min_dir_step));
+    const double t1 = now_s();
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t i = 0; i < elev_ids.size(); ++i) paths[i] = gen_path_cache(s, to_degrees((double)elev_ids[i] * fov.min_elev_step));
+    const double t2 = now_s();
+    // Cache::get_pixel, :86-117: the grid points in use
+    const size_t ne = elev_ids.size(), nd = dir_ids.size();
+    std::vector<char> used(ne * nd, 0);
+    for (const Corner& k : corner)
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j) used[pos(elev_ids, k.elev_index + i) * nd + pos(dir_ids, k.dir_index + j)] = 1;
+    std::vector<std::vector<TracePoint>> grid(ne * nd);
+    uint64_t ray_steps = 0, overflows = 0, path_steps = 0;
+    for (const auto& pc : paths) path_steps += pc.size() - 1;
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : ray_steps, overflows)
+    for (size_t g = 0; g < ne * nd; ++g) {
+        if (!used[g]) continue;
+        ZipSource zip{terrains[g % nd], paths[g / nd]};
+        uint64_t ov = 0;
+        ray_steps += (uint64_t)get_single_pixel(s, zip, &grid[g], &ov);
+        overflows += ov;
+    }
+    uint64_t ntp = 0, nhit = 0;
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : ntp, nhit)
+    for (size_t idx = 0; idx < (size_t)rows * cols; ++idx) {
+        const Corner& k = corner[idx];
+        const std::vector<TracePoint>* px[4];
+        for (int q = 0; q < 4; ++q) px[q] = &grid[pos(elev_ids, k.elev_index + q / 2) * nd + pos(dir_ids, k.dir_index + q % 2)];
+        const std::vector<TracePoint> tps = blend_pixels(px, k.rem_elev, k.rem_dir, p.simulation_step);
+        ntp += tps.size();
+        nhit += tps.empty() ? 0 : 1;
+        if (steps) steps[idx] = 0;
+        if (counts) counts[idx] = (int32_t)tps.size();
+        if (meta) {
+            const double nan = std::numeric_limits<double>::quiet_NaN();
+            if (tps.empty()) meta[idx] = {nan, nan, nan, nan};
+            else meta[idx] = {tps[0].lat, tps[0].lon, tps[0].elevation, tps[0].distance};
+        }
+        if (points && max_points > 0)
+            for (size_t i = 0; i < tps.size() && i < (size_t)max_points; ++i) {
+                const TracePoint& t = tps[i];
+                atmrt_trace_point& o = points[idx * max_points + i];
+                o.lat = t.lat, o.lon = t.lon, o.distance = t.distance, o.elevation = t.elevation, o.path_length = t.path_length;
+                o.normal[0] = t.normal.x, o.normal[1] = t.normal.y, o.normal[2] = t.normal.z;
+                o.color[0] = t.color.r, o.color[1] = t.color.g, o.color[2] = t.color.b, o.color[3] = t.color.a;
+                o.is_terrain = t.is_terrain ? 1 : 0;
+                o.step = t.step;
+            }
+        if (rgb) {
+            const Rgb8 c = draw_pixel(p, tps);
+            rgb[idx * 3 + 0] = c.c[0], rgb[idx * 3 + 1] = c.c[1], rgb[idx * 3 + 2] = c.c[2];
+        }
+    }
+    const double t3 = now_s();
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->ray_steps = ray_steps, stats->trace_points = ntp, stats->pixels_hit = nhit, stats->step_overflows = overflows;
+        stats->n_terrain = terrains.empty() ? 0 : (int)terrains[0].size();
+        stats->terrain_samples = (uint64_t)terrains.size() * (uint64_t)stats->n_terrain;
+        stats->path_steps = path_steps;
+        int mx = 0;
+        for (const auto& pc : paths) mx = std::max(mx, (int)pc.size());
+        stats->n_path_max = mx;
+        stats->ms_terrain = (float)((t1 - t0) * 1e3), stats->ms_paths = (float)((t2 - t1) * 1e3), stats->ms_march = (float)((t3 - t2) * 1e3);
+        stats->ms_total = (float)((t3 - t0) * 1e3);
+    }
+    if (timing) {
+        timing->s_terrain = t1 - t0, timing->s_paths = t2 - t1, timing->s_pixels = t3 - t2, timing->s_image = 0.0, timing->s_total = t3 - t0;
+#ifdef _OPENMP
+        timing->threads = omp_get_max_threads();
+#else
+        timing->threads = 1;
+#endif
+    }
+    return 0;
+}
+
 int oracle_render(const atmrt_params* p, const atmrt_tile_desc* tiles, int ntiles, const int16_t* const* posts,
                   const atmrt_object* objects, int nobjects, const uint8_t* const* textures, int stride_x,
                   int stride_y, uint8_t* rgb, atmrt_meta* meta, int32_t* steps, int32_t* counts,
@@ -1345,6 +1600,8 @@ int oracle_render(const atmrt_params* p, const atmrt_tile_desc* tiles, int ntile
     if (stride_y < 1) stride_y = 1;
     const int x0 = p->x0, x1 = p->x1, H = p->height;
     const int cols = (x1 - x0 + stride_x - 1) / stride_x, rows = (H + stride_y - 1) / stride_y;
+    if (p->generator == ATMRT_GENERATOR_INTERPOLATING_RECTILINEAR)
+        return render_interpolating(s, stride_x, stride_y, rgb, meta, steps, counts, points, max_points, stats, timing);
     const bool rectilinear = p->generator == ATMRT_GENERATOR_RECTILINEAR;
     double t0 = now_s();
     std::vector<std::vector<TerrainData>> terrain_cache(cols);
@@ -1585,12 +1842,36 @@ int oracle_ray_angles(const atmrt_params* p, double* dir /*[W]*/, double* elev /
 // Rectilinear generator (rectilinear.rs:78-116): the pixel's own (elevation, direction).to_degrees(), not wrapped.
 int oracle_pixel_angles(const atmrt_params* p, double* elevation_angle, double* azimuth) {
     const int wl = p->x1 - p->x0;
+    FovData fov{0.0, 0.0};
+    if (p->generator == ATMRT_GENERATOR_INTERPOLATING_RECTILINEAR) {
+        std::vector<RayParams> table((size_t)p->width * p->height);
+        for (int y = 0; y < p->height; ++y)
+            for (int x = 0; x < p->width; ++x) table[(size_t)y * p->width + x] = get_ray_params(*p, x, y);
+        fov = gen_fov_data(*p, table);
+    }
     for (int y = 0; y < p->height; ++y) {
         for (int c = 0; c < wl; ++c) {
             double el, az;
             if (p->generator == ATMRT_GENERATOR_RECTILINEAR) {
                 const RayParams r = get_ray_params(*p, p->x0 + c, y);
                 el = to_degrees(r.elevation), az = to_degrees(r.direction);
+            } else if (p->generator == ATMRT_GENERATOR_INTERPOLATING_RECTILINEAR) {
+                // interpolate(), interpolating_rectilinear.rs:405-417: the four grid points' angles (Cache::get_pixel, :97-107:
+                // azimuth wrapped once) weighted with the remainders
+                const RayParams r = get_ray_params(*p, p->x0 + c, y);
+                const double ef = r.elevation / fov.min_elev_step, df = r.direction / fov.min_dir_step;
+                const int ei = (int)std::floor(ef), di = (int)std::floor(df);
+                const double re = ef - (double)ei, rd = df - (double)di;
+                double e4[4], a4[4];
+                for (int q = 0; q < 4; ++q) {
+                    e4[q] = to_degrees((double)(ei + q / 2) * fov.min_elev_step);
+                    double a = to_degrees((double)(di + q % 2) * fov.min_dir_step);
+                    if (a < 0.0) a += 360.0;
+                    else if (a >= 360.0) a -= 360.0;
+                    a4[q] = a;
+                }
+                el = e4[0] * (1.0 - re) * (1.0 - rd) + e4[1] * (1.0 - re) * rd + e4[2] * re * (1.0 - rd) + e4[3] * re * rd;
+                az = a4[0] * (1.0 - re) * (1.0 - rd) + a4[1] * (1.0 - re) * rd + a4[2] * re * (1.0 - rd) + a4[3] * re * rd;
             } else {
                 el = get_ray_elev(*p, y);
                 az = get_ray_dir(*p, p->x0 + c);

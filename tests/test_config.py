@@ -128,6 +128,8 @@ def test_custom_atmosphere_and_scope_errors(tmp_path):
     c["output"]["generator"] = "Rectilinear"
     assert config.into_params(c).generator == abi.GENERATOR_RECTILINEAR and config.into_params(config.default_config()).generator == abi.GENERATOR_FAST
     c["output"]["generator"] = "InterpolatingRectilinear"
+    assert config.into_params(c).generator == abi.GENERATOR_INTERPOLATING_RECTILINEAR
+    c["output"]["generator"] = "Fisheye"
     with pytest.raises(config.ConfigError):
         config.into_params(c)
     c = config.default_config()

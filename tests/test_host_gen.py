@@ -176,7 +176,7 @@ def test_cpp_cli_overrides_match_the_mirror(tmp_path):
 
 
 def test_cpp_scope_errors(tmp_path):
-    for body in ("earth_shape: Geoid\n", "output: {generator: InterpolatingRectilinear}\n",
+    for body in ("earth_shape: Geoid\n", "output: {generator: Fisheye}\n",
                  "atmosphere:\n  pressure: {altitude: 0, pressure: 101325}\n  first_temperature_function:\n    Spline: {points: [[0, 288]]}\n"):
         f = tmp_path / "bad.yaml"
         f.write_text(body)
