@@ -1204,7 +1204,8 @@ int launch_interpolating(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         grid.max_points = INTERP_MAX_POINTS;
         rc = launch_render(ctx, grid, main);
     }
-    if (!rc) rc = collect_stats(ctx, &ctx->grid_stats);  // (synchronises) ray steps, path steps, terrain samples are the grid's
+    if (!rc && cudaStreamSynchronize(main) != cudaSuccess) rc = fail(ctx, ATMRT_ERR_CUDA, "InterpolatingRectilinear: the grid render failed");
+    if (!rc) rc = collect_stats(ctx, &ctx->grid_stats);  // ray steps, path steps, terrain samples are the grid's
     const int grid_launches = ctx->launches;
     ctx->params = image_params;
     ctx->grid_row_elev = ctx->grid_col_dir = nullptr;

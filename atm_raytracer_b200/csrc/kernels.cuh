@@ -1778,7 +1778,7 @@ __device__ inline bool blend_group(const atmrt_trace_point* const e[4], double r
     return true;
 }
 
-constexpr int INTERP_MAX_POINTS = 8;  // trace points kept per grid pixel (a grid pixel with more is counted in step_overflows)
+constexpr int INTERP_MAX_POINTS = 16;  // trace points kept per grid pixel (a grid pixel with more is counted in step_overflows)
 
 // interpolate (:394-419) + draw_image for one image pixel: group the trace points of the four grid pixels
 // (collect_trace_points, :213-243: a point joins the FIRST group holding a point of its class closer than one simulation
