@@ -1,6 +1,6 @@
 """Turn the CSV of an `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum
---csv` pass into the per-launch table DESIGN.md cites, and profiles/traffic.json (DRAM bytes per launch per kernel)
-that bench.py reports as `roofline.traffic`.  usage: python profiles/launch_list.py launches.csv workload > list.txt"""
+--csv` pass into the per-launch table DESIGN.md cites (bench.py's `roofline.traffic` comes from the --set full capture,
+profiles/ncu_summary.json).  usage: python profiles/launch_list.py launches.csv workload > list.txt"""
 import csv, json, os, re, sys
 
 path, workload = sys.argv[1], sys.argv[2]
@@ -36,20 +36,8 @@ print(f"# {workload} on one B200: every kernel of one render, ncu --metrics gpu_
 print("# --clock-control none (kernels serialised by ncu: compare SHARES of the frame, not absolutes; the live frame overlaps stage A and stage B)")
 print(f"# raw: {path}")
 print(f"{'id':>3} {'kernel':60s} {'ms':>8} {'share':>6} {'Ginst':>8} {'GB read':>8} {'GB written':>10}")
-traffic = {}
 for i in frame:
     e = per[i]
     name = re.sub(r"atmrt::", "", e["name"])
     print(f"{i:3d} {name[:60]:60s} {e.get('ms', 0):8.3f} {100 * e.get('ms', 0) / total:5.1f}% {e.get('inst', 0) / 1e9:8.3f} {e.get('rd', 0) / 1e9:8.2f} {e.get('wr', 0) / 1e9:10.2f}")
-    short = re.sub(r"^void ", "", name).split("<")[0].split("(")[0]
-    t = traffic.setdefault(f"{workload}:{short}", {"dram_bytes": 0, "source": os.path.relpath(path)})
-    t["dram_bytes"] += int(e.get("rd", 0) + e.get("wr", 0))
 print(f"sum of one render: {total:.3f} ms (serialised)")
-tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json")
-old = json.load(open(tj)) if os.path.exists(tj) else {}
-old = {k: v for k, v in old.items() if not k.startswith(workload + ":")}
-old.update(traffic)
-sw = [v["dram_bytes"] for k, v in traffic.items() if k.endswith(":k_sweep") or k.endswith(":k_sweep_shade")]
-if len(sw) == 2:
-    old[f"{workload}:k_sweep+k_sweep_shade"] = {"dram_bytes": sum(sw), "source": os.path.relpath(path)}
-json.dump(old, open(tj, "w"), indent=1)
