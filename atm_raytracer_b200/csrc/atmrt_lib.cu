@@ -2160,6 +2160,26 @@ int atmrt_group_render(atmrt_group* g, uint8_t* rgb, atmrt_meta* meta, int32_t* 
     return 0;
 }
 
+int atmrt_group_render_trace(atmrt_group* g, atmrt_trace_point* points, int32_t* counts, int max_points) {
+    if (!g || !counts || max_points < 0 || (max_points > 0 && !points)) return gfail(g, ATMRT_ERR_INVALID, "group_render_trace: bad argument");
+    if (!g->has_params) return gfail(g, ATMRT_ERR_STATE, "group_render_trace before group_set_params");
+    const int W = g->params.width, H = g->params.height;
+    return group_parallel(g, [&](int i) -> int {
+        int x0 = 0, x1 = 0;
+        atmrt_group_column_block(g, W, i, &x0, &x1);
+        const size_t wl = (size_t)(x1 - x0), P = (size_t)max_points;
+        std::vector<atmrt_trace_point> pts(wl * H * std::max<size_t>(P, 1));
+        std::vector<int32_t> cnt(wl * H);
+        const int rc = atmrt_render_trace(g->ctx[i], max_points > 0 ? pts.data() : nullptr, cnt.data(), max_points);
+        if (rc) return gfail(g, rc, atmrt_last_error(g->ctx[i]));
+        for (int y = 0; y < H; ++y) {  // the block's rows into the image's
+            memcpy(counts + (size_t)y * W + x0, cnt.data() + (size_t)y * wl, wl * sizeof(int32_t));
+            if (P) memcpy(points + ((size_t)y * W + x0) * P, pts.data() + (size_t)y * wl * P, wl * P * sizeof(atmrt_trace_point));
+        }
+        return 0;
+    });
+}
+
 int atmrt_group_pixel_angles(atmrt_group* g, double* elevation_angle, double* azimuth) {
     if (!g) return ATMRT_ERR_INVALID;
     if (!g->has_params) return gfail(g, ATMRT_ERR_STATE, "group_pixel_angles before group_set_params");

@@ -668,19 +668,26 @@ static atmrt_params into_params(const Config& c) {
 }
 
 static bool write_metadata(const std::string& path, const atmrt_params& p, const atmrt_meta* meta, size_t npix, const std::vector<double>& elevation_angle,
-                           const std::vector<double>& azimuth) {
+                           const std::vector<double>& azimuth, const std::vector<int32_t>* counts, const std::vector<atmrt_trace_point>* points,
+                           int max_points) {
     // NOT the reference's file: generator/mod.rs:26-45 writes gzip(bincode(AllData{params, result})), and `params` holds
     // atm_refraction's lowered Atmosphere and Environment, whose serde layout lives in an un-vendored crate (SURVEY section
-    // 8 f2) -- `view` cannot read what is written here. Own documented sidecar, version 2: gzip of
-    //   "ATMRTMETA2\n", i32 width, i32 height, i32 generator (0 Fast, 1 Rectilinear), i32 0,
-    //   ResultPixel.elevation_angle: Fast f64[height] (one per row), Rectilinear f64[height][width]
-    //   ResultPixel.azimuth:         Fast f64[width] (one per column, wrapped into [0, 360)), Rectilinear f64[height][width]
+    // 8 f2) -- `view` cannot read what is written here. Own documented sidecar: gzip of
+    //   "ATMRTMETA2\n" (or "ATMRTMETA3\n" with the trace lists below), i32 width, i32 height, i32 generator (0 Fast,
+    //   1 Rectilinear, 2 InterpolatingRectilinear), i32 0,
+    //   ResultPixel.elevation_angle: Fast f64[height] (one per row), else f64[height][width]
+    //   ResultPixel.azimuth:         Fast f64[width] (one per column, wrapped into [0, 360)), else f64[height][width]
     //   width * height records of 4 little-endian f64: lat, lon, elevation, distance of the FIRST trace point (NaN = none)
+    // version 3 (scenes in which a pixel can hold more than one trace point: translucent terrain, objects), after that:
+    //   i32 max_points, i32 counts[height][width] (true counts), then per pixel min(count, max_points) records of
+    //   atmrt_trace_point (include/atmrt.h: lat, lon, distance, elevation, path_length, normal[3], color[4] as f64,
+    //   i32 is_terrain, i32 step) -- ResultPixel.trace_points (generators/mod.rs:18-30)
     gzFile f = gzopen(path.c_str(), "wb6");
     if (!f) return false;
-    const char magic[] = "ATMRTMETA2\n";
+    const bool lists = counts && points;
+    const char* magic = lists ? "ATMRTMETA3\n" : "ATMRTMETA2\n";
     int32_t hdr[4] = {p.width, p.height, p.generator, 0};
-    bool ok = gzwrite(f, magic, sizeof(magic) - 1) > 0 && gzwrite(f, hdr, sizeof hdr) > 0;
+    bool ok = gzwrite(f, magic, 11) > 0 && gzwrite(f, hdr, sizeof hdr) > 0;
     auto put = [&](const char* data, size_t left) {
         while (ok && left > 0) {
             unsigned chunk = (unsigned)std::min<size_t>(left, 1u << 30);
@@ -691,6 +698,15 @@ static bool write_metadata(const std::string& path, const atmrt_params& p, const
     put((const char*)elevation_angle.data(), elevation_angle.size() * sizeof(double));
     put((const char*)azimuth.data(), azimuth.size() * sizeof(double));
     put((const char*)meta, npix * sizeof(atmrt_meta));
+    if (lists) {
+        const int32_t mp = max_points;
+        put((const char*)&mp, sizeof mp);
+        put((const char*)counts->data(), npix * sizeof(int32_t));
+        for (size_t i = 0; i < npix && ok; ++i) {
+            const size_t n = (size_t)std::min<int32_t>((*counts)[i], max_points);
+            if (n) put((const char*)(points->data() + i * (size_t)max_points), n * sizeof(atmrt_trace_point));
+        }
+    }
     return gzclose(f) == Z_OK && ok;
 }
 
@@ -796,9 +812,22 @@ extern "C" int atmrt_host_gen(int argc, const char* const* argv) {
                 for (int y = 0; y < p.height; ++y) el_rows[(size_t)y] = el[(size_t)y * p.width];
                 el.swap(el_rows), az.swap(az_cols);
             }
-            fprintf(stderr, "note: %s is this host's own sidecar layout (ATMRTMETA2), not the reference's bincode container: `view` cannot read it\n",
-                    c.file_metadata.c_str());
-            if (!write_metadata(c.file_metadata, p, meta, npix, el, az)) throw std::runtime_error("cannot write " + c.file_metadata);
+            // every trace point of every pixel where a pixel can hold more than its first (ResultPixel.trace_points)
+            const bool lists = p.terrain_alpha != 1.0 || !objects.empty();
+            const int max_points = 16;
+            std::vector<int32_t> counts;
+            std::vector<atmrt_trace_point> points;
+            if (lists) {
+                counts.resize(npix), points.resize(npix * (size_t)max_points);
+                check(atmrt_group_render_trace(group, points.data(), counts.data(), max_points), "atmrt_group_render_trace");
+                size_t clipped = 0;
+                for (int32_t n : counts) clipped += n > max_points;
+                if (clipped) fprintf(stderr, "warning: %zu pixels hold more than %d trace points; the sidecar keeps the first %d\n", clipped, max_points, max_points);
+            }
+            fprintf(stderr, "note: %s is this host's own sidecar layout (%s), not the reference's bincode container: `view` cannot read it\n",
+                    c.file_metadata.c_str(), lists ? "ATMRTMETA3" : "ATMRTMETA2");
+            if (!write_metadata(c.file_metadata, p, meta, npix, el, az, lists ? &counts : nullptr, lists ? &points : nullptr, max_points))
+                throw std::runtime_error("cannot write " + c.file_metadata);
         }
         printf("%.3f: Done.\n", t());
         atmrt_host_free(rgb), atmrt_host_free(meta);

@@ -75,6 +75,7 @@ def _load():
         "atmrt_group_set_objects": (C.c_int, [vp, P(abi.Object), C.c_int, P(vp)]),
         "atmrt_group_render": (C.c_int, [vp, vp, vp, vp, P(abi.Stats)]),
         "atmrt_group_pixel_angles": (C.c_int, [vp, vp, vp]),
+        "atmrt_group_render_trace": (C.c_int, [vp, vp, vp, C.c_int]),
         "atmrt_host_alloc": (vp, [C.c_size_t]),
         "atmrt_host_free": (None, [vp]),
     }
@@ -408,6 +409,14 @@ class Group:
         el, az = np.empty((p.height, p.width)), np.empty((p.height, p.width))
         self._check(lib.atmrt_group_pixel_angles(self._h, _ptr(el), _ptr(az)))
         return el, az
+
+    def render_trace(self, max_points=8):
+        """ResultPixel.trace_points of the whole image: (points[H][W][max_points], counts[H][W])."""
+        p = self.params
+        pts = np.zeros((p.height, p.width, max(max_points, 1)), dtype=TRACE_DTYPE)
+        cnt = np.zeros((p.height, p.width), dtype=np.int32)
+        self._check(lib.atmrt_group_render_trace(self._h, _ptr(pts), _ptr(cnt), int(max_points)))
+        return pts, cnt
 
     def render(self, rgb=True, meta=True, steps=True, out=None):
         """The full image (all column blocks) in host memory; ``out`` may carry preallocated arrays (host_array)."""

@@ -344,6 +344,10 @@ int atmrt_group_set_terrain(atmrt_group* g, const atmrt_tile_desc* tiles, int nt
 int atmrt_group_set_params(atmrt_group* g, const atmrt_params* params);
 int atmrt_group_set_objects(atmrt_group* g, const atmrt_object* objects, int nobjects, const uint8_t* const* rgba_textures);
 int atmrt_group_render(atmrt_group* g, uint8_t* rgb, atmrt_meta* meta, int32_t* steps, atmrt_stats* stats);
+/* atmrt_render_trace of every column block, assembled: points[H][W][max_points], counts[H][W] (true counts). Host buffers.
+ * What ResultPixel.trace_points holds in the reference (generators/mod.rs:18-30). */
+int atmrt_group_render_trace(atmrt_group* g, atmrt_trace_point* points, int32_t* counts, int max_points);
+
 /* atmrt_pixel_angles of the whole image: [H][W] each, either may be NULL. */
 int atmrt_group_pixel_angles(atmrt_group* g, double* elevation_angle, double* azimuth);
 /* Page-locked host memory visible to every GPU (the host image / metadata / decoded tiles). */

@@ -213,14 +213,22 @@ def test_gen_executable_end_to_end(tmp_path, ctx):
     img = host.read_png(str(png))[..., :3]
     assert img.shape == (120, 200, 3)
     raw = gzip.decompress(dat.read_bytes())
-    # the host's own sidecar (NOT the reference's bincode container, and it says so): ATMRTMETA2
-    assert raw.startswith(b"ATMRTMETA2\n") and "not the reference's bincode container" in r.stderr
+    # the host's own sidecar (NOT the reference's bincode container, and it says so): translucent terrain -> version 3,
+    # with every trace point of every pixel behind the version-2 content
+    assert raw.startswith(b"ATMRTMETA3\n") and "not the reference's bincode container" in r.stderr
     w, h, generator, _ = np.frombuffer(raw, "<i4", 4, 11)
     assert (w, h, generator) == (200, 120, 0)
     off = 11 + 16
     el = np.frombuffer(raw, "<f8", h, off)         # ResultPixel.elevation_angle, one per row (Fast generator)
     az = np.frombuffer(raw, "<f8", w, off + 8 * h)  # ResultPixel.azimuth, one per column, wrapped into [0, 360)
-    meta = np.frombuffer(raw, runtime.META_DTYPE, offset=off + 8 * (h + w)).reshape(h, w)
+    off += 8 * (h + w)
+    meta = np.frombuffer(raw, runtime.META_DTYPE, h * w, off).reshape(h, w)
+    off += meta.nbytes
+    max_points = int(np.frombuffer(raw, "<i4", 1, off)[0])
+    counts = np.frombuffer(raw, "<i4", h * w, off + 4).reshape(h, w)
+    kept = np.minimum(counts, max_points)
+    lists = np.frombuffer(raw, runtime.TRACE_DTYPE, int(kept.sum()), off + 4 + 4 * h * w)
+    assert max_points == 16 and len(raw) == off + 4 + 4 * h * w + lists.nbytes
     assert el[h // 2] == -2.0 and (np.diff(el) < 0).all() and az[w // 2] == 80.0 and (np.diff(az) > 0).all()
     # the same render through the Python mirror of the host
     cfg = config.read_config(argv)
@@ -231,3 +239,15 @@ def test_gen_executable_end_to_end(tmp_path, ctx):
     for k in ("lat", "lon", "elevation", "distance"):
         np.testing.assert_array_equal(meta[k], want["meta"][k])
     assert np.isfinite(meta["distance"]).mean() > 0.2
+    # ResultPixel.trace_points: the lists of the sidecar are the library's own trace render, pixel by pixel
+    pts, cnt = ctx.render_trace(max_points=16)
+    np.testing.assert_array_equal(counts, cnt)
+    assert counts.max() >= 2  # translucent terrain: rays go on behind the first surface
+    first = np.concatenate([[0], np.cumsum(kept.ravel())[:-1]]).reshape(h, w)
+    hit = counts > 0
+    np.testing.assert_array_equal(lists["distance"][first[hit]], meta["distance"][hit])
+    ys, xs = np.nonzero(counts >= 2)
+    for y, x in list(zip(ys, xs))[:200]:
+        got = lists[first[y, x]:first[y, x] + kept[y, x]]
+        for f in ("lat", "lon", "distance", "elevation", "path_length", "is_terrain", "step"):
+            np.testing.assert_array_equal(got[f], pts[f][y, x, :kept[y, x]])
