@@ -407,7 +407,7 @@ def run_b200(args):
     out = {
         "metric": METRIC, "value": W * H / (ms * 1e-3), "unit": "pixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": describe(args.workload, params, terrain, {"parallelism": f"column blocks x{world}", "march_mode": {0: "horizon sweep (opaque terrain, no objects) / hierarchical march", 1: "brute force", 2: "hierarchical march"}[args.march_mode]}),
+        "config": describe(args.workload, params, terrain, {"parallelism": f"column blocks x{world}", "march_mode": {0: "horizon sweep (opaque terrain, no objects) / crossing march (translucent terrain, objects)", 1: "brute force", 2: "hierarchical march"}[args.march_mode]}),
         "ray_steps_per_s": st["ray_steps"] / (ms * 1e-3),
         "ray_steps_per_step": st["ray_steps"],
         "stage_ms": {"terrain_profile": ms_a, "ray_paths": ms_b, "march": ms_c, "note": "terrain and paths overlap on two streams; max over ranks"},
@@ -490,6 +490,14 @@ def kernel_roofline(kernel, ms, fp, args, world):
     except Exception:
         table = {}
     e = table.get(f"{args.workload}:{kernel}")
+    if e is None and kernel == "k_march":
+        # translucent terrain / objects: the march bracket holds the crossing march (k_thresholds + k_cross_march)
+        parts = [table.get(f"{args.workload}:{k}") for k in ("k_cross_march", "k_thresholds")]
+        if all(parts) and len({q.get("source_sha") for q in parts}) == 1:
+            e = dict(parts[0])
+            for f in ("fp64_warp_instructions", "warp_instructions", "dram_read_bytes", "dram_write_bytes", "gpu_time_ms"):
+                e[f] = sum(q[f] for q in parts)
+            out["kernel"] = "k_thresholds + k_cross_march"
     sha = _source_sha()
     if e is None or args.scale != 1.0 or world != 1 or args.emulate_ranks > 1 or args.generator != "Fast":
         out["note"] = "no ncu capture of this kernel for this workload / shard under profiles/"
