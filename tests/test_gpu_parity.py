@@ -406,6 +406,62 @@ def test_sweep_falls_back_when_rays_cross(ctx, oracle_lib):
     compare_render(got, oracle_lib.render(q, terrain.tiles), "underground")
 
 
+def _three_modes(ctx):
+    out = []
+    for mode in (0, 1, 2):
+        ctx.set_march_mode(mode)
+        out.append(ctx.render())
+    ctx.set_march_mode(0)
+    _same_render(out[0], out[1])
+    _same_render(out[0], out[2])
+    return out[0]
+
+
+def test_crossing_march_edge_cases(ctx, oracle_lib):
+    """The crossing march (translucent terrain / objects) where its premises fail or its caches run out: rays that cross
+    (the duct: k_path_check sends the render to the hierarchical march), an observer inside the terrain (rays start below
+    the surface: exits are events too), translucent terrain without objects, and an object so wide that a column holds
+    more close samples than the cache of sines and cosines keeps (the rest is evaluated in place). Every case: the three
+    march modes bit for bit, and the oracle."""
+    # 1. the duct of test_sweep_falls_back_when_rays_cross, translucent
+    p, terrain, _, _ = scene("c2", 0.1)
+    a = p.atmosphere
+    a.n_functions = 3
+    a.fn_gradient[0], a.fn_start_altitude[1], a.fn_gradient[1] = -0.0065, 1850.0, 0.5
+    a.fn_start_altitude[2], a.fn_gradient[2] = 1890.0, -0.0065
+    p.tilt, p.fov, p.terrain_alpha = 0.0, 4.0, 0.5
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects([])
+    compare_render(_three_modes(ctx), oracle_lib.render(p, terrain.tiles), "cross-duct", finish_moves_frac=0.01)
+    # 2. observer inside the terrain, translucent
+    q, terrain, _, _ = scene("c2", 0.05)
+    q.altitude.kind, q.altitude.value, q.terrain_alpha = abi.ALT_ABSOLUTE, 200.0, 0.4
+    ctx.set_params(q)
+    got = _three_modes(ctx)
+    compare_render(got, oracle_lib.render(q, terrain.tiles), "cross-underground", finish_moves_frac=0.01)
+    assert got["stats"]["trace_points"] > got["stats"]["pixels_hit"]  # rays go on behind the first surface
+    # 3. translucent terrain, no objects, flat earth
+    r, terrain3, _, _ = scene("c3_flat", 0.05)
+    r.terrain_alpha = 0.3
+    ctx.set_terrain(terrain3)
+    ctx.set_params(r)
+    compare_render(_three_modes(ctx), oracle_lib.render(r, terrain3.tiles), "cross-flat", finish_moves_frac=0.01)
+    # 4. an object close to more samples of a column than the cache holds (1024): a frustum 40 km wide, opaque terrain
+    w, terrain, objects, textures = scene("c4", 0.06)
+    w.terrain_alpha = 1.0
+    big = abi.Object.from_buffer_copy(objects[2])
+    big.kind, big.r1, big.r2, big.height = abi.OBJECT_FRUSTUM, 40000.0, 39000.0, 300.0
+    big.color[3] = 0.5
+    ctx.set_terrain(terrain)
+    ctx.set_params(w)
+    ctx.set_objects([big], [None])
+    got = _three_modes(ctx)
+    prof = ctx.terrain_profile(w.width // 2)
+    assert (prof["close"] != 0).sum() > 1024
+    compare_render(got, oracle_lib.render(w, terrain.tiles, [big], [None]), "cross-wide-object", finish_moves_frac=0.01)
+
+
 def test_trace_point_lists_translucent_scene(ctx, oracle_lib):
     """c4: translucent terrain + objects -> variable-length ResultPixel.trace_points."""
     p, terrain, objects, textures = scene("c4", 0.08)
