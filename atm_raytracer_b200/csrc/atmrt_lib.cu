@@ -97,6 +97,11 @@ struct atmrt_ctx {
     int sweep_bands = 0;                // 0: chosen per render (launch_render)
     DevBuf d_stage;  // raw posts of pack_terrain on their way to the tiled layout
     bool sweep_enabled = true;
+    // the terrain on its way (atmrt_group_render_tiles): uploaded, retiled and gathered on s_t / s_r; whoever reads the terrain
+    // waits for ev_terrain
+    cudaStream_t s_t = nullptr, s_r = nullptr;
+    cudaEvent_t ev_terrain = nullptr, ev_tile = nullptr;
+    bool terrain_in_flight = false;
     // InterpolatingRectilinear generator: the grid's angle tables (device) while its Fast render is prepared, its trace lists,
     // the statistics of that render
     const double* grid_row_elev = nullptr;
@@ -915,6 +920,15 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
     int rc = upload_scene_inputs(ctx, main);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 8 * CNT_COUNT, main));
+    // A terrain that is still on its way (atmrt_group_render_tiles): the scene preparation reads it only for Relative altitudes
+    // (Altitude::abs, params.rs:23-30) and the ray paths not at all -- they are integrated while the tiles arrive. The
+    // Rectilinear generator's one kernel reads it from the start.
+    bool early_terrain = false;
+    if (ctx->terrain_in_flight) {
+        early_terrain = S.altitude.kind == ATMRT_ALT_RELATIVE || S.generator == ATMRT_GENERATOR_RECTILINEAR;
+        for (const atmrt_object& o : ctx->objects) early_terrain = early_terrain || o.altitude.kind == ATMRT_ALT_RELATIVE;
+        if (early_terrain) CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_terrain, 0));
+    }
     k_prepare_scene<<<(S.nobjects + 1 + 63) / 64, 64, 0, main>>>(S, ctx->terrain, B, (const atmrt_object*)ctx->d_objects_in.p);
     ctx->launches++;
 
@@ -993,6 +1007,7 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->s_b));
 
     // Stage A on s_a
+    if (ctx->terrain_in_flight && !early_terrain) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_a, ctx->ev_terrain, 0));
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->a0, ctx->s_a));
     k_column_setup<<<(wl + 127) / 128, 128, 0, ctx->s_a>>>(S, B);
     if (S.n_anchor > 0) {
@@ -1345,7 +1360,8 @@ int atmrt_create(int device, atmrt_ctx** out) {
     bool ok = cudaStreamCreateWithPriority(&ctx->s_a, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
               cudaStreamCreateWithPriority(&ctx->s_b, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking) == cudaSuccess;
-    cudaEvent_t* evs[] = {&ctx->ev_prep, &ctx->ev_a, &ctx->ev_b};
+    ok = ok && cudaStreamCreateWithFlags(&ctx->s_t, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->s_r, cudaStreamNonBlocking) == cudaSuccess;
+    cudaEvent_t* evs[] = {&ctx->ev_prep, &ctx->ev_a, &ctx->ev_b, &ctx->ev_terrain, &ctx->ev_tile};
     for (cudaEvent_t* ev : evs) ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
     for (cudaEvent_t& ev : ctx->ev_band) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
     cudaEvent_t* tevs[] = {&ctx->t_0, &ctx->t_1};
@@ -1387,6 +1403,10 @@ void atmrt_destroy(atmrt_ctx* ctx) {
     if (ctx->s_a) cudaStreamDestroy(ctx->s_a);
     if (ctx->s_b) cudaStreamDestroy(ctx->s_b);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
+    if (ctx->s_t) cudaStreamDestroy(ctx->s_t);
+    if (ctx->s_r) cudaStreamDestroy(ctx->s_r);
+    if (ctx->ev_terrain) cudaEventDestroy(ctx->ev_terrain);
+    if (ctx->ev_tile) cudaEventDestroy(ctx->ev_tile);
     delete ctx;
 }
 
@@ -2055,8 +2075,10 @@ int atmrt_group_column_block(const atmrt_group* g, int width, int i, int* x0, in
     return 0;
 }
 
-int atmrt_group_set_terrain(atmrt_group* g, const atmrt_tile_desc* tiles, int ntiles, const int16_t* const* posts) {
-    if (!g || ntiles < 0 || (ntiles > 0 && (!tiles || !posts))) return gfail(g, ATMRT_ERR_INVALID, "group_set_terrain: bad argument");
+// The terrain of a group: every GPU uploads a contiguous slice of the tiles over its own link (s_t), retiles every tile as it
+// lands (s_r, behind the tile's copy: the next tile's copy runs meanwhile) and then pulls the other slices from its peers.
+// `wait`: return when the terrain is in place on every GPU; otherwise ev_terrain of every context says when.
+static int group_upload_terrain(atmrt_group* g, const atmrt_tile_desc* tiles, int ntiles, const int16_t* const* posts, bool wait) {
     const int n = (int)g->ctx.size();
     TerrainLayout L;
     int rc = make_layout(g->ctx[0], tiles, ntiles, &L);
@@ -2073,7 +2095,7 @@ int atmrt_group_set_terrain(atmrt_group* g, const atmrt_tile_desc* tiles, int nt
             CUDA_TRY(ctx, cudaMalloc(&g->packed[i], L.total));
         }
         char* base = (char*)g->packed[i];
-        cudaStream_t s = ctx->s_main;
+        cudaStream_t s = ctx->s_t, r = ctx->s_r;
         const int t0 = first_tile(i), t1 = first_tile(i + 1);
         if (ntiles > 0) CUDA_TRY(ctx, cudaMemcpyAsync(base + L.off_tiles, L.tiles.data(), sizeof(DevTile) * ntiles, cudaMemcpyHostToDevice, s));
         if (!L.lookup.empty()) CUDA_TRY(ctx, cudaMemcpyAsync(base + L.off_lookup, L.lookup.data(), sizeof(int) * L.lookup.size(), cudaMemcpyHostToDevice, s));
@@ -2082,34 +2104,43 @@ int atmrt_group_set_terrain(atmrt_group* g, const atmrt_tile_desc* tiles, int nt
         int e = ensure(ctx, ctx->d_stage, std::max<size_t>(offs[t1 - t0], 256));
         if (e) return e;
         if (t1 > t0) CUDA_TRY(ctx, cudaMemsetAsync(base + post_byte(t0), 0, post_byte(t1) - post_byte(t0), s));  // the padding of the edge micro-tiles
-        for (int t = t0; t < t1; ++t)
-            CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->d_stage.p + offs[t - t0], posts[t], sizeof(int16_t) * (size_t)tiles[t].nlon * tiles[t].nlat, cudaMemcpyHostToDevice, s));
         for (int t = t0; t < t1; ++t) {
             const size_t np = (size_t)tiles[t].nlon * tiles[t].nlat;
-            k_retile<<<(unsigned)((np + 255) / 256), 256, 0, s>>>((const int16_t*)((const char*)ctx->d_stage.p + offs[t - t0]), (int16_t*)(base + L.off_posts), L.tiles[t]);
+            CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->d_stage.p + offs[t - t0], posts[t], sizeof(int16_t) * np, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tile, s));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(r, ctx->ev_tile, 0));  // (the wait captures this record: the event is reused tile after tile)
+            k_retile<<<(unsigned)((np + 255) / 256), 256, 0, r>>>((const int16_t*)((const char*)ctx->d_stage.p + offs[t - t0]), (int16_t*)(base + L.off_posts), L.tiles[t]);
         }
         CUDA_TRY(ctx, cudaGetLastError());
-        CUDA_TRY(ctx, cudaEventRecord(g->ev_slice[i], s));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tile, s));  // the descriptors and the lookup table too, when the slice is empty
+        CUDA_TRY(ctx, cudaStreamWaitEvent(r, ctx->ev_tile, 0));
+        CUDA_TRY(ctx, cudaEventRecord(g->ev_slice[i], r));
         return 0;
     });
     if (rc) return rc;
     g->packed_cap = std::max(g->packed_cap, L.total);
     // all-gather of the slices over the peer links: every GPU pulls the slices it does not own
-    rc = group_parallel(g, [&](int i) -> int {
+    return group_parallel(g, [&](int i) -> int {
         atmrt_ctx* ctx = g->ctx[i];
         CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-        cudaStream_t s = ctx->s_main;
+        cudaStream_t r = ctx->s_r;
         for (int k = 1; k < n; ++k) {
             const int o = (i + k) % n;  // staggered: no two GPUs start on the same peer
             const size_t b0 = post_byte(first_tile(o)), b1 = post_byte(first_tile(o + 1));
             if (b1 <= b0) continue;
-            CUDA_TRY(ctx, cudaStreamWaitEvent(s, g->ev_slice[o], 0));
-            CUDA_TRY(ctx, cudaMemcpyPeerAsync((char*)g->packed[i] + b0, ctx->device, (const char*)g->packed[o] + b0, g->ctx[o]->device, b1 - b0, s));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(r, g->ev_slice[o], 0));
+            CUDA_TRY(ctx, cudaMemcpyPeerAsync((char*)g->packed[i] + b0, ctx->device, (const char*)g->packed[o] + b0, g->ctx[o]->device, b1 - b0, r));
         }
-        CUDA_TRY(ctx, cudaStreamSynchronize(s));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_terrain, r));
+        if (wait) CUDA_TRY(ctx, cudaStreamSynchronize(r));
+        ctx->terrain_in_flight = !wait;
         return atmrt_bind_terrain(ctx, tiles, ntiles, g->packed[i]);
     });
-    return rc;
+}
+
+int atmrt_group_set_terrain(atmrt_group* g, const atmrt_tile_desc* tiles, int ntiles, const int16_t* const* posts) {
+    if (!g || ntiles < 0 || (ntiles > 0 && (!tiles || !posts))) return gfail(g, ATMRT_ERR_INVALID, "group_set_terrain: bad argument");
+    return group_upload_terrain(g, tiles, ntiles, posts, true);
 }
 
 int atmrt_group_set_params(atmrt_group* g, const atmrt_params* params) {
@@ -2158,6 +2189,22 @@ int atmrt_group_render(atmrt_group* g, uint8_t* rgb, atmrt_meta* meta, int32_t* 
         }
     }
     return 0;
+}
+
+int atmrt_group_render_tiles(atmrt_group* g, const atmrt_tile_desc* tiles, int ntiles, const int16_t* const* posts, uint8_t* rgb, atmrt_meta* meta,
+                             int32_t* steps, atmrt_stats* stats) {
+    if (!g || ntiles < 0 || (ntiles > 0 && (!tiles || !posts))) return gfail(g, ATMRT_ERR_INVALID, "group_render_tiles: bad argument");
+    if (!g->has_params) return gfail(g, ATMRT_ERR_STATE, "group_render_tiles before group_set_params");
+    int rc = group_upload_terrain(g, tiles, ntiles, posts, false);
+    if (!rc) rc = atmrt_group_render(g, rgb, meta, steps, stats);  // (returns when the image is in host memory: the tiles have landed)
+    for (atmrt_ctx* ctx : g->ctx) {
+        if (rc && ctx->terrain_in_flight) {  // a failed render may not have waited for the copies
+            cudaSetDevice(ctx->device);
+            cudaStreamSynchronize(ctx->s_r);
+        }
+        ctx->terrain_in_flight = false;
+    }
+    return rc;
 }
 
 int atmrt_group_render_trace(atmrt_group* g, atmrt_trace_point* points, int32_t* counts, int max_points) {

@@ -788,7 +788,6 @@ extern "C" int atmrt_host_gen(int argc, const char* const* argv) {
             if (rc != 0) throw std::runtime_error(std::string(what) + ": " + atmrt_group_last_error(group));
         };
         check(atmrt_group_create(nullptr, c.gpus, &group), "atmrt_group_create");
-        check(atmrt_group_set_terrain(group, terrain.descs.data(), (int)terrain.descs.size(), terrain.ptrs().data()), "atmrt_group_set_terrain");
         check(atmrt_group_set_params(group, &p), "atmrt_group_set_params");
         check(atmrt_group_set_objects(group, objects.data(), (int)objects.size(), tex_ptrs.data()), "atmrt_group_set_objects");
         printf("%.3f: Generating terrain cache...\n%.3f: Generating path cache...\n%.3f: Calculating pixels...\n", t(), t(), t());
@@ -797,7 +796,9 @@ extern "C" int atmrt_host_gen(int argc, const char* const* argv) {
         if (!c.file_metadata.empty()) meta = (atmrt_meta*)atmrt_host_alloc(npix * sizeof(atmrt_meta));
         if (!rgb || (!c.file_metadata.empty() && !meta)) throw std::runtime_error("cannot allocate page-locked memory for the image");
         atmrt_stats st{};
-        check(atmrt_group_render(group, rgb, meta, nullptr, &st), "atmrt_group_render");
+        // the tiles go up, the image comes back: one call (the ray paths are integrated while the tiles are on their way)
+        check(atmrt_group_render_tiles(group, terrain.descs.data(), (int)terrain.descs.size(), terrain.ptrs().data(), rgb, meta, nullptr, &st),
+              "atmrt_group_render_tiles");
         printf("%.3f: Done calculating (terrain %.2f ms, paths %.2f ms, march %.2f ms on the GPU; %llu ray steps, %llu pixels hit)\n", t(),
                st.ms_terrain, st.ms_paths, st.ms_march, (unsigned long long)st.ray_steps, (unsigned long long)st.pixels_hit);
         printf("%.3f: Outputting image...\n", t());

@@ -76,6 +76,7 @@ def _load():
         "atmrt_group_render": (C.c_int, [vp, vp, vp, vp, P(abi.Stats)]),
         "atmrt_group_pixel_angles": (C.c_int, [vp, vp, vp]),
         "atmrt_group_render_trace": (C.c_int, [vp, vp, vp, C.c_int]),
+        "atmrt_group_render_tiles": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, vp]),
         "atmrt_host_alloc": (vp, [C.c_size_t]),
         "atmrt_host_free": (None, [vp]),
     }
@@ -418,8 +419,10 @@ class Group:
         self._check(lib.atmrt_group_render_trace(self._h, _ptr(pts), _ptr(cnt), int(max_points)))
         return pts, cnt
 
-    def render(self, rgb=True, meta=True, steps=True, out=None):
-        """The full image (all column blocks) in host memory; ``out`` may carry preallocated arrays (host_array)."""
+    def render(self, rgb=True, meta=True, steps=True, out=None, terrain=None):
+        """The full image (all column blocks) in host memory; ``out`` may carry preallocated arrays (host_array). With
+        ``terrain``: upload it and render in one call (atmrt_group_render_tiles: the ray paths are integrated while the tiles
+        are on their way)."""
         p = self.params
         h, w = p.height, p.width
         out = out or {}
@@ -433,7 +436,11 @@ class Group:
         if steps and a_steps is None:
             a_steps = host_array((h, w), np.int32)
         st = abi.Stats()
-        self._check(lib.atmrt_group_render(self._h, _ptr(a_rgb), _ptr(a_meta), _ptr(a_steps), C.byref(st)))
+        if terrain is not None:
+            descs, ptrs, n = terrain.c_arrays()
+            self._check(lib.atmrt_group_render_tiles(self._h, descs, n, ptrs, _ptr(a_rgb), _ptr(a_meta), _ptr(a_steps), C.byref(st)))
+        else:
+            self._check(lib.atmrt_group_render(self._h, _ptr(a_rgb), _ptr(a_meta), _ptr(a_steps), C.byref(st)))
         return {"rgb": a_rgb, "meta": a_meta, "steps": a_steps, "stats": st.as_dict()}
 
 

@@ -346,8 +346,8 @@ def run_b200(args):
                 e2e_steps = max(1, min(args.steps, 3))
 
                 def one():
-                    group.set_terrain(terrain_pinned)  # H2D of the decoded tiles (sliced) + retile + all-gather
-                    group.render(rgb=True, meta=with_meta, steps=False, out=host)
+                    # H2D of the decoded tiles (sliced) + retile + all-gather, the render and the image's way back: one call
+                    group.render(rgb=True, meta=with_meta, steps=False, out=host, terrain=terrain_pinned)
 
                 one()
                 t0 = time.perf_counter()
@@ -356,7 +356,7 @@ def run_b200(args):
                 dt = (time.perf_counter() - t0) / e2e_steps
                 return {"value": W * H / dt, "unit": "pixels/s", "h2d_bytes_per_step": int(terrain.bytes),
                         "d2h_bytes_per_step": int(W * H * 3 + (W * H * 32 if with_meta else 0)), "ms_per_step": dt * 1e3, "steps": e2e_steps,
-                        "api": f"atmrt_group_set_terrain + atmrt_group_render on {world} GPU(s) from one process (the path of `atm-raytracer gen --gpus {world}`): "
+                        "api": f"atmrt_group_render_tiles on {world} GPU(s) from one process (the path of `atm-raytracer gen --gpus {world}`): "
                                "decoded tiles in page-locked host memory in, rgb" + (" and per-pixel metadata" if with_meta else "") + " in page-locked host memory out"}
 
             wants_meta = bool(cfg["output"].get("file_metadata"))

@@ -344,6 +344,12 @@ int atmrt_group_set_terrain(atmrt_group* g, const atmrt_tile_desc* tiles, int nt
 int atmrt_group_set_params(atmrt_group* g, const atmrt_params* params);
 int atmrt_group_set_objects(atmrt_group* g, const atmrt_object* objects, int nobjects, const uint8_t* const* rgba_textures);
 int atmrt_group_render(atmrt_group* g, uint8_t* rgb, atmrt_meta* meta, int32_t* steps, atmrt_stats* stats);
+/* What `gen` does between the decoded tiles and the image, as one call: atmrt_group_set_terrain + atmrt_group_render. The ray
+ * paths do not read the terrain (nor does the scene preparation when every altitude is Absolute), so they are integrated
+ * while the tiles are still on their way. Returns when the image is in host memory; the posts may be released then. */
+int atmrt_group_render_tiles(atmrt_group* g, const atmrt_tile_desc* tiles, int ntiles, const int16_t* const* posts, uint8_t* rgb, atmrt_meta* meta,
+                             int32_t* steps, atmrt_stats* stats);
+
 /* atmrt_render_trace of every column block, assembled: points[H][W][max_points], counts[H][W] (true counts). Host buffers.
  * What ResultPixel.trace_points holds in the reference (generators/mod.rs:18-30). */
 int atmrt_group_render_trace(atmrt_group* g, atmrt_trace_point* points, int32_t* counts, int max_points);

@@ -573,6 +573,43 @@ def test_group_of_contexts_equals_single_render(ctx, name, scale, n):
     np.testing.assert_array_equal(third["rgb"], want["rgb"])
 
 
+@pytest.mark.parametrize("name,scale,n,relative,generator", [("c2", 0.25, 2, False, 0), ("c4", 0.1, 3, False, 0), ("c2", 0.1, 2, True, 0),
+                                                             ("c2", 0.05, 1, False, 1), ("c2", 0.08, 2, False, 2)])
+def test_group_render_tiles_equals_set_terrain_then_render(ctx, name, scale, n, relative, generator):
+    """atmrt_group_render_tiles -- the tiles go up and the image comes back in one call, the ray paths integrated while the
+    tiles are on their way -- against set_terrain followed by render: byte for byte, with Absolute altitudes (the overlap),
+    a Relative observer (the scene preparation waits for the terrain), and the two generators that are not the Fast one. A
+    second frame over different tiles must not see the first frame's."""
+    p, terrain, objects, textures = scene(name, scale)
+    p.generator = generator
+    if generator:
+        p.fov = 12.0
+    if relative:
+        p.altitude.kind, p.altitude.value = abi.ALT_RELATIVE, 30.0
+    other = runtime.Terrain([(d, np.ascontiguousarray(posts[::-1, ::-1])) for d, posts in terrain.tiles])
+    g = runtime.Group(n, devices=[0] * n)
+    try:
+        g.set_params(p)
+        g.set_objects(objects, textures)
+        g.set_terrain(terrain)
+        want = g.render()
+        got = g.render(terrain=terrain)
+        g.set_terrain(other)
+        want2 = g.render(steps=False)
+        got2 = g.render(steps=False, terrain=other)
+        back = g.render(terrain=terrain)
+    finally:
+        g.close()
+    for a, b in ((got, want), (back, want)):
+        np.testing.assert_array_equal(a["rgb"], b["rgb"])
+        np.testing.assert_array_equal(a["steps"], b["steps"])
+        for f in ("lat", "lon", "elevation", "distance"):
+            np.testing.assert_array_equal(a["meta"][f], b["meta"][f])
+    np.testing.assert_array_equal(got2["rgb"], want2["rgb"])
+    np.testing.assert_array_equal(got2["meta"]["distance"], want2["meta"]["distance"])
+    assert (want2["rgb"] != want["rgb"]).any()
+
+
 def test_fog_simple_colouring_and_relative_altitude(ctx, oracle_lib):
     p, terrain, objects, textures = scene("c2", 0.1)
     p.coloring = abi.COLORING_SIMPLE
