@@ -66,6 +66,23 @@ def make_scene(name, scale=1.0):
         c["output"]["generator"] = "Rectilinear"
         c["view"]["frame"]["tilt"] = -1.5
         return c, grid
+    if name.startswith("interp_"):  # ... and through the InterpolatingRectilinear generator
+        c, grid = make_scene(name[7:], scale)
+        c["output"]["generator"] = "InterpolatingRectilinear"
+        c["view"]["frame"]["tilt"] = -1.5
+        return c, grid
+    if name.startswith("spline_"):  # a surface inversion as a Spline temperature function between two Linear ones (README.md:296-316)
+        c, grid = make_scene(name[7:], scale)
+        c["atmosphere"] = {
+            "pressure": {"altitude": 0.0, "pressure": 101325.0},
+            "first_temperature_function": {"Linear": {"gradient": -0.0065}},
+            "next_functions": [
+                {"altitude": 1700.0, "function": {"Spline": {"boundary_condition": {"Derivatives": [-0.0065, -0.0065]},
+                                                            "points": [[1700.0, 277.0], [1760.0, 280.5], [1840.0, 282.0], [2000.0, 280.0], [2500.0, 276.5]]}}},
+                {"altitude": 2500.0, "function": {"Linear": {"gradient": -0.0065}}},
+            ],
+        }
+        return c, grid
     c = _base()
     out, view = c["output"], c["view"]
 

@@ -1,7 +1,7 @@
 # round 2, call X (2 GPUs): torchrun bench at N = 2 with the host-side standby barrier, the reference arm under torchrun, group == context on two real GPUs
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r2x_n2.json 2> gpurun_out/r2x_n2.err; echo "n2 rc $?"
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/r2x_ref2.json 2> gpurun_out/r2x_ref2.err; echo "ref2 rc $?"
-python - > gpurun_out/r2x_group2.log 2>&1 <<'PY'
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r3i_n2.json 2> gpurun_out/r3i_n2.err; echo "n2 rc $?"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/r3i_ref2.json 2> gpurun_out/r3i_ref2.err; echo "ref2 rc $?"
+python - > gpurun_out/r3i_group2.log 2>&1 <<'PY'
 import numpy as np, time
 from atm_raytracer_b200 import runtime, config, scenes
 for name, scale, gen in (("c4", 0.2, None), ("c5", 0.25, None), ("c2", 0.1, "InterpolatingRectilinear")):
@@ -15,4 +15,4 @@ for name, scale, gen in (("c4", 0.2, None), ("c5", 0.25, None), ("c2", 0.1, "Int
     same = all(np.array_equal(got[k], want[k]) for k in ("rgb", "steps")) and all(np.array_equal(got["meta"][f], want["meta"][f], equal_nan=True) for f in ("lat", "lon", "elevation", "distance"))
     print(name, scale, gen or "Fast", p.width, p.height, "2-GPU group == 1-GPU context:", same, "frame+terrain %.2f ms" % (dt * 1e3))
 PY
-cat gpurun_out/r2x_group2.log; tail -2 gpurun_out/r2x_n2.err
+cat gpurun_out/r3i_group2.log; tail -2 gpurun_out/r3i_n2.err

@@ -20,7 +20,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 CASES = {"c1": 0.075, "c2": 0.025, "c3_flat": 0.0125, "c3_sph": 0.0125, "c4": 0.025,
          # the other earth models and the Rectilinear generator
-         "c3_wgs84": 0.0125, "c3_azeq": 0.0125, "c4_obsae": 0.02, "rect_c2": 0.02, "rect_c4": 0.02}
+         "c3_wgs84": 0.0125, "c3_azeq": 0.0125, "c4_obsae": 0.02, "rect_c2": 0.02, "rect_c4": 0.02,
+         # f4 and the Spline temperature functions
+         "interp_c2": 0.025, "interp_c4": 0.025, "spline_c2": 0.025}
 
 
 def tiles_digest(terrain):
@@ -42,8 +44,13 @@ def main():
         r = oracle.render(p, terrain.tiles, objects, textures, max_points=12)
         cols = [0, p.width // 2, p.width - 1]
         rows = [0, p.height // 2, p.height - 1]
-        tc = [oracle.terrain_cache(p, terrain.tiles, x, objects) for x in cols]
-        pc = [oracle.path_cache(p, terrain.tiles, y) for y in rows]
+        if p.generator != 0:  # no image-aligned caches: the probes below describe the Fast generator's
+            q = type(p).from_buffer_copy(p)
+            q.generator = 0
+        else:
+            q = p
+        tc = [oracle.terrain_cache(q, terrain.tiles, x, objects) for x in cols]
+        pc = [oracle.path_cache(q, terrain.tiles, y) for y in rows]
         n = min(len(c["dist"]) for c in pc)
         np.savez_compressed(
             os.path.join(HERE, f"{name}.npz"),

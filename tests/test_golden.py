@@ -10,7 +10,7 @@ import pytest
 from conftest import scene
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CASES = ["c1", "c2", "c3_flat", "c3_sph", "c4", "c3_wgs84", "c3_azeq", "c4_obsae", "rect_c2", "rect_c4"]
+CASES = ["c1", "c2", "c3_flat", "c3_sph", "c4", "c3_wgs84", "c3_azeq", "c4_obsae", "rect_c2", "rect_c4", "interp_c2", "interp_c4", "spline_c2"]
 
 
 def load(name):
@@ -59,7 +59,7 @@ def test_cuda_matches_golden(ctx, name):
     got = ctx.render()
     want = {"rgb": g["rgb"], "meta": g["meta"], "steps": g["steps"]}
     compare_render(got, want, f"golden-{name}", finish_moves_frac=0.01 if objects else 0.001)
-    if name.startswith("rect_"):  # the Rectilinear generator keeps no caches to probe
+    if name.startswith(("rect_", "interp_")):  # these generators keep no image-aligned caches to probe
         return
     for i, x in enumerate(g["cols"]):
         t = ctx.terrain_profile(int(x))
