@@ -100,6 +100,9 @@ struct atmrt_ctx {
     // the terrain on its way (atmrt_group_render_tiles): uploaded, retiled and gathered on s_t / s_r; whoever reads the terrain
     // waits for ev_terrain
     cudaStream_t s_t = nullptr, s_r = nullptr;
+    // a frame split below the horizon (launch_render): the lower rows' rays on s_b2, the lower band's sweep on s_c
+    cudaStream_t s_b2 = nullptr, s_c = nullptr;
+    cudaEvent_t ev_b1 = nullptr, ev_s1 = nullptr;
     cudaEvent_t ev_terrain = nullptr, ev_tile = nullptr;
     bool terrain_in_flight = false;
     // InterpolatingRectilinear generator: the grid's angle tables (device) while its Fast render is prepared, its trace lists,
@@ -861,17 +864,19 @@ int copy_rows_to_host(atmrt_ctx* ctx, const RenderTargets& rt, int wl, int r0, i
 // The ray-path stage with macro steps: as many simulation steps per macro step as keep it within
 // MACRO_MAX_METRES (16 at 25 or 50 m; fewer for coarser simulation steps, none above 400 m).
 template <bool FLAT>
-int launch_macro_paths(atmrt_ctx* ctx, const DevScene& S, const DevBuffers& B, int h, atmrt_ctx::StageEvents* E) {
-    const int warps = MACRO_THREADS / 32;
-    auto blocks = [&](int m) { return (h + warps * (32 / m) - 1) / (warps * (32 / m)); };
-    CUDA_TRY(ctx, cudaEventRecord(E->k0[ATMRT_KERNEL_RAY_PATHS], ctx->s_b));
-    if (16.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 16><<<blocks(16), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
-    else if (8.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 8><<<blocks(8), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
-    else if (4.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 4><<<blocks(4), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
-    else if (2.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 2><<<blocks(2), MACRO_THREADS, 0, ctx->s_b>>>(S, B);
-    else k_ray_paths<FLAT, false><<<(h + 31) / 32, 32, 0, ctx->s_b>>>(S, B);
-    CUDA_TRY(ctx, cudaEventRecord(E->k1[ATMRT_KERNEL_RAY_PATHS], ctx->s_b));
-    E->kmask |= 1u << ATMRT_KERNEL_RAY_PATHS;
+int launch_macro_paths(atmrt_ctx* ctx, const DevScene& S, const DevBuffers& B, int row0, int row1, cudaStream_t st, atmrt_ctx::StageEvents* E) {
+    const int warps = MACRO_THREADS / 32, rows = row1 - row0;
+    auto blocks = [&](int m) { return (rows + warps * (32 / m) - 1) / (warps * (32 / m)); };
+    if (E) CUDA_TRY(ctx, cudaEventRecord(E->k0[ATMRT_KERNEL_RAY_PATHS], st));
+    if (16.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 16><<<blocks(16), MACRO_THREADS, 0, st>>>(S, B, row0, row1);
+    else if (8.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 8><<<blocks(8), MACRO_THREADS, 0, st>>>(S, B, row0, row1);
+    else if (4.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 4><<<blocks(4), MACRO_THREADS, 0, st>>>(S, B, row0, row1);
+    else if (2.0 * S.step <= MACRO_MAX_METRES) k_ray_paths_macro<FLAT, 2><<<blocks(2), MACRO_THREADS, 0, st>>>(S, B, row0, row1);
+    else return 1;  // steps too long for macro steps: the caller integrates all rows with k_ray_paths
+    if (E) {
+        CUDA_TRY(ctx, cudaEventRecord(E->k1[ATMRT_KERNEL_RAY_PATHS], st));
+        E->kmask |= 1u << ATMRT_KERNEL_RAY_PATHS;
+    }
     return 0;
 }
 
@@ -969,24 +974,80 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
     // hierarchical march behind it.
     const bool cross = ctx->sweep_enabled && !sweep && !trace && !brute;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_sweep_flags.p, 0, 16, main));
+    if (sweep) CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_sweep_col.p, 0, (size_t)wl, main));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_prep, main));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_a, ctx->ev_prep, 0));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_b, ctx->ev_prep, 0));
 
+    // A narrow column block (one of several GPUs) is bound by the chain of stage B: the frame is split at a row below the
+    // horizon from which every ray ends within a quarter of the distance (it dives to -1000 m: utils.rs:167-170). The rays
+    // below the split are short chains, done long before the others; the sweep's lower band -- most of the hits -- needs
+    // only them and the terrain, and runs while the long rays are still being integrated. The upper band then enters where
+    // the lower one's top row left off (the row bands of k_sweep_bits), so the image is the unsplit one's, bit for bit.
+    int split = 0;
+    if (sweep && !S.straight && ctx->path_mode == 0 && 2.0 * S.step <= MACRO_MAX_METRES && S.altitude.kind == ATMRT_ALT_ABSOLUTE &&
+        S.row_elev_deg == nullptr && (ctx->sweep_bands == -1 || (ctx->sweep_bands == 0 && wl <= ctx->num_sms * 32))) {
+        const double drop = S.altitude.value + 1000.0, reach = 0.25 * S.max_distance;
+        if (drop > 0.0 && reach > 0.0) {
+            const double e0 = to_degrees(std::atan(drop / reach));  // rays steeper than this end within `reach`
+            // get_ray_elev(y) = tilt - (y - h / 2) / h * fov / (w / h) (fast.rs:118-125)
+            const double per_row = S.fov / (double)S.width;
+            const double y0 = (double)(h / 2) + (S.tilt + e0) / per_row;
+            if (y0 > 0.0 && y0 < (double)h) {
+                const int cand = ((int)std::ceil(y0) + 31) / 32 * 32;
+                if (cand >= 256 && cand <= h - 256) split = cand;
+            }
+        }
+    }
+    SweepLists L{};
+    size_t segs = 0;
+    if (sweep) {
+        // Row bands: one walk per column unless the column block is so narrow that its walks could not fill a fraction of
+        // the machine. (Measured at config 5: a band costs the scan of one whole row, +0.9 ms per extra band on the full
+        // panorama and +0.1 ms on a 2048-column block of an 8-GPU frame; uniform bands pay below ~1000 columns.)
+        int bands = ctx->sweep_bands > 0 ? ctx->sweep_bands : ctx->sweep_bands < 0 ? 1 : (int)(((long long)ctx->num_sms * 8) / std::max(wl, 1));
+        bands = std::max(1, std::min(bands, std::max(1, h / 128)));
+        if (bands > 1) split = 0;
+        L.band_rows = ((h + bands - 1) / bands + 31) / 32 * 32;
+        L.bands = (h + L.band_rows - 1) / L.band_rows;
+        L.split = split;
+        if (split) L.bands = 2, L.band_rows = std::max(split, h - split);
+        L.cap = std::min(2 * L.band_rows + 2, S.n_pad);
+        segs = (size_t)wl * L.bands;
+        if ((rc = ensure(ctx, ctx->d_list, sizeof(int) * segs * L.cap))) return rc;
+        if ((rc = ensure(ctx, ctx->d_count, sizeof(int) * segs))) return rc;
+        if ((rc = ensure(ctx, ctx->d_normals, sizeof(double) * 3 * segs * L.cap))) return rc;
+        L.list = (int*)ctx->d_list.p, L.count = (int*)ctx->d_count.p, L.normals = (double*)ctx->d_normals.p;
+    }
     // Stage B on s_b: all rows (every column needs every row)
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->b0, ctx->s_b));
     {
         const int rb = (h + 31) / 32;
         if (S.straight) {
             k_ray_paths_straight<<<(h + 127) / 128, 128, 0, ctx->s_b>>>(S, B);
-        } else if (S.flat) {
-            if (ctx->path_mode == 1) k_ray_paths<true, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
-            else if (ctx->path_mode == 2) k_ray_paths<true, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
-            else if ((rc = launch_macro_paths<true>(ctx, S, B, h, E))) return rc;
+        } else if (ctx->path_mode == 1 || ctx->path_mode == 2) {
+            if (S.flat) {
+                if (ctx->path_mode == 1) k_ray_paths<true, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
+                else k_ray_paths<true, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
+            } else {
+                if (ctx->path_mode == 1) k_ray_paths<false, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
+                else k_ray_paths<false, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
+            }
         } else {
-            if (ctx->path_mode == 1) k_ray_paths<false, true><<<rb, 32, 0, ctx->s_b>>>(S, B);
-            else if (ctx->path_mode == 2) k_ray_paths<false, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
-            else if ((rc = launch_macro_paths<false>(ctx, S, B, h, E))) return rc;
+            // the long rays first, on the stream whose blocks are placed first
+            int mrc = S.flat ? launch_macro_paths<true>(ctx, S, B, 0, split ? split : h, ctx->s_b, E) : launch_macro_paths<false>(ctx, S, B, 0, split ? split : h, ctx->s_b, E);
+            if (mrc < 0) return mrc;
+            if (mrc > 0) {  // steps too long for macro steps (never with a split frame: the condition above)
+                if (S.flat) k_ray_paths<true, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
+                else k_ray_paths<false, false><<<rb, 32, 0, ctx->s_b>>>(S, B);
+            } else if (split) {
+                CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_b2, ctx->ev_prep, 0));
+                mrc = S.flat ? launch_macro_paths<true>(ctx, S, B, split, h, ctx->s_b2, nullptr) : launch_macro_paths<false>(ctx, S, B, split, h, ctx->s_b2, nullptr);
+                if (mrc) return mrc < 0 ? mrc : fail(ctx, ATMRT_ERR_CUDA, "stage B: inconsistent macro step");
+                CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b1, ctx->s_b2));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_b, ctx->ev_b1, 0));  // the path check below looks at every row
+                ctx->launches++;
+            }
         }
         ctx->launches++;
     }
@@ -1031,6 +1092,13 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
     if (!sweep && !cross) terrain_pyramids(ctx->s_a, 0);
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->a1, ctx->s_a));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->s_a));
+    if (split) {  // the lower band of the sweep: the terrain and the short rays are all it reads
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_c, ctx->ev_a, 0));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_c, ctx->ev_b1, 0));
+        k_sweep_bits<<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, 1), 32 * BITS_WARPS, 0, ctx->s_c>>>(S, B, L, 0, wl, 1);
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_s1, ctx->s_c));
+        ctx->launches++;
+    }
 
     // Stage C on main
     CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_a, 0));
@@ -1043,20 +1111,15 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         // Row bands: one walk per column unless the column block is so narrow that its walks could not fill a fraction of
         // the machine. (Measured at config 5: a band costs the scan of one whole row, +0.9 ms per extra band on the full
         // panorama and +0.1 ms on a 2048-column block of an 8-GPU frame; bands pay below ~1000 columns.)
-        SweepLists L{};
-        int bands = ctx->sweep_bands > 0 ? ctx->sweep_bands : (int)(((long long)ctx->num_sms * 8) / std::max(wl, 1));
-        bands = std::max(1, std::min(bands, std::max(1, h / 128)));
-        L.band_rows = ((h + bands - 1) / bands + 31) / 32 * 32;
-        L.bands = (h + L.band_rows - 1) / L.band_rows;
-        L.cap = std::min(2 * L.band_rows + 2, S.n_pad);
-        const size_t segs = (size_t)wl * L.bands;
-        if ((rc = ensure(ctx, ctx->d_list, sizeof(int) * segs * L.cap))) return rc;
-        if ((rc = ensure(ctx, ctx->d_count, sizeof(int) * segs))) return rc;
-        if ((rc = ensure(ctx, ctx->d_normals, sizeof(double) * 3 * segs * L.cap))) return rc;
-        L.list = (int*)ctx->d_list.p, L.count = (int*)ctx->d_count.p, L.normals = (double*)ctx->d_normals.p;
-        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_sweep_col.p, 0, (size_t)wl, main));
         KT_BEGIN(ATMRT_KERNEL_SWEEP, main)
-        k_sweep_bits<<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, L.bands), 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl);
+        if (split) {
+            // the upper band here (after every ray and the terrain); the lower one was launched on s_c behind stage A and the
+            // short rays (below), and joins in before the normals
+            k_sweep_bits<<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, 1), 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl, 0);
+            CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_s1, 0));
+        } else {
+            k_sweep_bits<<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, L.bands), 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl, -1);
+        }
         KT_END(ATMRT_KERNEL_SWEEP, main)
         // enough blocks per (column, band) that a narrow column block still fills the machine
         const int parts = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)ctx->num_sms * 16 + segs - 1) / segs));
@@ -1361,7 +1424,8 @@ int atmrt_create(int device, atmrt_ctx** out) {
               cudaStreamCreateWithPriority(&ctx->s_b, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->s_t, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->s_r, cudaStreamNonBlocking) == cudaSuccess;
-    cudaEvent_t* evs[] = {&ctx->ev_prep, &ctx->ev_a, &ctx->ev_b, &ctx->ev_terrain, &ctx->ev_tile};
+    ok = ok && cudaStreamCreateWithPriority(&ctx->s_b2, cudaStreamNonBlocking, prio_hi) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->s_c, cudaStreamNonBlocking) == cudaSuccess;
+    cudaEvent_t* evs[] = {&ctx->ev_prep, &ctx->ev_a, &ctx->ev_b, &ctx->ev_terrain, &ctx->ev_tile, &ctx->ev_b1, &ctx->ev_s1};
     for (cudaEvent_t* ev : evs) ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
     for (cudaEvent_t& ev : ctx->ev_band) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
     cudaEvent_t* tevs[] = {&ctx->t_0, &ctx->t_1};
@@ -1403,6 +1467,10 @@ void atmrt_destroy(atmrt_ctx* ctx) {
     if (ctx->s_a) cudaStreamDestroy(ctx->s_a);
     if (ctx->s_b) cudaStreamDestroy(ctx->s_b);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
+    if (ctx->s_b2) cudaStreamDestroy(ctx->s_b2);
+    if (ctx->s_c) cudaStreamDestroy(ctx->s_c);
+    if (ctx->ev_b1) cudaEventDestroy(ctx->ev_b1);
+    if (ctx->ev_s1) cudaEventDestroy(ctx->ev_s1);
     if (ctx->s_t) cudaStreamDestroy(ctx->s_t);
     if (ctx->s_r) cudaStreamDestroy(ctx->s_r);
     if (ctx->ev_terrain) cudaEventDestroy(ctx->ev_terrain);
@@ -1591,7 +1659,7 @@ int atmrt_set_march_mode(atmrt_ctx* ctx, int mode) {
 }
 
 int atmrt_set_sweep_bands(atmrt_ctx* ctx, int bands) {
-    if (!ctx || bands < 0) return fail(ctx, ATMRT_ERR_INVALID, "sweep bands must be >= 0 (0: automatic)");
+    if (!ctx || bands < -1) return fail(ctx, ATMRT_ERR_INVALID, "sweep bands must be >= -1 (0: automatic, -1: split below the horizon)");
     ctx->sweep_bands = bands;
     return 0;
 }

@@ -666,8 +666,8 @@ constexpr int MACRO_THREADS = 128;  // 4 warps share one copy of the table
 constexpr double MACRO_MAX_METRES = 800.0;  // longest macro step: 16 x 50 m (truncation error < 3e-8 m, section 4.B); longer simulation steps get fewer per macro step
 constexpr int ATM_MAX_BND = ATMRT_MAX_ATM_FUNCTIONS + 4;
 
-template <bool FLAT, int MACRO>  // MACRO steps per macro step (16, 8, 4 or 2), 32 / MACRO rows per warp
-__global__ void __launch_bounds__(MACRO_THREADS) k_ray_paths_macro(const __grid_constant__ DevScene S, DevBuffers B) {
+template <bool FLAT, int MACRO>  // MACRO steps per macro step (16, 8, 4 or 2), 32 / MACRO rows per warp; rows [row0, row1)
+__global__ void __launch_bounds__(MACRO_THREADS) k_ray_paths_macro(const __grid_constant__ DevScene S, DevBuffers B, int row0, int row1) {
     __shared__ double tab_smem[ATM_FIELDS * ATM_CELLS];
     __shared__ double s_bnd[ATM_MAX_BND];          // sorted altitudes where g is not smooth (+inf padded)
     __shared__ unsigned char s_first[ATM_CELLS];   // per cell: index of the first of them at or above the cell's lower edge
@@ -679,9 +679,9 @@ __global__ void __launch_bounds__(MACRO_THREADS) k_ray_paths_macro(const __grid_
     constexpr int MACRO_ROWS = 32 / MACRO;
     const GSource gs{(unsigned)__cvta_generic_to_shared(tab_smem), B.atm_pieces, B.n_atm_pieces};
     const int lane = threadIdx.x & 31, rr = lane % MACRO_ROWS, j = lane / MACRO_ROWS;
-    const int y_raw = (blockIdx.x * (MACRO_THREADS / 32) + (threadIdx.x >> 5)) * MACRO_ROWS + rr;
-    const int y = min(y_raw, S.height - 1);
-    const bool writer = y_raw < S.height;
+    const int y_raw = row0 + (blockIdx.x * (MACRO_THREADS / 32) + (threadIdx.x >> 5)) * MACRO_ROWS + rr;
+    const int y = min(y_raw, row1 - 1);
+    const bool writer = y_raw < row1;
     const double alt = *B.obs_alt;
     const double radius = S.radius, off = FLAT ? 0.0 : radius;
     const double d = FLAT ? S.step : S.step / radius;
@@ -2009,7 +2009,9 @@ struct SweepLists {
     int cap;          // entries per (column, band)
     int bands;        // a column is swept in row bands, numbered from the top of the image ...
     int band_rows;    // ... of this many rows (a multiple of 32)
+    int split;        // or, when > 0: two bands, rows [0, split) and [split, height) (a multiple of 32)
 };
+__host__ __device__ __forceinline__ int sweep_band_of_row(const SweepLists& L, int y) { return L.split > 0 ? (y >= L.split ? 1 : 0) : y / L.band_rows; }
 
 // predicated global stores (no branch): the sweep's control flow is warp-uniform, only lane 0 writes
 __device__ __forceinline__ void st_if_s32(int* p, int v, bool ok) {
@@ -2021,7 +2023,8 @@ __device__ __forceinline__ void st_if_v4s32(int* p, int a, int b, int c, int d, 
                  : "memory");
 }
 
-__global__ void __launch_bounds__(32 * BITS_WARPS, 8) k_sweep_bits(const __grid_constant__ DevScene S, DevBuffers B, SweepLists L, int col0, int col1) {
+__global__ void __launch_bounds__(32 * BITS_WARPS, 8) k_sweep_bits(const __grid_constant__ DevScene S, DevBuffers B, SweepLists L, int col0, int col1,
+                                                                   int only_band) {
     if (B.sweep_flags[0] != 0) return;
     const int lane = threadIdx.x & 31;
     const bool lane0 = lane == 0;
@@ -2031,8 +2034,11 @@ __global__ void __launch_bounds__(32 * BITS_WARPS, 8) k_sweep_bits(const __grid_
     // narrow column block (one of eight GPUs) busy. By the monotonicity the sweep rests on, the walk enters a band in the
     // state the row just below the band leaves behind -- its first-hit step, or the end of its path -- which the band
     // finds by scanning that ONE row from step 1: the same cells, the same tests. blockIdx.y = 0 is the bottom band.
-    const int band = L.bands - 1 - (int)blockIdx.y;
-    const int y_lo = band * L.band_rows, y_hi = min(S.height, y_lo + L.band_rows) - 1;
+    // (`only_band` >= 0: a launch for that one band -- the lower band of a split frame is swept while the rays of the upper
+    // one are still being integrated)
+    const int band = only_band >= 0 ? only_band : L.bands - 1 - (int)blockIdx.y;
+    const int y_lo = L.split > 0 ? (band ? L.split : 0) : band * L.band_rows;
+    const int y_hi = (L.split > 0 ? (band ? S.height : L.split) : min(S.height, y_lo + L.band_rows)) - 1;
     const double* __restrict__ te = B.t_elev + (size_t)xl * S.n_pad;
     int* __restrict__ hit = B.sweep_hit + (size_t)xl * S.h_pad;  // per pixel: 1 + the slot of its first-hit step in the band's list (0: no hit)
     int* const list = L.list + ((size_t)xl * L.bands + band) * L.cap;
@@ -2265,7 +2271,7 @@ __global__ void __launch_bounds__(32 * TILE_COLS, 4) k_shade_tiles(const __grid_
     int consumed = nlim > 0 ? nlim - 1 : 0;
     if (hit) {
         const int s = slot1 - 1;
-        const size_t seg = ((size_t)xx * L.bands + yy / L.band_rows) * L.cap;  // the lists of this pixel's band
+        const size_t seg = ((size_t)xx * L.bands + sweep_band_of_row(L, yy)) * L.cap;  // the lists of this pixel's band
         const int kh = L.list[seg + s];
         const double* __restrict__ nr = L.normals + (seg + s - 1) * 3;  // slots s - 1, s: samples kh - 1, kh
         const V3 n0{nr[0], nr[1], nr[2]}, n1{nr[3], nr[4], nr[5]};

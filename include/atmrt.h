@@ -279,8 +279,9 @@ int atmrt_render_trace(atmrt_ctx* ctx, atmrt_trace_point* points, int32_t* count
  * All three produce identical images. */
 int atmrt_set_march_mode(atmrt_ctx* ctx, int mode);
 /* Horizon sweep: the number of row bands a column is walked in (0 = automatic: enough bands that a narrow column
- * block still fills the GPU; clamped to bands of at least 128 rows). Every value gives the same image (tuning and
- * validation hook). */
+ * block still fills the GPU, clamped to bands of at least 128 rows -- or, for a block of a multi-GPU frame, two bands
+ * split below the horizon, the lower one swept while the long rays above it are still being integrated; -1 = that
+ * split whenever the frame allows it). Every value gives the same image (tuning and validation hook). */
 int atmrt_set_sweep_bands(atmrt_ctx* ctx, int bands);
 /* Ray-path stage: 0 (default) g(h) from the table, macro steps of 8 steps where g is smooth and the
  * reference's single steps across the starts of the temperature functions; 1 every evaluation through

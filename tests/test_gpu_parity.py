@@ -371,6 +371,40 @@ def test_sweep_row_bands_are_bit_identical(ctx, name, scale):
     assert brute["stats"]["pixels_hit"] > 0.2 * p.width * p.height
 
 
+@pytest.mark.parametrize("name,scale,tilt", [("c5", 0.25, 0.0), ("c5", 0.125, -8.0), ("c2", 1.0, -2.0)])
+def test_frame_split_below_the_horizon_is_bit_identical(ctx, name, scale, tilt):
+    """A column block of a multi-GPU frame is bound by the chain of stage B, so the frame is split at a row below the horizon
+    from which every ray ends early: those rays are integrated by a launch of their own, and the sweep's lower band runs on
+    them while the long rays are still on their way (atmrt_set_sweep_bands(-1) asks for the split on any width). The image,
+    the metadata, the step counts and the statistics must be the unsplit frame's."""
+    p, terrain, _, _ = scene(name, scale)
+    p.tilt = tilt
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects([])
+    try:
+        ctx.set_sweep_bands(1)
+        whole = ctx.render()
+        ctx.set_sweep_bands(-1)
+        split = ctx.render()
+        again = ctx.render()
+        q = abi.Params.from_buffer_copy(p)  # ... and on a narrow block, where the default chooses it by itself
+        q.x0, q.x1 = p.width // 3, p.width // 3 + 96
+        ctx.set_params(q)
+        ctx.set_sweep_bands(0)
+        block = ctx.render()
+    finally:
+        ctx.set_sweep_bands(0)
+    _same_render(split, whole)
+    _same_render(again, whole)
+    np.testing.assert_array_equal(block["rgb"], whole["rgb"][:, q.x0:q.x1])
+    np.testing.assert_array_equal(block["steps"], whole["steps"][:, q.x0:q.x1])
+    assert whole["stats"]["pixels_hit"] > 0.2 * p.width * p.height
+    # the rays below the split are the short ones: the split is there at all only if some rows dive early
+    lens = np.array([len(ctx.path(y)["dist"]) for y in (p.height - 1, 0)])
+    assert lens[0] < 0.3 * lens[1]
+
+
 def test_sweep_falls_back_when_rays_cross(ctx, oracle_lib):
     """A strong temperature inversion (duct) bends rays back down and makes neighbouring rays cross: the
     path cache is no longer monotone in the row, k_path_check says so on the device and the general
