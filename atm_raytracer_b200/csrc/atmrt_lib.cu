@@ -1019,6 +1019,35 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         if ((rc = ensure(ctx, ctx->d_normals, sizeof(double) * 3 * segs * L.cap))) return rc;
         L.list = (int*)ctx->d_list.p, L.count = (int*)ctx->d_count.p, L.normals = (double*)ctx->d_normals.p;
     }
+    MarchOut O{rt.rgb, rt.meta, rt.steps, rt.points, rt.counts, rt.max_points};
+    // the normals of the listed hit samples (one band or all) and the shading of rows [r0, r1) on a stream; every shaded band
+    // of rows travels to the host on the (by then idle) stage-A stream while the next one is shaded
+    const bool to_host = rt.host_rgb || rt.host_meta || rt.host_steps;
+    int shade_band = 0;
+    auto launch_normals = [&](cudaStream_t st, int only_band) {
+        const size_t nseg = only_band >= 0 ? (size_t)wl : segs;
+        // enough blocks per (column, band) that a narrow column block still fills the machine
+        const int parts = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)ctx->num_sms * 16 + nseg - 1) / nseg));
+        if (S.earth.walker == WALK_SPHERICAL) k_hit_normals<WALK_SPHERICAL><<<(unsigned)(nseg * parts), 128, 0, st>>>(S, B, L, parts, only_band);
+        else k_hit_normals<-1><<<(unsigned)(nseg * parts), 128, 0, st>>>(S, B, L, parts, only_band);
+        ctx->launches++;
+    };
+    auto launch_shade = [&](cudaStream_t st, int row0, int row1, int nbands) -> int {
+        const int band_rows = ((row1 - row0 + nbands - 1) / nbands + 31) / 32 * 32;
+        for (int r0 = row0; r0 < row1; r0 += band_rows) {
+            const int r1 = std::min(row1, r0 + band_rows);
+            k_shade_tiles<<<dim3((r1 - r0 + 31) / 32, (wl + TILE_COLS - 1) / TILE_COLS), 32 * TILE_COLS, 0, st>>>(S, B, O, L, r0);
+            ctx->launches++;
+            if (to_host) {
+                cudaEvent_t ev = ctx->ev_band[shade_band++ % SHADE_BANDS];
+                CUDA_TRY(ctx, cudaEventRecord(ev, st));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_a, ev, 0));
+                const int crc = copy_rows_to_host(ctx, rt, wl, r0, r1, ctx->s_a);
+                if (crc) return crc;
+            }
+        }
+        return 0;
+    };
     // Stage B on s_b: all rows (every column needs every row)
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->b0, ctx->s_b));
     {
@@ -1096,15 +1125,16 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_c, ctx->ev_a, 0));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_c, ctx->ev_b1, 0));
         k_sweep_bits<<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, 1), 32 * BITS_WARPS, 0, ctx->s_c>>>(S, B, L, 0, wl, 1);
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_s1, ctx->s_c));
         ctx->launches++;
+        launch_normals(ctx->s_c, 1);
+        if ((rc = launch_shade(ctx->s_c, split, h, to_host ? SHADE_BANDS / 2 : 1))) return rc;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_s1, ctx->s_c));
     }
 
     // Stage C on main
     CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_a, 0));
     CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_b, 0));
     if (timed) CUDA_TRY(ctx, cudaEventRecord(E->c0, main));
-    MarchOut O{rt.rgb, rt.meta, rt.steps, rt.points, rt.counts, rt.max_points};
     const dim3 grid((h + MARCH_THREADS - 1) / MARCH_THREADS, wl);
     if (sweep) {
         // Bit-mask sweep -> normals of the distinct hit samples -> row-major shading (kernels.cuh).
@@ -1112,38 +1142,19 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         // the machine. (Measured at config 5: a band costs the scan of one whole row, +0.9 ms per extra band on the full
         // panorama and +0.1 ms on a 2048-column block of an 8-GPU frame; bands pay below ~1000 columns.)
         KT_BEGIN(ATMRT_KERNEL_SWEEP, main)
-        if (split) {
-            // the upper band here (after every ray and the terrain); the lower one was launched on s_c behind stage A and the
-            // short rays (below), and joins in before the normals
-            k_sweep_bits<<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, 1), 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl, 0);
-            CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_s1, 0));
-        } else {
-            k_sweep_bits<<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, L.bands), 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl, -1);
-        }
+        // (a split frame: the upper band here, after every ray and the terrain; the lower one went out on s_c behind stage A
+        // and the short rays, with its normals and its shading)
+        if (split) k_sweep_bits<<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, 1), 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl, 0);
+        else k_sweep_bits<<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, L.bands), 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl, -1);
         KT_END(ATMRT_KERNEL_SWEEP, main)
-        // enough blocks per (column, band) that a narrow column block still fills the machine
-        const int parts = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)ctx->num_sms * 16 + segs - 1) / segs));
+        ctx->launches++;
         KT_BEGIN(ATMRT_KERNEL_HIT_NORMALS, main)
-        if (S.earth.walker == WALK_SPHERICAL) k_hit_normals<WALK_SPHERICAL><<<(unsigned)(segs * parts), 128, 0, main>>>(S, B, L, parts);
-        else k_hit_normals<-1><<<(unsigned)(segs * parts), 128, 0, main>>>(S, B, L, parts);
+        launch_normals(main, split ? 0 : -1);
         KT_END(ATMRT_KERNEL_HIT_NORMALS, main)
-        ctx->launches += 2;
         KT_BEGIN(ATMRT_KERNEL_SHADE, main)
-        const bool to_host = rt.host_rgb || rt.host_meta || rt.host_steps;
-        const int nbands = to_host && h >= 256 ? SHADE_BANDS : 1;
-        const int band_rows = ((h + nbands - 1) / nbands + 31) / 32 * 32;
-        int bi = 0;
-        for (int r0 = 0; r0 < h; r0 += band_rows, ++bi) {
-            const int r1 = std::min(h, r0 + band_rows);
-            k_shade_tiles<<<dim3((r1 - r0 + 31) / 32, (wl + TILE_COLS - 1) / TILE_COLS), 32 * TILE_COLS, 0, main>>>(S, B, O, L, r0);
-            ctx->launches++;
-            if (to_host) {  // the finished band goes to the host on the (idle) stage-A stream while the next band is shaded
-                CUDA_TRY(ctx, cudaEventRecord(ctx->ev_band[bi], main));
-                CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_a, ctx->ev_band[bi], 0));
-                if ((rc = copy_rows_to_host(ctx, rt, wl, r0, r1, ctx->s_a))) return rc;
-            }
-        }
+        if ((rc = launch_shade(main, 0, split ? split : h, to_host && h >= 256 ? (split ? SHADE_BANDS / 2 : SHADE_BANDS) : 1))) return rc;
         KT_END(ATMRT_KERNEL_SHADE, main)
+        if (split) CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_s1, 0));  // the lower band's pixels
         if (to_host) {
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->s_a));
             CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_a, 0));

@@ -2219,9 +2219,10 @@ __global__ void __launch_bounds__(32 * BITS_WARPS, 8) k_sweep_bits(const __grid_
 
 // TerrainData::normal of the listed samples (sample_normal: find_normal at the sample's cached coordinates).
 template <int W>
-__global__ void __launch_bounds__(128, 8) k_hit_normals(const __grid_constant__ DevScene S, DevBuffers B, SweepLists L, int parts) {
+__global__ void __launch_bounds__(128, 8) k_hit_normals(const __grid_constant__ DevScene S, DevBuffers B, SweepLists L, int parts, int only_band) {
     if (B.sweep_flags[0] != 0) return;
-    const int seg = blockIdx.x / parts, part = blockIdx.x % parts;  // seg = column * bands + band
+    const int part = blockIdx.x % parts;
+    const int seg = only_band >= 0 ? (blockIdx.x / parts) * L.bands + only_band : blockIdx.x / parts;  // seg = column * bands + band
     const int xl = seg / L.bands;
     if (B.sweep_col[xl] != 0) return;  // flagged columns belong to the brute-force march
     const int cnt = L.count[seg];
