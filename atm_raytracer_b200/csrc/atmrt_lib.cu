@@ -1124,7 +1124,7 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
     if (split) {  // the lower band of the sweep: the terrain and the short rays are all it reads
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_c, ctx->ev_a, 0));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_c, ctx->ev_b1, 0));
-        k_sweep_bits<<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, 1), 32 * BITS_WARPS, 0, ctx->s_c>>>(S, B, L, 0, wl, 1);
+        k_sweep_bits<true><<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, 1), 32 * BITS_WARPS, 0, ctx->s_c>>>(S, B, L, 0, wl, 1);
         ctx->launches++;
         launch_normals(ctx->s_c, 1);
         if ((rc = launch_shade(ctx->s_c, split, h, to_host ? SHADE_BANDS / 2 : 1))) return rc;
@@ -1144,8 +1144,8 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         KT_BEGIN(ATMRT_KERNEL_SWEEP, main)
         // (a split frame: the upper band here, after every ray and the terrain; the lower one went out on s_c behind stage A
         // and the short rays, with its normals and its shading)
-        if (split) k_sweep_bits<<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, 1), 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl, 0);
-        else k_sweep_bits<<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, L.bands), 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl, -1);
+        if (split) k_sweep_bits<true><<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, 1), 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl, 0);
+        else k_sweep_bits<false><<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, L.bands), 32 * BITS_WARPS, 0, main>>>(S, B, L, 0, wl, -1);
         KT_END(ATMRT_KERNEL_SWEEP, main)
         ctx->launches++;
         KT_BEGIN(ATMRT_KERNEL_HIT_NORMALS, main)

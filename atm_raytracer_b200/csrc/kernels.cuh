@@ -2023,6 +2023,7 @@ __device__ __forceinline__ void st_if_v4s32(int* p, int a, int b, int c, int d, 
                  : "memory");
 }
 
+template <bool SPLIT>  // SPLIT: one band of a frame split in two (L.split), `only_band` of them; else every band of L.bands uniform ones
 __global__ void __launch_bounds__(32 * BITS_WARPS, 8) k_sweep_bits(const __grid_constant__ DevScene S, DevBuffers B, SweepLists L, int col0, int col1,
                                                                    int only_band) {
     if (B.sweep_flags[0] != 0) return;
@@ -2036,9 +2037,9 @@ __global__ void __launch_bounds__(32 * BITS_WARPS, 8) k_sweep_bits(const __grid_
     // finds by scanning that ONE row from step 1: the same cells, the same tests. blockIdx.y = 0 is the bottom band.
     // (`only_band` >= 0: a launch for that one band -- the lower band of a split frame is swept while the rays of the upper
     // one are still being integrated)
-    const int band = only_band >= 0 ? only_band : L.bands - 1 - (int)blockIdx.y;
-    const int y_lo = L.split > 0 ? (band ? L.split : 0) : band * L.band_rows;
-    const int y_hi = (L.split > 0 ? (band ? S.height : L.split) : min(S.height, y_lo + L.band_rows)) - 1;
+    const int band = SPLIT ? only_band : L.bands - 1 - (int)blockIdx.y;
+    const int y_lo = SPLIT ? (band ? L.split : 0) : band * L.band_rows;
+    const int y_hi = (SPLIT ? (band ? S.height : L.split) : min(S.height, y_lo + L.band_rows)) - 1;
     const double* __restrict__ te = B.t_elev + (size_t)xl * S.n_pad;
     int* __restrict__ hit = B.sweep_hit + (size_t)xl * S.h_pad;  // per pixel: 1 + the slot of its first-hit step in the band's list (0: no hit)
     int* const list = L.list + ((size_t)xl * L.bands + band) * L.cap;
