@@ -97,6 +97,11 @@ struct atmrt_ctx {
     int sweep_bands = 0;                // 0: chosen per render (launch_render)
     DevBuf d_stage;  // raw posts of pack_terrain on their way to the tiled layout
     bool sweep_enabled = true;
+    struct Uploaded {  // what upload_scene_inputs sent last, and where
+        void* dst = nullptr;
+        std::vector<char> bytes;
+    };
+    Uploaded up[6];
     // the terrain on its way (atmrt_group_render_tiles): uploaded, retiled and gathered on s_t / s_r; whoever reads the terrain
     // waits for ev_terrain
     cudaStream_t s_t = nullptr, s_r = nullptr;
@@ -796,16 +801,27 @@ int prepare_render(atmrt_ctx* ctx) {
     return 0;
 }
 
+// A copy from pageable memory is staged by the driver and holds up the head of the frame; the tables below change only
+// with the parameters, so each is sent again only when its bytes (or its place on the device) differ from what was sent last.
+static int upload_if_changed(atmrt_ctx* ctx, atmrt_ctx::Uploaded& u, void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    if (u.dst == dst && u.bytes.size() == bytes && (bytes == 0 || memcmp(u.bytes.data(), src, bytes) == 0)) return 0;
+    if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    u.dst = dst;
+    u.bytes.assign((const char*)src, (const char*)src + bytes);
+    return 0;
+}
+
 int upload_scene_inputs(atmrt_ctx* ctx, cudaStream_t s) {
     const DevScene& S = ctx->scene;
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dist.p, ctx->dist_k.data(), sizeof(double) * ctx->dist_k.size(), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pdist.p, ctx->path_x.data(), sizeof(double) * 2 * S.n_x, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_atm_cells.p, ctx->atm_cells.data(), sizeof(double) * ATM_FIELDS * ATM_CELLS, cudaMemcpyHostToDevice, s));
-    if (!ctx->atm_pieces.empty())
-        CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->d_atm_cells.p + sizeof(double) * ATM_FIELDS * ATM_CELLS, ctx->atm_pieces.data(),
-                                      sizeof(DevGPiece) * ctx->atm_pieces.size(), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_atm_aux.p, ctx->atm_bnd.data(), sizeof(double) * ATM_MAX_BND, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->d_atm_aux.p + sizeof(double) * ATM_MAX_BND, ctx->atm_first.data(), ATM_CELLS, cudaMemcpyHostToDevice, s));
+    int rc;
+    if ((rc = upload_if_changed(ctx, ctx->up[0], ctx->d_dist.p, ctx->dist_k.data(), sizeof(double) * ctx->dist_k.size(), s))) return rc;
+    if ((rc = upload_if_changed(ctx, ctx->up[1], ctx->d_pdist.p, ctx->path_x.data(), sizeof(double) * 2 * S.n_x, s))) return rc;
+    if ((rc = upload_if_changed(ctx, ctx->up[2], ctx->d_atm_cells.p, ctx->atm_cells.data(), sizeof(double) * ATM_FIELDS * ATM_CELLS, s))) return rc;
+    if ((rc = upload_if_changed(ctx, ctx->up[3], (char*)ctx->d_atm_cells.p + sizeof(double) * ATM_FIELDS * ATM_CELLS, ctx->atm_pieces.data(),
+                                sizeof(DevGPiece) * ctx->atm_pieces.size(), s)))
+        return rc;
+    if ((rc = upload_if_changed(ctx, ctx->up[4], ctx->d_atm_aux.p, ctx->atm_bnd.data(), sizeof(double) * ATM_MAX_BND, s))) return rc;
+    if ((rc = upload_if_changed(ctx, ctx->up[5], (char*)ctx->d_atm_aux.p + sizeof(double) * ATM_MAX_BND, ctx->atm_first.data(), ATM_CELLS, s))) return rc;
     if (S.nobjects > 0) {
         std::vector<DevObject> host(S.nobjects);
         for (int i = 0; i < S.nobjects; ++i) {
