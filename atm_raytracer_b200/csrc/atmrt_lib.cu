@@ -1048,11 +1048,11 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         else k_hit_normals<-1><<<(unsigned)(nseg * parts), 128, 0, st>>>(S, B, L, parts, only_band);
         ctx->launches++;
     };
-    auto launch_shade = [&](cudaStream_t st, int row0, int row1, int nbands) -> int {
+    auto launch_shade = [&](cudaStream_t st, int row0, int row1, int nbands, int count) -> int {
         const int band_rows = ((row1 - row0 + nbands - 1) / nbands + 31) / 32 * 32;
         for (int r0 = row0; r0 < row1; r0 += band_rows) {
             const int r1 = std::min(row1, r0 + band_rows);
-            k_shade_tiles<<<dim3((r1 - r0 + 31) / 32, (wl + TILE_COLS - 1) / TILE_COLS), 32 * TILE_COLS, 0, st>>>(S, B, O, L, r0);
+            k_shade_tiles<<<dim3((r1 - r0 + 31) / 32, (wl + TILE_COLS - 1) / TILE_COLS), 32 * TILE_COLS, 0, st>>>(S, B, O, L, r0, count);
             ctx->launches++;
             if (to_host) {
                 cudaEvent_t ev = ctx->ev_band[shade_band++ % SHADE_BANDS];
@@ -1143,7 +1143,7 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         k_sweep_bits<true><<<dim3((wl + BITS_WARPS - 1) / BITS_WARPS, 1), 32 * BITS_WARPS, 0, ctx->s_c>>>(S, B, L, 0, wl, 1);
         ctx->launches++;
         launch_normals(ctx->s_c, 1);
-        if ((rc = launch_shade(ctx->s_c, split, h, to_host ? SHADE_BANDS / 2 : 1))) return rc;
+        if ((rc = launch_shade(ctx->s_c, split, h, to_host ? SHADE_BANDS / 2 : 1, 0))) return rc;  // (counted below, once every check is in)
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_s1, ctx->s_c));
     }
 
@@ -1168,9 +1168,13 @@ int launch_render(atmrt_ctx* ctx, RenderTargets& rt, cudaStream_t main) {
         launch_normals(main, split ? 0 : -1);
         KT_END(ATMRT_KERNEL_HIT_NORMALS, main)
         KT_BEGIN(ATMRT_KERNEL_SHADE, main)
-        if ((rc = launch_shade(main, 0, split ? split : h, to_host && h >= 256 ? (split ? SHADE_BANDS / 2 : SHADE_BANDS) : 1))) return rc;
+        if ((rc = launch_shade(main, 0, split ? split : h, to_host && h >= 256 ? (split ? SHADE_BANDS / 2 : SHADE_BANDS) : 1, 1))) return rc;
         KT_END(ATMRT_KERNEL_SHADE, main)
-        if (split) CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_s1, 0));  // the lower band's pixels
+        if (split) {
+            CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_s1, 0));  // the lower band's pixels
+            k_count_swept<<<(wl + 7) / 8, 256, 0, main>>>(S, B, L, split, h);
+            ctx->launches++;
+        }
         if (to_host) {
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->s_a));
             CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_a, 0));

@@ -2248,7 +2248,8 @@ __global__ void __launch_bounds__(128, 8) k_hit_normals(const __grid_constant__ 
 // (fogged) colour of its trace point, and a pixel without one is add([0,0,0], default, 1.0) == default.
 constexpr int TILE_COLS = 8;
 
-__global__ void __launch_bounds__(32 * TILE_COLS, 4) k_shade_tiles(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, SweepLists L, int row0) {
+__global__ void __launch_bounds__(32 * TILE_COLS, 4) k_shade_tiles(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, SweepLists L, int row0,
+                                                                   int count) {
     if (B.sweep_flags[0] != 0) return;
     __shared__ double s_meta[32][TILE_COLS * 4];
     __shared__ __align__(16) unsigned char s_rgb[32][TILE_COLS * 3];
@@ -2334,9 +2335,47 @@ __global__ void __launch_bounds__(32 * TILE_COLS, 4) k_shade_tiles(const __grid_
             }
         }
     }
-    if (threadIdx.x == 0) {
+    // (`count` == 0: the lower band of a split frame is shaded before every check of the frame is in; its pixels are counted
+    // afterwards, by k_count_swept)
+    if (threadIdx.x == 0 && count) {
         unsigned long long st = 0ull, ht = 0ull;
         for (int i = 0; i < TILE_COLS; ++i) st += s_cnt[i], ht += s_hits[i];
+        if (st) atomicAdd(B.counters + CNT_RAY_STEPS, st);
+        if (ht) atomicAdd(B.counters + CNT_TRACE_POINTS, ht), atomicAdd(B.counters + CNT_PIXELS_HIT, ht);
+    }
+}
+
+// The render counters of the swept pixels of rows [row0, row1): what k_shade_tiles adds when it counts itself -- the steps
+// a pixel consumed (its first-hit step, or its ray's last) and the hits -- for the columns the sweep did not hand to the
+// brute-force march, unless the whole image went to the general march. One thread per pixel, lanes along the rows.
+__global__ void __launch_bounds__(256) k_count_swept(const __grid_constant__ DevScene S, DevBuffers B, SweepLists L, int row0, int row1) {
+    if (B.sweep_flags[0] != 0) return;
+    __shared__ unsigned long long s_steps[8];
+    __shared__ unsigned s_hits[8];
+    const int wl = S.x1 - S.x0, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int xl = blockIdx.x * 8 + w;  // a warp per column, a block per eight columns: one set of atomics per block
+    unsigned long long steps = 0ull;
+    unsigned hits = 0u;
+    if (xl < wl && B.sweep_col[xl] == 0) {
+        const int* __restrict__ hit = B.sweep_hit + (size_t)xl * S.h_pad;
+        for (int y = row0 + lane; y < row1; y += 32) {
+            const int nlim = min(S.n_t, B.p_n[y]);
+            const int slot1 = hit[y];
+            if (slot1 > 0) {
+                steps += (unsigned long long)L.list[((size_t)xl * L.bands + sweep_band_of_row(L, y)) * L.cap + slot1 - 1];
+                hits += 1u;
+            } else {
+                steps += (unsigned long long)(nlim > 0 ? nlim - 1 : 0);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(FULL, steps, o);
+    hits = __reduce_add_sync(FULL, hits);
+    if (lane == 0) s_steps[w] = steps, s_hits[w] = hits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long st = 0ull, ht = 0ull;
+        for (int i = 0; i < 8; ++i) st += s_steps[i], ht += s_hits[i];
         if (st) atomicAdd(B.counters + CNT_RAY_STEPS, st);
         if (ht) atomicAdd(B.counters + CNT_TRACE_POINTS, ht), atomicAdd(B.counters + CNT_PIXELS_HIT, ht);
     }

@@ -405,6 +405,38 @@ def test_frame_split_below_the_horizon_is_bit_identical(ctx, name, scale, tilt):
     assert lens[0] < 0.3 * lens[1]
 
 
+def test_split_frame_with_crossing_rays_falls_back(ctx):
+    """The split frame's lower band is swept, shaded and on its way to the host before the order of all rays has been
+    checked. In a duct the check fails afterwards: the general march must repaint the whole image, lower band included."""
+    p, terrain, _, _ = scene("c2", 1.0)
+    a = p.atmosphere
+    a.n_functions = 3
+    a.fn_gradient[0], a.fn_start_altitude[1], a.fn_gradient[1] = -0.0065, 1850.0, 0.5   # +0.5 K/m over 40 m
+    a.fn_start_altitude[2], a.fn_gradient[2] = 1890.0, -0.0065
+    p.tilt = -2.0
+    ctx.set_terrain(terrain)
+    ctx.set_params(p)
+    ctx.set_objects([])
+    try:
+        ctx.set_march_mode(2)
+        want = ctx.render()
+        ctx.set_march_mode(0)
+        ctx.set_sweep_bands(-1)
+        got = ctx.render()
+        again = ctx.render(meta=False, steps=False)
+        ctx.set_sweep_bands(1)
+        whole = ctx.render()
+    finally:
+        ctx.set_sweep_bands(0)
+        ctx.set_march_mode(0)
+    _same_render(got, want)
+    _same_render(whole, want)
+    np.testing.assert_array_equal(again["rgb"], want["rgb"])
+    rows = [ctx.path(y)["elev"] for y in range(0, p.height // 4, 4)]  # the rays that climb into the duct
+    n = min(3000, min(len(r) for r in rows))
+    assert (np.diff(np.stack([r[:n] for r in rows]), axis=0) > 0).any(), "the duct was meant to make rays cross"
+
+
 def test_sweep_falls_back_when_rays_cross(ctx, oracle_lib):
     """A strong temperature inversion (duct) bends rays back down and makes neighbouring rays cross: the
     path cache is no longer monotone in the row, k_path_check says so on the device and the general
