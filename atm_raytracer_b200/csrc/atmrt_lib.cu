@@ -40,6 +40,8 @@ struct atmrt_ctx {
     cudaStream_t s_a = nullptr, s_b = nullptr, s_main = nullptr;
     cudaEvent_t ev_band[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_prep = nullptr, ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_last = nullptr;  // end of the most recent atmrt_render_device: the next one, on whatever stream, starts behind it
+    bool last_recorded = false;
     // Stage timing: one set of events per render since the last harvest (atmrt_stage_times), so a
     // whole timed region of asynchronous renders can be averaged without synchronising inside it.
     struct StageEvents {
@@ -1456,7 +1458,7 @@ int atmrt_create(int device, atmrt_ctx** out) {
               cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->s_t, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->s_r, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithPriority(&ctx->s_b2, cudaStreamNonBlocking, prio_hi) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->s_c, cudaStreamNonBlocking) == cudaSuccess;
-    cudaEvent_t* evs[] = {&ctx->ev_prep, &ctx->ev_a, &ctx->ev_b, &ctx->ev_terrain, &ctx->ev_tile, &ctx->ev_b1, &ctx->ev_s1};
+    cudaEvent_t* evs[] = {&ctx->ev_prep, &ctx->ev_a, &ctx->ev_b, &ctx->ev_terrain, &ctx->ev_tile, &ctx->ev_b1, &ctx->ev_s1, &ctx->ev_last};
     for (cudaEvent_t* ev : evs) ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
     for (cudaEvent_t& ev : ctx->ev_band) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
     cudaEvent_t* tevs[] = {&ctx->t_0, &ctx->t_1};
@@ -1481,7 +1483,7 @@ void atmrt_destroy(atmrt_ctx* ctx) {
     for (DevBuf* b : bufs) release(*b);
     for (DevBuf& b : ctx->textures) release(b);
     if (ctx->terrain_owned) cudaFree(ctx->terrain_owned);
-    cudaEvent_t evs[] = {ctx->ev_prep, ctx->ev_a, ctx->ev_b, ctx->t_0, ctx->t_1};
+    cudaEvent_t evs[] = {ctx->ev_prep, ctx->ev_a, ctx->ev_b, ctx->t_0, ctx->t_1, ctx->ev_last};
     for (cudaEvent_t ev : evs)
         if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->ev_band)
@@ -1707,10 +1709,15 @@ int atmrt_render_device(atmrt_ctx* ctx, void* rgb_dev, void* meta_dev, void* ste
     int rc = prepare_render(ctx);
     if (rc) return rc;
     cudaStream_t main = stream ? (cudaStream_t)stream : ctx->s_main;
+    // every render of a context works in the context's caches, flags and counters: a render on another stream than the one
+    // before it starts behind that one
+    if (ctx->last_recorded) CUDA_TRY(ctx, cudaStreamWaitEvent(main, ctx->ev_last, 0));
     RenderTargets rt;
     rt.rgb = (unsigned char*)rgb_dev, rt.meta = (atmrt_meta*)meta_dev, rt.steps = (int*)steps_dev;
     rc = launch_render(ctx, rt, main);
     if (rc) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_last, main));
+    ctx->last_recorded = true;
     if (stats) {
         CUDA_TRY(ctx, cudaStreamSynchronize(main));
         return collect_stats(ctx, stats);
@@ -2165,6 +2172,8 @@ void atmrt_group_destroy(atmrt_group* g) {
 }
 
 const char* atmrt_group_last_error(const atmrt_group* g) { return g ? g->err.c_str() : g_create_error.c_str(); }
+atmrt_ctx* atmrt_group_context(atmrt_group* g, int i) { return g && i >= 0 && i < (int)g->ctx.size() ? g->ctx[(size_t)i] : nullptr; }
+
 int atmrt_group_size(const atmrt_group* g) { return g ? (int)g->ctx.size() : 0; }
 
 int atmrt_group_column_block(const atmrt_group* g, int width, int i, int* x0, int* x1) {

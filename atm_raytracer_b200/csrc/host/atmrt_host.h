@@ -19,6 +19,40 @@ int atmrt_host_read_dted(const char* path, atmrt_tile_desc* desc, int16_t* posts
 int atmrt_host_write_png(const char* path, const uint8_t* pixels, int width, int height, int channels);
 int atmrt_host_read_png(const char* path, uint8_t* rgba, size_t capacity, int* width, int* height);
 const char* atmrt_host_last_error(void);
+/* The overlays renderer::output_image draws over the finished picture (renderer/mod.rs:22-365, 416-431): ticks with
+ * labels, the flat-earth horizon line, the eye-level line. Tick / VerticalTick (params.rs:325-385) as one POD. */
+typedef struct atmrt_host_tick {
+    int32_t multiple;  /* 0: Single { azimuth | elevation, size, labelled }, 1: Multiple { bias, step, size, labelled } */
+    int32_t labelled;
+    uint32_t size;     /* pixels */
+    uint32_t reserved;
+    double angle;      /* Single: azimuth (ticks) / elevation (vertical_ticks), degrees */
+    double bias, step; /* Multiple */
+} atmrt_host_tick;
+typedef struct atmrt_host_overlays {
+    const atmrt_host_tick* ticks;          /* params.output.ticks */
+    const atmrt_host_tick* vertical_ticks; /* params.output.vertical_ticks */
+    int32_t nticks, nvertical_ticks;
+    double direction, fov, tilt;           /* params.view.frame, degrees */
+    int32_t show_eye_level;                /* params.output.show_eye_level */
+    int32_t show_flat_horizon;             /* ALREADY gated as output_image gates it: show_flat_horizon && shape == Flat && !straight_rays */
+    double flat_horizon_elevation;         /* degrees: atmrt_host_flat_horizon_elevation(n at the observer's altitude) */
+} atmrt_host_overlays;
+/* Draws into rgb[height][width][3] in output_image's order (ticks, flat horizon, eye level). elevation_angle / azimuth:
+ * ResultPixel.elevation_angle / .azimuth as atmrt_pixel_angles returns them, [height][width] each. */
+int atmrt_host_draw_overlays(uint8_t* rgb, int width, int height, const double* elevation_angle, const double* azimuth,
+                             const atmrt_host_overlays* overlays);
+/* The ticks draw_ticks draws (gen_ticks, renderer/mod.rs:225-266), by ascending pixel position: x for ticks (vertical == 0),
+ * y for vertical_ticks. label = format!("{:.1$}", angle, decimals). n = how many there are (may exceed capacity). */
+typedef struct atmrt_host_draw_tick {
+    uint32_t position, size;
+    int32_t labelled;
+    char label[28];
+} atmrt_host_draw_tick;
+int atmrt_host_gen_ticks(int width, int height, const double* elevation_angle, const double* azimuth, const atmrt_host_overlays* overlays,
+                         int vertical, atmrt_host_draw_tick* out, int capacity, int* n);
+int atmrt_host_num_decimals(double x); /* renderer/mod.rs:206-214 (the reference's own test: renderer/mod.rs:438-459) */
+int atmrt_host_flat_horizon_elevation(double n_at_observer, double* elevation_deg); /* renderer/mod.rs:424-425 */
 /* The subcommands of the reference's binary on this path (main.rs:17-39), argv without the subcommand name; each
  * returns the process exit code. gen: generator/mod.rs:47-99; the three text dumpers: ray_path.rs, elev_profile.rs,
  * atm_printer.rs (same flags, same text layout; the numbers come from the device through the C-ABI probes). */
@@ -30,6 +64,11 @@ int atmrt_host_output_atm(int argc, const char* const* argv);
 int atmrt_host_parse_config(int argc, const char* const* argv, atmrt_params* params, atmrt_object* objects, int max_objects,
                             int* nobjects, char* terrain_folder, size_t folder_cap, char* output_file, size_t file_cap,
                             char* meta_file, size_t meta_cap);
+
+/* Parse-only: output.ticks / vertical_ticks / show_eye_level / show_flat_horizon as read_config lowers them (tests). */
+int atmrt_host_parse_overlays(int argc, const char* const* argv, atmrt_host_tick* ticks, int max_ticks, int* nticks,
+                              atmrt_host_tick* vertical_ticks, int max_vertical_ticks, int* nvertical_ticks, int* show_eye_level,
+                              int* show_flat_horizon);
 
 #ifdef __cplusplus
 }

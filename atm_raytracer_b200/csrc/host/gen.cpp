@@ -306,6 +306,9 @@ struct Config {
     std::string file = "./output.png", file_metadata;
     int width = 640, height = 480;
     int gpus = 1;  // --gpus N (not a flag of the reference): column blocks over N GPUs of this box
+    // the overlays of renderer::output_image (params.rs:403-410)
+    std::vector<atmrt_host_tick> ticks, vertical_ticks;
+    bool show_eye_level = false, show_flat_horizon = false;
 };
 
 static atmrt_atmosphere_def us_76() {  // AtmosphereDef::us_76() (params.rs:453)
@@ -357,6 +360,37 @@ static void parse_position(const Node& n, double* lat, double* lon, atmrt_altitu
     *lat = num(n, "latitude", 0.0);
     *lon = num(n, "longitude", 0.0);
     if (const Node* a = n.get("altitude")) *alt = parse_altitude(*a);
+}
+
+// Vec<Tick> / Vec<VerticalTick> (params.rs:325-385): externally tagged Single { azimuth | elevation, size, labelled } or
+// Multiple { bias, step, size, labelled }; serde has no defaults for these fields
+static std::vector<atmrt_host_tick> parse_ticks(const Node& list, const std::string& what, const char* single_key) {
+    std::vector<atmrt_host_tick> out;
+    if (list.is_null()) return out;
+    if (list.kind != Node::Seq) throw std::runtime_error("output." + what + ": expected a list");
+    for (const Node& n : list.seq) {
+        std::string tag;
+        const Node* body;
+        tagged(n, "output." + what + " entry", &tag, &body);
+        auto field = [&](const char* key) -> const Node& {
+            const Node* f = body->get(key);
+            if (!f || f->is_null()) throw std::runtime_error("output." + what + ": " + tag + " is missing field `" + key + "`");
+            return *f;
+        };
+        atmrt_host_tick t{};
+        if (tag == "Single")
+            t.multiple = 0, t.angle = field(single_key).as_double(single_key);
+        else if (tag == "Multiple")
+            t.multiple = 1, t.bias = field("bias").as_double("bias"), t.step = field("step").as_double("step");
+        else
+            throw std::runtime_error("output." + what + ": unknown variant " + tag + " (Single, Multiple)");
+        const double size = field("size").as_double("size");
+        if (!(size >= 0.0) || size > 4294967295.0 || size != std::floor(size)) throw std::runtime_error("output." + what + ": size must be a u32");
+        t.size = (uint32_t)size;
+        t.labelled = field("labelled").as_bool("labelled") ? 1 : 0;
+        out.push_back(t);
+    }
+    return out;
 }
 
 static void apply_yaml(const Node& doc, Config* c) {
@@ -541,12 +575,10 @@ static void apply_yaml(const Node& doc, Config* c) {
             else if (g->scalar == "InterpolatingRectilinear") c->generator = ATMRT_GENERATOR_INTERPOLATING_RECTILINEAR;
             else throw std::runtime_error("unknown generator " + g->scalar + " (Fast, Rectilinear, InterpolatingRectilinear)");
         }
-        for (const char* k : {"ticks", "vertical_ticks"})
-            if (const Node* t = out->get(k))
-                if (t->kind == Node::Seq && !t->seq.empty()) fprintf(stderr, "warning: output.%s is ignored (overlays are out of scope)\n", k);
-        for (const char* k : {"show_eye_level", "show_flat_horizon"})
-            if (const Node* t = out->get(k))
-                if (t->kind == Node::Scalar && t->as_bool(k)) fprintf(stderr, "warning: output.%s is ignored (overlays are out of scope)\n", k);
+        if (const Node* t = out->get("ticks")) c->ticks = parse_ticks(*t, "ticks", "azimuth");
+        if (const Node* t = out->get("vertical_ticks")) c->vertical_ticks = parse_ticks(*t, "vertical_ticks", "elevation");
+        if (const Node* t = out->get("show_eye_level")) c->show_eye_level = t->as_bool("show_eye_level");
+        if (const Node* t = out->get("show_flat_horizon")) c->show_flat_horizon = t->as_bool("show_flat_horizon");
     }
 }
 
@@ -802,12 +834,37 @@ extern "C" int atmrt_host_gen(int argc, const char* const* argv) {
         printf("%.3f: Done calculating (terrain %.2f ms, paths %.2f ms, march %.2f ms on the GPU; %llu ray steps, %llu pixels hit)\n", t(),
                st.ms_terrain, st.ms_paths, st.ms_march, (unsigned long long)st.ray_steps, (unsigned long long)st.pixels_hit);
         printf("%.3f: Outputting image...\n", t());
+        // ResultPixel.elevation_angle / azimuth (fast.rs:67-76, rectilinear.rs:78-116): the overlays and the sidecar read them
+        const bool overlays = !c.ticks.empty() || !c.vertical_ticks.empty() || c.show_eye_level || c.show_flat_horizon;
+        std::vector<double> el, az;
+        if (overlays || !c.file_metadata.empty()) {
+            el.resize(npix), az.resize(npix);
+            check(atmrt_group_pixel_angles(group, el.data(), az.data()), "atmrt_group_pixel_angles");
+        }
+        if (overlays) {  // renderer::output_image (renderer/mod.rs:416-431): ticks, flat horizon, eye level over the picture
+            atmrt_host_overlays ov{};
+            ov.ticks = c.ticks.data(), ov.nticks = (int32_t)c.ticks.size();
+            ov.vertical_ticks = c.vertical_ticks.data(), ov.nvertical_ticks = (int32_t)c.vertical_ticks.size();
+            ov.direction = c.direction, ov.fov = c.fov, ov.tilt = c.tilt;
+            ov.show_eye_level = c.show_eye_level;
+            const bool flat_shape = c.earth_model == ATMRT_EARTH_FLAT_DISTORTED || c.earth_model == ATMRT_EARTH_AZIMUTHAL_EQUIDISTANT ||
+                                    c.earth_model == ATMRT_EARTH_OBSERVER_AE;  // EarthModel::to_shape (earth_model/mod.rs:95-112)
+            if (c.show_flat_horizon && flat_shape && !c.straight_rays) {
+                atmrt_ctx* ctx0 = atmrt_group_context(group, 0);
+                double alt = 0.0, n = 1.0;
+                if (!ctx0 || atmrt_observer_altitude(ctx0, &alt) != 0 || atmrt_atmosphere_probe(ctx0, &alt, 1, nullptr, nullptr, &n) != 0)
+                    throw std::runtime_error(std::string("show_flat_horizon: ") + (ctx0 ? atmrt_last_error(ctx0) : "no context"));
+                ov.show_flat_horizon = 1;
+                atmrt_host_flat_horizon_elevation(n, &ov.flat_horizon_elevation);
+            }
+            if (atmrt_host_draw_overlays(rgb, p.width, p.height, el.data(), az.data(), &ov) != 0) throw std::runtime_error(g_error);
+            auto labelled = [](const atmrt_host_tick& tk) { return tk.labelled != 0; };
+            if (std::any_of(c.ticks.begin(), c.ticks.end(), labelled) || std::any_of(c.vertical_ticks.begin(), c.vertical_ticks.end(), labelled))
+                fprintf(stderr, "note: tick labels are drawn with a built-in bitmap face, not the reference's DejaVu Sans: label pixels differ\n");
+        }
         if (atmrt_host_write_png(c.file.c_str(), rgb, p.width, p.height, 3) != 0) throw std::runtime_error(g_error);
         if (!c.file_metadata.empty()) {
             printf("%.3f: Outputting metadata...\n", t());
-            // ResultPixel.elevation_angle / azimuth (fast.rs:67-76, rectilinear.rs:78-116)
-            std::vector<double> el(npix), az(npix);
-            check(atmrt_group_pixel_angles(group, el.data(), az.data()), "atmrt_group_pixel_angles");
             if (p.generator == ATMRT_GENERATOR_FAST) {  // separable: one elevation per row, one azimuth per column
                 std::vector<double> el_rows((size_t)p.height), az_cols(az.begin(), az.begin() + p.width);
                 for (int y = 0; y < p.height; ++y) el_rows[(size_t)y] = el[(size_t)y * p.width];
@@ -858,6 +915,24 @@ extern "C" int atmrt_host_parse_config(int argc, const char* const* argv, atmrt_
         put(terrain_folder, folder_cap, c.terrain_folder);
         put(output_file, file_cap, c.file);
         put(meta_file, meta_cap, c.file_metadata);
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(ATMRT_ERR_INVALID, e.what());
+    }
+}
+
+// Parse-only: the overlay keys of `output` (params.rs:403-410) as read_config lowers them.
+extern "C" int atmrt_host_parse_overlays(int argc, const char* const* argv, atmrt_host_tick* ticks, int max_ticks, int* nticks,
+                                         atmrt_host_tick* vertical_ticks, int max_vertical_ticks, int* nvertical_ticks, int* show_eye_level,
+                                         int* show_flat_horizon) {
+    try {
+        Config c = read_config(argc, argv);
+        if (nticks) *nticks = (int)c.ticks.size();
+        if (nvertical_ticks) *nvertical_ticks = (int)c.vertical_ticks.size();
+        for (int i = 0; ticks && i < max_ticks && i < (int)c.ticks.size(); ++i) ticks[i] = c.ticks[(size_t)i];
+        for (int i = 0; vertical_ticks && i < max_vertical_ticks && i < (int)c.vertical_ticks.size(); ++i) vertical_ticks[i] = c.vertical_ticks[(size_t)i];
+        if (show_eye_level) *show_eye_level = c.show_eye_level;
+        if (show_flat_horizon) *show_flat_horizon = c.show_flat_horizon;
         return 0;
     } catch (const std::exception& e) {
         return fail(ATMRT_ERR_INVALID, e.what());

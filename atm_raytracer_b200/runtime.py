@@ -69,6 +69,7 @@ def _load():
         "atmrt_group_destroy": (None, [vp]),
         "atmrt_group_last_error": (C.c_char_p, [vp]),
         "atmrt_group_size": (C.c_int, [vp]),
+        "atmrt_group_context": (vp, [vp, C.c_int]),
         "atmrt_group_column_block": (C.c_int, [vp, C.c_int, C.c_int, P(C.c_int), P(C.c_int)]),
         "atmrt_group_set_terrain": (C.c_int, [vp, P(abi.TileDesc), C.c_int, P(vp)]),
         "atmrt_group_set_params": (C.c_int, [vp, P(abi.Params)]),

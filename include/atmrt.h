@@ -256,7 +256,10 @@ int atmrt_set_objects(atmrt_ctx* ctx, const atmrt_object* objects, int nobjects,
  * iterations consumed per pixel. Copies are part of the call. */
 int atmrt_render(atmrt_ctx* ctx, uint8_t* rgb, atmrt_meta* meta, int32_t* steps, atmrt_stats* stats);
 /* Same, writing to caller-owned DEVICE buffers on `stream` (a cudaStream_t, may be NULL);
- * asynchronous unless stats != NULL (stats requires the stage timings, so it synchronises). */
+ * asynchronous unless stats != NULL (stats requires the stage timings, so it synchronises).
+ * Every render of a context works in the context's caches, flags and counters: the library orders a render behind the
+ * previous atmrt_render_device of the same context even when the two are given different streams (an event wait), so
+ * renders of ONE context never overlap -- use one context per concurrent render. Still one host thread per context. */
 int atmrt_render_device(atmrt_ctx* ctx, void* rgb_dev, void* meta_dev, void* steps_dev,
                         atmrt_stats* stats, void* stream);
 /* Harvest the per-stage CUDA-event timings of every render issued since the last call (the renders
@@ -340,6 +343,9 @@ int atmrt_group_create(const int* devices /* NULL: 0..n-1 */, int n, atmrt_group
 void atmrt_group_destroy(atmrt_group* g);
 const char* atmrt_group_last_error(const atmrt_group* g); /* g may be NULL: last create() error */
 int atmrt_group_size(const atmrt_group* g);
+/* Context i of the group (owned by the group; NULL when out of range): for the per-context probes -- atmrt_observer_altitude,
+ * atmrt_atmosphere_probe, atmrt_get_path ... -- after a group render. Do not set params / terrain / objects through it. */
+atmrt_ctx* atmrt_group_context(atmrt_group* g, int i);
 int atmrt_group_column_block(const atmrt_group* g, int width, int i, int* x0, int* x1);
 int atmrt_group_set_terrain(atmrt_group* g, const atmrt_tile_desc* tiles, int ntiles, const int16_t* const* posts);
 int atmrt_group_set_params(atmrt_group* g, const atmrt_params* params);

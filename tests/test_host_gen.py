@@ -251,3 +251,55 @@ def test_gen_executable_end_to_end(tmp_path, ctx):
         got = lists[first[y, x]:first[y, x] + kept[y, x]]
         for f in ("lat", "lon", "distance", "elevation", "path_length", "is_terrain", "step"):
             np.testing.assert_array_equal(got[f], pts[f][y, x, :kept[y, x]])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_gen_executable_draws_the_overlays(tmp_path, ctx, oracle_lib, gpus):
+    """`gen` with output.ticks / vertical_ticks / show_eye_level / show_flat_horizon (renderer::output_image,
+    renderer/mod.rs:416-431) == the plain render + the oracle's restatement of the overlays on the oracle's ResultPixel angles,
+    the flat-earth horizon at acos(1 / n) of the oracle's atmosphere at the observer's altitude."""
+    import torch
+    from atm_raytracer_b200 import runtime
+    from oracle import overlays as ref
+
+    if gpus > torch.cuda.device_count():
+        pytest.skip("needs two GPUs")
+    folder = tmp_path / "terrain"
+    folder.mkdir()
+    synth.write_tile_grid(str(folder), 45, 5, 1, 2, level=0)
+    conf = tmp_path / "c.yaml"
+    conf.write_text("view:\n  position: {latitude: 45.4, longitude: 5.9, altitude: {Absolute: 1200.0}}\n"
+                    "  frame: {direction: 80.0, tilt: -1.0, fov: 40.0, max_distance: 60000.0}\n"
+                    "earth_shape: FlatDistorted\n"
+                    "output:\n  width: 240\n  height: 140\n  show_eye_level: true\n  show_flat_horizon: true\n"
+                    "  ticks:\n    - Multiple: {bias: 0, step: 10, size: 10, labelled: true}\n    - Multiple: {bias: 0, step: 2, size: 5, labelled: false}\n"
+                    "    - Single: {azimuth: 75.5, size: 15, labelled: true}\n"
+                    "  vertical_ticks:\n    - Multiple: {bias: 0, step: 5, size: 8, labelled: true}\n    - Multiple: {bias: 0, step: 1, size: 4, labelled: false}\n")
+    png = tmp_path / "out.png"
+    argv = ["-c", str(conf), "-t", str(folder), "--output", str(png), "--step", "100"]
+    r = subprocess.run([host.EXECUTABLE, "gen"] + argv + ["--gpus", str(gpus)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "built-in bitmap face" in r.stderr and "ignored" not in r.stderr
+    img = host.read_png(str(png))[..., :3]
+
+    cfg = config.read_config(argv)
+    params = config.into_params(cfg)
+    terrain = runtime.Terrain.from_folder(str(folder))
+    want = runtime.FastGenerator(params, terrain, [], [], context=ctx).generate()["rgb"].copy()
+    plain = want.copy()
+    el, az = oracle_lib.pixel_angles(params)
+    _, _, n = oracle_lib.atmosphere(params.atmosphere, params.wavelength, np.array([1200.0]))
+    ticks, vticks, eye, flat = host.parse_overlays(argv)
+    assert eye and flat and len(ticks) == 3 and len(vticks) == 2
+    labels = ref.output_overlays(want, el.tolist(), az.tolist(), ticks, vticks, dict(direction=80.0, fov=40.0, tilt=-1.0), show_eye_level=True,
+                                 flat_horizon_elev=ref.flat_horizon_elevation(float(n[0])))
+    boxes = np.zeros(img.shape[:2], bool)
+    for x, y, text in labels:
+        boxes[max(y, 0):max(y + 15, 0), max(x, 0):max(x + 8 * len(text) + 2, 0)] = True
+    assert len(labels) >= 6 and boxes.mean() < 0.2
+    np.testing.assert_array_equal(img[~boxes], want[~boxes])
+    drawn = (want != plain).any(axis=2)
+    assert (want[drawn] == [255, 128, 255]).all(axis=1).sum() >= 200  # the eye-level line crosses the picture
+    assert (want[drawn] == [0, 128, 255]).all(axis=1).sum() >= 200    # so does the flat-earth horizon, 1.3 degrees above it
+    assert ((img != want).any(axis=2) & boxes).any()                   # and the labels left glyphs
