@@ -253,7 +253,9 @@ int atmrt_set_objects(atmrt_ctx* ctx, const atmrt_object* objects, int nobjects,
 
 /* ---- render (replaces FastGenerator::generate + renderer::draw_image) -------------------- */
 /* Host buffers (any may be NULL): rgb[H][x1-x0][3], meta[H][x1-x0], steps[H][x1-x0] = zip
- * iterations consumed per pixel. Copies are part of the call. */
+ * iterations consumed per pixel. Copies are part of the call. The rows leave the device in bands while the sweep is still
+ * working on the rows above them; that overlap needs PAGE-LOCKED buffers (atmrt_host_alloc, or cudaHostRegister'ed memory):
+ * into pageable memory every band copy is host-synchronous and the call is as correct, but serial. */
 int atmrt_render(atmrt_ctx* ctx, uint8_t* rgb, atmrt_meta* meta, int32_t* steps, atmrt_stats* stats);
 /* Same, writing to caller-owned DEVICE buffers on `stream` (a cudaStream_t, may be NULL);
  * asynchronous unless stats != NULL (stats requires the stage timings, so it synchronises).
