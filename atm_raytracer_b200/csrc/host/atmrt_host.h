@@ -15,6 +15,15 @@ extern "C" {
 /* read_dted_header / read_dted: bit-exact decode of a DTED file (MIL-PRF-89020B): big-endian
  * signed-magnitude posts, [lon line][lat point]. posts == NULL reads only the header. */
 int atmrt_host_read_dted(const char* path, atmrt_tile_desc* desc, int16_t* posts, size_t capacity);
+/* GeoTIFF terrain tiles (terrain/geotiff.rs; external crate geotiff-rs 0.1 for the pixels): the key and the south-west corner
+ * come from the FILE NAME -- the first (N|S)(\d+)(E|W)(\d+) in it (geotiff.rs:16-31) -- and the tile becomes 3601 x 3601 posts
+ * one arc-second apart, [lon line][lat point] west->east, south->north like a DTED tile, which DtedData::get_elev then samples
+ * exactly as GeoTiffWrapper::get_elev does (geotiff.rs:62-99). posts == NULL reads only the descriptor. Classic TIFF, strips
+ * or tiles, 8/16/32-bit integers, none / PackBits / LZW / Deflate, predictor 2; samples must fit i16. */
+int atmrt_host_geotiff_coords_from_name(const char* path, int* lat, int* lon);
+int atmrt_host_read_geotiff(const char* path, atmrt_tile_desc* desc, int16_t* posts, size_t capacity);
+/* TerrainDataInner::read_tile / Terrain::buffer_file (terrain/mod.rs:23-31, 85-118): DTED first, GeoTIFF second. */
+int atmrt_host_read_tile(const char* path, atmrt_tile_desc* desc, int16_t* posts, size_t capacity);
 /* RGB8 or RGBA8 PNG writer/reader on zlib (channels = 3 or 4). */
 int atmrt_host_write_png(const char* path, const uint8_t* pixels, int width, int height, int channels);
 int atmrt_host_read_png(const char* path, uint8_t* rgba, size_t capacity, int* width, int* height);

@@ -770,13 +770,14 @@ static HostTerrain load_terrain_folder(const std::string& folder) {
     for (const std::string& n : names) {
         std::string path = folder + "/" + n;
         atmrt_tile_desc d{};
-        if (atmrt_host_read_dted(path.c_str(), &d, nullptr, 0) != 0) throw std::runtime_error("Could not buffer terrain file " + path);
+        // DTED by its header, else GeoTIFF by its name (Terrain::buffer_file, terrain/mod.rs:113-118)
+        if (atmrt_host_read_tile(path.c_str(), &d, nullptr, 0) != 0) throw std::runtime_error("Could not buffer terrain file " + path + " (" + g_error + ")");
         const size_t np = (size_t)d.nlon * d.nlat;
         int16_t* buf = (int16_t*)atmrt_host_alloc(np * sizeof(int16_t));
         if (!buf) throw std::runtime_error("cannot allocate page-locked memory for " + path);
         t.descs.push_back(d);
         t.posts.push_back(buf);
-        if (atmrt_host_read_dted(path.c_str(), &d, buf, np) != 0) throw std::runtime_error(g_error);
+        if (atmrt_host_read_tile(path.c_str(), &d, buf, np) != 0) throw std::runtime_error(g_error);
     }
     printf("Detected %zu terrain files\n", names.size());
     return t;
