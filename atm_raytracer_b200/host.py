@@ -20,6 +20,11 @@ def _load():
     lib = C.CDLL(HOST_LIB_PATH)
     lib.atmrt_host_read_dted.restype = C.c_int
     lib.atmrt_host_read_dted.argtypes = [C.c_char_p, C.POINTER(abi.TileDesc), C.c_void_p, C.c_size_t]
+    for fn in (lib.atmrt_host_read_geotiff, lib.atmrt_host_read_tile):
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_char_p, C.POINTER(abi.TileDesc), C.c_void_p, C.c_size_t]
+    lib.atmrt_host_geotiff_coords_from_name.restype = C.c_int
+    lib.atmrt_host_geotiff_coords_from_name.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.atmrt_host_write_png.restype = C.c_int
     lib.atmrt_host_write_png.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.atmrt_host_read_png.restype = C.c_int
@@ -84,6 +89,33 @@ def read_dted(path):
     posts = np.empty((d.nlon, d.nlat), dtype=np.int16)
     _check(lib.atmrt_host_read_dted(os.fsencode(path), C.byref(d), posts.ctypes.data_as(C.c_void_p), posts.size))
     return d, posts
+
+
+def _read_posts(fn, path):
+    d = abi.TileDesc()
+    _check(fn(os.fsencode(path), C.byref(d), None, 0))
+    posts = np.empty((d.nlon, d.nlat), dtype=np.int16)
+    _check(fn(os.fsencode(path), C.byref(d), posts.ctypes.data_as(C.c_void_p), posts.size))
+    return d, posts
+
+
+def read_geotiff(path):
+    """(TileDesc, int16 posts [3601][3601]) of a GeoTIFF tile (terrain/geotiff.rs): key and corner from the file name, posts
+    [lon line][lat point] west->east, south->north, one arc-second apart."""
+    return _read_posts(lib.atmrt_host_read_geotiff, path)
+
+
+def read_tile(path):
+    """TerrainDataInner::read_tile (terrain/mod.rs:23-31): a DTED tile if the header reads as one, else a GeoTIFF tile."""
+    return _read_posts(lib.atmrt_host_read_tile, path)
+
+
+def geotiff_coords_from_name(path):
+    """GeoTiffWrapper::coords_from_name (terrain/geotiff.rs:16-31): (lat, lon) or None."""
+    lat, lon = C.c_int(), C.c_int()
+    if lib.atmrt_host_geotiff_coords_from_name(os.fsencode(path), C.byref(lat), C.byref(lon)) != 0:
+        return None
+    return lat.value, lon.value
 
 
 def write_png(path, pixels):

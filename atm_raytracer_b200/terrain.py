@@ -41,13 +41,13 @@ class Terrain:
 
     @classmethod
     def from_folder(cls, folder):
-        """``Terrain::from_folder`` (terrain/mod.rs:66-83): every entry must be a DTED file."""
+        """``Terrain::from_folder`` (terrain/mod.rs:66-83): every entry must be a DTED or a GeoTIFF tile."""
         from . import host
 
         tiles = []
         names = sorted(os.listdir(folder))
         for name in names:
-            tiles.append(host.read_dted(os.path.join(folder, name)))
+            tiles.append(host.read_tile(os.path.join(folder, name)))
         print(f"Detected {len(names)} terrain files")
         return cls(tiles)
 
