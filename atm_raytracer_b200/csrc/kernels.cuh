@@ -1399,6 +1399,8 @@ struct CrossPixel {
     PixelState st;
     int nlim;    // steps of the ray inside the terrain profile
     int done_k;  // the step the pixel finished at, -1 while it is live
+    double pad_; // 72 bytes, not 64: lanes work on adjacent rows of the band in shared memory, and a stride of 16 words puts
+                 // every second row on the same banks (2/3 of the kernel's shared-memory wavefronts were conflicts)
 };
 
 // Can the segment pos1 -> pos2 touch object o at all? Every point Frustum / Billboard::check_collision returns lies
@@ -2248,12 +2250,15 @@ __global__ void __launch_bounds__(128, 8) k_hit_normals(const __grid_constant__ 
 // (fogged) colour of its trace point, and a pixel without one is add([0,0,0], default, 1.0) == default.
 constexpr int TILE_COLS = 8;
 
-__global__ void __launch_bounds__(32 * TILE_COLS, 4) k_shade_tiles(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, SweepLists L, int row0,
+__global__ void __launch_bounds__(32 * TILE_COLS, 6) k_shade_tiles(const __grid_constant__ DevScene S, DevBuffers B, MarchOut O, SweepLists L, int row0,
                                                                    int count) {
     if (B.sweep_flags[0] != 0) return;
-    __shared__ double s_meta[32][TILE_COLS * 4];
-    __shared__ __align__(16) unsigned char s_rgb[32][TILE_COLS * 3];
-    __shared__ int s_steps[32][TILE_COLS];
+    // staging rows padded: a warp stages 32 ROWS of one column, so the row stride decides the banks -- 32 doubles put every lane
+    // of a store on one bank (32 wavefronts per store); 34 doubles (16-byte aligned rows for the double2 read-out) spread them
+    // over 8 bank pairs, 7 words of colour and 9 of steps over all 32 banks
+    __shared__ __align__(16) double s_meta[32][TILE_COLS * 4 + 2];
+    __shared__ __align__(16) unsigned char s_rgb[32][TILE_COLS * 3 + 4];
+    __shared__ int s_steps[32][TILE_COLS + 1];
     __shared__ unsigned char s_skip[TILE_COLS];
     __shared__ unsigned long long s_cnt[TILE_COLS];
     __shared__ unsigned s_hits[TILE_COLS];
