@@ -460,8 +460,51 @@ class FastGenerator:
         return self.ctx.render(**kw)
 
 
-def output_image(rgb, path):
-    """``renderer::output_image`` tail (renderer/mod.rs:433-436): save the RGB8 image as PNG."""
+def overlay_ticks(entries, single_key):
+    """``Vec<Tick>`` / ``Vec<VerticalTick>`` of the YAML (params.rs:325-385) as the host's tick dictionaries."""
+    from .config import ConfigError, _tagged
+
+    out = []
+    for e in entries or []:
+        kind, body = _tagged(e, "tick")
+        body = body or {}
+        try:
+            if kind == "Single":
+                t = dict(kind="Single", angle=float(body[single_key]))
+            elif kind == "Multiple":
+                t = dict(kind="Multiple", bias=float(body["bias"]), step=float(body["step"]))
+            else:
+                raise ConfigError(f"unknown tick variant {kind} (Single, Multiple)")
+            t["size"], t["labelled"] = int(body["size"]), bool(body["labelled"])
+        except KeyError as k:  # serde has no defaults for these fields
+            raise ConfigError(f"tick {kind} is missing field {k}") from None
+        out.append(t)
+    return out
+
+
+def output_image(rgb, path, cfg=None, context=None):
+    """``renderer::output_image`` (renderer/mod.rs:416-437): the overlays the configuration asks for -- ticks, the flat-earth
+    horizon, the eye-level line -- drawn over ``rgb`` (in place) by the host library, then the PNG. ``cfg``: the dictionary of
+    ``config.read_config``; ``context``: the Context (or Group context 0) that rendered ``rgb`` -- the overlays read its
+    ``ResultPixel`` angles, the flat horizon its observer altitude and atmosphere. Without ``cfg`` only the PNG is written."""
     from . import host
 
+    out = (cfg or {}).get("output", {})
+    ticks, vticks = overlay_ticks(out.get("ticks"), "azimuth"), overlay_ticks(out.get("vertical_ticks"), "elevation")
+    eye, flat = bool(out.get("show_eye_level")), bool(out.get("show_flat_horizon"))
+    if ticks or vticks or eye or flat:
+        if context is None:
+            raise ValueError("output_image: the overlays need the context that rendered the image")
+        from .config import _tagged
+
+        el, az = context.pixel_angles()
+        frame = cfg["view"]["frame"]
+        shape, _ = _tagged(cfg.get("earth_shape", "SimpleSphere"), "earth_shape")
+        flat_elev = None
+        # show_flat_horizon && shape == Flat && !straight_rays (renderer/mod.rs:420-427; to_shape: earth_model/mod.rs:95-112)
+        if flat and shape in ("FlatDistorted", "AzimuthalEquidistant", "ObserverAe", "SimpleObserverAe") and not cfg.get("straight_rays"):
+            _, _, n = context.atmosphere_probe(np.array([context.observer_altitude()]))
+            flat_elev = host.flat_horizon_elevation(float(n[0]))
+        host.draw_overlays(rgb, el, az, ticks, vticks, dict(direction=float(frame["direction"]), fov=float(frame["fov"]), tilt=float(frame["tilt"])),
+                           show_eye_level=eye, flat_horizon_elev=flat_elev)
     host.write_png(path, rgb)

@@ -303,3 +303,7 @@ def test_gen_executable_draws_the_overlays(tmp_path, ctx, oracle_lib, gpus):
     assert (want[drawn] == [255, 128, 255]).all(axis=1).sum() >= 200  # the eye-level line crosses the picture
     assert (want[drawn] == [0, 128, 255]).all(axis=1).sum() >= 200    # so does the flat-earth horizon, 1.3 degrees above it
     assert ((img != want).any(axis=2) & boxes).any()                   # and the labels left glyphs
+    # the Python mirror of output_image draws the same picture from the same configuration
+    mirror = tmp_path / "mirror.png"
+    runtime.output_image(plain.copy(), str(mirror), cfg, ctx)
+    np.testing.assert_array_equal(host.read_png(str(mirror))[..., :3], img)

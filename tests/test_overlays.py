@@ -190,6 +190,15 @@ def test_yaml_overlay_keys(tmp_path):
     assert [(t["kind"], t["angle"], t["size"], t["labelled"]) for t in vticks] == [("Single", -1.5, 7, True)]
     assert eye and not flat
     assert host.parse_overlays([]) == ([], [], False, False)  # Output::default (params.rs:432-444)
+    # the Python mirror lowers the same YAML to the same ticks
+    from atm_raytracer_b200 import config, runtime
+
+    out = config.read_config(["-c", str(cfg)])["output"]
+    strip = lambda ts: [{k: v for k, v in t.items() if not (k == "angle" and t["kind"] == "Multiple") and not (k in ("bias", "step") and t["kind"] == "Single")} for t in ts]
+    assert runtime.overlay_ticks(out["ticks"], "azimuth") == strip(ticks)
+    assert runtime.overlay_ticks(out["vertical_ticks"], "elevation") == strip(vticks)
+    with pytest.raises(config.ConfigError):
+        runtime.overlay_ticks([{"Single": {"azimuth": 1.0, "size": 3}}], "azimuth")
 
 
 @pytest.mark.parametrize("bad", ["- Single: {azimuth: 1, size: 3}", "- Triple: {azimuth: 1, size: 3, labelled: true}",
