@@ -2014,6 +2014,10 @@ struct SweepLists {
     int split;        // or, when > 0: two bands, rows [0, split) and [split, height) (a multiple of 32)
 };
 __host__ __device__ __forceinline__ int sweep_band_of_row(const SweepLists& L, int y) { return L.split > 0 ? (y >= L.split ? 1 : 0) : y / L.band_rows; }
+// The hit plane holds, per pixel, 1 + the slot of its first-hit step in the band's list (0: no hit) -- and, when both fit 16 bits,
+// the step itself above it: (step << 16) | (slot + 1). The shading then has the step after ONE dependent load instead of two
+// (hit plane -> list -> caches was the chain that bound it). Warp-uniform, the same in the sweep and in its readers.
+__device__ __forceinline__ bool sweep_hit_packed(const DevScene& S, const SweepLists& L) { return S.n_t <= 32767 && L.cap <= 65535; }
 
 // predicated global stores (no branch): the sweep's control flow is warp-uniform, only lane 0 writes
 __device__ __forceinline__ void st_if_s32(int* p, int v, bool ok) {
@@ -2043,7 +2047,8 @@ __global__ void __launch_bounds__(32 * BITS_WARPS, 8) k_sweep_bits(const __grid_
     const int y_lo = SPLIT ? (band ? L.split : 0) : band * L.band_rows;
     const int y_hi = (SPLIT ? (band ? S.height : L.split) : min(S.height, y_lo + L.band_rows)) - 1;
     const double* __restrict__ te = B.t_elev + (size_t)xl * S.n_pad;
-    int* __restrict__ hit = B.sweep_hit + (size_t)xl * S.h_pad;  // per pixel: 1 + the slot of its first-hit step in the band's list (0: no hit)
+    int* __restrict__ hit = B.sweep_hit + (size_t)xl * S.h_pad;  // per pixel: 1 + the slot of its first-hit step in the band's list (0: no hit), the step above it (sweep_hit_packed)
+    const int hit_mul = sweep_hit_packed(S, L) ? 65536 : 0;
     int* const list = L.list + ((size_t)xl * L.bands + band) * L.cap;
     const int n_t = S.n_t, k_last = n_t - 1;
     static_assert(SWEEP_ROWS == PATH_ROWS && SWEEP_ROWS == 4, "the sweep reads one row group of the path cache per 32-byte load");
@@ -2124,7 +2129,7 @@ __global__ void __launch_bounds__(32 * BITS_WARPS, 8) k_sweep_bits(const __grid_
 #define ATMRT_BITS_ROW(C, R, LEN, HOUT)                                                                          \
     if (R <= rmax) {                                                                                             \
         if ((same >> R) & 1u) {                                                                                  \
-            HOUT = cnt; /* the same step, the same slot */                                                       \
+            HOUT = last * hit_mul + cnt; /* the same step, the same slot */                                      \
         } else {                                                                                                 \
             const int nlim = min(n_t, LEN);                                                                      \
             int adv = 0; /* windows this row has moved on without a hit */                                       \
@@ -2154,7 +2159,7 @@ __global__ void __launch_bounds__(32 * BITS_WARPS, 8) k_sweep_bits(const __grid_
                         st_if_s32(lp, kh, lane0 && new1);                                                        \
                         lp += new1 ? 1 : 0, cnt += new1 ? 1 : 0;                                                 \
                         last = kh;                                                                               \
-                        HOUT = cnt; /* 1 + slot of kh */                                                         \
+                        HOUT = kh * hit_mul + cnt; /* 1 + slot of kh (and kh) */                                 \
                         lo = hl;    /* the row above continues from the same step */                             \
                         same = __shfl_sync(FULL, m4, hl);                                                        \
                         break;                                                                                   \
@@ -2271,7 +2276,9 @@ __global__ void __launch_bounds__(32 * TILE_COLS, 6) k_shade_tiles(const __grid_
     if (lane == 0) s_skip[w] = col_ok ? 0 : 1;
     const int xx = min(xl, wl - 1), yy = min(y, S.height - 1);
     const int nlim = min(n_t, B.p_n[yy]);
-    const int slot1 = active ? B.sweep_hit[(size_t)xx * S.h_pad + yy] : 0;
+    const bool packed = sweep_hit_packed(S, L);
+    const int hv = active ? B.sweep_hit[(size_t)xx * S.h_pad + yy] : 0;
+    const int slot1 = packed ? hv & 0xffff : hv;
     const bool hit = slot1 > 0;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     Rgb8 px{{S.shade.def_color[0], S.shade.def_color[1], S.shade.def_color[2]}};
@@ -2280,7 +2287,7 @@ __global__ void __launch_bounds__(32 * TILE_COLS, 6) k_shade_tiles(const __grid_
     if (hit) {
         const int s = slot1 - 1;
         const size_t seg = ((size_t)xx * L.bands + sweep_band_of_row(L, yy)) * L.cap;  // the lists of this pixel's band
-        const int kh = L.list[seg + s];
+        const int kh = packed ? hv >> 16 : L.list[seg + s];
         const double* __restrict__ nr = L.normals + (seg + s - 1) * 3;  // slots s - 1, s: samples kh - 1, kh
         const V3 n0{nr[0], nr[1], nr[2]}, n1{nr[3], nr[4], nr[5]};
         const size_t ti = (size_t)xx * S.n_pad + kh;
@@ -2358,6 +2365,7 @@ __global__ void __launch_bounds__(256) k_count_swept(const __grid_constant__ Dev
     __shared__ unsigned long long s_steps[8];
     __shared__ unsigned s_hits[8];
     const int wl = S.x1 - S.x0, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool packed = sweep_hit_packed(S, L);
     const int xl = blockIdx.x * 8 + w;  // a warp per column, a block per eight columns: one set of atomics per block
     unsigned long long steps = 0ull;
     unsigned hits = 0u;
@@ -2365,9 +2373,10 @@ __global__ void __launch_bounds__(256) k_count_swept(const __grid_constant__ Dev
         const int* __restrict__ hit = B.sweep_hit + (size_t)xl * S.h_pad;
         for (int y = row0 + lane; y < row1; y += 32) {
             const int nlim = min(S.n_t, B.p_n[y]);
-            const int slot1 = hit[y];
+            const int hv = hit[y];
+            const int slot1 = packed ? hv & 0xffff : hv;
             if (slot1 > 0) {
-                steps += (unsigned long long)L.list[((size_t)xl * L.bands + sweep_band_of_row(L, y)) * L.cap + slot1 - 1];
+                steps += (unsigned long long)(packed ? hv >> 16 : L.list[((size_t)xl * L.bands + sweep_band_of_row(L, y)) * L.cap + slot1 - 1]);
                 hits += 1u;
             } else {
                 steps += (unsigned long long)(nlim > 0 ? nlim - 1 : 0);
