@@ -22,7 +22,7 @@ def raster(seed, lo=-400, hi=4500):
 
 
 def write_pillow(path, a, compression, predictor=None):
-    from PIL import Image
+    Image = pytest.importorskip("PIL.Image")  # libtiff through Pillow: the independent encoder
 
     im = Image.fromarray(a.view(np.uint16))  # mode I;16; SampleFormat 2 marks the samples as two's complement
     info = {339: 2}
