@@ -205,3 +205,37 @@ def test_device_samples_a_geotiff_tile_like_the_wrapper(tmp_path, picture, ctx):
     rows = picture.tolist()
     want = np.array([ref.get_elev(rows, -3.0, -71.0, float(a), float(b)) if (np.floor(a), np.floor(b)) == (-3.0, -71.0) else np.nan for a, b in zip(lat, lon)])
     assert np.isnan(want).sum() == 3 and np.array_equal(got, want, equal_nan=True)
+
+
+def test_damaged_files_are_refused_not_crashed_on(tmp_path, picture):
+    """Truncated and bit-flipped TIFFs (LZW strips, deflate tiles): the reader answers with an error or with a tile, never
+    with a crash -- every offset, count and code of the file is checked before it is used."""
+    good = {}
+    write_pillow(str(tmp_path / "N20E020.tif"), picture, "tiff_lzw", 2)
+    good["lzw"] = (tmp_path / "N20E020.tif").read_bytes()
+    write_minimal(str(tmp_path / "N20E020.tif"), picture, tile=512, deflate=True)
+    good["tiles"] = (tmp_path / "N20E020.tif").read_bytes()
+    rng = np.random.default_rng(12)
+    path = tmp_path / "N21E021.tif"
+    outcomes = set()
+    for kind, data in good.items():
+        n = len(data)
+        for trial in range(10):
+            b = bytearray(data)
+            if trial < 3:
+                b = b[: int(n * rng.random())]  # truncated
+            elif trial < 7:
+                for pos in rng.integers(0, n, 40):  # noise anywhere (mostly in the compressed data)
+                    b[pos] ^= 1 << int(rng.integers(0, 8))
+            else:
+                ifd = struct.unpack("<I", data[4:8])[0]  # noise in the directory: tags, types, counts, offsets
+                for pos in rng.integers(ifd, min(ifd + 200, n), 6):
+                    b[pos] = int(rng.integers(0, 256))
+            path.write_bytes(bytes(b))
+            try:
+                d, posts = host.read_geotiff(str(path))
+                assert posts.shape == (N, N)
+                outcomes.add("read")
+            except host.HostError:
+                outcomes.add("refused")
+    assert "refused" in outcomes
