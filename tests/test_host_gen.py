@@ -307,3 +307,17 @@ def test_gen_executable_draws_the_overlays(tmp_path, ctx, oracle_lib, gpus):
     mirror = tmp_path / "mirror.png"
     runtime.output_image(plain.copy(), str(mirror), cfg, ctx)
     np.testing.assert_array_equal(host.read_png(str(mirror))[..., :3], img)
+
+
+def test_example_configuration_parses_the_same_in_both_hosts():
+    """examples/panorama.yaml: every key of the schema, through the C++ YAML-subset parser and through PyYAML."""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "panorama.yaml")
+    p_cpp, objs, folder, out, meta = host.parse_config(["-c", path])
+    cfg = config.read_config(["-c", path])
+    _same_params(p_cpp, config.into_params(cfg))
+    assert (len(objs), folder, out, meta) == (2, "./terrain", "./panorama.png", "")
+    from atm_raytracer_b200 import runtime
+
+    ticks, vticks, eye, flat = host.parse_overlays(["-c", path])
+    assert (len(ticks), len(vticks), eye, flat) == (3, 1, True, False)
+    assert [t["size"] for t in runtime.overlay_ticks(cfg["output"]["ticks"], "azimuth")] == [12, 5, 18]
