@@ -239,3 +239,29 @@ def test_damaged_files_are_refused_not_crashed_on(tmp_path, picture):
             except host.HostError:
                 outcomes.add("refused")
     assert "refused" in outcomes
+
+
+@pytest.mark.gpu
+def test_gen_renders_from_a_folder_with_a_geotiff_tile(tmp_path, picture, ctx):
+    """`atm-raytracer gen` on a folder holding a GeoTIFF tile and DTED tiles == the library driven through the Python mirror on
+    Terrain.from_folder of the same folder (Terrain::from_folder / buffer_file, terrain/mod.rs:66-118)."""
+    import subprocess
+
+    from atm_raytracer_b200 import config, runtime
+
+    folder = tmp_path / "terrain"
+    folder.mkdir()
+    synth.write_tile_grid(str(folder), 45, 5, 1, 2, level=0)           # DTED: (45, 5), (45, 6)
+    write_pillow(str(folder / "srtm_N46E005.tif"), picture, "tiff_lzw", 2)  # GeoTIFF: (46, 5), 3601 x 3601
+    png = tmp_path / "out.png"
+    argv = ["-t", str(folder), "--output", str(png), "-l", "45.9", "-g", "5.5", "-a", "3000", "-d", "10", "-f", "50", "-m", "60", "--step", "100",
+            "-w", "320", "-h", "200", "-i", "-8"]
+    r = subprocess.run([host.EXECUTABLE, "gen"] + argv, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Detected 3 terrain files" in r.stdout
+    img = host.read_png(str(png))[..., :3]
+    t = terrain.Terrain.from_folder(str(folder))
+    want = runtime.FastGenerator(config.into_params(config.read_config(argv)), t, [], [], context=ctx).generate()
+    np.testing.assert_array_equal(img, want["rgb"])
+    north = np.isfinite(want["meta"]["lat"]) & (want["meta"]["lat"] > 46.0)
+    assert north.mean() > 0.05  # the picture does look onto the GeoTIFF tile
