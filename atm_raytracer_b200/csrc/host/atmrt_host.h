@@ -28,6 +28,9 @@ int atmrt_host_read_tile(const char* path, atmrt_tile_desc* desc, int16_t* posts
 int atmrt_host_write_png(const char* path, const uint8_t* pixels, int width, int height, int channels);
 int atmrt_host_read_png(const char* path, uint8_t* rgba, size_t capacity, int* width, int* height);
 const char* atmrt_host_last_error(void);
+/* The writer of the metadata sidecar, on its own (tests): gzip as a series of members compressed on `threads` host threads
+ * (0: all), block_bytes of input per member (0: 4 MiB). */
+int atmrt_host_gzip_write(const char* path, const void* data, size_t bytes, size_t block_bytes, int threads);
 /* The overlays renderer::output_image draws over the finished picture (renderer/mod.rs:22-365, 416-431): ticks with
  * labels, the flat-earth horizon line, the eye-level line. Tick / VerticalTick (params.rs:325-385) as one POD. */
 typedef struct atmrt_host_tick {

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "atmrt_host.h"
+#include "pgzip.h"
 #include "../../../include/atmrt_fmt.h"
 
 namespace atmrt_host {
@@ -714,32 +715,26 @@ static bool write_metadata(const std::string& path, const atmrt_params& p, const
     //   i32 max_points, i32 counts[height][width] (true counts), then per pixel min(count, max_points) records of
     //   atmrt_trace_point (include/atmrt.h: lat, lon, distance, elevation, path_length, normal[3], color[4] as f64,
     //   i32 is_terrain, i32 step) -- ResultPixel.trace_points (generators/mod.rs:18-30)
-    gzFile f = gzopen(path.c_str(), "wb6");
-    if (!f) return false;
+    // (a series of gzip members compressed on all host threads -- pgzip.h; any gzip reader sees one stream)
+    ParallelGzip z(path);
+    if (!z.ok()) return false;
     const bool lists = counts && points;
     const char* magic = lists ? "ATMRTMETA3\n" : "ATMRTMETA2\n";
     int32_t hdr[4] = {p.width, p.height, p.generator, 0};
-    bool ok = gzwrite(f, magic, 11) > 0 && gzwrite(f, hdr, sizeof hdr) > 0;
-    auto put = [&](const char* data, size_t left) {
-        while (ok && left > 0) {
-            unsigned chunk = (unsigned)std::min<size_t>(left, 1u << 30);
-            ok = gzwrite(f, data, chunk) == (int)chunk;
-            data += chunk, left -= chunk;
-        }
-    };
-    put((const char*)elevation_angle.data(), elevation_angle.size() * sizeof(double));
-    put((const char*)azimuth.data(), azimuth.size() * sizeof(double));
-    put((const char*)meta, npix * sizeof(atmrt_meta));
+    z.put(magic, 11), z.put(hdr, sizeof hdr);
+    z.put(elevation_angle.data(), elevation_angle.size() * sizeof(double));
+    z.put(azimuth.data(), azimuth.size() * sizeof(double));
+    z.put(meta, npix * sizeof(atmrt_meta));
     if (lists) {
         const int32_t mp = max_points;
-        put((const char*)&mp, sizeof mp);
-        put((const char*)counts->data(), npix * sizeof(int32_t));
-        for (size_t i = 0; i < npix && ok; ++i) {
+        z.put(&mp, sizeof mp);
+        z.put(counts->data(), npix * sizeof(int32_t));
+        for (size_t i = 0; i < npix && z.ok(); ++i) {
             const size_t n = (size_t)std::min<int32_t>((*counts)[i], max_points);
-            if (n) put((const char*)(points->data() + i * (size_t)max_points), n * sizeof(atmrt_trace_point));
+            if (n) z.put(points->data() + i * (size_t)max_points, n * sizeof(atmrt_trace_point));
         }
     }
-    return gzclose(f) == Z_OK && ok;
+    return z.close();
 }
 
 // Terrain::from_folder (terrain/mod.rs:66-83): every entry of the folder must be a terrain file; decoded on the host.

@@ -25,6 +25,8 @@ def _load():
         fn.argtypes = [C.c_char_p, C.POINTER(abi.TileDesc), C.c_void_p, C.c_size_t]
     lib.atmrt_host_geotiff_coords_from_name.restype = C.c_int
     lib.atmrt_host_geotiff_coords_from_name.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.atmrt_host_gzip_write.restype = C.c_int
+    lib.atmrt_host_gzip_write.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]
     lib.atmrt_host_write_png.restype = C.c_int
     lib.atmrt_host_write_png.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.atmrt_host_read_png.restype = C.c_int
@@ -116,6 +118,12 @@ def geotiff_coords_from_name(path):
     if lib.atmrt_host_geotiff_coords_from_name(os.fsencode(path), C.byref(lat), C.byref(lon)) != 0:
         return None
     return lat.value, lon.value
+
+
+def gzip_write(path, data, block_bytes=0, threads=0):
+    """The metadata sidecar's writer on its own: ``data`` (bytes) as a gzip file of members compressed in parallel."""
+    buf = (C.c_char * len(data)).from_buffer_copy(data) if data else None
+    _check(lib.atmrt_host_gzip_write(os.fsencode(path), buf, len(data), int(block_bytes), int(threads)))
 
 
 def write_png(path, pixels):

@@ -321,3 +321,19 @@ def test_example_configuration_parses_the_same_in_both_hosts():
     ticks, vticks, eye, flat = host.parse_overlays(["-c", path])
     assert (len(ticks), len(vticks), eye, flat) == (3, 1, True, False)
     assert [t["size"] for t in runtime.overlay_ticks(cfg["output"]["ticks"], "azimuth")] == [12, 5, 18]
+
+
+@pytest.mark.parametrize("size,block,threads", [(0, 0, 0), (1, 0, 0), (70_000, 65536, 3), (65536 * 4, 65536, 2), (9_000_001, 1 << 20, 0), (40_000_000, 0, 0),
+                                                (3_000_000, 65536, 1)])
+def test_parallel_gzip_reads_back_as_one_stream(tmp_path, size, block, threads):
+    """The sidecar's writer (csrc/host/pgzip.cpp): a series of gzip members compressed on several threads is, to any gzip reader,
+    the stream of the bytes that went in -- sizes around the block edges, more blocks than one wave holds, an empty input."""
+    rng = np.random.default_rng(size % 1000)
+    data = (np.cumsum(rng.integers(-3, 4, size, dtype=np.int64)) & 0xff).astype(np.uint8).tobytes()  # compressible, not trivial
+    path = tmp_path / "x.gz"
+    host.gzip_write(str(path), data, block, threads)
+    raw = path.read_bytes()
+    assert gzip.decompress(raw) == data
+    assert raw[:2] == b"\x1f\x8b" and (size < 1000 or len(raw) < size)
+    r = subprocess.run(["gzip", "-dc", str(path)], capture_output=True)
+    assert r.returncode == 0 and r.stdout == data
