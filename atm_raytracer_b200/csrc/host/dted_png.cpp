@@ -1,10 +1,13 @@
 // dted_png.cpp -- host file formats: DTED decode and PNG encode/decode (on zlib).
 #include <zlib.h>
 
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "atmrt_host.h"
@@ -134,19 +137,82 @@ int paeth(int a, int b, int c) {
 
 }  // namespace
 
+// The image crate's encoder of the reference (renderer/mod.rs:433-436) is one deflate stream on one core; a 16384 x 4096 picture
+// is 201 MB of scanlines -- seconds of deflate against 8 ms of rendering. Here the scanlines are deflated in bands on all host
+// threads (raw deflate ended by a sync flush, so that the bands' outputs concatenate into ONE zlib stream -- the pigz
+// construction --, Adler-32 of the whole by adler32_combine) and written as one IDAT chunk per band. Any PNG decoder reads it.
 extern "C" int atmrt_host_write_png(const char* path, const uint8_t* pixels, int width, int height, int channels) {
     if (!path || !pixels || width <= 0 || height <= 0 || (channels != 3 && channels != 4))
         return fail(ATMRT_ERR_INVALID, "write_png: bad argument");
     const size_t stride = (size_t)width * channels;
-    std::vector<unsigned char> raw((stride + 1) * (size_t)height);
-    for (int y = 0; y < height; ++y) {
-        raw[(stride + 1) * y] = 0;  // filter type None
-        memcpy(&raw[(stride + 1) * y + 1], pixels + stride * y, stride);
+    const int band_rows = (int)std::max<size_t>(1, std::min<size_t>((size_t)height, ((size_t)2 << 20) / (stride + 1) + 1));  // ~2 MB of scanlines
+    const int nbands = (height + band_rows - 1) / band_rows;
+    struct Band {
+        std::vector<unsigned char> chunk;  // the whole IDAT chunk: length, "IDAT", data, CRC
+        uLong adler = 0;
+        size_t raw_len = 0;
+        bool ok = false;
+    };
+    std::vector<Band> bands((size_t)nbands);
+    std::atomic<int> next{0};
+    auto work = [&] {
+        std::vector<unsigned char> raw;
+        for (int b; (b = next.fetch_add(1)) < nbands;) {
+            Band& B = bands[(size_t)b];
+            const int y0 = b * band_rows, y1 = std::min(height, y0 + band_rows);
+            raw.resize((stride + 1) * (size_t)(y1 - y0));
+            for (int y = y0; y < y1; ++y) {
+                raw[(stride + 1) * (size_t)(y - y0)] = 0;  // filter type None
+                memcpy(&raw[(stride + 1) * (size_t)(y - y0) + 1], pixels + stride * (size_t)y, stride);
+            }
+            B.raw_len = raw.size();
+            B.adler = adler32(adler32(0L, Z_NULL, 0), raw.data(), (uInt)raw.size());
+            z_stream z{};
+            if (deflateInit2(&z, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) continue;
+            const bool first = b == 0, last = b == nbands - 1;
+            const size_t bound = deflateBound(&z, (uLong)raw.size()) + 16;
+            B.chunk.resize(8 + (first ? 2 : 0) + bound + 4 + 4);
+            size_t at = 8;
+            if (first) B.chunk[at++] = 0x78, B.chunk[at++] = 0x9C;  // zlib header: deflate, 32 K window, default level
+            z.next_in = raw.data(), z.avail_in = (uInt)raw.size();
+            z.next_out = &B.chunk[at], z.avail_out = (uInt)bound;
+            const int rc = deflate(&z, last ? Z_FINISH : Z_SYNC_FLUSH);
+            const bool done = last ? rc == Z_STREAM_END : (rc == Z_OK && z.avail_in == 0 && z.avail_out > 0);
+            at += z.total_out;
+            deflateEnd(&z);
+            if (!done) continue;
+            B.chunk.resize(at + (last ? 4 : 0) + 4);  // (+ the stream's Adler-32, filled in below) + the chunk's CRC
+            B.ok = true;
+        }
+    };
+    {
+        const unsigned nt = std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 64u, (unsigned)nbands}));
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; ++t) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
     }
-    uLongf clen = compressBound((uLong)raw.size());
-    std::vector<unsigned char> comp(clen);
-    if (compress2(comp.data(), &clen, raw.data(), (uLong)raw.size(), 6) != Z_OK) return fail(ATMRT_ERR_IO, "write_png: deflate failed");
-    std::vector<unsigned char> out = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    uLong adler = adler32(0L, Z_NULL, 0);
+    for (const Band& B : bands) {
+        if (!B.ok) return fail(ATMRT_ERR_IO, "write_png: deflate failed");
+        adler = adler32_combine(adler, B.adler, (z_off_t)B.raw_len);
+    }
+    for (size_t b = 0; b < bands.size(); ++b) {  // chunk framing: length and type in front, (Adler-32 and) CRC behind
+        std::vector<unsigned char>& c = bands[b].chunk;
+        const bool last = b + 1 == bands.size();
+        const size_t n = c.size() - 12;  // data bytes
+        if (last) c[c.size() - 8] = (unsigned char)(adler >> 24), c[c.size() - 7] = (unsigned char)(adler >> 16), c[c.size() - 6] = (unsigned char)(adler >> 8), c[c.size() - 5] = (unsigned char)adler;
+        c[0] = (unsigned char)(n >> 24), c[1] = (unsigned char)(n >> 16), c[2] = (unsigned char)(n >> 8), c[3] = (unsigned char)n;
+        memcpy(&c[4], "IDAT", 4);
+        uLong crc = crc32(0L, Z_NULL, 0);
+        for (size_t o = 4; o < c.size() - 4;) {  // crc32 takes 32-bit lengths
+            const size_t m = std::min<size_t>(c.size() - 4 - o, (size_t)1 << 30);
+            crc = crc32(crc, &c[o], (uInt)m);
+            o += m;
+        }
+        c[c.size() - 4] = (unsigned char)(crc >> 24), c[c.size() - 3] = (unsigned char)(crc >> 16), c[c.size() - 2] = (unsigned char)(crc >> 8), c[c.size() - 1] = (unsigned char)crc;
+    }
+    std::vector<unsigned char> head = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
     std::vector<unsigned char> ihdr;
     put_u32(ihdr, (uint32_t)width);
     put_u32(ihdr, (uint32_t)height);
@@ -155,12 +221,14 @@ extern "C" int atmrt_host_write_png(const char* path, const uint8_t* pixels, int
     ihdr.push_back(0);
     ihdr.push_back(0);
     ihdr.push_back(0);
-    put_chunk(out, "IHDR", ihdr.data(), ihdr.size());
-    put_chunk(out, "IDAT", comp.data(), clen);
-    put_chunk(out, "IEND", nullptr, 0);
+    put_chunk(head, "IHDR", ihdr.data(), ihdr.size());
+    std::vector<unsigned char> tail;
+    put_chunk(tail, "IEND", nullptr, 0);
     FILE* f = fopen(path, "wb");
     if (!f) return fail(ATMRT_ERR_IO, std::string("cannot create ") + path);
-    bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+    bool ok = fwrite(head.data(), 1, head.size(), f) == head.size();
+    for (const Band& B : bands) ok = ok && fwrite(B.chunk.data(), 1, B.chunk.size(), f) == B.chunk.size();
+    ok = ok && fwrite(tail.data(), 1, tail.size(), f) == tail.size();
     ok = fclose(f) == 0 && ok;
     return ok ? 0 : fail(ATMRT_ERR_IO, std::string("short write to ") + path);
 }

@@ -67,3 +67,26 @@ def test_png_round_trip(tmp_path):
     from PIL import Image  # independent decoder
 
     np.testing.assert_array_equal(np.asarray(Image.open(str(p)).convert("RGB")), img)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 3), (7, 5, 4), (33, 1000, 3), (900, 1200, 3), (2600, 1700, 4), (5, 700001, 3)])
+def test_png_written_in_parallel_bands_decodes_everywhere(tmp_path, shape):
+    """write_png deflates the scanlines in bands on all host threads and writes one IDAT chunk per band (one zlib stream, the
+    pigz construction): the host's own reader and an independent decoder (Pillow / libpng) must both return the pixels."""
+    rng = np.random.default_rng(shape[1])
+    h, w, ch = shape
+    img = (np.add.outer(np.arange(h) * 3, np.arange(w) * 5)[..., None] // (1 + np.arange(ch)) + rng.integers(0, 9, (h, w, ch))).astype(np.uint8)
+    path = str(tmp_path / "x.png")
+    host.write_png(path, img)
+    back = host.read_png(path)
+    np.testing.assert_array_equal(back[..., :ch], img)
+    if ch == 3:
+        assert (back[..., 3] == 255).all()
+    Image = pytest.importorskip("PIL.Image")
+    Image.MAX_IMAGE_PIXELS = None
+    with Image.open(path) as im:
+        im.load()
+        assert im.mode == ("RGB" if ch == 3 else "RGBA")
+        np.testing.assert_array_equal(np.asarray(im), img)
+    raw = open(path, "rb").read()
+    assert raw.count(b"IDAT") >= max(1, (h * (w * ch + 1)) // (4 << 20))  # several bands for a large picture
