@@ -230,6 +230,18 @@ def test_gen_executable_end_to_end(tmp_path, ctx):
     lists = np.frombuffer(raw, runtime.TRACE_DTYPE, int(kept.sum()), off + 4 + 4 * h * w)
     assert max_points == 16 and len(raw) == off + 4 + 4 * h * w + lists.nbytes
     assert el[h // 2] == -2.0 and (np.diff(el) < 0).all() and az[w // 2] == 80.0 and (np.diff(az) > 0).all()
+    # the package's reader of the sidecar sees the same content
+    from atm_raytracer_b200 import sidecar
+
+    sc = sidecar.read_sidecar(str(dat))
+    assert (sc.version, sc.width, sc.height, sc.generator, sc.max_points) == (3, 200, 120, "Fast", 16)
+    np.testing.assert_array_equal(sc.elevation_angle[:, 7], el)
+    np.testing.assert_array_equal(sc.azimuth[5], az)
+    np.testing.assert_array_equal(sc.first, meta)
+    np.testing.assert_array_equal(sc.counts, counts)
+    yy, xx = np.unravel_index(int(np.argmax(counts)), counts.shape)
+    tp = sc.trace_points(yy, xx)
+    assert len(tp) == min(counts[yy, xx], 16) and tp["distance"][0] == meta["distance"][yy, xx]
     # the same render through the Python mirror of the host
     cfg = config.read_config(argv)
     terrain = runtime.Terrain.from_folder(str(folder))
@@ -337,3 +349,38 @@ def test_parallel_gzip_reads_back_as_one_stream(tmp_path, size, block, threads):
     assert raw[:2] == b"\x1f\x8b" and (size < 1000 or len(raw) < size)
     r = subprocess.run(["gzip", "-dc", str(path)], capture_output=True)
     assert r.returncode == 0 and r.stdout == data
+
+
+def test_sidecar_reader_on_hand_made_files(tmp_path):
+    """atm_raytracer_b200/sidecar.py against the layout write_metadata documents (versions 2 and 3), without a GPU."""
+    from atm_raytracer_b200 import sidecar
+
+    h, w = 3, 4
+    el, az = np.linspace(1, -1, h), np.linspace(10, 13, w)
+    first = np.zeros((h, w), sidecar.META_DTYPE)
+    first["distance"] = np.arange(12).reshape(h, w)
+    first["distance"][0, 0] = np.nan
+    body = np.array([w, h, 0, 0], "<i4").tobytes() + el.tobytes() + az.tobytes() + first.tobytes()
+    p2 = tmp_path / "v2.meta"
+    p2.write_bytes(gzip.compress(b"ATMRTMETA2\n" + body))
+    s = sidecar.read_sidecar(str(p2))
+    assert (s.version, s.generator, s.counts) == (2, "Fast", None) and s.elevation_angle.shape == (h, w) and s.azimuth[2, 3] == 13.0
+    assert len(s.trace_points(0, 0)) == 0 and s.trace_points(1, 1)["distance"][0] == 5.0
+    counts = np.array([[0, 1, 2, 3], [0, 0, 0, 0], [5, 0, 0, 1]], "<i4")
+    kept = np.minimum(counts, 2)
+    pts = np.zeros(int(kept.sum()), sidecar.TRACE_DTYPE)
+    pts["distance"] = np.arange(len(pts))
+    p3 = tmp_path / "v3.meta"
+    p3.write_bytes(gzip.compress(b"ATMRTMETA3\n" + body + np.array([2], "<i4").tobytes() + counts.tobytes() + pts.tobytes()))
+    s = sidecar.read_sidecar(str(p3))
+    assert (s.version, s.max_points) == (3, 2)
+    assert [len(s.trace_points(y, x)) for y in range(h) for x in range(w)] == kept.ravel().tolist()
+    assert s.trace_points(2, 0)["distance"].tolist() == [5.0, 6.0]
+    per = np.array([w, h, 1, 0], "<i4").tobytes() + np.zeros((h, w)).tobytes() + np.ones((h, w)).tobytes() + first.tobytes()
+    p4 = tmp_path / "rect.meta"
+    p4.write_bytes(gzip.compress(b"ATMRTMETA2\n" + per))
+    assert sidecar.read_sidecar(str(p4)).generator == "Rectilinear" and sidecar.read_sidecar(str(p4)).azimuth.sum() == h * w
+    bad = tmp_path / "bad.meta"
+    bad.write_bytes(gzip.compress(b"ATMRTMETA2\n" + body + b"x"))
+    with pytest.raises(ValueError):
+        sidecar.read_sidecar(str(bad))
